@@ -1,0 +1,158 @@
+/*
+ * pixelpick_b200 — C-ABI of the B200-native hot paths of PixelPick.
+ *
+ * The reference (NoelShin/PixelPick) is pure Python and has NO FFI: its boundary is Python
+ * duck-typing.  Every entry point below therefore cites the reference Python
+ * call site it replaces; the Python host (`pixelpick_b200/query.py`, `pixelpick_b200/loss.py`, …)
+ * mirrors those classes and binds this library through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; device pointers unless the name says `_host`
+ *   - caller owns all memory; the only hidden allocations are inside `pp_acq_session_*`
+ *   - every device call takes a `cudaStream_t` passed as `void*` (0 = legacy default stream)
+ *   - return 0 on success, negative PP_ERR_* otherwise; `pp_last_error()` gives the text
+ *   - thread-compatible: one thread per stream/session at a time
+ */
+#ifndef PIXELPICK_B200_H_
+#define PIXELPICK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_OK 0
+#define PP_ERR_INVALID_ARG (-1)
+#define PP_ERR_CUDA (-2)
+#define PP_ERR_WORKSPACE (-3)
+#define PP_ERR_UNSUPPORTED (-4)
+
+/* dtypes of logits / feature maps */
+#define PP_F32 0
+#define PP_BF16 1
+
+/* acquisition strategies — reference `UncertaintySampler` (query.py:224-247) */
+#define PP_STRAT_ENTROPY 0          /* query.py:229-230  sum_c -p log p            (top-k: largest)  */
+#define PP_STRAT_LEAST_CONFIDENCE 1 /* query.py:233-234  1 - max_c p              (top-k: largest)  */
+#define PP_STRAT_MARGIN 2           /* query.py:237-239  |p_(1) - p_(2)|  (BvSB)  (top-k: smallest) */
+
+int pp_version(void);
+const char* pp_last_error(void);
+/* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
+long long pp_launch_count(void);
+/* number of SMs / device name of the current device: used by bench.py for the grid/roofline note */
+int pp_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
+
+/* ------------------------------------------------------------------------------------------
+ * Q path: per-pixel acquisition score.
+ * Replaces  prob = softmax(model(x)["pred"][:, :, :h, :w], dim=1)           query.py:190
+ *           uc_map = UncertaintySampler(strategy)(prob)                      query.py:192,229-239
+ *           uc_map[mask] = fill ; uc_map[mask_void] = fill                   query.py:195-201
+ *           (reverse_order) uc_map[~sampling_mask] = fill                    query.py:43-48
+ * fill = 0.0 for entropy / least-confidence, 1.0 for margin (query.py:198).
+ *
+ * logits: [n_img, C, H, W] viewed through element strides (stride_w == 1); a sliced view of a
+ *         padded forward (`[:, :, :h, :w]`) is expressed with stride_h > W.
+ * labelled / void_mask / keep: uint8 [n_img, H, W] contiguous, each may be NULL.
+ *         score <- fill where labelled!=0 or void_mask!=0 or keep==0.
+ * score_map: float32 [n_img, H*W] contiguous (required).
+ * hist0: optional uint32 [n_img, 2048], ZEROED by the caller: receives the level-0 radix histogram
+ *        of the ordering key so `pp_acq_topk` can skip its first pass (pass NULL to skip).
+ * ------------------------------------------------------------------------------------------ */
+int pp_acq_score(const void* logits, int dtype, int n_img, int C, int H, int W,
+                 int64_t stride_n, int64_t stride_c, int64_t stride_h,
+                 const uint8_t* labelled, const uint8_t* void_mask, const uint8_t* keep,
+                 int strategy, float* score_map, uint32_t* hist0, void* stream);
+
+/* Fused variant: the DeepLab head produces logits at 1/4 resolution and the model's last op is a
+ * bilinear align_corners=True upsample to the input size (deeplab.py:55).  This entry point reads
+ * the LOW-RES logits [n_img, C, h_in, w_in] (contiguous NCHW f32) and evaluates the upsample
+ * on the fly, so the full-resolution logits are never written to HBM.  Same outputs as pp_acq_score. */
+int pp_acq_score_upsampled(const float* logits_lowres, int n_img, int C, int h_in, int w_in,
+                           int H, int W,
+                           const uint8_t* labelled, const uint8_t* void_mask, const uint8_t* keep,
+                           int strategy, float* score_map, uint32_t* hist0, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Q path: per-image sorted top-k of a score map.
+ * Replaces  uc_map.flatten().topk(k, largest=strategy in {entropy, LC}).indices   query.py:57-61
+ * Order contract: sorted by score (descending if largest else ascending), NaN ranks
+ * as the largest value (torch semantics), -0.0 == +0.0, ties broken by LOWER flat index first.
+ *
+ * topk_idx: int32 [n_img, k]; topk_val: optional float32 [n_img, k].
+ * hist0_valid != 0 says the workspace histogram was already filled by pp_acq_score(hist0=...),
+ * where hist0 must be the pointer returned by pp_acq_topk_hist0(workspace).
+ * ------------------------------------------------------------------------------------------ */
+int pp_acq_topk_workspace_bytes(int n_img, int HW, int k, size_t* out_bytes);
+/* Zeroes the counters/histograms inside the workspace; must run (on the same stream) before
+ * pp_acq_score(hist0=...) / pp_acq_topk for every batch. */
+int pp_acq_topk_prepare(void* workspace, size_t workspace_bytes, int n_img, int HW, int k, void* stream);
+uint32_t* pp_acq_topk_hist0(void* workspace);
+int pp_acq_topk(const float* score_map, int n_img, int HW, int k, int largest, int hist0_valid,
+                int32_t* topk_idx, float* topk_val,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[i, j] = topk_idx[i, pos[i, j]] — the device half of
+ *   np.random.choice(ind_queries, n_pixels_by_us, False)                       query.py:63-64
+ * (the host draws pos = np.random.permutation(k)[:n] from the global NumPy stream). */
+int pp_acq_gather(const int32_t* topk_idx, int n_img, int k, const int32_t* pos, int n,
+                  int32_t* out, void* stream);
+
+/* entropy of softmax(logits) at given flat pixel indices — the device half of
+ * QueryStats._get_entropy (query.py:260-264), evaluated only at the selected pixels. */
+int pp_acq_entropy_at(const void* logits, int dtype, int n_img, int C, int H, int W,
+                      int64_t stride_n, int64_t stride_c, int64_t stride_h,
+                      const int32_t* px_idx, int n, float* out, void* stream);
+
+/* same, reading the 1/4-resolution head logits through the on-the-fly bilinear upsample */
+int pp_acq_entropy_at_upsampled(const float* logits_lowres, int n_img, int C, int h_in, int w_in,
+                                int H, int W, const int32_t* px_idx, int n, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Q path through HOST buffers (the call a non-PyTorch host makes; bench.py's `e2e`).
+ * A session owns device staging buffers, pinned host buffers and two streams; `run_host` copies
+ * the logits and masks H2D in image chunks (double-buffered against the kernels), runs
+ * score -> top-k -> gather and copies the selected indices back.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct pp_acq_session pp_acq_session;
+int pp_acq_session_create(pp_acq_session** out, int chunk_imgs, int C, int H, int W, int k, int n_sel);
+int pp_acq_session_destroy(pp_acq_session* s);
+/* h_logits: float32 [n_img, C, H, W]; h_labelled/h_void: uint8 [n_img, H, W] or NULL;
+ * h_pos: int32 [n_img, n_sel] positions in the sorted top-k list (NULL => first n_sel);
+ * h_sel_idx: int32 [n_img, n_sel] (out); h_topk_idx: optional int32 [n_img, k] (out, may be NULL).
+ * Host pointers may be pageable; pinned memory (cudaHostAlloc / torch pin_memory) is faster. */
+int pp_acq_session_run_host(pp_acq_session* s, const float* h_logits, const uint8_t* h_labelled,
+                            const uint8_t* h_void, int n_img, int strategy,
+                            const int32_t* h_pos, int32_t* h_sel_idx, int32_t* h_topk_idx);
+
+/* ------------------------------------------------------------------------------------------
+ * T path: sparse-pixel cross entropy.
+ * Replaces  y.flatten()[~mask.flatten()] = ignore_index                        model.py:108-110
+ *           F.cross_entropy(logits, y, ignore_index)  (+ its backward)         model.py:116,120-121
+ *           pred = F.interpolate(head_logits, size, 'bilinear', align_corners=True)  deeplab.py:55
+ * The labelled pixels are given as a list (img, flat index, label); the kernel gathers the four
+ * low-res neighbours x C, applies the bilinear weights, log-softmax and NLL, and scatter-adds
+ * d(loss)/d(logits_lowres).  Mean over labelled pixels (NaN when n_px == 0, as the reference).
+ *
+ * logits_lowres: float32 [n_img, C, h_in, w_in] NCHW contiguous (h_in==H, w_in==W => no upsample).
+ * px_img/px_idx/px_label: int32 [n_px].  loss: float32 [1].  grad_lowres: float32 same shape as
+ * logits_lowres, ZEROED by the caller (may be NULL for forward only).  pred_at: optional int32
+ * [n_px] argmax class at each labelled pixel (train-time running metrics, model.py:124).
+ * ------------------------------------------------------------------------------------------ */
+int pp_sparse_ce(const float* logits_lowres, int n_img, int C, int h_in, int w_in, int H, int W,
+                 const int32_t* px_img, const int32_t* px_idx, const int32_t* px_label, int n_px,
+                 float grad_scale, float* loss, float* grad_lowres, int32_t* pred_at, void* stream);
+
+/* Bilinear resize, align_corners=True (deeplab.py:49,55,58; aspp.py:70), NCHW float32,
+ * forward and its adjoint (grad_in must be zeroed by the caller). */
+int pp_upsample_bilinear_ac(const float* in, int n_img, int C, int h_in, int w_in,
+                            float* out, int H, int W, void* stream);
+int pp_upsample_bilinear_ac_bwd(const float* grad_out, int n_img, int C, int H, int W,
+                                float* grad_in, int h_in, int w_in, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXELPICK_B200_H_ */

@@ -1,0 +1,287 @@
+"""ctypes binding of `libpixelpick_b200.so` (the C-ABI declared in include/pixelpick_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, an exception is raised.  PyTorch is
+used only as the owner of device memory and streams — the wrappers below unwrap `data_ptr()`,
+shapes/strides and `torch.cuda.current_stream().cuda_stream` and pass plain pointers.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpixelpick_b200.so")
+
+PP_F32, PP_BF16 = 0, 1
+STRATEGIES = {"entropy": 0, "least_confidence": 1, "margin_sampling": 2}
+# fill value for excluded pixels and top-k direction (query.py:50,57-61,198)
+FILL = {"entropy": 0.0, "least_confidence": 0.0, "margin_sampling": 1.0, "random": 1.0}
+LARGEST = {"entropy": True, "least_confidence": True, "margin_sampling": False, "random": False}
+
+_lib = None
+
+
+class PixelPickError(RuntimeError):
+    pass
+
+
+_vp, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
+
+_SIGNATURES = {
+    "pp_version": ([], _i),
+    "pp_last_error": ([], C.c_char_p),
+    "pp_launch_count": ([], C.c_longlong),
+    "pp_device_info": ([C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.c_char_p, _i], _i),
+    "pp_acq_score": ([_vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp], _i),
+    "pp_acq_score_upsampled": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp], _i),
+    "pp_acq_topk_workspace_bytes": ([_i, _i, _i, C.POINTER(_sz)], _i),
+    "pp_acq_topk_prepare": ([_vp, _sz, _i, _i, _i, _vp], _i),
+    "pp_acq_topk_hist0": ([_vp], _vp),
+    "pp_acq_topk": ([_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp], _i),
+    "pp_acq_gather": ([_vp, _i, _i, _vp, _i, _vp, _vp], _i),
+    "pp_acq_entropy_at": ([_vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _i, _vp, _vp], _i),
+    "pp_acq_entropy_at_upsampled": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp], _i),
+    "pp_acq_session_create": ([C.POINTER(_vp), _i, _i, _i, _i, _i, _i], _i),
+    "pp_acq_session_destroy": ([_vp], _i),
+    "pp_acq_session_run_host": ([_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp], _i),
+    "pp_sparse_ce": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp], _i),
+    "pp_upsample_bilinear_ac": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
+    "pp_upsample_bilinear_ac_bwd": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
+}
+
+
+def exported_symbols():
+    """Names include/pixelpick_b200.h declares (kept in sync by tests/test_abi.py)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PixelPickError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU / PyTorch fallback for the hot paths)")
+        l = C.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise PixelPickError(f"{what} failed ({rc}): {lib().pp_last_error().decode()}")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float32:
+        return PP_F32
+    if t.dtype == torch.bfloat16:
+        return PP_BF16
+    raise PixelPickError(f"unsupported logits dtype {t.dtype}")
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise PixelPickError("pixelpick_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def _mask(t, n, H, W):
+    if t is None:
+        return None
+    if t.dtype == torch.bool:
+        t = t.view(torch.uint8)
+    if t.dtype != torch.uint8:
+        raise PixelPickError("masks must be bool/uint8")
+    t = t.reshape(n, H, W)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class TopKWorkspace:
+    """Device workspace of the radix-select/sort, reusable across batches of the same shape."""
+
+    def __init__(self, n_img, HW, k, device):
+        sz = _sz()
+        check(lib().pp_acq_topk_workspace_bytes(n_img, HW, k, C.byref(sz)), "pp_acq_topk_workspace_bytes")
+        self.n_img, self.HW, self.k = n_img, HW, k
+        self.nbytes = sz.value
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        assert self.buf.data_ptr() % 256 == 0
+
+    def prepare(self, n_img=None):
+        n = self.n_img if n_img is None else n_img
+        check(lib().pp_acq_topk_prepare(_ptr(self.buf), self.nbytes, n, self.HW, self.k, _stream(self.buf)),
+              "pp_acq_topk_prepare")
+
+    def hist0_ptr(self):
+        return C.c_void_p(lib().pp_acq_topk_hist0(_ptr(self.buf)))
+
+
+def acq_score(logits, strategy, labelled=None, void_mask=None, keep=None, out=None, hist0_ws=None):
+    """score map [n, H, W] float32 of `logits` [n, C, H, W] (any strides with stride_w == 1)."""
+    _need_cuda(logits, labelled, void_mask, keep)
+    n, Cc, H, W = logits.shape
+    if logits.stride(3) != 1:
+        logits = logits.contiguous()
+    labelled, void_mask, keep = (_mask(m, n, H, W) for m in (labelled, void_mask, keep))
+    if out is None:
+        out = torch.empty((n, H, W), dtype=torch.float32, device=logits.device)
+    check(lib().pp_acq_score(_ptr(logits), _dtype_code(logits), n, Cc, H, W, logits.stride(0), logits.stride(1),
+                             logits.stride(2), _ptr(labelled), _ptr(void_mask), _ptr(keep),
+                             STRATEGIES[strategy], _ptr(out),
+                             hist0_ws.hist0_ptr() if hist0_ws is not None else None, _stream(logits)),
+          "pp_acq_score")
+    return out
+
+
+def acq_score_upsampled(logits_lowres, size, strategy, labelled=None, void_mask=None, keep=None, out=None,
+                        hist0_ws=None):
+    _need_cuda(logits_lowres, labelled, void_mask, keep)
+    n, Cc, h, w = logits_lowres.shape
+    H, W = size
+    logits_lowres = logits_lowres.float().contiguous()
+    labelled, void_mask, keep = (_mask(m, n, H, W) for m in (labelled, void_mask, keep))
+    if out is None:
+        out = torch.empty((n, H, W), dtype=torch.float32, device=logits_lowres.device)
+    check(lib().pp_acq_score_upsampled(_ptr(logits_lowres), n, Cc, h, w, H, W, _ptr(labelled), _ptr(void_mask),
+                                       _ptr(keep), STRATEGIES[strategy], _ptr(out),
+                                       hist0_ws.hist0_ptr() if hist0_ws is not None else None,
+                                       _stream(logits_lowres)),
+          "pp_acq_score_upsampled")
+    return out
+
+
+def acq_topk(score_map, k, largest, ws=None, hist0_valid=False, return_values=False):
+    """sorted top-k flat indices [n, k] int32 of score_map [n, H*W] (NaN largest, ties -> lower index)."""
+    _need_cuda(score_map)
+    n = score_map.shape[0]
+    sm = score_map.reshape(n, -1)
+    if not sm.is_contiguous() or sm.dtype != torch.float32:
+        sm = sm.float().contiguous()
+    HW = sm.shape[1]
+    if ws is None:
+        ws = TopKWorkspace(n, HW, k, sm.device)
+        ws.prepare()
+        hist0_valid = False
+    idx = torch.empty((n, k), dtype=torch.int32, device=sm.device)
+    val = torch.empty((n, k), dtype=torch.float32, device=sm.device) if return_values else None
+    check(lib().pp_acq_topk(_ptr(sm), n, HW, k, int(bool(largest)), int(bool(hist0_valid)), _ptr(idx), _ptr(val),
+                            _ptr(ws.buf), ws.nbytes, _stream(sm)), "pp_acq_topk")
+    return (idx, val) if return_values else idx
+
+
+def acq_gather(topk_idx, pos):
+    n, k = topk_idx.shape
+    nsel = pos.shape[1]
+    out = torch.empty((n, nsel), dtype=torch.int32, device=topk_idx.device)
+    pos = pos.to(device=topk_idx.device, dtype=torch.int32).contiguous()
+    check(lib().pp_acq_gather(_ptr(topk_idx), n, k, _ptr(pos), nsel, _ptr(out), _stream(topk_idx)), "pp_acq_gather")
+    return out
+
+
+def acq_entropy_at(logits, px_idx):
+    _need_cuda(logits, px_idx)
+    n, Cc, H, W = logits.shape
+    if logits.stride(3) != 1:
+        logits = logits.contiguous()
+    px_idx = px_idx.to(torch.int32).contiguous()
+    nsel = px_idx.shape[1]
+    out = torch.empty((n, nsel), dtype=torch.float32, device=logits.device)
+    check(lib().pp_acq_entropy_at(_ptr(logits), _dtype_code(logits), n, Cc, H, W, logits.stride(0), logits.stride(1),
+                                  logits.stride(2), _ptr(px_idx), nsel, _ptr(out), _stream(logits)),
+          "pp_acq_entropy_at")
+    return out
+
+
+def acq_entropy_at_upsampled(logits_lowres, size, px_idx):
+    _need_cuda(logits_lowres, px_idx)
+    n, Cc, h, w = logits_lowres.shape
+    H, W = size
+    x = logits_lowres.float().contiguous()
+    px_idx = px_idx.to(torch.int32).contiguous()
+    nsel = px_idx.shape[1]
+    out = torch.empty((n, nsel), dtype=torch.float32, device=x.device)
+    check(lib().pp_acq_entropy_at_upsampled(_ptr(x), n, Cc, h, w, H, W, _ptr(px_idx), nsel, _ptr(out), _stream(x)),
+          "pp_acq_entropy_at_upsampled")
+    return out
+
+
+def sparse_ce(logits_lowres, size, px_img, px_idx, px_label, grad_scale=1.0, want_grad=True, want_pred=False):
+    """(loss[1], grad_lowres | None, pred_at | None); see pp_sparse_ce in the header."""
+    _need_cuda(logits_lowres, px_img, px_idx, px_label)
+    n, Cc, h, w = logits_lowres.shape
+    H, W = size
+    x = logits_lowres.float().contiguous()
+    loss = torch.empty(1, dtype=torch.float32, device=x.device)
+    grad = torch.zeros_like(x) if want_grad else None
+    n_px = int(px_idx.numel())
+    pred = torch.empty(n_px, dtype=torch.int32, device=x.device) if want_pred else None
+    check(lib().pp_sparse_ce(_ptr(x), n, Cc, h, w, H, W, _ptr(px_img), _ptr(px_idx), _ptr(px_label), n_px,
+                             float(grad_scale), _ptr(loss), _ptr(grad), _ptr(pred), _stream(x)), "pp_sparse_ce")
+    return loss, grad, pred
+
+
+def upsample_bilinear_ac(x, size):
+    _need_cuda(x)
+    n, Cc, h, w = x.shape
+    H, W = size
+    x = x.float().contiguous()
+    out = torch.empty((n, Cc, H, W), dtype=torch.float32, device=x.device)
+    check(lib().pp_upsample_bilinear_ac(_ptr(x), n, Cc, h, w, _ptr(out), H, W, _stream(x)), "pp_upsample_bilinear_ac")
+    return out
+
+
+def upsample_bilinear_ac_bwd(grad_out, in_size):
+    _need_cuda(grad_out)
+    n, Cc, H, W = grad_out.shape
+    h, w = in_size
+    g = grad_out.float().contiguous()
+    gin = torch.zeros((n, Cc, h, w), dtype=torch.float32, device=g.device)
+    check(lib().pp_upsample_bilinear_ac_bwd(_ptr(g), n, Cc, H, W, _ptr(gin), h, w, _stream(g)),
+          "pp_upsample_bilinear_ac_bwd")
+    return gin
+
+
+class AcqSession:
+    """Host-buffer acquisition session (pp_acq_session_*): numpy / pinned-torch in, numpy out."""
+
+    def __init__(self, chunk_imgs, Cc, H, W, k, n_sel):
+        h = _vp()
+        check(lib().pp_acq_session_create(C.byref(h), chunk_imgs, Cc, H, W, k, n_sel), "pp_acq_session_create")
+        self._h = h
+        self.shape = (Cc, H, W)
+        self.k, self.n_sel = k, n_sel
+
+    def run(self, h_logits, h_labelled, h_void, strategy, h_pos, h_sel, h_topk=None):
+        """All arguments are CPU torch tensors (pinned for speed); h_sel (and h_topk) are outputs."""
+        n = h_logits.shape[0]
+        for t in (h_logits, h_labelled, h_void, h_pos, h_sel, h_topk):
+            if t is not None and (t.is_cuda or not t.is_contiguous()):
+                raise PixelPickError("AcqSession.run wants contiguous host tensors")
+        check(lib().pp_acq_session_run_host(self._h, _ptr(h_logits), _ptr(h_labelled), _ptr(h_void), n,
+                                            STRATEGIES[strategy], _ptr(h_pos), _ptr(h_sel), _ptr(h_topk)),
+              "pp_acq_session_run_host")
+        return h_sel
+
+    def close(self):
+        if self._h is not None:
+            lib().pp_acq_session_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

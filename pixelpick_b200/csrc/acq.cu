@@ -1,0 +1,976 @@
+// Q path — fused acquisition scoring and per-image sorted top-k.
+//
+//   K1  acq_score_*      logits[n,C,H,W] (+masks) -> score[n,H*W] (+ level-0 radix histogram)
+//                        one coalesced, vectorised pass over the logits: HBM-bound, C*4+2 B/px.
+//   K2  select_level     MSD radix select on the 64-bit composite (ord_key(score) << 32 | flat idx):
+//                        level L partitions its input by digit L into {selected, boundary bucket}
+//                        and builds the histogram of digit L+1 over the boundary bucket, so the
+//                        score map is read exactly once after K1 and later levels touch only the
+//                        (small) boundary bucket.  Exits as soon as a bucket is wholly selected.
+//   K3  bitonic_*        sort the k selected composites (ties -> lower flat index first).
+//
+// Reference semantics restated (query.py:33-69,190-201,224-247): see include/pixelpick_b200.h.
+#include "pp_common.cuh"
+
+namespace pp {
+
+// ------------------------------------------------------------------------------------------
+// loads
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ldg_stream_bf4(const __nv_bfloat16* p) {
+  uint32_t a, b;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+  float4 r;
+  r.x = __uint_as_float(a << 16);
+  r.y = __uint_as_float(a & 0xFFFF0000u);
+  r.z = __uint_as_float(b << 16);
+  r.w = __uint_as_float(b & 0xFFFF0000u);
+  return r;
+}
+template <typename T> struct Ld4;
+template <> struct Ld4<float> {
+  static __device__ __forceinline__ float4 ld(const float* p) { return ldg_stream_f4(p); }
+  static __device__ __forceinline__ float ld1(const float* p) { return __ldg(p); }
+};
+template <> struct Ld4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p) { return ldg_stream_bf4(p); }
+  static __device__ __forceinline__ float ld1(const __nv_bfloat16* p) {
+    return __bfloat162float(*p);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// per-pixel score from C logits held in registers
+// ------------------------------------------------------------------------------------------
+template <int C, int STRAT>
+__device__ __forceinline__ float score_from_logits(const float (&x)[C]) {
+  const float qnan = __uint_as_float(0x7FC00000u);
+  if (STRAT == PP_STRAT_ENTROPY) {
+    // H = sum_c -p_c log p_c with log p_c = (x_c - m) - log S  =>  H = log S - (sum_c e_c d_c) / S.
+    // The reference evaluates -p*log(p) literally, so a class whose probability underflows to 0
+    // gives 0 * -inf = NaN (query.py:230); reproduced through the smallest class probability.
+    float m = x[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) m = fmaxf(m, x[c]);
+    float S = 0.f, T = 0.f, dmin = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float d = x[c] - m;
+      const float e = expf(d);
+      S += e;
+      T = fmaf(e, d, T);
+      dmin = fminf(dmin, d);
+    }
+    float h = logf(S) - T / S;
+    const float pmin = expf(dmin) / S;
+    if (pmin == 0.f) h = qnan;
+    return h;
+  } else if (STRAT == PP_STRAT_LEAST_CONFIDENCE) {
+    float m = x[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) m = fmaxf(m, x[c]);
+    float S = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) S += expf(x[c] - m);
+    return 1.0f - 1.0f / S;  // max_c p_c = exp(0) / S
+  } else {
+    float m1 = x[0], m2 = -INFINITY;
+#pragma unroll
+    for (int c = 1; c < C; ++c) {
+      m2 = fmaxf(m2, fminf(m1, x[c]));
+      m1 = fmaxf(m1, x[c]);
+    }
+    float S = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) S += expf(x[c] - m1);
+    const float p1 = 1.0f / S;
+    const float p2 = expf(m2 - m1) / S;
+    return fabsf(p1 - p2);
+  }
+}
+
+// runtime-C version (scalar fallback): re-reads the logits through L1/L2
+template <int STRAT, typename F>
+__device__ __forceinline__ float score_runtime_c(int C, F&& get) {
+  const float qnan = __uint_as_float(0x7FC00000u);
+  float m1 = get(0), m2 = -INFINITY;
+  for (int c = 1; c < C; ++c) {
+    const float v = get(c);
+    m2 = fmaxf(m2, fminf(m1, v));
+    m1 = fmaxf(m1, v);
+  }
+  float S = 0.f, T = 0.f, dmin = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float d = get(c) - m1;
+    const float e = expf(d);
+    S += e;
+    T = fmaf(e, d, T);
+    dmin = fminf(dmin, d);
+  }
+  if (STRAT == PP_STRAT_ENTROPY) {
+    float h = logf(S) - T / S;
+    if (expf(dmin) / S == 0.f) h = qnan;
+    return h;
+  } else if (STRAT == PP_STRAT_LEAST_CONFIDENCE) {
+    return 1.0f - 1.0f / S;
+  } else {
+    return fabsf(1.0f / S - expf(m2 - m1) / S);
+  }
+}
+
+constexpr int kHistBins = 2048;
+constexpr int kScoreThreads = 256;
+
+struct ScoreParams {
+  const void* logits;
+  int64_t sn, sc, sh;
+  int n_img, C, H, W;
+  const uint8_t* lab;
+  const uint8_t* vd;
+  const uint8_t* keep;
+  float* score;
+  uint32_t* hist0;
+  float fill;
+  int largest;
+};
+
+// Vector kernel: one thread = 4 consecutive pixels of one row; class planes are read as 16 B
+// (f32) / 8 B (bf16) streaming loads, C of them in flight per thread.
+template <int C, int STRAT, typename T, bool HIST, int ITERS>
+__global__ void __launch_bounds__(kScoreThreads) acq_score_vec_kernel(const ScoreParams p) {
+  __shared__ uint32_t sh_hist[HIST ? kHistBins : 1];
+  if (HIST) {
+    for (int i = threadIdx.x; i < kHistBins; i += kScoreThreads) sh_hist[i] = 0;
+    __syncthreads();
+  }
+  const int img = blockIdx.y;
+  const int W4 = p.W >> 2;
+  const int nquad = p.H * W4;
+  const int64_t HW = (int64_t)p.H * p.W;
+  const T* __restrict__ base = reinterpret_cast<const T*>(p.logits) + (int64_t)img * p.sn;
+  const bool largest = p.largest != 0;
+
+#pragma unroll 1
+  for (int it = 0; it < ITERS; ++it) {
+    const int q = (blockIdx.x * ITERS + it) * kScoreThreads + threadIdx.x;
+    if (q >= nquad) break;
+    const int y = q / W4;
+    const int x = (q - y * W4) << 2;
+    const T* __restrict__ src = base + (int64_t)y * p.sh + x;
+    float4 v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = Ld4<T>::ld(src + (int64_t)c * p.sc);
+    const int64_t pix = (int64_t)img * HW + (int64_t)y * p.W + x;
+    uint32_t msk = 0;
+    if (p.lab) msk |= __ldg(reinterpret_cast<const uint32_t*>(p.lab + pix));
+    if (p.vd) msk |= __ldg(reinterpret_cast<const uint32_t*>(p.vd + pix));
+    if (p.keep) {
+      const uint32_t k4 = __ldg(reinterpret_cast<const uint32_t*>(p.keep + pix));
+      // byte-wise "== 0" -> 0xFF
+      uint32_t z = 0;
+      z |= ((k4 & 0x000000FFu) == 0) ? 0x000000FFu : 0u;
+      z |= ((k4 & 0x0000FF00u) == 0) ? 0x0000FF00u : 0u;
+      z |= ((k4 & 0x00FF0000u) == 0) ? 0x00FF0000u : 0u;
+      z |= ((k4 & 0xFF000000u) == 0) ? 0xFF000000u : 0u;
+      msk |= z;
+    }
+    float xs[C];
+    float4 out;
+#pragma unroll
+    for (int c = 0; c < C; ++c) xs[c] = v[c].x;
+    out.x = score_from_logits<C, STRAT>(xs);
+#pragma unroll
+    for (int c = 0; c < C; ++c) xs[c] = v[c].y;
+    out.y = score_from_logits<C, STRAT>(xs);
+#pragma unroll
+    for (int c = 0; c < C; ++c) xs[c] = v[c].z;
+    out.z = score_from_logits<C, STRAT>(xs);
+#pragma unroll
+    for (int c = 0; c < C; ++c) xs[c] = v[c].w;
+    out.w = score_from_logits<C, STRAT>(xs);
+    if (msk & 0x000000FFu) out.x = p.fill;
+    if (msk & 0x0000FF00u) out.y = p.fill;
+    if (msk & 0x00FF0000u) out.z = p.fill;
+    if (msk & 0xFF000000u) out.w = p.fill;
+    *reinterpret_cast<float4*>(p.score + pix) = out;
+    if (HIST) {
+      atomicAdd(&sh_hist[ord_key(out.x, largest) >> 21], 1u);
+      atomicAdd(&sh_hist[ord_key(out.y, largest) >> 21], 1u);
+      atomicAdd(&sh_hist[ord_key(out.z, largest) >> 21], 1u);
+      atomicAdd(&sh_hist[ord_key(out.w, largest) >> 21], 1u);
+    }
+  }
+  if (HIST) {
+    __syncthreads();
+    uint32_t* gh = p.hist0 + (size_t)img * kHistBins;
+    for (int i = threadIdx.x; i < kHistBins; i += kScoreThreads) {
+      const uint32_t c = sh_hist[i];
+      if (c) atomicAdd(gh + i, c);
+    }
+  }
+}
+
+// Scalar fallback: any C, any W, any stride/alignment. One thread = one pixel.
+template <int STRAT, typename T>
+__global__ void __launch_bounds__(kScoreThreads) acq_score_scalar_kernel(const ScoreParams p) {
+  __shared__ uint32_t sh_hist[kHistBins];
+  const bool hist = p.hist0 != nullptr;
+  if (hist) {
+    for (int i = threadIdx.x; i < kHistBins; i += kScoreThreads) sh_hist[i] = 0;
+    __syncthreads();
+  }
+  const int img = blockIdx.y;
+  const int64_t HW = (int64_t)p.H * p.W;
+  const T* __restrict__ base = reinterpret_cast<const T*>(p.logits) + (int64_t)img * p.sn;
+  for (int64_t i = (int64_t)blockIdx.x * kScoreThreads + threadIdx.x; i < HW;
+       i += (int64_t)gridDim.x * kScoreThreads) {
+    const int y = (int)(i / p.W);
+    const int x = (int)(i - (int64_t)y * p.W);
+    const T* __restrict__ src = base + (int64_t)y * p.sh + x;
+    const int64_t sc = p.sc;
+    float s = score_runtime_c<STRAT>(p.C, [&](int c) { return Ld4<T>::ld1(src + (int64_t)c * sc); });
+    const int64_t pix = (int64_t)img * HW + i;
+    bool masked = false;
+    if (p.lab) masked |= p.lab[pix] != 0;
+    if (p.vd) masked |= p.vd[pix] != 0;
+    if (p.keep) masked |= p.keep[pix] == 0;
+    if (masked) s = p.fill;
+    p.score[pix] = s;
+    if (hist) atomicAdd(&sh_hist[ord_key(s, p.largest != 0) >> 21], 1u);
+  }
+  if (hist) {
+    __syncthreads();
+    uint32_t* gh = p.hist0 + (size_t)img * kHistBins;
+    for (int i = threadIdx.x; i < kHistBins; i += kScoreThreads) {
+      const uint32_t c = sh_hist[i];
+      if (c) atomicAdd(gh + i, c);
+    }
+  }
+}
+
+// Fused bilinear(align_corners=True) upsample + score: reads 1/s-resolution logits.
+struct ScoreUpParams {
+  const float* logits;  // [n, C, h_in, w_in]
+  int n_img, C, h_in, w_in, H, W;
+  float scale_h, scale_w;
+  const uint8_t* lab;
+  const uint8_t* vd;
+  const uint8_t* keep;
+  float* score;
+  uint32_t* hist0;
+  float fill;
+  int largest;
+};
+
+template <int C, int STRAT>
+__global__ void __launch_bounds__(kScoreThreads) acq_score_up_kernel(const ScoreUpParams p) {
+  __shared__ uint32_t sh_hist[kHistBins];
+  const bool hist = p.hist0 != nullptr;
+  if (hist) {
+    for (int i = threadIdx.x; i < kHistBins; i += kScoreThreads) sh_hist[i] = 0;
+    __syncthreads();
+  }
+  const int img = blockIdx.y;
+  const int64_t HW = (int64_t)p.H * p.W;
+  const int64_t plane = (int64_t)p.h_in * p.w_in;
+  const float* __restrict__ base = p.logits + (int64_t)img * p.C * plane;
+  for (int64_t i = (int64_t)blockIdx.x * kScoreThreads + threadIdx.x; i < HW;
+       i += (int64_t)gridDim.x * kScoreThreads) {
+    const int y = (int)(i / p.W);
+    const int x = (int)(i - (int64_t)y * p.W);
+    const Lerp ly = lerp_ac(y, p.h_in, p.H, p.scale_h);
+    const Lerp lx = lerp_ac(x, p.w_in, p.W, p.scale_w);
+    const int x0 = lx.i0, x1 = lx.i1;
+    const float ly0 = ly.l0, ly1 = ly.l1, lx0 = lx.l0, lx1 = lx.l1;
+    const float* r0 = base + (int64_t)ly.i0 * p.w_in;
+    const float* r1 = base + (int64_t)ly.i1 * p.w_in;
+    float xs[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float v00 = __ldg(r0 + c * plane + x0), v01 = __ldg(r0 + c * plane + x1);
+      const float v10 = __ldg(r1 + c * plane + x0), v11 = __ldg(r1 + c * plane + x1);
+      xs[c] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+    }
+    float s = score_from_logits<C, STRAT>(xs);
+    const int64_t pix = (int64_t)img * HW + i;
+    bool masked = false;
+    if (p.lab) masked |= p.lab[pix] != 0;
+    if (p.vd) masked |= p.vd[pix] != 0;
+    if (p.keep) masked |= p.keep[pix] == 0;
+    if (masked) s = p.fill;
+    p.score[pix] = s;
+    if (hist) atomicAdd(&sh_hist[ord_key(s, p.largest != 0) >> 21], 1u);
+  }
+  if (hist) {
+    __syncthreads();
+    uint32_t* gh = p.hist0 + (size_t)img * kHistBins;
+    for (int i = threadIdx.x; i < kHistBins; i += kScoreThreads) {
+      const uint32_t c = sh_hist[i];
+      if (c) atomicAdd(gh + i, c);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// radix select
+// ------------------------------------------------------------------------------------------
+constexpr int kLevels = 5;
+__constant__ int c_shift[kLevels + 1] = {53, 42, 32, 11, 0, 0};
+__constant__ int c_bits[kLevels + 1] = {11, 11, 10, 11, 11, 0};
+constexpr int kSelThreads = 256;
+constexpr int kSelItems = 16;
+constexpr int kSelTile = kSelThreads * kSelItems;  // 4096
+
+struct SelState {
+  uint32_t remaining;
+  uint32_t done;
+};
+
+struct Workspace {
+  uint32_t* hist;        // [kLevels][n_img][2048]
+  SelState* state;       // [kLevels+1][n_img]
+  uint32_t* cand_count;  // [n_img]
+  uint32_t* filt_count;  // [2][n_img]
+  uint64_t* cand;        // [n_img][kpad]
+  uint64_t* filt;        // [2][n_img][HW]
+  size_t zero_bytes;     // hist..filt_count are contiguous from the workspace base
+  size_t total_bytes;
+  int kpad;
+};
+
+static int next_pow2(int x) {
+  int p = 32;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+static Workspace carve(void* base, int n_img, int HW, int k) {
+  Workspace w;
+  char* p = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  w.hist = reinterpret_cast<uint32_t*>(p + off);
+  off += align_up((size_t)kLevels * n_img * kHistBins * sizeof(uint32_t), 256);
+  w.state = reinterpret_cast<SelState*>(p + off);
+  off += align_up((size_t)(kLevels + 1) * n_img * sizeof(SelState), 256);
+  w.cand_count = reinterpret_cast<uint32_t*>(p + off);
+  off += align_up((size_t)n_img * sizeof(uint32_t), 256);
+  w.filt_count = reinterpret_cast<uint32_t*>(p + off);
+  off += align_up((size_t)2 * n_img * sizeof(uint32_t), 256);
+  w.zero_bytes = off;
+  w.kpad = next_pow2(k);
+  w.cand = reinterpret_cast<uint64_t*>(p + off);
+  off += align_up((size_t)n_img * w.kpad * sizeof(uint64_t), 256);
+  w.filt = reinterpret_cast<uint64_t*>(p + off);
+  off += align_up((size_t)2 * n_img * HW * sizeof(uint64_t), 256);
+  w.total_bytes = off;
+  return w;
+}
+
+struct SelParams {
+  const float* scores;  // level 0 input [n_img][HW]
+  const uint64_t* in_list;
+  const uint32_t* in_count;
+  uint64_t* out_list;
+  uint32_t* out_count;
+  uint64_t* cand;
+  uint32_t* cand_count;
+  const uint32_t* hist_cur;
+  uint32_t* hist_next;
+  const SelState* state_cur;
+  SelState* state_next;
+  int level, n_img, HW, k, kpad, largest;
+};
+
+// standalone level-0 histogram (used when pp_acq_score did not fuse it)
+__global__ void __launch_bounds__(kSelThreads) hist0_kernel(const float* __restrict__ scores,
+                                                             uint32_t* __restrict__ hist0, int HW,
+                                                             int largest) {
+  __shared__ uint32_t sh_hist[kHistBins];
+  for (int i = threadIdx.x; i < kHistBins; i += kSelThreads) sh_hist[i] = 0;
+  __syncthreads();
+  const int img = blockIdx.y;
+  const float* s = scores + (size_t)img * HW;
+  for (int i = blockIdx.x * kSelThreads + threadIdx.x; i < HW; i += gridDim.x * kSelThreads)
+    atomicAdd(&sh_hist[ord_key(__ldg(s + i), largest != 0) >> 21], 1u);
+  __syncthreads();
+  uint32_t* gh = hist0 + (size_t)img * kHistBins;
+  for (int i = threadIdx.x; i < kHistBins; i += kSelThreads) {
+    const uint32_t c = sh_hist[i];
+    if (c) atomicAdd(gh + i, c);
+  }
+}
+
+template <bool L0>
+__global__ void __launch_bounds__(kSelThreads) select_level_kernel(const SelParams p) {
+  __shared__ uint32_t sh_hist[kHistBins];
+  __shared__ uint32_t sh_warp[kSelThreads / 32];
+  __shared__ uint32_t sh_pick[3];  // bucket, count before, count in bucket
+  __shared__ uint32_t sh_base[2];
+
+  const int img = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  uint32_t rem;
+  if (L0) {
+    rem = (uint32_t)p.k;
+  } else {
+    const SelState st = p.state_cur[img];
+    if (st.done) {  // a previous level already selected everything: propagate and leave
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        SelState nx;
+        nx.remaining = 0;
+        nx.done = 1;
+        p.state_next[img] = nx;
+      }
+      return;
+    }
+    rem = st.remaining;
+  }
+
+  // ---- pick the bucket holding the rem-th element of this level's histogram ----
+  const uint32_t* hc = p.hist_cur + (size_t)img * kHistBins;
+  uint32_t h[8];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = hc[tid * 8 + i];
+    mine += h[i];
+  }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) sh_warp[warp] = incl;
+  for (int i = tid; i < kHistBins; i += kSelThreads) sh_hist[i] = 0;
+  __syncthreads();
+  uint32_t wbase = 0;
+#pragma unroll
+  for (int w = 0; w < kSelThreads / 32; ++w)
+    if (w < warp) wbase += sh_warp[w];
+  uint32_t run = wbase + incl - mine;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (run < rem && rem <= run + h[i]) {
+      sh_pick[0] = tid * 8 + i;
+      sh_pick[1] = run;
+      sh_pick[2] = h[i];
+    }
+    run += h[i];
+  }
+  __syncthreads();
+  const uint32_t bucket = sh_pick[0];
+  const uint32_t rem_next = rem - sh_pick[1];
+  const bool take_all = (sh_pick[2] == rem_next);
+  if (blockIdx.x == 0 && tid == 0) {
+    SelState st;
+    st.remaining = rem_next;
+    st.done = take_all ? 1u : 0u;
+    p.state_next[img] = st;
+  }
+
+  const int shift = c_shift[p.level];
+  const uint32_t dmask = (1u << c_bits[p.level]) - 1u;
+  const int shift_n = c_shift[p.level + 1];
+  const uint32_t dmask_n = (1u << c_bits[p.level + 1]) - 1u;
+  const uint32_t n_in = L0 ? (uint32_t)p.HW : p.in_count[img];
+  const float* sc = L0 ? p.scores + (size_t)img * p.HW : nullptr;
+  const uint64_t* il = L0 ? nullptr : p.in_list + (size_t)img * p.HW;
+  uint64_t* cand = p.cand + (size_t)img * p.kpad;
+  uint64_t* ol = p.out_list + (size_t)img * p.HW;
+  const bool largest = p.largest != 0;
+  bool any_filt = false;
+
+  for (uint32_t tile = blockIdx.x; (uint64_t)tile * kSelTile < n_in; tile += gridDim.x) {
+    uint64_t comp[kSelItems];
+    uint32_t cls = 0;  // 2 bits per item: 1 = selected, 2 = boundary bucket
+    uint32_t nc = 0, nf = 0;
+#pragma unroll
+    for (int i = 0; i < kSelItems; ++i) {
+      const uint32_t idx = tile * kSelTile + i * kSelThreads + tid;
+      if (idx < n_in) {
+        uint64_t cv;
+        if (L0) cv = ((uint64_t)ord_key(__ldg(sc + idx), largest) << 32) | idx;
+        else cv = il[idx];
+        comp[i] = cv;
+        const uint32_t d = (uint32_t)(cv >> shift) & dmask;
+        if (d < bucket || (d == bucket && take_all)) {
+          cls |= 1u << (2 * i);
+          ++nc;
+        } else if (d == bucket) {
+          cls |= 2u << (2 * i);
+          ++nf;
+        }
+      }
+    }
+    // block exclusive scan of (nc, nf) packed 16:16 (tile has 4096 items)
+    const uint32_t packed = nc | (nf << 16);
+    uint32_t inc = packed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    __syncthreads();  // previous iteration done with sh_warp / sh_base
+    if (lane == 31) sh_warp[warp] = inc;
+    __syncthreads();
+    uint32_t wb = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kSelThreads / 32; ++w) {
+      const uint32_t v = sh_warp[w];
+      if (w < warp) wb += v;
+      tot += v;
+    }
+    if (tid == 0) {
+      const uint32_t tc = tot & 0xFFFFu, tf = tot >> 16;
+      sh_base[0] = tc ? atomicAdd(p.cand_count + img, tc) : 0u;
+      sh_base[1] = tf ? atomicAdd(p.out_count + img, tf) : 0u;
+    }
+    __syncthreads();
+    const uint32_t excl = wb + inc - packed;
+    uint32_t oc = sh_base[0] + (excl & 0xFFFFu);
+    uint32_t of = sh_base[1] + (excl >> 16);
+#pragma unroll
+    for (int i = 0; i < kSelItems; ++i) {
+      const uint32_t c2 = (cls >> (2 * i)) & 3u;
+      if (c2 == 1u) {
+        if (oc < (uint32_t)p.kpad) cand[oc] = comp[i];
+        ++oc;
+      } else if (c2 == 2u) {
+        ol[of++] = comp[i];
+        atomicAdd(&sh_hist[(uint32_t)(comp[i] >> shift_n) & dmask_n], 1u);
+        any_filt = true;
+      }
+    }
+  }
+  if (__syncthreads_or(any_filt ? 1 : 0)) {
+    uint32_t* gh = p.hist_next + (size_t)img * kHistBins;
+    for (int i = tid; i < kHistBins; i += kSelThreads) {
+      const uint32_t c = sh_hist[i];
+      if (c) atomicAdd(gh + i, c);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// bitonic sort of the selected composites
+// ------------------------------------------------------------------------------------------
+constexpr int kSortThreads = 1024;
+constexpr int kSortChunkMax = 16384;  // 128 KB of shared memory
+
+struct SortParams {
+  uint64_t* cand;  // [n_img][kpad]
+  int kpad, k, chunk;
+  int size_lo;   // first bitonic size handled by this launch (2 => full local sort)
+  int size_hi;   // last bitonic size handled locally (== chunk for FULL, == size for MERGE-FINISH)
+  int pad_on_load;
+  int write_out;
+  int largest;
+  int32_t* out_idx;  // [n_img][k]
+  float* out_val;    // optional
+};
+
+__device__ __forceinline__ void cmpx(uint64_t& a, uint64_t& b, bool asc) {
+  if ((a > b) == asc) {
+    const uint64_t t = a;
+    a = b;
+    b = t;
+  }
+}
+
+// One CTA sorts/merges one chunk in shared memory. For size <= chunk the whole network lives in
+// the chunk; for size > chunk only strides < chunk are done here (global strides run before).
+__global__ void __launch_bounds__(kSortThreads) bitonic_local_kernel(const SortParams p) {
+  extern __shared__ uint64_t sh[];
+  const int img = blockIdx.y;
+  const int cbase = blockIdx.x * p.chunk;
+  uint64_t* g = p.cand + (size_t)img * p.kpad + cbase;
+  for (int i = threadIdx.x; i < p.chunk; i += kSortThreads) {
+    uint64_t v = g[i];
+    if (p.pad_on_load && cbase + i >= p.k) v = ~0ull;
+    sh[i] = v;
+  }
+  __syncthreads();
+  for (int size = p.size_lo; size <= p.size_hi; size <<= 1) {
+    int stride = size >> 1;
+    if (stride >= p.chunk) stride = p.chunk >> 1;
+    for (; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (p.chunk >> 1); t += kSortThreads) {
+        const int pos = 2 * t - (t & (stride - 1));
+        const bool asc = ((cbase + pos) & size) == 0;
+        uint64_t a = sh[pos], b = sh[pos + stride];
+        cmpx(a, b, asc);
+        sh[pos] = a;
+        sh[pos + stride] = b;
+      }
+      __syncthreads();
+    }
+  }
+  if (p.write_out) {
+    for (int i = threadIdx.x; i < p.chunk; i += kSortThreads) {
+      const int j = cbase + i;
+      if (j < p.k) {
+        const uint64_t v = sh[i];
+        p.out_idx[(size_t)img * p.k + j] = (int32_t)(uint32_t)(v & 0xFFFFFFFFull);
+        if (p.out_val) p.out_val[(size_t)img * p.k + j] = ord_key_inv((uint32_t)(v >> 32), p.largest != 0);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < p.chunk; i += kSortThreads) g[i] = sh[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) bitonic_global_step_kernel(uint64_t* cand, int kpad, int size,
+                                                                  int stride) {
+  const int img = blockIdx.y;
+  uint64_t* g = cand + (size_t)img * kpad;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < (kpad >> 1); t += gridDim.x * 256) {
+    const int pos = 2 * t - (t & (stride - 1));
+    const bool asc = (pos & size) == 0;
+    uint64_t a = g[pos], b = g[pos + stride];
+    if ((a > b) == asc) {
+      g[pos] = b;
+      g[pos + stride] = a;
+    }
+  }
+}
+
+__global__ void gather_kernel(const int32_t* __restrict__ topk_idx, int k, const int32_t* __restrict__ pos,
+                              int n, int32_t* __restrict__ out, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int img = i / n;
+  const int ps = pos ? pos[i] : (i - img * n);
+  out[i] = topk_idx[(size_t)img * k + ps];
+}
+
+template <typename T>
+__global__ void entropy_at_kernel(const T* __restrict__ logits, int C, int W, int64_t sn, int64_t sc,
+                                  int64_t sh, const int32_t* __restrict__ px, int n, float* __restrict__ out,
+                                  int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int img = i / n;
+  const int idx = px[i];
+  const int y = idx / W, x = idx - y * W;
+  const T* src = logits + (int64_t)img * sn + (int64_t)y * sh + x;
+  out[i] = score_runtime_c<PP_STRAT_ENTROPY>(C, [&](int c) { return Ld4<T>::ld1(src + (int64_t)c * sc); });
+}
+
+__global__ void entropy_at_up_kernel(const float* __restrict__ logits, int C, int h_in, int w_in, int H, int W,
+                                     float scale_h, float scale_w, const int32_t* __restrict__ px, int n,
+                                     float* __restrict__ out, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int img = i / n;
+  const int idx = px[i];
+  const int y = idx / W, x = idx - y * W;
+  const Lerp ly = lerp_ac(y, h_in, H, scale_h);
+  const Lerp lx = lerp_ac(x, w_in, W, scale_w);
+  const int64_t plane = (int64_t)h_in * w_in;
+  const float* b = logits + (int64_t)img * C * plane;
+  const int64_t o00 = (int64_t)ly.i0 * w_in + lx.i0, o01 = (int64_t)ly.i0 * w_in + lx.i1;
+  const int64_t o10 = (int64_t)ly.i1 * w_in + lx.i0, o11 = (int64_t)ly.i1 * w_in + lx.i1;
+  out[i] = score_runtime_c<PP_STRAT_ENTROPY>(C, [&](int c) {
+    const float* pc = b + c * plane;
+    return ly.l0 * (lx.l0 * pc[o00] + lx.l1 * pc[o01]) + ly.l1 * (lx.l0 * pc[o10] + lx.l1 * pc[o11]);
+  });
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------
+template <int C, int STRAT, typename T>
+static void launch_score_vec(const ScoreParams& p, cudaStream_t st) {
+  constexpr int ITERS = 4;
+  const int nquad = p.H * (p.W >> 2);
+  dim3 grid((nquad + kScoreThreads * ITERS - 1) / (kScoreThreads * ITERS), p.n_img);
+  if (p.hist0) acq_score_vec_kernel<C, STRAT, T, true, ITERS><<<grid, kScoreThreads, 0, st>>>(p);
+  else acq_score_vec_kernel<C, STRAT, T, false, ITERS><<<grid, kScoreThreads, 0, st>>>(p);
+}
+
+template <int STRAT, typename T>
+static bool dispatch_c(const ScoreParams& p, cudaStream_t st) {
+  switch (p.C) {
+    case 11: launch_score_vec<11, STRAT, T>(p, st); return true;
+    case 19: launch_score_vec<19, STRAT, T>(p, st); return true;
+    case 21: launch_score_vec<21, STRAT, T>(p, st); return true;
+    default: return false;
+  }
+}
+
+template <int STRAT, typename T>
+static void launch_score_scalar(const ScoreParams& p, cudaStream_t st) {
+  const int64_t HW = (int64_t)p.H * p.W;
+  int gx = (int)((HW + kScoreThreads * 4 - 1) / (kScoreThreads * 4));
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, p.n_img);
+  acq_score_scalar_kernel<STRAT, T><<<grid, kScoreThreads, 0, st>>>(p);
+}
+
+template <typename T>
+static int score_dispatch(const ScoreParams& p, int strategy, bool vec_ok, cudaStream_t st) {
+  bool done = false;
+  if (vec_ok) {
+    if (strategy == PP_STRAT_ENTROPY) done = dispatch_c<PP_STRAT_ENTROPY, T>(p, st);
+    else if (strategy == PP_STRAT_LEAST_CONFIDENCE) done = dispatch_c<PP_STRAT_LEAST_CONFIDENCE, T>(p, st);
+    else done = dispatch_c<PP_STRAT_MARGIN, T>(p, st);
+  }
+  if (!done) {
+    if (strategy == PP_STRAT_ENTROPY) launch_score_scalar<PP_STRAT_ENTROPY, T>(p, st);
+    else if (strategy == PP_STRAT_LEAST_CONFIDENCE) launch_score_scalar<PP_STRAT_LEAST_CONFIDENCE, T>(p, st);
+    else launch_score_scalar<PP_STRAT_MARGIN, T>(p, st);
+  }
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+template <int STRAT>
+static bool dispatch_up(const ScoreUpParams& p, dim3 grid, cudaStream_t st) {
+  switch (p.C) {
+    case 11: acq_score_up_kernel<11, STRAT><<<grid, kScoreThreads, 0, st>>>(p); return true;
+    case 19: acq_score_up_kernel<19, STRAT><<<grid, kScoreThreads, 0, st>>>(p); return true;
+    case 21: acq_score_up_kernel<21, STRAT><<<grid, kScoreThreads, 0, st>>>(p); return true;
+    default: return false;
+  }
+}
+
+static int topk_impl(const float* score_map, int n_img, int HW, int k, int largest, int hist0_valid,
+                     int32_t* topk_idx, float* topk_val, void* workspace, size_t workspace_bytes,
+                     cudaStream_t st) {
+  Workspace w = carve(workspace, n_img, HW, k);
+  if (workspace_bytes < w.total_bytes) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, w.total_bytes);
+    return PP_ERR_WORKSPACE;
+  }
+  const int tiles = (HW + kSelTile - 1) / kSelTile;
+  if (!hist0_valid) {
+    int gx = tiles < 64 ? tiles : 64;
+    hist0_kernel<<<dim3(gx, n_img), kSelThreads, 0, st>>>(score_map, w.hist, HW, largest);
+    PP_LAUNCH_CHECK();
+  }
+  for (int L = 0; L < kLevels; ++L) {
+    SelParams p;
+    p.scores = score_map;
+    p.in_list = w.filt + (size_t)((L + 1) & 1) * n_img * HW;
+    p.in_count = w.filt_count + (size_t)((L + 1) & 1) * n_img;
+    p.out_list = w.filt + (size_t)(L & 1) * n_img * HW;
+    p.out_count = w.filt_count + (size_t)(L & 1) * n_img;
+    p.cand = w.cand;
+    p.cand_count = w.cand_count;
+    p.hist_cur = w.hist + (size_t)L * n_img * kHistBins;
+    p.hist_next = w.hist + (size_t)((L + 1) % kLevels) * n_img * kHistBins;  // unused at the last level
+    p.state_cur = w.state + (size_t)L * n_img;
+    p.state_next = w.state + (size_t)(L + 1) * n_img;
+    p.level = L;
+    p.n_img = n_img;
+    p.HW = HW;
+    p.k = k;
+    p.kpad = w.kpad;
+    p.largest = largest;
+    if (L == 0) {
+      int gx = tiles;
+      const int cap = (148 * 16 + n_img - 1) / n_img;
+      if (gx > cap) gx = cap;
+      if (gx < 1) gx = 1;
+      select_level_kernel<true><<<dim3(gx, n_img), kSelThreads, 0, st>>>(p);
+    } else {
+      if (L >= 2) {
+        // out_count of this level is the ping-pong partner that level L-2 filled: re-zero it
+        PP_CUDA(cudaMemsetAsync(p.out_count, 0, (size_t)n_img * sizeof(uint32_t), st));
+      }
+      int cap = 592 / n_img;
+      if (cap < 8) cap = 8;
+      int gx = tiles < cap ? tiles : cap;
+      select_level_kernel<false><<<dim3(gx, n_img), kSelThreads, 0, st>>>(p);
+    }
+    PP_LAUNCH_CHECK();
+  }
+  // sort
+  SortParams sp;
+  sp.cand = w.cand;
+  sp.kpad = w.kpad;
+  sp.k = k;
+  sp.largest = largest;
+  sp.out_idx = topk_idx;
+  sp.out_val = topk_val;
+  const int chunk = w.kpad < kSortChunkMax ? w.kpad : 8192;
+  sp.chunk = chunk;
+  const size_t smem = (size_t)chunk * sizeof(uint64_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PP_CUDA(cudaFuncSetAttribute(bitonic_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSortChunkMax * (int)sizeof(uint64_t)));
+    attr_set = true;
+  }
+  sp.size_lo = 2;
+  sp.size_hi = chunk;
+  sp.pad_on_load = 1;
+  sp.write_out = (chunk == w.kpad) ? 1 : 0;
+  bitonic_local_kernel<<<dim3(w.kpad / chunk, n_img), kSortThreads, smem, st>>>(sp);
+  PP_LAUNCH_CHECK();
+  for (int size = chunk << 1; size <= w.kpad; size <<= 1) {
+    for (int stride = size >> 1; stride >= chunk; stride >>= 1) {
+      int gx = (w.kpad / 2 + 255) / 256;
+      if (gx > 1024) gx = 1024;
+      bitonic_global_step_kernel<<<dim3(gx, n_img), 256, 0, st>>>(w.cand, w.kpad, size, stride);
+      PP_LAUNCH_CHECK();
+    }
+    sp.size_lo = size;
+    sp.size_hi = size;
+    sp.pad_on_load = 0;
+    sp.write_out = (size == w.kpad) ? 1 : 0;
+    bitonic_local_kernel<<<dim3(w.kpad / chunk, n_img), kSortThreads, smem, st>>>(sp);
+    PP_LAUNCH_CHECK();
+  }
+  return PP_OK;
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" {
+
+int pp_acq_score(const void* logits, int dtype, int n_img, int C, int H, int W, int64_t stride_n,
+                 int64_t stride_c, int64_t stride_h, const uint8_t* labelled, const uint8_t* void_mask,
+                 const uint8_t* keep, int strategy, float* score_map, uint32_t* hist0, void* stream) {
+  PP_CHECK_ARG(logits && score_map, "pp_acq_score: null logits/score_map");
+  PP_CHECK_ARG(n_img > 0 && C >= 2 && H > 0 && W > 0, "pp_acq_score: bad shape n=%d C=%d H=%d W=%d", n_img, C, H, W);
+  PP_CHECK_ARG((int64_t)H * W <= (1 << 22), "pp_acq_score: H*W=%lld exceeds 2^22", (long long)H * W);
+  PP_CHECK_ARG(n_img <= 65535, "pp_acq_score: n_img=%d exceeds 65535 per call", n_img);
+  PP_CHECK_ARG(strategy >= 0 && strategy <= 2, "pp_acq_score: bad strategy %d", strategy);
+  PP_CHECK_ARG(dtype == PP_F32 || dtype == PP_BF16, "pp_acq_score: bad dtype %d", dtype);
+  PP_CHECK_ARG(stride_h >= W, "pp_acq_score: stride_h < W");
+  ScoreParams p;
+  p.logits = logits;
+  p.sn = stride_n; p.sc = stride_c; p.sh = stride_h;
+  p.n_img = n_img; p.C = C; p.H = H; p.W = W;
+  p.lab = labelled; p.vd = void_mask; p.keep = keep;
+  p.score = score_map; p.hist0 = hist0;
+  p.fill = (strategy == PP_STRAT_MARGIN) ? 1.0f : 0.0f;
+  p.largest = (strategy == PP_STRAT_MARGIN) ? 0 : 1;
+  const size_t esz = dtype == PP_F32 ? 4 : 2;
+  const size_t valign = esz * 4;
+  auto al = [](const void* q, size_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
+  const bool vec_ok = (W % 4 == 0) && (stride_n % 4 == 0) && (stride_c % 4 == 0) && (stride_h % 4 == 0) &&
+                      al(logits, valign) && al(score_map, 16) && al(labelled, 4) && al(void_mask, 4) && al(keep, 4);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == PP_F32) return score_dispatch<float>(p, strategy, vec_ok, st);
+  return score_dispatch<__nv_bfloat16>(p, strategy, vec_ok, st);
+}
+
+int pp_acq_score_upsampled(const float* logits_lowres, int n_img, int C, int h_in, int w_in, int H, int W,
+                           const uint8_t* labelled, const uint8_t* void_mask, const uint8_t* keep,
+                           int strategy, float* score_map, uint32_t* hist0, void* stream) {
+  PP_CHECK_ARG(logits_lowres && score_map, "pp_acq_score_upsampled: null pointer");
+  PP_CHECK_ARG(n_img > 0 && n_img <= 65535 && h_in > 0 && w_in > 0 && H > 0 && W > 0, "pp_acq_score_upsampled: bad shape");
+  PP_CHECK_ARG((int64_t)H * W <= (1 << 22), "pp_acq_score_upsampled: H*W exceeds 2^22");
+  PP_CHECK_ARG(strategy >= 0 && strategy <= 2, "pp_acq_score_upsampled: bad strategy %d", strategy);
+  ScoreUpParams p;
+  p.logits = logits_lowres;
+  p.n_img = n_img; p.C = C; p.h_in = h_in; p.w_in = w_in; p.H = H; p.W = W;
+  // ATen area_pixel_compute_scale(align_corners=True): (in-1)/(out-1), 0 when out == 1
+  p.scale_h = ac_scale(h_in, H);
+  p.scale_w = ac_scale(w_in, W);
+  p.lab = labelled; p.vd = void_mask; p.keep = keep;
+  p.score = score_map; p.hist0 = hist0;
+  p.fill = (strategy == PP_STRAT_MARGIN) ? 1.0f : 0.0f;
+  p.largest = (strategy == PP_STRAT_MARGIN) ? 0 : 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid((unsigned)((HW + kScoreThreads - 1) / kScoreThreads), n_img);
+  bool ok;
+  if (strategy == PP_STRAT_ENTROPY) ok = dispatch_up<PP_STRAT_ENTROPY>(p, grid, st);
+  else if (strategy == PP_STRAT_LEAST_CONFIDENCE) ok = dispatch_up<PP_STRAT_LEAST_CONFIDENCE>(p, grid, st);
+  else ok = dispatch_up<PP_STRAT_MARGIN>(p, grid, st);
+  if (!ok) {
+    set_error("pp_acq_score_upsampled: C=%d not instantiated (11, 19, 21)", C);
+    return PP_ERR_UNSUPPORTED;
+  }
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+int pp_acq_topk_workspace_bytes(int n_img, int HW, int k, size_t* out_bytes) {
+  PP_CHECK_ARG(out_bytes, "pp_acq_topk_workspace_bytes: null out");
+  PP_CHECK_ARG(n_img > 0 && HW > 0 && k > 0 && k <= HW, "pp_acq_topk_workspace_bytes: bad n_img=%d HW=%d k=%d", n_img, HW, k);
+  PP_CHECK_ARG(HW <= (1 << 22), "pp_acq_topk_workspace_bytes: HW=%d exceeds 2^22", HW);
+  Workspace w = carve(nullptr, n_img, HW, k);
+  *out_bytes = w.total_bytes;
+  return PP_OK;
+}
+
+int pp_acq_topk_prepare(void* workspace, size_t workspace_bytes, int n_img, int HW, int k, void* stream) {
+  PP_CHECK_ARG(workspace, "pp_acq_topk_prepare: null workspace");
+  PP_CHECK_ARG(n_img > 0 && HW > 0 && k > 0 && k <= HW && HW <= (1 << 22), "pp_acq_topk_prepare: bad shape");
+  PP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) % 256) == 0, "pp_acq_topk_prepare: workspace must be 256-B aligned");
+  Workspace w = carve(workspace, n_img, HW, k);
+  if (workspace_bytes < w.total_bytes) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, w.total_bytes);
+    return PP_ERR_WORKSPACE;
+  }
+  PP_CUDA(cudaMemsetAsync(workspace, 0, w.zero_bytes, reinterpret_cast<cudaStream_t>(stream)));
+  return PP_OK;
+}
+
+uint32_t* pp_acq_topk_hist0(void* workspace) { return reinterpret_cast<uint32_t*>(workspace); }
+
+int pp_acq_topk(const float* score_map, int n_img, int HW, int k, int largest, int hist0_valid,
+                int32_t* topk_idx, float* topk_val, void* workspace, size_t workspace_bytes, void* stream) {
+  PP_CHECK_ARG(score_map && topk_idx && workspace, "pp_acq_topk: null pointer");
+  PP_CHECK_ARG(n_img > 0 && n_img <= 65535 && HW > 0 && k > 0 && k <= HW, "pp_acq_topk: bad n_img=%d HW=%d k=%d", n_img, HW, k);
+  PP_CHECK_ARG(HW <= (1 << 22), "pp_acq_topk: HW=%d exceeds 2^22", HW);
+  PP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) % 256) == 0, "pp_acq_topk: workspace must be 256-B aligned");
+  return topk_impl(score_map, n_img, HW, k, largest, hist0_valid, topk_idx, topk_val, workspace,
+                   workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pp_acq_gather(const int32_t* topk_idx, int n_img, int k, const int32_t* pos, int n, int32_t* out,
+                  void* stream) {
+  PP_CHECK_ARG(topk_idx && out, "pp_acq_gather: null pointer");
+  PP_CHECK_ARG(n_img > 0 && k > 0 && n > 0 && n <= k, "pp_acq_gather: bad n_img=%d k=%d n=%d", n_img, k, n);
+  const int total = n_img * n;
+  gather_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(topk_idx, k, pos, n, out, total);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+int pp_acq_entropy_at(const void* logits, int dtype, int n_img, int C, int H, int W, int64_t stride_n,
+                      int64_t stride_c, int64_t stride_h, const int32_t* px_idx, int n, float* out,
+                      void* stream) {
+  PP_CHECK_ARG(logits && px_idx && out, "pp_acq_entropy_at: null pointer");
+  PP_CHECK_ARG(n_img > 0 && C >= 2 && H > 0 && W > 0 && n > 0, "pp_acq_entropy_at: bad shape");
+  const int total = n_img * n;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == PP_F32)
+    entropy_at_kernel<float><<<(total + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float*>(logits), C, W, stride_n, stride_c, stride_h, px_idx, n, out, total);
+  else if (dtype == PP_BF16)
+    entropy_at_kernel<__nv_bfloat16><<<(total + 127) / 128, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(logits), C, W, stride_n, stride_c, stride_h, px_idx, n, out, total);
+  else {
+    set_error("pp_acq_entropy_at: bad dtype %d", dtype);
+    return PP_ERR_INVALID_ARG;
+  }
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+int pp_acq_entropy_at_upsampled(const float* logits_lowres, int n_img, int C, int h_in, int w_in, int H, int W,
+                                const int32_t* px_idx, int n, float* out, void* stream) {
+  PP_CHECK_ARG(logits_lowres && px_idx && out, "pp_acq_entropy_at_upsampled: null pointer");
+  PP_CHECK_ARG(n_img > 0 && C >= 2 && h_in > 0 && w_in > 0 && H > 0 && W > 0 && n > 0, "pp_acq_entropy_at_upsampled: bad shape");
+  const int total = n_img * n;
+  entropy_at_up_kernel<<<(total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits_lowres, C, h_in, w_in, H, W, ac_scale(h_in, H), ac_scale(w_in, W), px_idx, n, out, total);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+}  // extern "C"

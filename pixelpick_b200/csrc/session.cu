@@ -1,0 +1,120 @@
+// Q path through HOST buffers: pp_acq_session_* (include/pixelpick_b200.h).
+// Two slots, one stream each: slot s owns device staging for `chunk_imgs` images; chunk i runs
+// H2D -> score(+hist0) -> radix select -> sort -> gather -> D2H on stream (i & 1), so the copy
+// engine fills one slot while the SMs work on the other.
+#include "pp_common.cuh"
+#include <new>
+
+struct pp_acq_session {
+  int chunk, C, H, W, k, n_sel;
+  size_t ws_bytes;
+  struct Slot {
+    cudaStream_t st;
+    float* logits;
+    uint8_t* lab;
+    uint8_t* vd;
+    float* score;
+    void* ws;
+    int32_t* topk;
+    int32_t* pos;
+    int32_t* sel;
+  } slot[2];
+};
+
+using namespace pp;
+
+extern "C" {
+
+int pp_acq_session_destroy(pp_acq_session* s) {
+  if (!s) return PP_OK;
+  for (int i = 0; i < 2; ++i) {
+    auto& sl = s->slot[i];
+    if (sl.st) cudaStreamSynchronize(sl.st);
+    cudaFree(sl.logits);
+    cudaFree(sl.lab);
+    cudaFree(sl.vd);
+    cudaFree(sl.score);
+    cudaFree(sl.ws);
+    cudaFree(sl.topk);
+    cudaFree(sl.pos);
+    cudaFree(sl.sel);
+    if (sl.st) cudaStreamDestroy(sl.st);
+  }
+  delete s;
+  return PP_OK;
+}
+
+int pp_acq_session_create(pp_acq_session** out, int chunk_imgs, int C, int H, int W, int k, int n_sel) {
+  PP_CHECK_ARG(out, "pp_acq_session_create: null out");
+  PP_CHECK_ARG(chunk_imgs > 0 && C >= 2 && H > 0 && W > 0, "pp_acq_session_create: bad shape");
+  const int64_t HW = (int64_t)H * W;
+  PP_CHECK_ARG(HW <= (1 << 22) && k > 0 && k <= HW && n_sel > 0 && n_sel <= k, "pp_acq_session_create: bad k/n_sel");
+  pp_acq_session* s = new (std::nothrow) pp_acq_session();
+  PP_CHECK_ARG(s, "pp_acq_session_create: out of host memory");
+  memset(s, 0, sizeof(*s));
+  s->chunk = chunk_imgs; s->C = C; s->H = H; s->W = W; s->k = k; s->n_sel = n_sel;
+  int rc = pp_acq_topk_workspace_bytes(chunk_imgs, (int)HW, k, &s->ws_bytes);
+  if (rc != PP_OK) { delete s; return rc; }
+  for (int i = 0; i < 2; ++i) {
+    auto& sl = s->slot[i];
+    cudaError_t e = cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.logits, (size_t)chunk_imgs * C * HW * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&sl.lab, (size_t)chunk_imgs * HW);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.vd, (size_t)chunk_imgs * HW);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.score, (size_t)chunk_imgs * HW * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&sl.ws, s->ws_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.topk, (size_t)chunk_imgs * k * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&sl.pos, (size_t)chunk_imgs * n_sel * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&sl.sel, (size_t)chunk_imgs * n_sel * sizeof(int32_t));
+    if (e != cudaSuccess) {
+      set_error("pp_acq_session_create: %s", cudaGetErrorString(e));
+      pp_acq_session_destroy(s);
+      return PP_ERR_CUDA;
+    }
+  }
+  *out = s;
+  return PP_OK;
+}
+
+int pp_acq_session_run_host(pp_acq_session* s, const float* h_logits, const uint8_t* h_labelled,
+                            const uint8_t* h_void, int n_img, int strategy, const int32_t* h_pos,
+                            int32_t* h_sel_idx, int32_t* h_topk_idx) {
+  PP_CHECK_ARG(s && h_logits && h_sel_idx && n_img > 0, "pp_acq_session_run_host: bad args");
+  PP_CHECK_ARG(strategy >= 0 && strategy <= 2, "pp_acq_session_run_host: bad strategy %d", strategy);
+  const int64_t HW = (int64_t)s->H * s->W;
+  const int largest = strategy == PP_STRAT_MARGIN ? 0 : 1;
+  int ci = 0;
+  for (int i0 = 0; i0 < n_img; i0 += s->chunk, ++ci) {
+    auto& sl = s->slot[ci & 1];
+    const int n = (n_img - i0) < s->chunk ? (n_img - i0) : s->chunk;
+    PP_CUDA(cudaMemcpyAsync(sl.logits, h_logits + (size_t)i0 * s->C * HW, (size_t)n * s->C * HW * sizeof(float),
+                            cudaMemcpyHostToDevice, sl.st));
+    if (h_labelled)
+      PP_CUDA(cudaMemcpyAsync(sl.lab, h_labelled + (size_t)i0 * HW, (size_t)n * HW, cudaMemcpyHostToDevice, sl.st));
+    if (h_void)
+      PP_CUDA(cudaMemcpyAsync(sl.vd, h_void + (size_t)i0 * HW, (size_t)n * HW, cudaMemcpyHostToDevice, sl.st));
+    if (h_pos)
+      PP_CUDA(cudaMemcpyAsync(sl.pos, h_pos + (size_t)i0 * s->n_sel, (size_t)n * s->n_sel * sizeof(int32_t),
+                              cudaMemcpyHostToDevice, sl.st));
+    int rc = pp_acq_topk_prepare(sl.ws, s->ws_bytes, n, (int)HW, s->k, sl.st);
+    if (rc != PP_OK) return rc;
+    rc = pp_acq_score(sl.logits, PP_F32, n, s->C, s->H, s->W, (int64_t)s->C * HW, HW, s->W,
+                      h_labelled ? sl.lab : nullptr, h_void ? sl.vd : nullptr, nullptr, strategy, sl.score,
+                      pp_acq_topk_hist0(sl.ws), sl.st);
+    if (rc != PP_OK) return rc;
+    rc = pp_acq_topk(sl.score, n, (int)HW, s->k, largest, 1, sl.topk, nullptr, sl.ws, s->ws_bytes, sl.st);
+    if (rc != PP_OK) return rc;
+    rc = pp_acq_gather(sl.topk, n, s->k, h_pos ? sl.pos : nullptr, s->n_sel, sl.sel, sl.st);
+    if (rc != PP_OK) return rc;
+    PP_CUDA(cudaMemcpyAsync(h_sel_idx + (size_t)i0 * s->n_sel, sl.sel, (size_t)n * s->n_sel * sizeof(int32_t),
+                            cudaMemcpyDeviceToHost, sl.st));
+    if (h_topk_idx)
+      PP_CUDA(cudaMemcpyAsync(h_topk_idx + (size_t)i0 * s->k, sl.topk, (size_t)n * s->k * sizeof(int32_t),
+                              cudaMemcpyDeviceToHost, sl.st));
+  }
+  PP_CUDA(cudaStreamSynchronize(s->slot[0].st));
+  PP_CUDA(cudaStreamSynchronize(s->slot[1].st));
+  return PP_OK;
+}
+
+}  // extern "C"

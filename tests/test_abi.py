@@ -1,0 +1,50 @@
+"""CPU: the C-ABI library loads and exports every symbol include/pixelpick_b200.h declares."""
+import ctypes
+import os
+import re
+
+from pixelpick_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "pixelpick_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert _header_functions() == _lib.exported_symbols()
+
+
+def test_library_exports_every_declared_symbol():
+    l = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _header_functions():
+        assert hasattr(l, name), name
+
+
+def test_version_and_error_string():
+    l = _lib.lib()
+    assert l.pp_version() >= 100
+    assert isinstance(l.pp_last_error(), bytes)
+
+
+def test_argument_validation_without_gpu():
+    # workspace query is pure host arithmetic; bad shapes are rejected before any CUDA call
+    l = _lib.lib()
+    sz = ctypes.c_size_t()
+    assert l.pp_acq_topk_workspace_bytes(4, 256 * 512, 6553, ctypes.byref(sz)) == 0
+    assert sz.value > 4 * 8192 * 8
+    assert l.pp_acq_topk_workspace_bytes(4, 100, 200, ctypes.byref(sz)) == -1
+    assert b"bad" in l.pp_last_error()
+    assert l.pp_acq_topk_workspace_bytes(1, (1 << 22) + 4, 10, ctypes.byref(sz)) == -1
+
+
+def test_product_path_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "pixelpick_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), f

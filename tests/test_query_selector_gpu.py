@@ -1,0 +1,174 @@
+"""GPU: the drop-in QuerySelector (pixelpick_b200/query.py) vs the reference's QuerySelector.__call__
+output captured in tests/golden (stub dataloader + stub model whose input carries the logits)."""
+import pickle
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import acq_oracle as orc
+from pixelpick_b200.query import QuerySelector, UncertaintySampler
+
+pytestmark = pytest.mark.gpu
+STRATS = ["entropy", "least_confidence", "margin_sampling"]
+DEV = torch.device("cuda:0")
+
+
+def make_args(strategy, n_classes, ignore_index, dir_root, top_n_percent=0.05, n_pixels_by_us=10,
+              reverse_order=False, dataset_name="cs"):
+    return Namespace(dataset_name=dataset_name, debug=False, dir_root=dir_root, experim_name="t",
+                     ignore_index=ignore_index, mc_n_steps=20, n_classes=n_classes, n_pixels_by_us=n_pixels_by_us,
+                     network_name="deeplab", query_strategy=strategy, reverse_order=reverse_order, stride_total=8,
+                     top_n_percent=top_n_percent, use_mc_dropout=False, vote_type="soft")
+
+
+class StubDataset:
+    def __init__(self, logits, y, lab):
+        self.logits, self.y = logits, y
+        self.queries = [m.copy() for m in lab]
+        self.labelled = None
+
+    def label_queries(self, dict_queries, nth_query=None):
+        self.labelled = (dict_queries, nth_query)
+
+
+class StubLoader:
+    def __init__(self, ds):
+        self.dataset = ds
+
+    def __iter__(self):
+        for i in range(self.dataset.logits.shape[0]):
+            d = {"x": self.dataset.logits[i:i + 1], "p_img": [f"img_{i:04d}.png"]}
+            if self.dataset.y is not None:
+                d["y"] = torch.from_numpy(self.dataset.y[i:i + 1])
+            yield d
+
+
+class StubModel:
+    def __init__(self):
+        self.evaled = False
+
+    def eval(self):
+        self.evaled = True
+        return self
+
+    def __call__(self, x):
+        return {"pred": x}
+
+
+@pytest.mark.parametrize("strat", STRATS)
+@pytest.mark.parametrize("batch_imgs", [1, 2, 32])
+def test_call_matches_reference_golden(golden, tmp_path, strat, batch_imgs):
+    logits = torch.from_numpy(golden["call_logits"])
+    ds = StubDataset(logits, golden["call_y"], golden["call_lab"])
+    qs = QuerySelector(make_args(strat, 19, 19, str(tmp_path)), StubLoader(ds), device=DEV, batch_imgs=batch_imgs)
+    model = StubModel()
+    np.random.seed(0)
+    d = qs(0, model)
+    assert model.evaled
+    assert sorted(d) == [f"img_{i:04d}.png" for i in range(3)]
+    for i, (p, info) in enumerate(sorted(d.items())):
+        assert info["height"] == 32 and info["width"] == 48
+        assert np.array_equal(np.stack([info["x_coords"], info["y_coords"]]), golden[f"call_{strat}_{i}_xy"])
+    assert ds.labelled[1] == 0 and ds.labelled[0] is d  # label_queries side effect (query.py:220)
+    stats = pickle.load(open(tmp_path / "checkpoints" / "t" / "0_query" / "query_stats.pkl", "rb"))
+    assert sum(stats["label_distribution"].values()) == 30
+    # same stats as the reference formulas evaluated by the oracle
+    ents = []
+    for i, (p, info) in enumerate(sorted(d.items())):
+        q = np.zeros((32, 48), dtype=bool)
+        q[info["y_coords"], info["x_coords"]] = True
+        ents += orc.entropy_at(logits[i:i + 1], q)
+    assert abs(stats["avg_entropy"] - np.mean(ents)) < 1e-5
+
+
+@pytest.mark.parametrize("strat", STRATS)
+@pytest.mark.parametrize("kw", [dict(top_n_percent=0.0), dict(top_n_percent=0.05, reverse_order=True),
+                                dict(top_n_percent=0.05)])
+def test_call_variants_match_oracle(tmp_path, strat, kw):
+    g = torch.Generator().manual_seed(17)
+    logits = (torch.randn((4, 11, 24, 40), generator=g) * 3).float()
+    rs = np.random.RandomState(17)
+    y = rs.randint(0, 12, size=(4, 24, 40)).astype(np.int64)
+    lab = rs.rand(4, 24, 40) < 0.01
+    ds = StubDataset(logits, y, lab)
+    qs = QuerySelector(make_args(strat, 11, 11, str(tmp_path), **kw), StubLoader(ds), device=DEV, batch_imgs=3)
+    np.random.seed(5)
+    got = qs(1, StubModel())
+    state_after = np.random.get_state()[1].copy()
+    np.random.seed(5)
+    want = orc.query_images([logits[i:i + 1] for i in range(4)], strat, lab, y == 11,
+                            [f"img_{i:04d}.png" for i in range(4)], 10, kw["top_n_percent"],
+                            kw.get("reverse_order", False), topk=orc.topk_indices_spec)
+    assert np.array_equal(state_after, np.random.get_state()[1])  # identical RNG consumption
+    for p in want:
+        assert np.array_equal(got[p]["x_coords"], want[p]["x_coords"]), p
+        assert np.array_equal(got[p]["y_coords"], want[p]["y_coords"]), p
+
+
+def test_voc_padding_and_mixed_sizes(tmp_path):
+    """VOC images differ in size and are reflect-padded to a stride multiple before the forward (query.py:171-174)."""
+    g = torch.Generator().manual_seed(3)
+    sizes = [(30, 44), (30, 44), (27, 41)]
+    imgs = [(torch.randn((1, 21, h, w), generator=g) * 3).float() for h, w in sizes]
+
+    class DS:
+        queries = [np.zeros(s, dtype=bool) for s in sizes]
+
+        def label_queries(self, d, n=None):
+            pass
+
+    class DL:
+        dataset = DS()
+
+        def __iter__(self):
+            for i, x in enumerate(imgs):
+                yield {"x": x, "p_img": [f"v_{i}.png"]}
+
+    qs = QuerySelector(make_args("margin_sampling", 21, 255, str(tmp_path), dataset_name="voc"), DL(), device=DEV)
+    np.random.seed(1)
+    got = qs(0, StubModel())
+    np.random.seed(1)
+    want = orc.query_images(imgs, "margin_sampling", None, None, [f"v_{i}.png" for i in range(3)],
+                            topk=orc.topk_indices_spec)
+    for p in want:
+        assert got[p]["height"] == want[p]["height"] and got[p]["width"] == want[p]["width"]
+        assert np.array_equal(got[p]["x_coords"], want[p]["x_coords"]) and np.array_equal(got[p]["y_coords"], want[p]["y_coords"])
+
+
+def test_human_labels_mask_and_random_strategy(tmp_path):
+    g = torch.Generator().manual_seed(4)
+    logits = (torch.randn((2, 11, 16, 24), generator=g) * 3).float()
+    labelled = np.full((2, 16, 24), 11, dtype=np.int64)
+    labelled[:, :8] = 3  # top half already labelled by a human
+
+    class DS:
+        list_labelled_queries = [labelled[0], labelled[1]]
+        queries = None
+
+    class DL:
+        dataset = DS()
+
+        def __iter__(self):
+            for i in range(2):
+                yield {"x": logits[i:i + 1], "p_img": [f"h_{i}.png"]}
+
+    qs = QuerySelector(make_args("entropy", 11, 11, str(tmp_path)), DL(), device=DEV)
+    d = qs(2, StubModel(), human_labels=True)
+    for info in d.values():
+        assert (info["y_coords"] >= 8).all() and len(info["y_coords"]) == 10
+    qs = QuerySelector(make_args("random", 11, 11, str(tmp_path)), DL(), device=DEV)
+    torch.manual_seed(0)
+    d = qs(2, StubModel(), human_labels=True)
+    for info in d.values():
+        assert (info["y_coords"] >= 8).all() and len(info["y_coords"]) == 10
+
+
+@pytest.mark.parametrize("strat", STRATS)
+def test_uncertainty_sampler_on_probabilities(golden, strat):
+    logits = torch.from_numpy(golden["logits_c19"])
+    prob = torch.softmax(logits, dim=1)
+    got = UncertaintySampler(strat)(prob.to(DEV)).cpu().numpy()
+    assert np.allclose(got, golden[f"scores_{strat}_c19"], atol=5e-6, rtol=1e-5)
+    assert np.allclose(getattr(UncertaintySampler, f"_{strat}")(prob.to(DEV)).cpu().numpy(), got)
