@@ -152,6 +152,61 @@ int pp_upsample_bilinear_ac(const float* in, int n_img, int C, int h_in, int w_i
 int pp_upsample_bilinear_ac_bwd(const float* grad_out, int n_img, int C, int H, int W,
                                 float* grad_in, int h_in, int w_in, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * T path: NHWC bf16 implicit-GEMM convolution on tcgen05 tensor cores (stride 1, padding == dilation,
+ * 1x1 or 3x3).  Replaces every nn.Conv2d of the DeepLabv3+ head — ASPP branches and projection
+ * (aspp.py:49-52,73), SegmentHead convs and classifier (decoders.py:107-116) — with the following
+ * BatchNorm(eval)/bias + ReLU folded into the epilogue:  out = relu?((acc + pre_bias[n]) * scale + shift).
+ *
+ * x: bf16 [N, H, W, ld_in] (first Cin channels used; Cin % 64 == 0).
+ * w_packed: bf16 [taps][Cout_pad][Cin] (tap = ky*3+kx; rows >= Cout are zero).
+ * pre_bias: f32 [N][Cout_pad] or NULL; scale/shift: f32 [Cout_pad] or NULL.
+ * out_mode 0: bf16 NHWC written at out[pixel * ld_out + c_off + c];  1: f32 NCHW [N, Cout, H, W].
+ * block_n: 0 = auto, else 32/64/128/256 (must divide Cout_pad).
+ * The data gradient of the same convolution is this call with w_packed = flipped/transposed weights.
+ * ------------------------------------------------------------------------------------------ */
+int pp_conv_igemm(const void* x, int N, int H, int W, int Cin, int ld_in, const void* w_packed, int taps, int dil,
+                  int Cout_pad, int Cout, const float* pre_bias, const float* scale, const float* shift, int relu,
+                  void* out, int out_mode, int ld_out, int c_off, int block_n, void* stream);
+
+/* Weight gradient of the same convolution on tcgen05 (both operands MN-major, split over pixels):
+ *   dw[tap][ci][co] += sum_p x[p + shift(tap)][ci] * dy[p][co]
+ * x: bf16 [N,H,W,ld_x] (Cin valid channels); dy: bf16 [N,H,W,ld_dy] (first Cout_pad channels, 64/128/256);
+ * dw: f32 [taps][Cin_rows][Cout_pad], ZEROED by the caller (Cin_rows >= Cin); splits: 0 = auto. */
+int pp_conv_wgrad(const void* x, int ld_x, int Cin, const void* dy, int ld_dy, int Cout_pad, int N, int H, int W,
+                  int taps, int dil, float* dw, int Cin_rows, int splits, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * T path: the HBM-bound layers between the convolutions, NHWC bf16 (channel counts multiples of 8).
+ * Replaces nn.BatchNorm2d (train mode) + nn.ReLU + nn.Dropout (aspp.py:16-20,73-79; decoders.py:107-114;
+ * deeplab.py:24-26) and the decoder-input upsample + concat (deeplab.py:49-50).
+ * ------------------------------------------------------------------------------------------ */
+/* sums[0][c] = sum_rows raw[:, c_off+c], sums[1][c] = sum of squares (f32 [2][C], zeroed inside). */
+int pp_bn_stats(const void* raw, int64_t M, int ld, int c_off, int C, float* sums, void* stream);
+/* (sum, sum sq) -> out[4][Cpad] = (scale = gamma*rstd, shift = beta - mean*scale, mean, rstd), zero for c >= C;
+ * updates running_mean / running_var in place with nn.BatchNorm2d semantics when non-NULL. */
+int pp_bn_finalize(const float* sums, int C, int64_t M, float eps, float momentum, const float* gamma,
+                   const float* beta, float* running_mean, float* running_var, float* out, int Cpad, void* stream);
+/* out[:, c_off_out+c] = dropout_p(relu?(raw[:, c_off_in+c] * scale[c] + shift[c])); Philox mask keyed by
+ * (seed, offset, element index) so the backward regenerates it. */
+int pp_bn_apply(const void* raw, int64_t M, int ld_in, int c_off_in, int C, const float* scale, const float* shift,
+                int relu, float drop_p, uint64_t seed, uint64_t offset, void* out, int ld_out, int c_off_out,
+                void* stream);
+/* BatchNorm(train)+ReLU+Dropout backward: draw = scale * (g - mean(g) - xhat * mean(g * xhat)) with
+ * g = dy * dropmask/(1-p) * [raw*scale+shift > 0]; sums (f32 [2][C]) returns sum g (= d beta) and
+ * sum g*xhat (= d gamma).  g_tmp / draw: bf16 [M][C] (may alias each other is NOT allowed). */
+int pp_bn_bwd(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_raw, int c_off_raw, int64_t M, int C,
+              const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
+              uint64_t seed, uint64_t offset, void* g_tmp, float* sums, void* draw, void* stream);
+/* bilinear align_corners=True resize of bf16 NHWC into a channel slice, and its adjoint (f32 accumulate). */
+int pp_upsample_nhwc_bf16(const void* in, int N, int h, int w, int C, int ld_in, void* out, int H, int W, int ld_out,
+                          int c_off, void* stream);
+int pp_upsample_nhwc_bf16_bwd(const void* grad_out, int N, int H, int W, int ld, int c_off, int C, float* grad_in,
+                              int h, int w, void* stream);
+/* strided [N,C,H,W] f32/bf16 -> bf16 NHWC channel slice (backbone boundary, d(logits) for the classifier) */
+int pp_to_nhwc_bf16(const void* in, int dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw, int N, int C, int H,
+                    int W, void* out, int ld, int c_off, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,16 @@ _SIGNATURES = {
     "pp_sparse_ce": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp], _i),
     "pp_upsample_bilinear_ac": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_upsample_bilinear_ac_bwd": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
+    "pp_conv_wgrad": ([_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
+    "pp_bn_stats": ([_vp, _i64, _i, _i, _i, _vp, _vp], _i),
+    "pp_bn_finalize": ([_vp, _i, _i64, _f, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
+    "pp_bn_apply": ([_vp, _i64, _i, _i, _i, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _i, _i, _vp], _i),
+    "pp_bn_bwd": ([_vp, _i, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp,
+                   _vp, _vp], _i),
+    "pp_upsample_nhwc_bf16": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp], _i),
+    "pp_upsample_nhwc_bf16_bwd": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
+    "pp_to_nhwc_bf16": ([_vp, _i, _i64, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
+    "pp_conv_igemm": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp], _i),
 }
 
 
@@ -252,6 +262,138 @@ def upsample_bilinear_ac_bwd(grad_out, in_size):
     check(lib().pp_upsample_bilinear_ac_bwd(_ptr(g), n, Cc, H, W, _ptr(gin), h, w, _stream(g)),
           "pp_upsample_bilinear_ac_bwd")
     return gin
+
+
+def pack_conv_weight(w, cin_pad=None, cout_pad=None, transpose_for_dgrad=False):
+    """torch conv weight [Cout, Cin, kh, kw] -> packed bf16 [taps][Cout_pad][Cin_pad] (tap = ky*kw + kx).
+    transpose_for_dgrad: weights of the data-gradient convolution, [taps][Cin_pad][Cout_pad] with flipped taps."""
+    if transpose_for_dgrad:
+        w = w.flip(2, 3).transpose(0, 1)
+    co, ci, kh, kw = w.shape
+    cin_pad = cin_pad or -(-ci // 64) * 64
+    cout_pad = cout_pad or -(-co // 32) * 32
+    out = torch.zeros((kh * kw, cout_pad, cin_pad), dtype=torch.bfloat16, device=w.device)
+    out[:, :co, :ci] = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).to(torch.bfloat16)
+    return out
+
+
+def conv_igemm(x_nhwc, w_packed, cout, dil=1, pre_bias=None, scale=None, shift=None, relu=False, out=None,
+               out_mode=0, c_off=0, cin=None, block_n=0):
+    """x_nhwc: bf16 [N, H, W, ld_in]; returns bf16 NHWC [N, H, W, ld_out] (out_mode 0) or f32 NCHW (out_mode 1)."""
+    _need_cuda(x_nhwc, w_packed)
+    assert x_nhwc.dtype == torch.bfloat16 and x_nhwc.is_contiguous() and w_packed.dtype == torch.bfloat16
+    N, H, W, ld_in = x_nhwc.shape
+    taps, cout_pad, cin_w = w_packed.shape
+    cin = cin_w if cin is None else cin
+    assert cin == cin_w and cin <= ld_in
+    if out is None:
+        if out_mode == 0:
+            out = torch.empty((N, H, W, cout), dtype=torch.bfloat16, device=x_nhwc.device)
+        else:
+            out = torch.empty((N, cout, H, W), dtype=torch.float32, device=x_nhwc.device)
+    ld_out = out.shape[3] if out_mode == 0 else 0
+    for t in (pre_bias, scale, shift):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.shape[-1] == cout_pad)
+    check(lib().pp_conv_igemm(_ptr(x_nhwc), N, H, W, cin, ld_in, _ptr(w_packed), taps, dil, cout_pad, cout,
+                              _ptr(pre_bias), _ptr(scale), _ptr(shift), int(relu), _ptr(out), out_mode, ld_out, c_off,
+                              block_n, _stream(x_nhwc)), "pp_conv_igemm")
+    return out
+
+
+def conv_wgrad(x_nhwc, cin, dy_nhwc, cout_pad, taps, dil=1, splits=0):
+    """dW as f32 [taps][Cin_rows][Cout_pad] (Cin_rows = Cin rounded up to 128)."""
+    _need_cuda(x_nhwc, dy_nhwc)
+    assert x_nhwc.dtype == torch.bfloat16 and dy_nhwc.dtype == torch.bfloat16
+    assert x_nhwc.is_contiguous() and dy_nhwc.is_contiguous()
+    N, H, W, ld_x = x_nhwc.shape
+    ld_dy = dy_nhwc.shape[3]
+    rows = -(-cin // 128) * 128
+    dw = torch.zeros((taps, rows, cout_pad), dtype=torch.float32, device=x_nhwc.device)
+    check(lib().pp_conv_wgrad(_ptr(x_nhwc), ld_x, cin, _ptr(dy_nhwc), ld_dy, cout_pad, N, H, W, taps, dil, _ptr(dw),
+                              rows, splits, _stream(x_nhwc)), "pp_conv_wgrad")
+    return dw
+
+
+def bn_stats(raw, c_off, C):
+    """per-channel (sum, sum of squares) of raw[..., c_off:c_off+C] as f32 [2, C]; raw is bf16 [..., ld]."""
+    _need_cuda(raw)
+    ld = raw.shape[-1]
+    M = raw.numel() // ld
+    sums = torch.empty((2, C), dtype=torch.float32, device=raw.device)
+    check(lib().pp_bn_stats(_ptr(raw), M, ld, c_off, C, _ptr(sums), _stream(raw)), "pp_bn_stats")
+    return sums
+
+
+def bn_finalize(sums, M, bn, Cpad=None, update_running=True):
+    """f32 [4, Cpad] = (scale, shift, mean, rstd) from bn_stats output and an nn.BatchNorm2d's parameters."""
+    C = sums.shape[1]
+    Cpad = Cpad or C
+    out = torch.empty((4, Cpad), dtype=torch.float32, device=sums.device)
+    upd = update_running and bn.track_running_stats and bn.running_mean is not None
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    check(lib().pp_bn_finalize(_ptr(sums), C, M, bn.eps, mom, _ptr(bn.weight.detach()), _ptr(bn.bias.detach()),
+                               _ptr(bn.running_mean) if upd else None, _ptr(bn.running_var) if upd else None,
+                               _ptr(out), Cpad, _stream(sums)), "pp_bn_finalize")
+    if upd:
+        bn.num_batches_tracked += 1
+    return out
+
+
+def bn_apply(raw, c_off_in, C, scale, shift, relu, out, c_off_out, drop_p=0.0, seed=0, offset=0):
+    _need_cuda(raw, out)
+    ld_in, ld_out = raw.shape[-1], out.shape[-1]
+    M = raw.numel() // ld_in
+    check(lib().pp_bn_apply(_ptr(raw), M, ld_in, c_off_in, C, _ptr(scale), _ptr(shift), int(relu), float(drop_p),
+                            int(seed), int(offset), _ptr(out), ld_out, c_off_out, _stream(raw)), "pp_bn_apply")
+    return out
+
+
+def bn_bwd(dy, c_off_dy, raw, c_off_raw, C, scale, shift, mean, rstd, relu, drop_p=0.0, seed=0, offset=0):
+    """returns (draw bf16 [M, C], sums f32 [2, C] = (d beta, d gamma))."""
+    _need_cuda(dy, raw)
+    ld_dy, ld_raw = dy.shape[-1], raw.shape[-1]
+    M = raw.numel() // ld_raw
+    g = torch.empty((M, C), dtype=torch.bfloat16, device=raw.device)
+    draw = torch.empty((M, C), dtype=torch.bfloat16, device=raw.device)
+    sums = torch.empty((2, C), dtype=torch.float32, device=raw.device)
+    check(lib().pp_bn_bwd(_ptr(dy), ld_dy, c_off_dy, _ptr(raw), ld_raw, c_off_raw, M, C, _ptr(scale), _ptr(shift),
+                          _ptr(mean), _ptr(rstd), int(relu), float(drop_p), int(seed), int(offset), _ptr(g), _ptr(sums),
+                          _ptr(draw), _stream(raw)), "pp_bn_bwd")
+    return draw, sums
+
+
+def upsample_nhwc(x, out, c_off, C=None):
+    """bilinear align_corners=True of bf16 NHWC x[..., :C] into out[..., c_off:c_off+C]."""
+    _need_cuda(x, out)
+    N, h, w, ld_in = x.shape
+    _, H, W, ld_out = out.shape
+    C = ld_in if C is None else C
+    check(lib().pp_upsample_nhwc_bf16(_ptr(x), N, h, w, C, ld_in, _ptr(out), H, W, ld_out, c_off, _stream(x)),
+          "pp_upsample_nhwc_bf16")
+    return out
+
+
+def upsample_nhwc_bwd(grad_out, c_off, C, in_hw):
+    _need_cuda(grad_out)
+    N, H, W, ld = grad_out.shape
+    h, w = in_hw
+    gin = torch.zeros((N, h, w, C), dtype=torch.float32, device=grad_out.device)
+    check(lib().pp_upsample_nhwc_bf16_bwd(_ptr(grad_out), N, H, W, ld, c_off, C, _ptr(gin), h, w, _stream(grad_out)),
+          "pp_upsample_nhwc_bf16_bwd")
+    return gin
+
+
+def to_nhwc_bf16(x_nchw, out=None, c_off=0, ld=None):
+    """any-strided [N, C, H, W] f32/bf16 -> bf16 NHWC (channel slice of `out`, zero padded when allocated here)."""
+    _need_cuda(x_nchw)
+    N, Cc, H, W = x_nchw.shape
+    if out is None:
+        ld = ld or -(-Cc // 64) * 64
+        out = (torch.zeros if ld != Cc else torch.empty)((N, H, W, ld), dtype=torch.bfloat16, device=x_nchw.device)
+    sn, sc, sh, sw = x_nchw.stride()
+    check(lib().pp_to_nhwc_bf16(_ptr(x_nchw), _dtype_code(x_nchw), sn, sc, sh, sw, N, Cc, H, W, _ptr(out), out.shape[3],
+                                c_off, _stream(x_nchw)), "pp_to_nhwc_bf16")
+    return out
 
 
 class AcqSession:

@@ -11,6 +11,7 @@
 //
 // Reference semantics restated (query.py:33-69,190-201,224-247): see include/pixelpick_b200.h.
 #include "pp_common.cuh"
+#include <stdlib.h>
 
 namespace pp {
 
@@ -48,6 +49,16 @@ template <> struct Ld4<__nv_bfloat16> {
 // ------------------------------------------------------------------------------------------
 // per-pixel score from C logits held in registers
 // ------------------------------------------------------------------------------------------
+// exp(x - m) for the softmax denominator: one FFMA + MUFU.EX2 (ex2.approx, rel. error 2^-22) instead of
+// the ~8-instruction expf.  The kernel is co-limited by instruction issue and HBM, so this matters;
+// the induced score error (~1e-7 abs) is far inside the 2e-6 / 1e-5 parity tolerance.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
 template <int C, int STRAT>
 __device__ __forceinline__ float score_from_logits(const float (&x)[C]) {
   const float qnan = __uint_as_float(0x7FC00000u);
@@ -62,22 +73,24 @@ __device__ __forceinline__ float score_from_logits(const float (&x)[C]) {
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const float d = x[c] - m;
-      const float e = expf(d);
+      const float e = ex2_approx(d * kLog2e);
       S += e;
       T = fmaf(e, d, T);
       dmin = fminf(dmin, d);
     }
     float h = logf(S) - T / S;
-    const float pmin = expf(dmin) / S;
-    if (pmin == 0.f) h = qnan;
-    return h;
+    if (dmin < -87.0f) {  // rare: only then can a probability underflow to exactly 0 (precise expf)
+      if (expf(dmin) / S == 0.f) h = qnan;
+    }
+    return h;  // NaN / inf logits propagate through S and T as in torch
   } else if (STRAT == PP_STRAT_LEAST_CONFIDENCE) {
     float m = x[0];
 #pragma unroll
     for (int c = 1; c < C; ++c) m = fmaxf(m, x[c]);
+    const float mb = -m * kLog2e;
     float S = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) S += expf(x[c] - m);
+    for (int c = 0; c < C; ++c) S += ex2_approx(fmaf(x[c], kLog2e, mb));
     return 1.0f - 1.0f / S;  // max_c p_c = exp(0) / S
   } else {
     float m1 = x[0], m2 = -INFINITY;
@@ -86,9 +99,10 @@ __device__ __forceinline__ float score_from_logits(const float (&x)[C]) {
       m2 = fmaxf(m2, fminf(m1, x[c]));
       m1 = fmaxf(m1, x[c]);
     }
+    const float mb = -m1 * kLog2e;
     float S = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) S += expf(x[c] - m1);
+    for (int c = 0; c < C; ++c) S += ex2_approx(fmaf(x[c], kLog2e, mb));
     const float p1 = 1.0f / S;
     const float p2 = expf(m2 - m1) / S;
     return fabsf(p1 - p2);
@@ -140,18 +154,53 @@ struct ScoreParams {
   int largest;
 };
 
-// Vector kernel: one thread = 4 consecutive pixels of one row; class planes are read as 16 B
-// (f32) / 8 B (bf16) streaming loads, C of them in flight per thread.
-template <int C, int STRAT, typename T, bool HIST, int ITERS>
-__global__ void __launch_bounds__(kScoreThreads) acq_score_vec_kernel(const ScoreParams p) {
+// Vector kernel: one thread = PX (4 or 2) consecutive pixels of one row; class planes are read as
+// 16 B / 8 B streaming loads, C of them in flight per thread.  PX and MINB (min resident CTAs per SM,
+// i.e. the register cap) trade per-thread memory-level parallelism against occupancy.
+template <typename T, int PX> struct LdPx;
+template <> struct LdPx<float, 4> {
+  static __device__ __forceinline__ void ld(const float* p, float (&o)[4]) {
+    const float4 r = ldg_stream_f4(p);
+    o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
+  }
+};
+template <> struct LdPx<float, 2> {
+  static __device__ __forceinline__ void ld(const float* p, float (&o)[2]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(o[0]), "=f"(o[1]) : "l"(p));
+  }
+};
+template <> struct LdPx<__nv_bfloat16, 4> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&o)[4]) {
+    const float4 r = ldg_stream_bf4(p);
+    o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
+  }
+};
+template <> struct LdPx<__nv_bfloat16, 2> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&o)[2]) {
+    uint32_t a;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(a) : "l"(p));
+    o[0] = __uint_as_float(a << 16);
+    o[1] = __uint_as_float(a & 0xFFFF0000u);
+  }
+};
+template <int PX> __device__ __forceinline__ uint32_t ld_mask(const uint8_t* p);
+template <> __device__ __forceinline__ uint32_t ld_mask<4>(const uint8_t* p) {
+  return __ldg(reinterpret_cast<const uint32_t*>(p));
+}
+template <> __device__ __forceinline__ uint32_t ld_mask<2>(const uint8_t* p) {
+  return __ldg(reinterpret_cast<const uint16_t*>(p));
+}
+
+template <int C, int STRAT, typename T, bool HIST, int ITERS, int PX, int MINB>
+__global__ void __launch_bounds__(kScoreThreads, MINB) acq_score_vec_kernel(const ScoreParams p) {
   __shared__ uint32_t sh_hist[HIST ? kHistBins : 1];
   if (HIST) {
     for (int i = threadIdx.x; i < kHistBins; i += kScoreThreads) sh_hist[i] = 0;
     __syncthreads();
   }
   const int img = blockIdx.y;
-  const int W4 = p.W >> 2;
-  const int nquad = p.H * W4;
+  const int Wv = p.W / PX;
+  const int nvec = p.H * Wv;
   const int64_t HW = (int64_t)p.H * p.W;
   const T* __restrict__ base = reinterpret_cast<const T*>(p.logits) + (int64_t)img * p.sn;
   const bool largest = p.largest != 0;
@@ -159,51 +208,37 @@ __global__ void __launch_bounds__(kScoreThreads) acq_score_vec_kernel(const Scor
 #pragma unroll 1
   for (int it = 0; it < ITERS; ++it) {
     const int q = (blockIdx.x * ITERS + it) * kScoreThreads + threadIdx.x;
-    if (q >= nquad) break;
-    const int y = q / W4;
-    const int x = (q - y * W4) << 2;
+    if (q >= nvec) break;
+    const int y = q / Wv;
+    const int x = (q - y * Wv) * PX;
     const T* __restrict__ src = base + (int64_t)y * p.sh + x;
-    float4 v[C];
+    float v[C][PX];
 #pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = Ld4<T>::ld(src + (int64_t)c * p.sc);
+    for (int c = 0; c < C; ++c) LdPx<T, PX>::ld(src + (int64_t)c * p.sc, v[c]);
     const int64_t pix = (int64_t)img * HW + (int64_t)y * p.W + x;
     uint32_t msk = 0;
-    if (p.lab) msk |= __ldg(reinterpret_cast<const uint32_t*>(p.lab + pix));
-    if (p.vd) msk |= __ldg(reinterpret_cast<const uint32_t*>(p.vd + pix));
+    if (p.lab) msk |= ld_mask<PX>(p.lab + pix);
+    if (p.vd) msk |= ld_mask<PX>(p.vd + pix);
     if (p.keep) {
-      const uint32_t k4 = __ldg(reinterpret_cast<const uint32_t*>(p.keep + pix));
-      // byte-wise "== 0" -> 0xFF
-      uint32_t z = 0;
-      z |= ((k4 & 0x000000FFu) == 0) ? 0x000000FFu : 0u;
-      z |= ((k4 & 0x0000FF00u) == 0) ? 0x0000FF00u : 0u;
-      z |= ((k4 & 0x00FF0000u) == 0) ? 0x00FF0000u : 0u;
-      z |= ((k4 & 0xFF000000u) == 0) ? 0xFF000000u : 0u;
-      msk |= z;
+      const uint32_t k4 = ld_mask<PX>(p.keep + pix);
+#pragma unroll
+      for (int j = 0; j < PX; ++j)
+        if (((k4 >> (8 * j)) & 0xFFu) == 0) msk |= 0xFFu << (8 * j);  // keep == 0 -> excluded
     }
-    float xs[C];
-    float4 out;
+    float out[PX];
 #pragma unroll
-    for (int c = 0; c < C; ++c) xs[c] = v[c].x;
-    out.x = score_from_logits<C, STRAT>(xs);
+    for (int j = 0; j < PX; ++j) {
+      float xs[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) xs[c] = v[c].y;
-    out.y = score_from_logits<C, STRAT>(xs);
-#pragma unroll
-    for (int c = 0; c < C; ++c) xs[c] = v[c].z;
-    out.z = score_from_logits<C, STRAT>(xs);
-#pragma unroll
-    for (int c = 0; c < C; ++c) xs[c] = v[c].w;
-    out.w = score_from_logits<C, STRAT>(xs);
-    if (msk & 0x000000FFu) out.x = p.fill;
-    if (msk & 0x0000FF00u) out.y = p.fill;
-    if (msk & 0x00FF0000u) out.z = p.fill;
-    if (msk & 0xFF000000u) out.w = p.fill;
-    *reinterpret_cast<float4*>(p.score + pix) = out;
+      for (int c = 0; c < C; ++c) xs[c] = v[c][j];
+      out[j] = score_from_logits<C, STRAT>(xs);
+      if ((msk >> (8 * j)) & 0xFFu) out[j] = p.fill;
+    }
+    if (PX == 4) *reinterpret_cast<float4*>(p.score + pix) = make_float4(out[0], out[1], out[2], out[PX - 1]);
+    else *reinterpret_cast<float2*>(p.score + pix) = make_float2(out[0], out[1]);
     if (HIST) {
-      atomicAdd(&sh_hist[ord_key(out.x, largest) >> 21], 1u);
-      atomicAdd(&sh_hist[ord_key(out.y, largest) >> 21], 1u);
-      atomicAdd(&sh_hist[ord_key(out.z, largest) >> 21], 1u);
-      atomicAdd(&sh_hist[ord_key(out.w, largest) >> 21], 1u);
+#pragma unroll
+      for (int j = 0; j < PX; ++j) atomicAdd(&sh_hist[ord_key(out[j], largest) >> 21], 1u);
     }
   }
   if (HIST) {
@@ -687,13 +722,35 @@ __global__ void entropy_at_up_kernel(const float* __restrict__ logits, int C, in
 // ------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------
+// Tuning knob (bench/experiments only): PP_SCORE_VARIANT = 0 (4 px, 2 CTAs/SM: default), 1 (4 px, 3 CTAs/SM),
+// 2 (2 px, 4 CTAs/SM), 3 (2 px, 6 CTAs/SM).
+static int score_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PP_SCORE_VARIANT");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 3) v = 0;
+  }
+  return v;
+}
+
+template <int C, int STRAT, typename T, int PX, int MINB>
+static void launch_score_vec_v(const ScoreParams& p, cudaStream_t st) {
+  constexpr int ITERS = 4;
+  const int nvec = p.H * (p.W / PX);
+  dim3 grid((nvec + kScoreThreads * ITERS - 1) / (kScoreThreads * ITERS), p.n_img);
+  if (p.hist0) acq_score_vec_kernel<C, STRAT, T, true, ITERS, PX, MINB><<<grid, kScoreThreads, 0, st>>>(p);
+  else acq_score_vec_kernel<C, STRAT, T, false, ITERS, PX, MINB><<<grid, kScoreThreads, 0, st>>>(p);
+}
+
 template <int C, int STRAT, typename T>
 static void launch_score_vec(const ScoreParams& p, cudaStream_t st) {
-  constexpr int ITERS = 4;
-  const int nquad = p.H * (p.W >> 2);
-  dim3 grid((nquad + kScoreThreads * ITERS - 1) / (kScoreThreads * ITERS), p.n_img);
-  if (p.hist0) acq_score_vec_kernel<C, STRAT, T, true, ITERS><<<grid, kScoreThreads, 0, st>>>(p);
-  else acq_score_vec_kernel<C, STRAT, T, false, ITERS><<<grid, kScoreThreads, 0, st>>>(p);
+  switch (score_variant()) {
+    case 1: launch_score_vec_v<C, STRAT, T, 4, 3>(p, st); break;
+    case 2: launch_score_vec_v<C, STRAT, T, 2, 4>(p, st); break;
+    case 3: launch_score_vec_v<C, STRAT, T, 2, 6>(p, st); break;
+    default: launch_score_vec_v<C, STRAT, T, 4, 2>(p, st); break;
+  }
 }
 
 template <int STRAT, typename T>
@@ -776,7 +833,8 @@ static int topk_impl(const float* score_map, int n_img, int HW, int k, int large
     p.kpad = w.kpad;
     p.largest = largest;
     if (L == 0) {
-      int gx = tiles;
+      // each CTA walks ~4 tiles so the bucket-pick prologue (2048-bin scan) is amortised
+      int gx = (tiles + 3) / 4;
       const int cap = (148 * 16 + n_img - 1) / n_img;
       if (gx > cap) gx = cap;
       if (gx < 1) gx = 1;

@@ -1,0 +1,474 @@
+// T path — the HBM-bound companions of the tensor-core convolutions, NHWC bf16, fused per layer:
+//   bn_stats        per-channel sum / sum-of-squares of a raw conv output (train-mode BatchNorm statistics)
+//   bn_apply        y = dropout(relu(raw * scale + shift))                       (aspp.py:16-20,75-79; decoders.py:107-114)
+//   bn_bwd_reduce   g = dy * dropmask * relu'(.) ;  sum_c g, sum_c g*xhat          (BatchNorm backward, pass 1)
+//   bn_bwd_apply    d_raw = scale * (g - mean(g) - xhat * mean(g*xhat))           (BatchNorm backward, pass 2)
+//   upsample_nhwc   bilinear align_corners=True into a channel slice of the decoder input (deeplab.py:49-50) + adjoint
+//   nchw->nhwc      layout/precision change at the backbone boundary
+// One thread owns 8 consecutive channels (one 16-byte vector) of a pixel row; warps read/write whole
+// 128-byte lines.  Dropout masks come from a counter-based Philox4x32-10 keyed by (seed, layer offset,
+// element index), so the backward pass regenerates them instead of storing them.
+#include "pp_common.cuh"
+
+namespace pp {
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// keep-mask bits for the 8 channels starting at element index e (multiple of 8): bit j set = keep
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t offset, uint64_t e, float p) {
+  const uint64_t ctr = offset + (e >> 3);
+  const uint4 a = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint4 b = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 1u, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t thr = (uint32_t)fminf(p * 4294967296.0f, 4294967295.0f);
+  uint32_t m = 0;
+  m |= (a.x >= thr) << 0; m |= (a.y >= thr) << 1; m |= (a.z >= thr) << 2; m |= (a.w >= thr) << 3;
+  m |= (b.x >= thr) << 4; m |= (b.y >= thr) << 5; m |= (b.z >= thr) << 6; m |= (b.w >= thr) << 7;
+  return m;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+constexpr int kEwThreads = 256;
+
+// ---- BN statistics -------------------------------------------------------------------------
+// sums[0][c] += sum_rows raw, sums[1][c] += sum_rows raw^2   (fp32, caller zeroes)
+__global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const __nv_bfloat16* __restrict__ raw, int64_t M, int ld,
+                                                              int c_off, int C, float* __restrict__ sums) {
+  extern __shared__ float sh[];  // [kEwThreads][16] reduced per channel group
+  const int groups = C >> 3;     // 8-channel groups per row
+  const int rows_per_block = kEwThreads / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (r < rows_per_block) {
+    for (int64_t row = (int64_t)blockIdx.x * rows_per_block + r; row < M; row += (int64_t)gridDim.x * rows_per_block) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(raw + row * ld + c_off + g * 8));
+      float f[8];
+      unpack8(v, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        q[i] = fmaf(f[i], f[i], q[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sh[threadIdx.x * 16 + i] = s[i];
+    sh[threadIdx.x * 16 + 8 + i] = q[i];
+  }
+  __syncthreads();
+  // thread t < groups*16 reduces (group, slot) over the rows of the block
+  for (int t = threadIdx.x; t < groups * 16; t += kEwThreads) {
+    const int gg = t / 16, slot = t % 16;
+    float acc = 0.f;
+    for (int rr = 0; rr < rows_per_block; ++rr) acc += sh[(rr * groups + gg) * 16 + slot];
+    const int c = gg * 8 + (slot & 7);
+    atomicAdd(sums + (slot >> 3) * C + c, acc);
+  }
+}
+
+// ---- BN apply (+ReLU, +dropout) --------------------------------------------------------------
+struct BnApplyParams {
+  const __nv_bfloat16* raw;
+  int64_t M;
+  int ld_in, c_off_in, C;
+  const float* scale;
+  const float* shift;
+  int relu;
+  float drop_p;
+  uint64_t seed, offset;
+  __nv_bfloat16* out;
+  int ld_out, c_off_out;
+};
+__global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParams p) {
+  const int groups = p.C >> 3;
+  const int64_t total = p.M * groups;
+  const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kEwThreads) {
+    const int64_t row = i / groups;
+    const int g = (int)(i - row * groups);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.raw + row * p.ld_in + p.c_off_in + g * 8));
+    float f[8];
+    unpack8(v, f);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + g * 8));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + g * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.shift + g * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.shift + g * 8 + 4));
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sf[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint32_t keep = 0xFFu;
+    if (p.drop_p > 0.f) keep = dropout_keep8(p.seed, p.offset, (uint64_t)i * 8, p.drop_p);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = fmaf(f[j], sc[j], sf[j]);
+      if (p.relu) y = fmaxf(y, 0.f);
+      f[j] = ((keep >> j) & 1u) ? y * keep_scale : 0.f;
+    }
+    *reinterpret_cast<uint4*>(p.out + row * p.ld_out + p.c_off_out + g * 8) = pack8(f);
+  }
+}
+
+// ---- BN backward -----------------------------------------------------------------------------
+struct BnBwdParams {
+  const __nv_bfloat16* dy;  // grad wrt the layer output (after dropout), [M][ld_dy] slice c_off_dy
+  int ld_dy, c_off_dy;
+  const __nv_bfloat16* raw;  // saved raw conv output
+  int ld_raw, c_off_raw;
+  int64_t M;
+  int C;
+  const float* scale;  // gamma * rstd
+  const float* shift;  // beta - mean * scale
+  const float* mean;
+  const float* rstd;
+  int relu;
+  float drop_p;
+  uint64_t seed, offset;
+  __nv_bfloat16* g;  // [M][C] masked gradient (out of pass 1, in of pass 2)
+  float* sums;       // [2][C]: sum g, sum g*xhat
+  const float* inv_m_sums;  // pass 2: the same buffer
+  __nv_bfloat16* draw;      // pass 2 output [M][C]
+};
+
+__global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdParams p) {
+  extern __shared__ float sh[];
+  const int groups = p.C >> 3;
+  const int rows_per_block = kEwThreads / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (r < rows_per_block) {
+    float sc[8], sf[8], mu[8], rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(p.scale + g * 8 + j);
+      sf[j] = __ldg(p.shift + g * 8 + j);
+      mu[j] = __ldg(p.mean + g * 8 + j);
+      rs[j] = __ldg(p.rstd + g * 8 + j);
+    }
+    for (int64_t row = (int64_t)blockIdx.x * rows_per_block + r; row < p.M; row += (int64_t)gridDim.x * rows_per_block) {
+      float dy[8], x[8], go[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.dy + row * p.ld_dy + p.c_off_dy + g * 8)), dy);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.raw + row * p.ld_raw + p.c_off_raw + g * 8)), x);
+      uint32_t keep = 0xFFu;
+      if (p.drop_p > 0.f) keep = dropout_keep8(p.seed, p.offset, (uint64_t)(row * groups + g) * 8, p.drop_p);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gg = ((keep >> j) & 1u) ? dy[j] * keep_scale : 0.f;
+        if (p.relu && !(fmaf(x[j], sc[j], sf[j]) > 0.f)) gg = 0.f;
+        go[j] = gg;
+        s[j] += gg;
+        q[j] = fmaf(gg, (x[j] - mu[j]) * rs[j], q[j]);
+      }
+      *reinterpret_cast<uint4*>(p.g + row * p.C + g * 8) = pack8(go);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sh[threadIdx.x * 16 + i] = s[i];
+    sh[threadIdx.x * 16 + 8 + i] = q[i];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < groups * 16; t += kEwThreads) {
+    const int gg = t / 16, slot = t % 16;
+    float acc = 0.f;
+    for (int rr = 0; rr < rows_per_block; ++rr) acc += sh[(rr * groups + gg) * 16 + slot];
+    atomicAdd(p.sums + (slot >> 3) * p.C + gg * 8 + (slot & 7), acc);
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdParams p) {
+  const int groups = p.C >> 3;
+  const int64_t total = p.M * groups;
+  const float inv_m = 1.f / (float)p.M;
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kEwThreads) {
+    const int64_t row = i / groups;
+    const int g = (int)(i - row * groups);
+    float gg[8], x[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.g + row * p.C + g * 8)), gg);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.raw + row * p.ld_raw + p.c_off_raw + g * 8)), x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      const float xh = (x[j] - __ldg(p.mean + c)) * __ldg(p.rstd + c);
+      const float mg = __ldg(p.inv_m_sums + c) * inv_m, mgx = __ldg(p.inv_m_sums + p.C + c) * inv_m;
+      o[j] = __ldg(p.scale + c) * (gg[j] - mg - xh * mgx);
+    }
+    *reinterpret_cast<uint4*>(p.draw + row * p.C + g * 8) = pack8(o);
+  }
+}
+
+// ---- bilinear upsample NHWC bf16 (align_corners=True) -----------------------------------------
+__global__ void __launch_bounds__(kEwThreads) upsample_nhwc_kernel(const __nv_bfloat16* __restrict__ in, int N, int h, int w,
+                                                                   int C, int ld_in, __nv_bfloat16* __restrict__ out, int H,
+                                                                   int W, int ld_out, int c_off, float sh_, float sw_) {
+  const int groups = C >> 3;
+  const int64_t total = (int64_t)N * H * W * groups;
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kEwThreads) {
+    const int g = (int)(i % groups);
+    int64_t t = i / groups;
+    const int x = (int)(t % W);
+    t /= W;
+    const int y = (int)(t % H);
+    const int n = (int)(t / H);
+    const Lerp ly = lerp_ac(y, h, H, sh_), lx = lerp_ac(x, w, W, sw_);
+    const __nv_bfloat16* b = in + (int64_t)n * h * w * ld_in + g * 8;
+    float v00[8], v01[8], v10[8], v11[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((int64_t)ly.i0 * w + lx.i0) * ld_in)), v00);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((int64_t)ly.i0 * w + lx.i1) * ld_in)), v01);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((int64_t)ly.i1 * w + lx.i0) * ld_in)), v10);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((int64_t)ly.i1 * w + lx.i1) * ld_in)), v11);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = ly.l0 * (lx.l0 * v00[j] + lx.l1 * v01[j]) + ly.l1 * (lx.l0 * v10[j] + lx.l1 * v11[j]);
+    *reinterpret_cast<uint4*>(out + (((int64_t)n * H + y) * W + x) * ld_out + c_off + g * 8) = pack8(o);
+  }
+}
+
+// adjoint: grad_in (f32 [N,h,w,C], zeroed) += scatter of grad_out slice (bf16 [N,H,W,ld] at c_off)
+__global__ void __launch_bounds__(kEwThreads) upsample_nhwc_bwd_kernel(const __nv_bfloat16* __restrict__ gout, int N, int H,
+                                                                       int W, int ld, int c_off, int C,
+                                                                       float* __restrict__ gin, int h, int w, float sh_,
+                                                                       float sw_) {
+  const int groups = C >> 3;
+  const int64_t total = (int64_t)N * H * W * groups;
+  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kEwThreads) {
+    const int g = (int)(i % groups);
+    int64_t t = i / groups;
+    const int x = (int)(t % W);
+    t /= W;
+    const int y = (int)(t % H);
+    const int n = (int)(t / H);
+    const Lerp ly = lerp_ac(y, h, H, sh_), lx = lerp_ac(x, w, W, sw_);
+    float gv[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gout + (((int64_t)n * H + y) * W + x) * ld + c_off + g * 8)), gv);
+    float* b = gin + (int64_t)n * h * w * C + g * 8;
+    float* p00 = b + ((int64_t)ly.i0 * w + lx.i0) * C;
+    float* p01 = b + ((int64_t)ly.i0 * w + lx.i1) * C;
+    float* p10 = b + ((int64_t)ly.i1 * w + lx.i0) * C;
+    float* p11 = b + ((int64_t)ly.i1 * w + lx.i1) * C;
+    const float w00 = ly.l0 * lx.l0, w01 = ly.l0 * lx.l1, w10 = ly.l1 * lx.l0, w11 = ly.l1 * lx.l1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(p00 + j, gv[j] * w00);
+      if (w01 != 0.f) atomicAdd(p01 + j, gv[j] * w01);
+      if (w10 != 0.f) atomicAdd(p10 + j, gv[j] * w10);
+      if (w11 != 0.f) atomicAdd(p11 + j, gv[j] * w11);
+    }
+  }
+}
+
+// ---- NCHW (f32 / bf16, any strides) -> NHWC bf16 with channel padding ----------------------------
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads) to_nhwc_bf16_kernel(const T* __restrict__ in, int64_t sn, int64_t sc, int64_t sh_,
+                                                                  int64_t sw_, int N, int C, int H, int W,
+                                                                  __nv_bfloat16* __restrict__ out, int ld, int c_off) {
+  // tile transpose through shared memory: 32 channels x 32 pixels
+  __shared__ float tile[32][33];
+  const int64_t HW = (int64_t)H * W;
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 256 threads: ty in 0..7
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int c = c0 + cc;
+    const int64_t pix = p0 + tx;
+    float v = 0.f;
+    if (c < C && pix < HW) {
+      const int y = (int)(pix / W), x = (int)(pix - (int64_t)y * W);
+      v = (float)in[(int64_t)n * sn + (int64_t)c * sc + (int64_t)y * sh_ + (int64_t)x * sw_];
+    }
+    tile[cc][tx] = v;
+  }
+  __syncthreads();
+  for (int pp_ = ty; pp_ < 32; pp_ += 8) {
+    const int64_t pix = p0 + pp_;
+    const int c = c0 + tx;
+    if (pix < HW && c < C) out[((int64_t)n * HW + pix) * ld + c_off + c] = __float2bfloat16(tile[tx][pp_]);
+  }
+}
+
+static inline int ew_grid(int64_t total) {
+  int64_t b = (total + kEwThreads - 1) / kEwThreads;
+  if (b > 148 * 16) b = 148 * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" {
+
+int pp_bn_stats(const void* raw, int64_t M, int ld, int c_off, int C, float* sums, void* stream) {
+  PP_CHECK_ARG(raw && sums && M > 0, "pp_bn_stats: bad args");
+  PP_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && ld % 8 == 0 && c_off % 8 == 0,
+               "pp_bn_stats: C=%d ld=%d c_off=%d must be multiples of 8 (C <= 2048)", C, ld, c_off);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  PP_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
+  const int rows_per_block = kEwThreads / (C / 8);
+  int64_t blocks = (M + rows_per_block * 8 - 1) / (rows_per_block * 8);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  bn_stats_kernel<<<(int)blocks, kEwThreads, kEwThreads * 16 * sizeof(float), st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(raw), M, ld, c_off, C, sums);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+int pp_bn_apply(const void* raw, int64_t M, int ld_in, int c_off_in, int C, const float* scale, const float* shift,
+                int relu, float drop_p, uint64_t seed, uint64_t offset, void* out, int ld_out, int c_off_out,
+                void* stream) {
+  PP_CHECK_ARG(raw && out && scale && shift && M > 0, "pp_bn_apply: bad args");
+  PP_CHECK_ARG(C % 8 == 0 && ld_in % 8 == 0 && c_off_in % 8 == 0 && ld_out % 8 == 0 && c_off_out % 8 == 0,
+               "pp_bn_apply: channel counts/offsets must be multiples of 8");
+  PP_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "pp_bn_apply: drop_p=%f", drop_p);
+  BnApplyParams p;
+  p.raw = reinterpret_cast<const __nv_bfloat16*>(raw);
+  p.M = M; p.ld_in = ld_in; p.c_off_in = c_off_in; p.C = C; p.scale = scale; p.shift = shift; p.relu = relu;
+  p.drop_p = drop_p; p.seed = seed; p.offset = offset;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ld_out = ld_out; p.c_off_out = c_off_out;
+  bn_apply_kernel<<<ew_grid(M * (C / 8)), kEwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+int pp_bn_bwd(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_raw, int c_off_raw, int64_t M, int C,
+              const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
+              uint64_t seed, uint64_t offset, void* g_tmp, float* sums, void* draw, void* stream) {
+  PP_CHECK_ARG(dy && raw && g_tmp && sums && draw && M > 0, "pp_bn_bwd: bad args");
+  PP_CHECK_ARG(C % 8 == 0 && C <= 2048 && ld_dy % 8 == 0 && c_off_dy % 8 == 0 && ld_raw % 8 == 0 && c_off_raw % 8 == 0,
+               "pp_bn_bwd: C=%d must be a multiple of 8 and <= 2048", C);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  BnBwdParams p;
+  p.dy = reinterpret_cast<const __nv_bfloat16*>(dy); p.ld_dy = ld_dy; p.c_off_dy = c_off_dy;
+  p.raw = reinterpret_cast<const __nv_bfloat16*>(raw); p.ld_raw = ld_raw; p.c_off_raw = c_off_raw;
+  p.M = M; p.C = C; p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.relu = relu;
+  p.drop_p = drop_p; p.seed = seed; p.offset = offset;
+  p.g = reinterpret_cast<__nv_bfloat16*>(g_tmp); p.sums = sums; p.inv_m_sums = sums;
+  p.draw = reinterpret_cast<__nv_bfloat16*>(draw);
+  PP_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
+  const int rows_per_block = kEwThreads / (C / 8);
+  int64_t blocks = (M + rows_per_block * 8 - 1) / (rows_per_block * 8);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  bn_bwd_reduce_kernel<<<(int)blocks, kEwThreads, kEwThreads * 16 * sizeof(float), st>>>(p);
+  PP_LAUNCH_CHECK();
+  bn_bwd_apply_kernel<<<ew_grid(M * (C / 8)), kEwThreads, 0, st>>>(p);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+int pp_upsample_nhwc_bf16(const void* in, int N, int h, int w, int C, int ld_in, void* out, int H, int W, int ld_out,
+                          int c_off, void* stream) {
+  PP_CHECK_ARG(in && out && N > 0 && h > 0 && w > 0 && H > 0 && W > 0, "pp_upsample_nhwc_bf16: bad args");
+  PP_CHECK_ARG(C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && c_off % 8 == 0, "pp_upsample_nhwc_bf16: multiples of 8");
+  upsample_nhwc_kernel<<<ew_grid((int64_t)N * H * W * (C / 8)), kEwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), N, h, w, C, ld_in, reinterpret_cast<__nv_bfloat16*>(out), H, W, ld_out,
+      c_off, ac_scale(h, H), ac_scale(w, W));
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+int pp_upsample_nhwc_bf16_bwd(const void* grad_out, int N, int H, int W, int ld, int c_off, int C, float* grad_in, int h,
+                              int w, void* stream) {
+  PP_CHECK_ARG(grad_out && grad_in && N > 0 && h > 0 && w > 0 && H > 0 && W > 0, "pp_upsample_nhwc_bf16_bwd: bad args");
+  PP_CHECK_ARG(C % 8 == 0 && ld % 8 == 0 && c_off % 8 == 0, "pp_upsample_nhwc_bf16_bwd: multiples of 8");
+  upsample_nhwc_bwd_kernel<<<ew_grid((int64_t)N * H * W * (C / 8)), kEwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(grad_out), N, H, W, ld, c_off, C, grad_in, h, w, ac_scale(h, H), ac_scale(w, W));
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+int pp_to_nhwc_bf16(const void* in, int dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw, int N, int C, int H, int W,
+                    void* out, int ld, int c_off, void* stream) {
+  PP_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0 && ld >= c_off + C, "pp_to_nhwc_bf16: bad args");
+  PP_CHECK_ARG(N <= 65535, "pp_to_nhwc_bf16: N too large");
+  dim3 grid((unsigned)(((int64_t)H * W + 31) / 32), (C + 31) / 32, N);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == PP_F32)
+    to_nhwc_bf16_kernel<float><<<grid, kEwThreads, 0, st>>>(reinterpret_cast<const float*>(in), sn, sc, sh, sw, N, C, H, W,
+                                                             reinterpret_cast<__nv_bfloat16*>(out), ld, c_off);
+  else if (dtype == PP_BF16)
+    to_nhwc_bf16_kernel<__nv_bfloat16><<<grid, kEwThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), sn, sc, sh, sw,
+                                                                     N, C, H, W, reinterpret_cast<__nv_bfloat16*>(out), ld, c_off);
+  else {
+    set_error("pp_to_nhwc_bf16: bad dtype %d", dtype);
+    return PP_ERR_INVALID_ARG;
+  }
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+}  // extern "C"
+
+// ---- BN finalize: statistics -> (scale, shift, mean, rstd) + running-stat update ------------------
+// nn.BatchNorm2d train-mode semantics (biased variance to normalise, unbiased for running_var,
+// momentum update), one thread per channel.
+namespace pp {
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, int C, float inv_m, float unbias, float eps,
+                                   float momentum, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ out /*[4][Cpad]: scale, shift, mean, rstd*/, int Cpad) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cpad) return;
+  float scale = 0.f, shift = 0.f, mean = 0.f, rstd = 0.f;
+  if (c < C) {
+    mean = sums[c] * inv_m;
+    float var = fmaf(-mean, mean, sums[C + c] * inv_m);
+    var = fmaxf(var, 0.f);
+    rstd = rsqrtf(var + eps);
+    scale = gamma[c] * rstd;
+    shift = fmaf(-mean, scale, beta[c]);
+    if (running_mean) {
+      running_mean[c] = fmaf(momentum, mean - running_mean[c], running_mean[c]);
+      running_var[c] = fmaf(momentum, var * unbias - running_var[c], running_var[c]);
+    }
+  }
+  out[c] = scale;
+  out[Cpad + c] = shift;
+  out[2 * Cpad + c] = mean;
+  out[3 * Cpad + c] = rstd;
+}
+}  // namespace pp
+
+extern "C" int pp_bn_finalize(const float* sums, int C, int64_t M, float eps, float momentum, const float* gamma,
+                              const float* beta, float* running_mean, float* running_var, float* out, int Cpad,
+                              void* stream) {
+  PP_CHECK_ARG(sums && gamma && beta && out && C > 0 && Cpad >= C && M > 0, "pp_bn_finalize: bad args");
+  const float unbias = M > 1 ? (float)M / (float)(M - 1) : 1.f;
+  pp::bn_finalize_kernel<<<(Cpad + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      sums, C, 1.f / (float)M, unbias, eps, momentum, gamma, beta, running_mean, running_var, out, Cpad);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}

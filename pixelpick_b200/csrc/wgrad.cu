@@ -1,0 +1,260 @@
+// T path — weight gradient of the NHWC bf16 convolutions on tcgen05 tensor cores.
+//
+//   dW[tap][ci][co] = sum over pixels p of  X[p + shift(tap)][ci] * dY[p][co]
+//
+// GEMM view: M = input channels (128 per tile), N = output channels (BN <= 256), K = pixels.
+// Both operands are stored pixel-major (NHWC), i.e. "MN-major" for this GEMM: a TMA box
+// {64 ch, 8, 8, 1} lands as 64 pixel rows x 128 B with the 128-byte swizzle, which is the canonical
+// MN-major UMMA layout (8-row K groups 1024 B apart = SBO, 64-channel chunks one box apart = LBO);
+// the instruction descriptor carries a_major = b_major = MN.  The shifted X box is zero-filled by TMA
+// outside the image (the conv's padding).  K is split over CTAs; partial tiles are reduced with
+// fp32 red.global.add into dW (zeroed by the caller).
+#include "tc_common.cuh"
+
+namespace pp {
+
+constexpr int kWgThreads = 192;
+constexpr int kPB = 8;                       // pixel block is kPB x kPB = 64 pixels (one K block)
+constexpr uint32_t kBoxBytes = 64 * 64 * 2;  // one {64 ch, 8, 8} box = 8 KB
+
+struct WgradParams {
+  int N, H, W;
+  int Cin, Cout_pad;  // valid input channels (rows written), padded output channels (BN multiple)
+  int taps, dil;
+  int pby, pbx;       // pixel blocks per image
+  int n_ci_tiles, splits;
+  float* dw;          // [taps][Cin_rows][Cout_pad] fp32, Cin_rows = n_ci_tiles * 128 rows allocated >= Cin
+  int Cin_rows;
+};
+
+template <int BN>
+struct WgCfg {
+  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
+  static constexpr uint32_t A_BYTES = 2 * kBoxBytes;
+  static constexpr uint32_t B_BYTES = (BN / 64) * kBoxBytes;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ bool pb_skipped(int dy, int dx, int y0, int x0, int H, int W) {
+  return (y0 + dy + kPB <= 0) || (y0 + dy >= H) || (x0 + dx + kPB <= 0) || (x0 + dx >= W);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WgradParams p) {
+  using Cfg = WgCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto sA = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES; };
+  auto sB = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * Cfg::STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - tc::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work item
+  int item = blockIdx.x;
+  const int split = item % p.splits;
+  item /= p.splits;
+  const int ci_tile = item % p.n_ci_tiles;
+  const int tap = item / p.n_ci_tiles;
+  const int ci0 = ci_tile * 128;
+  int dy = 0, dx = 0;
+  if (p.taps == 9) {
+    dy = (tap / 3 - 1) * p.dil;
+    dx = (tap % 3 - 1) * p.dil;
+  }
+  const int pb_per_img = p.pby * p.pbx;
+  const int total_pb = p.N * pb_per_img;
+  const int pb_lo = (int)((int64_t)total_pb * split / p.splits);
+  const int pb_hi = (int)((int64_t)total_pb * (split + 1) / p.splits);
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmX);
+    tc::tma_prefetch_desc(&tmDY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      tc::mbar_init(full_bar(s), 1);
+      tc::mbar_init(empty_bar(s), 1);
+    }
+    tc::mbar_init(tfull_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto decode = [&](int pb, int& img, int& y0, int& x0) {
+    img = pb / pb_per_img;
+    const int r = pb - img * pb_per_img;
+    const int ty = r / p.pbx;
+    y0 = ty * kPB;
+    x0 = (r - ty * p.pbx) * kPB;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int pb = pb_lo; pb < pb_hi; ++pb) {
+        int img, y0, x0;
+        decode(pb, img, y0, x0);
+        if (pb_skipped(dy, dx, y0, x0, p.H, p.W)) continue;
+        const int s = it % Cfg::STAGES;
+        const uint32_t ph = (it / Cfg::STAGES) & 1u;
+        tc::mbar_wait(empty_bar(s), ph ^ 1u);
+        tc::mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          tc::tma_load_4d(sA(s) + j * kBoxBytes, &tmX, full_bar(s), ci0 + 64 * j, x0 + dx, y0 + dy, img);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tc::tma_load_4d(sB(s) + j * kBoxBytes, &tmDY, full_bar(s), 64 * j, x0, y0, img);
+        ++it;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN, 1, 1);
+      uint32_t it = 0, accumulate = 0;
+      for (int pb = pb_lo; pb < pb_hi; ++pb) {
+        int img, y0, x0;
+        decode(pb, img, y0, x0);
+        if (pb_skipped(dy, dx, y0, x0, p.H, p.W)) continue;
+        const int s = it % Cfg::STAGES;
+        const uint32_t ph = (it / Cfg::STAGES) & 1u;
+        tc::mbar_wait(full_bar(s), ph);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 64 pixels = 4 x K16; 16 pixel rows = 2048 B
+          const uint64_t da = tc::umma_desc_sw128(sA(s) + k * 2048, kBoxBytes, 1024);
+          const uint64_t db = tc::umma_desc_sw128(sB(s) + k * 2048, kBoxBytes, 1024);
+          tc::umma_bf16(tmem_base, da, db, idesc, accumulate);
+          accumulate = 1;
+        }
+        tc::umma_commit(empty_bar(s));
+        ++it;
+      }
+      tc::umma_commit(tfull_bar);
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // input channel within the tile
+    int n_valid = 0;
+    for (int pb = pb_lo; pb < pb_hi; ++pb) {
+      int img, y0, x0;
+      decode(pb, img, y0, x0);
+      n_valid += pb_skipped(dy, dx, y0, x0, p.H, p.W) ? 0 : 1;
+    }
+    tc::mbar_wait(tfull_bar, 0);
+    tc::tc_fence_after();
+    if (n_valid > 0) {
+      const int ci = ci0 + row;
+      float* dst = p.dw + ((size_t)tap * p.Cin_rows + ci) * p.Cout_pad;
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + j * 32, r);
+        tc::tmem_ld_wait();
+        if (ci < p.Cin) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) atomicAdd(dst + j * 32 + c, __uint_as_float(r[c]));
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradParams& p, cudaStream_t st) {
+  using Cfg = WgCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    PP_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr = true;
+  }
+  const int grid = p.taps * p.n_ci_tiles * p.splits;
+  wgrad_kernel<BN><<<grid, kWgThreads, Cfg::SMEM, st>>>(tmX, tmDY, p);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" {
+
+int pp_conv_wgrad(const void* x, int ld_x, int Cin, const void* dy, int ld_dy, int Cout_pad, int N, int H, int W,
+                  int taps, int dil, float* dw, int Cin_rows, int splits, void* stream) {
+  PP_CHECK_ARG(x && dy && dw, "pp_conv_wgrad: null pointer");
+  PP_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0, "pp_conv_wgrad: bad shape");
+  PP_CHECK_ARG(taps == 1 || taps == 9, "pp_conv_wgrad: taps=%d", taps);
+  PP_CHECK_ARG(ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_x >= Cin && ld_dy >= Cout_pad, "pp_conv_wgrad: bad leading dims");
+  PP_CHECK_ARG(Cout_pad == 64 || Cout_pad == 128 || Cout_pad == 256, "pp_conv_wgrad: Cout_pad=%d (64, 128 or 256)", Cout_pad);
+  const int n_ci_tiles = (Cin + 127) / 128;
+  PP_CHECK_ARG(Cin_rows >= n_ci_tiles * 128 || Cin_rows >= Cin, "pp_conv_wgrad: Cin_rows=%d too small", Cin_rows);
+  PP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(dy) % 16) == 0,
+               "pp_conv_wgrad: x / dy must be 16-byte aligned");
+  WgradParams p;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout_pad = Cout_pad; p.taps = taps; p.dil = dil;
+  p.pby = (H + kPB - 1) / kPB;
+  p.pbx = (W + kPB - 1) / kPB;
+  p.n_ci_tiles = n_ci_tiles;
+  const int total_pb = N * p.pby * p.pbx;
+  if (splits <= 0) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    splits = (2 * sms + taps * n_ci_tiles - 1) / (taps * n_ci_tiles);
+    const int max_splits = (total_pb + 7) / 8;  // at least 8 pixel blocks (512 pixels) per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > total_pb) splits = total_pb;
+  p.splits = splits;
+  p.dw = dw;
+  p.Cin_rows = Cin_rows;
+  CUtensorMap tmX, tmDY;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t strides[3] = {(uint64_t)ld_x * 2, (uint64_t)W * ld_x * 2, (uint64_t)H * W * ld_x * 2};
+    const uint32_t box[4] = {64, kPB, kPB, 1};
+    int rc = make_tmap_bf16(&tmX, x, 4, dims, strides, box);
+    if (rc != PP_OK) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)Cout_pad, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t strides[3] = {(uint64_t)ld_dy * 2, (uint64_t)W * ld_dy * 2, (uint64_t)H * W * ld_dy * 2};
+    const uint32_t box[4] = {64, kPB, kPB, 1};
+    int rc = make_tmap_bf16(&tmDY, dy, 4, dims, strides, box);
+    if (rc != PP_OK) return rc;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (Cout_pad) {
+    case 256: return launch_wgrad<256>(tmX, tmDY, p, st);
+    case 128: return launch_wgrad<128>(tmX, tmDY, p, st);
+    default: return launch_wgrad<64>(tmX, tmDY, p, st);
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,574 @@
+"""Host-side mirror of the reference DeepLabv3+ (networks/deeplab.py, aspp.py, decoders.py:104-132,
+mobilenet_v2.py, backbones/resnet_*.py) for the T path.
+
+Same module tree and parameter names as the reference, so `state_dict()`s interchange and
+`get_optimizer`'s `model.backbone / model.aspp / model.low_level_conv / model.seg_head` groups work.
+What differs is WHERE the head (ASPP -> low-level 1x1 -> upsample+concat -> SegmentHead -> classifier) runs:
+every dense contraction is `pp_conv_igemm` / `pp_conv_wgrad` (tcgen05 tensor cores, NHWC bf16, fp32
+accumulate) and every normalisation / activation / dropout / resize is a fused NHWC kernel of
+`libpixelpick_b200.so`; `nn.Conv2d` / `nn.BatchNorm2d` objects of the head are parameter containers only.
+The encoders (MobileNetV2 / dilated ResNet-50: not kernels named by the north star) run as PyTorch modules
+in bf16 channels_last on the GPU.
+
+`forward(x)` keeps the reference contract ({"pred": full-resolution logits, "emb": ...});
+`forward_lowres(x)` returns the 1/4-resolution head logits that the fused sparse-CE and acquisition kernels
+consume (the x4 bilinear upsample of deeplab.py:55 is evaluated inside those kernels, never materialised).
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+
+# =============================================================================================
+# encoders (PyTorch modules; structure mirrors the reference so parameter names match)
+# =============================================================================================
+def _conv_bn(inp, oup, stride):
+    return nn.Sequential(nn.Conv2d(inp, oup, 3, stride, 1, bias=False), nn.BatchNorm2d(oup), nn.ReLU6(inplace=True))
+
+
+def fixed_padding(inputs, kernel_size, dilation):
+    """mobilenet_v2.py:15-21 — explicit zero padding applied BEFORE the expansion conv."""
+    k_eff = kernel_size + (kernel_size - 1) * (dilation - 1)
+    pad_total = k_eff - 1
+    beg = pad_total // 2
+    return F.pad(inputs, (beg, pad_total - beg, beg, pad_total - beg))
+
+
+class InvertedResidual(nn.Module):
+    """mobilenet_v2.py:24-66."""
+
+    def __init__(self, inp, oup, stride, dilation, expand_ratio):
+        super().__init__()
+        hidden = round(inp * expand_ratio)
+        self.use_res_connect = stride == 1 and inp == oup
+        self.kernel_size, self.dilation = 3, dilation
+        layers = []
+        if expand_ratio != 1:
+            layers += [nn.Conv2d(inp, hidden, 1, 1, 0, 1, bias=False), nn.BatchNorm2d(hidden), nn.ReLU6(inplace=True)]
+        layers += [nn.Conv2d(hidden, hidden, 3, stride, 0, dilation, groups=hidden, bias=False), nn.BatchNorm2d(hidden),
+                   nn.ReLU6(inplace=True), nn.Conv2d(hidden, oup, 1, 1, 0, 1, bias=False), nn.BatchNorm2d(oup)]
+        self.conv = nn.Sequential(*layers)
+
+    def forward(self, x):
+        x_pad = fixed_padding(x, self.kernel_size, self.dilation)
+        return x + self.conv(x_pad) if self.use_res_connect else self.conv(x_pad)
+
+
+class MobileNetV2(nn.Module):
+    """mobilenet_v2.py:69-137 (no weight download: there is no network; weights come from a state_dict)."""
+
+    def __init__(self, output_stride=16, mc_dropout=False, mc_dropout_p=0.2):
+        super().__init__()
+        setting = [[1, 16, 1, 1], [6, 24, 2, 2], [6, 32, 3, 2], [6, 64, 4, 2], [6, 96, 3, 1], [6, 160, 3, 2], [6, 320, 1, 1]]
+        inp, cur, rate = 32, 2, 1
+        feats = [_conv_bn(3, inp, 2)]
+        for t, c, n, s in setting:
+            if cur == output_stride:
+                stride, dil = 1, rate
+                rate *= s
+            else:
+                stride, dil = s, 1
+                cur *= s
+            for i in range(n):
+                feats.append(InvertedResidual(inp, c, stride if i == 0 else 1, dil, t))
+                inp = c
+        if mc_dropout:
+            feats.append(nn.Dropout2d(p=mc_dropout_p))
+        self.features = nn.Sequential(*feats)
+        for m in self.modules():  # mobilenet_v2.py:149-155
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight)
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+        self.low_level_features = self.features[0:4]
+        self.high_level_features = self.features[4:]
+        self.dropout = nn.Dropout2d(p=mc_dropout_p)
+        self.mc_dropout = mc_dropout
+        self.out_channels, self.low_channels = 320, 24
+
+    def forward(self, x):
+        low = self.low_level_features(x)
+        x = self.high_level_features(low)
+        if self.mc_dropout:
+            low = self.dropout(low)
+        return x, low
+
+
+class Bottleneck(nn.Module):
+    """resnet_models.py:58-94 (stride on the 3x3)."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+
+    def forward(self, x):
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        return self.relu(out + (x if self.downsample is None else self.downsample(x)))
+
+
+class ResNet50Dilated8(nn.Module):
+    """ResNet-50 with layer3/layer4 strides removed and dilations 2/4 (resnet_backbone.py:42-104): returns
+    (c5 [2048, 1/8], c2 [256, 1/4]) — the encoder of the RN50-DeepLabv3+ composition."""
+
+    def __init__(self):
+        super().__init__()
+        self.prefix = nn.Sequential(OrderedDict([("conv1", nn.Conv2d(3, 64, 7, 2, 3, bias=False)), ("bn1", nn.BatchNorm2d(64)),
+                                                 ("relu", nn.ReLU(inplace=False))]))
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        self.inplanes = 64
+        self.layer1 = self._make_layer(64, 3, 1)
+        self.layer2 = self._make_layer(128, 4, 2)
+        self.layer3 = self._make_layer(256, 6, 2)
+        self.layer4 = self._make_layer(512, 3, 2)
+        for m in self.modules():  # resnet_models.py:131-137
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2.0 / n))
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+        self.layer3.apply(lambda m: self._nostride_dilate(m, 2))
+        self.layer4.apply(lambda m: self._nostride_dilate(m, 4))
+        self.out_channels, self.low_channels = 2048, 256
+
+    def _make_layer(self, planes, blocks, stride):
+        down = None
+        if stride != 1 or self.inplanes != planes * 4:
+            down = nn.Sequential(nn.Conv2d(self.inplanes, planes * 4, 1, stride, bias=False), nn.BatchNorm2d(planes * 4))
+        layers = [Bottleneck(self.inplanes, planes, stride, down)]
+        self.inplanes = planes * 4
+        layers += [Bottleneck(self.inplanes, planes) for _ in range(1, blocks)]
+        return nn.Sequential(*layers)
+
+    @staticmethod
+    def _nostride_dilate(m, dilate):  # resnet_backbone.py:72-85
+        if isinstance(m, nn.Conv2d):
+            if m.stride == (2, 2):
+                m.stride = (1, 1)
+                if m.kernel_size == (3, 3):
+                    m.dilation, m.padding = (dilate // 2, dilate // 2), (dilate // 2, dilate // 2)
+            elif m.kernel_size == (3, 3):
+                m.dilation, m.padding = (dilate, dilate), (dilate, dilate)
+
+    def forward(self, x):
+        x = self.maxpool(self.prefix(x))
+        c2 = self.layer1(x)
+        c5 = self.layer4(self.layer3(self.layer2(c2)))
+        return c5, c2
+
+
+# =============================================================================================
+# head: parameter containers with the reference names
+# =============================================================================================
+def _init_head(mod):
+    for m in mod.modules():  # aspp.py:22-28,81-88; decoders.py:125-132
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight)
+        elif isinstance(m, nn.BatchNorm2d):
+            m.weight.data.fill_(1)
+            m.bias.data.zero_()
+
+
+class _ASPPModule(nn.Module):
+    def __init__(self, inplanes, planes, kernel_size, padding, dilation):
+        super().__init__()
+        self.atrous_conv = nn.Conv2d(inplanes, planes, kernel_size, 1, padding, dilation, bias=False)
+        self.bn = nn.BatchNorm2d(planes)
+        self.relu = nn.ReLU()
+
+
+class ASPP(nn.Module):
+    """aspp.py:31-88."""
+
+    def __init__(self, backbone, output_stride):
+        super().__init__()
+        inplanes = {"drn": 512, "mobilenet": 320}.get(backbone, 2048)
+        self.dilations = {16: [1, 6, 12, 18], 8: [1, 12, 24, 36]}[output_stride]
+        d = self.dilations
+        self.aspp1 = _ASPPModule(inplanes, 256, 1, 0, d[0])
+        self.aspp2 = _ASPPModule(inplanes, 256, 3, d[1], d[1])
+        self.aspp3 = _ASPPModule(inplanes, 256, 3, d[2], d[2])
+        self.aspp4 = _ASPPModule(inplanes, 256, 3, d[3], d[3])
+        self.global_avg_pool = nn.Sequential(nn.AdaptiveAvgPool2d((1, 1)), nn.Conv2d(inplanes, 256, 1, stride=1, bias=False),
+                                             nn.BatchNorm2d(256), nn.ReLU())
+        self.conv1 = nn.Conv2d(1280, 256, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(256)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(0.5)
+        self.inplanes = inplanes
+        _init_head(self)
+
+
+class SegmentHead(nn.Module):
+    """decoders.py:104-132."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.segment_head = nn.Sequential(nn.Conv2d(304, 256, 3, 1, 1, bias=False), nn.BatchNorm2d(256), nn.ReLU(),
+                                          nn.Dropout(0.5),
+                                          nn.Conv2d(256, 256, 3, 1, 1, bias=False), nn.BatchNorm2d(256), nn.ReLU(),
+                                          nn.Dropout(args.mc_dropout_p))
+        self.classifier = nn.Conv2d(256, args.n_classes, 1)
+        self.n_classes = args.n_classes
+        _init_head(self)
+
+
+# =============================================================================================
+# head: kernels
+# =============================================================================================
+def _pack(w, cin_pad=None, cout_pad=None, dgrad=False):
+    return _lib.pack_conv_weight(w.detach(), cin_pad, cout_pad, dgrad)
+
+
+def _fold_bn(bn, cpad=None):
+    """eval-mode BatchNorm as (scale, shift) f32 vectors."""
+    scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+    shift = bn.bias.detach().float() - bn.running_mean.float() * scale
+    if cpad is not None and cpad != scale.numel():
+        scale, shift = F.pad(scale, (0, cpad - scale.numel())), F.pad(shift, (0, cpad - shift.numel()))
+    return scale.contiguous(), shift.contiguous()
+
+
+def _as_nhwc(x):
+    """[N, C, H, W] -> contiguous bf16 NHWC with C padded to 64 (zero-copy for channels_last bf16, C % 64 == 0)."""
+    N, C, H, W = x.shape
+    if x.dtype == torch.bfloat16 and C % 64 == 0:
+        v = x.permute(0, 2, 3, 1)
+        if v.is_contiguous():
+            return v
+    return _lib.to_nhwc_bf16(x)
+
+
+class _Layer:
+    """What the backward of one conv+BN(+ReLU)(+Dropout) layer needs."""
+    __slots__ = ("x", "cin", "w", "taps", "dil", "raw", "c_off", "C", "stats", "relu", "p", "offset", "bn")
+
+
+class _HeadFn(torch.autograd.Function):
+    """Train-mode forward/backward of the whole head as one autograd node.
+    inputs : high [B, Cin, h, w], low [B, Cl, h4, w4], pre_bias [B, 256] (ASPP image-pooling branch, computed by
+             autograd-tracked torch ops on tiny tensors), then the head parameters.
+    output : 1/4-resolution logits, f32 NCHW [B, n_classes, h4, w4]."""
+
+    @staticmethod
+    def forward(ctx, model, seed, high, low, pre_bias, *params):
+        (w1, g1, b1, w2, g2, b2, w3, g3, b3, w4, g4, b4, wc, gc, bc, wl, gl, bl, wd1, gd1, bd1, wd2, gd2, bd2, wk, bk) = params
+        aspp, sh = model.aspp, model.seg_head
+        xh = _as_nhwc(high)
+        xl = _as_nhwc(low)
+        B, h, w, cin = xh.shape
+        _, hq, wq, _ = xl.shape
+        dev = xh.device
+        layers = []
+        off = [0]
+
+        def next_offset(n_elem):
+            o = off[0]
+            off[0] += (n_elem + 7) // 8 + 1
+            return o
+
+        def run_layer(x, cin_valid, wt, bn, dil, raw, c_off, C, out, out_c_off, relu=True, p=0.0, pre=None, cpad=None):
+            taps = wt.shape[2] * wt.shape[3]
+            cin_pad = x.shape[3]
+            wp = _pack(wt[:, :cin_valid], cin_pad, cpad or -(-C // 64) * 64)
+            _lib.conv_igemm(x, wp, C, dil=dil, pre_bias=pre, out=raw, c_off=c_off, cin=cin_pad)
+            rows = raw.numel() // raw.shape[-1]
+            stats = _lib.bn_finalize(_lib.bn_stats(raw, c_off, C), rows, bn, Cpad=cpad or C)
+            L = _Layer()
+            L.x, L.cin, L.w, L.taps, L.dil, L.raw, L.c_off, L.C = x, cin_valid, wt, taps, dil, raw, c_off, C
+            L.stats, L.relu, L.p, L.bn = stats, relu, p, bn
+            L.offset = next_offset(rows * (cpad or C)) if p > 0 else 0
+            _lib.bn_apply(raw, c_off, cpad or C, stats[0], stats[1], relu, out, out_c_off, drop_p=p, seed=seed, offset=L.offset)
+            layers.append(L)
+            return L
+
+        # ---- ASPP branches -> concat buffer (aspp.py:64-73) ----
+        raw_cat = torch.empty((B, h, w, 1024), dtype=torch.bfloat16, device=dev)
+        cat = torch.empty_like(raw_cat)
+        for i, (br, wt, d) in enumerate(zip((aspp.aspp1, aspp.aspp2, aspp.aspp3, aspp.aspp4), (w1, w2, w3, w4), aspp.dilations)):
+            run_layer(xh, cin, wt, br.bn, d, raw_cat, 256 * i, 256, cat, 256 * i)
+        # ---- projection + BN + ReLU + Dropout(0.5) (aspp.py:75-79) ----
+        raw_c1 = torch.empty((B, h, w, 256), dtype=torch.bfloat16, device=dev)
+        aspp_out = torch.empty_like(raw_c1)
+        pre = pre_bias.detach().float().contiguous()
+        run_layer(cat, 1024, wc, aspp.bn1, 1, raw_c1, 0, 256, aspp_out, 0, p=aspp.dropout.p, pre=pre)
+        # ---- decoder input: upsample + low-level 1x1 + concat (deeplab.py:48-50) ----
+        dec_in = torch.zeros((B, hq, wq, 320), dtype=torch.bfloat16, device=dev)
+        _lib.upsample_nhwc(aspp_out, dec_in, 0, 256)
+        raw_ll = torch.zeros((B, hq, wq, 64), dtype=torch.bfloat16, device=dev)
+        run_layer(xl, low.shape[1], wl, model.low_level_conv[1], 1, raw_ll, 0, 48, dec_in, 256, cpad=64)
+        # ---- SegmentHead (decoders.py:107-116) ----
+        raw_d1 = torch.empty((B, hq, wq, 256), dtype=torch.bfloat16, device=dev)
+        act_d1 = torch.empty_like(raw_d1)
+        run_layer(dec_in, 304, wd1, sh.segment_head[1], 1, raw_d1, 0, 256, act_d1, 0, p=sh.segment_head[3].p)
+        raw_d2 = torch.empty_like(raw_d1)
+        act_d2 = torch.empty_like(raw_d1)
+        run_layer(act_d1, 256, wd2, sh.segment_head[5], 1, raw_d2, 0, 256, act_d2, 0, p=sh.segment_head[7].p)
+        ncls = wk.shape[0]
+        shift = F.pad(bk.detach().float(), (0, 32 - ncls % 32 if ncls % 32 else 0)).contiguous()
+        logits = _lib.conv_igemm(act_d2, _pack(wk, 256), ncls, shift=shift, out_mode=1)
+        ctx.model, ctx.seed, ctx.layers = model, seed, layers
+        ctx.saved = (xh, xl, cat, aspp_out, dec_in, act_d1, act_d2)
+        ctx.shapes = (B, h, w, cin, hq, wq, low.shape[1], ncls)
+        ctx.high_dtype, ctx.low_dtype = high.dtype, low.dtype
+        ctx.save_for_backward(wk)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        model, seed, layers = ctx.model, ctx.seed, ctx.layers
+        xh, xl, cat, aspp_out, dec_in, act_d1, act_d2 = ctx.saved
+        B, h, w, cin, hq, wq, cl, ncls = ctx.shapes
+        (wk,) = ctx.saved_tensors
+        L1, L2, L3, L4, Lc, Ll, Ld1, Ld2 = layers
+
+        def layer_bwd(L, dy, c_off_dy, need_dx=True, cout_pad=256, dx_valid=None, dx_pad=None):
+            """returns (dW [Cout, Cin, k, k], dgamma, dbeta, dX bf16 NHWC or None, draw)."""
+            st = L.stats
+            C = st.shape[1]
+            draw, sums = _lib.bn_bwd(dy, c_off_dy, L.raw, L.c_off, C, st[0], st[1], st[2], st[3], L.relu, drop_p=L.p,
+                                     seed=seed, offset=L.offset)
+            N_, H_, W_ = L.x.shape[0], L.x.shape[1], L.x.shape[2]
+            draw4 = draw.view(N_, H_, W_, C)
+            dw = _lib.conv_wgrad(L.x, L.cin, draw4, C if C in (64, 128, 256) else cout_pad, L.taps, L.dil)
+            k = int(round(L.taps ** 0.5))
+            dW = dw[:, :L.cin, :L.C].permute(2, 1, 0).reshape(L.C, L.cin, k, k)
+            dx = None
+            if need_dx:
+                cin_pad = L.x.shape[3]
+                wt = L.w[:, :L.cin] if L.w.shape[1] != L.cin else L.w
+                wp = _pack(wt, C, dx_pad or cin_pad, dgrad=True)  # [taps][Cin_pad][C]
+                dx = _lib.conv_igemm(draw4, wp, dx_valid or cin_pad, dil=L.dil)
+            return dW, sums[1][:L.C], sums[0][:L.C], dx, draw4
+
+        # classifier (decoders.py:116): logits = act_d2 * wk + bk
+        dl = _lib.to_nhwc_bf16(dlogits.float().contiguous(), ld=64)
+        dwk = _lib.conv_wgrad(act_d2, 256, dl, 64, 1)[0, :256, :ncls].t().reshape(ncls, 256, 1, 1)
+        dbk = dlogits.float().sum(dim=(0, 2, 3))
+        d_act_d2 = _lib.conv_igemm(dl, _pack(wk, 64, 256, dgrad=True), 256)
+        dwd2, dgd2, dbd2, d_act_d1, _ = layer_bwd(Ld2, d_act_d2, 0)
+        dwd1, dgd1, dbd1, d_dec_in, _ = layer_bwd(Ld1, d_act_d1, 0)
+        # low-level branch: channels 256..303 of the decoder input (+16 zero pad channels)
+        dwl, dgl, dbl, d_low_nhwc, _ = layer_bwd(Ll, d_dec_in, 256, dx_valid=-(-cl // 8) * 8, dx_pad=-(-cl // 32) * 32)
+        d_low = d_low_nhwc[..., :cl].permute(0, 3, 1, 2).to(ctx.low_dtype)
+        # ASPP output: adjoint of the x4 bilinear upsample
+        d_aspp_out = _lib.upsample_nhwc_bwd(d_dec_in, 0, 256, (h, w)).to(torch.bfloat16)
+        dwc_main, dgc, dbc, d_cat, draw_c1 = layer_bwd(Lc, d_aspp_out, 0)
+        d_pre = draw_c1.float().sum(dim=(1, 2))  # gradient of the per-image bias = pooled-branch contribution
+        dwc = torch.zeros((256, 1280, 1, 1), dtype=torch.float32, device=dlogits.device)
+        dwc[:, :1024] = dwc_main
+        d_xh = None
+        outs = []
+        for i, L in enumerate((L1, L2, L3, L4)):
+            dW, dg, db, dx, _ = layer_bwd(L, d_cat, 256 * i)
+            outs += [dW, dg, db]
+            d_xh = dx.float() if d_xh is None else d_xh + dx.float()
+        d_high = d_xh[..., :cin].permute(0, 3, 1, 2).to(ctx.high_dtype)
+        grads = outs + [dwc, dgc, dbc, dwl, dgl, dbl, dwd1, dgd1, dbd1, dwd2, dgd2, dbd2, dwk, dbk]
+        return (None, None, d_high, d_low, d_pre) + tuple(grads)
+
+
+class DeepLab(nn.Module):
+    """Drop-in for networks/deeplab.py:DeepLab.  backbone: 'mobilenet' (reference) or 'resnet' (dilated-8 ResNet-50
+    -> ASPP(2048, OS8): the RN50-DeepLabv3+ composition of BASELINE configs 3-5)."""
+
+    def __init__(self, args, backbone="mobilenet", output_stride=16):
+        super().__init__()
+        if backbone == "mobilenet":
+            self.backbone = MobileNetV2(output_stride, mc_dropout=args.use_mc_dropout)
+        else:
+            self.backbone = ResNet50Dilated8()
+            output_stride = 8
+        self.aspp = ASPP(backbone, output_stride)
+        self.low_level_conv = nn.Sequential(nn.Conv2d(self.backbone.low_channels, 48, 1, bias=False), nn.BatchNorm2d(48),
+                                            nn.ReLU())
+        self.seg_head = SegmentHead(args)
+        _init_head(self.low_level_conv)
+        self.return_features = False
+        self.return_attention = False
+        self._step = 0
+        self.base_seed = 0
+        self._cache = {}
+        # encoder precision: torch.bfloat16 (default, BASELINE config 2) or None = fp32 (used by the parity tests to
+        # separate the encoder's bf16 rounding from the head kernels')
+        self.encoder_autocast = torch.bfloat16
+
+    # ---- reference API ----
+    def turn_on_dropout(self):
+        for m in self.modules():
+            if isinstance(m, nn.Dropout):
+                m.train()
+
+    def turn_off_dropout(self):
+        for m in self.modules():
+            if isinstance(m, nn.Dropout):
+                m.eval()
+
+    def set_return_features(self, return_features):
+        self.return_features = return_features
+
+    def set_return_attention(self, return_attention):
+        self.return_attention = return_attention
+
+    def get_1x_lr_params(self):
+        for m in self.backbone.modules():
+            if isinstance(m, (nn.Conv2d, nn.BatchNorm2d)):
+                for p in m.parameters():
+                    if p.requires_grad:
+                        yield p
+
+    def get_10x_lr_params(self):
+        for mod in (self.aspp, self.low_level_conv, self.seg_head):
+            for m in mod.modules():
+                if isinstance(m, (nn.Conv2d, nn.BatchNorm2d)):
+                    for p in m.parameters():
+                        if p.requires_grad:
+                            yield p
+
+    def train(self, mode=True):
+        self._cache.clear()
+        return super().train(mode)
+
+    def load_state_dict(self, *a, **k):
+        self._cache.clear()
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._cache.clear()
+        return super()._apply(fn, *a, **k)
+
+    # ---- encoder ----
+    def _encode(self, x):
+        if not x.is_cuda:
+            raise _lib.PixelPickError("pixelpick_b200.DeepLab runs on CUDA only (no CPU fallback)")
+        x = x.contiguous(memory_format=torch.channels_last)
+        if self.encoder_autocast is None:
+            return self.backbone(x)
+        with torch.autocast("cuda", dtype=self.encoder_autocast):
+            return self.backbone(x)
+
+    def _pooled_branch(self, high):
+        """aspp.py:54-57,69-70: image pooling -> 1x1 -> BN -> ReLU; its broadcast through the projection is a
+        per-image bias pre[b, :] = x5[b] @ W1[:, 1024:1280]^T (tiny tensors: autograd-tracked torch ops, fp32)."""
+        a = self.aspp
+        pooled = high.float().mean(dim=(2, 3))
+        g = F.linear(pooled, a.global_avg_pool[1].weight.flatten(1))
+        bn = a.global_avg_pool[2]
+        g = F.batch_norm(g, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum or 0.1, bn.eps)
+        if bn.training:
+            bn.num_batches_tracked += 1
+        x5 = F.relu(g)
+        return F.linear(x5, a.conv1.weight[:, 1024:].flatten(1))
+
+    # ---- head, eval mode (BatchNorm folded into the conv epilogues) ----
+    def _eval_weights(self):
+        c = self._cache
+        if "eval" not in c:
+            a, sh, cin = self.aspp, self.seg_head, self.aspp.inplanes
+            e = {}
+            e["br"] = [(_pack(m.atrous_conv.weight, cin, 256),) + _fold_bn(m.bn) for m in (a.aspp1, a.aspp2, a.aspp3, a.aspp4)]
+            e["c1"] = (_pack(a.conv1.weight[:, :1024], 1024, 256),) + _fold_bn(a.bn1)
+            e["ll"] = (_pack(self.low_level_conv[0].weight, -(-self.backbone.low_channels // 64) * 64, 64),) + _fold_bn(
+                self.low_level_conv[1], 64)
+            e["d1"] = (_pack(sh.segment_head[0].weight, 320, 256),) + _fold_bn(sh.segment_head[1])
+            e["d2"] = (_pack(sh.segment_head[4].weight, 256, 256),) + _fold_bn(sh.segment_head[5])
+            ncls = sh.n_classes
+            cp = -(-ncls // 32) * 32
+            e["cls"] = (_pack(sh.classifier.weight, 256, cp), F.pad(sh.classifier.bias.detach().float(), (0, cp - ncls)).contiguous())
+            c["eval"] = e
+        return c["eval"]
+
+    def _head_eval(self, high, low, want_emb=False):
+        e = self._eval_weights()
+        a, sh = self.aspp, self.seg_head
+        xh, xl = _as_nhwc(high), _as_nhwc(low)
+        B, h, w, _ = xh.shape
+        _, h4, w4, _ = xl.shape
+        dev = xh.device
+        cat = torch.empty((B, h, w, 1024), dtype=torch.bfloat16, device=dev)
+        for i, ((wp, sc, sf), d) in enumerate(zip(e["br"], a.dilations)):
+            _lib.conv_igemm(xh, wp, 256, dil=d, scale=sc, shift=sf, relu=True, out=cat, c_off=256 * i)
+        pre = self._pooled_branch(high).float().contiguous()
+        wp, sc, sf = e["c1"]
+        aspp_out = _lib.conv_igemm(cat, wp, 256, pre_bias=pre, scale=sc, shift=sf, relu=True)
+        dec_in = torch.zeros((B, h4, w4, 320), dtype=torch.bfloat16, device=dev)
+        _lib.upsample_nhwc(aspp_out, dec_in, 0, 256)
+        wp, sc, sf = e["ll"]
+        _lib.conv_igemm(xl, wp, 48, scale=sc, shift=sf, relu=True, out=dec_in, c_off=256)
+        wp, sc, sf = e["d1"]
+        h1 = _lib.conv_igemm(dec_in, wp, 256, scale=sc, shift=sf, relu=True)
+        wp, sc, sf = e["d2"]
+        h2 = _lib.conv_igemm(h1, wp, 256, scale=sc, shift=sf, relu=True)
+        wp, bias = e["cls"]
+        logits = _lib.conv_igemm(h2, wp, sh.n_classes, shift=bias, out_mode=1)
+        return (logits, h2) if want_emb else logits
+
+    def _head_params(self):
+        a, sh = self.aspp, self.seg_head
+        ps = []
+        for m in (a.aspp1, a.aspp2, a.aspp3, a.aspp4):
+            ps += [m.atrous_conv.weight, m.bn.weight, m.bn.bias]
+        ps += [a.conv1.weight, a.bn1.weight, a.bn1.bias]
+        ps += [self.low_level_conv[0].weight, self.low_level_conv[1].weight, self.low_level_conv[1].bias]
+        ps += [sh.segment_head[0].weight, sh.segment_head[1].weight, sh.segment_head[1].bias]
+        ps += [sh.segment_head[4].weight, sh.segment_head[5].weight, sh.segment_head[5].bias]
+        ps += [sh.classifier.weight, sh.classifier.bias]
+        return ps
+
+    def _dropout_active(self):
+        return any(m.training for m in self.modules() if isinstance(m, nn.Dropout))
+
+    def forward_lowres(self, x):
+        """1/4-resolution logits [B, n_classes, H/4, W/4] (f32 NCHW); the final x4 upsample is left to the caller."""
+        high, low = self._encode(x)
+        bn_train = self.aspp.bn1.training
+        if not bn_train and not (torch.is_grad_enabled() and any(p.requires_grad for p in self._head_params())) \
+                and not self._dropout_active():
+            return self._head_eval(high, low)
+        if not bn_train:
+            raise _lib.PixelPickError("head kernels support eval mode without grad/dropout, or full train mode")
+        pre = self._pooled_branch(high)
+        self._step += 1
+        seed = (self.base_seed * 1000003 + self._step) & 0x7FFFFFFFFFFFFFFF
+        return _HeadFn.apply(self, seed, high, low, pre, *self._head_params())
+
+    def forward(self, inputs):
+        """deeplab.py:43-61: {"pred": logits upsampled to the input size, "emb": 256-ch embedding (only
+        materialised when set_return_features(True): 134 MB / image at 256x512 and unused by train/query)}."""
+        size = tuple(inputs.shape[2:])
+        if self.return_features and not self.training:
+            high, low = self._encode(inputs)
+            lr, h2 = self._head_eval(high, low, want_emb=True)
+            emb = _UpsampleAC.apply(h2.permute(0, 3, 1, 2).float(), size)
+        else:
+            lr, emb = self.forward_lowres(inputs), None
+        return {"pred": _UpsampleAC.apply(lr, size), "emb": emb}
+
+
+class _UpsampleAC(torch.autograd.Function):
+    """F.interpolate(x, size, mode='bilinear', align_corners=True) through pp_upsample_bilinear_ac (+ adjoint)."""
+
+    @staticmethod
+    def forward(ctx, x, size):
+        ctx.in_size = tuple(x.shape[2:])
+        return _lib.upsample_bilinear_ac(x, size)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _lib.upsample_bilinear_ac_bwd(g, ctx.in_size), None

@@ -1,0 +1,88 @@
+"""GPU: tcgen05 implicit-GEMM convolution (pp_conv_igemm) vs torch fp32 conv2d on bf16-rounded operands.
+
+Tolerance: operands are rounded to bf16 on both sides, products are exact in fp32 and only the
+accumulation order differs, so f32 outputs agree to 1e-3 relative of the output scale (K up to 18432);
+bf16 outputs add one bf16 rounding (2^-9 relative)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from pixelpick_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def _case(N, H, W, Cin, Cout, k, dil, seed=0, ld_in=None):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((N, Cin, H, W), generator=g).to(torch.bfloat16)
+    w = (torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+    ref = F.conv2d(x.float(), w.float(), padding=dil if k == 3 else 0, dilation=dil)
+    cin_pad = -(-Cin // 64) * 64
+    ld = ld_in or cin_pad
+    x_nhwc = torch.zeros((N, H, W, ld), dtype=torch.bfloat16)
+    x_nhwc[..., :Cin] = x.permute(0, 2, 3, 1)
+    return x_nhwc.to(DEV), w, ref
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,dil,bn", [
+    (2, 64, 128, 320, 256, 3, 1, 0),     # SegmentHead conv #1 (304 padded to 320)
+    (2, 64, 128, 256, 256, 3, 1, 128),   # SegmentHead conv #2
+    (2, 16, 32, 320, 256, 1, 1, 0),      # ASPP 1x1 (MobileNetV2)
+    (2, 16, 32, 320, 256, 3, 6, 0),      # ASPP dilated branches
+    (2, 16, 32, 320, 256, 3, 12, 64),
+    (2, 16, 32, 320, 256, 3, 18, 32),
+    (1, 32, 64, 2048, 256, 3, 12, 0),    # ASPP ResNet-50 OS8
+    (1, 32, 64, 1024, 256, 1, 1, 256),   # ASPP projection (without the pooled branch)
+    (2, 23, 30, 320, 256, 3, 6, 0),      # CamVid 360x480 / 16: ragged tiles
+    (1, 90, 120, 256, 256, 3, 1, 0),     # CamVid decoder
+    (3, 5, 7, 64, 32, 3, 2, 0),          # tiny
+])
+def test_conv_matches_torch(N, H, W, Cin, Cout, k, dil, bn):
+    x, w, ref = _case(N, H, W, Cin, Cout, k, dil)
+    wp = _lib.pack_conv_weight(w.to(DEV))
+    out = _lib.conv_igemm(x, wp, Cout, dil=dil, block_n=bn)
+    got = out.float().permute(0, 3, 1, 2).cpu()
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() < 8e-3 * scale, ((got - ref).abs().max().item(), scale)
+    out32 = _lib.conv_igemm(x, wp, Cout, dil=dil, out_mode=1, block_n=bn).cpu()
+    assert (out32 - ref).abs().max().item() < 1e-3 * scale
+
+
+def test_classifier_bias_f32_nchw():
+    x, w, ref = _case(2, 64, 128, 256, 19, 1, 1, seed=3)
+    g = torch.Generator().manual_seed(9)
+    bias = torch.randn(19, generator=g)
+    wp = _lib.pack_conv_weight(w.to(DEV))
+    shift = torch.zeros(32)
+    shift[:19] = bias
+    out = _lib.conv_igemm(x, wp, 19, shift=shift.to(DEV), out_mode=1).cpu()
+    assert out.shape == (2, 19, 64, 128)
+    assert torch.allclose(out, ref + bias.view(1, -1, 1, 1), atol=2e-3, rtol=1e-3)
+
+
+def test_epilogue_bn_relu_prebias_and_concat_slice():
+    x, w, ref = _case(2, 16, 32, 320, 256, 3, 6, seed=5)
+    g = torch.Generator().manual_seed(6)
+    scale, shift = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g)
+    pre = torch.randn((2, 256), generator=g)
+    wp = _lib.pack_conv_weight(w.to(DEV))
+    buf = torch.full((2, 16, 32, 1024), 7.0, dtype=torch.bfloat16, device=DEV)
+    _lib.conv_igemm(x, wp, 256, dil=6, pre_bias=pre.to(DEV), scale=scale.to(DEV), shift=shift.to(DEV), relu=True,
+                    out=buf, c_off=512)
+    want = torch.relu((ref + pre.view(2, 256, 1, 1)) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    got = buf[..., 512:768].float().permute(0, 3, 1, 2).cpu()
+    assert (got - want).abs().max().item() < 1e-2 * want.abs().max().item()
+    assert bool((buf[..., :512] == 7).all()) and bool((buf[..., 768:] == 7).all())  # neighbours untouched
+
+
+def test_dgrad_is_conv_with_flipped_transposed_weights():
+    N, H, W, Cin, Cout, dil = 2, 16, 32, 320, 256, 6
+    g = torch.Generator().manual_seed(2)
+    w = (torch.randn((Cout, Cin, 3, 3), generator=g) / 50).to(torch.bfloat16)
+    gy = torch.randn((N, Cout, H, W), generator=g).to(torch.bfloat16)
+    x = torch.zeros((N, Cin, H, W), requires_grad=True)
+    F.conv2d(x, w.float(), padding=dil, dilation=dil).backward(gy.float())
+    wp = _lib.pack_conv_weight(w.to(DEV), transpose_for_dgrad=True)
+    gx = _lib.conv_igemm(gy.permute(0, 2, 3, 1).contiguous().to(DEV), wp, Cin, dil=dil, out_mode=1).cpu()
+    assert (gx - x.grad).abs().max().item() < 1e-3 * x.grad.abs().max().item()

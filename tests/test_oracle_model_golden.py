@@ -1,0 +1,88 @@
+"""CPU: pins oracle/deeplab_oracle.py (functional fp32 restatement) against tests/golden/model_golden.npz, which
+was produced by the UNMODIFIED reference modules (tests/golden/make_golden_model.py)."""
+import os
+import sys
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import deeplab_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ARGS = Namespace(use_mc_dropout=False, mc_dropout_p=0.2, n_classes=19)
+
+
+@pytest.fixture(scope="module")
+def mg():
+    return np.load(os.path.join(ROOT, "tests", "golden", "model_golden.npz"))
+
+
+def _shapes(backbone):
+    from pixelpick_b200.deeplab import DeepLab  # parameter names/shapes only (CPU construction, no kernels)
+    m = DeepLab(ARGS, backbone=backbone)
+    return {k: tuple(v.shape) for k, v in m.state_dict().items()}
+
+
+def _x(seed, shape):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+
+
+def test_mobilenet_deeplab_eval_matches_reference(mg):
+    sd = orc.synthetic_state_dict(_shapes("mobilenet"), seed=1)
+    with torch.no_grad():
+        out = orc.deeplab_forward(sd, _x(10, (1, 3, 48, 64)))
+    assert np.allclose(out["pred"].numpy(), mg["mnv2_eval_pred"], atol=1e-5, rtol=1e-5)
+
+
+def test_rn50_composition_eval_matches_reference(mg):
+    sd = orc.synthetic_state_dict(_shapes("resnet"), seed=2)
+    with torch.no_grad():
+        out = orc.deeplab_forward(sd, _x(12, (1, 3, 64, 96)), backbone="resnet")
+    assert np.allclose(out["pred"].numpy(), mg["rn50_eval_pred"], atol=2e-5, rtol=1e-4)
+    assert sum(v.numel() for k, v in sd.items() if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))) \
+        == int(mg["rn50_n_params"]) == 40351667
+
+
+def test_train_step_loss_grads_and_running_stats(mg):
+    shapes = _shapes("mobilenet")
+    sd = orc.synthetic_state_dict(shapes, seed=1)
+    # the reference registers features / low_level_features / high_level_features as aliases of the same tensors
+    params = {}
+    for k in sorted(sd):
+        if k.endswith(("running_mean", "running_var", "num_batches_tracked")):
+            continue
+        if k.startswith(("backbone.low_level_features.", "backbone.high_level_features.")):
+            continue
+        sd[k] = sd[k].clone().requires_grad_(True)
+        params[k] = sd[k]
+    x = _x(11, (2, 3, 64, 64))
+    rs = np.random.RandomState(11)
+    y = torch.from_numpy(rs.randint(0, 19, size=(2, 64, 64)).astype(np.int64))
+    q = torch.zeros((2, 64 * 64), dtype=torch.bool)
+    for i in range(2):
+        q[i, torch.from_numpy(rs.choice(64 * 64, 10, replace=False))] = True
+    out = orc.deeplab_forward(sd, x, training=True, return_ctx=True)
+    loss = orc.sparse_ce_loss(out["pred"], y, q.view(2, 64, 64), 19)
+    loss.backward()
+    assert np.allclose(out["pred"].detach().numpy(), mg["mnv2_train_pred"], atol=2e-5, rtol=1e-4)
+    assert abs(loss.item() - float(mg["mnv2_train_loss"])) < 1e-5
+    names, norms = list(mg["mnv2_train_grad_names"]), mg["mnv2_train_grad_norms"]
+    assert set(names) == set(params)
+    for n, ref in zip(names, norms):
+        got = params[n].grad.norm().item()
+        assert abs(got - ref) <= 1e-3 * max(ref, 1e-6) + 1e-7, (n, got, ref)
+    for key in mg.files:
+        if key.startswith("mnv2_train_grad::"):
+            n = key.split("::")[1]
+            g = params[n.split("[")[0]].grad
+            if n.endswith("[:8]"):
+                g = g[:8]
+            elif n.endswith("[:4]"):
+                g = g[:4]
+            assert np.allclose(g.numpy(), mg[key], atol=1e-6 + 1e-4 * np.abs(mg[key]).max(), rtol=1e-3), n
+    ctx = out["ctx"]
+    assert np.allclose(ctx.new_stats["aspp.bn1"][0].numpy(), mg["mnv2_train_running_mean::aspp.bn1"], atol=1e-6)
+    assert np.allclose(ctx.new_stats["seg_head.segment_head.1"][1].numpy(),
+                       mg["mnv2_train_running_var::seg_head.segment_head.1"], atol=1e-6, rtol=1e-5)

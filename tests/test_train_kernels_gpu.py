@@ -1,0 +1,118 @@
+"""GPU: wgrad (tcgen05, MN-major operands), BatchNorm/ReLU/Dropout forward+backward, NHWC upsample and layout
+kernels vs torch fp32 on CPU.  Tolerances are relative to the tensor scale: 2e-3 for f32 outputs of bf16-operand
+contractions, 1e-2 for bf16 outputs (one bf16 rounding = 2^-9)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from pixelpick_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def _nhwc(x, ld=None):
+    N, C, H, W = x.shape
+    ld = ld or C
+    out = torch.zeros((N, H, W, ld), dtype=torch.bfloat16)
+    out[..., :C] = x.permute(0, 2, 3, 1)
+    return out.to(DEV)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,dil,splits", [
+    (2, 64, 128, 304, 256, 3, 1, 0),   # SegmentHead conv #1 (ld 320)
+    (2, 64, 128, 256, 256, 3, 1, 3),   # SegmentHead conv #2
+    (2, 16, 32, 320, 256, 3, 6, 0),    # ASPP
+    (2, 16, 32, 320, 256, 3, 18, 0),   # ASPP, most taps outside
+    (2, 16, 32, 320, 256, 1, 1, 1),
+    (1, 32, 64, 1024, 256, 1, 1, 0),   # projection
+    (2, 64, 128, 24, 48, 1, 1, 0),     # low-level conv (Cin 24 -> ld 64, Cout 48 -> 64)
+    (2, 64, 128, 256, 19, 1, 1, 0),    # classifier (Cout 19 -> 64)
+    (1, 23, 30, 320, 256, 3, 12, 2),   # ragged
+])
+def test_wgrad_matches_torch(N, H, W, Cin, Cout, k, dil, splits):
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = torch.randn((N, Cin, H, W), generator=g).to(torch.bfloat16)
+    gy = torch.randn((N, Cout, H, W), generator=g).to(torch.bfloat16)
+    w = torch.zeros((Cout, Cin, k, k), requires_grad=True)
+    F.conv2d(x.float(), w, padding=dil if k == 3 else 0, dilation=dil).backward(gy.float())
+    cout_pad = 64 if Cout <= 64 else (128 if Cout <= 128 else 256)
+    ld_x = -(-Cin // 64) * 64
+    dw = _lib.conv_wgrad(_nhwc(x, ld_x), Cin, _nhwc(gy, cout_pad), cout_pad, k * k, dil, splits)
+    got = dw[:, :Cin, :Cout].permute(2, 1, 0).reshape(Cout, Cin, k, k).cpu()
+    scale = w.grad.abs().max().item()
+    assert (got - w.grad).abs().max().item() < 2e-3 * scale, ((got - w.grad).abs().max().item(), scale)
+    assert bool((dw[:, Cin:, :] == 0).all()) and bool((dw[:, :, Cout:].abs() < 1e-6 * scale).all() if Cout < cout_pad else True)
+
+
+@pytest.mark.parametrize("M,ld,c_off,C", [(8192, 256, 0, 256), (4100, 1024, 256, 256), (32768, 64, 0, 48), (1000, 1024, 0, 1024)])
+def test_bn_stats(M, ld, c_off, C):
+    g = torch.Generator().manual_seed(M)
+    raw = (torch.randn((M, ld), generator=g) * 2 + 0.5).to(torch.bfloat16)
+    sums = _lib.bn_stats(raw.to(DEV), c_off, C).cpu()
+    ref = raw[:, c_off:c_off + C].double()
+    assert torch.allclose(sums[0].double(), ref.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(sums[1].double(), (ref * ref).sum(0), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("relu,p", [(True, 0.0), (True, 0.5), (False, 0.2)])
+def test_bn_apply_and_backward_match_autograd(relu, p):
+    M, C = 4096, 256
+    g = torch.Generator().manual_seed(3)
+    raw = torch.randn((M, C), generator=g).to(torch.bfloat16)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    x = raw.float()
+    mean, var = x.mean(0), x.var(0, unbiased=False)
+    rstd = (var + 1e-5).rsqrt()
+    scale, shift = gamma * rstd, beta - mean * gamma * rstd
+    out = torch.empty((M, 320), dtype=torch.bfloat16, device=DEV)
+    _lib.bn_apply(raw.to(DEV), 0, C, scale.to(DEV), shift.to(DEV), relu, out, 64, drop_p=p, seed=11, offset=5)
+    y = out[:, 64:64 + C].float().cpu()
+    keep = (y != 0) if p > 0 else torch.ones_like(y, dtype=torch.bool)
+    if p > 0:
+        frac = 1.0 - keep.float().mean().item() if not relu else None
+        if frac is not None:
+            assert abs(frac - p) < 0.02
+    # autograd reference with the SAME dropout mask (recovered from the kernel output)
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    bn = F.batch_norm(xr, None, None, gr, br, training=True, eps=1e-5)
+    act = torch.relu(bn) if relu else bn
+    if p > 0:
+        mask = keep if not relu else ((y != 0) | (act.detach() <= 0))
+        act = act * mask / (1 - p)
+    assert (act.detach() - y).abs().max().item() < 2e-2 * act.detach().abs().max().item()
+    dy = torch.randn((M, C), generator=g).to(torch.bfloat16)
+    act.backward(dy.float())
+    draw, sums = _lib.bn_bwd(dy.to(DEV), 0, raw.to(DEV), 0, C, scale.to(DEV), shift.to(DEV), mean.to(DEV), rstd.to(DEV),
+                             relu, drop_p=p, seed=11, offset=5)
+    assert (draw.float().cpu() - xr.grad).abs().max().item() < 2e-2 * xr.grad.abs().max().item()
+    assert torch.allclose(sums[0].cpu(), br.grad, rtol=2e-2, atol=2e-2 * br.grad.abs().max().item())
+    assert torch.allclose(sums[1].cpu(), gr.grad, rtol=2e-2, atol=2e-2 * gr.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("N,h,w,H,W,C", [(2, 16, 32, 64, 128, 256), (1, 23, 30, 90, 120, 256), (2, 32, 64, 64, 128, 64)])
+def test_upsample_nhwc_fwd_bwd(N, h, w, H, W, C):
+    g = torch.Generator().manual_seed(h)
+    x = torch.randn((N, C, h, w), generator=g).to(torch.bfloat16)
+    out = torch.zeros((N, H, W, 320), dtype=torch.bfloat16, device=DEV)
+    _lib.upsample_nhwc(_nhwc(x), out, 0, C)
+    xr = x.float().requires_grad_(True)
+    ref = F.interpolate(xr, size=(H, W), mode="bilinear", align_corners=True)
+    got = out[..., :C].float().permute(0, 3, 1, 2).cpu()
+    assert (got - ref.detach()).abs().max().item() < 1e-2 * ref.abs().max().item()
+    go = torch.randn((N, C, H, W), generator=g).to(torch.bfloat16)
+    ref.backward(go.float())
+    gin = _lib.upsample_nhwc_bwd(_nhwc(go, 320), 0, C, (h, w)).permute(0, 3, 1, 2).cpu()
+    assert (gin - xr.grad).abs().max().item() < 1e-3 * xr.grad.abs().max().item()
+
+
+def test_to_nhwc_bf16_layouts():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 24, 17, 33), generator=g)
+    got = _lib.to_nhwc_bf16(x.to(DEV))  # padded to 64 channels
+    assert got.shape == (2, 17, 33, 64) and bool((got[..., 24:] == 0).all())
+    assert torch.equal(got[..., :24].cpu(), x.to(torch.bfloat16).permute(0, 2, 3, 1))
+    xc = x.to(DEV).to(memory_format=torch.channels_last).to(torch.bfloat16)
+    got2 = _lib.to_nhwc_bf16(xc)
+    assert torch.equal(got2.cpu(), got.cpu())
