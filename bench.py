@@ -3,18 +3,25 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[2], Cityscapes 256x512, C=19, margin_sampling, top-5 % -> k=6553,
-n_pixels_by_us=10; synthetic logits/masks, seeded):
-  step      = one pass of the query/acquisition hot path over one batch of B images per GPU:
-              fused softmax+margin+mask score -> per-image sorted top-k -> gather of the n picks
-  value     = Mpixels/s over all ranks, inputs resident in HBM (CUDA events, max over ranks)
-  e2e       = the same metric through the C-ABI host-buffer call (pp_acq_session_run_host): pinned host
-              logits/masks -> H2D -> kernels -> D2H of the selected indices, every step, including the
-              host-side NumPy draw of the pick positions (np.random.choice semantics)
-  roofline  = the scoring kernel alone, timed with CUDA events INSIDE the timed steps, algorithmic
-              bytes = (C*4 + 2) B/px over MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline / --impl reference = the oracle port of the reference's CPU path (torch CPU kernels +
-              NumPy RNG, all host threads) on a bounded sample of the same workload.
+BASELINE.json metric: "train images/sec + query Mpixels/sec, Cityscapes 256x512" (configs[1]/[2]).  One JSON line:
+
+  primary (metric/value/roofline/e2e/cpu_baseline) = the QUERY hot path, margin_sampling, top-5 % (k=6553), n=10:
+      step     = one pass over a batch of B images per GPU: fused softmax+margin+mask score -> per-image sorted
+                 top-k -> gather of the n picks                                   [all hand-written CUDA]
+      value    = Mpixels/s over all ranks, logits resident in HBM (CUDA events, max over ranks)
+      e2e      = the same metric through the C-ABI host-buffer call (pp_acq_session_run_host): pinned host
+                 logits/masks -> H2D -> kernels -> D2H of the picks, incl. the host NumPy draw of the pick positions
+      roofline = the scoring kernel alone, timed with CUDA events INSIDE the timed steps; algorithmic bytes
+                 (C*4 + 2) B/px over MEASURED_PEAKS.json hbm_gbs
+  "train"  = images/s of the DeepLabv3+ train step (encoder bf16 channels_last -> tcgen05 ASPP/decoder head ->
+             fused upsample+sparse-CE -> custom backward -> fused Adam), dropout on, 10 labelled px/image,
+             for MobileNetV2 (configs[1]) and ResNet-50 (configs[2]) at the reference batch (4/GPU) and a
+             throughput batch; its own e2e (pinned host batch -> H2D every step, loss read back every step) and the
+             tensor-core roofline of the SegmentHead 3x3 conv kernel (nominal FLOPs / CUDA-event time / measured bf16 peak)
+  "query_model" = Mpixels/s of QuerySelector-style querying with the model in the loop (forward_lowres + fused
+             upsample/score + top-k), images resident in HBM and from pinned host memory.
+  cpu_baseline / --impl reference = the oracle port of the reference's CPU path (torch CPU + NumPy, all host
+             threads) on a bounded sample of the same workloads.
 """
 import argparse
 import json
@@ -23,6 +30,7 @@ import subprocess
 import sys
 import threading
 import time
+from argparse import Namespace
 
 import numpy as np
 import torch
@@ -36,16 +44,19 @@ TOP_N_PERCENT, N_SEL = 0.05, 10
 K_TOP = int(H * W * TOP_N_PERCENT)
 ALG_BYTES_PER_PX = C * 4 + 2  # logits + labelled mask + void mask
 WORKLOAD = f"cityscapes 256x512 C={C} {STRATEGY} top-5% (k={K_TOP}) n={N_SEL}: logits -> score -> top-k -> picks"
+MARGS = Namespace(use_mc_dropout=False, mc_dropout_p=0.2, n_classes=C)
+OPT = {"lr": 5e-4, "weight_decay": 2e-4}  # args.py:101-106 (cs)
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), float(d["bf16_tflops"]), float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -61,8 +72,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
@@ -78,19 +88,20 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
                 for nme, v in zip(names, r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def synth(n_img, seed, device=None, pin=False):
@@ -112,8 +123,25 @@ def synth(n_img, seed, device=None, pin=False):
     return logits, lab_t, void_t
 
 
-def cpu_reference_rate(n_img, reps, threads):
-    """Oracle port of the reference CPU path (query.py:159-212 loop body over pre-computed logits)."""
+def synth_train_batch(B, seed, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((B, 3, H, W), generator=g)
+    rs = np.random.RandomState(seed)
+    y = torch.from_numpy(rs.randint(0, C, size=(B, H, W)).astype(np.int64))
+    y[torch.from_numpy(rs.rand(B, H, W) < 0.01)] = C
+    q = np.zeros((B, H * W), dtype=np.uint8)
+    for i in range(B):
+        q[i, rs.choice(H * W, 10, replace=False)] = 1
+    q = torch.from_numpy(q).view(B, H, W)
+    if pin:
+        x, y, q = x.pin_memory(), y.pin_memory(), q.pin_memory()
+    return x, y, q
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: oracle ports of the reference CPU path
+# ----------------------------------------------------------------------------------------------
+def cpu_query_rate(n_img, reps, threads):
     from oracle import acq_oracle as orc  # checker / baseline only
     torch.set_num_threads(threads)
     logits, lab, void = synth(n_img, 1234)
@@ -128,6 +156,34 @@ def cpu_reference_rate(n_img, reps, threads):
         orc.query_images(imgs, STRATEGY, lab_np, void_np, names, N_SEL, TOP_N_PERCENT)
         times.append(time.perf_counter() - t0)
     return n_img * H * W / 1e6 / min(times), times
+
+
+def cpu_train_rate(backbone, B, steps, threads):
+    """oracle train step (fp32, torch CPU, Adam) — model.py:103-122 restated; returns images/s."""
+    from oracle import deeplab_oracle as dorc
+    from pixelpick_b200.deeplab import DeepLab  # parameter names / shapes only
+    torch.set_num_threads(threads)
+    shapes = {k: tuple(v.shape) for k, v in DeepLab(MARGS, backbone=backbone).state_dict().items()}
+    sd = dorc.synthetic_state_dict(shapes, seed=1)
+    params = []
+    for k in sorted(sd):
+        if sd[k].dtype.is_floating_point and not k.endswith(("running_mean", "running_var")) and \
+                not k.startswith(("backbone.low_level_features.", "backbone.high_level_features.")):
+            sd[k] = sd[k].clone().requires_grad_(True)
+            params.append(sd[k])
+    opt = torch.optim.Adam(params, lr=OPT["lr"], weight_decay=OPT["weight_decay"])
+    x, y, q = synth_train_batch(B, 7)
+    times = []
+    for i in range(steps + 1):
+        t0 = time.perf_counter()
+        out = dorc.deeplab_forward(sd, x, backbone=backbone, training=True, drop=(0.5, 0.5, 0.2))
+        loss = dorc.sparse_ce_loss(out["pred"], y, q, C)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        if i > 0:
+            times.append(time.perf_counter() - t0)
+    return B / float(np.mean(times)), times
 
 
 def run_reference(args, rank, world):
@@ -151,7 +207,7 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     val = K_ * n_img * H * W / 1e6 / dt
     sample = f"{n_img} images of 256x512x19 fp32 per step (logits pre-computed), torch CPU + NumPy, {threads} threads"
-    print(json.dumps({
+    out = {
         "impl": "reference", "metric": "query_mpixels_per_sec", "value": val, "unit": "Mpixels/s", "n_gpus": world,
         "steps": K_, "warmup": W_, "ms_per_step": dt / K_ * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -159,7 +215,147 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }
+    if not args.no_train:
+        r_mn, t_mn = cpu_train_rate("mobilenet", 4, 2, threads)
+        out["train"] = {"metric": "train_images_per_sec", "unit": "images/s", "dtype": "f32",
+                        "mobilenetv2_b4": {"value": r_mn, "ms_per_step": float(np.mean(t_mn)) * 1e3, "steps": len(t_mn)},
+                        "sample": "oracle port of model.py:103-122 (fp32, torch CPU, Adam, dropout on), B=4, 2 timed steps"}
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def bench_train(backbone, B, steps, warmup, dev, world, e2e=False):
+    """images/s of the full train step; returns dict(value, ms_per_step, ...)."""
+    import torch.distributed as dist
+    from pixelpick_b200 import _lib, dist as ppdist
+    from pixelpick_b200.deeplab import DeepLab
+    from pixelpick_b200.loss import sparse_cross_entropy
+    torch.manual_seed(0)
+    model = DeepLab(MARGS, backbone=backbone).to(dev)
+    model.train()
+    ppdist.broadcast_parameters(model)
+    groups = [{"params": model.backbone.parameters(), "lr": OPT["lr"] / 10, "weight_decay": OPT["weight_decay"]}]
+    for part in (model.aspp, model.low_level_conv, model.seg_head):
+        groups.append({"params": part.parameters(), "lr": OPT["lr"], "weight_decay": OPT["weight_decay"]})
+    opt = torch.optim.Adam(groups, fused=True)
+    reducer = ppdist.GradAllReducer(model) if world > 1 else None
+    hx, hy, hq = synth_train_batch(B, 11 + ppdist.rank(), pin=True)
+    dx, dy, dq = hx.to(dev), hy.to(dev), hq.to(dev)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(from_host):
+        if from_host:
+            x, y, q = hx.to(dev, non_blocking=True), hy.to(dev, non_blocking=True), hq.to(dev, non_blocking=True)
+        else:
+            x, y, q = dx, dy, dq
+        lowres = model.forward_lowres(x)
+        loss = sparse_cross_entropy(lowres, y, q.bool(), C)
+        opt.zero_grad(set_to_none=True)
+        if world > 1:
+            n_local = torch.tensor(float(B * 10), device=dev)
+            (loss * ppdist.global_mean_loss_scale(n_local)).backward()
+            reducer()
+        else:
+            loss.backward()
+        opt.step()
+        if from_host:
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=False)  # D2H read of the step's result
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step(e2e)
+    barrier()
+    l0 = _lib.lib().pp_launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(steps):
+        last = step(e2e)
+    b.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = a.elapsed_time(b) if not e2e else wall * 1e3
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"value": world * B * steps / (ms / 1e3), "ms_per_step": ms / steps, "batch_per_gpu": B, "steps": steps,
+            "our_kernel_launches_per_step": (_lib.lib().pp_launch_count() - l0) / steps, "final_loss": float(last.item()),
+            "h2d_bytes_per_step": B * (3 * H * W * 4 + H * W * 8 + H * W) if e2e else 0, "d2h_bytes_per_step": 4 if e2e else 0}
+
+
+def bench_conv_roofline(dev, peak_tf):
+    """SegmentHead conv #1 (3x3, 304(320)->256) at B=32, 64x128: nominal FLOPs / CUDA-event time."""
+    from pixelpick_b200 import _lib
+    B = 32
+    x = torch.randn((B, 64, 128, 320), device=dev).to(torch.bfloat16)
+    w = _lib.pack_conv_weight(torch.randn((256, 304, 3, 3), device=dev) * 0.02, 320, 256)
+    sc, sf = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+    out = torch.empty((B, 64, 128, 256), dtype=torch.bfloat16, device=dev)
+    for _ in range(3):
+        _lib.conv_igemm(x, w, 256, scale=sc, shift=sf, relu=True, out=out)
+    torch.cuda.synchronize()
+    n = 20
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        _lib.conv_igemm(x, w, 256, scale=sc, shift=sf, relu=True, out=out)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / n
+    flops = 2.0 * B * 64 * 128 * 256 * 9 * 304
+    ach = flops / (ms / 1e3) / 1e12
+    return {"kernel": "conv_igemm_kernel<256> (SegmentHead 3x3 304->256, B=32, 64x128, BN+ReLU epilogue)", "bound": "tensor",
+            "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "kernel_ms": ms,
+            "nominal_flops_per_launch": flops, "traffic": None}
+
+
+def bench_query_model(backbone, n_img, steps, dev, from_host):
+    """QuerySelector-style querying with the model in the loop (eval forward_lowres + fused upsample/score + top-k)."""
+    from pixelpick_b200 import _lib
+    from pixelpick_b200.deeplab import DeepLab
+    torch.manual_seed(0)
+    model = DeepLab(MARGS, backbone=backbone).to(dev).eval()
+    hx, hy, hq = synth_train_batch(n_img, 21, pin=True)
+    hvoid = (hy == C).pin_memory()
+    dx, dq, dvoid = hx.to(dev), hq.to(dev), hvoid.to(dev)
+    ws = _lib.TopKWorkspace(n_img, H * W, K_TOP, dev)
+    pos = torch.from_numpy(np.stack([np.random.permutation(K_TOP)[:N_SEL] for _ in range(n_img)]).astype(np.int32)).to(dev)
+    out_host = torch.empty((n_img, N_SEL), dtype=torch.int32).pin_memory()
+
+    def step():
+        with torch.no_grad():
+            if from_host:
+                x, q, v = hx.to(dev, non_blocking=True), hq.to(dev, non_blocking=True), hvoid.to(dev, non_blocking=True)
+            else:
+                x, q, v = dx, dq, dvoid
+            lr = model.forward_lowres(x)
+            ws.prepare()
+            score = _lib.acq_score_upsampled(lr, (H, W), STRATEGY, q, v, hist0_ws=ws)
+            topk = _lib.acq_topk(score.view(n_img, -1), K_TOP, False, ws=ws, hist0_valid=True)
+            sel = _lib.acq_gather(topk, pos)
+            if from_host:
+                out_host.copy_(sel)
+        return sel
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": n_img * H * W * steps / 1e6 / dt, "images_per_s": n_img * steps / dt, "ms_per_step": dt / steps * 1e3,
+            "images_per_step": n_img}
 
 
 def main():
@@ -168,9 +364,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per step per GPU (device-resident leg)")
-    ap.add_argument("--e2e-batch", type=int, default=64, help="images per step per GPU (host-buffer leg)")
+    ap.add_argument("--batch", type=int, default=256, help="images per step per GPU (device-resident query leg)")
+    ap.add_argument("--e2e-batch", type=int, default=64, help="images per step per GPU (host-buffer query leg)")
+    ap.add_argument("--train-batch", type=int, default=32, help="throughput batch of the train leg (per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -190,6 +388,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
+    hbm_peak, tf_burst, tf_sust, peak_src = peaks()
 
     B, K, Wm = args.batch, args.steps, args.warmup
     HW = H * W
@@ -200,7 +399,6 @@ def main():
     np.random.seed(rank)
     pos = torch.from_numpy(np.stack([np.random.permutation(K_TOP)[:N_SEL] for _ in range(B)]).astype(np.int32)).to(dev)
     gathered = [torch.empty((B, N_SEL), dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
-
     ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
 
@@ -263,16 +461,40 @@ def main():
     e2e_s = time.perf_counter() - t0
     launches_e2e = lib.pp_launch_count() - le0
     barrier()
-    clk = clocks.stop() if rank == 0 else None
     sess.close()
+    del logits, score, ws, h_logits
+    torch.cuda.empty_cache()
 
     t = torch.tensor([ms_total, score_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, score_ms, e2e_s = [float(v) for v in t.cpu()]
 
+    # ---- train leg + model-in-the-loop query -------------------------------------------------------
+    train = None
+    qmodel = None
+    if not args.no_train:
+        train = {"metric": "train_images_per_sec", "unit": "images/s", "dtype": "bf16 (fp32 accumulate, fp32 master weights)",
+                 "config": "cityscapes 256x512, 10 labelled px/image, Adam lr 5e-4 (encoder lr/10) wd 2e-4, dropout on; "
+                           "synthetic batch resident in HBM (value) / pinned host -> H2D every step + loss D2H (e2e)"}
+        ts = max(5, min(K, 20))
+        for name, bb in (("mobilenetv2", "mobilenet"), ("resnet50", "resnet")):
+            train[f"{name}_b4"] = bench_train(bb, 4, ts, 5, dev, world)
+            train[f"{name}_b{args.train_batch}"] = bench_train(bb, args.train_batch, ts, 3, dev, world)
+            train[f"{name}_b{args.train_batch}_e2e"] = bench_train(bb, args.train_batch, ts, 3, dev, world, e2e=True)
+            torch.cuda.empty_cache()
+        if rank == 0:
+            train["roofline_tensor"] = bench_conv_roofline(dev, tf_burst)
+            train["roofline_tensor"]["peak_source"] = peak_src + " bf16_tflops (burst; kernel timed alone)"
+            qmodel = {"unit": "Mpixels/s",
+                      "mobilenetv2_hbm": bench_query_model("mobilenet", 64, 5, dev, False),
+                      "mobilenetv2_host": bench_query_model("mobilenet", 64, 5, dev, True),
+                      "resnet50_hbm": bench_query_model("resnet", 32, 5, dev, False),
+                      "resnet50_host": bench_query_model("resnet", 32, 5, dev, True)}
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+
     if rank == 0:
-        peak, peak_src = peaks()
         value = world * B * HW * K / 1e6 / (ms_total / 1e3)
         achieved = B * HW * ALG_BYTES_PER_PX / (score_ms / 1e3) / 1e9
         e2e_val = world * Be * HW * Ke / 1e6 / e2e_s
@@ -286,7 +508,7 @@ def main():
                        "l2": f"inputs larger than L2 ({B * C * HW * 4 / 1e6:.0f} MB of logits per step)",
                        "parallelism": f"images sharded over {world} rank(s); all_gather of picks" if world > 1 else "single GPU"},
             "roofline": {"kernel": "acq_score_vec_kernel<19, margin, f32, fused hist0>", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "peak_source": peak_src, "kernel_ms": score_ms,
                          "alg_bytes_per_launch": B * HW * ALG_BYTES_PER_PX,
                          "share_of_step": score_ms / (ms_total / K)},
@@ -296,17 +518,28 @@ def main():
             "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
             "clocks": clk,
         }
+        if train is not None:
+            out["train"] = train
+            out["query_model"] = qmodel
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n_cpu = 32
-            rate, times = cpu_reference_rate(n_cpu, 3, threads)
+            rate, times = cpu_query_rate(n_cpu, 3, threads)
             out["cpu_baseline"] = {"value": rate, "unit": "Mpixels/s", "cores": threads, "kind": "port",
                                    "sample": f"{n_cpu} images of the same workload x 3 repetitions (best), "
                                              f"oracle port of query.py:159-212 on torch CPU + NumPy, {sum(times):.1f} s"}
+            if train is not None:
+                r_mn, t_mn = cpu_train_rate("mobilenet", 4, 2, threads)
+                out["train"]["cpu_baseline"] = {"value": r_mn, "unit": "images/s", "cores": threads, "kind": "port",
+                                                "sample": f"MobileNetV2-DeepLab B=4, 2 timed steps of the oracle train "
+                                                          f"step (fp32 torch CPU, Adam), {sum(t_mn):.1f} s"}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                out["roofline"]["traffic"] = json.load(open(tpath)).get("acq_score_bytes_per_px") * B * HW
+                tj = json.load(open(tpath))
+                out["roofline"]["traffic"] = tj.get("acq_score_bytes_per_px") * B * HW
+                if train is not None and tj.get("conv_d1_b32_bytes"):
+                    out["train"]["roofline_tensor"]["traffic"] = tj.get("conv_d1_b32_bytes")
             except Exception:
                 pass
         print(json.dumps(out))

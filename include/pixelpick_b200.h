@@ -203,6 +203,10 @@ int pp_upsample_nhwc_bf16(const void* in, int N, int h, int w, int C, int ld_in,
                           int c_off, void* stream);
 int pp_upsample_nhwc_bf16_bwd(const void* grad_out, int N, int H, int W, int ld, int c_off, int C, float* grad_in,
                               int h, int w, void* stream);
+/* f32 conv weight [Cout][Cin_total][kh][kw] (first Cin input channels) -> bf16 operand tensors of pp_conv_igemm:
+ * fwd [taps][Cout_pad][Cin_pad] and/or dgrad [taps][Cin_rows][Cout_cols] (taps flipped); zero padded; either NULL. */
+int pp_pack_conv_weight(const float* w, int Cout, int Cin, int Cin_total, int taps, void* fwd, int Cout_pad,
+                        int Cin_pad, void* dgrad, int Cin_rows, int Cout_cols, void* stream);
 /* strided [N,C,H,W] f32/bf16 -> bf16 NHWC channel slice (backbone boundary, d(logits) for the classifier) */
 int pp_to_nhwc_bf16(const void* in, int dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw, int N, int C, int H,
                     int W, void* out, int ld, int c_off, void* stream);

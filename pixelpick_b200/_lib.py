@@ -55,6 +55,7 @@ _SIGNATURES = {
                    _vp, _vp], _i),
     "pp_upsample_nhwc_bf16": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp], _i),
     "pp_upsample_nhwc_bf16_bwd": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
+    "pp_pack_conv_weight": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_to_nhwc_bf16": ([_vp, _i, _i64, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_conv_igemm": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp], _i),
 }
@@ -275,6 +276,24 @@ def pack_conv_weight(w, cin_pad=None, cout_pad=None, transpose_for_dgrad=False):
     out = torch.zeros((kh * kw, cout_pad, cin_pad), dtype=torch.bfloat16, device=w.device)
     out[:, :co, :ci] = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci).to(torch.bfloat16)
     return out
+
+
+def pack_conv_weights(w, cin=None, fwd_pad=None, dgrad_pad=None):
+    """One launch: f32 conv weight [Cout, Cin_total, kh, kw] (first `cin` input channels) -> bf16 operand tensors.
+    fwd_pad = (Cout_pad, Cin_pad) -> [taps, Cout_pad, Cin_pad]; dgrad_pad = (Cin_rows, Cout_cols) -> flipped/transposed."""
+    _need_cuda(w)
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    co, ci_tot, kh, kw = w.shape
+    cin = ci_tot if cin is None else cin
+    taps = kh * kw
+    fwd = torch.empty((taps,) + tuple(fwd_pad), dtype=torch.bfloat16, device=w.device) if fwd_pad else None
+    dgr = torch.empty((taps,) + tuple(dgrad_pad), dtype=torch.bfloat16, device=w.device) if dgrad_pad else None
+    check(lib().pp_pack_conv_weight(_ptr(w), co, cin, ci_tot, taps, _ptr(fwd), fwd_pad[0] if fwd_pad else 0,
+                                    fwd_pad[1] if fwd_pad else 0, _ptr(dgr), dgrad_pad[0] if dgrad_pad else 0,
+                                    dgrad_pad[1] if dgrad_pad else 0, _stream(w)), "pp_pack_conv_weight")
+    return fwd, dgr
 
 
 def conv_igemm(x_nhwc, w_packed, cout, dil=1, pre_bias=None, scale=None, shift=None, relu=False, out=None,

@@ -527,15 +527,32 @@ __global__ void __launch_bounds__(kSelThreads) select_level_kernel(const SelPara
     uint64_t comp[kSelItems];
     uint32_t cls = 0;  // 2 bits per item: 1 = selected, 2 = boundary bucket
     uint32_t nc = 0, nf = 0;
+    // all loads of the tile are issued before the first use (predicated, no branch): one memory round trip per
+    // tile instead of kSelItems serialised ones
+    if (L0) {
+      float sv[kSelItems];
+#pragma unroll
+      for (int i = 0; i < kSelItems; ++i) {
+        const uint32_t idx = tile * kSelTile + i * kSelThreads + tid;
+        sv[i] = (idx < n_in) ? __ldg(sc + (idx < n_in ? idx : 0u)) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kSelItems; ++i) {
+        const uint32_t idx = tile * kSelTile + i * kSelThreads + tid;
+        comp[i] = ((uint64_t)ord_key(sv[i], largest) << 32) | idx;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kSelItems; ++i) {
+        const uint32_t idx = tile * kSelTile + i * kSelThreads + tid;
+        comp[i] = (idx < n_in) ? il[idx < n_in ? idx : 0u] : ~0ull;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < kSelItems; ++i) {
       const uint32_t idx = tile * kSelTile + i * kSelThreads + tid;
       if (idx < n_in) {
-        uint64_t cv;
-        if (L0) cv = ((uint64_t)ord_key(__ldg(sc + idx), largest) << 32) | idx;
-        else cv = il[idx];
-        comp[i] = cv;
-        const uint32_t d = (uint32_t)(cv >> shift) & dmask;
+        const uint32_t d = (uint32_t)(comp[i] >> shift) & dmask;
         if (d < bucket || (d == bucket && take_all)) {
           cls |= 1u << (2 * i);
           ++nc;
@@ -659,6 +676,116 @@ __global__ void __launch_bounds__(kSortThreads) bitonic_local_kernel(const SortP
     }
   } else {
     for (int i = threadIdx.x; i < p.chunk; i += kSortThreads) g[i] = sh[i];
+  }
+}
+
+// Register-blocked bitonic network for 8192-element chunks (1024 threads x 8 elements).  Element bit b of a
+// compare-exchange decides where it runs: bits 0-2 inside the thread's registers, bits 3-7 across lanes with warp
+// shuffles, bits 8-12 through shared memory in groups of up to three bits per round trip (12 shared-memory passes
+// for a full sort instead of 91).  Shared-memory position of element e is e ^ (((e >> 4) & 3) << 1), which makes
+// both the per-thread 64-byte reads and the strided round accesses bank-conflict free.
+constexpr int kB8 = 8192;
+__device__ __forceinline__ int sw8(int e) { return e ^ (((e >> 4) & 3) << 1); }
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int mask) {
+  const uint32_t lo = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)v, mask);
+  const uint32_t hi = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)(v >> 32), mask);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(1024) bitonic8k_kernel(const SortParams p) {
+  extern __shared__ uint64_t sh[];
+  const int img = blockIdx.y;
+  const int t = threadIdx.x, lane = t & 31;
+  const int cbase = blockIdx.x * kB8;
+  uint64_t* g = p.cand + (size_t)img * p.kpad + cbase;
+  uint64_t a[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    uint64_t v = g[8 * t + r];
+    if (p.pad_on_load && cbase + 8 * t + r >= p.k) v = ~0ull;
+    a[r] = v;
+  }
+  auto smem_phase = [&](int hi, int size) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sh[sw8(8 * t + r)] = a[r];
+    __syncthreads();
+    int b = hi;
+    while (b >= 8) {
+      const int gb = (b - 7) < 3 ? (b - 7) : 3;
+      const int b0 = b - gb + 1;
+      const int n = 1 << gb;
+      for (int k = 0; k < (8 >> gb); ++k) {
+        const int v = t + 1024 * k;
+        const int base = (v & ((1 << b0) - 1)) | ((v >> b0) << (b0 + gb));
+        const bool asc = ((cbase + base) & size) == 0;
+        uint64_t x[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < n) x[c] = sh[sw8(base | (c << b0))];
+#pragma unroll
+        for (int j = 2; j >= 0; --j) {
+          if (j < gb) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c < n && !(c & (1 << j))) cmpx(x[c], x[c | (1 << j)], asc);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < n) sh[sw8(base | (c << b0))] = x[c];
+      }
+      __syncthreads();
+      b -= gb;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a[r] = sh[sw8(8 * t + r)];
+    __syncthreads();
+  };
+  auto merge = [&](int s, int size) {
+    int hi = s - 1;
+    if (hi >= 8) {
+      smem_phase(hi > 12 ? 12 : hi, size);
+      hi = 7;
+    }
+    for (int b = hi; b >= 3; --b) {
+      const int mask = 1 << (b - 3);
+      const bool lower = (lane & mask) == 0;
+      const bool asc = ((cbase + 8 * t) & size) == 0;
+      const bool keep_min = lower == asc;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const uint64_t o = shfl_xor_u64(a[r], mask);
+        a[r] = keep_min ? (a[r] < o ? a[r] : o) : (a[r] > o ? a[r] : o);
+      }
+    }
+    const int top = hi < 2 ? hi : 2;
+#pragma unroll
+    for (int b = 2; b >= 0; --b) {
+      if (b <= top) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (!(r & (1 << b))) cmpx(a[r], a[r | (1 << b)], ((cbase + 8 * t + r) & size) == 0);
+      }
+    }
+  };
+  if (FULL) {
+    for (int s = 1; s <= 13; ++s) merge(s, 1 << s);
+  } else {
+    merge(13, p.size_lo);
+  }
+  if (p.write_out) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int j = cbase + 8 * t + r;
+      if (j < p.k) {
+        p.out_idx[(size_t)img * p.k + j] = (int32_t)(uint32_t)(a[r] & 0xFFFFFFFFull);
+        if (p.out_val) p.out_val[(size_t)img * p.k + j] = ord_key_inv((uint32_t)(a[r] >> 32), p.largest != 0);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) g[8 * t + r] = a[r];
   }
 }
 
@@ -859,35 +986,46 @@ static int topk_impl(const float* score_map, int n_img, int HW, int k, int large
   sp.largest = largest;
   sp.out_idx = topk_idx;
   sp.out_val = topk_val;
-  const int chunk = w.kpad < kSortChunkMax ? w.kpad : 8192;
+  if (w.kpad >= kB8) {
+    static bool attr8 = false;
+    if (!attr8) {
+      PP_CUDA(cudaFuncSetAttribute(bitonic8k_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB8 * (int)sizeof(uint64_t)));
+      PP_CUDA(cudaFuncSetAttribute(bitonic8k_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kB8 * (int)sizeof(uint64_t)));
+      attr8 = true;
+    }
+    const size_t smem8 = (size_t)kB8 * sizeof(uint64_t);
+    sp.chunk = kB8;
+    sp.size_lo = 2;
+    sp.size_hi = kB8;
+    sp.pad_on_load = 1;
+    sp.write_out = (w.kpad == kB8) ? 1 : 0;
+    bitonic8k_kernel<true><<<dim3(w.kpad / kB8, n_img), 1024, smem8, st>>>(sp);
+    PP_LAUNCH_CHECK();
+    for (int size = kB8 << 1; size <= w.kpad; size <<= 1) {
+      for (int stride = size >> 1; stride >= kB8; stride >>= 1) {
+        int gx = (w.kpad / 2 + 255) / 256;
+        if (gx > 1024) gx = 1024;
+        bitonic_global_step_kernel<<<dim3(gx, n_img), 256, 0, st>>>(w.cand, w.kpad, size, stride);
+        PP_LAUNCH_CHECK();
+      }
+      sp.size_lo = size;
+      sp.size_hi = size;
+      sp.pad_on_load = 0;
+      sp.write_out = (size == w.kpad) ? 1 : 0;
+      bitonic8k_kernel<false><<<dim3(w.kpad / kB8, n_img), 1024, smem8, st>>>(sp);
+      PP_LAUNCH_CHECK();
+    }
+    return PP_OK;
+  }
+  const int chunk = w.kpad;  // < 8192: one shared-memory chunk
   sp.chunk = chunk;
   const size_t smem = (size_t)chunk * sizeof(uint64_t);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PP_CUDA(cudaFuncSetAttribute(bitonic_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kSortChunkMax * (int)sizeof(uint64_t)));
-    attr_set = true;
-  }
   sp.size_lo = 2;
   sp.size_hi = chunk;
   sp.pad_on_load = 1;
-  sp.write_out = (chunk == w.kpad) ? 1 : 0;
-  bitonic_local_kernel<<<dim3(w.kpad / chunk, n_img), kSortThreads, smem, st>>>(sp);
+  sp.write_out = 1;
+  bitonic_local_kernel<<<dim3(1, n_img), kSortThreads, smem, st>>>(sp);
   PP_LAUNCH_CHECK();
-  for (int size = chunk << 1; size <= w.kpad; size <<= 1) {
-    for (int stride = size >> 1; stride >= chunk; stride >>= 1) {
-      int gx = (w.kpad / 2 + 255) / 256;
-      if (gx > 1024) gx = 1024;
-      bitonic_global_step_kernel<<<dim3(gx, n_img), 256, 0, st>>>(w.cand, w.kpad, size, stride);
-      PP_LAUNCH_CHECK();
-    }
-    sp.size_lo = size;
-    sp.size_hi = size;
-    sp.pad_on_load = 0;
-    sp.write_out = (size == w.kpad) ? 1 : 0;
-    bitonic_local_kernel<<<dim3(w.kpad / chunk, n_img), kSortThreads, smem, st>>>(sp);
-    PP_LAUNCH_CHECK();
-  }
   return PP_OK;
 }
 

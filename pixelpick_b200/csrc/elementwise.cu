@@ -472,3 +472,47 @@ extern "C" int pp_bn_finalize(const float* sums, int C, int64_t M, float eps, fl
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
+
+// ---- conv weight packing: f32 [Cout][Cin_total][kh][kw] -> bf16 K-major operand tensors ------------
+// fwd   [taps][Cout_pad][Cin_pad]          (tap = ky*kw + kx)
+// dgrad [taps][Cin_rows][Cout_cols]        (tap flipped: the data-gradient conv), either may be NULL
+namespace pp {
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int Cin_total,
+                                                          int taps, __nv_bfloat16* __restrict__ fwd, int Cout_pad,
+                                                          int Cin_pad, __nv_bfloat16* __restrict__ dgr, int Cin_rows,
+                                                          int Cout_cols) {
+  const int64_t n_f = fwd ? (int64_t)taps * Cout_pad * Cin_pad : 0;
+  const int64_t n_d = dgr ? (int64_t)taps * Cin_rows * Cout_cols : 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_f + n_d; i += (int64_t)gridDim.x * 256) {
+    if (i < n_f) {
+      const int ci = (int)(i % Cin_pad);
+      const int64_t t = i / Cin_pad;
+      const int co = (int)(t % Cout_pad), tap = (int)(t / Cout_pad);
+      float v = 0.f;
+      if (ci < Cin && co < Cout) v = w[((int64_t)co * Cin_total + ci) * taps + tap];
+      fwd[i] = __float2bfloat16(v);
+    } else {
+      const int64_t j = i - n_f;
+      const int co = (int)(j % Cout_cols);
+      const int64_t t = j / Cout_cols;
+      const int ci = (int)(t % Cin_rows), tap = (int)(t / Cin_rows);
+      float v = 0.f;
+      if (ci < Cin && co < Cout) v = w[((int64_t)co * Cin_total + ci) * taps + (taps - 1 - tap)];
+      dgr[j] = __float2bfloat16(v);
+    }
+  }
+}
+}  // namespace pp
+
+extern "C" int pp_pack_conv_weight(const float* w, int Cout, int Cin, int Cin_total, int taps, void* fwd, int Cout_pad,
+                                   int Cin_pad, void* dgrad, int Cin_rows, int Cout_cols, void* stream) {
+  PP_CHECK_ARG(w && (fwd || dgrad) && Cout > 0 && Cin > 0 && Cin <= Cin_total && taps > 0, "pp_pack_conv_weight: bad args");
+  PP_CHECK_ARG(!fwd || (Cout_pad >= Cout && Cin_pad >= Cin), "pp_pack_conv_weight: fwd padding smaller than the tensor");
+  PP_CHECK_ARG(!dgrad || (Cin_rows >= Cin && Cout_cols >= Cout), "pp_pack_conv_weight: dgrad padding smaller than the tensor");
+  const int64_t total = (fwd ? (int64_t)taps * Cout_pad * Cin_pad : 0) + (dgrad ? (int64_t)taps * Cin_rows * Cout_cols : 0);
+  pp::pack_weight_kernel<<<pp::ew_grid(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w, Cout, Cin, Cin_total, taps, reinterpret_cast<__nv_bfloat16*>(fwd), Cout_pad, Cin_pad,
+      reinterpret_cast<__nv_bfloat16*>(dgrad), Cin_rows, Cout_cols);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}

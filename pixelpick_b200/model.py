@@ -1,0 +1,170 @@
+"""Mirror of the reference `model.py:Model` (active-learning round loop, model.py:14-239) on the B200 hot paths.
+
+Same constructor/`__call__` contract, files written (log_train.txt, log_val.txt, best_miou_model.pt,
+{n}_query/queries.pkl, query_stats.pkl) and round structure: every round re-initialises the model (model.py:163),
+trains n_epochs, then queries with the LAST-epoch model (model.py:80-83).  The train step is
+  forward_lowres (tcgen05 head) -> fused upsample + sparse CE kernel -> custom backward -> optimiser
+and the running metrics are computed from the labelled pixels only (identical confusion matrix, see
+utils.RunningScore.update_pairs) instead of copying two full int64 maps to the host every step (model.py:125).
+Not mirrored: the PNG visualiser (model.py:150-158, host-side matplotlib-style drawing, out of scope)."""
+import os
+from copy import deepcopy
+from math import ceil
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import dist as ppdist
+from .loss import sparse_cross_entropy
+from .query import QuerySelector
+from .utils import AverageMeter, RunningScore, get_dataloader, get_lr_scheduler, get_model, get_optimizer, write_log
+
+
+class Model:
+    def __init__(self, args, dataloaders=None):
+        self.args = args
+        self.best_miou = -1.0
+        self.dataset_name = args.dataset_name
+        self.debug = args.debug
+        if not torch.cuda.is_available():
+            raise RuntimeError("pixelpick_b200.Model needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dir_checkpoints = f"{args.dir_root}/checkpoints/{args.experim_name}"
+        self.experim_name = args.experim_name
+        self.ignore_index = args.ignore_index
+        self.init_n_pixels = args.n_init_pixels
+        self.max_budget = args.max_budget
+        self.n_classes = args.n_classes
+        self.n_epochs = args.n_epochs
+        self.n_pixels_by_us = args.n_pixels_by_us
+        self.network_name = args.network_name
+        self.nth_query = -1
+        self.stride_total = args.stride_total
+        if dataloaders is None:
+            self.dataloader = get_dataloader(deepcopy(args), val=False, query=False, shuffle=True,
+                                             batch_size=args.batch_size, n_workers=args.n_workers)
+            self.dataloader_query = get_dataloader(deepcopy(args), val=False, query=True, shuffle=False, batch_size=1,
+                                                   n_workers=args.n_workers)
+            self.dataloader_val = get_dataloader(deepcopy(args), val=True, query=False, shuffle=False, batch_size=1,
+                                                 n_workers=args.n_workers)
+        else:
+            self.dataloader, self.dataloader_query, self.dataloader_val = dataloaders
+        self.lr_scheduler_type = args.lr_scheduler_type
+        self.query_selector = QuerySelector(args, self.dataloader_query, device=self.device)
+        self.running_loss, self.running_score = AverageMeter(), RunningScore(args.n_classes)
+
+    def __call__(self):
+        if self.n_pixels_by_us == 0:  # fully-supervised model (model.py:55-64)
+            d = f"{self.dir_checkpoints}/fully_sup"
+            os.makedirs(d, exist_ok=True)
+            self.log_train, self.log_val = f"{d}/log_train.txt", f"{d}/log_val.txt"
+            write_log(self.log_train, header=["epoch", "mIoU", "pixel_acc", "loss"])
+            write_log(self.log_val, header=["epoch", "mIoU", "pixel_acc"])
+            self._train()
+            return
+        n_stages = self.max_budget // self.n_pixels_by_us
+        n_stages += 1 if self.init_n_pixels > 0 else 0
+        print("n_stages:", n_stages)
+        for nth_query in range(n_stages):
+            d = f"{self.dir_checkpoints}/{nth_query}_query"
+            os.makedirs(d, exist_ok=True)
+            self.log_train, self.log_val = f"{d}/log_train.txt", f"{d}/log_val.txt"
+            write_log(self.log_train, header=["epoch", "mIoU", "pixel_acc", "loss"])
+            write_log(self.log_val, header=["epoch", "mIoU", "pixel_acc"])
+            self.nth_query = nth_query
+            model = self._train()
+            queries = self.query_selector(nth_query, model)
+            self.dataloader.dataset.label_queries(queries, nth_query + 1)
+            if nth_query == n_stages - 1:
+                break
+
+    def train_step(self, model, optimizer, dict_data, reducer=None):
+        """model.py:103-129 for one batch; returns (loss tensor, labels, predictions at the labelled pixels)."""
+        x = dict_data["x"].to(self.device, non_blocking=True)
+        y = dict_data["y"].to(self.device, non_blocking=True)
+        mask = dict_data["queries"].to(self.device, torch.bool) if self.n_pixels_by_us != 0 else None
+        lowres = model.forward_lowres(x)
+        loss, pred_at, (_, _, px_label) = sparse_cross_entropy(lowres, y, mask, self.ignore_index, return_pred=True)
+        optimizer.zero_grad(set_to_none=True)
+        if ppdist.world() > 1:
+            n_local = torch.tensor(float(px_label.numel()), device=self.device)
+            (loss * ppdist.global_mean_loss_scale(n_local)).backward()
+            reducer()
+        else:
+            loss.backward()
+        optimizer.step()
+        return loss.detach(), px_label, pred_at
+
+    def _train_epoch(self, epoch, model, optimizer, lr_scheduler, reducer=None):
+        if self.n_pixels_by_us != 0:
+            print(f"training an epoch {epoch} of {self.nth_query}th query "
+                  f"({self.dataloader.dataset.n_pixels_total} labelled pixels)")
+        model.train()
+        miou = pixel_acc = float("nan")
+        for dict_data in self.dataloader:
+            loss, labels, preds = self.train_step(model, optimizer, dict_data, reducer)
+            self.running_score.update_pairs(labels.cpu().numpy(), preds.cpu().numpy())
+            self.running_loss.update(loss.item())
+            scores = self.running_score.get_scores()[0]
+            miou, pixel_acc = scores["Mean IoU"], scores["Pixel Acc"]
+            if self.lr_scheduler_type == "Poly":
+                lr_scheduler.step(epoch=epoch - 1)
+            if self.debug:
+                break
+        if self.lr_scheduler_type == "MultiStepLR":
+            lr_scheduler.step(epoch=epoch - 1)
+        print(f"({self.experim_name}) Epoch {epoch} | mIoU.: {miou:.3f} | pixel acc.: {pixel_acc:.3f} | "
+              f"avg loss: {self.running_loss.avg:.3f}")
+        if ppdist.rank() == 0:
+            write_log(self.log_train, list_entities=[epoch, miou, pixel_acc, self.running_loss.avg])
+        self._reset_meters()
+        return model, optimizer, lr_scheduler
+
+    def _train(self):
+        print(f"\n({self.experim_name}) training...\n")
+        model = get_model(self.args).to(self.device)
+        model.base_seed = self.args.seed * 131 + self.nth_query + 1
+        ppdist.broadcast_parameters(model)
+        optimizer = get_optimizer(self.args, model)
+        lr_scheduler = get_lr_scheduler(self.args, optimizer=optimizer, iters_per_epoch=len(self.dataloader))
+        reducer = ppdist.GradAllReducer(model) if ppdist.world() > 1 else None
+        for e in range(1, 1 + self.n_epochs):
+            model, optimizer, lr_scheduler = self._train_epoch(e, model, optimizer, lr_scheduler, reducer)
+            self._val(e, model)
+            if self.debug:
+                break
+        self.best_miou = -1.0
+        return model
+
+    @torch.no_grad()
+    def _val(self, epoch, model):
+        """model.py:177-239: bs=1 eval over the validation set, full-map confusion matrix, best-mIoU checkpoint."""
+        model.eval()
+        for dict_data in self.dataloader_val:
+            x, y = dict_data["x"].to(self.device), dict_data["y"]
+            h, w = y.shape[1:]
+            if self.dataset_name == "voc":
+                pad_h = ceil(h / self.stride_total) * self.stride_total - x.shape[2]
+                pad_w = ceil(w / self.stride_total) * self.stride_total - x.shape[3]
+                x = F.pad(x, pad=(0, pad_w, 0, pad_h), mode="reflect")
+            pred = model(x)["pred"][:, :, :h, :w].argmax(dim=1)
+            self.running_score.update(y.numpy(), pred.cpu().numpy())
+            if self.debug:
+                break
+        scores = self.running_score.get_scores()[0]
+        miou, pixel_acc = scores["Mean IoU"], scores["Pixel Acc"]
+        print(f"({self.experim_name}) Epoch {epoch} | val mIoU: {miou:.3f} | pixel acc.: {pixel_acc:.3f}")
+        if ppdist.rank() == 0:
+            if miou > self.best_miou:
+                d = f"{self.dir_checkpoints}/{self.nth_query}_query" if self.n_pixels_by_us != 0 else \
+                    f"{self.dir_checkpoints}/fully_sup"
+                os.makedirs(d, exist_ok=True)
+                torch.save({"model": model.state_dict()}, f"{d}/best_miou_model.pt")
+                self.best_miou = miou
+            write_log(self.log_val, list_entities=[epoch, miou, pixel_acc])
+        self._reset_meters()
+
+    def _reset_meters(self):
+        self.running_loss.reset()
+        self.running_score.reset()

@@ -1,0 +1,190 @@
+"""Host glue mirrored from the reference `utils/utils.py`, `utils/lr_scheduler.py`, `utils/metrics.py` — the parts
+the hot paths' callers need (model factory, optimiser groups, schedulers, meters, CSV log) plus a synthetic
+dataset with the reference dataset interface (no real datasets exist offline)."""
+import csv
+import os
+import pickle as pkl
+from typing import Dict, List
+
+import numpy as np
+import torch
+from torch.optim.lr_scheduler import _LRScheduler
+from torch.utils.data import DataLoader, Dataset
+
+from .deeplab import DeepLab
+from .query import QuerySelector
+
+
+def get_model(args):
+    """utils/utils.py:15-51.  network_name 'deeplab' -> MobileNetV2-DeepLabv3+ (reference) ; 'deeplab_rn50' -> the
+    ResNet-50(dilated-8) + ASPP(2048, OS8) composition of BASELINE configs 3-5.  'FPN' is out of scope."""
+    if args.network_name == "deeplab":
+        return DeepLab(args)
+    if args.network_name == "deeplab_rn50":
+        return DeepLab(args, backbone="resnet")
+    raise NotImplementedError(f"network_name={args.network_name}: only the DeepLabv3+ hot path is implemented")
+
+
+def get_optimizer(args, model):
+    """utils/utils.py:112-306 for the deeplab branch: backbone lr/10, rest lr; note that the declared Adam eps/betas
+    are NOT forwarded by the reference (torch defaults apply, utils.py:141,206) — mirrored."""
+    op = args.optimizer_params
+    groups = [{"params": model.backbone.parameters(), "lr": op["lr"] / 10, "weight_decay": op["weight_decay"]}]
+    for part in (model.aspp, model.low_level_conv, model.seg_head):
+        groups.append({"params": part.parameters(), "lr": op["lr"], "weight_decay": op["weight_decay"]})
+    if args.optimizer_type == "Adam":
+        return torch.optim.Adam(groups, fused=next(model.parameters()).is_cuda)
+    if args.optimizer_type == "SGD":
+        return torch.optim.SGD(groups, momentum=op["momentum"])
+    raise ValueError(args.optimizer_type)
+
+
+class Poly(_LRScheduler):
+    """utils/lr_scheduler.py:4-21 — per-iteration polynomial decay, called as step(epoch=epoch-1)."""
+
+    def __init__(self, optimizer, num_epochs, iters_per_epoch, warmup_epochs=0, last_epoch=-1):
+        self.iters_per_epoch = iters_per_epoch
+        self.cur_iter = 0
+        self.N = num_epochs * iters_per_epoch
+        self.warmup_iters = warmup_epochs * iters_per_epoch
+        super().__init__(optimizer, last_epoch)
+
+    def get_lr(self):
+        T = self.last_epoch * self.iters_per_epoch + self.cur_iter
+        factor = pow((1 - 1.0 * T / self.N), 0.9)
+        if self.warmup_iters > 0 and T < self.warmup_iters:
+            factor = 1.0 * T / self.warmup_iters
+        self.cur_iter %= self.iters_per_epoch
+        self.cur_iter += 1
+        assert factor >= 0, "error in lr_scheduler"
+        return [base_lr * factor for base_lr in self.base_lrs]
+
+
+def get_lr_scheduler(args, optimizer, iters_per_epoch=-1):
+    """utils/utils.py:309-335."""
+    if args.lr_scheduler_type == "MultiStepLR":
+        return torch.optim.lr_scheduler.MultiStepLR(optimizer, milestones=[20, 40], gamma=0.1)
+    return Poly(optimizer, args.n_epochs, iters_per_epoch)
+
+
+def write_log(fp, list_entities=None, header=None):
+    """utils/utils.py:66-72."""
+    with open(fp, "w" if header is not None else "a") as f:
+        csv.writer(f).writerow(header if header is not None else list_entities)
+
+
+class AverageMeter:
+    """utils/metrics.py:85-126."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.val = self.avg = self.sum = self.count = 0
+
+    def update(self, val, weight=1):
+        self.val = val
+        self.sum += val * weight
+        self.count += weight
+        self.avg = self.sum / self.count
+
+
+class RunningScore:
+    """utils/metrics.py:162-207: confusion matrix over pixels whose label is < n_classes.  `update_pairs` takes the
+    (label, prediction) pairs of the labelled pixels only — identical counts, since `_fast_hist` drops every
+    ignore_index pixel (utils/metrics.py:168-173) and the train loop sets unlabelled pixels to ignore_index."""
+
+    def __init__(self, n_classes):
+        self.n_classes = n_classes
+        self.confusion_matrix = np.zeros((n_classes, n_classes))
+
+    def _fast_hist(self, lt, lp):
+        n = self.n_classes
+        mask = (lt >= 0) & (lt < n)
+        return np.bincount(n * lt[mask].astype(int) + lp[mask], minlength=n ** 2).reshape(n, n)
+
+    def update(self, label_trues, label_preds):
+        for lt, lp in zip(label_trues, label_preds):
+            self.confusion_matrix += self._fast_hist(lt.flatten(), lp.flatten())
+
+    def update_pairs(self, labels, preds):
+        self.confusion_matrix += self._fast_hist(np.asarray(labels).flatten(), np.asarray(preds).flatten())
+
+    def get_scores(self):
+        hist = self.confusion_matrix
+        with np.errstate(divide="ignore", invalid="ignore"):
+            acc = np.diag(hist).sum() / hist.sum()
+            acc_cls = np.nanmean(np.diag(hist) / hist.sum(axis=1))
+            iu = np.diag(hist) / (hist.sum(axis=1) + hist.sum(axis=0) - np.diag(hist))
+            freq = hist.sum(axis=1) / hist.sum()
+        return ({"Pixel Acc": acc, "Mean Acc": acc_cls, "FreqW Acc": (freq[freq > 0] * iu[freq > 0]).sum(),
+                 "Mean IoU": np.nanmean(iu)}, dict(zip(range(self.n_classes), iu)))
+
+    def reset(self):
+        self.confusion_matrix = np.zeros((self.n_classes, self.n_classes))
+
+
+class SyntheticDataset(Dataset):
+    """Reference dataset interface (datasets/base_dataset.py:18-46,151-189) over seeded synthetic tensors:
+    items {'x','y','queries','p_img'}; `.queries` (list of bool [H,W]), `.n_pixels_total`, `.label_queries`."""
+
+    def __init__(self, args, n_images, size, val=False, query=False, seed=0):
+        self.H, self.W = size
+        self.n, self.val, self.query = n_images, val, query
+        self.n_classes, self.ignore_index = args.n_classes, args.ignore_index
+        self.dir_checkpoints = f"{args.dir_root}/checkpoints/{args.experim_name}"
+        self.seed = seed + (10_000 if val else 0)
+        self.list_labelled_queries = None
+        rs = np.random.RandomState(self.seed)
+        n_init = args.n_pixels_by_us if args.n_pixels_by_us > 0 else 0
+        self.queries: List[np.ndarray] = []
+        for _ in range(n_images):  # initial random queries (camvid.py:50-96)
+            q = np.zeros(self.H * self.W, dtype=bool)
+            if n_init:
+                q[rs.choice(self.H * self.W, n_init, replace=False)] = True
+            self.queries.append(q.reshape(self.H, self.W))
+        self.n_pixels_total = int(sum(q.sum() for q in self.queries))
+
+    def __len__(self):
+        return self.n
+
+    def _xy(self, i):
+        g = torch.Generator().manual_seed(self.seed * 1_000_003 + i)
+        y = torch.randint(0, self.n_classes, (self.H // 16, self.W // 16), generator=g)
+        y = y.repeat_interleave(16, 0).repeat_interleave(16, 1)  # blocky "segments"
+        x = torch.randn((3, self.H, self.W), generator=g) * 0.5 + (y.float() / self.n_classes - 0.5)[None]
+        void = torch.rand((self.H, self.W), generator=g) < 0.01
+        y = y.clone()
+        y[void] = self.ignore_index
+        return x, y
+
+    def __getitem__(self, i):
+        x, y = self._xy(i)
+        d = {"x": x, "y": y, "p_img": f"synthetic/{i:06d}.png"}
+        if not self.val:
+            d["queries"] = torch.from_numpy(self.queries[i].astype(np.uint8))
+        return d
+
+    def label_queries(self, dict_queries: Dict[str, dict], nth_query=None):
+        """datasets/base_dataset.py:24-46: OR-merge the new picks, persist the wire-format dict."""
+        assert len(dict_queries) == len(self.queries), f"{len(dict_queries)} != {len(self.queries)}"
+        new_q = QuerySelector.decode_queries(dict_queries)
+        previous = self.n_pixels_total
+        self.queries = [np.logical_or(p, q) for p, q in zip(self.queries, new_q)]
+        self.n_pixels_total = int(sum(q.sum() for q in self.queries))
+        print(f"# labelled pixels is changed from {previous} to {self.n_pixels_total} (delta: {self.n_pixels_total - previous})")
+        if isinstance(nth_query, int):
+            os.makedirs(f"{self.dir_checkpoints}/{nth_query}_query", exist_ok=True)
+            pkl.dump(dict_queries, open(f"{self.dir_checkpoints}/{nth_query}_query/queries.pkl", "wb"))
+
+
+def get_dataloader(args, batch_size, n_workers, shuffle, val=False, query=False, generate_init_queries=True):
+    """utils/utils.py:75-109.  The real datasets (CamVid / Cityscapes / VOC files) are not part of the hot path and
+    do not exist offline; `args.synthetic = (n_images, H, W)` selects the synthetic stand-in."""
+    if getattr(args, "synthetic", None) is None:
+        raise NotImplementedError("dataset readers are out of scope (SURVEY.md §2 #9): pass args.synthetic=(n, H, W) "
+                                  "or plug a dataset with the reference interface into Model(dataloaders=...)")
+    n, H, W = args.synthetic
+    ds = SyntheticDataset(args, n if not val else max(2, n // 4), (H, W), val=val, query=query, seed=args.seed)
+    return DataLoader(ds, batch_size=batch_size, num_workers=n_workers, shuffle=shuffle,
+                      drop_last=len(ds) % batch_size == 1)

@@ -1,0 +1,63 @@
+"""CPU, world_size 2 over gloo: the multi-GPU plumbing of pixelpick_b200/dist.py (gradient all-reduce, exact
+global-mean loss scaling, round-robin image sharding + all-gather of the picks)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pixelpick_b200 import dist as ppdist
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    if rank == 1:
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(1.0)
+    ppdist.broadcast_parameters(model)
+    # per-rank shards with DIFFERENT numbers of labelled samples
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn((10, 6), generator=g), torch.randint(0, 3, (10,), generator=g)
+    lo, hi = (0, 3) if rank == 0 else (3, 10)
+    loss = torch.nn.functional.cross_entropy(model(X[lo:hi]), Y[lo:hi])
+    scale = ppdist.global_mean_loss_scale(torch.tensor(float(hi - lo)))
+    (loss * scale).backward()
+    ppdist.GradAllReducer(model)()
+    grads = torch.cat([p.grad.flatten() for p in model.parameters()])
+    # sharded query bookkeeping
+    idx = ppdist.shard_indices(7)
+    rows = torch.tensor([[i, i * 10] for i in idx])
+    allrows = ppdist.all_gather_rows(rows)
+    if rank == 0:
+        torch.save({"grads": grads, "rows": allrows, "params": [p.detach().clone() for p in model.parameters()]}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_gradients_equal_single_process(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    for p, q in zip(model.parameters(), got["params"]):
+        assert torch.equal(p, q)  # broadcast from rank 0
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn((10, 6), generator=g), torch.randint(0, 3, (10,), generator=g)
+    torch.nn.functional.cross_entropy(model(X), Y).backward()
+    ref = torch.cat([p.grad.flatten() for p in model.parameters()])
+    assert torch.allclose(got["grads"], ref, atol=1e-6)
+    assert np.array_equal(got["rows"].numpy(), np.array([[i, i * 10] for i in range(7)]))
