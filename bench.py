@@ -227,6 +227,63 @@ def run_reference(args, rank, world):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def bench_train_graph(backbone, B, steps, warmup, dev, world, e2e=False):
+    """Same train step captured ONCE as a CUDA graph (pixelpick_b200/graph.py) and replayed: removes the ~1000 kernel
+    launches / step of CPU overhead that bound the reference batch size."""
+    import torch.distributed as dist
+    from pixelpick_b200 import _lib, dist as ppdist
+    from pixelpick_b200.deeplab import DeepLab
+    from pixelpick_b200.graph import GraphedTrainStep, make_capturable_adam
+    torch.manual_seed(0)
+    model = DeepLab(MARGS, backbone=backbone).to(dev)
+    model.train()
+    ppdist.broadcast_parameters(model)
+    groups = [{"params": model.backbone.parameters(), "lr": OPT["lr"] / 10, "weight_decay": OPT["weight_decay"]}]
+    for part in (model.aspp, model.low_level_conv, model.seg_head):
+        groups.append({"params": part.parameters(), "lr": OPT["lr"], "weight_decay": OPT["weight_decay"]})
+    opt = make_capturable_adam(groups)
+    reducer = ppdist.GradAllReducer(model) if world > 1 else None
+    hx, hy, hq = synth_train_batch(B, 11 + ppdist.rank(), pin=True)
+    gs = GraphedTrainStep(model, opt, (B, H, W), C, capacity=B * 16, device=dev, reducer=reducer)
+    gs.load(hx, hy, hq)
+    gs.capture()
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step():
+        if e2e:
+            gs.load(hx, hy, hq)  # host batch -> static device buffers (H2D inside the timed region)
+        loss, _ = gs()
+        if e2e:
+            loss_host.copy_(loss.detach().reshape(1))
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    l0 = _lib.lib().pp_launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(steps):
+        last = step()
+    b.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = a.elapsed_time(b) if not e2e else wall * 1e3
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"value": world * B * steps / (ms / 1e3), "ms_per_step": ms / steps, "batch_per_gpu": B, "steps": steps,
+            "cuda_graph": True, "final_loss": float(last.item()),
+            "h2d_bytes_per_step": B * (3 * H * W * 4) + 3 * B * 16 * 4 + 4 if e2e else 0, "d2h_bytes_per_step": 4 if e2e else 0}
+
+
 def bench_train(backbone, B, steps, warmup, dev, world, e2e=False):
     """images/s of the full train step; returns dict(value, ms_per_step, ...)."""
     import torch.distributed as dist
@@ -386,7 +443,18 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at the first collective: keep stdout = ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     lib = _lib.lib()
     hbm_peak, tf_burst, tf_sust, peak_src = peaks()
 
@@ -480,6 +548,8 @@ def main():
         ts = max(5, min(K, 20))
         for name, bb in (("mobilenetv2", "mobilenet"), ("resnet50", "resnet")):
             train[f"{name}_b4"] = bench_train(bb, 4, ts, 5, dev, world)
+            train[f"{name}_b4_graph"] = bench_train_graph(bb, 4, ts, 5, dev, world)
+            train[f"{name}_b4_graph_e2e"] = bench_train_graph(bb, 4, ts, 5, dev, world, e2e=True)
             train[f"{name}_b{args.train_batch}"] = bench_train(bb, args.train_batch, ts, 3, dev, world)
             train[f"{name}_b{args.train_batch}_e2e"] = bench_train(bb, args.train_batch, ts, 3, dev, world, e2e=True)
             torch.cuda.empty_cache()

@@ -140,10 +140,13 @@ int pp_acq_session_run_host(pp_acq_session* s, const float* h_logits, const uint
  * px_img/px_idx/px_label: int32 [n_px].  loss: float32 [1].  grad_lowres: float32 same shape as
  * logits_lowres, ZEROED by the caller (may be NULL for forward only).  pred_at: optional int32
  * [n_px] argmax class at each labelled pixel (train-time running metrics, model.py:124).
+ * n_px_dev: optional device int32: the number of valid list entries (<= n_px = list capacity), so a CUDA graph
+ * captured once can be replayed with a different number of labelled pixels.
  * ------------------------------------------------------------------------------------------ */
 int pp_sparse_ce(const float* logits_lowres, int n_img, int C, int h_in, int w_in, int H, int W,
                  const int32_t* px_img, const int32_t* px_idx, const int32_t* px_label, int n_px,
-                 float grad_scale, float* loss, float* grad_lowres, int32_t* pred_at, void* stream);
+                 const int32_t* n_px_dev, float grad_scale, float* loss, float* grad_lowres, int32_t* pred_at,
+                 void* stream);
 
 /* Bilinear resize, align_corners=True (deeplab.py:49,55,58; aspp.py:70), NCHW float32,
  * forward and its adjoint (grad_in must be zeroed by the caller). */
@@ -187,17 +190,18 @@ int pp_bn_stats(const void* raw, int64_t M, int ld, int c_off, int C, float* sum
  * updates running_mean / running_var in place with nn.BatchNorm2d semantics when non-NULL. */
 int pp_bn_finalize(const float* sums, int C, int64_t M, float eps, float momentum, const float* gamma,
                    const float* beta, float* running_mean, float* running_var, float* out, int Cpad, void* stream);
-/* out[:, c_off_out+c] = dropout_p(relu?(raw[:, c_off_in+c] * scale[c] + shift[c])); Philox mask keyed by
- * (seed, offset, element index) so the backward regenerates it. */
+/* relu: 0 none, 1 ReLU, 2 ReLU6.  out[:, c_off_out+c] = dropout_p(relu?(raw[:, c_off_in+c] * scale[c] + shift[c])); Philox mask keyed by
+ * (seed + *seed_dev, offset, element index) so the backward regenerates it; seed_dev (optional device uint64) lets a
+ * captured CUDA graph draw fresh masks on every replay. */
 int pp_bn_apply(const void* raw, int64_t M, int ld_in, int c_off_in, int C, const float* scale, const float* shift,
-                int relu, float drop_p, uint64_t seed, uint64_t offset, void* out, int ld_out, int c_off_out,
-                void* stream);
+                int relu, float drop_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, void* out, int ld_out,
+                int c_off_out, void* stream);
 /* BatchNorm(train)+ReLU+Dropout backward: draw = scale * (g - mean(g) - xhat * mean(g * xhat)) with
  * g = dy * dropmask/(1-p) * [raw*scale+shift > 0]; sums (f32 [2][C]) returns sum g (= d beta) and
- * sum g*xhat (= d gamma).  g_tmp / draw: bf16 [M][C] (may alias each other is NOT allowed). */
+ * sum g*xhat (= d gamma).  draw: bf16 [M][C].  g is recomputed in the second pass, never stored. */
 int pp_bn_bwd(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_raw, int c_off_raw, int64_t M, int C,
               const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
-              uint64_t seed, uint64_t offset, void* g_tmp, float* sums, void* draw, void* stream);
+              uint64_t seed, uint64_t offset, const uint64_t* seed_dev, float* sums, void* draw, void* stream);
 /* bilinear align_corners=True resize of bf16 NHWC into a channel slice, and its adjoint (f32 accumulate). */
 int pp_upsample_nhwc_bf16(const void* in, int N, int h, int w, int C, int ld_in, void* out, int H, int W, int ld_out,
                           int c_off, void* stream);

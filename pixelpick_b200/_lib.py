@@ -44,13 +44,13 @@ _SIGNATURES = {
     "pp_acq_session_create": ([C.POINTER(_vp), _i, _i, _i, _i, _i, _i], _i),
     "pp_acq_session_destroy": ([_vp], _i),
     "pp_acq_session_run_host": ([_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp], _i),
-    "pp_sparse_ce": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp], _i),
+    "pp_sparse_ce": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _f, _vp, _vp, _vp, _vp], _i),
     "pp_upsample_bilinear_ac": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_upsample_bilinear_ac_bwd": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_conv_wgrad": ([_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_bn_stats": ([_vp, _i64, _i, _i, _i, _vp, _vp], _i),
     "pp_bn_finalize": ([_vp, _i, _i64, _f, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp], _i),
-    "pp_bn_apply": ([_vp, _i64, _i, _i, _i, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _i, _i, _vp], _i),
+    "pp_bn_apply": ([_vp, _i64, _i, _i, _i, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i, _i, _vp], _i),
     "pp_bn_bwd": ([_vp, _i, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp,
                    _vp, _vp], _i),
     "pp_upsample_nhwc_bf16": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp], _i),
@@ -229,8 +229,10 @@ def acq_entropy_at_upsampled(logits_lowres, size, px_idx):
     return out
 
 
-def sparse_ce(logits_lowres, size, px_img, px_idx, px_label, grad_scale=1.0, want_grad=True, want_pred=False):
-    """(loss[1], grad_lowres | None, pred_at | None); see pp_sparse_ce in the header."""
+def sparse_ce(logits_lowres, size, px_img, px_idx, px_label, grad_scale=1.0, want_grad=True, want_pred=False,
+              n_valid=None):
+    """(loss[1], grad_lowres | None, pred_at | None); see pp_sparse_ce in the header.  n_valid: optional device int32
+    [1] with the number of valid list entries (the lists then have a fixed capacity: CUDA-graph friendly)."""
     _need_cuda(logits_lowres, px_img, px_idx, px_label)
     n, Cc, h, w = logits_lowres.shape
     H, W = size
@@ -240,7 +242,8 @@ def sparse_ce(logits_lowres, size, px_img, px_idx, px_label, grad_scale=1.0, wan
     n_px = int(px_idx.numel())
     pred = torch.empty(n_px, dtype=torch.int32, device=x.device) if want_pred else None
     check(lib().pp_sparse_ce(_ptr(x), n, Cc, h, w, H, W, _ptr(px_img), _ptr(px_idx), _ptr(px_label), n_px,
-                             float(grad_scale), _ptr(loss), _ptr(grad), _ptr(pred), _stream(x)), "pp_sparse_ce")
+                             _ptr(n_valid), float(grad_scale), _ptr(loss), _ptr(grad), _ptr(pred), _stream(x)),
+          "pp_sparse_ce")
     return loss, grad, pred
 
 
@@ -358,26 +361,27 @@ def bn_finalize(sums, M, bn, Cpad=None, update_running=True):
     return out
 
 
-def bn_apply(raw, c_off_in, C, scale, shift, relu, out, c_off_out, drop_p=0.0, seed=0, offset=0):
+def bn_apply(raw, c_off_in, C, scale, shift, relu, out, c_off_out, drop_p=0.0, seed=0, offset=0, seed_dev=None):
     _need_cuda(raw, out)
     ld_in, ld_out = raw.shape[-1], out.shape[-1]
     M = raw.numel() // ld_in
     check(lib().pp_bn_apply(_ptr(raw), M, ld_in, c_off_in, C, _ptr(scale), _ptr(shift), int(relu), float(drop_p),
-                            int(seed), int(offset), _ptr(out), ld_out, c_off_out, _stream(raw)), "pp_bn_apply")
+                            int(seed), int(offset), _ptr(seed_dev), _ptr(out), ld_out, c_off_out, _stream(raw)),
+          "pp_bn_apply")
     return out
 
 
-def bn_bwd(dy, c_off_dy, raw, c_off_raw, C, scale, shift, mean, rstd, relu, drop_p=0.0, seed=0, offset=0):
+def bn_bwd(dy, c_off_dy, raw, c_off_raw, C, scale, shift, mean, rstd, relu, drop_p=0.0, seed=0, offset=0,
+           seed_dev=None):
     """returns (draw bf16 [M, C], sums f32 [2, C] = (d beta, d gamma))."""
     _need_cuda(dy, raw)
     ld_dy, ld_raw = dy.shape[-1], raw.shape[-1]
     M = raw.numel() // ld_raw
-    g = torch.empty((M, C), dtype=torch.bfloat16, device=raw.device)
     draw = torch.empty((M, C), dtype=torch.bfloat16, device=raw.device)
     sums = torch.empty((2, C), dtype=torch.float32, device=raw.device)
     check(lib().pp_bn_bwd(_ptr(dy), ld_dy, c_off_dy, _ptr(raw), ld_raw, c_off_raw, M, C, _ptr(scale), _ptr(shift),
-                          _ptr(mean), _ptr(rstd), int(relu), float(drop_p), int(seed), int(offset), _ptr(g), _ptr(sums),
-                          _ptr(draw), _stream(raw)), "pp_bn_bwd")
+                          _ptr(mean), _ptr(rstd), int(relu), float(drop_p), int(seed), int(offset), _ptr(seed_dev),
+                          _ptr(sums), _ptr(draw), _stream(raw)), "pp_bn_bwd")
     return draw, sums
 
 

@@ -76,6 +76,7 @@ struct ConvParams {
   int Cout_pad;      // rows of the packed weight tensor (multiple of BN)
   int Cout;          // valid output channels (<= Cout_pad)
   int taps, dil;     // 1 or 9; dilation (== padding)
+  int n_off, n_tiles_n;  // this launch covers output channels [n_off, n_off + n_tiles_n * BN)
   int TH, TW;        // tile rectangle, TH * TW == 128
   int tiles_y, tiles_x;
   const float* pre_bias;  // [N][Cout_pad] added before scale/shift (ASPP image-pooling branch) or null
@@ -126,7 +127,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - tc::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_n_tiles = p.Cout_pad / BN;
+  const int n_n_tiles = p.n_tiles_n;
   const int m_tiles_per_img = p.tiles_y * p.tiles_x;
   const int total_tiles = p.N * m_tiles_per_img * n_n_tiles;
   const int kc_per_tap = p.Cin / kBK;
@@ -158,7 +159,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto decode = [&](int tile, int& n0, int& img, int& y0, int& x0) {
     const int nt = tile % n_n_tiles;
     int mt = tile / n_n_tiles;
-    n0 = nt * BN;
+    n0 = p.n_off + nt * BN;
     img = mt / m_tiles_per_img;
     mt -= img * m_tiles_per_img;
     const int ty = mt / p.tiles_x;
@@ -307,7 +308,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
     PP_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr = true;
   }
-  const int total = p.N * p.tiles_y * p.tiles_x * (p.Cout_pad / BN);
+  const int total = p.N * p.tiles_y * p.tiles_x * p.n_tiles_n;
   const int grid = total < sm_count ? total : sm_count;
   conv_igemm_kernel<BN><<<grid, kConvThreads, Cfg::SMEM, st>>>(tmA, tmB, p);
   PP_LAUNCH_CHECK();
@@ -348,17 +349,23 @@ int pp_conv_igemm(const void* x, int N, int H, int W, int Cin, int ld_in, const 
     PP_CHECK_ARG(ld_out % 8 == 0 && c_off % 8 == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0,
                  "pp_conv_igemm: bf16 output needs ld_out, c_off multiples of 8 and a 16-byte aligned base");
   int BN = block_n;
+  int n_main = Cout_pad;  // channels covered by the first launch; a remainder gets a second, narrower launch
   if (BN == 0) {
-    if (Cout_pad % 256 == 0) BN = 256;
+    if (Cout_pad > 256 && Cout_pad % 256 != 0 && Cout_pad % 64 == 0) {
+      // e.g. the data gradient into the 320-wide decoder input: 256-wide tiles + one 64/128-wide remainder
+      // (N=64 tiles alone are shared-memory-bandwidth bound: (128+N)*32 B per N/2 cycles)
+      BN = 256;
+      n_main = Cout_pad / 256 * 256;
+    } else if (Cout_pad % 256 == 0) BN = 256;
     else if (Cout_pad % 128 == 0) BN = 128;
     else if (Cout_pad % 64 == 0) BN = 64;
     else BN = 32;
     // small problems: halve N tiles until the grid can fill the machine
     const int th = 8, tw = 16;
     long tiles = (long)N * ((H + th - 1) / th) * ((W + tw - 1) / tw);
-    while (BN > 64 && tiles * (Cout_pad / BN) < sm_count_cached()) BN >>= 1;
+    while (n_main == Cout_pad && BN > 64 && tiles * (Cout_pad / BN) < sm_count_cached()) BN >>= 1;
   }
-  PP_CHECK_ARG((BN == 32 || BN == 64 || BN == 128 || BN == 256) && Cout_pad % BN == 0,
+  PP_CHECK_ARG((BN == 32 || BN == 64 || BN == 128 || BN == 256) && n_main % BN == 0,
                "pp_conv_igemm: block_n=%d does not divide Cout_pad=%d", BN, Cout_pad);
   ConvParams p;
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout_pad = Cout_pad; p.Cout = Cout; p.taps = taps; p.dil = dil;
@@ -368,6 +375,8 @@ int pp_conv_igemm(const void* x, int N, int H, int W, int Cin, int ld_in, const 
   p.tiles_x = (W + p.TW - 1) / p.TW;
   p.pre_bias = pre_bias; p.scale = scale; p.shift = shift; p.relu = relu;
   p.out_mode = out_mode; p.out = out; p.ld_out = ld_out; p.c_off = c_off;
+  p.n_off = 0;
+  p.n_tiles_n = n_main / BN;
 
   CUtensorMap tmA, tmB;
   {
@@ -386,12 +395,28 @@ int pp_conv_igemm(const void* x, int N, int H, int W, int Cin, int ld_in, const 
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int sms = sm_count_cached();
+  int rc;
   switch (BN) {
-    case 256: return launch_conv<256>(tmA, tmB, p, sms, st);
-    case 128: return launch_conv<128>(tmA, tmB, p, sms, st);
-    case 64: return launch_conv<64>(tmA, tmB, p, sms, st);
-    default: return launch_conv<32>(tmA, tmB, p, sms, st);
+    case 256: rc = launch_conv<256>(tmA, tmB, p, sms, st); break;
+    case 128: rc = launch_conv<128>(tmA, tmB, p, sms, st); break;
+    case 64: rc = launch_conv<64>(tmA, tmB, p, sms, st); break;
+    default: rc = launch_conv<32>(tmA, tmB, p, sms, st); break;
   }
+  if (rc != PP_OK || n_main == Cout_pad) return rc;
+  // remainder launch: narrower tiles over output channels [n_main, Cout_pad)
+  const int rem = Cout_pad - n_main;
+  const int BR = (rem % 128 == 0) ? 128 : 64;
+  CUtensorMap tmB2;
+  {
+    const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout_pad, (uint64_t)taps};
+    const uint64_t strides[2] = {(uint64_t)Cin * 2, (uint64_t)Cout_pad * Cin * 2};
+    const uint32_t box[3] = {64, (uint32_t)BR, 1};
+    rc = make_tmap_bf16(&tmB2, w_packed, 3, dims, strides, box);
+    if (rc != PP_OK) return rc;
+  }
+  p.n_off = n_main;
+  p.n_tiles_n = rem / BR;
+  return BR == 128 ? launch_conv<128>(tmA, tmB2, p, sms, st) : launch_conv<64>(tmA, tmB2, p, sms, st);
 }
 
 }  // extern "C"

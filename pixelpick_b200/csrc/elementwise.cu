@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const __nv_bfloat1
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (r < rows_per_block) {
+#pragma unroll 4
     for (int64_t row = (int64_t)blockIdx.x * rows_per_block + r; row < M; row += (int64_t)gridDim.x * rows_per_block) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(raw + row * ld + c_off + g * 8));
       float f[8];
@@ -107,6 +108,7 @@ struct BnApplyParams {
   int relu;
   float drop_p;
   uint64_t seed, offset;
+  const uint64_t* seed_dev;  // optional device-side addend to the seed (CUDA-graph replays advance it)
   __nv_bfloat16* out;
   int ld_out, c_off_out;
 };
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParam
   const int groups = p.C >> 3;
   const int64_t total = p.M * groups;
   const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  const uint64_t seed = p.seed + ((p.drop_p > 0.f && p.seed_dev) ? *p.seed_dev : 0ull);
   for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kEwThreads) {
     const int64_t row = i / groups;
     const int g = (int)(i - row * groups);
@@ -127,11 +130,12 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParam
     const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
     const float sf[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     uint32_t keep = 0xFFu;
-    if (p.drop_p > 0.f) keep = dropout_keep8(p.seed, p.offset, (uint64_t)i * 8, p.drop_p);
+    if (p.drop_p > 0.f) keep = dropout_keep8(seed, p.offset, (uint64_t)i * 8, p.drop_p);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float y = fmaf(f[j], sc[j], sf[j]);
       if (p.relu) y = fmaxf(y, 0.f);
+      if (p.relu == 2) y = fminf(y, 6.f);  // ReLU6 (mobilenet_v2.py:7-12)
       f[j] = ((keep >> j) & 1u) ? y * keep_scale : 0.f;
     }
     *reinterpret_cast<uint4*>(p.out + row * p.ld_out + p.c_off_out + g * 8) = pack8(f);
@@ -153,11 +157,29 @@ struct BnBwdParams {
   int relu;
   float drop_p;
   uint64_t seed, offset;
-  __nv_bfloat16* g;  // [M][C] masked gradient (out of pass 1, in of pass 2)
-  float* sums;       // [2][C]: sum g, sum g*xhat
-  const float* inv_m_sums;  // pass 2: the same buffer
-  __nv_bfloat16* draw;      // pass 2 output [M][C]
+  const uint64_t* seed_dev;
+  float* sums;          // [2][C]: sum g, sum g*xhat
+  __nv_bfloat16* draw;  // pass 2 output [M][C]
 };
+
+// masked upstream gradient of 8 channels: dropout mask/scale and the ReLU / ReLU6 gate (recomputed, never stored)
+__device__ __forceinline__ void bn_bwd_g8(const BnBwdParams& p, uint64_t seed, float keep_scale, int64_t row, int g,
+                                          int groups, const float (&sc)[8], const float (&sf)[8], float (&x)[8],
+                                          float (&go)[8]) {
+  float dy[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(p.dy + row * p.ld_dy + p.c_off_dy + g * 8)), dy);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(p.raw + row * p.ld_raw + p.c_off_raw + g * 8)), x);
+  uint32_t keep = 0xFFu;
+  if (p.drop_p > 0.f) keep = dropout_keep8(seed, p.offset, (uint64_t)(row * groups + g) * 8, p.drop_p);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float gg = ((keep >> j) & 1u) ? dy[j] * keep_scale : 0.f;
+    const float yv = fmaf(x[j], sc[j], sf[j]);
+    if (p.relu && !(yv > 0.f)) gg = 0.f;
+    if (p.relu == 2 && !(yv < 6.f)) gg = 0.f;
+    go[j] = gg;
+  }
+}
 
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdParams p) {
   extern __shared__ float sh[];
@@ -165,6 +187,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdPa
   const int rows_per_block = kEwThreads / groups;
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
   const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  const uint64_t seed = p.seed + ((p.drop_p > 0.f && p.seed_dev) ? *p.seed_dev : 0ull);
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
@@ -177,21 +200,16 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdPa
       mu[j] = __ldg(p.mean + g * 8 + j);
       rs[j] = __ldg(p.rstd + g * 8 + j);
     }
-    for (int64_t row = (int64_t)blockIdx.x * rows_per_block + r; row < p.M; row += (int64_t)gridDim.x * rows_per_block) {
-      float dy[8], x[8], go[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.dy + row * p.ld_dy + p.c_off_dy + g * 8)), dy);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.raw + row * p.ld_raw + p.c_off_raw + g * 8)), x);
-      uint32_t keep = 0xFFu;
-      if (p.drop_p > 0.f) keep = dropout_keep8(p.seed, p.offset, (uint64_t)(row * groups + g) * 8, p.drop_p);
+    const int64_t stride = (int64_t)gridDim.x * rows_per_block;
+#pragma unroll 2
+    for (int64_t row = (int64_t)blockIdx.x * rows_per_block + r; row < p.M; row += stride) {
+      float x[8], go[8];
+      bn_bwd_g8(p, seed, keep_scale, row, g, groups, sc, sf, x, go);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float gg = ((keep >> j) & 1u) ? dy[j] * keep_scale : 0.f;
-        if (p.relu && !(fmaf(x[j], sc[j], sf[j]) > 0.f)) gg = 0.f;
-        go[j] = gg;
-        s[j] += gg;
-        q[j] = fmaf(gg, (x[j] - mu[j]) * rs[j], q[j]);
+        s[j] += go[j];
+        q[j] = fmaf(go[j], (x[j] - mu[j]) * rs[j], q[j]);
       }
-      *reinterpret_cast<uint4*>(p.g + row * p.C + g * 8) = pack8(go);
     }
   }
 #pragma unroll
@@ -212,18 +230,24 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdPar
   const int groups = p.C >> 3;
   const int64_t total = p.M * groups;
   const float inv_m = 1.f / (float)p.M;
+  const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  const uint64_t seed = p.seed + ((p.drop_p > 0.f && p.seed_dev) ? *p.seed_dev : 0ull);
   for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kEwThreads) {
     const int64_t row = i / groups;
     const int g = (int)(i - row * groups);
-    float gg[8], x[8], o[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(p.g + row * p.C + g * 8)), gg);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(p.raw + row * p.ld_raw + p.c_off_raw + g * 8)), x);
+    float sc[8], sf[8], x[8], gg[8], o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(p.scale + g * 8 + j);
+      sf[j] = __ldg(p.shift + g * 8 + j);
+    }
+    bn_bwd_g8(p, seed, keep_scale, row, g, groups, sc, sf, x, gg);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = g * 8 + j;
       const float xh = (x[j] - __ldg(p.mean + c)) * __ldg(p.rstd + c);
-      const float mg = __ldg(p.inv_m_sums + c) * inv_m, mgx = __ldg(p.inv_m_sums + p.C + c) * inv_m;
-      o[j] = __ldg(p.scale + c) * (gg[j] - mg - xh * mgx);
+      const float mg = __ldg(p.sums + c) * inv_m, mgx = __ldg(p.sums + p.C + c) * inv_m;
+      o[j] = sc[j] * (gg[j] - mg - xh * mgx);
     }
     *reinterpret_cast<uint4*>(p.draw + row * p.C + g * 8) = pack8(o);
   }
@@ -339,8 +363,8 @@ int pp_bn_stats(const void* raw, int64_t M, int ld, int c_off, int C, float* sum
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   PP_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
   const int rows_per_block = kEwThreads / (C / 8);
-  int64_t blocks = (M + rows_per_block * 8 - 1) / (rows_per_block * 8);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  int64_t blocks = (M + rows_per_block * 4 - 1) / (rows_per_block * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
   bn_stats_kernel<<<(int)blocks, kEwThreads, kEwThreads * 16 * sizeof(float), st>>>(
       reinterpret_cast<const __nv_bfloat16*>(raw), M, ld, c_off, C, sums);
   PP_LAUNCH_CHECK();
@@ -348,8 +372,8 @@ int pp_bn_stats(const void* raw, int64_t M, int ld, int c_off, int C, float* sum
 }
 
 int pp_bn_apply(const void* raw, int64_t M, int ld_in, int c_off_in, int C, const float* scale, const float* shift,
-                int relu, float drop_p, uint64_t seed, uint64_t offset, void* out, int ld_out, int c_off_out,
-                void* stream) {
+                int relu, float drop_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, void* out, int ld_out,
+                int c_off_out, void* stream) {
   PP_CHECK_ARG(raw && out && scale && shift && M > 0, "pp_bn_apply: bad args");
   PP_CHECK_ARG(C % 8 == 0 && ld_in % 8 == 0 && c_off_in % 8 == 0 && ld_out % 8 == 0 && c_off_out % 8 == 0,
                "pp_bn_apply: channel counts/offsets must be multiples of 8");
@@ -357,7 +381,7 @@ int pp_bn_apply(const void* raw, int64_t M, int ld_in, int c_off_in, int C, cons
   BnApplyParams p;
   p.raw = reinterpret_cast<const __nv_bfloat16*>(raw);
   p.M = M; p.ld_in = ld_in; p.c_off_in = c_off_in; p.C = C; p.scale = scale; p.shift = shift; p.relu = relu;
-  p.drop_p = drop_p; p.seed = seed; p.offset = offset;
+  p.drop_p = drop_p; p.seed = seed; p.offset = offset; p.seed_dev = seed_dev;
   p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ld_out = ld_out; p.c_off_out = c_off_out;
   bn_apply_kernel<<<ew_grid(M * (C / 8)), kEwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   PP_LAUNCH_CHECK();
@@ -366,8 +390,8 @@ int pp_bn_apply(const void* raw, int64_t M, int ld_in, int c_off_in, int C, cons
 
 int pp_bn_bwd(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_raw, int c_off_raw, int64_t M, int C,
               const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
-              uint64_t seed, uint64_t offset, void* g_tmp, float* sums, void* draw, void* stream) {
-  PP_CHECK_ARG(dy && raw && g_tmp && sums && draw && M > 0, "pp_bn_bwd: bad args");
+              uint64_t seed, uint64_t offset, const uint64_t* seed_dev, float* sums, void* draw, void* stream) {
+  PP_CHECK_ARG(dy && raw && sums && draw && M > 0, "pp_bn_bwd: bad args");
   PP_CHECK_ARG(C % 8 == 0 && C <= 2048 && ld_dy % 8 == 0 && c_off_dy % 8 == 0 && ld_raw % 8 == 0 && c_off_raw % 8 == 0,
                "pp_bn_bwd: C=%d must be a multiple of 8 and <= 2048", C);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -375,13 +399,13 @@ int pp_bn_bwd(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_r
   p.dy = reinterpret_cast<const __nv_bfloat16*>(dy); p.ld_dy = ld_dy; p.c_off_dy = c_off_dy;
   p.raw = reinterpret_cast<const __nv_bfloat16*>(raw); p.ld_raw = ld_raw; p.c_off_raw = c_off_raw;
   p.M = M; p.C = C; p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.relu = relu;
-  p.drop_p = drop_p; p.seed = seed; p.offset = offset;
-  p.g = reinterpret_cast<__nv_bfloat16*>(g_tmp); p.sums = sums; p.inv_m_sums = sums;
+  p.drop_p = drop_p; p.seed = seed; p.offset = offset; p.seed_dev = seed_dev;
+  p.sums = sums;
   p.draw = reinterpret_cast<__nv_bfloat16*>(draw);
   PP_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
   const int rows_per_block = kEwThreads / (C / 8);
-  int64_t blocks = (M + rows_per_block * 8 - 1) / (rows_per_block * 8);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  int64_t blocks = (M + rows_per_block * 4 - 1) / (rows_per_block * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
   bn_bwd_reduce_kernel<<<(int)blocks, kEwThreads, kEwThreads * 16 * sizeof(float), st>>>(p);
   PP_LAUNCH_CHECK();
   bn_bwd_apply_kernel<<<ew_grid(M * (C / 8)), kEwThreads, 0, st>>>(p);

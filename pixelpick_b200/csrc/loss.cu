@@ -15,8 +15,12 @@ constexpr int kCeThreads = 1024;
 __global__ void __launch_bounds__(kCeThreads) sparse_ce_kernel(
     const float* __restrict__ logits, int n_img, int C, int h_in, int w_in, int H, int W, float scale_h,
     float scale_w, const int32_t* __restrict__ px_img, const int32_t* __restrict__ px_idx,
-    const int32_t* __restrict__ px_label, int n_px, float grad_coef, float inv_n,
+    const int32_t* __restrict__ px_label, int n_px_cap, const int32_t* __restrict__ n_px_dev, float grad_scale,
     float* __restrict__ loss, float* __restrict__ grad, int32_t* __restrict__ pred_at) {
+  // the labelled-pixel count may live on the device (CUDA-graph replays with a fixed-capacity list)
+  const int n_px = n_px_dev ? min(*n_px_dev, n_px_cap) : n_px_cap;
+  const float inv_n = n_px > 0 ? 1.0f / (float)n_px : __int_as_float(0x7FC00000);
+  const float grad_coef = grad_scale * inv_n;
   __shared__ float sh_part[kCeThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps_per_block = kCeThreads / 32;
@@ -134,11 +138,12 @@ extern "C" {
 
 int pp_sparse_ce(const float* logits_lowres, int n_img, int C, int h_in, int w_in, int H, int W,
                  const int32_t* px_img, const int32_t* px_idx, const int32_t* px_label, int n_px,
-                 float grad_scale, float* loss, float* grad_lowres, int32_t* pred_at, void* stream) {
+                 const int32_t* n_px_dev, float grad_scale, float* loss, float* grad_lowres, int32_t* pred_at,
+                 void* stream) {
   PP_CHECK_ARG(logits_lowres && loss, "pp_sparse_ce: null pointer");
   PP_CHECK_ARG(n_img > 0 && C >= 2 && h_in > 0 && w_in > 0 && H > 0 && W > 0 && n_px >= 0, "pp_sparse_ce: bad shape");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (n_px == 0) {  // F.cross_entropy over an empty selection is NaN (mean of nothing)
+  if (n_px == 0 && !n_px_dev) {  // F.cross_entropy over an empty selection is NaN (mean of nothing)
     fill_kernel<<<1, 1, 0, st>>>(loss, __builtin_nanf(""));
     PP_LAUNCH_CHECK();
     return PP_OK;
@@ -151,10 +156,9 @@ int pp_sparse_ce(const float* logits_lowres, int n_img, int C, int h_in, int w_i
     if (grid > 148 * 2) grid = 148 * 2;
     PP_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
   }
-  const float inv_n = 1.0f / (float)n_px;
   sparse_ce_kernel<<<grid, kCeThreads, 0, st>>>(logits_lowres, n_img, C, h_in, w_in, H, W, ac_scale(h_in, H),
-                                                 ac_scale(w_in, W), px_img, px_idx, px_label, n_px,
-                                                 grad_scale * inv_n, inv_n, loss, grad_lowres, pred_at);
+                                                 ac_scale(w_in, W), px_img, px_idx, px_label, n_px, n_px_dev,
+                                                 grad_scale, loss, grad_lowres, pred_at);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

@@ -225,7 +225,7 @@ int pp_conv_wgrad(const void* x, int ld_x, int Cin, const void* dy, int ld_dy, i
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    splits = (2 * sms + taps * n_ci_tiles - 1) / (taps * n_ci_tiles);
+    splits = (2 * sms) / (taps * n_ci_tiles);  // <= 2 full waves: one extra CTA would cost a whole third wave
     const int max_splits = (total_pb + 7) / 8;  // at least 8 pixel blocks (512 pixels) per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

@@ -25,10 +25,68 @@ from . import _lib
 
 
 # =============================================================================================
+# BatchNorm (+ReLU / ReLU6) of the encoders on the NHWC bf16 kernels of elementwise.cu
+# =============================================================================================
+class _BNActFn(torch.autograd.Function):
+    """train-mode BatchNorm2d + activation as two fused NHWC passes (pp_bn_stats/finalize + pp_bn_apply) and a
+    two-pass backward (pp_bn_bwd); x is a contiguous NHWC bf16 view."""
+
+    @staticmethod
+    def forward(ctx, xn, weight, bias, mod, act):
+        C = xn.shape[-1]
+        M = xn.numel() // C
+        stats = _lib.bn_finalize(_lib.bn_stats(xn, 0, C), M, mod)
+        y = torch.empty_like(xn)
+        _lib.bn_apply(xn, 0, C, stats[0], stats[1], act, y, 0)
+        ctx.save_for_backward(xn, stats)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xn, stats = ctx.saved_tensors
+        C = xn.shape[-1]
+        if dy.dtype != torch.bfloat16 or not dy.is_contiguous():
+            dy = dy.to(torch.bfloat16).contiguous()
+        draw, sums = _lib.bn_bwd(dy, 0, xn, 0, C, stats[0], stats[1], stats[2], stats[3], ctx.act)
+        return draw.view_as(xn), sums[1], sums[0], None, None
+
+
+class FusedBNAct(nn.BatchNorm2d):
+    """nn.BatchNorm2d (same parameters / buffers / state_dict keys) whose forward also applies `act`
+    (0 none, 1 ReLU, 2 ReLU6).  CUDA bf16 inputs run on the fused NHWC kernels; anything else (fp32 parity mode,
+    CPU construction) falls back to torch with identical semantics."""
+
+    def __init__(self, num_features, act=0):
+        super().__init__(num_features)
+        self.act = act
+
+    def _torch_act(self, y):
+        return F.relu(y) if self.act == 1 else (F.relu6(y) if self.act == 2 else y)
+
+    def forward(self, x):
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0 and x.dim() == 4):
+            return self._torch_act(super().forward(x))
+        xn = x.permute(0, 2, 3, 1)
+        if not xn.is_contiguous():
+            xn = xn.contiguous()
+        if self.training:
+            y = _BNActFn.apply(xn, self.weight, self.bias, self, self.act)
+        else:
+            if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+                return self._torch_act(super().forward(x))
+            scale, shift = _fold_bn(self)
+            y = torch.empty_like(xn)
+            _lib.bn_apply(xn, 0, xn.shape[-1], scale, shift, self.act, y, 0)
+        return y.permute(0, 3, 1, 2)
+
+
+# =============================================================================================
 # encoders (PyTorch modules; structure mirrors the reference so parameter names match)
 # =============================================================================================
 def _conv_bn(inp, oup, stride):
-    return nn.Sequential(nn.Conv2d(inp, oup, 3, stride, 1, bias=False), nn.BatchNorm2d(oup), nn.ReLU6(inplace=True))
+    # index 2 was nn.ReLU6 in the reference: the activation is fused into the BatchNorm kernel (no parameters there)
+    return nn.Sequential(nn.Conv2d(inp, oup, 3, stride, 1, bias=False), FusedBNAct(oup, act=2), nn.Identity())
 
 
 def fixed_padding(inputs, kernel_size, dilation):
@@ -49,9 +107,9 @@ class InvertedResidual(nn.Module):
         self.kernel_size, self.dilation = 3, dilation
         layers = []
         if expand_ratio != 1:
-            layers += [nn.Conv2d(inp, hidden, 1, 1, 0, 1, bias=False), nn.BatchNorm2d(hidden), nn.ReLU6(inplace=True)]
-        layers += [nn.Conv2d(hidden, hidden, 3, stride, 0, dilation, groups=hidden, bias=False), nn.BatchNorm2d(hidden),
-                   nn.ReLU6(inplace=True), nn.Conv2d(hidden, oup, 1, 1, 0, 1, bias=False), nn.BatchNorm2d(oup)]
+            layers += [nn.Conv2d(inp, hidden, 1, 1, 0, 1, bias=False), FusedBNAct(hidden, act=2), nn.Identity()]
+        layers += [nn.Conv2d(hidden, hidden, 3, stride, 0, dilation, groups=hidden, bias=False), FusedBNAct(hidden, act=2),
+                   nn.Identity(), nn.Conv2d(hidden, oup, 1, 1, 0, 1, bias=False), FusedBNAct(oup, act=0)]
         self.conv = nn.Sequential(*layers)
 
     def forward(self, x):
@@ -107,17 +165,17 @@ class Bottleneck(nn.Module):
     def __init__(self, inplanes, planes, stride=1, downsample=None):
         super().__init__()
         self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
+        self.bn1 = FusedBNAct(planes, act=1)
         self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = FusedBNAct(planes, act=1)
         self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
-        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.bn3 = FusedBNAct(planes * 4, act=0)
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
 
     def forward(self, x):
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.relu(self.bn2(self.conv2(out)))
+        out = self.bn1(self.conv1(x))  # BatchNorm + ReLU fused
+        out = self.bn2(self.conv2(out))
         out = self.bn3(self.conv3(out))
         return self.relu(out + (x if self.downsample is None else self.downsample(x)))
 
@@ -128,8 +186,8 @@ class ResNet50Dilated8(nn.Module):
 
     def __init__(self):
         super().__init__()
-        self.prefix = nn.Sequential(OrderedDict([("conv1", nn.Conv2d(3, 64, 7, 2, 3, bias=False)), ("bn1", nn.BatchNorm2d(64)),
-                                                 ("relu", nn.ReLU(inplace=False))]))
+        self.prefix = nn.Sequential(OrderedDict([("conv1", nn.Conv2d(3, 64, 7, 2, 3, bias=False)), ("bn1", FusedBNAct(64, act=1)),
+                                                 ("relu", nn.Identity())]))
         self.maxpool = nn.MaxPool2d(3, 2, 1)
         self.inplanes = 64
         self.layer1 = self._make_layer(64, 3, 1)
@@ -150,7 +208,7 @@ class ResNet50Dilated8(nn.Module):
     def _make_layer(self, planes, blocks, stride):
         down = None
         if stride != 1 or self.inplanes != planes * 4:
-            down = nn.Sequential(nn.Conv2d(self.inplanes, planes * 4, 1, stride, bias=False), nn.BatchNorm2d(planes * 4))
+            down = nn.Sequential(nn.Conv2d(self.inplanes, planes * 4, 1, stride, bias=False), FusedBNAct(planes * 4, act=0))
         layers = [Bottleneck(self.inplanes, planes, stride, down)]
         self.inplanes = planes * 4
         layers += [Bottleneck(self.inplanes, planes) for _ in range(1, blocks)]
@@ -232,8 +290,14 @@ class SegmentHead(nn.Module):
 # =============================================================================================
 # head: kernels
 # =============================================================================================
-def _pack(w, cin_pad=None, cout_pad=None, dgrad=False):
-    return _lib.pack_conv_weight(w.detach(), cin_pad, cout_pad, dgrad)
+def _pack(w, cin_pad=None, cout_pad=None, dgrad=False, cin=None):
+    """conv weight [Cout, Cin_total, kh, kw] (first `cin` input channels) -> bf16 operand of pp_conv_igemm in ONE launch.
+    forward: [taps][cout_pad][cin_pad];  dgrad: [taps][cout_pad (padded Cin rows)][cin_pad (padded Cout cols)], taps flipped."""
+    co, ci_tot = w.shape[:2]
+    cin = ci_tot if cin is None else cin
+    if dgrad:
+        return _lib.pack_conv_weights(w, cin, dgrad_pad=(cout_pad or -(-cin // 32) * 32, cin_pad or -(-co // 64) * 64))[1]
+    return _lib.pack_conv_weights(w, cin, fwd_pad=(cout_pad or -(-co // 32) * 32, cin_pad or -(-cin // 64) * 64))[0]
 
 
 def _fold_bn(bn, cpad=None):
@@ -286,7 +350,7 @@ class _HeadFn(torch.autograd.Function):
         def run_layer(x, cin_valid, wt, bn, dil, raw, c_off, C, out, out_c_off, relu=True, p=0.0, pre=None, cpad=None):
             taps = wt.shape[2] * wt.shape[3]
             cin_pad = x.shape[3]
-            wp = _pack(wt[:, :cin_valid], cin_pad, cpad or -(-C // 64) * 64)
+            wp = _pack(wt, cin_pad, cpad or -(-C // 64) * 64, cin=cin_valid)
             _lib.conv_igemm(x, wp, C, dil=dil, pre_bias=pre, out=raw, c_off=c_off, cin=cin_pad)
             rows = raw.numel() // raw.shape[-1]
             stats = _lib.bn_finalize(_lib.bn_stats(raw, c_off, C), rows, bn, Cpad=cpad or C)
@@ -294,7 +358,8 @@ class _HeadFn(torch.autograd.Function):
             L.x, L.cin, L.w, L.taps, L.dil, L.raw, L.c_off, L.C = x, cin_valid, wt, taps, dil, raw, c_off, C
             L.stats, L.relu, L.p, L.bn = stats, relu, p, bn
             L.offset = next_offset(rows * (cpad or C)) if p > 0 else 0
-            _lib.bn_apply(raw, c_off, cpad or C, stats[0], stats[1], relu, out, out_c_off, drop_p=p, seed=seed, offset=L.offset)
+            _lib.bn_apply(raw, c_off, cpad or C, stats[0], stats[1], relu, out, out_c_off, drop_p=p, seed=seed, offset=L.offset,
+                          seed_dev=model._rng_step)
             layers.append(L)
             return L
 
@@ -343,7 +408,7 @@ class _HeadFn(torch.autograd.Function):
             st = L.stats
             C = st.shape[1]
             draw, sums = _lib.bn_bwd(dy, c_off_dy, L.raw, L.c_off, C, st[0], st[1], st[2], st[3], L.relu, drop_p=L.p,
-                                     seed=seed, offset=L.offset)
+                                     seed=seed, offset=L.offset, seed_dev=model._rng_step)
             N_, H_, W_ = L.x.shape[0], L.x.shape[1], L.x.shape[2]
             draw4 = draw.view(N_, H_, W_, C)
             dw = _lib.conv_wgrad(L.x, L.cin, draw4, C if C in (64, 128, 256) else cout_pad, L.taps, L.dil)
@@ -352,8 +417,7 @@ class _HeadFn(torch.autograd.Function):
             dx = None
             if need_dx:
                 cin_pad = L.x.shape[3]
-                wt = L.w[:, :L.cin] if L.w.shape[1] != L.cin else L.w
-                wp = _pack(wt, C, dx_pad or cin_pad, dgrad=True)  # [taps][Cin_pad][C]
+                wp = _pack(L.w, C, dx_pad or cin_pad, dgrad=True, cin=L.cin)  # [taps][Cin_pad][C]
                 dx = _lib.conv_igemm(draw4, wp, dx_valid or cin_pad, dil=L.dil)
             return dW, sums[1][:L.C], sums[0][:L.C], dx, draw4
 
@@ -402,7 +466,7 @@ class DeepLab(nn.Module):
         _init_head(self.low_level_conv)
         self.return_features = False
         self.return_attention = False
-        self._step = 0
+        self._rng_step = None  # device int64 [1]: dropout step counter (device-side so CUDA-graph replays advance it)
         self.base_seed = 0
         self._cache = {}
         # encoder precision: torch.bfloat16 (default, BASELINE config 2) or None = fp32 (used by the parity tests to
@@ -483,7 +547,7 @@ class DeepLab(nn.Module):
             a, sh, cin = self.aspp, self.seg_head, self.aspp.inplanes
             e = {}
             e["br"] = [(_pack(m.atrous_conv.weight, cin, 256),) + _fold_bn(m.bn) for m in (a.aspp1, a.aspp2, a.aspp3, a.aspp4)]
-            e["c1"] = (_pack(a.conv1.weight[:, :1024], 1024, 256),) + _fold_bn(a.bn1)
+            e["c1"] = (_pack(a.conv1.weight, 1024, 256, cin=1024),) + _fold_bn(a.bn1)
             e["ll"] = (_pack(self.low_level_conv[0].weight, -(-self.backbone.low_channels // 64) * 64, 64),) + _fold_bn(
                 self.low_level_conv[1], 64)
             e["d1"] = (_pack(sh.segment_head[0].weight, 320, 256),) + _fold_bn(sh.segment_head[1])
@@ -544,8 +608,10 @@ class DeepLab(nn.Module):
         if not bn_train:
             raise _lib.PixelPickError("head kernels support eval mode without grad/dropout, or full train mode")
         pre = self._pooled_branch(high)
-        self._step += 1
-        seed = (self.base_seed * 1000003 + self._step) & 0x7FFFFFFFFFFFFFFF
+        if self._rng_step is None or self._rng_step.device != high.device:
+            self._rng_step = torch.zeros(1, dtype=torch.int64, device=high.device)
+        self._rng_step += 1
+        seed = (self.base_seed * 1000003) & 0x7FFFFFFFFFFFFFFF
         return _HeadFn.apply(self, seed, high, low, pre, *self._head_params())
 
     def forward(self, inputs):

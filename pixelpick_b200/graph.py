@@ -1,0 +1,80 @@
+"""CUDA-graph capture of the whole train step (forward_lowres -> fused sparse CE -> backward -> [grad all-reduce]
+-> optimiser), for the launch-bound regime of the reference batch size (B = 4: ~1000 kernels, CPU-bound in eager mode).
+
+Static inputs: the image batch, a fixed-capacity labelled-pixel list + its device-side count (pp_sparse_ce reads the
+count on the device), the dropout step counter (device int64 advanced inside the graph) and tensor learning rates.
+"""
+import torch
+
+from . import dist as ppdist
+from .loss import labelled_pixel_list_host, sparse_cross_entropy
+
+
+def make_capturable_adam(param_groups):
+    """torch.optim.Adam(fused, capturable) with TENSOR learning rates so a scheduler can change them between replays."""
+    dev = param_groups[0]["params"][0].device if not hasattr(param_groups[0]["params"], "__next__") else None
+    groups = []
+    for g in param_groups:
+        g = dict(g)
+        g["params"] = list(g["params"])
+        dev = g["params"][0].device
+        g["lr"] = torch.tensor(float(g["lr"]), dtype=torch.float32, device=dev)
+        groups.append(g)
+    return torch.optim.Adam(groups, fused=True, capturable=True)
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, batch_shape, ignore_index, capacity, device, reducer=None, warmup=3):
+        B, H, W = batch_shape
+        self.model, self.opt, self.ignore_index, self.capacity, self.size = model, optimizer, ignore_index, capacity, (H, W)
+        self.reducer = reducer
+        self.x = torch.zeros((B, 3, H, W), dtype=torch.float32, device=device)
+        self.px = [torch.zeros(capacity, dtype=torch.int32, device=device) for _ in range(3)]
+        self.n_valid = torch.ones(1, dtype=torch.int32, device=device)
+        self.loss_scale = torch.ones((), dtype=torch.float32, device=device)
+        self.graph = None
+        self._warm = warmup
+
+    def _step(self):
+        lowres = self.model.forward_lowres(self.x)
+        loss, pred, _ = sparse_cross_entropy(lowres, None, None, self.ignore_index, size=self.size, return_pred=True,
+                                             px=self.px, n_valid=self.n_valid)
+        (loss * self.loss_scale).backward()
+        if self.reducer is not None:
+            self.reducer()
+        self.opt.step()
+        return loss, pred
+
+    def load(self, x, y, queries):
+        """host batch (CPU tensors from the dataloader) -> static device buffers; returns the host label list."""
+        pi, px, pl, n = labelled_pixel_list_host(y, queries, self.ignore_index, self.capacity)
+        self.x.copy_(x, non_blocking=True)
+        for dst, src in zip(self.px, (pi, px, pl)):
+            dst.copy_(src, non_blocking=True)
+        self.n_valid.copy_(n, non_blocking=True)
+        if ppdist.world() > 1:
+            self.loss_scale.copy_(ppdist.global_mean_loss_scale(self.n_valid.float().reshape(())))
+        return pl[: int(n)]
+
+    def capture(self):
+        self.model.train()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(self._warm):
+                self.opt.zero_grad(set_to_none=True)
+                self._step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.loss, self.pred = self._step()
+        return self
+
+    def __call__(self):
+        """replay on the current contents of the static buffers; returns (loss [0-d], pred_at [capacity]) device tensors."""
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+        return self.loss, self.pred

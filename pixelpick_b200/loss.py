@@ -27,8 +27,9 @@ def labelled_pixel_list(y, queries, ignore_index):
 
 class _SparseCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits_lowres, size, px_img, px_idx, px_label):
-        loss, grad, pred = _lib.sparse_ce(logits_lowres, size, px_img, px_idx, px_label, want_grad=True, want_pred=True)
+    def forward(ctx, logits_lowres, size, px_img, px_idx, px_label, n_valid=None):
+        loss, grad, pred = _lib.sparse_ce(logits_lowres, size, px_img, px_idx, px_label, want_grad=True, want_pred=True,
+                                          n_valid=n_valid)
         ctx.save_for_backward(grad)
         ctx.in_dtype = logits_lowres.dtype
         ctx.mark_non_differentiable(pred)
@@ -37,15 +38,39 @@ class _SparseCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _g_pred):
         (grad,) = ctx.saved_tensors
-        return (grad * g_loss).to(ctx.in_dtype), None, None, None, None
+        return (grad * g_loss).to(ctx.in_dtype), None, None, None, None, None
 
 
-def sparse_cross_entropy(logits_lowres, y, queries, ignore_index, size=None, return_pred=False):
+def labelled_pixel_list_host(y, queries, ignore_index, capacity=None):
+    """Host-side (NumPy) version for CPU batches straight from the dataloader: no device sync, optional padding to a
+    fixed `capacity` (CUDA graphs).  Returns (px_img, px_idx, px_label, n_valid) as int32 CPU tensors."""
+    import numpy as np
+    yn = y.numpy() if isinstance(y, torch.Tensor) else np.asarray(y)
+    B = yn.shape[0]
+    yf = yn.reshape(B, -1)
+    keep = yf != ignore_index
+    if queries is not None:
+        qn = queries.numpy() if isinstance(queries, torch.Tensor) else np.asarray(queries)
+        keep &= qn.reshape(B, -1).astype(bool)
+    img, idx = np.nonzero(keep)
+    lab = yf[img, idx]
+    n = img.size
+    cap = n if capacity is None else capacity
+    if n > cap:
+        raise _lib.PixelPickError(f"{n} labelled pixels exceed the captured capacity {cap}")
+    out = [np.zeros(cap, dtype=np.int32) for _ in range(3)]
+    out[0][:n], out[1][:n], out[2][:n] = img, idx, lab
+    return tuple(torch.from_numpy(a) for a in out) + (torch.tensor([n], dtype=torch.int32),)
+
+
+def sparse_cross_entropy(logits_lowres, y, queries, ignore_index, size=None, return_pred=False, px=None, n_valid=None):
     """== F.cross_entropy(F.interpolate(logits_lowres, size, 'bilinear', align_corners=True), y*, ignore_index)
-    with y* = y where queries else ignore_index.  NaN when no pixel is labelled (as the reference)."""
-    size = tuple(y.shape[-2:]) if size is None else tuple(size)
-    px = labelled_pixel_list(y, queries, ignore_index)
-    loss, pred = _SparseCE.apply(logits_lowres, size, *px)
+    with y* = y where queries else ignore_index.  NaN when no pixel is labelled (as the reference).
+    px = (px_img, px_idx, px_label) device lists may be given instead of (y, queries) (+ n_valid: device int32 [1])."""
+    if px is None:
+        size = tuple(y.shape[-2:]) if size is None else tuple(size)
+        px = labelled_pixel_list(y, queries, ignore_index)
+    loss, pred = _SparseCE.apply(logits_lowres, tuple(size), px[0], px[1], px[2], n_valid)
     if return_pred:
         return loss, pred, px
     return loss

@@ -35,6 +35,7 @@ ref_loss = orc.sparse_ce_loss(pred, y, q, 19); ref_loss.backward()
 # ours
 hg, lg = high.to(DEV).requires_grad_(True), low.to(DEV).requires_grad_(True)
 pre = m._pooled_branch(hg)
+m._rng_step = torch.zeros(1, dtype=torch.int64, device=DEV)
 out = _HeadFn.apply(m, 1, hg, lg, pre, *m._head_params())
 loss = sparse_cross_entropy(out, y.to(DEV), q.to(DEV), 19); loss.backward()
 print("loss", loss.item(), ref_loss.item(), "lowres rel", ((out.detach().cpu() - pred_lr.detach()).abs().max() / pred_lr.abs().max()).item())

@@ -175,7 +175,7 @@ def test_reference_style_call_through_full_resolution_pred():
     loss.backward()
     g1 = m.seg_head.classifier.weight.grad.clone()
     m.zero_grad()
-    m._step -= 1
+    m._rng_step -= 1
     for mod in m.modules():
         if isinstance(mod, nn.BatchNorm2d):
             mod.momentum = 0.0  # keep running stats fixed for the second pass
@@ -189,9 +189,10 @@ def test_dropout_is_reproducible_per_step_and_scales():
     m, _ = _model("mobilenet", 1)
     m.train()
     x = _x(4, (2, 3, 64, 64)).to(DEV)
-    m._step = 7
+    m.forward_lowres(x)  # creates the device-side step counter
+    m._rng_step.fill_(7)
     a = m.forward_lowres(x).detach().clone()
-    m._step = 7
+    m._rng_step.fill_(7)
     b = m.forward_lowres(x).detach().clone()
     c = m.forward_lowres(x).detach()
     # same step -> same Philox masks (float atomics in the BN statistics leave ~1e-3 noise); next step -> new masks

@@ -10,10 +10,16 @@ STRATS = ["entropy", "least_confidence", "margin_sampling"]
 CASES = [11, 19, 21]
 
 
+def _t(a):
+    """torch-allocated (64-byte aligned) copy: torch's vectorised CPU kernels peel unaligned heads with scalar code, so
+    bit-exact comparisons must not depend on NumPy's 16-byte malloc alignment of the .npz arrays."""
+    return torch.from_numpy(a).clone()
+
+
 @pytest.mark.parametrize("C", CASES)
 @pytest.mark.parametrize("strat", STRATS)
 def test_scores_bit_exact(golden, C, strat):
-    logits = torch.from_numpy(golden[f"logits_c{C}"])
+    logits = _t(golden[f"logits_c{C}"])
     got = orc.uncertainty(orc.probabilities(logits), strat).numpy()
     assert np.array_equal(got, golden[f"scores_{strat}_c{C}"], equal_nan=True)
 
@@ -21,7 +27,7 @@ def test_scores_bit_exact(golden, C, strat):
 @pytest.mark.parametrize("C", CASES)
 @pytest.mark.parametrize("strat", STRATS)
 def test_masked_scores_bit_exact(golden, C, strat):
-    logits = torch.from_numpy(golden[f"logits_c{C}"])
+    logits = _t(golden[f"logits_c{C}"])
     y, lab = golden[f"y_c{C}"], golden[f"lab_c{C}"]
     uc = orc.uncertainty(orc.probabilities(logits), strat)  # same batch shape as the golden run
     for i in range(2):
@@ -37,7 +43,7 @@ def test_masked_scores_bit_exact(golden, C, strat):
 @pytest.mark.parametrize("tag,kw", [("top5", dict(top_n_percent=0.05)), ("topn", dict(top_n_percent=0.0)),
                                     ("rev", dict(top_n_percent=0.05, reverse_order=True))])
 def test_select_queries_matches_reference(golden, C, strat, tag, kw):
-    uc = torch.from_numpy(golden[f"uc_{strat}_c{C}"])
+    uc = _t(golden[f"uc_{strat}_c{C}"])
     for topk in (orc.topk_indices_torch, orc.topk_indices_spec):
         np.random.seed(7)
         sel = np.stack([orc.select_queries(uc[i], strat, 10, topk=topk, **kw) for i in range(2)])
@@ -45,7 +51,7 @@ def test_select_queries_matches_reference(golden, C, strat, tag, kw):
 
 
 def test_entropy_nan_ranks_first(golden):
-    logits = torch.from_numpy(golden["logits_nan"])
+    logits = _t(golden["logits_nan"])
     uc = orc.uncertainty(orc.probabilities(logits), "entropy")
     assert np.array_equal(uc.numpy(), golden["scores_entropy_nan"], equal_nan=True)
     assert np.isnan(uc.numpy()).sum() >= 2
@@ -57,7 +63,7 @@ def test_entropy_nan_ranks_first(golden):
 
 @pytest.mark.parametrize("strat", STRATS)
 def test_query_call_end_to_end(golden, strat):
-    logits = torch.from_numpy(golden["call_logits"])
+    logits = _t(golden["call_logits"])
     y, lab = golden["call_y"], golden["call_lab"]
     np.random.seed(0)
     d = orc.query_images([logits[i:i + 1] for i in range(3)], strat, lab, y == 19,

@@ -116,3 +116,40 @@ def test_to_nhwc_bf16_layouts():
     xc = x.to(DEV).to(memory_format=torch.channels_last).to(torch.bfloat16)
     got2 = _lib.to_nhwc_bf16(xc)
     assert torch.equal(got2.cpu(), got.cpu())
+
+
+@pytest.mark.parametrize("act,C", [(0, 24), (1, 256), (2, 144), (2, 960)])
+def test_fused_bn_act_module_matches_torch(act, C):
+    """Encoder BatchNorm(+ReLU/ReLU6) on the NHWC kernels vs nn.BatchNorm2d + activation (fp32, CPU)."""
+    from pixelpick_b200.deeplab import FusedBNAct
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn((3, C, 12, 20), generator=g) * 2 + 1).to(torch.bfloat16)
+    go = torch.randn((3, C, 12, 20), generator=g).to(torch.bfloat16)
+    ref_bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        ref_bn.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        ref_bn.bias.copy_(torch.randn(C, generator=g) * 0.3)
+    m = FusedBNAct(C, act=act)
+    m.load_state_dict(ref_bn.state_dict())
+    m = m.to(DEV)
+    xr = x.float().requires_grad_(True)
+    yr = ref_bn(xr)
+    yr = F.relu(yr) if act == 1 else (F.relu6(yr) if act == 2 else yr)
+    yr.backward(go.float())
+    xg = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = m(xg)
+    y.backward(go.to(DEV))
+    assert y.dtype == torch.bfloat16 and y.shape == yr.shape
+    assert (y.float().cpu() - yr.detach()).abs().max().item() < 2e-2 * yr.abs().max().item()
+    assert (xg.grad.float().cpu() - xr.grad).abs().max().item() < 3e-2 * xr.grad.abs().max().item()
+    assert torch.allclose(m.weight.grad.cpu(), ref_bn.weight.grad, rtol=3e-2, atol=3e-2 * ref_bn.weight.grad.abs().max().item())
+    assert torch.allclose(m.bias.grad.cpu(), ref_bn.bias.grad, rtol=3e-2, atol=3e-2 * ref_bn.bias.grad.abs().max().item())
+    assert torch.allclose(m.running_mean.cpu(), ref_bn.running_mean, atol=1e-2)
+    assert torch.allclose(m.running_var.cpu(), ref_bn.running_var, rtol=2e-2, atol=1e-2)
+    assert int(m.num_batches_tracked) == 1
+    m.eval(); ref_bn.eval()
+    with torch.no_grad():
+        ye = m(x.to(DEV).contiguous(memory_format=torch.channels_last)).float().cpu()
+        yre = ref_bn(x.float())
+        yre = F.relu(yre) if act == 1 else (F.relu6(yre) if act == 2 else yre)
+    assert (ye - yre).abs().max().item() < 2e-2 * yre.abs().max().item()
