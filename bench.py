@@ -43,7 +43,7 @@ STRATEGY = "margin_sampling"
 TOP_N_PERCENT, N_SEL = 0.05, 10
 K_TOP = int(H * W * TOP_N_PERCENT)
 ALG_BYTES_PER_PX = C * 4 + 2  # logits + labelled mask + void mask
-WORKLOAD = f"cityscapes 256x512 C={C} {STRATEGY} top-5% (k={K_TOP}) n={N_SEL}: logits -> score -> top-k -> picks"
+WORKLOAD = f"cityscapes 256x512 C={C} {STRATEGY} top-5% (k={K_TOP}) n={N_SEL}: logits -> score -> top-k select -> n random ranks"
 MARGS = Namespace(use_mc_dropout=False, mc_dropout_p=0.2, n_classes=C)
 OPT = {"lr": 5e-4, "weight_decay": 2e-4}  # args.py:101-106 (cs)
 
@@ -397,8 +397,7 @@ def bench_query_model(backbone, n_img, steps, dev, from_host):
             lr = model.forward_lowres(x)
             ws.prepare()
             score = _lib.acq_score_upsampled(lr, (H, W), STRATEGY, q, v, hist0_ws=ws)
-            topk = _lib.acq_topk(score.view(n_img, -1), K_TOP, False, ws=ws, hist0_valid=True)
-            sel = _lib.acq_gather(topk, pos)
+            sel = _lib.acq_select_pick(score.view(n_img, -1), K_TOP, False, pos, ws=ws, hist0_valid=True)
             if from_host:
                 out_host.copy_(sel)
         return sel
@@ -425,6 +424,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=64, help="images per step per GPU (host-buffer query leg)")
     ap.add_argument("--train-batch", type=int, default=32, help="throughput batch of the train leg (per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sorted-topk", action="store_true", help="query step materialises the sorted top-k list (pp_acq_topk)")
     ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -477,8 +477,11 @@ def main():
         _lib.acq_score(logits, STRATEGY, lab, void, out=score, hist0_ws=ws)
         if i is not None:
             ev_b[i].record()
-        topk = _lib.acq_topk(score.view(B, HW), K_TOP, largest, ws=ws, hist0_valid=True)
-        sel = _lib.acq_gather(topk, pos)
+        if args.sorted_topk:  # materialise the whole sorted top-k list, then gather the drawn ranks
+            topk = _lib.acq_topk(score.view(B, HW), K_TOP, largest, ws=ws, hist0_valid=True)
+            sel = _lib.acq_gather(topk, pos)
+        else:  # what QuerySelector runs: only the n drawn ranks are needed (query.py:63-64) -> radix pick, no sort
+            sel = _lib.acq_select_pick(score.view(B, HW), K_TOP, largest, pos, ws=ws, hist0_valid=True)
         if world > 1:  # the path's one exchange: per-rank picks -> every rank (rank 0 builds the dict)
             dist.all_gather(gathered, sel)
         return sel
@@ -575,6 +578,7 @@ def main():
             "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_step_per_gpu": B, "e2e_images_per_step_per_gpu": Be,
+                       "selection": "sorted top-k list + gather" if args.sorted_topk else "radix select + order statistics at the drawn ranks (no sort; identical picks)",
                        "l2": f"inputs larger than L2 ({B * C * HW * 4 / 1e6:.0f} MB of logits per step)",
                        "parallelism": f"images sharded over {world} rank(s); all_gather of picks" if world > 1 else "single GPU"},
             "roofline": {"kernel": "acq_score_vec_kernel<19, margin, f32, fused hist0>", "bound": "hbm",

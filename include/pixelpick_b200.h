@@ -94,6 +94,16 @@ int pp_acq_topk(const float* score_map, int n_img, int HW, int k, int largest, i
                 int32_t* topk_idx, float* topk_val,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same selection WITHOUT the sort, for callers that only need a few ranks of the sorted list — which is all
+ * `np.random.choice(ind_queries, n, False)` (query.py:63-64) reads.  pp_acq_select leaves the k selected (unsorted)
+ * composites in the workspace; pp_acq_pick returns out[i, j] = flat index of the element of rank pos[i, j] (0-based, in
+ * the order contract above; pos == NULL means ranks 0..n-1) by a radix walk over the k candidates: O(k), bit-identical
+ * to topk_idx[i, pos[i, j]]. */
+int pp_acq_select(const float* score_map, int n_img, int HW, int k, int largest, int hist0_valid, void* workspace,
+                  size_t workspace_bytes, void* stream);
+int pp_acq_pick(void* workspace, size_t workspace_bytes, int n_img, int HW, int k, const int32_t* pos, int n,
+                int32_t* out, void* stream);
+
 /* out[i, j] = topk_idx[i, pos[i, j]] — the device half of
  *   np.random.choice(ind_queries, n_pixels_by_us, False)                       query.py:63-64
  * (the host draws pos = np.random.permutation(k)[:n] from the global NumPy stream). */

@@ -38,6 +38,8 @@ _SIGNATURES = {
     "pp_acq_topk_prepare": ([_vp, _sz, _i, _i, _i, _vp], _i),
     "pp_acq_topk_hist0": ([_vp], _vp),
     "pp_acq_topk": ([_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp], _i),
+    "pp_acq_select": ([_vp, _i, _i, _i, _i, _i, _vp, _sz, _vp], _i),
+    "pp_acq_pick": ([_vp, _sz, _i, _i, _i, _vp, _i, _vp, _vp], _i),
     "pp_acq_gather": ([_vp, _i, _i, _vp, _i, _vp, _vp], _i),
     "pp_acq_entropy_at": ([_vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _i, _vp, _vp], _i),
     "pp_acq_entropy_at_upsampled": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp], _i),
@@ -191,6 +193,29 @@ def acq_topk(score_map, k, largest, ws=None, hist0_valid=False, return_values=Fa
     check(lib().pp_acq_topk(_ptr(sm), n, HW, k, int(bool(largest)), int(bool(hist0_valid)), _ptr(idx), _ptr(val),
                             _ptr(ws.buf), ws.nbytes, _stream(sm)), "pp_acq_topk")
     return (idx, val) if return_values else idx
+
+
+def acq_select_pick(score_map, k, largest, pos, n=None, ws=None, hist0_valid=False):
+    """flat indices [n_img, n] of the elements at ranks `pos` ([n_img, n] int32, or None for ranks 0..n-1) of the sorted
+    top-k list — without sorting it (pp_acq_select + pp_acq_pick).  Equals acq_gather(acq_topk(...), pos)."""
+    _need_cuda(score_map)
+    n_img = score_map.shape[0]
+    sm = score_map.reshape(n_img, -1)
+    if not sm.is_contiguous() or sm.dtype != torch.float32:
+        sm = sm.float().contiguous()
+    HW = sm.shape[1]
+    if ws is None:
+        ws = TopKWorkspace(n_img, HW, k, sm.device)
+        ws.prepare()
+        hist0_valid = False
+    if pos is not None:
+        pos = pos.to(device=sm.device, dtype=torch.int32).contiguous()
+        n = pos.shape[1]
+    out = torch.empty((n_img, n), dtype=torch.int32, device=sm.device)
+    check(lib().pp_acq_select(_ptr(sm), n_img, HW, k, int(bool(largest)), int(bool(hist0_valid)), _ptr(ws.buf), ws.nbytes,
+                              _stream(sm)), "pp_acq_select")
+    check(lib().pp_acq_pick(_ptr(ws.buf), ws.nbytes, n_img, HW, k, _ptr(pos), n, _ptr(out), _stream(sm)), "pp_acq_pick")
+    return out
 
 
 def acq_gather(topk_idx, pos):

@@ -420,6 +420,7 @@ struct SelParams {
   const SelState* state_cur;
   SelState* state_next;
   int level, n_img, HW, k, kpad, largest;
+  int build_next_hist;  // 0: the single-CTA tail kernel builds its own histograms (no merge atomics here)
 };
 
 // standalone level-0 histogram (used when pp_acq_score did not fuse it)
@@ -522,6 +523,7 @@ __global__ void __launch_bounds__(kSelThreads) select_level_kernel(const SelPara
   uint64_t* ol = p.out_list + (size_t)img * p.HW;
   const bool largest = p.largest != 0;
   bool any_filt = false;
+  const bool vec4 = L0 && (p.HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.scores) & 15) == 0);
 
   for (uint32_t tile = blockIdx.x; (uint64_t)tile * kSelTile < n_in; tile += gridDim.x) {
     uint64_t comp[kSelItems];
@@ -529,28 +531,48 @@ __global__ void __launch_bounds__(kSelThreads) select_level_kernel(const SelPara
     uint32_t nc = 0, nf = 0;
     // all loads of the tile are issued before the first use (predicated, no branch): one memory round trip per
     // tile instead of kSelItems serialised ones
+    uint32_t idxs[kSelItems];
     if (L0) {
-      float sv[kSelItems];
+      if (vec4) {
+        // 4 x 16-byte loads per thread, all issued before the first use (asm volatile keeps them batched: with scalar
+        // __ldg the compiler serialised load->use pairs, i.e. 16 memory round trips per tile)
+        float4 q[4];
 #pragma unroll
-      for (int i = 0; i < kSelItems; ++i) {
-        const uint32_t idx = tile * kSelTile + i * kSelThreads + tid;
-        sv[i] = (idx < n_in) ? __ldg(sc + (idx < n_in ? idx : 0u)) : 0.f;
-      }
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t base = tile * kSelTile + (j * kSelThreads + tid) * 4;
+          q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (base < n_in) q[j] = ldg_stream_f4(sc + base);
+        }
 #pragma unroll
-      for (int i = 0; i < kSelItems; ++i) {
-        const uint32_t idx = tile * kSelTile + i * kSelThreads + tid;
-        comp[i] = ((uint64_t)ord_key(sv[i], largest) << 32) | idx;
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t base = tile * kSelTile + (j * kSelThreads + tid) * 4;
+          const float e4[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            idxs[j * 4 + e] = base + e;
+            comp[j * 4 + e] = ((uint64_t)ord_key(e4[e], largest) << 32) | (base + e);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kSelItems; ++i) {
+          const uint32_t idx = tile * kSelTile + i * kSelThreads + tid;
+          idxs[i] = idx;
+          const float v = (idx < n_in) ? __ldg(sc + (idx < n_in ? idx : 0u)) : 0.f;
+          comp[i] = ((uint64_t)ord_key(v, largest) << 32) | idx;
+        }
       }
     } else {
 #pragma unroll
       for (int i = 0; i < kSelItems; ++i) {
         const uint32_t idx = tile * kSelTile + i * kSelThreads + tid;
+        idxs[i] = idx;
         comp[i] = (idx < n_in) ? il[idx < n_in ? idx : 0u] : ~0ull;
       }
     }
 #pragma unroll
     for (int i = 0; i < kSelItems; ++i) {
-      const uint32_t idx = tile * kSelTile + i * kSelThreads + tid;
+      const uint32_t idx = idxs[i];
       if (idx < n_in) {
         const uint32_t d = (uint32_t)(comp[i] >> shift) & dmask;
         if (d < bucket || (d == bucket && take_all)) {
@@ -597,8 +619,10 @@ __global__ void __launch_bounds__(kSelThreads) select_level_kernel(const SelPara
         ++oc;
       } else if (c2 == 2u) {
         ol[of++] = comp[i];
-        atomicAdd(&sh_hist[(uint32_t)(comp[i] >> shift_n) & dmask_n], 1u);
-        any_filt = true;
+        if (p.build_next_hist) {
+          atomicAdd(&sh_hist[(uint32_t)(comp[i] >> shift_n) & dmask_n], 1u);
+          any_filt = true;
+        }
       }
     }
   }
@@ -611,11 +635,196 @@ __global__ void __launch_bounds__(kSelThreads) select_level_kernel(const SelPara
   }
 }
 
+// Levels 1..4 for one image in ONE CTA: the boundary bucket of level 0 is small (L2-resident), so the remaining
+// radix levels (histogram in shared memory -> pick -> partition) run back to back without further launches or
+// global histogram traffic.  Appends are warp-aggregated shared-memory atomics; order is irrelevant (sorted later).
+constexpr int kRestThreads = 1024;
+struct RestParams {
+  uint64_t* list_a;        // [n_img][HW] boundary list written by level 0
+  uint64_t* list_b;        // [n_img][HW] scratch
+  const uint32_t* count_a; // [n_img]
+  uint64_t* cand;
+  uint32_t* cand_count;
+  const SelState* state1;  // {remaining, done} after level 0
+  int HW, kpad;
+};
+
+__global__ void __launch_bounds__(kRestThreads) select_rest_kernel(const RestParams p) {
+  __shared__ uint32_t sh_hist[kHistBins];
+  __shared__ uint32_t sh_warp[kRestThreads / 32];
+  __shared__ uint32_t sh_pick[3];
+  __shared__ uint32_t sh_cnt[2];  // cand count, next-list count
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const SelState st = p.state1[img];
+  if (st.done) return;
+  uint32_t rem = st.remaining;
+  uint64_t* in = p.list_a + (size_t)img * p.HW;
+  uint64_t* out = p.list_b + (size_t)img * p.HW;
+  uint64_t* cand = p.cand + (size_t)img * p.kpad;
+  uint32_t n = p.count_a[img];
+  if (tid == 0) sh_cnt[0] = p.cand_count[img];
+  for (int level = 1; level < kLevels; ++level) {
+    const int shift = c_shift[level];
+    const uint32_t dmask = (1u << c_bits[level]) - 1u;
+    for (int i = tid; i < kHistBins; i += kRestThreads) sh_hist[i] = 0;
+    if (tid == 0) sh_cnt[1] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += kRestThreads) atomicAdd(&sh_hist[(uint32_t)(in[i] >> shift) & dmask], 1u);
+    __syncthreads();
+    // pick: thread t owns bins 2t, 2t+1
+    const uint32_t h0 = sh_hist[2 * tid], h1 = sh_hist[2 * tid + 1];
+    uint32_t incl = h0 + h1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) sh_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += sh_warp[w];
+    uint32_t run = wbase + incl - (h0 + h1);
+    if (run < rem && rem <= run + h0) { sh_pick[0] = 2 * tid; sh_pick[1] = run; sh_pick[2] = h0; }
+    run += h0;
+    if (run < rem && rem <= run + h1) { sh_pick[0] = 2 * tid + 1; sh_pick[1] = run; sh_pick[2] = h1; }
+    __syncthreads();
+    const uint32_t bucket = sh_pick[0];
+    rem -= sh_pick[1];
+    const bool take_all = (sh_pick[2] == rem);
+    // partition
+    for (uint32_t base = 0; base < n; base += kRestThreads) {
+      const uint32_t i = base + tid;
+      uint64_t v = 0;
+      int cls = 0;
+      if (i < n) {
+        v = in[i];
+        const uint32_t d = (uint32_t)(v >> shift) & dmask;
+        if (d < bucket || (d == bucket && take_all)) cls = 1;
+        else if (d == bucket) cls = 2;
+      }
+      const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, cls == 1);
+      const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, cls == 2);
+      uint32_t b1 = 0, b2 = 0;
+      if (lane == 0) {
+        if (m1) b1 = atomicAdd(&sh_cnt[0], __popc(m1));
+        if (m2) b2 = atomicAdd(&sh_cnt[1], __popc(m2));
+      }
+      b1 = __shfl_sync(0xFFFFFFFFu, b1, 0);
+      b2 = __shfl_sync(0xFFFFFFFFu, b2, 0);
+      const uint32_t lt = (1u << lane) - 1u;
+      if (cls == 1) {
+        const uint32_t pos = b1 + __popc(m1 & lt);
+        if (pos < (uint32_t)p.kpad) cand[pos] = v;
+      } else if (cls == 2) {
+        out[b2 + __popc(m2 & lt)] = v;
+      }
+    }
+    __syncthreads();
+    if (take_all) break;
+    n = sh_cnt[1];
+    uint64_t* t = in; in = out; out = t;
+    __syncthreads();
+  }
+  if (tid == 0) p.cand_count[img] = sh_cnt[0];
+}
+
+// Order statistics instead of a sort: the reference draws n random RANKS of the sorted top-k list
+// (np.random.choice(ind_queries, n, False), query.py:63-64), so only the elements at those ranks are needed.
+// One CTA per image runs the same 5-level radix walk for up to kPickRanks ranks at once over the k unsorted
+// composites: rank j keeps (prefix_j, rem_j); every level histograms the elements matching prefix_j by their next
+// digit, then narrows.  Composites are unique, so after the last level prefix_j IS the element of rank j.  O(5 k).
+constexpr int kPickThreads = 512;
+constexpr int kPickRanks = 12;  // 12 x 2048 x 4 B = 96 KB of histograms
+
+struct PickParams {
+  const uint64_t* cand;  // [n_img][kpad]
+  int kpad, k, n;
+  const int32_t* pos;    // [n_img][n] ranks (nullptr: 0..n-1)
+  int32_t* out;          // [n_img][n]
+};
+
+__global__ void __launch_bounds__(kPickThreads) pick_ranks_kernel(const PickParams p) {
+  extern __shared__ uint32_t sh_h[];  // [kPickRanks][2048]
+  __shared__ uint64_t sh_prefix[kPickRanks];
+  __shared__ uint32_t sh_rem[kPickRanks];
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t* c = p.cand + (size_t)img * p.kpad;
+  for (int j0 = 0; j0 < p.n; j0 += kPickRanks) {
+    const int nr = (p.n - j0) < kPickRanks ? (p.n - j0) : kPickRanks;
+    if (tid < nr) {
+      sh_prefix[tid] = 0;
+      int r = p.pos ? p.pos[(size_t)img * p.n + j0 + tid] : (j0 + tid);
+      r = r < 0 ? 0 : (r >= p.k ? p.k - 1 : r);
+      sh_rem[tid] = (uint32_t)r + 1u;  // 1-based rank inside the current bucket
+    }
+    for (int level = 0; level < kLevels; ++level) {
+      const int shift = c_shift[level];
+      const int bits = c_bits[level];
+      const uint32_t dmask = (1u << bits) - 1u;
+      const int nh = (level == 0) ? 1 : nr;  // level 0: every rank shares the empty prefix
+      for (int i = tid; i < nh * kHistBins; i += kPickThreads) sh_h[i] = 0;
+      __syncthreads();
+      uint64_t pre[kPickRanks];
+#pragma unroll
+      for (int j = 0; j < kPickRanks; ++j) pre[j] = (j < nr) ? sh_prefix[j] : 0;
+      const int hs = shift + bits;  // bits above this position form the prefix
+      for (int i = tid; i < p.k; i += kPickThreads) {
+        const uint64_t v = c[i];
+        const uint32_t d = (uint32_t)(v >> shift) & dmask;
+        if (level == 0) {
+          atomicAdd(&sh_h[d], 1u);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kPickRanks; ++j)
+            if (j < nr && ((v ^ pre[j]) >> hs) == 0) atomicAdd(&sh_h[j * kHistBins + d], 1u);
+        }
+      }
+      __syncthreads();
+      // warp j narrows rank j: find the bin holding the rem-th element (64 bins per lane)
+      for (int j = warp; j < nr; j += kPickThreads / 32) {
+        const uint32_t* h = sh_h + (level == 0 ? 0 : j * kHistBins);
+        const uint32_t rem = sh_rem[j];
+        uint32_t mine = 0;
+        for (int b = 0; b < 64; ++b) mine += h[lane * 64 + b];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        uint32_t run = incl - mine;
+        const bool here = run < rem && rem <= incl;
+        int found = -1;
+        uint32_t before = 0;
+        if (here) {
+          for (int b = 0; b < 64; ++b) {
+            const uint32_t hb = h[lane * 64 + b];
+            if (run < rem && rem <= run + hb) { found = lane * 64 + b; before = run; break; }
+            run += hb;
+          }
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, found >= 0);
+        const int src = __ffs(m) - 1;
+        found = __shfl_sync(0xFFFFFFFFu, found, src);
+        before = __shfl_sync(0xFFFFFFFFu, before, src);
+        if (lane == 0) {
+          sh_prefix[j] |= (uint64_t)(uint32_t)found << shift;
+          sh_rem[j] = rem - before;
+        }
+      }
+      __syncthreads();
+    }
+    if (tid < nr) p.out[(size_t)img * p.n + j0 + tid] = (int32_t)(uint32_t)(sh_prefix[tid] & 0xFFFFFFFFull);
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // bitonic sort of the selected composites
 // ------------------------------------------------------------------------------------------
 constexpr int kSortThreads = 1024;
-constexpr int kSortChunkMax = 16384;  // 128 KB of shared memory
 
 struct SortParams {
   uint64_t* cand;  // [n_img][kpad]
@@ -926,9 +1135,23 @@ static bool dispatch_up(const ScoreUpParams& p, dim3 grid, cudaStream_t st) {
   }
 }
 
+static int select_impl(const float* score_map, int n_img, int HW, int k, int largest, int hist0_valid,
+                       void* workspace, size_t workspace_bytes, cudaStream_t st);
+static int sort_impl(const Workspace& w, int n_img, int k, int largest, int32_t* topk_idx, float* topk_val,
+                     cudaStream_t st);
+
 static int topk_impl(const float* score_map, int n_img, int HW, int k, int largest, int hist0_valid,
                      int32_t* topk_idx, float* topk_val, void* workspace, size_t workspace_bytes,
                      cudaStream_t st) {
+  int rc = select_impl(score_map, n_img, HW, k, largest, hist0_valid, workspace, workspace_bytes, st);
+  if (rc != PP_OK) return rc;
+  Workspace w = carve(workspace, n_img, HW, k);
+  return sort_impl(w, n_img, k, largest, topk_idx, topk_val, st);
+}
+
+// phase 1: leaves exactly k unsorted composites per image in the workspace candidate list
+static int select_impl(const float* score_map, int n_img, int HW, int k, int largest, int hist0_valid,
+                       void* workspace, size_t workspace_bytes, cudaStream_t st) {
   Workspace w = carve(workspace, n_img, HW, k);
   if (workspace_bytes < w.total_bytes) {
     set_error("workspace too small: %zu < %zu", workspace_bytes, w.total_bytes);
@@ -940,45 +1163,51 @@ static int topk_impl(const float* score_map, int n_img, int HW, int k, int large
     hist0_kernel<<<dim3(gx, n_img), kSelThreads, 0, st>>>(score_map, w.hist, HW, largest);
     PP_LAUNCH_CHECK();
   }
-  for (int L = 0; L < kLevels; ++L) {
+  {
     SelParams p;
     p.scores = score_map;
-    p.in_list = w.filt + (size_t)((L + 1) & 1) * n_img * HW;
-    p.in_count = w.filt_count + (size_t)((L + 1) & 1) * n_img;
-    p.out_list = w.filt + (size_t)(L & 1) * n_img * HW;
-    p.out_count = w.filt_count + (size_t)(L & 1) * n_img;
+    p.in_list = nullptr;
+    p.in_count = nullptr;
+    p.out_list = w.filt;  // boundary bucket of level 0
+    p.out_count = w.filt_count;
     p.cand = w.cand;
     p.cand_count = w.cand_count;
-    p.hist_cur = w.hist + (size_t)L * n_img * kHistBins;
-    p.hist_next = w.hist + (size_t)((L + 1) % kLevels) * n_img * kHistBins;  // unused at the last level
-    p.state_cur = w.state + (size_t)L * n_img;
-    p.state_next = w.state + (size_t)(L + 1) * n_img;
-    p.level = L;
+    p.hist_cur = w.hist;
+    p.hist_next = w.hist + (size_t)n_img * kHistBins;
+    p.state_cur = w.state;
+    p.state_next = w.state + (size_t)n_img;
+    p.level = 0;
     p.n_img = n_img;
     p.HW = HW;
     p.k = k;
     p.kpad = w.kpad;
     p.largest = largest;
-    if (L == 0) {
-      // each CTA walks ~4 tiles so the bucket-pick prologue (2048-bin scan) is amortised
-      int gx = (tiles + 3) / 4;
-      const int cap = (148 * 16 + n_img - 1) / n_img;
-      if (gx > cap) gx = cap;
-      if (gx < 1) gx = 1;
-      select_level_kernel<true><<<dim3(gx, n_img), kSelThreads, 0, st>>>(p);
-    } else {
-      if (L >= 2) {
-        // out_count of this level is the ping-pong partner that level L-2 filled: re-zero it
-        PP_CUDA(cudaMemsetAsync(p.out_count, 0, (size_t)n_img * sizeof(uint32_t), st));
-      }
-      int cap = 592 / n_img;
-      if (cap < 8) cap = 8;
-      int gx = tiles < cap ? tiles : cap;
-      select_level_kernel<false><<<dim3(gx, n_img), kSelThreads, 0, st>>>(p);
-    }
+    p.build_next_hist = 0;
+    // each CTA walks ~4 tiles so the bucket-pick prologue (2048-bin scan) is amortised
+    int gx = (tiles + 3) / 4;
+    const int cap = (148 * 16 + n_img - 1) / n_img;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    select_level_kernel<true><<<dim3(gx, n_img), kSelThreads, 0, st>>>(p);
+    PP_LAUNCH_CHECK();
+    RestParams r;
+    r.list_a = w.filt;
+    r.list_b = w.filt + (size_t)n_img * HW;
+    r.count_a = w.filt_count;
+    r.cand = w.cand;
+    r.cand_count = w.cand_count;
+    r.state1 = w.state + (size_t)n_img;
+    r.HW = HW;
+    r.kpad = w.kpad;
+    select_rest_kernel<<<n_img, kRestThreads, 0, st>>>(r);
     PP_LAUNCH_CHECK();
   }
-  // sort
+  return PP_OK;
+}
+
+// phase 2a: full sort of the k composites
+static int sort_impl(const Workspace& w, int n_img, int k, int largest, int32_t* topk_idx, float* topk_val,
+                     cudaStream_t st) {
   SortParams sp;
   sp.cand = w.cand;
   sp.kpad = w.kpad;
@@ -1127,6 +1356,43 @@ int pp_acq_topk(const float* score_map, int n_img, int HW, int k, int largest, i
   PP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) % 256) == 0, "pp_acq_topk: workspace must be 256-B aligned");
   return topk_impl(score_map, n_img, HW, k, largest, hist0_valid, topk_idx, topk_val, workspace,
                    workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pp_acq_select(const float* score_map, int n_img, int HW, int k, int largest, int hist0_valid, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  PP_CHECK_ARG(score_map && workspace, "pp_acq_select: null pointer");
+  PP_CHECK_ARG(n_img > 0 && n_img <= 65535 && HW > 0 && k > 0 && k <= HW, "pp_acq_select: bad n_img=%d HW=%d k=%d", n_img, HW, k);
+  PP_CHECK_ARG(HW <= (1 << 22), "pp_acq_select: HW=%d exceeds 2^22", HW);
+  PP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) % 256) == 0, "pp_acq_select: workspace must be 256-B aligned");
+  return select_impl(score_map, n_img, HW, k, largest, hist0_valid, workspace, workspace_bytes,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pp_acq_pick(void* workspace, size_t workspace_bytes, int n_img, int HW, int k, const int32_t* pos, int n,
+                int32_t* out, void* stream) {
+  PP_CHECK_ARG(workspace && out, "pp_acq_pick: null pointer");
+  PP_CHECK_ARG(n_img > 0 && HW > 0 && k > 0 && k <= HW && n > 0 && n <= k, "pp_acq_pick: bad n_img=%d HW=%d k=%d n=%d", n_img, HW, k, n);
+  Workspace w = carve(workspace, n_img, HW, k);
+  if (workspace_bytes < w.total_bytes) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, w.total_bytes);
+    return PP_ERR_WORKSPACE;
+  }
+  static bool attr = false;
+  const int smem = kPickRanks * kHistBins * (int)sizeof(uint32_t);
+  if (!attr) {
+    PP_CUDA(cudaFuncSetAttribute(pick_ranks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  PickParams p;
+  p.cand = w.cand;
+  p.kpad = w.kpad;
+  p.k = k;
+  p.n = n;
+  p.pos = pos;
+  p.out = out;
+  pick_ranks_kernel<<<n_img, kPickThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
 }
 
 int pp_acq_gather(const int32_t* topk_idx, int n_img, int k, const int32_t* pos, int n, int32_t* out,

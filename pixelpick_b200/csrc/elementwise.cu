@@ -113,24 +113,27 @@ struct BnApplyParams {
   int ld_out, c_off_out;
 };
 __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParams p) {
+  // thread -> fixed 8-channel group (scale/shift live in registers), rows strided over the grid
   const int groups = p.C >> 3;
-  const int64_t total = p.M * groups;
+  const int rows_per_block = kEwThreads / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  if (r >= rows_per_block) return;
   const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
   const uint64_t seed = p.seed + ((p.drop_p > 0.f && p.seed_dev) ? *p.seed_dev : 0ull);
-  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kEwThreads) {
-    const int64_t row = i / groups;
-    const int g = (int)(i - row * groups);
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(p.scale + g * 8 + j);
+    sf[j] = __ldg(p.shift + g * 8 + j);
+  }
+  const int64_t stride = (int64_t)gridDim.x * rows_per_block;
+#pragma unroll 4
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_block + r; row < p.M; row += stride) {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.raw + row * p.ld_in + p.c_off_in + g * 8));
     float f[8];
     unpack8(v, f);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + g * 8));
-    const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + g * 8 + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.shift + g * 8));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.shift + g * 8 + 4));
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sf[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     uint32_t keep = 0xFFu;
-    if (p.drop_p > 0.f) keep = dropout_keep8(seed, p.offset, (uint64_t)i * 8, p.drop_p);
+    if (p.drop_p > 0.f) keep = dropout_keep8(seed, p.offset, (uint64_t)(row * groups + g) * 8, p.drop_p);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float y = fmaf(f[j], sc[j], sf[j]);
@@ -227,28 +230,32 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdPa
 }
 
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdParams p) {
+  // d_raw = scale * (g - mean(g) - xhat * mean(g xhat)) = A*g + B*x + K with per-channel A, B, K held in registers
   const int groups = p.C >> 3;
-  const int64_t total = p.M * groups;
+  const int rows_per_block = kEwThreads / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  if (r >= rows_per_block) return;
   const float inv_m = 1.f / (float)p.M;
   const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
   const uint64_t seed = p.seed + ((p.drop_p > 0.f && p.seed_dev) ? *p.seed_dev : 0ull);
-  for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kEwThreads) {
-    const int64_t row = i / groups;
-    const int g = (int)(i - row * groups);
-    float sc[8], sf[8], x[8], gg[8], o[8];
+  float sc[8], sf[8], cb[8], ck[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = __ldg(p.scale + g * 8 + j);
-      sf[j] = __ldg(p.shift + g * 8 + j);
-    }
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    sc[j] = __ldg(p.scale + c);
+    sf[j] = __ldg(p.shift + c);
+    const float mu = __ldg(p.mean + c), rs = __ldg(p.rstd + c);
+    const float mg = __ldg(p.sums + c) * inv_m, mgx = __ldg(p.sums + p.C + c) * inv_m;
+    cb[j] = -sc[j] * rs * mgx;
+    ck[j] = -sc[j] * (mg - mu * rs * mgx);
+  }
+  const int64_t stride = (int64_t)gridDim.x * rows_per_block;
+#pragma unroll 2
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_block + r; row < p.M; row += stride) {
+    float x[8], gg[8], o[8];
     bn_bwd_g8(p, seed, keep_scale, row, g, groups, sc, sf, x, gg);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      const float xh = (x[j] - __ldg(p.mean + c)) * __ldg(p.rstd + c);
-      const float mg = __ldg(p.sums + c) * inv_m, mgx = __ldg(p.sums + p.C + c) * inv_m;
-      o[j] = sc[j] * (gg[j] - mg - xh * mgx);
-    }
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[j], gg[j], fmaf(cb[j], x[j], ck[j]));
     *reinterpret_cast<uint4*>(p.draw + row * p.C + g * 8) = pack8(o);
   }
 }
@@ -375,15 +382,20 @@ int pp_bn_apply(const void* raw, int64_t M, int ld_in, int c_off_in, int C, cons
                 int relu, float drop_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, void* out, int ld_out,
                 int c_off_out, void* stream) {
   PP_CHECK_ARG(raw && out && scale && shift && M > 0, "pp_bn_apply: bad args");
-  PP_CHECK_ARG(C % 8 == 0 && ld_in % 8 == 0 && c_off_in % 8 == 0 && ld_out % 8 == 0 && c_off_out % 8 == 0,
-               "pp_bn_apply: channel counts/offsets must be multiples of 8");
+  PP_CHECK_ARG(C % 8 == 0 && C <= 2048 && ld_in % 8 == 0 && c_off_in % 8 == 0 && ld_out % 8 == 0 && c_off_out % 8 == 0,
+               "pp_bn_apply: channel counts/offsets must be multiples of 8 (C <= 2048)");
   PP_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "pp_bn_apply: drop_p=%f", drop_p);
   BnApplyParams p;
   p.raw = reinterpret_cast<const __nv_bfloat16*>(raw);
   p.M = M; p.ld_in = ld_in; p.c_off_in = c_off_in; p.C = C; p.scale = scale; p.shift = shift; p.relu = relu;
   p.drop_p = drop_p; p.seed = seed; p.offset = offset; p.seed_dev = seed_dev;
   p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ld_out = ld_out; p.c_off_out = c_off_out;
-  bn_apply_kernel<<<ew_grid(M * (C / 8)), kEwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  {
+    const int rows_per_block = kEwThreads / (C / 8);
+    int64_t blocks = (M + rows_per_block * 4 - 1) / (rows_per_block * 4);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    bn_apply_kernel<<<(int)blocks, kEwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  }
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -408,7 +420,7 @@ int pp_bn_bwd(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_r
   if (blocks > 148 * 8) blocks = 148 * 8;
   bn_bwd_reduce_kernel<<<(int)blocks, kEwThreads, kEwThreads * 16 * sizeof(float), st>>>(p);
   PP_LAUNCH_CHECK();
-  bn_bwd_apply_kernel<<<ew_grid(M * (C / 8)), kEwThreads, 0, st>>>(p);
+  bn_bwd_apply_kernel<<<(int)blocks, kEwThreads, 0, st>>>(p);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

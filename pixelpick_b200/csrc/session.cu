@@ -102,9 +102,15 @@ int pp_acq_session_run_host(pp_acq_session* s, const float* h_logits, const uint
                       h_labelled ? sl.lab : nullptr, h_void ? sl.vd : nullptr, nullptr, strategy, sl.score,
                       pp_acq_topk_hist0(sl.ws), sl.st);
     if (rc != PP_OK) return rc;
-    rc = pp_acq_topk(sl.score, n, (int)HW, s->k, largest, 1, sl.topk, nullptr, sl.ws, s->ws_bytes, sl.st);
-    if (rc != PP_OK) return rc;
-    rc = pp_acq_gather(sl.topk, n, s->k, h_pos ? sl.pos : nullptr, s->n_sel, sl.sel, sl.st);
+    if (h_topk_idx) {  // the caller wants the whole sorted list: sort, then gather the picks from it
+      rc = pp_acq_topk(sl.score, n, (int)HW, s->k, largest, 1, sl.topk, nullptr, sl.ws, s->ws_bytes, sl.st);
+      if (rc != PP_OK) return rc;
+      rc = pp_acq_gather(sl.topk, n, s->k, h_pos ? sl.pos : nullptr, s->n_sel, sl.sel, sl.st);
+    } else {  // picks only: radix select + order statistics, no sort
+      rc = pp_acq_select(sl.score, n, (int)HW, s->k, largest, 1, sl.ws, s->ws_bytes, sl.st);
+      if (rc != PP_OK) return rc;
+      rc = pp_acq_pick(sl.ws, s->ws_bytes, n, (int)HW, s->k, h_pos ? sl.pos : nullptr, s->n_sel, sl.sel, sl.st);
+    }
     if (rc != PP_OK) return rc;
     PP_CUDA(cudaMemcpyAsync(h_sel_idx + (size_t)i0 * s->n_sel, sl.sel, (size_t)n * s->n_sel * sizeof(int32_t),
                             cudaMemcpyDeviceToHost, sl.st));

@@ -240,23 +240,21 @@ class QuerySelector:
         keep = None if keep_np is None else torch.from_numpy(keep_np).to(self.device)
         n_top = self.n_pixels_by_us if self.reverse_order else k
         largest = _lib.LARGEST[st]
+        pos_t = None if pos_np is None else torch.from_numpy(pos_np)
         if st == "random":
             uc = torch.stack([self.uncertainty_sampler(torch.empty(1, 1, h, w))[0] for _ in range(n)]).to(self.device)
             excl = labelled if void is None else (labelled | void)
             if keep is not None:
                 excl = excl | ~keep.view(n, h, w)
             uc[excl] = _lib.FILL[st]
-            topk = _lib.acq_topk(uc.view(n, hw), n_top, largest)
+            sel = _lib.acq_select_pick(uc.view(n, hw), n_top, largest, pos_t, n=self.n_pixels_by_us)
             handle = None
         else:
             ws = self._workspace(n, hw, n_top)
             ws.prepare()
             score, handle = self._score_batch(model, xs, h, w, labelled, void, keep, ws)
-            topk = _lib.acq_topk(score.view(n, hw), n_top, largest, ws=ws, hist0_valid=True)
-        if pos_np is not None:
-            sel = _lib.acq_gather(topk, torch.from_numpy(pos_np))
-        else:
-            sel = topk[:, : self.n_pixels_by_us]
+            # only the n drawn ranks of the sorted top-k are needed (query.py:63-64): radix pick, no sort
+            sel = _lib.acq_select_pick(score.view(n, hw), n_top, largest, pos_t, n=self.n_pixels_by_us, ws=ws, hist0_valid=True)
         sel, _ = torch.sort(sel.long(), dim=1)  # np.where order: row-major ascending (query.py:77)
         ent = None
         if stats_on and handle is not None:

@@ -307,3 +307,20 @@ def test_errors_are_loud():
         _lib.acq_score(torch.zeros(1, 19, 8, 8), "entropy")  # CPU tensor: no fallback
     with pytest.raises(_lib.PixelPickError):
         _lib.acq_topk(torch.zeros(1, 16, device=DEV), 17, True)  # k > HW
+
+
+@pytest.mark.parametrize("largest", [True, False])
+@pytest.mark.parametrize("n,hw,k,nsel", [(3, 768, 38, 10), (2, 131072, 6553, 10), (1, 172800, 8640, 10), (2, 1000, 1, 1),
+                                          (2, 999, 999, 30), (1, 2097152, 104857, 10), (4, 4096, 33, 13)])
+def test_pick_ranks_equals_sorted_topk_gather(n, hw, k, nsel, largest):
+    """pp_acq_select + pp_acq_pick (order statistics, no sort) == pp_acq_topk + pp_acq_gather, incl. heavy ties."""
+    g = torch.Generator().manual_seed(hw + k)
+    for scores in (torch.rand((n, hw), generator=g), (torch.randint(0, 5, (n, hw), generator=g).float() / 4.0)):
+        rs = np.random.RandomState(k)
+        pos = torch.from_numpy(np.stack([rs.permutation(k)[:nsel] for _ in range(n)]).astype(np.int32))
+        topk = _lib.acq_topk(scores.to(DEV), k, largest)
+        want = _lib.acq_gather(topk, pos)
+        got = _lib.acq_select_pick(scores.to(DEV), k, largest, pos)
+        assert torch.equal(got, want)
+        first = _lib.acq_select_pick(scores.to(DEV), k, largest, None, n=nsel)
+        assert torch.equal(first, topk[:, :nsel])
