@@ -744,6 +744,8 @@ struct PickParams {
   int32_t* out;          // [n_img][n]
 };
 
+constexpr int kPickItems = 16;  // candidates cached in registers when k <= 512 * 16
+
 __global__ void __launch_bounds__(kPickThreads) pick_ranks_kernel(const PickParams p) {
   extern __shared__ uint32_t sh_h[];  // [kPickRanks][2048]
   __shared__ uint64_t sh_prefix[kPickRanks];
@@ -751,8 +753,22 @@ __global__ void __launch_bounds__(kPickThreads) pick_ranks_kernel(const PickPara
   const int img = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t* c = p.cand + (size_t)img * p.kpad;
+  // the k candidates are read ONCE into registers (all loads in flight together) and reused by every level;
+  // larger k (e.g. 5 % of a 1024x2048 image) streams them from L2 at each level instead
+  const bool cached = p.k <= kPickThreads * kPickItems;
+  uint64_t reg[kPickItems];
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < kPickItems; ++i) {
+      const int idx = i * kPickThreads + tid;
+      reg[i] = (idx < p.k) ? c[idx < p.k ? idx : 0] : ~0ull;  // ~0 never matches a prefix below level 0's bucket
+    }
+  }
   for (int j0 = 0; j0 < p.n; j0 += kPickRanks) {
     const int nr = (p.n - j0) < kPickRanks ? (p.n - j0) : kPickRanks;
+    uint32_t alive = 0;
+#pragma unroll
+    for (int i = 0; i < kPickItems; ++i) alive |= (i * kPickThreads + tid < p.k) ? (1u << i) : 0u;
     if (tid < nr) {
       sh_prefix[tid] = 0;
       int r = p.pos ? p.pos[(size_t)img * p.n + j0 + tid] : (j0 + tid);
@@ -766,28 +782,53 @@ __global__ void __launch_bounds__(kPickThreads) pick_ranks_kernel(const PickPara
       const int nh = (level == 0) ? 1 : nr;  // level 0: every rank shares the empty prefix
       for (int i = tid; i < nh * kHistBins; i += kPickThreads) sh_h[i] = 0;
       __syncthreads();
-      uint64_t pre[kPickRanks];
+      // prefix of rank j above the current digit, pre-shifted so the per-element test is one 64-bit compare
+      const int hs = shift + bits;
+      uint64_t preh[kPickRanks];
 #pragma unroll
-      for (int j = 0; j < kPickRanks; ++j) pre[j] = (j < nr) ? sh_prefix[j] : 0;
-      const int hs = shift + bits;  // bits above this position form the prefix
-      for (int i = tid; i < p.k; i += kPickThreads) {
-        const uint64_t v = c[i];
+      for (int j = 0; j < kPickRanks; ++j) preh[j] = (j < nr) ? (sh_prefix[j] >> (hs & 63)) : ~0ull;
+      auto visit = [&](uint64_t v) -> bool {
         const uint32_t d = (uint32_t)(v >> shift) & dmask;
-        if (level == 0) {
-          atomicAdd(&sh_h[d], 1u);
-        } else {
+        const uint64_t vh = v >> (hs & 63);
+        bool any = false;
 #pragma unroll
-          for (int j = 0; j < kPickRanks; ++j)
-            if (j < nr && ((v ^ pre[j]) >> hs) == 0) atomicAdd(&sh_h[j * kHistBins + d], 1u);
+        for (int j = 0; j < kPickRanks; ++j)
+          if (vh == preh[j]) {
+            atomicAdd(&sh_h[j * kHistBins + d], 1u);
+            any = true;
+          }
+        return any;
+      };
+      if (cached && level == 0) {
+        // the selected candidates sit in a narrow score range, so their leading digit takes only a few values:
+        // aggregate equal digits inside the warp (match.any) and issue ONE shared-memory atomic per distinct digit
+#pragma unroll
+        for (int i = 0; i < kPickItems; ++i) {
+          const bool valid = i * kPickThreads + tid < p.k;
+          const uint32_t d = valid ? ((uint32_t)(reg[i] >> shift) & dmask) : 0xFFFFFFFFu;
+          const uint32_t m = __match_any_sync(0xFFFFFFFFu, d);
+          if (valid && lane == __ffs(m) - 1) atomicAdd(&sh_h[d], (uint32_t)__popc(m));
         }
+      } else if (cached) {
+        // an element that matches no rank's prefix at this level can never match again: drop it from later levels
+        uint32_t still = 0;
+#pragma unroll
+        for (int i = 0; i < kPickItems; ++i)
+          if ((alive >> i) & 1u) still |= visit(reg[i]) ? (1u << i) : 0u;
+        alive = still;
+      } else if (level == 0) {
+        for (int i = tid; i < p.k; i += kPickThreads) atomicAdd(&sh_h[(uint32_t)(c[i] >> shift) & dmask], 1u);
+      } else {
+        for (int i = tid; i < p.k; i += kPickThreads) visit(c[i]);
       }
       __syncthreads();
-      // warp j narrows rank j: find the bin holding the rem-th element (64 bins per lane)
+      // warp j narrows rank j: lane l owns bins [64 l, 64 l + 64); reads are rotated by the lane id so the 32 lanes
+      // hit 32 different banks
       for (int j = warp; j < nr; j += kPickThreads / 32) {
         const uint32_t* h = sh_h + (level == 0 ? 0 : j * kHistBins);
         const uint32_t rem = sh_rem[j];
         uint32_t mine = 0;
-        for (int b = 0; b < 64; ++b) mine += h[lane * 64 + b];
+        for (int b = 0; b < 64; ++b) mine += h[lane * 64 + ((b + lane) & 63)];
         uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
