@@ -212,11 +212,32 @@ int pp_bn_apply(const void* raw, int64_t M, int ld_in, int c_off_in, int C, cons
 int pp_bn_bwd(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_raw, int c_off_raw, int64_t M, int C,
               const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
               uint64_t seed, uint64_t offset, const uint64_t* seed_dev, float* sums, void* draw, void* stream);
-/* bilinear align_corners=True resize of bf16 NHWC into a channel slice, and its adjoint (f32 accumulate). */
+/* Residual variants for the ResNet bottleneck tail out = relu(bn3(conv3(.)) + identity) (resnet_models.py:88-92):
+ * res (bf16 [M][ld_res], channels 0..C) is added before the activation in ONE pass; the backward gates on
+ * bn(raw) + res and also returns dres = gated upstream gradient (bf16 [M][C]) = gradient wrt the identity branch. */
+int pp_bn_apply_res(const void* raw, int64_t M, int ld_in, int c_off_in, int C, const float* scale, const float* shift,
+                    int relu, float drop_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const void* res,
+                    int ld_res, void* out, int ld_out, int c_off_out, void* stream);
+int pp_bn_bwd_res(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_raw, int c_off_raw, int64_t M, int C,
+                  const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
+                  uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const void* res, int ld_res, void* dres,
+                  float* sums, void* draw, void* stream);
+/* bilinear align_corners=True resize of bf16 NHWC into a channel slice, and its adjoint (gather form: deterministic,
+ * grad_in f32 [N,h,w,C] fully overwritten). */
 int pp_upsample_nhwc_bf16(const void* in, int N, int h, int w, int C, int ld_in, void* out, int H, int W, int ld_out,
                           int c_off, void* stream);
 int pp_upsample_nhwc_bf16_bwd(const void* grad_out, int N, int H, int W, int ld, int c_off, int C, float* grad_in,
                               int h, int w, void* stream);
+/* Depthwise 3x3 convolution of the MobileNetV2 inverted residual (mobilenet_v2.py:33-35,46-48: groups = channels, no
+ * bias, padding 0 because fixed_padding (mobilenet_v2.py:15-21) padded the tensor explicitly), NHWC bf16, fp32
+ * accumulate.  x [N][Hi][Wi][C], w = the module's f32 [C][1][3][3], y / dy [N][Ho][Wo][C] with
+ * Ho = (Hi - 2*dil - 1)/stride + 1.  dgrad writes dx [N][Hi][Wi][C]; wgrad writes dw f32 [C][1][3][3]. */
+int pp_dwconv3x3_fwd(const void* x, const float* w, void* y, int N, int Hi, int Wi, int C, int stride, int dil,
+                     void* stream);
+int pp_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, int N, int Hi, int Wi, int C, int stride, int dil,
+                       void* stream);
+int pp_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, int Wi, int C, int stride, int dil,
+                       void* stream);
 /* f32 conv weight [Cout][Cin_total][kh][kw] (first Cin input channels) -> bf16 operand tensors of pp_conv_igemm:
  * fwd [taps][Cout_pad][Cin_pad] and/or dgrad [taps][Cin_rows][Cout_cols] (taps flipped); zero padded; either NULL. */
 int pp_pack_conv_weight(const float* w, int Cout, int Cin, int Cin_total, int taps, void* fwd, int Cout_pad,

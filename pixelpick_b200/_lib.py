@@ -55,6 +55,12 @@ _SIGNATURES = {
     "pp_bn_apply": ([_vp, _i64, _i, _i, _i, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i, _i, _vp], _i),
     "pp_bn_bwd": ([_vp, _i, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp,
                    _vp, _vp], _i),
+    "pp_bn_apply_res": ([_vp, _i64, _i, _i, _i, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i, _vp, _i, _i, _vp], _i),
+    "pp_bn_bwd_res": ([_vp, _i, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i,
+                       _vp, _vp, _vp, _vp], _i),
+    "pp_dwconv3x3_fwd": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "pp_dwconv3x3_dgrad": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "pp_dwconv3x3_wgrad": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "pp_upsample_nhwc_bf16": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp], _i),
     "pp_upsample_nhwc_bf16_bwd": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_pack_conv_weight": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp], _i),
@@ -386,28 +392,78 @@ def bn_finalize(sums, M, bn, Cpad=None, update_running=True):
     return out
 
 
-def bn_apply(raw, c_off_in, C, scale, shift, relu, out, c_off_out, drop_p=0.0, seed=0, offset=0, seed_dev=None):
-    _need_cuda(raw, out)
+def bn_apply(raw, c_off_in, C, scale, shift, relu, out, c_off_out, drop_p=0.0, seed=0, offset=0, seed_dev=None, res=None):
+    """out = dropout(act(raw * scale + shift [+ res])); res: bf16 [..., ld_res] residual added before the activation."""
+    _need_cuda(raw, out, res)
     ld_in, ld_out = raw.shape[-1], out.shape[-1]
     M = raw.numel() // ld_in
-    check(lib().pp_bn_apply(_ptr(raw), M, ld_in, c_off_in, C, _ptr(scale), _ptr(shift), int(relu), float(drop_p),
-                            int(seed), int(offset), _ptr(seed_dev), _ptr(out), ld_out, c_off_out, _stream(raw)),
-          "pp_bn_apply")
+    check(lib().pp_bn_apply_res(_ptr(raw), M, ld_in, c_off_in, C, _ptr(scale), _ptr(shift), int(relu), float(drop_p),
+                                int(seed), int(offset), _ptr(seed_dev), _ptr(res), res.shape[-1] if res is not None else 0,
+                                _ptr(out), ld_out, c_off_out, _stream(raw)), "pp_bn_apply")
     return out
 
 
 def bn_bwd(dy, c_off_dy, raw, c_off_raw, C, scale, shift, mean, rstd, relu, drop_p=0.0, seed=0, offset=0,
-           seed_dev=None):
-    """returns (draw bf16 [M, C], sums f32 [2, C] = (d beta, d gamma))."""
-    _need_cuda(dy, raw)
+           seed_dev=None, res=None):
+    """returns (draw bf16 [M, C], sums f32 [2, C] = (d beta, d gamma)) — plus dres bf16 [M, C] (gradient wrt the
+    residual that was added before the activation) when `res` is given."""
+    _need_cuda(dy, raw, res)
     ld_dy, ld_raw = dy.shape[-1], raw.shape[-1]
     M = raw.numel() // ld_raw
     draw = torch.empty((M, C), dtype=torch.bfloat16, device=raw.device)
     sums = torch.empty((2, C), dtype=torch.float32, device=raw.device)
-    check(lib().pp_bn_bwd(_ptr(dy), ld_dy, c_off_dy, _ptr(raw), ld_raw, c_off_raw, M, C, _ptr(scale), _ptr(shift),
-                          _ptr(mean), _ptr(rstd), int(relu), float(drop_p), int(seed), int(offset), _ptr(seed_dev),
-                          _ptr(sums), _ptr(draw), _stream(raw)), "pp_bn_bwd")
+    dres = torch.empty((M, C), dtype=torch.bfloat16, device=raw.device) if res is not None else None
+    check(lib().pp_bn_bwd_res(_ptr(dy), ld_dy, c_off_dy, _ptr(raw), ld_raw, c_off_raw, M, C, _ptr(scale), _ptr(shift),
+                              _ptr(mean), _ptr(rstd), int(relu), float(drop_p), int(seed), int(offset), _ptr(seed_dev),
+                              _ptr(res), res.shape[-1] if res is not None else 0, _ptr(dres),
+                              _ptr(sums), _ptr(draw), _stream(raw)), "pp_bn_bwd")
+    if res is not None:
+        return draw, sums, dres
     return draw, sums
+
+
+def _dw_out(Hi, Wi, stride, dil):
+    return (Hi - 2 * dil - 1) // stride + 1, (Wi - 2 * dil - 1) // stride + 1
+
+
+def _dw_check(x, w):
+    _need_cuda(x, w)
+    if x.dtype != torch.bfloat16 or not x.is_contiguous() or w.dtype != torch.float32 or not w.is_contiguous():
+        raise PixelPickError("depthwise conv: x must be contiguous bf16 NHWC and w contiguous f32 [C,1,3,3]")
+    if w.numel() != x.shape[-1] * 9:
+        raise PixelPickError("depthwise conv: weight does not match the channel count")
+
+
+def dwconv_fwd(x, w, stride, dil):
+    """valid depthwise 3x3 of bf16 NHWC x [N,Hi,Wi,C] with f32 w [C,1,3,3] -> bf16 [N,Ho,Wo,C]."""
+    _dw_check(x, w)
+    N, Hi, Wi, Cc = x.shape
+    Ho, Wo = _dw_out(Hi, Wi, stride, dil)
+    y = torch.empty((N, Ho, Wo, Cc), dtype=torch.bfloat16, device=x.device)
+    check(lib().pp_dwconv3x3_fwd(_ptr(x), _ptr(w), _ptr(y), N, Hi, Wi, Cc, stride, dil, _stream(x)), "pp_dwconv3x3_fwd")
+    return y
+
+
+def dwconv_dgrad(dy, w, in_hw, stride, dil):
+    _dw_check(dy, w)
+    N, Cc = dy.shape[0], dy.shape[-1]
+    Hi, Wi = in_hw
+    if tuple(dy.shape[1:3]) != _dw_out(Hi, Wi, stride, dil):
+        raise PixelPickError("depthwise dgrad: dy does not match the input size")
+    dx = torch.empty((N, Hi, Wi, Cc), dtype=torch.bfloat16, device=dy.device)
+    check(lib().pp_dwconv3x3_dgrad(_ptr(dy), _ptr(w), _ptr(dx), N, Hi, Wi, Cc, stride, dil, _stream(dy)), "pp_dwconv3x3_dgrad")
+    return dx
+
+
+def dwconv_wgrad(x, dy, stride, dil):
+    _need_cuda(x, dy)
+    N, Hi, Wi, Cc = x.shape
+    if tuple(dy.shape) != (N,) + _dw_out(Hi, Wi, stride, dil) + (Cc,) or not (x.is_contiguous() and dy.is_contiguous()) \
+            or x.dtype != torch.bfloat16 or dy.dtype != torch.bfloat16:
+        raise PixelPickError("depthwise wgrad: x / dy must be contiguous bf16 NHWC of matching sizes")
+    dw = torch.empty((Cc, 1, 3, 3), dtype=torch.float32, device=x.device)
+    check(lib().pp_dwconv3x3_wgrad(_ptr(x), _ptr(dy), _ptr(dw), N, Hi, Wi, Cc, stride, dil, _stream(x)), "pp_dwconv3x3_wgrad")
+    return dw
 
 
 def upsample_nhwc(x, out, c_off, C=None):
@@ -425,7 +481,7 @@ def upsample_nhwc_bwd(grad_out, c_off, C, in_hw):
     _need_cuda(grad_out)
     N, H, W, ld = grad_out.shape
     h, w = in_hw
-    gin = torch.zeros((N, h, w, C), dtype=torch.float32, device=grad_out.device)
+    gin = torch.empty((N, h, w, C), dtype=torch.float32, device=grad_out.device)
     check(lib().pp_upsample_nhwc_bf16_bwd(_ptr(grad_out), N, H, W, ld, c_off, C, _ptr(gin), h, w, _stream(grad_out)),
           "pp_upsample_nhwc_bf16_bwd")
     return gin

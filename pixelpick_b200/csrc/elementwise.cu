@@ -58,6 +58,15 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 constexpr int kEwThreads = 256;
 
+// 16-byte read-only streaming load (no L1 allocation: every activation byte is touched once per pass)
+__device__ __forceinline__ uint4 ldg_stream_u4(const __nv_bfloat16* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
 // ---- BN statistics -------------------------------------------------------------------------
 // sums[0][c] += sum_rows raw, sums[1][c] += sum_rows raw^2   (fp32, caller zeroes)
 __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const __nv_bfloat16* __restrict__ raw, int64_t M, int ld,
@@ -70,9 +79,11 @@ __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const __nv_bfloat1
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (r < rows_per_block) {
-#pragma unroll 4
-    for (int64_t row = (int64_t)blockIdx.x * rows_per_block + r; row < M; row += (int64_t)gridDim.x * rows_per_block) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(raw + row * ld + c_off + g * 8));
+    // 4 independent 16-byte loads in flight per thread (the bounds check of a plain strided loop serialises them)
+    const int64_t stride = (int64_t)gridDim.x * rows_per_block;
+    const __nv_bfloat16* base = raw + c_off + g * 8;
+    int64_t row = (int64_t)blockIdx.x * rows_per_block + r;
+    auto acc8 = [&](const uint4& v) {
       float f[8];
       unpack8(v, f);
 #pragma unroll
@@ -80,7 +91,15 @@ __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const __nv_bfloat1
         s[i] += f[i];
         q[i] = fmaf(f[i], f[i], q[i]);
       }
+    };
+    for (; row + 3 * stride < M; row += 4 * stride) {
+      const uint4 v0 = ldg_stream_u4(base + row * ld);
+      const uint4 v1 = ldg_stream_u4(base + (row + stride) * ld);
+      const uint4 v2 = ldg_stream_u4(base + (row + 2 * stride) * ld);
+      const uint4 v3 = ldg_stream_u4(base + (row + 3 * stride) * ld);
+      acc8(v0); acc8(v1); acc8(v2); acc8(v3);
     }
+    for (; row < M; row += stride) acc8(ldg_stream_u4(base + row * ld));
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -111,15 +130,18 @@ struct BnApplyParams {
   const uint64_t* seed_dev;  // optional device-side addend to the seed (CUDA-graph replays advance it)
   __nv_bfloat16* out;
   int ld_out, c_off_out;
+  const __nv_bfloat16* res;  // optional residual added BEFORE the activation (resnet_models.py:88-92), [M][ld_res]
+  int ld_res;
 };
-__global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParams p) {
+template <bool RES, bool DROP>
+__global__ void __launch_bounds__(kEwThreads, 4) bn_apply_kernel(const BnApplyParams p) {
   // thread -> fixed 8-channel group (scale/shift live in registers), rows strided over the grid
   const int groups = p.C >> 3;
   const int rows_per_block = kEwThreads / groups;
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
   if (r >= rows_per_block) return;
-  const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-  const uint64_t seed = p.seed + ((p.drop_p > 0.f && p.seed_dev) ? *p.seed_dev : 0ull);
+  const float keep_scale = DROP ? 1.f / (1.f - p.drop_p) : 1.f;
+  const uint64_t seed = p.seed + ((DROP && p.seed_dev) ? *p.seed_dev : 0ull);
   float sc[8], sf[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -127,22 +149,39 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParam
     sf[j] = __ldg(p.shift + g * 8 + j);
   }
   const int64_t stride = (int64_t)gridDim.x * rows_per_block;
-#pragma unroll 4
-  for (int64_t row = (int64_t)blockIdx.x * rows_per_block + r; row < p.M; row += stride) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.raw + row * p.ld_in + p.c_off_in + g * 8));
-    float f[8];
+  const __nv_bfloat16* base = p.raw + p.c_off_in + g * 8;
+  const __nv_bfloat16* rbase = RES ? p.res + g * 8 : nullptr;
+  auto finish = [&](int64_t row, const uint4& v, const uint4& rv) {
+    float f[8], rs[8];
     unpack8(v, f);
+    if (RES) unpack8(rv, rs);
     uint32_t keep = 0xFFu;
-    if (p.drop_p > 0.f) keep = dropout_keep8(seed, p.offset, (uint64_t)(row * groups + g) * 8, p.drop_p);
+    if (DROP) keep = dropout_keep8(seed, p.offset, (uint64_t)(row * groups + g) * 8, p.drop_p);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float y = fmaf(f[j], sc[j], sf[j]);
+      if (RES) y += rs[j];
       if (p.relu) y = fmaxf(y, 0.f);
       if (p.relu == 2) y = fminf(y, 6.f);  // ReLU6 (mobilenet_v2.py:7-12)
       f[j] = ((keep >> j) & 1u) ? y * keep_scale : 0.f;
     }
     *reinterpret_cast<uint4*>(p.out + row * p.ld_out + p.c_off_out + g * 8) = pack8(f);
+  };
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  int64_t row = (int64_t)blockIdx.x * rows_per_block + r;
+  // 4 rows (x2 tensors with a residual) in flight per thread
+  for (; row + 3 * stride < p.M; row += 4 * stride) {
+    uint4 v[4], rv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u] = ldg_stream_u4(base + (row + u * stride) * p.ld_in);
+      rv[u] = RES ? ldg_stream_u4(rbase + (row + u * stride) * p.ld_res) : z;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) finish(row + u * stride, v[u], rv[u]);
   }
+  for (; row < p.M; row += stride)
+    finish(row, ldg_stream_u4(base + row * p.ld_in), RES ? ldg_stream_u4(rbase + row * p.ld_res) : z);
 }
 
 // ---- BN backward -----------------------------------------------------------------------------
@@ -163,34 +202,52 @@ struct BnBwdParams {
   const uint64_t* seed_dev;
   float* sums;          // [2][C]: sum g, sum g*xhat
   __nv_bfloat16* draw;  // pass 2 output [M][C]
+  const __nv_bfloat16* res;  // optional residual that was added before the activation (gate = act'(bn(x) + res))
+  int ld_res;
+  __nv_bfloat16* dres;  // optional pass 2 output [M][C]: gradient wrt the residual (= gated upstream gradient)
 };
 
 // masked upstream gradient of 8 channels: dropout mask/scale and the ReLU / ReLU6 gate (recomputed, never stored)
+struct BnBwdVec {
+  uint4 dy, x, res;
+};
+template <bool RES>
+__device__ __forceinline__ BnBwdVec bn_bwd_load(const BnBwdParams& p, int64_t row, int g) {
+  BnBwdVec v;
+  v.dy = ldg_stream_u4(p.dy + row * p.ld_dy + p.c_off_dy + g * 8);
+  v.x = ldg_stream_u4(p.raw + row * p.ld_raw + p.c_off_raw + g * 8);
+  v.res = RES ? ldg_stream_u4(p.res + row * p.ld_res + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+  return v;
+}
+template <bool RES, bool DROP>
 __device__ __forceinline__ void bn_bwd_g8(const BnBwdParams& p, uint64_t seed, float keep_scale, int64_t row, int g,
-                                          int groups, const float (&sc)[8], const float (&sf)[8], float (&x)[8],
-                                          float (&go)[8]) {
-  float dy[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(p.dy + row * p.ld_dy + p.c_off_dy + g * 8)), dy);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(p.raw + row * p.ld_raw + p.c_off_raw + g * 8)), x);
+                                          int groups, const float (&sc)[8], const float (&sf)[8], const BnBwdVec& v,
+                                          float (&x)[8], float (&go)[8]) {
+  float dy[8], rs[8];
+  unpack8(v.dy, dy);
+  unpack8(v.x, x);
+  if (RES) unpack8(v.res, rs);
   uint32_t keep = 0xFFu;
-  if (p.drop_p > 0.f) keep = dropout_keep8(seed, p.offset, (uint64_t)(row * groups + g) * 8, p.drop_p);
+  if (DROP) keep = dropout_keep8(seed, p.offset, (uint64_t)(row * groups + g) * 8, p.drop_p);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float gg = ((keep >> j) & 1u) ? dy[j] * keep_scale : 0.f;
-    const float yv = fmaf(x[j], sc[j], sf[j]);
+    float yv = fmaf(x[j], sc[j], sf[j]);
+    if (RES) yv += rs[j];
     if (p.relu && !(yv > 0.f)) gg = 0.f;
     if (p.relu == 2 && !(yv < 6.f)) gg = 0.f;
     go[j] = gg;
   }
 }
 
-__global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdParams p) {
+template <bool RES, bool DROP>
+__global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_reduce_kernel(const BnBwdParams p) {
   extern __shared__ float sh[];
   const int groups = p.C >> 3;
   const int rows_per_block = kEwThreads / groups;
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
-  const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-  const uint64_t seed = p.seed + ((p.drop_p > 0.f && p.seed_dev) ? *p.seed_dev : 0ull);
+  const float keep_scale = DROP ? 1.f / (1.f - p.drop_p) : 1.f;
+  const uint64_t seed = p.seed + ((DROP && p.seed_dev) ? *p.seed_dev : 0ull);
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
@@ -204,16 +261,22 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdPa
       rs[j] = __ldg(p.rstd + g * 8 + j);
     }
     const int64_t stride = (int64_t)gridDim.x * rows_per_block;
-#pragma unroll 2
-    for (int64_t row = (int64_t)blockIdx.x * rows_per_block + r; row < p.M; row += stride) {
+    auto acc = [&](int64_t row, const BnBwdVec& v) {
       float x[8], go[8];
-      bn_bwd_g8(p, seed, keep_scale, row, g, groups, sc, sf, x, go);
+      bn_bwd_g8<RES, DROP>(p, seed, keep_scale, row, g, groups, sc, sf, v, x, go);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s[j] += go[j];
         q[j] = fmaf(go[j], (x[j] - mu[j]) * rs[j], q[j]);
       }
+    };
+    int64_t row = (int64_t)blockIdx.x * rows_per_block + r;
+    for (; row + stride < p.M; row += 2 * stride) {  // 2 rows x (dy, raw[, res]) in flight per thread
+      const BnBwdVec v0 = bn_bwd_load<RES>(p, row, g), v1 = bn_bwd_load<RES>(p, row + stride, g);
+      acc(row, v0);
+      acc(row + stride, v1);
     }
+    for (; row < p.M; row += stride) acc(row, bn_bwd_load<RES>(p, row, g));
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -229,15 +292,16 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_reduce_kernel(const BnBwdPa
   }
 }
 
-__global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdParams p) {
+template <bool RES, bool DROP>
+__global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_apply_kernel(const BnBwdParams p) {
   // d_raw = scale * (g - mean(g) - xhat * mean(g xhat)) = A*g + B*x + K with per-channel A, B, K held in registers
   const int groups = p.C >> 3;
   const int rows_per_block = kEwThreads / groups;
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
   if (r >= rows_per_block) return;
   const float inv_m = 1.f / (float)p.M;
-  const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-  const uint64_t seed = p.seed + ((p.drop_p > 0.f && p.seed_dev) ? *p.seed_dev : 0ull);
+  const float keep_scale = DROP ? 1.f / (1.f - p.drop_p) : 1.f;
+  const uint64_t seed = p.seed + ((DROP && p.seed_dev) ? *p.seed_dev : 0ull);
   float sc[8], sf[8], cb[8], ck[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -250,14 +314,21 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const BnBwdPar
     ck[j] = -sc[j] * (mg - mu * rs * mgx);
   }
   const int64_t stride = (int64_t)gridDim.x * rows_per_block;
-#pragma unroll 2
-  for (int64_t row = (int64_t)blockIdx.x * rows_per_block + r; row < p.M; row += stride) {
+  auto finish = [&](int64_t row, const BnBwdVec& v) {
     float x[8], gg[8], o[8];
-    bn_bwd_g8(p, seed, keep_scale, row, g, groups, sc, sf, x, gg);
+    bn_bwd_g8<RES, DROP>(p, seed, keep_scale, row, g, groups, sc, sf, v, x, gg);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[j], gg[j], fmaf(cb[j], x[j], ck[j]));
     *reinterpret_cast<uint4*>(p.draw + row * p.C + g * 8) = pack8(o);
+    if (RES && p.dres) *reinterpret_cast<uint4*>(p.dres + row * p.C + g * 8) = pack8(gg);
+  };
+  int64_t row = (int64_t)blockIdx.x * rows_per_block + r;
+  for (; row + stride < p.M; row += 2 * stride) {
+    const BnBwdVec v0 = bn_bwd_load<RES>(p, row, g), v1 = bn_bwd_load<RES>(p, row + stride, g);
+    finish(row, v0);
+    finish(row + stride, v1);
   }
+  for (; row < p.M; row += stride) finish(row, bn_bwd_load<RES>(p, row, g));
 }
 
 // ---- bilinear upsample NHWC bf16 (align_corners=True) -----------------------------------------
@@ -287,36 +358,60 @@ __global__ void __launch_bounds__(kEwThreads) upsample_nhwc_kernel(const __nv_bf
   }
 }
 
-// adjoint: grad_in (f32 [N,h,w,C], zeroed) += scatter of grad_out slice (bf16 [N,H,W,ld] at c_off)
+// adjoint, as a GATHER: one thread owns 8 channels of one low-resolution pixel and sums the contributions of every
+// high-resolution pixel whose stencil touches it (weights re-evaluated with the forward's own lerp_ac, so the pair is
+// an exact adjoint).  No atomics, deterministic; grad_in (f32 [N,h,w,C]) is fully overwritten.
+__device__ __forceinline__ void adj_range(int i, int in_size, int out_size, float scale, int& lo, int& hi) {
+  if (in_size == out_size) {
+    lo = hi = i;
+  } else if (!(scale > 0.f)) {
+    lo = 0;
+    hi = out_size - 1;
+  } else {
+    lo = (int)floorf((float)(i - 1) / scale) - 1;
+    hi = (int)ceilf((float)(i + 1) / scale) + 1;
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > out_size - 1 ? out_size - 1 : hi;
+  }
+}
 __global__ void __launch_bounds__(kEwThreads) upsample_nhwc_bwd_kernel(const __nv_bfloat16* __restrict__ gout, int N, int H,
                                                                        int W, int ld, int c_off, int C,
                                                                        float* __restrict__ gin, int h, int w, float sh_,
                                                                        float sw_) {
   const int groups = C >> 3;
-  const int64_t total = (int64_t)N * H * W * groups;
+  const int64_t total = (int64_t)N * h * w * groups;
   for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kEwThreads) {
     const int g = (int)(i % groups);
     int64_t t = i / groups;
-    const int x = (int)(t % W);
-    t /= W;
-    const int y = (int)(t % H);
-    const int n = (int)(t / H);
-    const Lerp ly = lerp_ac(y, h, H, sh_), lx = lerp_ac(x, w, W, sw_);
-    float gv[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(gout + (((int64_t)n * H + y) * W + x) * ld + c_off + g * 8)), gv);
-    float* b = gin + (int64_t)n * h * w * C + g * 8;
-    float* p00 = b + ((int64_t)ly.i0 * w + lx.i0) * C;
-    float* p01 = b + ((int64_t)ly.i0 * w + lx.i1) * C;
-    float* p10 = b + ((int64_t)ly.i1 * w + lx.i0) * C;
-    float* p11 = b + ((int64_t)ly.i1 * w + lx.i1) * C;
-    const float w00 = ly.l0 * lx.l0, w01 = ly.l0 * lx.l1, w10 = ly.l1 * lx.l0, w11 = ly.l1 * lx.l1;
+    const int xi = (int)(t % w);
+    t /= w;
+    const int yi = (int)(t % h);
+    const int n = (int)(t / h);
+    int y_lo, y_hi, x_lo, x_hi;
+    adj_range(yi, h, H, sh_, y_lo, y_hi);
+    adj_range(xi, w, W, sw_, x_lo, x_hi);
+    float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(p00 + j, gv[j] * w00);
-      if (w01 != 0.f) atomicAdd(p01 + j, gv[j] * w01);
-      if (w10 != 0.f) atomicAdd(p10 + j, gv[j] * w10);
-      if (w11 != 0.f) atomicAdd(p11 + j, gv[j] * w11);
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const __nv_bfloat16* b = gout + (int64_t)n * H * W * ld + c_off + g * 8;
+    for (int y = y_lo; y <= y_hi; ++y) {
+      const Lerp ly = lerp_ac(y, h, H, sh_);
+      const float wy = (ly.i0 == yi ? ly.l0 : 0.f) + (ly.i1 == yi ? ly.l1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int x = x_lo; x <= x_hi; ++x) {
+        const Lerp lx = lerp_ac(x, w, W, sw_);
+        const float wx = (lx.i0 == xi ? lx.l0 : 0.f) + (lx.i1 == xi ? lx.l1 : 0.f);
+        if (wx == 0.f) continue;
+        float gv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((int64_t)y * W + x) * ld)), gv);
+        const float wgt = wy * wx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv[j], wgt, acc[j]);
+      }
     }
+    float* o = gin + (((int64_t)n * h + yi) * w + xi) * C + g * 8;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
 }
 
@@ -381,7 +476,15 @@ int pp_bn_stats(const void* raw, int64_t M, int ld, int c_off, int C, float* sum
 int pp_bn_apply(const void* raw, int64_t M, int ld_in, int c_off_in, int C, const float* scale, const float* shift,
                 int relu, float drop_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, void* out, int ld_out,
                 int c_off_out, void* stream) {
+  return pp_bn_apply_res(raw, M, ld_in, c_off_in, C, scale, shift, relu, drop_p, seed, offset, seed_dev, nullptr, 0, out,
+                         ld_out, c_off_out, stream);
+}
+
+int pp_bn_apply_res(const void* raw, int64_t M, int ld_in, int c_off_in, int C, const float* scale, const float* shift,
+                    int relu, float drop_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const void* res,
+                    int ld_res, void* out, int ld_out, int c_off_out, void* stream) {
   PP_CHECK_ARG(raw && out && scale && shift && M > 0, "pp_bn_apply: bad args");
+  PP_CHECK_ARG(!res || (ld_res % 8 == 0 && ld_res >= C), "pp_bn_apply: residual ld=%d", ld_res);
   PP_CHECK_ARG(C % 8 == 0 && C <= 2048 && ld_in % 8 == 0 && c_off_in % 8 == 0 && ld_out % 8 == 0 && c_off_out % 8 == 0,
                "pp_bn_apply: channel counts/offsets must be multiples of 8 (C <= 2048)");
   PP_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "pp_bn_apply: drop_p=%f", drop_p);
@@ -390,11 +493,17 @@ int pp_bn_apply(const void* raw, int64_t M, int ld_in, int c_off_in, int C, cons
   p.M = M; p.ld_in = ld_in; p.c_off_in = c_off_in; p.C = C; p.scale = scale; p.shift = shift; p.relu = relu;
   p.drop_p = drop_p; p.seed = seed; p.offset = offset; p.seed_dev = seed_dev;
   p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ld_out = ld_out; p.c_off_out = c_off_out;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.ld_res = ld_res;
   {
     const int rows_per_block = kEwThreads / (C / 8);
     int64_t blocks = (M + rows_per_block * 4 - 1) / (rows_per_block * 4);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    bn_apply_kernel<<<(int)blocks, kEwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool drop = drop_p > 0.f;
+    if (res && drop) bn_apply_kernel<true, true><<<(int)blocks, kEwThreads, 0, st>>>(p);
+    else if (res) bn_apply_kernel<true, false><<<(int)blocks, kEwThreads, 0, st>>>(p);
+    else if (drop) bn_apply_kernel<false, true><<<(int)blocks, kEwThreads, 0, st>>>(p);
+    else bn_apply_kernel<false, false><<<(int)blocks, kEwThreads, 0, st>>>(p);
   }
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -403,7 +512,16 @@ int pp_bn_apply(const void* raw, int64_t M, int ld_in, int c_off_in, int C, cons
 int pp_bn_bwd(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_raw, int c_off_raw, int64_t M, int C,
               const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
               uint64_t seed, uint64_t offset, const uint64_t* seed_dev, float* sums, void* draw, void* stream) {
+  return pp_bn_bwd_res(dy, ld_dy, c_off_dy, raw, ld_raw, c_off_raw, M, C, scale, shift, mean, rstd, relu, drop_p, seed,
+                       offset, seed_dev, nullptr, 0, nullptr, sums, draw, stream);
+}
+
+int pp_bn_bwd_res(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_raw, int c_off_raw, int64_t M, int C,
+                  const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
+                  uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const void* res, int ld_res, void* dres,
+                  float* sums, void* draw, void* stream) {
   PP_CHECK_ARG(dy && raw && sums && draw && M > 0, "pp_bn_bwd: bad args");
+  PP_CHECK_ARG(!res || (ld_res % 8 == 0 && ld_res >= C), "pp_bn_bwd: residual ld=%d", ld_res);
   PP_CHECK_ARG(C % 8 == 0 && C <= 2048 && ld_dy % 8 == 0 && c_off_dy % 8 == 0 && ld_raw % 8 == 0 && c_off_raw % 8 == 0,
                "pp_bn_bwd: C=%d must be a multiple of 8 and <= 2048", C);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -414,14 +532,26 @@ int pp_bn_bwd(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_r
   p.drop_p = drop_p; p.seed = seed; p.offset = offset; p.seed_dev = seed_dev;
   p.sums = sums;
   p.draw = reinterpret_cast<__nv_bfloat16*>(draw);
+  p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.ld_res = ld_res;
+  p.dres = reinterpret_cast<__nv_bfloat16*>(dres);
   PP_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
   const int rows_per_block = kEwThreads / (C / 8);
   int64_t blocks = (M + rows_per_block * 4 - 1) / (rows_per_block * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  bn_bwd_reduce_kernel<<<(int)blocks, kEwThreads, kEwThreads * 16 * sizeof(float), st>>>(p);
-  PP_LAUNCH_CHECK();
-  bn_bwd_apply_kernel<<<(int)blocks, kEwThreads, 0, st>>>(p);
-  PP_LAUNCH_CHECK();
+  const size_t sm = kEwThreads * 16 * sizeof(float);
+  const bool drop = drop_p > 0.f;
+#define PP_BN_BWD(R, D)                                                      \
+  do {                                                                       \
+    bn_bwd_reduce_kernel<R, D><<<(int)blocks, kEwThreads, sm, st>>>(p);      \
+    PP_LAUNCH_CHECK();                                                       \
+    bn_bwd_apply_kernel<R, D><<<(int)blocks, kEwThreads, 0, st>>>(p);        \
+    PP_LAUNCH_CHECK();                                                       \
+  } while (0)
+  if (res && drop) PP_BN_BWD(true, true);
+  else if (res) PP_BN_BWD(true, false);
+  else if (drop) PP_BN_BWD(false, true);
+  else PP_BN_BWD(false, false);
+#undef PP_BN_BWD
   return PP_OK;
 }
 
@@ -440,7 +570,7 @@ int pp_upsample_nhwc_bf16_bwd(const void* grad_out, int N, int H, int W, int ld,
                               int w, void* stream) {
   PP_CHECK_ARG(grad_out && grad_in && N > 0 && h > 0 && w > 0 && H > 0 && W > 0, "pp_upsample_nhwc_bf16_bwd: bad args");
   PP_CHECK_ARG(C % 8 == 0 && ld % 8 == 0 && c_off % 8 == 0, "pp_upsample_nhwc_bf16_bwd: multiples of 8");
-  upsample_nhwc_bwd_kernel<<<ew_grid((int64_t)N * H * W * (C / 8)), kEwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  upsample_nhwc_bwd_kernel<<<ew_grid((int64_t)N * h * w * (C / 8)), kEwThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(grad_out), N, H, W, ld, c_off, C, grad_in, h, w, ac_scale(h, H), ac_scale(w, W));
   PP_LAUNCH_CHECK();
   return PP_OK;

@@ -32,24 +32,30 @@ class _BNActFn(torch.autograd.Function):
     two-pass backward (pp_bn_bwd); x is a contiguous NHWC bf16 view."""
 
     @staticmethod
-    def forward(ctx, xn, weight, bias, mod, act):
+    def forward(ctx, xn, weight, bias, mod, act, res=None):
         C = xn.shape[-1]
         M = xn.numel() // C
         stats = _lib.bn_finalize(_lib.bn_stats(xn, 0, C), M, mod)
         y = torch.empty_like(xn)
-        _lib.bn_apply(xn, 0, C, stats[0], stats[1], act, y, 0)
-        ctx.save_for_backward(xn, stats)
+        _lib.bn_apply(xn, 0, C, stats[0], stats[1], act, y, 0, res=res)
+        if res is None:
+            ctx.save_for_backward(xn, stats)
+        else:
+            ctx.save_for_backward(xn, stats, res)
         ctx.act = act
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        xn, stats = ctx.saved_tensors
+        xn, stats = ctx.saved_tensors[:2]
+        res = ctx.saved_tensors[2] if len(ctx.saved_tensors) > 2 else None
         C = xn.shape[-1]
         if dy.dtype != torch.bfloat16 or not dy.is_contiguous():
             dy = dy.to(torch.bfloat16).contiguous()
-        draw, sums = _lib.bn_bwd(dy, 0, xn, 0, C, stats[0], stats[1], stats[2], stats[3], ctx.act)
-        return draw.view_as(xn), sums[1], sums[0], None, None
+        out = _lib.bn_bwd(dy, 0, xn, 0, C, stats[0], stats[1], stats[2], stats[3], ctx.act, res=res)
+        draw, sums = out[0], out[1]
+        dres = out[2].view_as(xn) if res is not None else None
+        return draw.view_as(xn), sums[1], sums[0], None, None, dres
 
 
 class FusedBNAct(nn.BatchNorm2d):
@@ -64,21 +70,70 @@ class FusedBNAct(nn.BatchNorm2d):
     def _torch_act(self, y):
         return F.relu(y) if self.act == 1 else (F.relu6(y) if self.act == 2 else y)
 
-    def forward(self, x):
+    def forward(self, x, residual=None):
+        """act(bn(x) [+ residual]) — the residual form is the bottleneck tail (resnet_models.py:88-92) in one pass."""
+        def torch_path():
+            y = super(FusedBNAct, self).forward(x)
+            return self._torch_act(y if residual is None else y + residual)
+
         if not (x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0 and x.dim() == 4):
-            return self._torch_act(super().forward(x))
+            return torch_path()
         xn = x.permute(0, 2, 3, 1)
         if not xn.is_contiguous():
             xn = xn.contiguous()
+        rn = None
+        if residual is not None:
+            rn = residual.permute(0, 2, 3, 1)
+            if rn.dtype != torch.bfloat16 or not rn.is_contiguous():
+                rn = rn.to(torch.bfloat16).contiguous()
         if self.training:
-            y = _BNActFn.apply(xn, self.weight, self.bias, self, self.act)
+            y = _BNActFn.apply(xn, self.weight, self.bias, self, self.act, rn)
         else:
             if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
-                return self._torch_act(super().forward(x))
+                return torch_path()
             scale, shift = _fold_bn(self)
             y = torch.empty_like(xn)
-            _lib.bn_apply(xn, 0, xn.shape[-1], scale, shift, self.act, y, 0)
+            _lib.bn_apply(xn, 0, xn.shape[-1], scale, shift, self.act, y, 0, res=rn)
         return y.permute(0, 3, 1, 2)
+
+
+# =============================================================================================
+# depthwise 3x3 of the MobileNetV2 inverted residual on the NHWC bf16 kernels of dwconv.cu
+# =============================================================================================
+class _DWConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xn, weight, stride, dil):
+        y = _lib.dwconv_fwd(xn, weight, stride, dil)
+        ctx.save_for_backward(xn, weight)
+        ctx.cfg = (stride, dil)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xn, weight = ctx.saved_tensors
+        stride, dil = ctx.cfg
+        if dy.dtype != torch.bfloat16 or not dy.is_contiguous():
+            dy = dy.to(torch.bfloat16).contiguous()
+        dx = _lib.dwconv_dgrad(dy, weight, tuple(xn.shape[1:3]), stride, dil) if ctx.needs_input_grad[0] else None
+        dw = _lib.dwconv_wgrad(xn, dy, stride, dil) if ctx.needs_input_grad[1] else None
+        return dx, dw, None, None
+
+
+class DepthwiseConv3x3(nn.Conv2d):
+    """nn.Conv2d(C, C, 3, stride, 0, dilation, groups=C, bias=False) (same parameter / state_dict key) whose CUDA bf16
+    forward/backward run on the hand-written NHWC kernels; fp32 parity mode and CPU construction use torch."""
+
+    def __init__(self, channels, stride, dilation):
+        super().__init__(channels, channels, 3, stride, 0, dilation, groups=channels, bias=False)
+
+    def forward(self, x):
+        C = x.shape[1]
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and C % 8 == 0 and x.dim() == 4 and self.weight.dtype == torch.float32):
+            return super().forward(x)
+        xn = x.permute(0, 2, 3, 1)
+        if not xn.is_contiguous():
+            xn = xn.contiguous()
+        return _DWConvFn.apply(xn, self.weight, self.stride[0], self.dilation[0]).permute(0, 3, 1, 2)
 
 
 # =============================================================================================
@@ -108,7 +163,7 @@ class InvertedResidual(nn.Module):
         layers = []
         if expand_ratio != 1:
             layers += [nn.Conv2d(inp, hidden, 1, 1, 0, 1, bias=False), FusedBNAct(hidden, act=2), nn.Identity()]
-        layers += [nn.Conv2d(hidden, hidden, 3, stride, 0, dilation, groups=hidden, bias=False), FusedBNAct(hidden, act=2),
+        layers += [DepthwiseConv3x3(hidden, stride, dilation), FusedBNAct(hidden, act=2),
                    nn.Identity(), nn.Conv2d(hidden, oup, 1, 1, 0, 1, bias=False), FusedBNAct(oup, act=0)]
         self.conv = nn.Sequential(*layers)
 
@@ -169,15 +224,15 @@ class Bottleneck(nn.Module):
         self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
         self.bn2 = FusedBNAct(planes, act=1)
         self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
-        self.bn3 = FusedBNAct(planes * 4, act=0)
+        self.bn3 = FusedBNAct(planes * 4, act=1)  # applied as relu(bn3(.) + identity): one fused pass
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
 
     def forward(self, x):
         out = self.bn1(self.conv1(x))  # BatchNorm + ReLU fused
         out = self.bn2(self.conv2(out))
-        out = self.bn3(self.conv3(out))
-        return self.relu(out + (x if self.downsample is None else self.downsample(x)))
+        identity = x if self.downsample is None else self.downsample(x)
+        return self.bn3(self.conv3(out), residual=identity)  # BatchNorm + residual add + ReLU fused
 
 
 class ResNet50Dilated8(nn.Module):
@@ -531,7 +586,7 @@ class DeepLab(nn.Module):
         """aspp.py:54-57,69-70: image pooling -> 1x1 -> BN -> ReLU; its broadcast through the projection is a
         per-image bias pre[b, :] = x5[b] @ W1[:, 1024:1280]^T (tiny tensors: autograd-tracked torch ops, fp32)."""
         a = self.aspp
-        pooled = high.float().mean(dim=(2, 3))
+        pooled = high.mean(dim=(2, 3), dtype=torch.float32)  # fp32 accumulate without materialising an fp32 copy
         g = F.linear(pooled, a.global_avg_pool[1].weight.flatten(1))
         bn = a.global_avg_pool[2]
         g = F.batch_norm(g, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum or 0.1, bn.eps)

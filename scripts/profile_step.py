@@ -55,6 +55,15 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
 ka = prof.key_averages()
 cuda_total = sum(e.self_device_time_total for e in ka) / 3e3
 print(f"  profiler: GPU kernel time {cuda_total:.2f} ms/step; kernels/step {sum(e.count for e in ka if e.self_device_time_total > 0 and e.device_type.name == 'CUDA') / 3:.0f}")
-rows = sorted(ka, key=lambda e: -e.self_device_time_total)[:14]
+rows = sorted(ka, key=lambda e: -e.self_device_time_total)[:45]
 for e in rows:
-    print(f"    {e.key[:70]:70s} n={e.count / 3:6.1f} gpu {e.self_device_time_total / 3e3:7.3f} ms")
+    print(f"    {e.key[:110]:110s} n={e.count / 3:6.1f} gpu {e.self_device_time_total / 3e3:7.3f} ms")
+# which torch glue ops move the most bytes?  (grouped by input shape)
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof2:
+    for _ in range(2): step()
+    torch.cuda.synchronize()
+glue = [e for e in prof2.key_averages(group_by_input_shape=True)
+        if e.key.startswith("aten::") and e.self_device_time_total > 0 and "conv" not in e.key]
+print("  torch glue ops by shape (per step):")
+for e in sorted(glue, key=lambda e: -e.self_device_time_total)[:40]:
+    print(f"    {e.key:34s} n={e.count / 2:5.1f} gpu {e.self_device_time_total / 2e3:7.3f} ms  {str(e.input_shapes)[:150]}")

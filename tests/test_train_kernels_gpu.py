@@ -91,7 +91,8 @@ def test_bn_apply_and_backward_match_autograd(relu, p):
     assert torch.allclose(sums[1].cpu(), gr.grad, rtol=2e-2, atol=2e-2 * gr.grad.abs().max().item())
 
 
-@pytest.mark.parametrize("N,h,w,H,W,C", [(2, 16, 32, 64, 128, 256), (1, 23, 30, 90, 120, 256), (2, 32, 64, 64, 128, 64)])
+@pytest.mark.parametrize("N,h,w,H,W,C", [(2, 16, 32, 64, 128, 256), (1, 23, 30, 90, 120, 256), (2, 32, 64, 64, 128, 64),
+                                         (1, 9, 7, 9, 7, 64), (1, 1, 5, 4, 17, 8), (1, 3, 3, 64, 2, 16)])
 def test_upsample_nhwc_fwd_bwd(N, h, w, H, W, C):
     g = torch.Generator().manual_seed(h)
     x = torch.randn((N, C, h, w), generator=g).to(torch.bfloat16)
@@ -153,3 +154,89 @@ def test_fused_bn_act_module_matches_torch(act, C):
         yre = ref_bn(x.float())
         yre = F.relu(yre) if act == 1 else (F.relu6(yre) if act == 2 else yre)
     assert (ye - yre).abs().max().item() < 2e-2 * yre.abs().max().item()
+
+
+@pytest.mark.parametrize("C,train", [(256, True), (2048, True), (64, False)])
+def test_fused_bn_residual_relu_matches_torch(C, train):
+    """Bottleneck tail relu(bn3(x) + identity) (resnet_models.py:88-92) as ONE fused pass, forward and backward."""
+    from pixelpick_b200.deeplab import FusedBNAct
+    g = torch.Generator().manual_seed(C + 1)
+    x = (torch.randn((2, C, 9, 14), generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    r = torch.randn((2, C, 9, 14), generator=g).to(torch.bfloat16)
+    go = torch.randn((2, C, 9, 14), generator=g).to(torch.bfloat16)
+    ref_bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        ref_bn.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        ref_bn.bias.copy_(torch.randn(C, generator=g) * 0.3)
+        ref_bn.running_mean.copy_(torch.randn(C, generator=g) * 0.1)
+        ref_bn.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    m = FusedBNAct(C, act=1)
+    m.load_state_dict(ref_bn.state_dict())
+    m = m.to(DEV)
+    if not train:
+        m.eval(); ref_bn.eval()
+        with torch.no_grad():
+            y = m(x.to(DEV).contiguous(memory_format=torch.channels_last), residual=r.to(DEV).contiguous(memory_format=torch.channels_last))
+            yr = F.relu(ref_bn(x.float()) + r.float())
+        assert (y.float().cpu() - yr).abs().max().item() < 2e-2 * yr.abs().max().item()
+        return
+    xr, rr = x.float().requires_grad_(True), r.float().requires_grad_(True)
+    yr = F.relu(ref_bn(xr) + rr)
+    yr.backward(go.float())
+    xg = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    rg = r.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = m(xg, residual=rg)
+    y.backward(go.to(DEV))
+    assert (y.float().cpu() - yr.detach()).abs().max().item() < 2e-2 * yr.abs().max().item()
+    # gate disagreements can only happen where |bn(x)+r| is within bf16 rounding of 0: compare away from the kink
+    near = ((ref_bn(x.float()) + r.float()).abs() < 0.05)
+    ok = ~near
+    assert ((rg.grad.float().cpu() - rr.grad).abs() * ok).max().item() < 1e-2 * go.float().abs().max().item()
+    assert ((xg.grad.float().cpu() - xr.grad).abs() * ok).max().item() < 4e-2 * xr.grad.abs().max().item()
+    assert torch.allclose(m.weight.grad.cpu(), ref_bn.weight.grad, rtol=3e-2, atol=4e-2 * ref_bn.weight.grad.abs().max().item())
+    assert torch.allclose(m.bias.grad.cpu(), ref_bn.bias.grad, rtol=3e-2, atol=4e-2 * ref_bn.bias.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("N,C,Hi,Wi,stride,dil", [(2, 32, 18, 34, 1, 1), (2, 96, 19, 35, 2, 1), (1, 144, 10, 11, 2, 1),
+                                                  (2, 960, 12, 20, 1, 2), (1, 576, 7, 9, 1, 1), (1, 8, 3, 3, 1, 1),
+                                                  (1, 2048, 9, 9, 1, 4)])
+def test_depthwise_conv3x3_fwd_dgrad_wgrad(N, C, Hi, Wi, stride, dil):
+    """Hand-written depthwise 3x3 (mobilenet_v2.py:33-35,46-48: groups=C, padding 0 on the pre-padded tensor) vs
+    F.conv2d in fp32 on the same bf16-rounded operands."""
+    g = torch.Generator().manual_seed(C + Hi)
+    x = torch.randn((N, C, Hi, Wi), generator=g).to(torch.bfloat16)
+    w = torch.randn((C, 1, 3, 3), generator=g) * 0.4
+    xr, wr = x.float().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, stride, 0, dil, groups=C)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    y = _lib.dwconv_fwd(xn, w.to(DEV), stride, dil)
+    assert tuple(y.shape) == (N, yr.shape[2], yr.shape[3], C)
+    got = y.float().permute(0, 3, 1, 2).cpu()
+    assert (got - yr.detach()).abs().max().item() < 1e-2 * yr.abs().max().item()
+    go = torch.randn(yr.shape, generator=g).to(torch.bfloat16)
+    yr.backward(go.float())
+    gon = go.permute(0, 2, 3, 1).contiguous().to(DEV)
+    dx = _lib.dwconv_dgrad(gon, w.to(DEV), (Hi, Wi), stride, dil).float().permute(0, 3, 1, 2).cpu()
+    assert (dx - xr.grad).abs().max().item() < 1e-2 * xr.grad.abs().max().item()
+    dw = _lib.dwconv_wgrad(xn, gon, stride, dil).cpu()
+    assert dw.shape == w.shape
+    assert (dw - wr.grad).abs().max().item() < 2e-3 * wr.grad.abs().max().item() + 1e-4
+
+
+def test_depthwise_module_matches_conv2d_through_autograd():
+    from pixelpick_b200.deeplab import DepthwiseConv3x3
+    g = torch.Generator().manual_seed(3)
+    m = DepthwiseConv3x3(64, 2, 1)
+    ref = torch.nn.Conv2d(64, 64, 3, 2, 0, 1, groups=64, bias=False)
+    ref.load_state_dict(m.state_dict())
+    x = torch.randn((2, 64, 21, 17), generator=g).to(torch.bfloat16)
+    go = torch.randn((2, 64, 10, 8), generator=g).to(torch.bfloat16)
+    xr = x.float().requires_grad_(True)
+    ref(xr).backward(go.float())
+    m = m.to(DEV)
+    xg = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = m(xg)
+    assert y.dtype == torch.bfloat16 and tuple(y.shape) == (2, 64, 10, 8)
+    y.backward(go.to(DEV))
+    assert (xg.grad.float().cpu() - xr.grad).abs().max().item() < 1e-2 * xr.grad.abs().max().item()
+    assert (m.weight.grad.cpu() - ref.weight.grad).abs().max().item() < 2e-3 * ref.weight.grad.abs().max().item()
