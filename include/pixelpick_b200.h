@@ -182,6 +182,16 @@ int pp_conv_igemm(const void* x, int N, int H, int W, int Cin, int ld_in, const 
                   int Cout_pad, int Cout, const float* pre_bias, const float* scale, const float* shift, int relu,
                   void* out, int out_mode, int ld_out, int c_off, int block_n, void* stream);
 
+/* Generalised form: K runs over n_entries tap entries; entry t reads the A tile shifted by (tap_dy[t], tap_dx[t])
+ * pixels from channels [tap_c0[t], tap_c0[t] + Cin) of x (a_channels wide) and multiplies weight slice t of
+ * w_packed [n_entries][Cout_pad][Cin].  One launch computes e.g. the data gradient of all four ASPP branches
+ * (aspp.py:49-52,64-68: 1 + 9 + 9 + 9 taps with their own dilations) accumulated in TMEM, no partial sums in HBM.
+ * Host arrays; n_entries <= 28. */
+int pp_conv_igemm_multi(const void* x, int N, int H, int W, int a_channels, int ld_in, int Cin, const void* w_packed,
+                        int n_entries, const int* tap_dy, const int* tap_dx, const int* tap_c0, int Cout_pad, int Cout,
+                        const float* pre_bias, const float* scale, const float* shift, int relu, void* out,
+                        int out_mode, int ld_out, int c_off, int block_n, void* stream);
+
 /* Weight gradient of the same convolution on tcgen05 (both operands MN-major, split over pixels):
  *   dw[tap][ci][co] += sum_p x[p + shift(tap)][ci] * dy[p][co]
  * x: bf16 [N,H,W,ld_x] (Cin valid channels); dy: bf16 [N,H,W,ld_dy] (first Cout_pad channels, 64/128/256);
@@ -214,14 +224,16 @@ int pp_bn_bwd(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_r
               uint64_t seed, uint64_t offset, const uint64_t* seed_dev, float* sums, void* draw, void* stream);
 /* Residual variants for the ResNet bottleneck tail out = relu(bn3(conv3(.)) + identity) (resnet_models.py:88-92):
  * res (bf16 [M][ld_res], channels 0..C) is added before the activation in ONE pass; the backward gates on
- * bn(raw) + res and also returns dres = gated upstream gradient (bf16 [M][C]) = gradient wrt the identity branch. */
+ * bn(raw) + res and also returns dres = gated upstream gradient (bf16 [M][C]) = gradient wrt the identity branch.
+ * pp_bn_bwd_res writes draw into the channel slice [c_off_draw, c_off_draw + C) of a [M][ld_draw] buffer (the four ASPP
+ * branches share one 1024-wide gradient buffer that pp_conv_igemm_multi then reads in one launch). */
 int pp_bn_apply_res(const void* raw, int64_t M, int ld_in, int c_off_in, int C, const float* scale, const float* shift,
                     int relu, float drop_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const void* res,
                     int ld_res, void* out, int ld_out, int c_off_out, void* stream);
 int pp_bn_bwd_res(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_raw, int c_off_raw, int64_t M, int C,
                   const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
                   uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const void* res, int ld_res, void* dres,
-                  float* sums, void* draw, void* stream);
+                  float* sums, void* draw, int ld_draw, int c_off_draw, void* stream);
 /* bilinear align_corners=True resize of bf16 NHWC into a channel slice, and its adjoint (gather form: deterministic,
  * grad_in f32 [N,h,w,C] fully overwritten). */
 int pp_upsample_nhwc_bf16(const void* in, int N, int h, int w, int C, int ld_in, void* out, int H, int W, int ld_out,

@@ -57,7 +57,9 @@ _SIGNATURES = {
                    _vp, _vp], _i),
     "pp_bn_apply_res": ([_vp, _i64, _i, _i, _i, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i, _vp, _i, _i, _vp], _i),
     "pp_bn_bwd_res": ([_vp, _i, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i,
-                       _vp, _vp, _vp, _vp], _i),
+                       _vp, _vp, _vp, _i, _i, _vp], _i),
+    "pp_conv_igemm_multi": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i,
+                             _i, _vp], _i),
     "pp_dwconv3x3_fwd": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "pp_dwconv3x3_dgrad": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "pp_dwconv3x3_wgrad": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
@@ -312,7 +314,7 @@ def pack_conv_weight(w, cin_pad=None, cout_pad=None, transpose_for_dgrad=False):
     return out
 
 
-def pack_conv_weights(w, cin=None, fwd_pad=None, dgrad_pad=None):
+def pack_conv_weights(w, cin=None, fwd_pad=None, dgrad_pad=None, dgrad_out=None):
     """One launch: f32 conv weight [Cout, Cin_total, kh, kw] (first `cin` input channels) -> bf16 operand tensors.
     fwd_pad = (Cout_pad, Cin_pad) -> [taps, Cout_pad, Cin_pad]; dgrad_pad = (Cin_rows, Cout_cols) -> flipped/transposed."""
     _need_cuda(w)
@@ -324,6 +326,9 @@ def pack_conv_weights(w, cin=None, fwd_pad=None, dgrad_pad=None):
     taps = kh * kw
     fwd = torch.empty((taps,) + tuple(fwd_pad), dtype=torch.bfloat16, device=w.device) if fwd_pad else None
     dgr = torch.empty((taps,) + tuple(dgrad_pad), dtype=torch.bfloat16, device=w.device) if dgrad_pad else None
+    if dgrad_out is not None:  # pack straight into a [taps, rows, cols] slice of a larger operand tensor
+        assert dgrad_out.is_contiguous() and dgrad_out.dtype == torch.bfloat16 and tuple(dgrad_out.shape) == (taps,) + tuple(dgrad_pad)
+        dgr = dgrad_out
     check(lib().pp_pack_conv_weight(_ptr(w), co, cin, ci_tot, taps, _ptr(fwd), fwd_pad[0] if fwd_pad else 0,
                                     fwd_pad[1] if fwd_pad else 0, _ptr(dgr), dgrad_pad[0] if dgrad_pad else 0,
                                     dgrad_pad[1] if dgrad_pad else 0, _stream(w)), "pp_pack_conv_weight")
@@ -353,13 +358,32 @@ def conv_igemm(x_nhwc, w_packed, cout, dil=1, pre_bias=None, scale=None, shift=N
     return out
 
 
+def conv_igemm_multi(x_nhwc, w_packed, entries, cout, out=None, block_n=0):
+    """Generalised implicit GEMM: entries = [(dy, dx, c0), ...]; entry t convolves channels [c0, c0 + Cin) of x shifted by
+    (dy, dx) with weight slice t of w_packed [n_entries][cout_pad][Cin]; all entries accumulate into one output."""
+    _need_cuda(x_nhwc, w_packed)
+    assert x_nhwc.dtype == torch.bfloat16 and x_nhwc.is_contiguous() and w_packed.dtype == torch.bfloat16
+    N, H, W, ld_in = x_nhwc.shape
+    n_e, cout_pad, cin = w_packed.shape
+    assert n_e == len(entries)
+    if out is None:
+        out = torch.empty((N, H, W, cout), dtype=torch.bfloat16, device=x_nhwc.device)
+    arr = lambda k: (C.c_int * n_e)(*[int(e[k]) for e in entries])
+    check(lib().pp_conv_igemm_multi(_ptr(x_nhwc), N, H, W, ld_in, ld_in, cin, _ptr(w_packed), n_e, arr(0), arr(1), arr(2),
+                                    cout_pad, cout, None, None, None, 0, _ptr(out), 0, out.shape[3], 0, block_n,
+                                    _stream(x_nhwc)), "pp_conv_igemm_multi")
+    return out
+
+
 def conv_wgrad(x_nhwc, cin, dy_nhwc, cout_pad, taps, dil=1, splits=0):
-    """dW as f32 [taps][Cin_rows][Cout_pad] (Cin_rows = Cin rounded up to 128)."""
+    """dW as f32 [taps][Cin_rows][Cout_pad] (Cin_rows = Cin rounded up to 128).  dy_nhwc may be a channel-slice view
+    [..., c0:c0+cout_pad] of a wider contiguous NHWC buffer."""
     _need_cuda(x_nhwc, dy_nhwc)
     assert x_nhwc.dtype == torch.bfloat16 and dy_nhwc.dtype == torch.bfloat16
-    assert x_nhwc.is_contiguous() and dy_nhwc.is_contiguous()
+    assert x_nhwc.is_contiguous() and dy_nhwc.stride(3) == 1 and dy_nhwc.stride(1) == dy_nhwc.shape[2] * dy_nhwc.stride(2) \
+        and dy_nhwc.stride(0) == dy_nhwc.shape[1] * dy_nhwc.stride(1) and dy_nhwc.data_ptr() % 16 == 0
     N, H, W, ld_x = x_nhwc.shape
-    ld_dy = dy_nhwc.shape[3]
+    ld_dy = dy_nhwc.stride(2)
     rows = -(-cin // 128) * 128
     dw = torch.zeros((taps, rows, cout_pad), dtype=torch.float32, device=x_nhwc.device)
     check(lib().pp_conv_wgrad(_ptr(x_nhwc), ld_x, cin, _ptr(dy_nhwc), ld_dy, cout_pad, N, H, W, taps, dil, _ptr(dw),
@@ -404,19 +428,23 @@ def bn_apply(raw, c_off_in, C, scale, shift, relu, out, c_off_out, drop_p=0.0, s
 
 
 def bn_bwd(dy, c_off_dy, raw, c_off_raw, C, scale, shift, mean, rstd, relu, drop_p=0.0, seed=0, offset=0,
-           seed_dev=None, res=None):
+           seed_dev=None, res=None, draw_out=None, draw_c_off=0):
     """returns (draw bf16 [M, C], sums f32 [2, C] = (d beta, d gamma)) — plus dres bf16 [M, C] (gradient wrt the
     residual that was added before the activation) when `res` is given."""
     _need_cuda(dy, raw, res)
     ld_dy, ld_raw = dy.shape[-1], raw.shape[-1]
     M = raw.numel() // ld_raw
-    draw = torch.empty((M, C), dtype=torch.bfloat16, device=raw.device)
+    if draw_out is None:
+        draw, ld_draw = torch.empty((M, C), dtype=torch.bfloat16, device=raw.device), C
+    else:  # write into a channel slice of a wider gradient buffer
+        draw, ld_draw = draw_out, draw_out.shape[-1]
+        assert draw.dtype == torch.bfloat16 and draw.is_contiguous() and draw.numel() // ld_draw == M
     sums = torch.empty((2, C), dtype=torch.float32, device=raw.device)
     dres = torch.empty((M, C), dtype=torch.bfloat16, device=raw.device) if res is not None else None
     check(lib().pp_bn_bwd_res(_ptr(dy), ld_dy, c_off_dy, _ptr(raw), ld_raw, c_off_raw, M, C, _ptr(scale), _ptr(shift),
                               _ptr(mean), _ptr(rstd), int(relu), float(drop_p), int(seed), int(offset), _ptr(seed_dev),
                               _ptr(res), res.shape[-1] if res is not None else 0, _ptr(dres),
-                              _ptr(sums), _ptr(draw), _stream(raw)), "pp_bn_bwd")
+                              _ptr(sums), _ptr(draw), ld_draw, draw_c_off, _stream(raw)), "pp_bn_bwd")
     if res is not None:
         return draw, sums, dres
     return draw, sums

@@ -69,13 +69,18 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 constexpr int kBM = 128;  // output pixels per tile (UMMA M)
 constexpr int kBK = 64;   // channels per k-block (128 B of bf16 = one swizzle row)
 constexpr int kConvThreads = 192;
+constexpr int kMaxTaps = 28;
 
 struct ConvParams {
   int N, H, W;       // images, spatial size (output == input)
   int Cin;           // padded to a multiple of 64
   int Cout_pad;      // rows of the packed weight tensor (multiple of BN)
   int Cout;          // valid output channels (<= Cout_pad)
-  int taps, dil;     // 1 or 9; dilation (== padding)
+  int taps;          // number of tap entries (K = taps x Cin)
+  // tap table: entry t reads the A tile shifted by (tdy, tdx) pixels at channel offset ta of the A tensor and uses
+  // weight slice t.  A plain 3x3 dilated conv is 9 entries (dy, dx) = ((t/3-1)*dil, (t%3-1)*dil), ta = 0; the fused
+  // ASPP data gradient is 1 + 9 + 9 + 9 entries with per-branch dilations and channel offsets.
+  short tdy[kMaxTaps], tdx[kMaxTaps], ta[kMaxTaps];
   int n_off, n_tiles_n;  // this launch covers output channels [n_off, n_off + n_tiles_n * BN)
   int TH, TW;        // tile rectangle, TH * TW == 128
   int tiles_y, tiles_x;
@@ -98,15 +103,10 @@ struct ConvCfg {
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ bool tap_skipped(int tap, int taps, int dil, int y0, int x0, int TH, int TW, int H, int W,
-                                            int& dy, int& dx) {
-  if (taps == 1) {
-    dy = dx = 0;
-    return false;
-  }
-  dy = (tap / 3 - 1) * dil;
-  dx = (tap % 3 - 1) * dil;
-  return (y0 + dy + TH <= 0) || (y0 + dy >= H) || (x0 + dx + TW <= 0) || (x0 + dx >= W);
+__device__ __forceinline__ bool tap_skipped(const ConvParams& p, int tap, int y0, int x0, int& dy, int& dx) {
+  dy = p.tdy[tap];
+  dx = p.tdx[tap];
+  return (y0 + dy + p.TH <= 0) || (y0 + dy >= p.H) || (x0 + dx + p.TW <= 0) || (x0 + dx >= p.W);
 }
 
 template <int BN>
@@ -176,13 +176,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         decode(tile, n0, img, y0, x0);
         for (int tap = 0; tap < p.taps; ++tap) {
           int dy, dx;
-          if (tap_skipped(tap, p.taps, p.dil, y0, x0, p.TH, p.TW, p.H, p.W, dy, dx)) continue;
+          if (tap_skipped(p, tap, y0, x0, dy, dx)) continue;
+          const int a0 = p.ta[tap];
           for (int kc = 0; kc < kc_per_tap; ++kc, ++it) {
             const int s = it % Cfg::STAGES;
             const uint32_t ph = (it / Cfg::STAGES) & 1u;
             tc::mbar_wait(empty_bar(s), ph ^ 1u);
             tc::mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-            tc::tma_load_4d(sA(s), &tmA, full_bar(s), kc * kBK, x0 + dx, y0 + dy, img);
+            tc::tma_load_4d(sA(s), &tmA, full_bar(s), a0 + kc * kBK, x0 + dx, y0 + dy, img);
             tc::tma_load_3d(sB(s), &tmB, full_bar(s), kc * kBK, n0, tap);
           }
         }
@@ -204,7 +205,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t accumulate = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
           int dy, dx;
-          if (tap_skipped(tap, p.taps, p.dil, y0, x0, p.TH, p.TW, p.H, p.W, dy, dx)) continue;
+          if (tap_skipped(p, tap, y0, x0, dy, dx)) continue;
           for (int kc = 0; kc < kc_per_tap; ++kc, ++it) {
             const int s = it % Cfg::STAGES;
             const uint32_t ph = (it / Cfg::STAGES) & 1u;
@@ -335,12 +336,34 @@ extern "C" {
 int pp_conv_igemm(const void* x, int N, int H, int W, int Cin, int ld_in, const void* w_packed, int taps, int dil,
                   int Cout_pad, int Cout, const float* pre_bias, const float* scale, const float* shift, int relu,
                   void* out, int out_mode, int ld_out, int c_off, int block_n, void* stream) {
+  PP_CHECK_ARG(taps == 1 || taps == 9, "pp_conv_igemm: taps=%d (1 or 9)", taps);
+  PP_CHECK_ARG(dil >= 1 && dil < 4096, "pp_conv_igemm: dil=%d", dil);
+  int tdy[9], tdx[9], tc0[9];
+  for (int t = 0; t < taps; ++t) {
+    tdy[t] = taps == 1 ? 0 : (t / 3 - 1) * dil;
+    tdx[t] = taps == 1 ? 0 : (t % 3 - 1) * dil;
+    tc0[t] = 0;
+  }
+  return pp_conv_igemm_multi(x, N, H, W, Cin, ld_in, Cin, w_packed, taps, tdy, tdx, tc0, Cout_pad, Cout, pre_bias, scale,
+                             shift, relu, out, out_mode, ld_out, c_off, block_n, stream);
+}
+
+int pp_conv_igemm_multi(const void* x, int N, int H, int W, int a_channels, int ld_in, int Cin, const void* w_packed,
+                        int n_entries, const int* tap_dy, const int* tap_dx, const int* tap_c0, int Cout_pad, int Cout,
+                        const float* pre_bias, const float* scale, const float* shift, int relu, void* out,
+                        int out_mode, int ld_out, int c_off, int block_n, void* stream) {
   PP_CHECK_ARG(x && w_packed && out, "pp_conv_igemm: null pointer");
   PP_CHECK_ARG(N > 0 && H > 0 && W > 0, "pp_conv_igemm: bad shape");
   PP_CHECK_ARG(Cin > 0 && Cin % 64 == 0, "pp_conv_igemm: Cin=%d must be a multiple of 64 (pad the buffer)", Cin);
-  PP_CHECK_ARG(ld_in >= Cin && ld_in % 8 == 0, "pp_conv_igemm: ld_in=%d must be >= Cin and a multiple of 8", ld_in);
-  PP_CHECK_ARG(taps == 1 || taps == 9, "pp_conv_igemm: taps=%d (1 or 9)", taps);
-  PP_CHECK_ARG(dil >= 1, "pp_conv_igemm: dil=%d", dil);
+  PP_CHECK_ARG(a_channels >= Cin && ld_in >= a_channels && ld_in % 8 == 0,
+               "pp_conv_igemm: ld_in=%d must be >= the A channel count %d and a multiple of 8", ld_in, a_channels);
+  PP_CHECK_ARG(n_entries >= 1 && n_entries <= kMaxTaps && tap_dy && tap_dx && tap_c0, "pp_conv_igemm: %d tap entries (1..%d)",
+               n_entries, kMaxTaps);
+  for (int t = 0; t < n_entries; ++t)
+    PP_CHECK_ARG(tap_c0[t] >= 0 && tap_c0[t] % 8 == 0 && tap_c0[t] + Cin <= a_channels && tap_dy[t] > -8192 &&
+                     tap_dy[t] < 8192 && tap_dx[t] > -8192 && tap_dx[t] < 8192,
+                 "pp_conv_igemm: bad tap entry %d (dy %d dx %d c0 %d)", t, tap_dy[t], tap_dx[t], tap_c0[t]);
+  const int taps = n_entries;
   PP_CHECK_ARG(Cout > 0 && Cout <= Cout_pad, "pp_conv_igemm: Cout=%d Cout_pad=%d", Cout, Cout_pad);
   PP_CHECK_ARG(out_mode == 0 || out_mode == 1, "pp_conv_igemm: out_mode=%d", out_mode);
   PP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(w_packed) % 16) == 0,
@@ -368,7 +391,12 @@ int pp_conv_igemm(const void* x, int N, int H, int W, int Cin, int ld_in, const 
   PP_CHECK_ARG((BN == 32 || BN == 64 || BN == 128 || BN == 256) && n_main % BN == 0,
                "pp_conv_igemm: block_n=%d does not divide Cout_pad=%d", BN, Cout_pad);
   ConvParams p;
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout_pad = Cout_pad; p.Cout = Cout; p.taps = taps; p.dil = dil;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout_pad = Cout_pad; p.Cout = Cout; p.taps = taps;
+  for (int t = 0; t < kMaxTaps; ++t) {
+    p.tdy[t] = (short)(t < taps ? tap_dy[t] : 0);
+    p.tdx[t] = (short)(t < taps ? tap_dx[t] : 0);
+    p.ta[t] = (short)(t < taps ? tap_c0[t] : 0);
+  }
   p.TW = 16; p.TH = 8;
   if (W <= 8) { p.TW = 8; p.TH = 16; }
   p.tiles_y = (H + p.TH - 1) / p.TH;
@@ -380,7 +408,7 @@ int pp_conv_igemm(const void* x, int N, int H, int W, int Cin, int ld_in, const 
 
   CUtensorMap tmA, tmB;
   {
-    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t dims[4] = {(uint64_t)a_channels, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     const uint64_t strides[3] = {(uint64_t)ld_in * 2, (uint64_t)W * ld_in * 2, (uint64_t)H * W * ld_in * 2};
     const uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
     int rc = make_tmap_bf16(&tmA, x, 4, dims, strides, box);

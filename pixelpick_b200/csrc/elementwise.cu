@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const __nv_bfloat1
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (r < rows_per_block) {
-    // 4 independent 16-byte loads in flight per thread (the bounds check of a plain strided loop serialises them)
+    // 8 independent 16-byte loads in flight per thread (the bounds check of a plain strided loop serialises them)
     const int64_t stride = (int64_t)gridDim.x * rows_per_block;
     const __nv_bfloat16* base = raw + c_off + g * 8;
     int64_t row = (int64_t)blockIdx.x * rows_per_block + r;
@@ -92,12 +92,12 @@ __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const __nv_bfloat1
         q[i] = fmaf(f[i], f[i], q[i]);
       }
     };
-    for (; row + 3 * stride < M; row += 4 * stride) {
-      const uint4 v0 = ldg_stream_u4(base + row * ld);
-      const uint4 v1 = ldg_stream_u4(base + (row + stride) * ld);
-      const uint4 v2 = ldg_stream_u4(base + (row + 2 * stride) * ld);
-      const uint4 v3 = ldg_stream_u4(base + (row + 3 * stride) * ld);
-      acc8(v0); acc8(v1); acc8(v2); acc8(v3);
+    for (; row + 7 * stride < M; row += 8 * stride) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = ldg_stream_u4(base + (row + u * stride) * ld);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc8(v[u]);
     }
     for (; row < M; row += stride) acc8(ldg_stream_u4(base + row * ld));
   }
@@ -201,7 +201,8 @@ struct BnBwdParams {
   uint64_t seed, offset;
   const uint64_t* seed_dev;
   float* sums;          // [2][C]: sum g, sum g*xhat
-  __nv_bfloat16* draw;  // pass 2 output [M][C]
+  __nv_bfloat16* draw;  // pass 2 output [M][ld_draw] at channel offset c_off_draw
+  int ld_draw, c_off_draw;
   const __nv_bfloat16* res;  // optional residual that was added before the activation (gate = act'(bn(x) + res))
   int ld_res;
   __nv_bfloat16* dres;  // optional pass 2 output [M][C]: gradient wrt the residual (= gated upstream gradient)
@@ -241,7 +242,7 @@ __device__ __forceinline__ void bn_bwd_g8(const BnBwdParams& p, uint64_t seed, f
 }
 
 template <bool RES, bool DROP>
-__global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_reduce_kernel(const BnBwdParams p) {
+__global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_kernel(const BnBwdParams p) {
   extern __shared__ float sh[];
   const int groups = p.C >> 3;
   const int rows_per_block = kEwThreads / groups;
@@ -271,10 +272,12 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_reduce_kernel(const BnBw
       }
     };
     int64_t row = (int64_t)blockIdx.x * rows_per_block + r;
-    for (; row + stride < p.M; row += 2 * stride) {  // 2 rows x (dy, raw[, res]) in flight per thread
-      const BnBwdVec v0 = bn_bwd_load<RES>(p, row, g), v1 = bn_bwd_load<RES>(p, row + stride, g);
-      acc(row, v0);
-      acc(row + stride, v1);
+    for (; row + 3 * stride < p.M; row += 4 * stride) {  // 4 rows x (dy, raw[, res]) in flight per thread
+      BnBwdVec v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = bn_bwd_load<RES>(p, row + u * stride, g);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc(row + u * stride, v[u]);
     }
     for (; row < p.M; row += stride) acc(row, bn_bwd_load<RES>(p, row, g));
   }
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_apply_kernel(const BnBwd
     bn_bwd_g8<RES, DROP>(p, seed, keep_scale, row, g, groups, sc, sf, v, x, gg);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[j], gg[j], fmaf(cb[j], x[j], ck[j]));
-    *reinterpret_cast<uint4*>(p.draw + row * p.C + g * 8) = pack8(o);
+    *reinterpret_cast<uint4*>(p.draw + row * p.ld_draw + p.c_off_draw + g * 8) = pack8(o);
     if (RES && p.dres) *reinterpret_cast<uint4*>(p.dres + row * p.C + g * 8) = pack8(gg);
   };
   int64_t row = (int64_t)blockIdx.x * rows_per_block + r;
@@ -465,8 +468,8 @@ int pp_bn_stats(const void* raw, int64_t M, int ld, int c_off, int C, float* sum
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   PP_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
   const int rows_per_block = kEwThreads / (C / 8);
-  int64_t blocks = (M + rows_per_block * 4 - 1) / (rows_per_block * 4);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  int64_t blocks = (M + rows_per_block * 8 - 1) / (rows_per_block * 8);
+  if (blocks > 148 * 4) blocks = 148 * 4;  // one resident wave (4 CTAs / SM), 8 loads in flight per thread
   bn_stats_kernel<<<(int)blocks, kEwThreads, kEwThreads * 16 * sizeof(float), st>>>(
       reinterpret_cast<const __nv_bfloat16*>(raw), M, ld, c_off, C, sums);
   PP_LAUNCH_CHECK();
@@ -513,14 +516,16 @@ int pp_bn_bwd(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_r
               const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
               uint64_t seed, uint64_t offset, const uint64_t* seed_dev, float* sums, void* draw, void* stream) {
   return pp_bn_bwd_res(dy, ld_dy, c_off_dy, raw, ld_raw, c_off_raw, M, C, scale, shift, mean, rstd, relu, drop_p, seed,
-                       offset, seed_dev, nullptr, 0, nullptr, sums, draw, stream);
+                       offset, seed_dev, nullptr, 0, nullptr, sums, draw, C, 0, stream);
 }
 
 int pp_bn_bwd_res(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_raw, int c_off_raw, int64_t M, int C,
                   const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
                   uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const void* res, int ld_res, void* dres,
-                  float* sums, void* draw, void* stream) {
+                  float* sums, void* draw, int ld_draw, int c_off_draw, void* stream) {
   PP_CHECK_ARG(dy && raw && sums && draw && M > 0, "pp_bn_bwd: bad args");
+  PP_CHECK_ARG(ld_draw % 8 == 0 && c_off_draw % 8 == 0 && c_off_draw + C <= ld_draw, "pp_bn_bwd: draw slice ld=%d c_off=%d",
+               ld_draw, c_off_draw);
   PP_CHECK_ARG(!res || (ld_res % 8 == 0 && ld_res >= C), "pp_bn_bwd: residual ld=%d", ld_res);
   PP_CHECK_ARG(C % 8 == 0 && C <= 2048 && ld_dy % 8 == 0 && c_off_dy % 8 == 0 && ld_raw % 8 == 0 && c_off_raw % 8 == 0,
                "pp_bn_bwd: C=%d must be a multiple of 8 and <= 2048", C);
@@ -531,7 +536,7 @@ int pp_bn_bwd_res(const void* dy, int ld_dy, int c_off_dy, const void* raw, int 
   p.M = M; p.C = C; p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.relu = relu;
   p.drop_p = drop_p; p.seed = seed; p.offset = offset; p.seed_dev = seed_dev;
   p.sums = sums;
-  p.draw = reinterpret_cast<__nv_bfloat16*>(draw);
+  p.draw = reinterpret_cast<__nv_bfloat16*>(draw); p.ld_draw = ld_draw; p.c_off_draw = c_off_draw;
   p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.ld_res = ld_res;
   p.dres = reinterpret_cast<__nv_bfloat16*>(dres);
   PP_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
@@ -540,9 +545,10 @@ int pp_bn_bwd_res(const void* dy, int ld_dy, int c_off_dy, const void* raw, int 
   if (blocks > 148 * 8) blocks = 148 * 8;
   const size_t sm = kEwThreads * 16 * sizeof(float);
   const bool drop = drop_p > 0.f;
+  const int64_t rblocks = blocks < 148 * 3 ? blocks : 148 * 3;  // reduce pass: one resident wave (3 CTAs / SM)
 #define PP_BN_BWD(R, D)                                                      \
   do {                                                                       \
-    bn_bwd_reduce_kernel<R, D><<<(int)blocks, kEwThreads, sm, st>>>(p);      \
+    bn_bwd_reduce_kernel<R, D><<<(int)rblocks, kEwThreads, sm, st>>>(p);     \
     PP_LAUNCH_CHECK();                                                       \
     bn_bwd_apply_kernel<R, D><<<(int)blocks, kEwThreads, 0, st>>>(p);        \
     PP_LAUNCH_CHECK();                                                       \

@@ -458,14 +458,15 @@ class _HeadFn(torch.autograd.Function):
         (wk,) = ctx.saved_tensors
         L1, L2, L3, L4, Lc, Ll, Ld1, Ld2 = layers
 
-        def layer_bwd(L, dy, c_off_dy, need_dx=True, cout_pad=256, dx_valid=None, dx_pad=None):
+        def layer_bwd(L, dy, c_off_dy, need_dx=True, cout_pad=256, dx_valid=None, dx_pad=None, draw_out=None, draw_c_off=0):
             """returns (dW [Cout, Cin, k, k], dgamma, dbeta, dX bf16 NHWC or None, draw)."""
             st = L.stats
             C = st.shape[1]
             draw, sums = _lib.bn_bwd(dy, c_off_dy, L.raw, L.c_off, C, st[0], st[1], st[2], st[3], L.relu, drop_p=L.p,
-                                     seed=seed, offset=L.offset, seed_dev=model._rng_step)
+                                     seed=seed, offset=L.offset, seed_dev=model._rng_step, draw_out=draw_out,
+                                     draw_c_off=draw_c_off)
             N_, H_, W_ = L.x.shape[0], L.x.shape[1], L.x.shape[2]
-            draw4 = draw.view(N_, H_, W_, C)
+            draw4 = draw.view(N_, H_, W_, C) if draw_out is None else draw_out[..., draw_c_off:draw_c_off + C]
             dw = _lib.conv_wgrad(L.x, L.cin, draw4, C if C in (64, 128, 256) else cout_pad, L.taps, L.dil)
             k = int(round(L.taps ** 0.5))
             dW = dw[:, :L.cin, :L.C].permute(2, 1, 0).reshape(L.C, L.cin, k, k)
@@ -492,12 +493,23 @@ class _HeadFn(torch.autograd.Function):
         d_pre = draw_c1.float().sum(dim=(1, 2))  # gradient of the per-image bias = pooled-branch contribution
         dwc = torch.zeros((256, 1280, 1, 1), dtype=torch.float32, device=dlogits.device)
         dwc[:, :1024] = dwc_main
-        d_xh = None
+        # four ASPP branches: BatchNorm backward of each writes its slice of ONE 1024-wide gradient buffer; the data
+        # gradient wrt the backbone feature is then a single implicit GEMM over all 1 + 9 + 9 + 9 taps (per-branch
+        # dilations), summed in the TMEM accumulator instead of four fp32 partial maps in HBM
         outs = []
+        draw_cat = torch.empty((B, h, w, 1024), dtype=torch.bfloat16, device=dlogits.device)
+        cin_pad = xh.shape[3]
+        n_taps = sum(L.taps for L in (L1, L2, L3, L4))
+        w_all = torch.empty((n_taps, cin_pad, 256), dtype=torch.bfloat16, device=dlogits.device)
+        entries, t0 = [], 0
         for i, L in enumerate((L1, L2, L3, L4)):
-            dW, dg, db, dx, _ = layer_bwd(L, d_cat, 256 * i)
+            dW, dg, db, _, _ = layer_bwd(L, d_cat, 256 * i, need_dx=False, draw_out=draw_cat, draw_c_off=256 * i)
             outs += [dW, dg, db]
-            d_xh = dx.float() if d_xh is None else d_xh + dx.float()
+            _lib.pack_conv_weights(L.w, L.cin, dgrad_pad=(cin_pad, 256), dgrad_out=w_all[t0:t0 + L.taps])
+            for t in range(L.taps):
+                entries.append(((t // 3 - 1) * L.dil, (t % 3 - 1) * L.dil, 256 * i) if L.taps == 9 else (0, 0, 256 * i))
+            t0 += L.taps
+        d_xh = _lib.conv_igemm_multi(draw_cat, w_all, entries, cin_pad)
         d_high = d_xh[..., :cin].permute(0, 3, 1, 2).to(ctx.high_dtype)
         grads = outs + [dwc, dgc, dbc, dwl, dgl, dbl, dwd1, dgd1, dbd1, dwd2, dgd2, dbd2, dwk, dbk]
         return (None, None, d_high, d_low, d_pre) + tuple(grads)

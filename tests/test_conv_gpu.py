@@ -86,3 +86,31 @@ def test_dgrad_is_conv_with_flipped_transposed_weights():
     wp = _lib.pack_conv_weight(w.to(DEV), transpose_for_dgrad=True)
     gx = _lib.conv_igemm(gy.permute(0, 2, 3, 1).contiguous().to(DEV), wp, Cin, dil=dil, out_mode=1).cpu()
     assert (gx - x.grad).abs().max().item() < 1e-3 * x.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("N,H,W,Cin,dils", [(2, 16, 32, 320, (1, 6, 12, 18)), (1, 32, 64, 2048, (1, 12, 24, 36)),
+                                            (1, 23, 30, 320, (1, 6, 12, 18))])
+def test_fused_aspp_dgrad_multi_tap_table(N, H, W, Cin, dils):
+    """pp_conv_igemm_multi: the data gradient of the four ASPP branches (aspp.py:49-52,64-68) as ONE implicit GEMM over
+    1 + 9 + 9 + 9 tap entries reading channel slices of a 1024-wide gradient buffer == sum of four conv2d input grads."""
+    g = torch.Generator().manual_seed(Cin + H)
+    ws = [(torch.randn((256, Cin, 1 if d == 1 else 3, 1 if d == 1 else 3), generator=g) / 40).to(torch.bfloat16) for d in dils]
+    gy = torch.randn((N, 1024, H, W), generator=g).to(torch.bfloat16)
+    x = torch.zeros((N, Cin, H, W), requires_grad=True)
+    tot = 0
+    for i, (w, d) in enumerate(zip(ws, dils)):
+        y = F.conv2d(x, w.float(), padding=0 if d == 1 else d, dilation=d)
+        tot = tot + (y * gy[:, 256 * i:256 * (i + 1)].float()).sum()
+    tot.backward()
+    cin_pad = -(-Cin // 64) * 64
+    n_taps = sum(w.shape[2] * w.shape[3] for w in ws)
+    w_all = torch.empty((n_taps, cin_pad, 256), dtype=torch.bfloat16, device=DEV)
+    entries, t0 = [], 0
+    for i, (w, d) in enumerate(zip(ws, dils)):
+        taps = w.shape[2] * w.shape[3]
+        _lib.pack_conv_weights(w.float().to(DEV), Cin, dgrad_pad=(cin_pad, 256), dgrad_out=w_all[t0:t0 + taps])
+        entries += [((t // 3 - 1) * d, (t % 3 - 1) * d, 256 * i) if taps == 9 else (0, 0, 256 * i) for t in range(taps)]
+        t0 += taps
+    gx = _lib.conv_igemm_multi(gy.permute(0, 2, 3, 1).contiguous().to(DEV), w_all, entries, cin_pad)
+    got = gx[..., :Cin].float().permute(0, 3, 1, 2).cpu()
+    assert (got - x.grad).abs().max().item() < 8e-3 * x.grad.abs().max().item()
