@@ -234,6 +234,22 @@ int pp_bn_bwd_res(const void* dy, int ld_dy, int c_off_dy, const void* raw, int 
                   const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
                   uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const void* res, int ld_res, void* dres,
                   float* sums, void* draw, int ld_draw, int c_off_draw, void* stream);
+/* Single-launch train-mode BatchNorm (+activation/residual/dropout) forward and backward: both passes of the layer
+ * (statistics -> normalise; reduce -> input gradient) in ONE cooperative kernel around a grid-wide barrier, instead of
+ * memset + stats + finalize + apply (+ memset + reduce + apply).  Same arithmetic as the separate entry points.
+ * scratch: pp_bn_scratch_bytes(C) bytes of device memory, ZERO before the first call; each call leaves it zeroed again
+ * (one scratch may serve the forward and the backward of a layer, not two kernels in flight at once).
+ * pp_bn_fwd_fused also writes stats_out f32 [4][C] = (scale, shift, mean, rstd), updates running_mean / running_var
+ * (nn.BatchNorm2d semantics; NULL to skip) and increments *num_batches_tracked (device int64; NULL to skip). */
+int pp_bn_scratch_bytes(int C, size_t* out_bytes);
+int pp_bn_fwd_fused(const void* raw, int64_t M, int ld_in, int c_off_in, int C, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, long long* num_batches_tracked, float eps, float momentum,
+                    int relu, float drop_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const void* res,
+                    int ld_res, void* out, int ld_out, int c_off_out, float* stats_out, void* scratch, void* stream);
+int pp_bn_bwd_fused(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_raw, int c_off_raw, int64_t M, int C,
+                    const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
+                    uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const void* res, int ld_res, void* dres,
+                    float* sums, void* draw, int ld_draw, int c_off_draw, void* scratch, void* stream);
 /* bilinear align_corners=True resize of bf16 NHWC into a channel slice, and its adjoint (gather form: deterministic,
  * grad_in f32 [N,h,w,C] fully overwritten). */
 int pp_upsample_nhwc_bf16(const void* in, int N, int h, int w, int C, int ld_in, void* out, int H, int W, int ld_out,

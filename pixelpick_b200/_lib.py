@@ -58,6 +58,11 @@ _SIGNATURES = {
     "pp_bn_apply_res": ([_vp, _i64, _i, _i, _i, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i, _vp, _i, _i, _vp], _i),
     "pp_bn_bwd_res": ([_vp, _i, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i,
                        _vp, _vp, _vp, _i, _i, _vp], _i),
+    "pp_bn_scratch_bytes": ([_i, C.POINTER(_sz)], _i),
+    "pp_bn_fwd_fused": ([_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i,
+                         _vp, _i, _i, _vp, _vp, _vp], _i),
+    "pp_bn_bwd_fused": ([_vp, _i, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i,
+                         _vp, _vp, _vp, _i, _i, _vp, _vp], _i),
     "pp_conv_igemm_multi": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i,
                              _i, _vp], _i),
     "pp_dwconv3x3_fwd": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
@@ -427,8 +432,41 @@ def bn_apply(raw, c_off_in, C, scale, shift, relu, out, c_off_out, drop_p=0.0, s
     return out
 
 
+# Single-launch (cooperative) BatchNorm passes.  PP_BN_FUSED=0 falls back to the separate stats/finalize/apply kernels
+# (same arithmetic; used by the tests to cross-check the two paths).
+BN_FUSED = os.environ.get("PP_BN_FUSED", "1") != "0"
+
+
+def bn_scratch(bn, C, device):
+    """Zero-initialised per-layer scratch (2*C partial sums + 2 counters) kept on the nn.BatchNorm2d object; every fused
+    launch leaves it zeroed again."""
+    sc = getattr(bn, "_pp_scratch", None)
+    if sc is None or sc.device != device or sc.numel() != 2 * C + 2:
+        sc = torch.zeros(2 * C + 2, dtype=torch.float32, device=device)
+        bn._pp_scratch = sc
+    return sc
+
+
+def bn_fwd_fused(raw, c_off_in, C, bn, relu, out, c_off_out, drop_p=0.0, seed=0, offset=0, seed_dev=None, res=None,
+                 update_running=True):
+    """train-mode BatchNorm statistics + normalise/activation/residual/dropout in ONE launch; returns stats f32 [4, C]."""
+    _need_cuda(raw, out, res)
+    ld_in, ld_out = raw.shape[-1], out.shape[-1]
+    M = raw.numel() // ld_in
+    stats = torch.empty((4, C), dtype=torch.float32, device=raw.device)
+    upd = update_running and bn.track_running_stats and bn.running_mean is not None
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    check(lib().pp_bn_fwd_fused(_ptr(raw), M, ld_in, c_off_in, C, _ptr(bn.weight.detach()), _ptr(bn.bias.detach()),
+                                _ptr(bn.running_mean) if upd else None, _ptr(bn.running_var) if upd else None,
+                                _ptr(bn.num_batches_tracked) if upd else None, bn.eps, mom, int(relu), float(drop_p),
+                                int(seed), int(offset), _ptr(seed_dev), _ptr(res), res.shape[-1] if res is not None else 0,
+                                _ptr(out), ld_out, c_off_out, _ptr(stats), _ptr(bn_scratch(bn, C, raw.device)),
+                                _stream(raw)), "pp_bn_fwd_fused")
+    return stats
+
+
 def bn_bwd(dy, c_off_dy, raw, c_off_raw, C, scale, shift, mean, rstd, relu, drop_p=0.0, seed=0, offset=0,
-           seed_dev=None, res=None, draw_out=None, draw_c_off=0):
+           seed_dev=None, res=None, draw_out=None, draw_c_off=0, scratch=None):
     """returns (draw bf16 [M, C], sums f32 [2, C] = (d beta, d gamma)) — plus dres bf16 [M, C] (gradient wrt the
     residual that was added before the activation) when `res` is given."""
     _need_cuda(dy, raw, res)
@@ -441,10 +479,17 @@ def bn_bwd(dy, c_off_dy, raw, c_off_raw, C, scale, shift, mean, rstd, relu, drop
         assert draw.dtype == torch.bfloat16 and draw.is_contiguous() and draw.numel() // ld_draw == M
     sums = torch.empty((2, C), dtype=torch.float32, device=raw.device)
     dres = torch.empty((M, C), dtype=torch.bfloat16, device=raw.device) if res is not None else None
-    check(lib().pp_bn_bwd_res(_ptr(dy), ld_dy, c_off_dy, _ptr(raw), ld_raw, c_off_raw, M, C, _ptr(scale), _ptr(shift),
-                              _ptr(mean), _ptr(rstd), int(relu), float(drop_p), int(seed), int(offset), _ptr(seed_dev),
-                              _ptr(res), res.shape[-1] if res is not None else 0, _ptr(dres),
-                              _ptr(sums), _ptr(draw), ld_draw, draw_c_off, _stream(raw)), "pp_bn_bwd")
+    if scratch is not None and BN_FUSED:  # one cooperative launch (reduce -> grid barrier -> apply)
+        check(lib().pp_bn_bwd_fused(_ptr(dy), ld_dy, c_off_dy, _ptr(raw), ld_raw, c_off_raw, M, C, _ptr(scale), _ptr(shift),
+                                    _ptr(mean), _ptr(rstd), int(relu), float(drop_p), int(seed), int(offset),
+                                    _ptr(seed_dev), _ptr(res), res.shape[-1] if res is not None else 0, _ptr(dres),
+                                    _ptr(sums), _ptr(draw), ld_draw, draw_c_off, _ptr(scratch), _stream(raw)),
+              "pp_bn_bwd_fused")
+    else:
+        check(lib().pp_bn_bwd_res(_ptr(dy), ld_dy, c_off_dy, _ptr(raw), ld_raw, c_off_raw, M, C, _ptr(scale), _ptr(shift),
+                                  _ptr(mean), _ptr(rstd), int(relu), float(drop_p), int(seed), int(offset), _ptr(seed_dev),
+                                  _ptr(res), res.shape[-1] if res is not None else 0, _ptr(dres),
+                                  _ptr(sums), _ptr(draw), ld_draw, draw_c_off, _stream(raw)), "pp_bn_bwd")
     if res is not None:
         return draw, sums, dres
     return draw, sums

@@ -69,9 +69,8 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const __nv_bfloat16* p) {
 
 // ---- BN statistics -------------------------------------------------------------------------
 // sums[0][c] += sum_rows raw, sums[1][c] += sum_rows raw^2   (fp32, caller zeroes)
-__global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const __nv_bfloat16* __restrict__ raw, int64_t M, int ld,
-                                                              int c_off, int C, float* __restrict__ sums) {
-  extern __shared__ float sh[];  // [kEwThreads][16] reduced per channel group
+__device__ __forceinline__ void bn_stats_body(const __nv_bfloat16* __restrict__ raw, int64_t M, int ld, int c_off, int C,
+                                              float* __restrict__ sums, float* sh /*[kEwThreads][16]*/) {
   const int groups = C >> 3;     // 8-channel groups per row
   const int rows_per_block = kEwThreads / groups;
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
@@ -99,7 +98,14 @@ __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const __nv_bfloat1
 #pragma unroll
       for (int u = 0; u < 8; ++u) acc8(v[u]);
     }
-    for (; row < M; row += stride) acc8(ldg_stream_u4(base + row * ld));
+    if (row < M) {  // tail: one predicated batch (bf16 zeros add nothing to either sum)
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (row + u * stride < M) ? ldg_stream_u4(base + (row + u * stride) * ld) : z;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc8(v[u]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -115,6 +121,11 @@ __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const __nv_bfloat1
     const int c = gg * 8 + (slot & 7);
     atomicAdd(sums + (slot >> 3) * C + c, acc);
   }
+}
+__global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const __nv_bfloat16* __restrict__ raw, int64_t M, int ld,
+                                                              int c_off, int C, float* __restrict__ sums) {
+  extern __shared__ float sh[];
+  bn_stats_body(raw, M, ld, c_off, C, sums, sh);
 }
 
 // ---- BN apply (+ReLU, +dropout) --------------------------------------------------------------
@@ -134,7 +145,7 @@ struct BnApplyParams {
   int ld_res;
 };
 template <bool RES, bool DROP>
-__global__ void __launch_bounds__(kEwThreads, 4) bn_apply_kernel(const BnApplyParams p) {
+__device__ __forceinline__ void bn_apply_body(const BnApplyParams& p, const float (&sc)[8], const float (&sf)[8]) {
   // thread -> fixed 8-channel group (scale/shift live in registers), rows strided over the grid
   const int groups = p.C >> 3;
   const int rows_per_block = kEwThreads / groups;
@@ -142,12 +153,6 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_apply_kernel(const BnApplyPa
   if (r >= rows_per_block) return;
   const float keep_scale = DROP ? 1.f / (1.f - p.drop_p) : 1.f;
   const uint64_t seed = p.seed + ((DROP && p.seed_dev) ? *p.seed_dev : 0ull);
-  float sc[8], sf[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = __ldg(p.scale + g * 8 + j);
-    sf[j] = __ldg(p.shift + g * 8 + j);
-  }
   const int64_t stride = (int64_t)gridDim.x * rows_per_block;
   const __nv_bfloat16* base = p.raw + p.c_off_in + g * 8;
   const __nv_bfloat16* rbase = RES ? p.res + g * 8 : nullptr;
@@ -180,8 +185,29 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_apply_kernel(const BnApplyPa
 #pragma unroll
     for (int u = 0; u < 4; ++u) finish(row + u * stride, v[u], rv[u]);
   }
-  for (; row < p.M; row += stride)
-    finish(row, ldg_stream_u4(base + row * p.ld_in), RES ? ldg_stream_u4(rbase + row * p.ld_res) : z);
+  if (row < p.M) {  // tail: one predicated batch, loads still issued together
+    uint4 v[4], rv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = row + u * stride < p.M;
+      v[u] = ok ? ldg_stream_u4(base + (row + u * stride) * p.ld_in) : z;
+      rv[u] = (RES && ok) ? ldg_stream_u4(rbase + (row + u * stride) * p.ld_res) : z;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (row + u * stride < p.M) finish(row + u * stride, v[u], rv[u]);
+  }
+}
+template <bool RES, bool DROP>
+__global__ void __launch_bounds__(kEwThreads, 4) bn_apply_kernel(const BnApplyParams p) {
+  const int g = threadIdx.x % (p.C >> 3);
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(p.scale + g * 8 + j);
+    sf[j] = __ldg(p.shift + g * 8 + j);
+  }
+  bn_apply_body<RES, DROP>(p, sc, sf);
 }
 
 // ---- BN backward -----------------------------------------------------------------------------
@@ -212,12 +238,14 @@ struct BnBwdParams {
 struct BnBwdVec {
   uint4 dy, x, res;
 };
-template <bool RES>
+template <bool RES, bool PRED = false>
 __device__ __forceinline__ BnBwdVec bn_bwd_load(const BnBwdParams& p, int64_t row, int g) {
   BnBwdVec v;
-  v.dy = ldg_stream_u4(p.dy + row * p.ld_dy + p.c_off_dy + g * 8);
-  v.x = ldg_stream_u4(p.raw + row * p.ld_raw + p.c_off_raw + g * 8);
-  v.res = RES ? ldg_stream_u4(p.res + row * p.ld_res + g * 8) : make_uint4(0u, 0u, 0u, 0u);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const bool ok = !PRED || row < p.M;  // tail batches past the end load nothing
+  v.dy = ok ? ldg_stream_u4(p.dy + row * p.ld_dy + p.c_off_dy + g * 8) : z;
+  v.x = ok ? ldg_stream_u4(p.raw + row * p.ld_raw + p.c_off_raw + g * 8) : z;
+  v.res = (RES && ok) ? ldg_stream_u4(p.res + row * p.ld_res + g * 8) : z;
   return v;
 }
 template <bool RES, bool DROP>
@@ -242,8 +270,7 @@ __device__ __forceinline__ void bn_bwd_g8(const BnBwdParams& p, uint64_t seed, f
 }
 
 template <bool RES, bool DROP>
-__global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_kernel(const BnBwdParams p) {
-  extern __shared__ float sh[];
+__device__ __forceinline__ void bn_bwd_reduce_body(const BnBwdParams& p, float* __restrict__ sums, float* sh) {
   const int groups = p.C >> 3;
   const int rows_per_block = kEwThreads / groups;
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
@@ -279,7 +306,14 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_kernel(const BnBw
 #pragma unroll
       for (int u = 0; u < 4; ++u) acc(row + u * stride, v[u]);
     }
-    for (; row < p.M; row += stride) acc(row, bn_bwd_load<RES>(p, row, g));
+    if (row < p.M) {
+      BnBwdVec v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = bn_bwd_load<RES, true>(p, row + u * stride, g);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (row + u * stride < p.M) acc(row + u * stride, v[u]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -291,12 +325,17 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_kernel(const BnBw
     const int gg = t / 16, slot = t % 16;
     float acc = 0.f;
     for (int rr = 0; rr < rows_per_block; ++rr) acc += sh[(rr * groups + gg) * 16 + slot];
-    atomicAdd(p.sums + (slot >> 3) * p.C + gg * 8 + (slot & 7), acc);
+    atomicAdd(sums + (slot >> 3) * p.C + gg * 8 + (slot & 7), acc);
   }
 }
-
 template <bool RES, bool DROP>
-__global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_apply_kernel(const BnBwdParams p) {
+__global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_kernel(const BnBwdParams p) {
+  extern __shared__ float sh[];
+  bn_bwd_reduce_body<RES, DROP>(p, p.sums, sh);
+}
+
+template <bool RES, bool DROP, int BATCH>
+__device__ __forceinline__ void bn_bwd_apply_body(const BnBwdParams& p, const float* __restrict__ sums) {
   // d_raw = scale * (g - mean(g) - xhat * mean(g xhat)) = A*g + B*x + K with per-channel A, B, K held in registers
   const int groups = p.C >> 3;
   const int rows_per_block = kEwThreads / groups;
@@ -312,7 +351,7 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_apply_kernel(const BnBwd
     sc[j] = __ldg(p.scale + c);
     sf[j] = __ldg(p.shift + c);
     const float mu = __ldg(p.mean + c), rs = __ldg(p.rstd + c);
-    const float mg = __ldg(p.sums + c) * inv_m, mgx = __ldg(p.sums + p.C + c) * inv_m;
+    const float mg = __ldcg(sums + c) * inv_m, mgx = __ldcg(sums + p.C + c) * inv_m;
     cb[j] = -sc[j] * rs * mgx;
     ck[j] = -sc[j] * (mg - mu * rs * mgx);
   }
@@ -326,12 +365,133 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_apply_kernel(const BnBwd
     if (RES && p.dres) *reinterpret_cast<uint4*>(p.dres + row * p.C + g * 8) = pack8(gg);
   };
   int64_t row = (int64_t)blockIdx.x * rows_per_block + r;
-  for (; row + stride < p.M; row += 2 * stride) {
-    const BnBwdVec v0 = bn_bwd_load<RES>(p, row, g), v1 = bn_bwd_load<RES>(p, row + stride, g);
-    finish(row, v0);
-    finish(row + stride, v1);
+  for (; row + (BATCH - 1) * stride < p.M; row += BATCH * stride) {
+    BnBwdVec v[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) v[u] = bn_bwd_load<RES>(p, row + u * stride, g);
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) finish(row + u * stride, v[u]);
   }
-  for (; row < p.M; row += stride) finish(row, bn_bwd_load<RES>(p, row, g));
+  if (row < p.M) {
+    BnBwdVec v[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) v[u] = bn_bwd_load<RES, true>(p, row + u * stride, g);
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u)
+      if (row + u * stride < p.M) finish(row + u * stride, v[u]);
+  }
+}
+template <bool RES, bool DROP>
+__global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_apply_kernel(const BnBwdParams p) {
+  bn_bwd_apply_body<RES, DROP, 2>(p, p.sums);
+}
+
+// ---- single-launch BatchNorm passes (cooperative grid barrier) ------------------------------------------
+// The 59-61 BatchNorm layers of a train step are each "reduce over everything, then touch everything again": as
+// separate kernels that is memset + stats + finalize + apply (+ memset + reduce + apply backward) = 7 launches per
+// layer, and at the reference batch (4 images) the step is launch-bound.  Launched cooperatively (all CTAs
+// co-resident), one kernel does both passes around a grid-wide barrier: 2 launches per layer, the second pass of a
+// small tensor re-reads L2.  scratch = 2*C fp32 partial sums + 2 u32 counters, zero before the launch; the last CTA to
+// leave zeroes it again, so one cudaMemset at allocation serves every later launch.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned n_ctas) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < n_ctas);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void scratch_release(float* sums, int n_sums, unsigned* bar, unsigned n_ctas) {
+  __shared__ unsigned last;
+  __syncthreads();  // every thread of this CTA is done reading the sums
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicAdd(bar + 1, 1u) == n_ctas - 1u) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (last) {
+    for (int i = threadIdx.x; i < n_sums; i += blockDim.x) sums[i] = 0.f;
+    if (threadIdx.x == 0) {
+      bar[0] = 0u;
+      bar[1] = 0u;
+    }
+  }
+}
+
+struct BnFwdFusedParams {
+  BnApplyParams a;  // a.scale / a.shift unused
+  const float* gamma;
+  const float* beta;
+  float* running_mean;  // nullable
+  float* running_var;
+  long long* nbt;  // nullable: num_batches_tracked += 1
+  float eps, momentum;
+  float* stats_out;  // [4][C]: scale, shift, mean, rstd (what the backward needs)
+  float* sums;       // scratch [2][C]
+  unsigned* bar;     // scratch [2]
+};
+__device__ __forceinline__ void bn_finalize_one(const float* sums, int C, int c, float inv_m, float eps, float gamma,
+                                                float beta, float& scale, float& shift, float& mean, float& var,
+                                                float& rstd) {
+  mean = __ldcg(sums + c) * inv_m;
+  var = fmaxf(fmaf(-mean, mean, __ldcg(sums + C + c) * inv_m), 0.f);
+  rstd = rsqrtf(var + eps);
+  scale = gamma * rstd;
+  shift = fmaf(-mean, scale, beta);
+}
+template <bool RES, bool DROP>
+__global__ void __launch_bounds__(kEwThreads, 4) bn_fwd_fused_kernel(const BnFwdFusedParams q) {
+  extern __shared__ float sh[];
+  const BnApplyParams& p = q.a;
+  bn_stats_body(p.raw, p.M, p.ld_in, p.c_off_in, p.C, q.sums, sh);
+  grid_barrier(q.bar, gridDim.x);
+  const float inv_m = 1.f / (float)p.M;
+  const int g = threadIdx.x % (p.C >> 3);
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    float mean, var, rstd;
+    bn_finalize_one(q.sums, p.C, c, inv_m, q.eps, __ldg(q.gamma + c), __ldg(q.beta + c), sc[j], sf[j], mean, var, rstd);
+  }
+  if (blockIdx.x == 0) {
+    const float unbias = p.M > 1 ? (float)p.M / (float)(p.M - 1) : 1.f;
+    for (int c = threadIdx.x; c < p.C; c += kEwThreads) {
+      float scale, shift, mean, var, rstd;
+      bn_finalize_one(q.sums, p.C, c, inv_m, q.eps, __ldg(q.gamma + c), __ldg(q.beta + c), scale, shift, mean, var, rstd);
+      q.stats_out[c] = scale;
+      q.stats_out[p.C + c] = shift;
+      q.stats_out[2 * p.C + c] = mean;
+      q.stats_out[3 * p.C + c] = rstd;
+      if (q.running_mean) {
+        q.running_mean[c] = fmaf(q.momentum, mean - q.running_mean[c], q.running_mean[c]);
+        q.running_var[c] = fmaf(q.momentum, var * unbias - q.running_var[c], q.running_var[c]);
+      }
+    }
+    if (threadIdx.x == 0 && q.nbt) *q.nbt += 1;
+  }
+  bn_apply_body<RES, DROP>(p, sc, sf);
+  scratch_release(q.sums, 2 * p.C, q.bar, gridDim.x);
+}
+
+struct BnBwdFusedParams {
+  BnBwdParams b;  // b.sums = OUTPUT copy of (d beta, d gamma) [2][C]
+  float* sums;    // scratch [2][C]
+  unsigned* bar;  // scratch [2]
+};
+template <bool RES, bool DROP>
+__global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_fused_kernel(const BnBwdFusedParams q) {
+  extern __shared__ float sh[];
+  bn_bwd_reduce_body<RES, DROP>(q.b, q.sums, sh);
+  grid_barrier(q.bar, gridDim.x);
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < 2 * q.b.C; i += kEwThreads) q.b.sums[i] = __ldcg(q.sums + i);
+  bn_bwd_apply_body<RES, DROP, 4>(q.b, q.sums);
+  scratch_release(q.sums, 2 * q.b.C, q.bar, gridDim.x);
 }
 
 // ---- bilinear upsample NHWC bf16 (align_corners=True) -----------------------------------------
@@ -457,6 +617,31 @@ static inline int ew_grid(int64_t total) {
 
 }  // namespace pp
 
+namespace pp {
+// cooperative launch with the grid clamped to what can be co-resident
+template <typename K, typename P>
+static int launch_coop(K kernel, const P& params, int64_t blocks_wanted, size_t smem, cudaStream_t st, const char* what) {
+  int dev = 0, sms = 0, occ = 0;
+  PP_CUDA(cudaGetDevice(&dev));
+  PP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kEwThreads, smem));
+  if (occ < 1) {
+    set_error("%s: kernel cannot be resident", what);
+    return PP_ERR_CUDA;
+  }
+  int64_t grid = (int64_t)occ * sms;
+  if (blocks_wanted < grid) grid = blocks_wanted;
+  if (grid < 1) grid = 1;
+  P local = params;
+  void* args[] = {&local};
+  PP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3((unsigned)grid), dim3(kEwThreads), args, smem,
+                                      st));
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+}  // namespace pp
+
 using namespace pp;
 
 extern "C" {
@@ -559,6 +744,77 @@ int pp_bn_bwd_res(const void* dy, int ld_dy, int c_off_dy, const void* raw, int 
   else PP_BN_BWD(false, false);
 #undef PP_BN_BWD
   return PP_OK;
+}
+
+int pp_bn_scratch_bytes(int C, size_t* out_bytes) {
+  PP_CHECK_ARG(out_bytes && C > 0, "pp_bn_scratch_bytes: bad args");
+  *out_bytes = ((size_t)2 * C + 2) * sizeof(float);
+  return PP_OK;
+}
+
+int pp_bn_fwd_fused(const void* raw, int64_t M, int ld_in, int c_off_in, int C, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, long long* num_batches_tracked, float eps, float momentum,
+                    int relu, float drop_p, uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const void* res,
+                    int ld_res, void* out, int ld_out, int c_off_out, float* stats_out, void* scratch, void* stream) {
+  PP_CHECK_ARG(raw && out && gamma && beta && stats_out && scratch && M > 0, "pp_bn_fwd_fused: bad args");
+  PP_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && ld_in % 8 == 0 && c_off_in % 8 == 0 && ld_out % 8 == 0 && c_off_out % 8 == 0,
+               "pp_bn_fwd_fused: channel counts/offsets must be multiples of 8 (C <= 2048)");
+  PP_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "pp_bn_fwd_fused: drop_p=%f", drop_p);
+  PP_CHECK_ARG(!res || (ld_res % 8 == 0 && ld_res >= C), "pp_bn_fwd_fused: residual ld=%d", ld_res);
+  PP_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "pp_bn_fwd_fused: running stats come in pairs");
+  BnFwdFusedParams q;
+  BnApplyParams& p = q.a;
+  p.raw = reinterpret_cast<const __nv_bfloat16*>(raw);
+  p.M = M; p.ld_in = ld_in; p.c_off_in = c_off_in; p.C = C; p.scale = nullptr; p.shift = nullptr; p.relu = relu;
+  p.drop_p = drop_p; p.seed = seed; p.offset = offset; p.seed_dev = seed_dev;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ld_out = ld_out; p.c_off_out = c_off_out;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.ld_res = ld_res;
+  q.gamma = gamma; q.beta = beta; q.running_mean = running_mean; q.running_var = running_var; q.nbt = num_batches_tracked;
+  q.eps = eps; q.momentum = momentum; q.stats_out = stats_out;
+  q.sums = reinterpret_cast<float*>(scratch);
+  q.bar = reinterpret_cast<unsigned*>(q.sums + 2 * (size_t)C);
+  const int rows_per_block = kEwThreads / (C / 8);
+  const int64_t blocks = (M + rows_per_block * 8 - 1) / (rows_per_block * 8);  // >= 8 rows per thread: fewer partial-sum atomics
+  const size_t sm = kEwThreads * 16 * sizeof(float);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool drop = drop_p > 0.f;
+  if (res && drop) return launch_coop(bn_fwd_fused_kernel<true, true>, q, blocks, sm, st, "pp_bn_fwd_fused");
+  if (res) return launch_coop(bn_fwd_fused_kernel<true, false>, q, blocks, sm, st, "pp_bn_fwd_fused");
+  if (drop) return launch_coop(bn_fwd_fused_kernel<false, true>, q, blocks, sm, st, "pp_bn_fwd_fused");
+  return launch_coop(bn_fwd_fused_kernel<false, false>, q, blocks, sm, st, "pp_bn_fwd_fused");
+}
+
+int pp_bn_bwd_fused(const void* dy, int ld_dy, int c_off_dy, const void* raw, int ld_raw, int c_off_raw, int64_t M, int C,
+                    const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
+                    uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const void* res, int ld_res, void* dres,
+                    float* sums, void* draw, int ld_draw, int c_off_draw, void* scratch, void* stream) {
+  PP_CHECK_ARG(dy && raw && sums && draw && scratch && M > 0, "pp_bn_bwd_fused: bad args");
+  PP_CHECK_ARG(C % 8 == 0 && C <= 2048 && ld_dy % 8 == 0 && c_off_dy % 8 == 0 && ld_raw % 8 == 0 && c_off_raw % 8 == 0,
+               "pp_bn_bwd_fused: C=%d must be a multiple of 8 and <= 2048", C);
+  PP_CHECK_ARG(!res || (ld_res % 8 == 0 && ld_res >= C), "pp_bn_bwd_fused: residual ld=%d", ld_res);
+  PP_CHECK_ARG(ld_draw % 8 == 0 && c_off_draw % 8 == 0 && c_off_draw + C <= ld_draw, "pp_bn_bwd_fused: draw slice ld=%d c_off=%d",
+               ld_draw, c_off_draw);
+  BnBwdFusedParams q;
+  BnBwdParams& p = q.b;
+  p.dy = reinterpret_cast<const __nv_bfloat16*>(dy); p.ld_dy = ld_dy; p.c_off_dy = c_off_dy;
+  p.raw = reinterpret_cast<const __nv_bfloat16*>(raw); p.ld_raw = ld_raw; p.c_off_raw = c_off_raw;
+  p.M = M; p.C = C; p.scale = scale; p.shift = shift; p.mean = mean; p.rstd = rstd; p.relu = relu;
+  p.drop_p = drop_p; p.seed = seed; p.offset = offset; p.seed_dev = seed_dev;
+  p.sums = sums;
+  p.draw = reinterpret_cast<__nv_bfloat16*>(draw); p.ld_draw = ld_draw; p.c_off_draw = c_off_draw;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.ld_res = ld_res;
+  p.dres = reinterpret_cast<__nv_bfloat16*>(dres);
+  q.sums = reinterpret_cast<float*>(scratch);
+  q.bar = reinterpret_cast<unsigned*>(q.sums + 2 * (size_t)C);
+  const int rows_per_block = kEwThreads / (C / 8);
+  const int64_t blocks = (M + rows_per_block * 8 - 1) / (rows_per_block * 8);  // >= 8 rows per thread: fewer partial-sum atomics
+  const size_t sm = kEwThreads * 16 * sizeof(float);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool drop = drop_p > 0.f;
+  if (res && drop) return launch_coop(bn_bwd_fused_kernel<true, true>, q, blocks, sm, st, "pp_bn_bwd_fused");
+  if (res) return launch_coop(bn_bwd_fused_kernel<true, false>, q, blocks, sm, st, "pp_bn_bwd_fused");
+  if (drop) return launch_coop(bn_bwd_fused_kernel<false, true>, q, blocks, sm, st, "pp_bn_bwd_fused");
+  return launch_coop(bn_bwd_fused_kernel<false, false>, q, blocks, sm, st, "pp_bn_bwd_fused");
 }
 
 int pp_upsample_nhwc_bf16(const void* in, int N, int h, int w, int C, int ld_in, void* out, int H, int W, int ld_out,

@@ -35,9 +35,13 @@ class _BNActFn(torch.autograd.Function):
     def forward(ctx, xn, weight, bias, mod, act, res=None):
         C = xn.shape[-1]
         M = xn.numel() // C
-        stats = _lib.bn_finalize(_lib.bn_stats(xn, 0, C), M, mod)
         y = torch.empty_like(xn)
-        _lib.bn_apply(xn, 0, C, stats[0], stats[1], act, y, 0, res=res)
+        if _lib.BN_FUSED and C <= 2048:
+            stats = _lib.bn_fwd_fused(xn, 0, C, mod, act, y, 0, res=res)
+        else:
+            stats = _lib.bn_finalize(_lib.bn_stats(xn, 0, C), M, mod)
+            _lib.bn_apply(xn, 0, C, stats[0], stats[1], act, y, 0, res=res)
+        ctx.mod = mod
         if res is None:
             ctx.save_for_backward(xn, stats)
         else:
@@ -52,7 +56,8 @@ class _BNActFn(torch.autograd.Function):
         C = xn.shape[-1]
         if dy.dtype != torch.bfloat16 or not dy.is_contiguous():
             dy = dy.to(torch.bfloat16).contiguous()
-        out = _lib.bn_bwd(dy, 0, xn, 0, C, stats[0], stats[1], stats[2], stats[3], ctx.act, res=res)
+        out = _lib.bn_bwd(dy, 0, xn, 0, C, stats[0], stats[1], stats[2], stats[3], ctx.act, res=res,
+                          scratch=_lib.bn_scratch(ctx.mod, C, xn.device) if C <= 2048 else None)
         draw, sums = out[0], out[1]
         dres = out[2].view_as(xn) if res is not None else None
         return draw.view_as(xn), sums[1], sums[0], None, None, dres
@@ -408,13 +413,17 @@ class _HeadFn(torch.autograd.Function):
             wp = _pack(wt, cin_pad, cpad or -(-C // 64) * 64, cin=cin_valid)
             _lib.conv_igemm(x, wp, C, dil=dil, pre_bias=pre, out=raw, c_off=c_off, cin=cin_pad)
             rows = raw.numel() // raw.shape[-1]
-            stats = _lib.bn_finalize(_lib.bn_stats(raw, c_off, C), rows, bn, Cpad=cpad or C)
             L = _Layer()
             L.x, L.cin, L.w, L.taps, L.dil, L.raw, L.c_off, L.C = x, cin_valid, wt, taps, dil, raw, c_off, C
-            L.stats, L.relu, L.p, L.bn = stats, relu, p, bn
+            L.relu, L.p, L.bn = relu, p, bn
             L.offset = next_offset(rows * (cpad or C)) if p > 0 else 0
-            _lib.bn_apply(raw, c_off, cpad or C, stats[0], stats[1], relu, out, out_c_off, drop_p=p, seed=seed, offset=L.offset,
-                          seed_dev=model._rng_step)
+            if _lib.BN_FUSED and (cpad is None or cpad == C):
+                L.stats = _lib.bn_fwd_fused(raw, c_off, C, bn, relu, out, out_c_off, drop_p=p, seed=seed, offset=L.offset,
+                                            seed_dev=model._rng_step)
+            else:
+                L.stats = _lib.bn_finalize(_lib.bn_stats(raw, c_off, C), rows, bn, Cpad=cpad or C)
+                _lib.bn_apply(raw, c_off, cpad or C, L.stats[0], L.stats[1], relu, out, out_c_off, drop_p=p, seed=seed,
+                              offset=L.offset, seed_dev=model._rng_step)
             layers.append(L)
             return L
 
@@ -464,7 +473,8 @@ class _HeadFn(torch.autograd.Function):
             C = st.shape[1]
             draw, sums = _lib.bn_bwd(dy, c_off_dy, L.raw, L.c_off, C, st[0], st[1], st[2], st[3], L.relu, drop_p=L.p,
                                      seed=seed, offset=L.offset, seed_dev=model._rng_step, draw_out=draw_out,
-                                     draw_c_off=draw_c_off)
+                                     draw_c_off=draw_c_off,
+                                     scratch=_lib.bn_scratch(L.bn, C, dy.device) if C == L.C else None)
             N_, H_, W_ = L.x.shape[0], L.x.shape[1], L.x.shape[2]
             draw4 = draw.view(N_, H_, W_, C) if draw_out is None else draw_out[..., draw_c_off:draw_c_off + C]
             dw = _lib.conv_wgrad(L.x, L.cin, draw4, C if C in (64, 128, 256) else cout_pad, L.taps, L.dil)

@@ -240,3 +240,64 @@ def test_depthwise_module_matches_conv2d_through_autograd():
     y.backward(go.to(DEV))
     assert (xg.grad.float().cpu() - xr.grad).abs().max().item() < 1e-2 * xr.grad.abs().max().item()
     assert (m.weight.grad.cpu() - ref.weight.grad).abs().max().item() < 2e-3 * ref.weight.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("M,C,relu,p,with_res", [(4 * 16 * 32, 960, 2, 0.0, False), (2 * 64 * 128, 256, 1, 0.5, False),
+                                                 (3 * 9 * 14, 2048, 1, 0.0, True), (1000, 24, 0, 0.0, False),
+                                                 (32 * 64 * 128, 64, 1, 0.0, True)])
+def test_single_launch_bn_matches_separate_kernels(M, C, relu, p, with_res):
+    """pp_bn_fwd_fused / pp_bn_bwd_fused (one cooperative launch, grid barrier) == stats + finalize + apply / reduce +
+    apply; repeated launches reuse the self-zeroing scratch; also replayed from a CUDA graph."""
+    g = torch.Generator().manual_seed(C + M)
+    raw = (torch.randn((M, C), generator=g) * 1.5 + 0.4).to(torch.bfloat16).to(DEV)
+    dy = torch.randn((M, C), generator=g).to(torch.bfloat16).to(DEV)
+    res = torch.randn((M, C), generator=g).to(torch.bfloat16).to(DEV) if with_res else None
+
+    def mk():
+        bn = torch.nn.BatchNorm2d(C)
+        with torch.no_grad():
+            bn.weight.copy_(torch.rand(C, generator=torch.Generator().manual_seed(1)) + 0.5)
+            bn.bias.copy_(torch.randn(C, generator=torch.Generator().manual_seed(2)) * 0.3)
+        return bn.to(DEV)
+
+    bn_a, bn_b = mk(), mk()
+    out_a, out_b = torch.empty_like(raw), torch.empty_like(raw)
+    st_a = _lib.bn_finalize(_lib.bn_stats(raw, 0, C), M, bn_a)
+    _lib.bn_apply(raw, 0, C, st_a[0], st_a[1], relu, out_a, 0, drop_p=p, seed=7, offset=3, res=res)
+    for rep in range(3):  # the scratch must come back zeroed after every launch
+        st_b = _lib.bn_fwd_fused(raw, 0, C, bn_b, relu, out_b, 0, drop_p=p, seed=7, offset=3, res=res,
+                                 update_running=(rep == 0))
+        assert torch.allclose(st_a, st_b, rtol=1e-5, atol=1e-6), rep
+        # the fp32 partial sums are combined by atomics in a different order: scale/shift may differ in the last ulp, so
+        # a few outputs may round to the neighbouring bf16 value
+        d = (out_a.float() - out_b.float()).abs()
+        assert float(d.max()) <= 2 ** -7 * float(out_a.float().abs().max()) and float((d > 0).float().mean()) < 1e-2, rep
+    assert torch.allclose(bn_a.running_mean, bn_b.running_mean, atol=1e-6)
+    assert torch.allclose(bn_a.running_var, bn_b.running_var, rtol=1e-5, atol=1e-6)
+    assert int(bn_b.num_batches_tracked) == 1
+    assert float(bn_b._pp_scratch.abs().max()) == 0.0
+    ref = _lib.bn_bwd(dy, 0, raw, 0, C, st_a[0], st_a[1], st_a[2], st_a[3], relu, drop_p=p, seed=7, offset=3, res=res)
+    sc = _lib.bn_scratch(bn_b, C, DEV)
+    for rep in range(2):
+        got = _lib.bn_bwd(dy, 0, raw, 0, C, st_a[0], st_a[1], st_a[2], st_a[3], relu, drop_p=p, seed=7, offset=3, res=res,
+                          scratch=sc)
+        assert torch.allclose(ref[1], got[1], rtol=2e-4, atol=2e-4 * float(ref[1].abs().max())), rep  # atomics order
+        assert (ref[0].float() - got[0].float()).abs().max().item() <= 2e-2 * ref[0].float().abs().max().item()
+        if with_res:
+            assert torch.equal(ref[2], got[2])
+    assert float(sc.abs().max()) == 0.0
+    # CUDA-graph capture of the cooperative launches
+    stream = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    out_g = torch.empty_like(raw)
+    with torch.cuda.stream(stream):
+        _lib.bn_fwd_fused(raw, 0, C, bn_b, relu, out_g, 0, drop_p=p, seed=7, offset=3, res=res, update_running=False)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=stream):
+            _lib.bn_fwd_fused(raw, 0, C, bn_b, relu, out_g, 0, drop_p=p, seed=7, offset=3, res=res, update_running=False)
+    out_g.zero_()
+    graph.replay()
+    graph.replay()
+    torch.cuda.synchronize()
+    dg = (out_a.float() - out_g.float()).abs()
+    assert float(dg.max()) <= 2 ** -7 * float(out_a.float().abs().max()) and float((dg > 0).float().mean()) < 1e-2
