@@ -365,6 +365,8 @@ constexpr int kSelTile = kSelThreads * kSelItems;  // 4096
 struct SelState {
   uint32_t remaining;
   uint32_t done;
+  uint32_t bucket;  // level-0 bucket (written by pick_bucket0_kernel, read by select_l0_kernel)
+  uint32_t pad;
 };
 
 struct Workspace {
@@ -442,42 +444,18 @@ __global__ void __launch_bounds__(kSelThreads) hist0_kernel(const float* __restr
   }
 }
 
-template <bool L0>
-__global__ void __launch_bounds__(kSelThreads) select_level_kernel(const SelParams p) {
-  __shared__ uint32_t sh_hist[kHistBins];
+// One CTA per image: find the bucket of the level-0 histogram that holds the k-th element; state[img] = {rank inside
+// the bucket, whole bucket selected?, bucket}.  Done once here instead of in the prologue of every select_l0 CTA.
+__global__ void __launch_bounds__(kSelThreads) pick_bucket0_kernel(const uint32_t* __restrict__ hist0, SelState* __restrict__ state,
+                                                                    uint32_t k) {
   __shared__ uint32_t sh_warp[kSelThreads / 32];
-  __shared__ uint32_t sh_pick[3];  // bucket, count before, count in bucket
-  __shared__ uint32_t sh_base[2];
-
-  const int img = blockIdx.y;
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  uint32_t rem;
-  if (L0) {
-    rem = (uint32_t)p.k;
-  } else {
-    const SelState st = p.state_cur[img];
-    if (st.done) {  // a previous level already selected everything: propagate and leave
-      if (blockIdx.x == 0 && threadIdx.x == 0) {
-        SelState nx;
-        nx.remaining = 0;
-        nx.done = 1;
-        p.state_next[img] = nx;
-      }
-      return;
-    }
-    rem = st.remaining;
-  }
-
-  // ---- pick the bucket holding the rem-th element of this level's histogram ----
-  const uint32_t* hc = p.hist_cur + (size_t)img * kHistBins;
-  uint32_t h[8];
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint4* hc = reinterpret_cast<const uint4*>(hist0 + (size_t)img * kHistBins) + tid * 2;
+  const uint4 ha = hc[0], hb = hc[1];
+  const uint32_t h[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
   uint32_t mine = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    h[i] = hc[tid * 8 + i];
-    mine += h[i];
-  }
+  for (int i = 0; i < 8; ++i) mine += h[i];
   uint32_t incl = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -485,7 +463,6 @@ __global__ void __launch_bounds__(kSelThreads) select_level_kernel(const SelPara
     if (lane >= o) incl += t;
   }
   if (lane == 31) sh_warp[warp] = incl;
-  for (int i = tid; i < kHistBins; i += kSelThreads) sh_hist[i] = 0;
   __syncthreads();
   uint32_t wbase = 0;
 #pragma unroll
@@ -494,143 +471,126 @@ __global__ void __launch_bounds__(kSelThreads) select_level_kernel(const SelPara
   uint32_t run = wbase + incl - mine;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    if (run < rem && rem <= run + h[i]) {
-      sh_pick[0] = tid * 8 + i;
-      sh_pick[1] = run;
-      sh_pick[2] = h[i];
+    if (run < k && k <= run + h[i]) {  // exactly one (thread, i) matches
+      SelState st;
+      st.remaining = k - run;
+      st.done = (h[i] == k - run) ? 1u : 0u;
+      st.bucket = (uint32_t)(tid * 8 + i);
+      st.pad = 0u;
+      state[img] = st;
     }
     run += h[i];
   }
-  __syncthreads();
-  const uint32_t bucket = sh_pick[0];
-  const uint32_t rem_next = rem - sh_pick[1];
-  const bool take_all = (sh_pick[2] == rem_next);
-  if (blockIdx.x == 0 && tid == 0) {
-    SelState st;
-    st.remaining = rem_next;
-    st.done = take_all ? 1u : 0u;
-    p.state_next[img] = st;
-  }
+}
 
-  const int shift = c_shift[p.level];
-  const uint32_t dmask = (1u << c_bits[p.level]) - 1u;
-  const int shift_n = c_shift[p.level + 1];
-  const uint32_t dmask_n = (1u << c_bits[p.level + 1]) - 1u;
-  const uint32_t n_in = L0 ? (uint32_t)p.HW : p.in_count[img];
-  const float* sc = L0 ? p.scores + (size_t)img * p.HW : nullptr;
-  const uint64_t* il = L0 ? nullptr : p.in_list + (size_t)img * p.HW;
+// Level 0 of the radix select: ONE pass over the score map.  Each CTA owns one contiguous chunk of 8192 scores, keeps
+// their 32-bit ordering keys in registers (8 x 16-byte streaming loads per thread, all issued before the first use),
+// classifies them against the level-0 bucket with two unsigned range compares, and claims its output ranges with ONE
+// pair of global atomics.  ncu on the previous versions: the tile-walking kernel (atomic round trip + 3 barriers per
+// 4096 scores) ran at 1.7 TB/s; a first single-pass version was ISSUE-bound (58 instructions per score: keys computed
+// twice, per-score range checks, 64-bit masks) — hence the FULL fast path and the key-in-place layout here.
+constexpr int kL0Items = 8;
+constexpr int kL0Chunk = kSelThreads * kL0Items;  // 2048
+template <bool FULL /* every score of the chunk is in range and 16-byte loadable */>
+__global__ void __launch_bounds__(kSelThreads, 8) select_l0_kernel(const SelParams p) {
+  __shared__ uint32_t sh_warp[kSelThreads / 32];
+  __shared__ uint32_t sh_base[2];
+
+  const int img = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t n_in = (uint32_t)p.HW;
+  const float* sc = p.scores + (size_t)img * p.HW;
+  const uint32_t chunk0 = blockIdx.x * (uint32_t)kL0Chunk;
+  const bool largest = p.largest != 0;
+
+  // ---- the chunk's loads go out first; the bucket pick below overlaps their latency ----
+  // FULL: item i = 4 j + e is score chunk0 + (j * 256 + tid) * 4 + e;  otherwise item i is score chunk0 + i * 256 + tid
+  uint32_t key[kL0Items];
+  if (FULL) {
+    // raw bits land in key[] and are turned into ordering keys in place (a separate float4 staging array spilled)
+#pragma unroll
+    for (int j = 0; j < kL0Items / 4; ++j) {
+      const float* src = sc + chunk0 + (uint32_t)(j * kSelThreads + tid) * 4u;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(key[4 * j]), "=r"(key[4 * j + 1]), "=r"(key[4 * j + 2]), "=r"(key[4 * j + 3])
+                   : "l"(src));
+    }
+#pragma unroll
+    for (int i = 0; i < kL0Items; ++i) key[i] = ord_key(__uint_as_float(key[i]), largest);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kL0Items; ++i) {
+      const uint32_t idx = chunk0 + (uint32_t)(i * kSelThreads + tid);
+      key[i] = ord_key((idx < n_in) ? __ldg(sc + idx) : 0.f, largest);
+    }
+  }
+  const uint32_t idx0 = FULL ? chunk0 + (uint32_t)tid * 4u : chunk0 + (uint32_t)tid;
+  auto index_of = [&](int i) -> uint32_t {
+    return FULL ? idx0 + (uint32_t)((i >> 2) * kSelThreads * 4 + (i & 3)) : idx0 + (uint32_t)(i * kSelThreads);
+  };
+
+  // ---- level-0 bucket of this image (pick_bucket0_kernel) ----
+  const SelState st0 = p.state_next[img];
+  const uint32_t bucket = st0.bucket;
+  const bool take_all = st0.done != 0u;
+
+  // ---- classify on the full key: selected <=> key <= sel_max; boundary <=> key - lo <= 0x1FFFFF (and !take_all) ----
+  const uint32_t lo = bucket << 21;
+  const bool sel_any = take_all || bucket > 0;
+  const uint32_t sel_max = take_all ? (lo | 0x1FFFFFu) : lo - 1u;
+  const uint32_t bnd_span = take_all ? 0u : 0x200000u;  // width of the boundary range (0: none)
+  static_assert(kL0Items <= 32, "one 32-bit mask per class");
+  uint32_t sel_m = 0, bnd_m = 0;  // bit i = item i
+#pragma unroll
+  for (int i = 0; i < kL0Items; ++i) {
+    const bool in = FULL || index_of(i) < n_in;
+    const bool s1 = in && sel_any && key[i] <= sel_max;
+    const bool s2 = in && (key[i] - lo) < bnd_span;
+    sel_m |= (uint32_t)s1 << i;
+    bnd_m |= (uint32_t)s2 << i;
+  }
+  const uint32_t nc = (uint32_t)__popc(sel_m), nf = (uint32_t)__popc(bnd_m);
+  // block exclusive scan of (nc, nf) packed 16:16 (a chunk has 8192 items: each count fits 14 bits)
+  const uint32_t packed = nc | (nf << 16);
+  uint32_t inc = packed;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) sh_warp[warp] = inc;
+  __syncthreads();
+  uint32_t wb = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kSelThreads / 32; ++w) {
+    const uint32_t x = sh_warp[w];
+    if (w < warp) wb += x;
+    tot += x;
+  }
+  if (tid == 0) {
+    const uint32_t tc = tot & 0xFFFFu, tf = tot >> 16;
+    sh_base[0] = tc ? atomicAdd(p.cand_count + img, tc) : 0u;
+    sh_base[1] = tf ? atomicAdd(p.out_count + img, tf) : 0u;
+  }
+  __syncthreads();
+  const uint32_t excl = wb + inc - packed;
+  uint32_t oc = sh_base[0] + (excl & 0xFFFFu);
+  uint32_t of = sh_base[1] + (excl >> 16);
   uint64_t* cand = p.cand + (size_t)img * p.kpad;
   uint64_t* ol = p.out_list + (size_t)img * p.HW;
-  const bool largest = p.largest != 0;
-  bool any_filt = false;
-  const bool vec4 = L0 && (p.HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.scores) & 15) == 0);
-
-  for (uint32_t tile = blockIdx.x; (uint64_t)tile * kSelTile < n_in; tile += gridDim.x) {
-    uint64_t comp[kSelItems];
-    uint32_t cls = 0;  // 2 bits per item: 1 = selected, 2 = boundary bucket
-    uint32_t nc = 0, nf = 0;
-    // all loads of the tile are issued before the first use (predicated, no branch): one memory round trip per
-    // tile instead of kSelItems serialised ones
-    uint32_t idxs[kSelItems];
-    if (L0) {
-      if (vec4) {
-        // 4 x 16-byte loads per thread, all issued before the first use (asm volatile keeps them batched: with scalar
-        // __ldg the compiler serialised load->use pairs, i.e. 16 memory round trips per tile)
-        float4 q[4];
+  if ((sel_m | bnd_m) == 0u) return;  // a thread of a 5 % selection often holds nothing
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t base = tile * kSelTile + (j * kSelThreads + tid) * 4;
-          q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (base < n_in) q[j] = ldg_stream_f4(sc + base);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t base = tile * kSelTile + (j * kSelThreads + tid) * 4;
-          const float e4[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            idxs[j * 4 + e] = base + e;
-            comp[j * 4 + e] = ((uint64_t)ord_key(e4[e], largest) << 32) | (base + e);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < kSelItems; ++i) {
-          const uint32_t idx = tile * kSelTile + i * kSelThreads + tid;
-          idxs[i] = idx;
-          const float v = (idx < n_in) ? __ldg(sc + (idx < n_in ? idx : 0u)) : 0.f;
-          comp[i] = ((uint64_t)ord_key(v, largest) << 32) | idx;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < kSelItems; ++i) {
-        const uint32_t idx = tile * kSelTile + i * kSelThreads + tid;
-        idxs[i] = idx;
-        comp[i] = (idx < n_in) ? il[idx < n_in ? idx : 0u] : ~0ull;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kSelItems; ++i) {
-      const uint32_t idx = idxs[i];
-      if (idx < n_in) {
-        const uint32_t d = (uint32_t)(comp[i] >> shift) & dmask;
-        if (d < bucket || (d == bucket && take_all)) {
-          cls |= 1u << (2 * i);
-          ++nc;
-        } else if (d == bucket) {
-          cls |= 2u << (2 * i);
-          ++nf;
-        }
-      }
-    }
-    // block exclusive scan of (nc, nf) packed 16:16 (tile has 4096 items)
-    const uint32_t packed = nc | (nf << 16);
-    uint32_t inc = packed;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    __syncthreads();  // previous iteration done with sh_warp / sh_base
-    if (lane == 31) sh_warp[warp] = inc;
-    __syncthreads();
-    uint32_t wb = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < kSelThreads / 32; ++w) {
-      const uint32_t v = sh_warp[w];
-      if (w < warp) wb += v;
-      tot += v;
-    }
-    if (tid == 0) {
-      const uint32_t tc = tot & 0xFFFFu, tf = tot >> 16;
-      sh_base[0] = tc ? atomicAdd(p.cand_count + img, tc) : 0u;
-      sh_base[1] = tf ? atomicAdd(p.out_count + img, tf) : 0u;
-    }
-    __syncthreads();
-    const uint32_t excl = wb + inc - packed;
-    uint32_t oc = sh_base[0] + (excl & 0xFFFFu);
-    uint32_t of = sh_base[1] + (excl >> 16);
-#pragma unroll
-    for (int i = 0; i < kSelItems; ++i) {
-      const uint32_t c2 = (cls >> (2 * i)) & 3u;
-      if (c2 == 1u) {
-        if (oc < (uint32_t)p.kpad) cand[oc] = comp[i];
+  for (int i = 0; i < kL0Items; ++i) {
+    const bool s1 = (sel_m >> i) & 1u, s2 = (bnd_m >> i) & 1u;
+    if (s1 | s2) {
+      const uint64_t comp = ((uint64_t)key[i] << 32) | index_of(i);
+      if (s1) {
+        if (oc < (uint32_t)p.kpad) cand[oc] = comp;
         ++oc;
-      } else if (c2 == 2u) {
-        ol[of++] = comp[i];
-        if (p.build_next_hist) {
-          atomicAdd(&sh_hist[(uint32_t)(comp[i] >> shift_n) & dmask_n], 1u);
-          any_filt = true;
-        }
+      } else {
+        ol[of++] = comp;
       }
-    }
-  }
-  if (__syncthreads_or(any_filt ? 1 : 0)) {
-    uint32_t* gh = p.hist_next + (size_t)img * kHistBins;
-    for (int i = tid; i < kHistBins; i += kSelThreads) {
-      const uint32_t c = sh_hist[i];
-      if (c) atomicAdd(gh + i, c);
     }
   }
 }
@@ -746,10 +706,13 @@ struct PickParams {
 
 constexpr int kPickItems = 16;  // candidates cached in registers when k <= 512 * 16
 
-__global__ void __launch_bounds__(kPickThreads) pick_ranks_kernel(const PickParams p) {
+__global__ void __launch_bounds__(kPickThreads, 2) pick_ranks_kernel(const PickParams p) {
   extern __shared__ uint32_t sh_h[];  // [kPickRanks][2048]
   __shared__ uint64_t sh_prefix[kPickRanks];
   __shared__ uint32_t sh_rem[kPickRanks];
+  __shared__ uint32_t sh_cnt[kPickRanks];  // elements still matching rank j's prefix after the current level
+  __shared__ uint32_t sh_n[kPickRanks];
+  __shared__ uint32_t sh_small;
   const int img = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t* c = p.cand + (size_t)img * p.kpad;
@@ -838,11 +801,11 @@ __global__ void __launch_bounds__(kPickThreads) pick_ranks_kernel(const PickPara
         uint32_t run = incl - mine;
         const bool here = run < rem && rem <= incl;
         int found = -1;
-        uint32_t before = 0;
+        uint32_t before = 0, in_bin = 0;
         if (here) {
           for (int b = 0; b < 64; ++b) {
             const uint32_t hb = h[lane * 64 + b];
-            if (run < rem && rem <= run + hb) { found = lane * 64 + b; before = run; break; }
+            if (run < rem && rem <= run + hb) { found = lane * 64 + b; before = run; in_bin = hb; break; }
             run += hb;
           }
         }
@@ -850,12 +813,53 @@ __global__ void __launch_bounds__(kPickThreads) pick_ranks_kernel(const PickPara
         const int src = __ffs(m) - 1;
         found = __shfl_sync(0xFFFFFFFFu, found, src);
         before = __shfl_sync(0xFFFFFFFFu, before, src);
+        in_bin = __shfl_sync(0xFFFFFFFFu, in_bin, src);
         if (lane == 0) {
           sh_prefix[j] |= (uint64_t)(uint32_t)found << shift;
           sh_rem[j] = rem - before;
+          sh_cnt[j] = in_bin;
         }
       }
       __syncthreads();
+      // After two levels (22 key bits) a rank's group is normally a handful of elements: finish by ranking each group
+      // directly in one warp instead of walking three more radix levels (each: clear 96 KB of histograms, a pass over
+      // the candidates, a 2048-bin scan per rank).  Falls through to the remaining levels if any group exceeds a warp.
+      if (cached && level == 1) {
+        if (tid == 0) {
+          uint32_t mx = 0;
+          for (int j = 0; j < nr; ++j) mx = sh_cnt[j] > mx ? sh_cnt[j] : mx;
+          sh_small = (mx <= 32u) ? 1u : 0u;
+        }
+        if (tid < kPickRanks) sh_n[tid] = 0;
+        __syncthreads();
+        if (sh_small) {
+          uint64_t* lists = reinterpret_cast<uint64_t*>(sh_h);  // [kPickRanks][32], the histograms are dead here
+          uint64_t pre22[kPickRanks];
+#pragma unroll
+          for (int j = 0; j < kPickRanks; ++j) pre22[j] = (j < nr) ? (sh_prefix[j] >> 42) : ~0ull;
+#pragma unroll
+          for (int i = 0; i < kPickItems; ++i) {
+            if (!((alive >> i) & 1u)) continue;
+            const uint64_t vh = reg[i] >> 42;
+#pragma unroll
+            for (int j = 0; j < kPickRanks; ++j)
+              if (vh == pre22[j]) lists[j * 32 + atomicAdd(&sh_n[j], 1u)] = reg[i];
+          }
+          __syncthreads();
+          for (int j = warp; j < nr; j += kPickThreads / 32) {
+            const uint32_t cnt = sh_n[j];
+            const uint64_t x = (uint32_t)lane < cnt ? lists[j * 32 + lane] : ~0ull;
+            uint32_t below = 0;
+            for (int o = 0; o < 32; ++o) {
+              const uint64_t y = __shfl_sync(0xFFFFFFFFu, x, o);
+              below += (y < x) ? 1u : 0u;
+            }
+            if ((uint32_t)lane < cnt && below + 1u == sh_rem[j]) sh_prefix[j] = x;  // composites are unique
+          }
+          __syncthreads();
+          break;
+        }
+      }
     }
     if (tid < nr) p.out[(size_t)img * p.n + j0 + tid] = (int32_t)(uint32_t)(sh_prefix[tid] & 0xFFFFFFFFull);
     __syncthreads();
@@ -1224,12 +1228,12 @@ static int select_impl(const float* score_map, int n_img, int HW, int k, int lar
     p.kpad = w.kpad;
     p.largest = largest;
     p.build_next_hist = 0;
-    // each CTA walks ~4 tiles so the bucket-pick prologue (2048-bin scan) is amortised
-    int gx = (tiles + 3) / 4;
-    const int cap = (148 * 16 + n_img - 1) / n_img;
-    if (gx > cap) gx = cap;
-    if (gx < 1) gx = 1;
-    select_level_kernel<true><<<dim3(gx, n_img), kSelThreads, 0, st>>>(p);
+    pick_bucket0_kernel<<<n_img, kSelThreads, 0, st>>>(w.hist, w.state + (size_t)n_img, (uint32_t)k);
+    PP_LAUNCH_CHECK();
+    const int gx = (HW + kL0Chunk - 1) / kL0Chunk;  // one chunk of scores per CTA
+    const bool full = (HW % kL0Chunk == 0) && ((reinterpret_cast<uintptr_t>(score_map) & 15) == 0);
+    if (full) select_l0_kernel<true><<<dim3(gx, n_img), kSelThreads, 0, st>>>(p);
+    else select_l0_kernel<false><<<dim3(gx, n_img), kSelThreads, 0, st>>>(p);
     PP_LAUNCH_CHECK();
     RestParams r;
     r.list_a = w.filt;
@@ -1422,6 +1426,8 @@ int pp_acq_pick(void* workspace, size_t workspace_bytes, int n_img, int HW, int 
   const int smem = kPickRanks * kHistBins * (int)sizeof(uint32_t);
   if (!attr) {
     PP_CUDA(cudaFuncSetAttribute(pick_ranks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // two 97 KB CTAs per SM (64 registers / thread): 256 images are then ONE wave on 148 SMs instead of two
+    PP_CUDA(cudaFuncSetAttribute(pick_ranks_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
   PickParams p;
