@@ -186,11 +186,13 @@ int pp_conv_igemm(const void* x, int N, int H, int W, int Cin, int ld_in, const 
  * pixels from channels [tap_c0[t], tap_c0[t] + Cin) of x (a_channels wide) and multiplies weight slice t of
  * w_packed [n_entries][Cout_pad][Cin].  One launch computes e.g. the data gradient of all four ASPP branches
  * (aspp.py:49-52,64-68: 1 + 9 + 9 + 9 taps with their own dilations) accumulated in TMEM, no partial sums in HBM.
- * Host arrays; n_entries <= 28. */
+ * Host arrays; n_entries <= 28.  Extras over pp_conv_igemm: relu = 2 is ReLU6; res (bf16 [pixel][ld_res]) is a residual
+ * added before the activation (the inverted-residual / bottleneck skip, mobilenet_v2.py:66, resnet_models.py:88-92);
+ * a_channels may be smaller than the K-padded Cin for a single channel group (TMA zero-fills the K padding). */
 int pp_conv_igemm_multi(const void* x, int N, int H, int W, int a_channels, int ld_in, int Cin, const void* w_packed,
                         int n_entries, const int* tap_dy, const int* tap_dx, const int* tap_c0, int Cout_pad, int Cout,
-                        const float* pre_bias, const float* scale, const float* shift, int relu, void* out,
-                        int out_mode, int ld_out, int c_off, int block_n, void* stream);
+                        const float* pre_bias, const float* scale, const float* shift, int relu, const void* res,
+                        int ld_res, void* out, int out_mode, int ld_out, int c_off, int block_n, void* stream);
 
 /* Weight gradient of the same convolution on tcgen05 (both operands MN-major, split over pixels):
  *   dw[tap][ci][co] += sum_p x[p + shift(tap)][ci] * dy[p][co]
@@ -262,6 +264,10 @@ int pp_upsample_nhwc_bf16_bwd(const void* grad_out, int N, int H, int W, int ld,
  * Ho = (Hi - 2*dil - 1)/stride + 1.  dgrad writes dx [N][Hi][Wi][C]; wgrad writes dw f32 [C][1][3][3]. */
 int pp_dwconv3x3_fwd(const void* x, const float* w, void* y, int N, int Hi, int Wi, int C, int stride, int dil,
                      void* stream);
+/* inference form: y = act(conv(x) * scale[c] + shift[c]) — eval-mode BatchNorm folded into the epilogue; act 0/1/2 =
+ * none / ReLU / ReLU6 (mobilenet_v2.py:33-37) */
+int pp_dwconv3x3_fwd_bnact(const void* x, const float* w, const float* scale, const float* shift, int act, void* y, int N,
+                           int Hi, int Wi, int C, int stride, int dil, void* stream);
 int pp_dwconv3x3_dgrad(const void* dy, const float* w, void* dx, int N, int Hi, int Wi, int C, int stride, int dil,
                        void* stream);
 int pp_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, int Wi, int C, int stride, int dil,

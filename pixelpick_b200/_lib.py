@@ -63,9 +63,10 @@ _SIGNATURES = {
                          _vp, _i, _i, _vp, _vp, _vp], _i),
     "pp_bn_bwd_fused": ([_vp, _i, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i,
                          _vp, _vp, _vp, _i, _i, _vp, _vp], _i),
-    "pp_conv_igemm_multi": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i,
-                             _i, _vp], _i),
+    "pp_conv_igemm_multi": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i,
+                             _i, _i, _i, _vp], _i),
     "pp_dwconv3x3_fwd": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "pp_dwconv3x3_fwd_bnact": ([_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "pp_dwconv3x3_dgrad": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "pp_dwconv3x3_wgrad": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "pp_upsample_nhwc_bf16": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp], _i),
@@ -375,8 +376,38 @@ def conv_igemm_multi(x_nhwc, w_packed, entries, cout, out=None, block_n=0):
         out = torch.empty((N, H, W, cout), dtype=torch.bfloat16, device=x_nhwc.device)
     arr = lambda k: (C.c_int * n_e)(*[int(e[k]) for e in entries])
     check(lib().pp_conv_igemm_multi(_ptr(x_nhwc), N, H, W, ld_in, ld_in, cin, _ptr(w_packed), n_e, arr(0), arr(1), arr(2),
-                                    cout_pad, cout, None, None, None, 0, _ptr(out), 0, out.shape[3], 0, block_n,
+                                    cout_pad, cout, None, None, None, 0, None, 0, _ptr(out), 0, out.shape[3], 0, block_n,
                                     _stream(x_nhwc)), "pp_conv_igemm_multi")
+    return out
+
+
+_TAPS = {}
+
+
+def conv_fused(x_nhwc, w_packed, cout, dil=1, scale=None, shift=None, act=0, res=None, out=None, flatten=True):
+    """Inference-time conv + folded BatchNorm + activation (+ residual) in one launch on activations whose channel count
+    need not be a multiple of 64 (TMA zero-fills the K padding).  x_nhwc bf16 [N,H,W,C]; w_packed [taps][cout_pad][Cin_pad];
+    act 0/1/2 = none/ReLU/ReLU6; res bf16 [N,H,W,cout].  1x1 convs are run on the flattened pixel list (no ragged tiles)."""
+    _need_cuda(x_nhwc, w_packed, res)
+    assert x_nhwc.dtype == torch.bfloat16 and x_nhwc.is_contiguous() and w_packed.dtype == torch.bfloat16
+    N, H, W, Cc = x_nhwc.shape
+    taps, cout_pad, cin_pad = w_packed.shape
+    if out is None:
+        out = torch.empty((N, H, W, cout), dtype=torch.bfloat16, device=x_nhwc.device)
+    key = (taps, dil)
+    if key not in _TAPS:
+        ent = [(0, 0, 0)] if taps == 1 else [((t // 3 - 1) * dil, (t % 3 - 1) * dil, 0) for t in range(9)]
+        _TAPS[key] = tuple((C.c_int * taps)(*[e[k] for e in ent]) for k in range(3))
+    dy, dx, c0 = _TAPS[key]
+    n_, h_, w_ = N, H, W
+    M = N * H * W
+    if taps == 1 and flatten and M % 16 == 0:
+        n_, h_, w_ = 1, M // 16, 16  # a 1x1 conv is a plain GEMM over pixels: 8x16 tiles of the flattened list
+    for t in (scale, shift):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == cout_pad)
+    check(lib().pp_conv_igemm_multi(_ptr(x_nhwc), n_, h_, w_, Cc, Cc, cin_pad, _ptr(w_packed), taps, dy, dx, c0, cout_pad, cout,
+                                    None, _ptr(scale), _ptr(shift), int(act), _ptr(res), res.shape[-1] if res is not None else 0,
+                                    _ptr(out), 0, out.shape[3], 0, 0, _stream(x_nhwc)), "pp_conv_igemm_multi")
     return out
 
 
@@ -507,13 +538,15 @@ def _dw_check(x, w):
         raise PixelPickError("depthwise conv: weight does not match the channel count")
 
 
-def dwconv_fwd(x, w, stride, dil):
-    """valid depthwise 3x3 of bf16 NHWC x [N,Hi,Wi,C] with f32 w [C,1,3,3] -> bf16 [N,Ho,Wo,C]."""
+def dwconv_fwd(x, w, stride, dil, scale=None, shift=None, act=0):
+    """valid depthwise 3x3 of bf16 NHWC x [N,Hi,Wi,C] with f32 w [C,1,3,3] -> bf16 [N,Ho,Wo,C]; with scale/shift (f32 [C])
+    the epilogue applies a folded BatchNorm + activation (0 none, 1 ReLU, 2 ReLU6)."""
     _dw_check(x, w)
     N, Hi, Wi, Cc = x.shape
     Ho, Wo = _dw_out(Hi, Wi, stride, dil)
     y = torch.empty((N, Ho, Wo, Cc), dtype=torch.bfloat16, device=x.device)
-    check(lib().pp_dwconv3x3_fwd(_ptr(x), _ptr(w), _ptr(y), N, Hi, Wi, Cc, stride, dil, _stream(x)), "pp_dwconv3x3_fwd")
+    check(lib().pp_dwconv3x3_fwd_bnact(_ptr(x), _ptr(w), _ptr(scale), _ptr(shift), int(act), _ptr(y), N, Hi, Wi, Cc, stride,
+                                       dil, _stream(x)), "pp_dwconv3x3_fwd")
     return y
 
 

@@ -11,8 +11,8 @@
 // 128-byte swizzle == the canonical K-major UMMA operand layout.  Taps that fall entirely outside
 // the image for a tile are skipped (ASPP at 16x32 with dilation 18: 6 of 9 taps).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-// warps 2-5 = epilogue (TMEM -> registers -> global).  Persistent over output tiles; the
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warps 2-9 = epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter).  Persistent over output tiles; the
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "tc_common.cuh"
 
@@ -68,7 +68,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // ------------------------------------------------------------------------------------------
 constexpr int kBM = 128;  // output pixels per tile (UMMA M)
 constexpr int kBK = 64;   // channels per k-block (128 B of bf16 = one swizzle row)
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kMaxTaps = 28;
 
 struct ConvParams {
@@ -87,10 +87,12 @@ struct ConvParams {
   const float* pre_bias;  // [N][Cout_pad] added before scale/shift (ASPP image-pooling branch) or null
   const float* scale;     // [Cout_pad] or null (=1)
   const float* shift;     // [Cout_pad] or null (=0)
-  int relu;
+  int relu;      // 0 none, 1 ReLU, 2 ReLU6
   int out_mode;  // 0: bf16 NHWC (ld_out, c_off)   1: f32 NCHW [N][Cout][H][W]
   void* out;
   int ld_out, c_off;
+  const __nv_bfloat16* res;  // optional residual [pixel][ld_res], channel c of the output adds res[c]; before the activation
+  int ld_res;
 };
 
 template <int BN>
@@ -143,7 +145,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(tfull_bar(a), 1);
-      tc::mbar_init(tempty_bar(a), 4);
+      tc::mbar_init(tempty_bar(a), 8);
     }
     tc::fence_barrier_init();
   }
@@ -226,8 +228,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps share each TMEM lane quarter and split the accumulator's 32-column chunks between them: with one warp
+    // per quarter the epilogue (not the MMA pipe) bounded every conv whose K is short relative to its output (ncu /
+    // per-layer timings in DESIGN.md).  A shared-memory transposed, fully coalesced store path was also measured here
+    // and was SLOWER: the epilogue is instruction/latency-bound, not store-pattern-bound.
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int eh = (warp - 2) >> 2;  // which half of the column chunks this warp converts and stores
     const int row = quarter * 32 + lane;
     const int ty_in = row / p.TW, tx_in = row - ty_in * p.TW;
     uint32_t tile_iter = 0;
@@ -241,20 +248,48 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool valid = (y < p.H) && (x < p.W);
       const size_t pix = ((size_t)img * p.H + y) * p.W + x;
 #pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
+      for (int j = eh; j < BN / 32; j += 2) {
         uint32_t r[32];
         tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + j * 32, r);
         tc::tmem_ld_wait();
         const int cbase = n0 + j * 32;
         float v[32];
+        float rs[32];
+        if (p.res) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          float a = __uint_as_float(r[c]);
-          if (p.pre_bias) a += __ldg(p.pre_bias + (size_t)img * p.Cout_pad + cbase + c);
-          if (p.scale) a *= __ldg(p.scale + cbase + c);
-          if (p.shift) a += __ldg(p.shift + cbase + c);
-          if (p.relu) a = fmaxf(a, 0.f);
-          v[c] = a;
+          for (int c = 0; c < 32; ++c) rs[c] = 0.f;
+          if (valid) {
+            const __nv_bfloat16* rp = p.res + pix * p.ld_res + cbase;
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+              if (cbase + c + 8 <= p.Cout) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + c));
+                const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  rs[c + 2 * e] = __uint_as_float(w4[e] << 16);
+                  rs[c + 2 * e + 1] = __uint_as_float(w4[e] & 0xFFFF0000u);
+                }
+              }
+            }
+          }
+        }
+        // per-channel vectors are warp-uniform: 16-byte loads (4 channels each) instead of one load per channel
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          float4 pb = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sf4 = pb;
+          if (p.pre_bias) pb = __ldg(reinterpret_cast<const float4*>(p.pre_bias + (size_t)img * p.Cout_pad + cbase + c));
+          if (p.scale) sc4 = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + c));
+          if (p.shift) sf4 = __ldg(reinterpret_cast<const float4*>(p.shift + cbase + c));
+          const float pbv[4] = {pb.x, pb.y, pb.z, pb.w}, scv[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sfv[4] = {sf4.x, sf4.y, sf4.z, sf4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float a = fmaf(__uint_as_float(r[c + e]) + pbv[e], scv[e], sfv[e]);
+            if (p.res) a += rs[c + e];
+            if (p.relu) a = fmaxf(a, 0.f);
+            if (p.relu == 2) a = fminf(a, 6.f);
+            v[c + e] = a;
+          }
         }
         if (valid) {
           if (p.out_mode == 0) {
@@ -274,9 +309,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 *reinterpret_cast<uint4*>(o + c) = pk;
               }
             } else {
+              // ragged tile (Cout not a multiple of 32): 16-byte stores while 8 channels fit, scalars for the rest
 #pragma unroll
-              for (int c = 0; c < 32; ++c)
-                if (cbase + c < p.Cout) o[c] = __float2bfloat16(v[c]);
+              for (int c = 0; c < 32; c += 8) {
+                if (cbase + c + 8 <= p.Cout) {
+                  uint4 pk;
+                  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[c], v[c + 1]);
+                  __nv_bfloat162 t1 = __floats2bfloat162_rn(v[c + 2], v[c + 3]);
+                  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[c + 4], v[c + 5]);
+                  __nv_bfloat162 t3 = __floats2bfloat162_rn(v[c + 6], v[c + 7]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&t0);
+                  pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                  pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                  *reinterpret_cast<uint4*>(o + c) = pk;
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (cbase + c + e < p.Cout) o[c + e] = __float2bfloat16(v[c + e]);
+                }
+              }
             }
           } else {
             float* o = reinterpret_cast<float*>(p.out);
@@ -345,22 +397,27 @@ int pp_conv_igemm(const void* x, int N, int H, int W, int Cin, int ld_in, const 
     tc0[t] = 0;
   }
   return pp_conv_igemm_multi(x, N, H, W, Cin, ld_in, Cin, w_packed, taps, tdy, tdx, tc0, Cout_pad, Cout, pre_bias, scale,
-                             shift, relu, out, out_mode, ld_out, c_off, block_n, stream);
+                             shift, relu, nullptr, 0, out, out_mode, ld_out, c_off, block_n, stream);
 }
 
 int pp_conv_igemm_multi(const void* x, int N, int H, int W, int a_channels, int ld_in, int Cin, const void* w_packed,
                         int n_entries, const int* tap_dy, const int* tap_dx, const int* tap_c0, int Cout_pad, int Cout,
-                        const float* pre_bias, const float* scale, const float* shift, int relu, void* out,
-                        int out_mode, int ld_out, int c_off, int block_n, void* stream) {
+                        const float* pre_bias, const float* scale, const float* shift, int relu, const void* res,
+                        int ld_res, void* out, int out_mode, int ld_out, int c_off, int block_n, void* stream) {
   PP_CHECK_ARG(x && w_packed && out, "pp_conv_igemm: null pointer");
+  PP_CHECK_ARG(relu >= 0 && relu <= 2, "pp_conv_igemm: relu=%d (0 none, 1 ReLU, 2 ReLU6)", relu);
+  PP_CHECK_ARG(!res || (ld_res % 8 == 0 && ld_res >= Cout && (reinterpret_cast<uintptr_t>(res) % 16) == 0),
+               "pp_conv_igemm: residual needs ld_res >= Cout, a multiple of 8, and a 16-byte aligned base");
   PP_CHECK_ARG(N > 0 && H > 0 && W > 0, "pp_conv_igemm: bad shape");
   PP_CHECK_ARG(Cin > 0 && Cin % 64 == 0, "pp_conv_igemm: Cin=%d must be a multiple of 64 (pad the buffer)", Cin);
-  PP_CHECK_ARG(a_channels >= Cin && ld_in >= a_channels && ld_in % 8 == 0,
+  // a_channels < Cin is allowed for a single channel group: TMA zero-fills the K padding of a tensor whose channel
+  // count is not a multiple of 64 (MobileNetV2: 16, 24, 32, 96, 144, ...), so activations need no padded copies
+  PP_CHECK_ARG(a_channels > 0 && ld_in >= a_channels && ld_in % 8 == 0,
                "pp_conv_igemm: ld_in=%d must be >= the A channel count %d and a multiple of 8", ld_in, a_channels);
   PP_CHECK_ARG(n_entries >= 1 && n_entries <= kMaxTaps && tap_dy && tap_dx && tap_c0, "pp_conv_igemm: %d tap entries (1..%d)",
                n_entries, kMaxTaps);
   for (int t = 0; t < n_entries; ++t)
-    PP_CHECK_ARG(tap_c0[t] >= 0 && tap_c0[t] % 8 == 0 && tap_c0[t] + Cin <= a_channels && tap_dy[t] > -8192 &&
+    PP_CHECK_ARG(tap_c0[t] >= 0 && tap_c0[t] % 8 == 0 && (tap_c0[t] + Cin <= a_channels || tap_c0[t] == 0) && tap_dy[t] > -8192 &&
                      tap_dy[t] < 8192 && tap_dx[t] > -8192 && tap_dx[t] < 8192,
                  "pp_conv_igemm: bad tap entry %d (dy %d dx %d c0 %d)", t, tap_dy[t], tap_dx[t], tap_c0[t]);
   const int taps = n_entries;
@@ -403,6 +460,7 @@ int pp_conv_igemm_multi(const void* x, int N, int H, int W, int a_channels, int 
   p.tiles_x = (W + p.TW - 1) / p.TW;
   p.pre_bias = pre_bias; p.scale = scale; p.shift = shift; p.relu = relu;
   p.out_mode = out_mode; p.out = out; p.ld_out = ld_out; p.c_off = c_off;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.ld_res = ld_res;
   p.n_off = 0;
   p.n_tiles_n = n_main / BN;
 

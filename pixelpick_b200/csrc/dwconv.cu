@@ -38,6 +38,9 @@ struct DwParams {
   __nv_bfloat16* out;        // fwd: y [N][Hout][Wout][C]; dgrad: dx
   float* dw;                 // wgrad output [C][9] (zeroed by the launcher)
   int N, Hin, Win, Hout, Wout, C;
+  const float* scale;        // fwd, inference: y = act(conv * scale[c] + shift[c]) (folded BatchNorm), or null
+  const float* shift;
+  int act;                   // 0 none, 1 ReLU, 2 ReLU6
   int off;                   // dgrad (stride 1): input coordinate = output - off + tap * dil  (off = 2 * dil)
   int flip;                  // dgrad: weights used flipped (tap 8 - t)
   // work decomposition: blockIdx.y = chunk of nq channel quads (<= 64); lanes = 256 / nq threads walk the CTA's
@@ -95,6 +98,14 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv_fwd_kernel(const DwParam
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int j = 0; j < 4; ++j) wr[t][j] = __ldg(p.w + (size_t)(c0 + j) * 9 + (p.flip ? 8 - t : t));
+  float esc[4] = {1.f, 1.f, 1.f, 1.f}, esf[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.scale) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      esc[j] = __ldg(p.scale + c0 + j);
+      esf[j] = __ldg(p.shift + c0 + j);
+    }
+  }
   const uint32_t total = dw_num_items(p, 3);
   const uint32_t per_cta = (total + gridDim.x - 1) / gridDim.x;
   const uint32_t begin = blockIdx.x * per_cta;
@@ -132,6 +143,17 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv_fwd_kernel(const DwParam
               for (int j = 0; j < 4; ++j) acc[a][j] = fmaf(f[j], wr[ky * 3 + kx][j], acc[a][j]);
             }
       }
+    }
+    if (p.scale) {
+#pragma unroll
+      for (int a = 0; a < kDwTX; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float y = fmaf(acc[a][j], esc[j], esf[j]);
+          if (p.act) y = fmaxf(y, 0.f);
+          if (p.act == 2) y = fminf(y, 6.f);
+          acc[a][j] = y;
+        }
     }
     __nv_bfloat16* o = p.out + (((int64_t)it.n * p.Hout + it.y) * p.Wout + it.x0) * p.C + c0;
 #pragma unroll
@@ -325,7 +347,14 @@ extern "C" {
 
 int pp_dwconv3x3_fwd(const void* x, const float* w, void* y, int N, int Hi, int Wi, int C, int stride, int dil,
                      void* stream) {
+  return pp_dwconv3x3_fwd_bnact(x, w, nullptr, nullptr, 0, y, N, Hi, Wi, C, stride, dil, stream);
+}
+
+int pp_dwconv3x3_fwd_bnact(const void* x, const float* w, const float* scale, const float* shift, int act, void* y, int N,
+                           int Hi, int Wi, int C, int stride, int dil, void* stream) {
+  PP_CHECK_ARG((scale == nullptr) == (shift == nullptr) && act >= 0 && act <= 2, "pp_dwconv3x3_fwd_bnact: scale/shift come in pairs, act 0..2");
   DwParams p{};
+  p.scale = scale; p.shift = shift; p.act = act;
   int Ho, Wo;
   int rc = dw_check("pp_dwconv3x3_fwd", x, w, y, N, Hi, Wi, C, stride, dil, &Ho, &Wo);
   if (rc != PP_OK) return rc;

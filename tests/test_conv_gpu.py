@@ -114,3 +114,33 @@ def test_fused_aspp_dgrad_multi_tap_table(N, H, W, Cin, dils):
     gx = _lib.conv_igemm_multi(gy.permute(0, 2, 3, 1).contiguous().to(DEV), w_all, entries, cin_pad)
     got = gx[..., :Cin].float().permute(0, 3, 1, 2).cpu()
     assert (got - x.grad).abs().max().item() < 8e-3 * x.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,dil,act,with_res", [
+    (2, 18, 34, 24, 144, 1, 1, 2, False),    # MobileNetV2 expansion on the padded tensor: Cin, Cout not multiples of 64
+    (2, 16, 32, 144, 24, 1, 1, 0, True),     # projection + residual, ragged 24-channel output
+    (1, 130, 258, 16, 96, 1, 1, 2, False),   # flattened pixel list (M % 16 == 0)
+    (1, 7, 9, 32, 16, 1, 1, 0, False),       # M % 16 != 0: real geometry
+    (2, 32, 64, 256, 256, 3, 4, 1, False),   # ResNet layer4 conv2 (dilated)
+    (2, 32, 64, 512, 2048, 1, 1, 1, True),   # bottleneck tail relu(bn3(conv3) + identity)
+    (1, 16, 32, 960, 320, 1, 1, 0, False),
+])
+def test_conv_fused_epilogue_ragged_channels(N, H, W, Cin, Cout, k, dil, act, with_res):
+    """conv_fused: conv + folded BatchNorm (scale/shift) + activation (+ residual) on UNPADDED activations (TMA zero-fills K)."""
+    g = torch.Generator().manual_seed(Cin * 7 + Cout)
+    x = torch.randn((N, Cin, H, W), generator=g).to(torch.bfloat16)
+    w = (torch.randn((Cout, Cin, k, k), generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+    sc, sf = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g) * 0.5
+    res = torch.randn((N, Cout, H, W), generator=g).to(torch.bfloat16) if with_res else None
+    ref = F.conv2d(x.float(), w.float(), padding=dil if k == 3 else 0, dilation=dil) * sc.view(1, -1, 1, 1) + sf.view(1, -1, 1, 1)
+    if with_res:
+        ref = ref + res.float()
+    ref = F.relu(ref) if act == 1 else (F.relu6(ref) if act == 2 else ref)
+    cp = 32 if Cout <= 32 else -(-Cout // 64) * 64
+    wp = _lib.pack_conv_weight(w.to(DEV), -(-Cin // 64) * 64, cp)
+    pad = lambda t: F.pad(t, (0, cp - Cout)).contiguous().to(DEV)
+    out = _lib.conv_fused(x.permute(0, 2, 3, 1).contiguous().to(DEV), wp, Cout, dil=dil, scale=pad(sc), shift=pad(sf), act=act,
+                          res=res.permute(0, 2, 3, 1).contiguous().to(DEV) if with_res else None)
+    assert tuple(out.shape) == (N, H, W, Cout)
+    got = out.float().permute(0, 3, 1, 2).cpu()
+    assert (got - ref).abs().max().item() < 1e-2 * ref.abs().max().item()

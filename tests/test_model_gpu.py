@@ -199,3 +199,31 @@ def test_dropout_is_reproducible_per_step_and_scales():
     scale = a.abs().max().item()
     assert (a - b).abs().max().item() < 2e-2 * scale
     assert (a - c).abs().max().item() > 0.2 * scale
+
+
+@pytest.mark.parametrize("backbone,shape", [("mobilenet", (2, 3, 256, 512)), ("mobilenet", (1, 3, 360, 480)),
+                                            ("resnet", (2, 3, 128, 256))])
+def test_fused_eval_encoder_matches_module_path(backbone, shape):
+    """Inference encoder on the hand-written kernels (pp_conv_igemm with folded BatchNorm / activation / residual epilogues,
+    fused depthwise) vs the PyTorch-module path on the same bf16 weights, and vs the fp32 oracle features."""
+    m, sd = _model(backbone, 3, encoder_fp32=False)
+    m.eval()
+    x = _x(11, shape).to(DEV)
+    with torch.no_grad():
+        m.fused_eval_encoder = True
+        hi_f, lo_f = m._encode(x)
+        m.fused_eval_encoder = False
+        hi_m, lo_m = m._encode(x)
+        ref = orc.deeplab_forward(sd, x.cpu(), backbone=backbone)
+    assert hi_f.shape == hi_m.shape and lo_f.shape == lo_m.shape
+    for name, f, mm, r in (("high", hi_f, hi_m, ref["high"]), ("low", lo_f, lo_m, ref["low"])):
+        f, mm = f.float().cpu(), mm.float().cpu()
+        scale = r.abs().max().item()
+        err_f, err_m = (f - r).abs().mean().item() / scale, (mm - r).abs().mean().item() / scale
+        print(f"{backbone} {name}: fused mean err {err_f:.5f}  module-path mean err {err_m:.5f} (of the fp32 oracle scale)")
+        # both are bf16 pipelines with different rounding points: the fused path must be at least as close to the fp32
+        # oracle as the module path (it rounds LESS: BatchNorm is applied to the fp32 accumulator), within 25 %
+        assert err_f < max(1.25 * err_m, 2e-3)
+        # two bf16 pipelines each ~err from the fp32 oracle (synthetic, badly conditioned weights): their mutual distance is
+        # bounded by the triangle inequality, not by a tighter number
+        assert (f - mm).abs().mean().item() / scale < 1.05 * (err_f + err_m)
