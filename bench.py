@@ -186,6 +186,27 @@ def cpu_train_rate(backbone, B, steps, threads):
     return B / float(np.mean(times)), times
 
 
+def cpu_query_model_rate(backbone, n_img, threads):
+    """oracle port of query.py:159-212 WITH the model forward (fp32 torch CPU), one image per forward as the reference."""
+    from oracle import acq_oracle as orc
+    from oracle import deeplab_oracle as dorc
+    from pixelpick_b200.deeplab import DeepLab  # parameter names / shapes only
+    torch.set_num_threads(threads)
+    shapes = {k: tuple(v.shape) for k, v in DeepLab(MARGS, backbone=backbone).state_dict().items()}
+    sd = dorc.synthetic_state_dict(shapes, seed=1)
+    x, y, q = synth_train_batch(n_img, 21)
+    lab_np, void_np = q.numpy().astype(bool), (y == C).numpy()
+    names = [f"img_{i:05d}.png" for i in range(n_img)]
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for i in range(n_img):
+            pred = dorc.deeplab_forward(sd, x[i:i + 1], backbone=backbone)["pred"]
+            orc.query_images([pred], STRATEGY, lab_np[i:i + 1], void_np[i:i + 1], names[i:i + 1], N_SEL, TOP_N_PERCENT)
+    dt = time.perf_counter() - t0
+    return n_img * H * W / 1e6 / dt, dt
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -217,6 +238,10 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     if not args.no_train:
+        qm, qdt = cpu_query_model_rate("mobilenet", 8, threads)
+        out["query_model"] = {"unit": "Mpixels/s", "mobilenetv2_bs1_host": {"value": qm, "images_per_s": 8 / qdt},
+                              "sample": "oracle port of query.py:159-212 incl. the MobileNetV2-DeepLab forward (fp32 torch CPU), "
+                                        "8 images, one per forward"}
         r_mn, t_mn = cpu_train_rate("mobilenet", 4, 2, threads)
         out["train"] = {"metric": "train_images_per_sec", "unit": "images/s", "dtype": "f32",
                         "mobilenetv2_b4": {"value": r_mn, "ms_per_step": float(np.mean(t_mn)) * 1e3, "steps": len(t_mn)},
@@ -376,7 +401,8 @@ def bench_conv_roofline(dev, peak_tf):
 
 
 def bench_query_model(backbone, n_img, steps, dev, from_host):
-    """QuerySelector-style querying with the model in the loop (eval forward_lowres + fused upsample/score + top-k)."""
+    """QuerySelector-style querying with the model in the loop (eval forward_lowres + fused upsample/score + top-k).
+    n_img = 1 is the reference's own query batch (model.py:36-37: the query dataloader has batch_size 1)."""
     from pixelpick_b200 import _lib
     from pixelpick_b200.deeplab import DeepLab
     torch.manual_seed(0)
@@ -564,7 +590,11 @@ def main():
                       "mobilenetv2_hbm": bench_query_model("mobilenet", 64, 5, dev, False),
                       "mobilenetv2_host": bench_query_model("mobilenet", 64, 5, dev, True),
                       "resnet50_hbm": bench_query_model("resnet", 32, 5, dev, False),
-                      "resnet50_host": bench_query_model("resnet", 32, 5, dev, True)}
+                      "resnet50_host": bench_query_model("resnet", 32, 5, dev, True),
+                      "mobilenetv2_bs1_host": bench_query_model("mobilenet", 1, 50, dev, True),
+                      "resnet50_bs1_host": bench_query_model("resnet", 1, 50, dev, True),
+                      "note": "bs1 = the reference's query loop (one image per forward, query.py:159-212); "
+                              "hbm/host = 64 (MobileNetV2) / 32 (ResNet-50) images per step"}
     barrier()
     clk = clocks.stop() if rank == 0 else None
 
@@ -604,6 +634,10 @@ def main():
                                    "sample": f"{n_cpu} images of the same workload x 3 repetitions (best), "
                                              f"oracle port of query.py:159-212 on torch CPU + NumPy, {sum(times):.1f} s"}
             if train is not None:
+                qm, qdt = cpu_query_model_rate("mobilenet", 8, threads)
+                out["query_model"]["cpu_baseline"] = {"value": qm, "unit": "Mpixels/s", "cores": threads, "kind": "port",
+                                                      "sample": f"MobileNetV2-DeepLab forward + query, 8 images one per forward "
+                                                                f"(oracle port, fp32 torch CPU), {qdt:.1f} s"}
                 r_mn, t_mn = cpu_train_rate("mobilenet", 4, 2, threads)
                 out["train"]["cpu_baseline"] = {"value": r_mn, "unit": "images/s", "cores": threads, "kind": "port",
                                                 "sample": f"MobileNetV2-DeepLab B=4, 2 timed steps of the oracle train "
