@@ -495,6 +495,9 @@ def main():
     gathered = [torch.empty((B, N_SEL), dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
     ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    # the path's one exchange (all_gather of the picks, 10 KB / rank) runs on its own stream so its launch + NVLink
+    # latency (~80 us) overlaps the next batch's scoring instead of serialising with it
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def step(i=None):
         ws.prepare()
@@ -509,7 +512,10 @@ def main():
         else:  # what QuerySelector runs: only the n drawn ranks are needed (query.py:63-64) -> radix pick, no sort
             sel = _lib.acq_select_pick(score.view(B, HW), K_TOP, largest, pos, ws=ws, hist0_valid=True)
         if world > 1:  # the path's one exchange: per-rank picks -> every rank (rank 0 builds the dict)
-            dist.all_gather(gathered, sel)
+            comm_stream.wait_stream(torch.cuda.current_stream(dev))
+            sel.record_stream(comm_stream)
+            with torch.cuda.stream(comm_stream):
+                dist.all_gather(gathered, sel)
         return sel
 
     def barrier():
@@ -528,6 +534,8 @@ def main():
     t_start.record()
     for i in range(K):
         step(i)
+    if world > 1:
+        torch.cuda.current_stream(dev).wait_stream(comm_stream)  # the timed region ends when the last exchange has landed
     t_end.record()
     barrier()
     launches = lib.pp_launch_count() - l0
