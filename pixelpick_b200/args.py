@@ -45,6 +45,8 @@ class Arguments:
         p.add_argument("--p_dataset_config", "-pdc", type=str, default=None)  # read at args.py:79, never registered there
         p.add_argument("--synthetic", type=int, nargs=3, default=None, metavar=("N", "H", "W"))
         p.add_argument("--n_epochs", type=int, default=None, help="override the per-dataset default (50)")
+        p.add_argument("--no_cuda_graph", dest="cuda_graph", action="store_false", default=True,
+                       help="run the train step eagerly instead of replaying one captured CUDA graph")
         self.parser = p
 
     @staticmethod

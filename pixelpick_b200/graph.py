@@ -56,8 +56,39 @@ class GraphedTrainStep:
             self.loss_scale.copy_(ppdist.global_mean_loss_scale(self.n_valid.float().reshape(())))
         return pl[: int(n)]
 
-    def capture(self):
+    def _snapshot(self):
+        """clones of everything the warm-up steps mutate: parameters, buffers (BatchNorm running statistics, counters),
+        the optimiser state and the dropout step counter — restored after capture so that capturing is free of side
+        effects on the training trajectory (the first replay is the first optimisation step)."""
+        snap = {"model": [t.detach().clone() for t in list(self.model.parameters()) + list(self.model.buffers())],
+                "rng": None if self.model._rng_step is None else self.model._rng_step.clone(), "opt": []}
+        for st in self.opt.state.values():
+            snap["opt"].append({k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()})
+        snap["opt_empty"] = len(self.opt.state) == 0
+        return snap
+
+    def _restore(self, snap):
+        with torch.no_grad():
+            for t, c in zip(list(self.model.parameters()) + list(self.model.buffers()), snap["model"]):
+                t.copy_(c)
+            if snap["rng"] is not None and self.model._rng_step is not None:
+                self.model._rng_step.copy_(snap["rng"])
+            elif self.model._rng_step is not None:
+                self.model._rng_step.zero_()
+            if snap["opt_empty"]:  # state was created by the warm-up: reset it in place (addresses are captured)
+                for st in self.opt.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+            else:
+                for st, c in zip(self.opt.state.values(), snap["opt"]):
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            v.copy_(c[k])
+
+    def capture(self, restore_state=False):
         self.model.train()
+        snap = self._snapshot() if restore_state else None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -70,6 +101,8 @@ class GraphedTrainStep:
         self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.graph):
             self.loss, self.pred = self._step()
+        if snap is not None:
+            self._restore(snap)
         return self
 
     def __call__(self):

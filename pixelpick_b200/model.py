@@ -52,6 +52,7 @@ class Model:
             self.dataloader, self.dataloader_query, self.dataloader_val = dataloaders
         self.lr_scheduler_type = args.lr_scheduler_type
         self.query_selector = QuerySelector(args, self.dataloader_query, device=self.device)
+        self._use_graph, self._graph, self._graph_shape = False, None, None
         self.running_loss, self.running_score = AverageMeter(), RunningScore(args.n_classes)
 
     def __call__(self):
@@ -96,6 +97,28 @@ class Model:
         optimizer.step()
         return loss.detach(), px_label, pred_at
 
+    def _graphed_step(self, model, optimizer, dict_data, reducer):
+        """The same step replayed from ONE captured CUDA graph (graph.py): at the reference batch of 4 the eager step is
+        ~900 kernel launches and CPU-bound (4.8x slower).  Captured lazily for the loop's batch shape; other shapes (a
+        ragged last batch) take the eager step.  Returns None when this batch cannot use the graph."""
+        x, y, q = dict_data["x"], dict_data["y"], dict_data["queries"]
+        shape = (x.shape[0], x.shape[2], x.shape[3])
+        gs = self._graph
+        if gs is None:
+            from .graph import GraphedTrainStep
+            per_img = min(shape[1] * shape[2], self.init_n_pixels + self.max_budget + self.n_pixels_by_us + 16)
+            gs = GraphedTrainStep(model, optimizer, shape, self.ignore_index, capacity=shape[0] * per_img,
+                                  device=self.device, reducer=reducer)
+            gs.load(x, y, q)
+            gs.capture(restore_state=True)  # warm-up steps leave no trace: the first replay is the first update
+            self._graph, self._graph_shape = gs, shape
+        if shape != self._graph_shape:
+            return None
+        labels = gs.load(x, y, q)
+        loss, pred = gs()
+        n = labels.numel()
+        return loss.detach(), labels, pred[:n]
+
     def _train_epoch(self, epoch, model, optimizer, lr_scheduler, reducer=None):
         if self.n_pixels_by_us != 0:
             print(f"training an epoch {epoch} of {self.nth_query}th query "
@@ -103,7 +126,8 @@ class Model:
         model.train()
         miou = pixel_acc = float("nan")
         for dict_data in self.dataloader:
-            loss, labels, preds = self.train_step(model, optimizer, dict_data, reducer)
+            out = self._graphed_step(model, optimizer, dict_data, reducer) if self._use_graph else None
+            loss, labels, preds = out if out is not None else self.train_step(model, optimizer, dict_data, reducer)
             self.running_score.update_pairs(labels.cpu().numpy(), preds.cpu().numpy())
             self.running_loss.update(loss.item())
             scores = self.running_score.get_scores()[0]
@@ -126,7 +150,11 @@ class Model:
         model = get_model(self.args).to(self.device)
         model.base_seed = self.args.seed * 131 + self.nth_query + 1
         ppdist.broadcast_parameters(model)
-        optimizer = get_optimizer(self.args, model)
+        # whole-step CUDA graph (Adam configs, sparse labels); --no_cuda_graph or SGD / fully-supervised runs stay eager
+        self._use_graph = (getattr(self.args, "cuda_graph", True) and self.args.optimizer_type == "Adam"
+                           and self.n_pixels_by_us != 0)
+        self._graph = None
+        optimizer = get_optimizer(self.args, model, capturable=self._use_graph)
         lr_scheduler = get_lr_scheduler(self.args, optimizer=optimizer, iters_per_epoch=len(self.dataloader))
         reducer = ppdist.GradAllReducer(model) if ppdist.world() > 1 else None
         for e in range(1, 1 + self.n_epochs):
@@ -135,6 +163,7 @@ class Model:
             if self.debug:
                 break
         self.best_miou = -1.0
+        self._graph = None  # the graph holds this round's model / optimiser storage
         return model
 
     @torch.no_grad()

@@ -25,14 +25,18 @@ def get_model(args):
     raise NotImplementedError(f"network_name={args.network_name}: only the DeepLabv3+ hot path is implemented")
 
 
-def get_optimizer(args, model):
+def get_optimizer(args, model, capturable=False):
     """utils/utils.py:112-306 for the deeplab branch: backbone lr/10, rest lr; note that the declared Adam eps/betas
-    are NOT forwarded by the reference (torch defaults apply, utils.py:141,206) — mirrored."""
+    are NOT forwarded by the reference (torch defaults apply, utils.py:141,206) — mirrored.
+    capturable: Adam with tensor learning rates, usable inside a captured CUDA graph (pixelpick_b200/graph.py)."""
     op = args.optimizer_params
     groups = [{"params": model.backbone.parameters(), "lr": op["lr"] / 10, "weight_decay": op["weight_decay"]}]
     for part in (model.aspp, model.low_level_conv, model.seg_head):
         groups.append({"params": part.parameters(), "lr": op["lr"], "weight_decay": op["weight_decay"]})
     if args.optimizer_type == "Adam":
+        if capturable:
+            from .graph import make_capturable_adam
+            return make_capturable_adam(groups)
         return torch.optim.Adam(groups, fused=next(model.parameters()).is_cuda)
     if args.optimizer_type == "SGD":
         return torch.optim.SGD(groups, momentum=op["momentum"])
@@ -57,7 +61,7 @@ class Poly(_LRScheduler):
         self.cur_iter %= self.iters_per_epoch
         self.cur_iter += 1
         assert factor >= 0, "error in lr_scheduler"
-        return [base_lr * factor for base_lr in self.base_lrs]
+        return [float(base_lr) * factor for base_lr in self.base_lrs]  # float(): base lrs may be device tensors
 
 
 def get_lr_scheduler(args, optimizer, iters_per_epoch=-1):
