@@ -133,6 +133,12 @@ int pp_acq_session_destroy(pp_acq_session* s);
  * h_pos: int32 [n_img, n_sel] positions in the sorted top-k list (NULL => first n_sel);
  * h_sel_idx: int32 [n_img, n_sel] (out); h_topk_idx: optional int32 [n_img, k] (out, may be NULL).
  * Host pointers may be pageable; pinned memory (cudaHostAlloc / torch pin_memory) is faster. */
+/* Split form for hosts that draw the pick positions themselves (query.py:63-64): begin launches H2D + scoring + select
+ * and returns immediately, the host draws its np.random.permutation positions while the logits cross PCIe, finish uploads
+ * them, picks and returns the selected pixel indices.  n_img <= 2 * chunk_imgs; one begin pending at a time. */
+int pp_acq_session_begin_host(pp_acq_session* s, const float* h_logits, const uint8_t* h_labelled, const uint8_t* h_void,
+                              int n_img, int strategy);
+int pp_acq_session_finish_host(pp_acq_session* s, const int32_t* h_pos, int32_t* h_sel_idx);
 int pp_acq_session_run_host(pp_acq_session* s, const float* h_logits, const uint8_t* h_labelled,
                             const uint8_t* h_void, int n_img, int strategy,
                             const int32_t* h_pos, int32_t* h_sel_idx, int32_t* h_topk_idx);

@@ -46,6 +46,8 @@ _SIGNATURES = {
     "pp_acq_session_create": ([C.POINTER(_vp), _i, _i, _i, _i, _i, _i], _i),
     "pp_acq_session_destroy": ([_vp], _i),
     "pp_acq_session_run_host": ([_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp], _i),
+    "pp_acq_session_begin_host": ([_vp, _vp, _vp, _vp, _i, _i], _i),
+    "pp_acq_session_finish_host": ([_vp, _vp, _vp], _i),
     "pp_sparse_ce": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _f, _vp, _vp, _vp, _vp], _i),
     "pp_upsample_bilinear_ac": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_upsample_bilinear_ac_bwd": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
@@ -625,6 +627,21 @@ class AcqSession:
         check(lib().pp_acq_session_run_host(self._h, _ptr(h_logits), _ptr(h_labelled), _ptr(h_void), n,
                                             STRATEGIES[strategy], _ptr(h_pos), _ptr(h_sel), _ptr(h_topk)),
               "pp_acq_session_run_host")
+        return h_sel
+
+    def begin(self, h_logits, h_labelled, h_void, strategy):
+        """asynchronous first half (H2D + scoring + radix select); draw the pick positions, then call finish()."""
+        for t in (h_logits, h_labelled, h_void):
+            if t is not None and (t.is_cuda or not t.is_contiguous()):
+                raise PixelPickError("AcqSession.begin wants contiguous host tensors")
+        check(lib().pp_acq_session_begin_host(self._h, _ptr(h_logits), _ptr(h_labelled), _ptr(h_void), h_logits.shape[0],
+                                              STRATEGIES[strategy]), "pp_acq_session_begin_host")
+
+    def finish(self, h_pos, h_sel):
+        for t in (h_pos, h_sel):
+            if t is not None and (t.is_cuda or not t.is_contiguous()):
+                raise PixelPickError("AcqSession.finish wants contiguous host tensors")
+        check(lib().pp_acq_session_finish_host(self._h, _ptr(h_pos), _ptr(h_sel)), "pp_acq_session_finish_host")
         return h_sel
 
     def close(self):

@@ -300,6 +300,21 @@ def test_host_buffer_session_equals_device_api(strat):
     assert torch.equal(h_topk, topk.cpu())
     assert torch.equal(h_sel, _lib.acq_gather(topk, torch.from_numpy(pos)).cpu())
     sess.close()
+    # split form: begin (async H2D + score + select) / host draws / finish (pick + D2H); needs all chunks resident
+    sess = _lib.AcqSession(3, C, h, w, k, nsel)
+    h_sel2 = torch.empty((n, nsel), dtype=torch.int32).pin_memory()
+    for _ in range(2):  # twice: the slots and the pending state are reusable
+        sess.begin(logits.pin_memory(), torch.from_numpy(lab).view(torch.uint8).pin_memory(),
+                   torch.from_numpy(void).view(torch.uint8).pin_memory(), strat)
+        sess.finish(torch.from_numpy(pos), h_sel2)
+        assert torch.equal(h_sel2, h_sel)
+    with pytest.raises(_lib.PixelPickError):
+        sess.finish(torch.from_numpy(pos), h_sel2)  # nothing pending
+    small = _lib.AcqSession(2, C, h, w, k, nsel)
+    with pytest.raises(_lib.PixelPickError):
+        small.begin(logits.pin_memory(), None, None, strat)  # 5 images > 2 resident chunks of 2
+    small.close()
+    sess.close()
 
 
 def test_errors_are_loud():
