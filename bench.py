@@ -596,7 +596,7 @@ def main():
             train[f"{name}_b4_graph_e2e"] = bench_train_graph(bb, 4, ts, 5, dev, world, e2e=True)
             train[f"{name}_b{args.train_batch}"] = bench_train(bb, args.train_batch, ts, 3, dev, world)
             train[f"{name}_b{args.train_batch}_graph"] = bench_train_graph(bb, args.train_batch, ts, 3, dev, world)
-            train[f"{name}_b{args.train_batch}_e2e"] = bench_train(bb, args.train_batch, ts, 3, dev, world, e2e=True)
+            train[f"{name}_b{args.train_batch}_graph_e2e"] = bench_train_graph(bb, args.train_batch, ts, 3, dev, world, e2e=True)
             torch.cuda.empty_cache()
         if rank == 0:
             train["roofline_tensor"] = bench_conv_roofline(dev, tf_burst)
