@@ -9,6 +9,7 @@
 // 128-byte lines.  Dropout masks come from a counter-based Philox4x32-10 keyed by (seed, layer offset,
 // element index), so the backward pass regenerates them instead of storing them.
 #include "pp_common.cuh"
+#include <cooperative_groups.h>
 
 namespace pp {
 
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_kernel(const BnBw
   bn_bwd_reduce_body<RES, DROP>(p, p.sums, sh);
 }
 
-template <bool RES, bool DROP, int BATCH>
+template <bool RES, bool DROP, int BATCH, bool SUMS_SHARED = false>
 __device__ __forceinline__ void bn_bwd_apply_body(const BnBwdParams& p, const float* __restrict__ sums) {
   // d_raw = scale * (g - mean(g) - xhat * mean(g xhat)) = A*g + B*x + K with per-channel A, B, K held in registers
   const int groups = p.C >> 3;
@@ -351,7 +352,8 @@ __device__ __forceinline__ void bn_bwd_apply_body(const BnBwdParams& p, const fl
     sc[j] = __ldg(p.scale + c);
     sf[j] = __ldg(p.shift + c);
     const float mu = __ldg(p.mean + c), rs = __ldg(p.rstd + c);
-    const float mg = __ldcg(sums + c) * inv_m, mgx = __ldcg(sums + p.C + c) * inv_m;
+    const float mg = (SUMS_SHARED ? sums[c] : __ldcg(sums + c)) * inv_m;
+    const float mgx = (SUMS_SHARED ? sums[p.C + c] : __ldcg(sums + p.C + c)) * inv_m;
     cb[j] = -sc[j] * rs * mgx;
     ck[j] = -sc[j] * (mg - mu * rs * mgx);
   }
@@ -494,6 +496,89 @@ __global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_fused_kernel(const BnBwd
   scratch_release(q.sums, 2 * q.b.C, q.bar, gridDim.x);
 }
 
+// ---- small tensors: the same two passes inside ONE thread-block cluster ---------------------------------------
+// For very small tensors (< 0.5 MB: the 1/16-resolution projections at the reference batch of 4) the cooperative
+// kernels above cost ~14 us, nearly all of it launch + global-atomic + grid-barrier latency.  A cluster of <= 8 CTAs is
+// co-scheduled by the hardware (ordinary launch), reduces its partial sums through distributed shared memory and
+// synchronises with the hardware cluster barrier: no global atomics, no scratch, no cooperative launch.  Above that size
+// 8 SMs cannot stream fast enough (~50 GB/s each) and the grid-wide version wins.
+namespace cg = cooperative_groups;
+constexpr int kBnClusterMax = 8;
+
+// every CTA sums the cluster's per-CTA partials [2C] into its own shared tot[2C]
+__device__ __forceinline__ void cluster_totals(cg::cluster_group& cluster, float* part, float* tot, int n2c) {
+  const unsigned n = cluster.num_blocks();
+  for (int i = threadIdx.x; i < n2c; i += blockDim.x) {
+    float a = 0.f;
+    for (unsigned r = 0; r < n; ++r) a += cluster.map_shared_rank(part, r)[i];
+    tot[i] = a;
+  }
+  __syncthreads();
+}
+
+template <bool RES, bool DROP>
+__global__ void __launch_bounds__(kEwThreads, 4) bn_fwd_cluster_kernel(const BnFwdFusedParams q) {
+  extern __shared__ float sh[];  // [kEwThreads * 16] reduce scratch | part [2C] | tot [2C]
+  const BnApplyParams& p = q.a;
+  float* part = sh + kEwThreads * 16;
+  float* tot = part + 2 * p.C;
+  cg::cluster_group cluster = cg::this_cluster();
+  for (int i = threadIdx.x; i < 2 * p.C; i += kEwThreads) part[i] = 0.f;
+  __syncthreads();
+  bn_stats_body(p.raw, p.M, p.ld_in, p.c_off_in, p.C, part, sh);  // the CTA's partial sums land in its shared memory
+  cluster.sync();
+  cluster_totals(cluster, part, tot, 2 * p.C);
+  const float inv_m = 1.f / (float)p.M;
+  const int g = threadIdx.x % (p.C >> 3);
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    const float mean = tot[c] * inv_m;
+    const float var = fmaxf(fmaf(-mean, mean, tot[p.C + c] * inv_m), 0.f);
+    sc[j] = __ldg(q.gamma + c) * rsqrtf(var + q.eps);
+    sf[j] = fmaf(-mean, sc[j], __ldg(q.beta + c));
+  }
+  if (blockIdx.x == 0) {
+    const float unbias = p.M > 1 ? (float)p.M / (float)(p.M - 1) : 1.f;
+    for (int c = threadIdx.x; c < p.C; c += kEwThreads) {
+      const float mean = tot[c] * inv_m;
+      const float var = fmaxf(fmaf(-mean, mean, tot[p.C + c] * inv_m), 0.f);
+      const float rstd = rsqrtf(var + q.eps);
+      const float scale = __ldg(q.gamma + c) * rstd;
+      q.stats_out[c] = scale;
+      q.stats_out[p.C + c] = fmaf(-mean, scale, __ldg(q.beta + c));
+      q.stats_out[2 * p.C + c] = mean;
+      q.stats_out[3 * p.C + c] = rstd;
+      if (q.running_mean) {
+        q.running_mean[c] = fmaf(q.momentum, mean - q.running_mean[c], q.running_mean[c]);
+        q.running_var[c] = fmaf(q.momentum, var * unbias - q.running_var[c], q.running_var[c]);
+      }
+    }
+    if (threadIdx.x == 0 && q.nbt) *q.nbt += 1;
+  }
+  bn_apply_body<RES, DROP>(p, sc, sf);
+  cluster.sync();  // no CTA may exit while a peer can still read its shared memory
+}
+
+template <bool RES, bool DROP>
+__global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_cluster_kernel(const BnBwdFusedParams q) {
+  extern __shared__ float sh[];
+  const BnBwdParams& p = q.b;
+  float* part = sh + kEwThreads * 16;
+  float* tot = part + 2 * p.C;
+  cg::cluster_group cluster = cg::this_cluster();
+  for (int i = threadIdx.x; i < 2 * p.C; i += kEwThreads) part[i] = 0.f;
+  __syncthreads();
+  bn_bwd_reduce_body<RES, DROP>(p, part, sh);
+  cluster.sync();
+  cluster_totals(cluster, part, tot, 2 * p.C);
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < 2 * p.C; i += kEwThreads) p.sums[i] = tot[i];
+  bn_bwd_apply_body<RES, DROP, 4, true>(p, tot);
+  cluster.sync();
+}
+
 // ---- bilinear upsample NHWC bf16 (align_corners=True) -----------------------------------------
 __global__ void __launch_bounds__(kEwThreads) upsample_nhwc_kernel(const __nv_bfloat16* __restrict__ in, int N, int h, int w,
                                                                    int C, int ld_in, __nv_bfloat16* __restrict__ out, int H,
@@ -618,6 +703,35 @@ static inline int ew_grid(int64_t total) {
 }  // namespace pp
 
 namespace pp {
+// single-cluster launch for small tensors; returns 0 CTAs when the tensor should take the cooperative path
+static int bn_cluster_ctas(int64_t M, int C) {
+  // measured (scripts/bench_dw.py, B=4): one SM streams only ~50 GB/s, so 8 CTAs beat the 14 us cooperative kernel only
+  // below ~0.5 MB (0.26 MB: 12.4 vs 14.1 us per fwd+bwd pair; 3.4 MB: 67 vs 36 us)
+  if (C > 1024 || (int64_t)M * C * 2 > (512ll << 10)) return 0;
+  const int rows_per_block = kEwThreads / (C / 8);
+  const int64_t want = (M + (int64_t)rows_per_block * 8 - 1) / ((int64_t)rows_per_block * 8);  // >= 8 rows per thread
+  int n = 1;
+  while (n < kBnClusterMax && n < want) n <<= 1;
+  return n;
+}
+template <typename K, typename P>
+static int launch_cluster(K kernel, const P& params, int n_ctas, size_t smem, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)n_ctas);
+  cfg.blockDim = dim3(kEwThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)n_ctas;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  PP_CUDA(cudaLaunchKernelEx(&cfg, kernel, params));
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
 // cooperative launch with the grid clamped to what can be co-resident
 template <typename K, typename P>
 static int launch_coop(K kernel, const P& params, int64_t blocks_wanted, size_t smem, cudaStream_t st, const char* what) {
@@ -746,7 +860,7 @@ int pp_bn_bwd_res(const void* dy, int ld_dy, int c_off_dy, const void* raw, int 
   return PP_OK;
 }
 
-int pp_bn_scratch_bytes(int C, size_t* out_bytes) {
+int pp_bn_scratch_bytes(int C, size_t* out_bytes) {  // (the cluster path for small tensors does not touch the scratch)
   PP_CHECK_ARG(out_bytes && C > 0, "pp_bn_scratch_bytes: bad args");
   *out_bytes = ((size_t)2 * C + 2) * sizeof(float);
   return PP_OK;
@@ -778,6 +892,13 @@ int pp_bn_fwd_fused(const void* raw, int64_t M, int ld_in, int c_off_in, int C, 
   const size_t sm = kEwThreads * 16 * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool drop = drop_p > 0.f;
+  if (const int nc = bn_cluster_ctas(M, C)) {
+    const size_t smc = sm + (size_t)4 * C * sizeof(float);
+    if (res && drop) return launch_cluster(bn_fwd_cluster_kernel<true, true>, q, nc, smc, st);
+    if (res) return launch_cluster(bn_fwd_cluster_kernel<true, false>, q, nc, smc, st);
+    if (drop) return launch_cluster(bn_fwd_cluster_kernel<false, true>, q, nc, smc, st);
+    return launch_cluster(bn_fwd_cluster_kernel<false, false>, q, nc, smc, st);
+  }
   if (res && drop) return launch_coop(bn_fwd_fused_kernel<true, true>, q, blocks, sm, st, "pp_bn_fwd_fused");
   if (res) return launch_coop(bn_fwd_fused_kernel<true, false>, q, blocks, sm, st, "pp_bn_fwd_fused");
   if (drop) return launch_coop(bn_fwd_fused_kernel<false, true>, q, blocks, sm, st, "pp_bn_fwd_fused");
@@ -811,6 +932,13 @@ int pp_bn_bwd_fused(const void* dy, int ld_dy, int c_off_dy, const void* raw, in
   const size_t sm = kEwThreads * 16 * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool drop = drop_p > 0.f;
+  if (const int nc = bn_cluster_ctas(M, C)) {
+    const size_t smc = sm + (size_t)4 * C * sizeof(float);
+    if (res && drop) return launch_cluster(bn_bwd_cluster_kernel<true, true>, q, nc, smc, st);
+    if (res) return launch_cluster(bn_bwd_cluster_kernel<true, false>, q, nc, smc, st);
+    if (drop) return launch_cluster(bn_bwd_cluster_kernel<false, true>, q, nc, smc, st);
+    return launch_cluster(bn_bwd_cluster_kernel<false, false>, q, nc, smc, st);
+  }
   if (res && drop) return launch_coop(bn_bwd_fused_kernel<true, true>, q, blocks, sm, st, "pp_bn_bwd_fused");
   if (res) return launch_coop(bn_bwd_fused_kernel<true, false>, q, blocks, sm, st, "pp_bn_bwd_fused");
   if (drop) return launch_coop(bn_bwd_fused_kernel<false, true>, q, blocks, sm, st, "pp_bn_bwd_fused");

@@ -244,6 +244,7 @@ def test_depthwise_module_matches_conv2d_through_autograd():
 
 @pytest.mark.parametrize("M,C,relu,p,with_res", [(4 * 16 * 32, 960, 2, 0.0, False), (2 * 64 * 128, 256, 1, 0.5, False),
                                                  (3 * 9 * 14, 2048, 1, 0.0, True), (1000, 24, 0, 0.0, False),
+                                                 (4 * 16 * 32, 96, 0, 0.0, True), (300, 160, 2, 0.5, False),  # cluster path
                                                  (32 * 64 * 128, 64, 1, 0.0, True)])
 def test_single_launch_bn_matches_separate_kernels(M, C, relu, p, with_res):
     """pp_bn_fwd_fused / pp_bn_bwd_fused (one cooperative launch, grid barrier) == stats + finalize + apply / reduce +
