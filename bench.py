@@ -252,7 +252,7 @@ def run_reference(args, rank, world):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
-def bench_train_graph(backbone, B, steps, warmup, dev, world, e2e=False):
+def bench_train_graph(backbone, B, steps, warmup, dev, world, e2e=False, loop=False):
     """Same train step captured ONCE as a CUDA graph (pixelpick_b200/graph.py) and replayed: removes the ~1000 kernel
     launches / step of CPU overhead that bound the reference batch size."""
     import torch.distributed as dist
@@ -269,20 +269,24 @@ def bench_train_graph(backbone, B, steps, warmup, dev, world, e2e=False):
     opt = make_capturable_adam(groups)
     reducer = ppdist.GradAllReducer(model) if world > 1 else None
     hx, hy, hq = synth_train_batch(B, 11 + ppdist.rank(), pin=True)
-    gs = GraphedTrainStep(model, opt, (B, H, W), C, capacity=B * 16, device=dev, reducer=reducer)
+    # loop=True is what pixelpick_b200.Model._train_epoch runs: host batch -> H2D every step (prefetched during the
+    # previous step's graph), running metrics accumulated on the device, ONE device->host read at the end of the epoch
+    gs = GraphedTrainStep(model, opt, (B, H, W), C, capacity=B * 16, device=dev, reducer=reducer,
+                          n_classes=C if loop else None)
     gs.load(hx, hy, hq)
     gs.capture()
     loss_host = torch.zeros(1).pin_memory()
 
-    if e2e:
+    if e2e or loop:
         gs.prefetch(hx, hy, hq)
 
     def step():
-        if e2e:
+        if e2e or loop:
             gs.commit()  # staging -> static inputs (the H2D of this batch ran during the previous step's graph)
         loss, _ = gs()
-        if e2e:
+        if e2e or loop:
             gs.prefetch(hx, hy, hq)  # next host batch -> staging on the copy stream, overlapping the graph (H2D every step)
+        if e2e:
             loss_host.copy_(loss.detach().reshape(1))  # D2H read of this step's loss every step
         return loss
 
@@ -300,17 +304,21 @@ def bench_train_graph(backbone, B, steps, warmup, dev, world, e2e=False):
     a.record()
     for _ in range(steps):
         last = step()
+    if loop:
+        gs.metrics.read()  # the epoch's confusion matrix + loss sum: the loop's only device->host read
     b.record()
     barrier()
     wall = time.perf_counter() - t0
-    ms = a.elapsed_time(b) if not e2e else wall * 1e3
+    ms = a.elapsed_time(b) if not (e2e or loop) else wall * 1e3
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    host = e2e or loop
     return {"value": world * B * steps / (ms / 1e3), "ms_per_step": ms / steps, "batch_per_gpu": B, "steps": steps,
             "cuda_graph": True, "final_loss": float(last.item()),
-            "h2d_bytes_per_step": B * (3 * H * W * 4) + 3 * B * 16 * 4 + 4 if e2e else 0, "d2h_bytes_per_step": 4 if e2e else 0}
+            "h2d_bytes_per_step": B * (3 * H * W * 4) + 3 * B * 16 * 4 + 4 if host else 0,
+            "d2h_bytes_per_step": 4 if e2e else (C * C * 8 + 16) / steps if loop else 0}
 
 
 def bench_train(backbone, B, steps, warmup, dev, world, e2e=False):
@@ -594,6 +602,7 @@ def main():
             train[f"{name}_b4"] = bench_train(bb, 4, ts, 5, dev, world)
             train[f"{name}_b4_graph"] = bench_train_graph(bb, 4, ts, 5, dev, world)
             train[f"{name}_b4_graph_e2e"] = bench_train_graph(bb, 4, ts, 5, dev, world, e2e=True)
+            train[f"{name}_b4_graph_loop"] = bench_train_graph(bb, 4, ts, 5, dev, world, loop=True)
             train[f"{name}_b{args.train_batch}"] = bench_train(bb, args.train_batch, ts, 3, dev, world)
             train[f"{name}_b{args.train_batch}_graph"] = bench_train_graph(bb, args.train_batch, ts, 3, dev, world)
             train[f"{name}_b{args.train_batch}_graph_e2e"] = bench_train_graph(bb, args.train_batch, ts, 3, dev, world, e2e=True)

@@ -258,6 +258,13 @@ int pp_bn_bwd_fused(const void* dy, int ld_dy, int c_off_dy, const void* raw, in
                     const float* scale, const float* shift, const float* mean, const float* rstd, int relu, float drop_p,
                     uint64_t seed, uint64_t offset, const uint64_t* seed_dev, const void* res, int ld_res, void* dres,
                     float* sums, void* draw, int ld_draw, int c_off_draw, void* scratch, void* stream);
+/* Running train metrics on the device (replaces the per-step D2H of two full maps for RunningScore.update,
+ * model.py:124-129 / utils/metrics.py:162-177): confusion[lt * n_classes + lp] += 1 for the first *n_valid_dev (or n_max)
+ * (label, prediction) pairs with lt, lp in [0, n_classes); *loss_sum += *loss; *n_steps += 1.  All accumulators are
+ * device memory owned and zeroed by the caller; one launch, CUDA-graph capturable. */
+int pp_metrics_accumulate(const int32_t* labels, const int32_t* preds, const int32_t* n_valid_dev, int n_max,
+                          int n_classes, const float* loss, long long* confusion, double* loss_sum,
+                          long long* n_steps, void* stream);
 /* bilinear align_corners=True resize of bf16 NHWC into a channel slice, and its adjoint (gather form: deterministic,
  * grad_in f32 [N,h,w,C] fully overwritten). */
 int pp_upsample_nhwc_bf16(const void* in, int N, int h, int w, int C, int ld_in, void* out, int H, int W, int ld_out,

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "pp_acq_session_begin_host": ([_vp, _vp, _vp, _vp, _i, _i], _i),
     "pp_acq_session_finish_host": ([_vp, _vp, _vp], _i),
     "pp_sparse_ce": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _f, _vp, _vp, _vp, _vp], _i),
+    "pp_metrics_accumulate": ([_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "pp_upsample_bilinear_ac": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_upsample_bilinear_ac_bwd": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_conv_wgrad": ([_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
@@ -286,6 +287,32 @@ def sparse_ce(logits_lowres, size, px_img, px_idx, px_label, grad_scale=1.0, wan
                              _ptr(n_valid), float(grad_scale), _ptr(loss), _ptr(grad), _ptr(pred), _stream(x)),
           "pp_sparse_ce")
     return loss, grad, pred
+
+
+class DeviceMetrics:
+    """Confusion matrix / loss sum / step count accumulated on the device (pp_metrics_accumulate); read() once per epoch."""
+
+    def __init__(self, n_classes, device):
+        self.n_classes = n_classes
+        self.confusion = torch.zeros((n_classes, n_classes), dtype=torch.int64, device=device)
+        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=device)
+        self.n_steps = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def accumulate(self, labels, preds, loss=None, n_valid=None):
+        _need_cuda(labels, preds)
+        assert labels.dtype == torch.int32 and preds.dtype == torch.int32 and labels.numel() == preds.numel()
+        check(lib().pp_metrics_accumulate(_ptr(labels), _ptr(preds), _ptr(n_valid), int(labels.numel()), self.n_classes,
+                                          _ptr(loss), _ptr(self.confusion), _ptr(self.loss_sum), _ptr(self.n_steps),
+                                          _stream(labels)), "pp_metrics_accumulate")
+
+    def read(self):
+        """(confusion [C, C] numpy int64, loss sum, steps) — one device->host sync."""
+        return self.confusion.cpu().numpy(), float(self.loss_sum.item()), int(self.n_steps.item())
+
+    def reset(self):
+        self.confusion.zero_()
+        self.loss_sum.zero_()
+        self.n_steps.zero_()
 
 
 def upsample_bilinear_ac(x, size):

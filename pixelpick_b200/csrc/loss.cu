@@ -132,6 +132,25 @@ __global__ void __launch_bounds__(256) upsample_ac_bwd_kernel(const float* __res
 
 }  // namespace pp
 
+namespace pp {
+__global__ void metrics_accumulate_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ preds,
+                                          const int32_t* __restrict__ n_valid_dev, int n_max, int n_classes,
+                                          const float* __restrict__ loss, unsigned long long* __restrict__ confusion,
+                                          double* __restrict__ loss_sum, unsigned long long* __restrict__ n_steps) {
+  int n = n_valid_dev ? *n_valid_dev : n_max;
+  n = n < n_max ? n : n_max;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int lt = labels[i], lp = preds[i];
+    if (lt >= 0 && lt < n_classes && lp >= 0 && lp < n_classes)  // utils/metrics.py:168-173 (_fast_hist mask)
+      atomicAdd(confusion + (size_t)lt * n_classes + lp, 1ull);
+  }
+  if (threadIdx.x == 0) {
+    if (loss && loss_sum) *loss_sum += (double)*loss;
+    if (n_steps) *n_steps += 1ull;
+  }
+}
+}  // namespace pp
+
 using namespace pp;
 
 extern "C" {
@@ -183,6 +202,22 @@ int pp_upsample_bilinear_ac_bwd(const float* grad_out, int n_img, int C, int H, 
   if (blocks > 148 * 32) blocks = 148 * 32;
   upsample_ac_bwd_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       grad_out, H, W, grad_in, h_in, w_in, ac_scale(h_in, H), ac_scale(w_in, W), total);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+
+/* Running train metrics on the device: the reference copies two full int64 maps to the host every
+ * step for RunningScore.update (model.py:124-129, utils/metrics.py:162-177).  Only labelled pixels count (every other
+ * pixel is ignore_index and _fast_hist drops it), so the confusion matrix is accumulated from the (label, prediction)
+ * pairs the sparse-CE kernel already produced — inside the captured step, read back once per epoch. */
+int pp_metrics_accumulate(const int32_t* labels, const int32_t* preds, const int32_t* n_valid_dev, int n_max,
+                          int n_classes, const float* loss, long long* confusion, double* loss_sum,
+                          long long* n_steps, void* stream) {
+  PP_CHECK_ARG(labels && preds && confusion && n_max >= 0 && n_classes > 0, "pp_metrics_accumulate: bad args");
+  pp::metrics_accumulate_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      labels, preds, n_valid_dev, n_max, n_classes, loss, reinterpret_cast<unsigned long long*>(confusion), loss_sum,
+      reinterpret_cast<unsigned long long*>(n_steps));
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

@@ -24,7 +24,8 @@ def make_capturable_adam(param_groups):
 
 
 class GraphedTrainStep:
-    def __init__(self, model, optimizer, batch_shape, ignore_index, capacity, device, reducer=None, warmup=3):
+    def __init__(self, model, optimizer, batch_shape, ignore_index, capacity, device, reducer=None, warmup=3,
+                 n_classes=None):
         B, H, W = batch_shape
         self.model, self.opt, self.ignore_index, self.capacity, self.size = model, optimizer, ignore_index, capacity, (H, W)
         self.reducer = reducer
@@ -47,6 +48,10 @@ class GraphedTrainStep:
         self.commit_done = torch.cuda.Event()
         self.commit_done.record()
         self._staged = False
+        # running metrics accumulated INSIDE the captured step (confusion matrix of the labelled pixels, loss sum): the
+        # loop needs no per-step device->host read at all
+        from . import _lib
+        self.metrics = _lib.DeviceMetrics(n_classes, device) if n_classes else None
         self.graph = None
         self._warm = warmup
 
@@ -58,6 +63,8 @@ class GraphedTrainStep:
         if self.reducer is not None:
             self.reducer()
         self.opt.step()
+        if self.metrics is not None:
+            self.metrics.accumulate(self.px[2], pred, loss=loss.detach().reshape(1), n_valid=self.n_valid)
         return loss, pred
 
     def prefetch(self, x, y, queries):
@@ -141,6 +148,8 @@ class GraphedTrainStep:
             self.loss, self.pred = self._step()
         if snap is not None:
             self._restore(snap)
+        if self.metrics is not None:
+            self.metrics.reset()  # the warm-up steps are not part of the epoch
         return self
 
     def __call__(self):

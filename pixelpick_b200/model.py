@@ -108,18 +108,18 @@ class Model:
             from .graph import GraphedTrainStep
             per_img = min(shape[1] * shape[2], self.init_n_pixels + self.max_budget + self.n_pixels_by_us + 16)
             gs = GraphedTrainStep(model, optimizer, shape, self.ignore_index, capacity=shape[0] * per_img,
-                                  device=self.device, reducer=reducer)
+                                  device=self.device, reducer=reducer, n_classes=self.n_classes)
             gs.load(x, y, q)
             gs.capture(restore_state=True)  # warm-up steps leave no trace: the first replay is the first update
             self._graph, self._graph_shape = gs, shape
         if shape != self._graph_shape:
             return None
-        labels = self._graph_labels if self._graph_labels is not None else gs.prefetch(x, y, q)
+        if self._graph_labels is None:
+            gs.prefetch(x, y, q)
         self._graph_labels = None
         gs.commit()
-        loss, pred = gs()
-        n = labels.numel()
-        return loss.detach(), labels, pred[:n]
+        gs()  # loss / predictions / confusion matrix stay on the device until the end of the epoch
+        return True
 
     def _prefetch_next(self, dict_data):
         """upload the NEXT batch while the graph of the current one runs (copy stream, double-buffered staging)."""
@@ -128,7 +128,8 @@ class Model:
             return
         x = dict_data["x"]
         if (x.shape[0], x.shape[2], x.shape[3]) == self._graph_shape:
-            self._graph_labels = gs.prefetch(x, dict_data["y"], dict_data["queries"])
+            gs.prefetch(x, dict_data["y"], dict_data["queries"])
+            self._graph_labels = True
 
     def _train_epoch(self, epoch, model, optimizer, lr_scheduler, reducer=None):
         if self.n_pixels_by_us != 0:
@@ -139,16 +140,15 @@ class Model:
         it = iter(self.dataloader)
         dict_data = next(it, None)
         while dict_data is not None:
-            out = self._graphed_step(model, optimizer, dict_data, reducer) if self._use_graph else None
-            loss, labels, preds = out if out is not None else self.train_step(model, optimizer, dict_data, reducer)
+            graphed = self._graphed_step(model, optimizer, dict_data, reducer) if self._use_graph else None
+            if graphed is None:  # eager step: metrics from the labelled pixels, read back per step (model.py:124-136)
+                loss, labels, preds = self.train_step(model, optimizer, dict_data, reducer)
+                self.running_score.update_pairs(labels.cpu().numpy(), preds.cpu().numpy())
+                self.running_loss.update(loss.item())
             nxt = next(it, None)
-            if self._use_graph and out is not None:
+            if graphed:
                 self._prefetch_next(nxt)  # H2D of the next batch overlaps this batch's graph
             dict_data = nxt
-            self.running_score.update_pairs(labels.cpu().numpy(), preds.cpu().numpy())
-            self.running_loss.update(loss.item())
-            scores = self.running_score.get_scores()[0]
-            miou, pixel_acc = scores["Mean IoU"], scores["Pixel Acc"]
             if self.lr_scheduler_type == "Poly":
                 lr_scheduler.step(epoch=epoch - 1)
             if self.debug:
@@ -156,6 +156,14 @@ class Model:
         self._graph_labels = None
         if self._graph is not None:
             self._graph._staged = False  # a batch prefetched before a debug break is dropped
+            if self._graph.metrics is not None:  # ONE device->host read per epoch
+                conf, loss_sum, n_steps = self._graph.metrics.read()
+                self._graph.metrics.reset()
+                self.running_score.update_confusion(conf)
+                if n_steps:
+                    self.running_loss.update(loss_sum / n_steps, weight=n_steps)
+        scores = self.running_score.get_scores()[0]
+        miou, pixel_acc = scores["Mean IoU"], scores["Pixel Acc"]
         if self.lr_scheduler_type == "MultiStepLR":
             lr_scheduler.step(epoch=epoch - 1)
         print(f"({self.experim_name}) Epoch {epoch} | mIoU.: {miou:.3f} | pixel acc.: {pixel_acc:.3f} | "

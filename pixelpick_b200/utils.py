@@ -114,6 +114,10 @@ class RunningScore:
     def update_pairs(self, labels, preds):
         self.confusion_matrix += self._fast_hist(np.asarray(labels).flatten(), np.asarray(preds).flatten())
 
+    def update_confusion(self, confusion):
+        """add a confusion matrix accumulated elsewhere (the on-device accumulator of the captured train step)."""
+        self.confusion_matrix += np.asarray(confusion, dtype=np.float64)
+
     def get_scores(self):
         hist = self.confusion_matrix
         with np.errstate(divide="ignore", invalid="ignore"):

@@ -136,16 +136,30 @@ def test_model_loop_uses_the_graphed_step_and_matches_eager(tmp_path):
         sched = get_lr_scheduler(args, optimizer=opt, iters_per_epoch=len(m.dataloader))
         batches = [b for b in m.dataloader][:2]
         model.train()
-        ls = []
+        ls, pairs = [], []
         for it in range(6):
             b = batches[it % 2]
             out = m._graphed_step(model, opt, b, None) if m._use_graph else None
             assert (out is not None) == (mode == "graph")
-            loss, labels, preds = out if out is not None else m.train_step(model, opt, b)
-            assert labels.numel() == preds.numel() > 0
+            if out is None:
+                loss, labels, preds = m.train_step(model, opt, b)
+                assert labels.numel() == preds.numel() > 0
+                pairs.append((labels.cpu().numpy(), preds.cpu().numpy()))
+            else:
+                loss = m._graph.loss  # stays on the device in the loop; read here only for the comparison
             ls.append(float(loss))
             sched.step(epoch=0)
         losses[mode] = ls
+        if mode == "graph":  # the on-device accumulator saw every replay exactly once
+            conf, loss_sum, n_steps = m._graph.metrics.read()
+            assert n_steps == 6 and abs(loss_sum - sum(ls)) < 1e-3 * abs(sum(ls))
+            assert conf.sum() == sum(int(b["queries"].sum()) for b in batches) * 3  # 10 px / image, none of them void
+        else:
+            from pixelpick_b200.utils import RunningScore
+            rs = RunningScore(19)
+            for lt, lp in pairs:
+                rs.update_pairs(lt, lp)
+            assert rs.confusion_matrix.sum() == sum(int(b["queries"].sum()) for b in batches) * 3
     print(losses)
     # the first replay is the first update from the SAME initial state (bf16 + float-atomic noise only) ...
     assert abs(losses["graph"][0] - losses["eager"][0]) < 5e-2 * losses["eager"][0], losses

@@ -70,3 +70,33 @@ def test_upsample_align_corners_fwd_bwd(shape, size):
     want.backward(go)
     gin = _lib.upsample_bilinear_ac_bwd(go.to(DEV), shape[2:]).cpu()
     assert torch.allclose(gin, xr.grad, atol=1e-5, rtol=1e-4)
+
+
+def test_device_metrics_equal_fast_hist():
+    """pp_metrics_accumulate == the reference's RunningScore._fast_hist (utils/metrics.py:168-173) on (label, prediction)
+    pairs, bit-exact, incl. ignore_index labels, a device-side valid count and accumulation over several launches."""
+    import numpy as np
+    from pixelpick_b200 import _lib
+    from pixelpick_b200.utils import RunningScore
+    dev = torch.device("cuda:0")
+    C = 19
+    rs = np.random.RandomState(0)
+    dm = _lib.DeviceMetrics(C, dev)
+    ref = RunningScore(C)
+    loss_total = 0.0
+    for step in range(4):
+        n_max = 500
+        lt = rs.randint(0, C + 2, size=n_max).astype(np.int32)  # C, C+1 play ignore_index: dropped
+        lt[rs.rand(n_max) < 0.05] = 255
+        lp = rs.randint(0, C, size=n_max).astype(np.int32)
+        n_valid = int(rs.randint(1, n_max + 1)) if step % 2 else n_max
+        loss = torch.tensor([0.5 + step], device=dev)
+        dm.accumulate(torch.from_numpy(lt).to(dev), torch.from_numpy(lp).to(dev), loss=loss,
+                      n_valid=torch.tensor([n_valid], dtype=torch.int32, device=dev) if step % 2 else None)
+        ref.update_pairs(np.where(lt[:n_valid] < C, lt[:n_valid], C + 5), lp[:n_valid])
+        loss_total += 0.5 + step
+    conf, loss_sum, n_steps = dm.read()
+    assert n_steps == 4 and abs(loss_sum - loss_total) < 1e-6
+    assert np.array_equal(conf, ref.confusion_matrix.astype(np.int64))
+    dm.reset()
+    assert dm.read()[0].sum() == 0
