@@ -265,6 +265,14 @@ int pp_bn_bwd_fused(const void* dy, int ld_dy, int c_off_dy, const void* raw, in
 int pp_metrics_accumulate(const int32_t* labels, const int32_t* preds, const int32_t* n_valid_dev, int n_max,
                           int n_classes, const float* loss, long long* confusion, double* loss_sum,
                           long long* n_steps, void* stream);
+/* Validation metrics in one pass (model.py:177-239 `_val`, eval.py:15-94 `evaluate`): pred = argmax over classes of the
+ * x4 bilinear (align_corners=True) upsample of the 1/4-resolution head logits [n, C, h_in, w_in] (first maximum, NaN =
+ * maximum, as torch.argmax); confusion[lt * C + pred] += 1 for every pixel whose label lt is in [0, C).  labels
+ * [n, H, W] of label_dtype 0 int64 / 1 int32 / 2 uint8 (device); confusion: device int64 [C*C], accumulated (caller zeroes
+ * it once per epoch); pred_out: optional int32 [n, H, W].  C in {11, 19, 21}. */
+int pp_eval_confusion_upsampled(const float* logits_lowres, int n_img, int C, int h_in, int w_in, int H, int W,
+                                const void* labels, int label_dtype, long long* confusion, int32_t* pred_out,
+                                void* stream);
 /* bilinear align_corners=True resize of bf16 NHWC into a channel slice, and its adjoint (gather form: deterministic,
  * grad_in f32 [N,h,w,C] fully overwritten). */
 int pp_upsample_nhwc_bf16(const void* in, int N, int h, int w, int C, int ld_in, void* out, int H, int W, int ld_out,

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "pp_acq_session_begin_host": ([_vp, _vp, _vp, _vp, _i, _i], _i),
     "pp_acq_session_finish_host": ([_vp, _vp, _vp], _i),
     "pp_sparse_ce": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _f, _vp, _vp, _vp, _vp], _i),
+    "pp_eval_confusion_upsampled": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp], _i),
     "pp_metrics_accumulate": ([_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "pp_upsample_bilinear_ac": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_upsample_bilinear_ac_bwd": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
@@ -313,6 +314,23 @@ class DeviceMetrics:
         self.confusion.zero_()
         self.loss_sum.zero_()
         self.n_steps.zero_()
+
+
+def eval_confusion_upsampled(logits_lowres, size, labels, confusion, want_pred=False):
+    """confusion (device int64 [C, C]) += confusion matrix of argmax(upsample(logits_lowres)) vs labels [n, H, W] (device,
+    int64 / int32 / uint8); returns the int32 prediction map when want_pred."""
+    _need_cuda(logits_lowres, labels, confusion)
+    n, Cc, h, w = logits_lowres.shape
+    H, W = size
+    x = logits_lowres.float().contiguous()
+    code = {torch.int64: 0, torch.int32: 1, torch.uint8: 2}.get(labels.dtype)
+    if code is None or tuple(labels.shape) != (n, H, W) or not labels.is_contiguous():
+        raise PixelPickError("labels must be a contiguous [n, H, W] int64 / int32 / uint8 tensor")
+    assert confusion.dtype == torch.int64 and confusion.numel() == Cc * Cc and confusion.is_contiguous()
+    pred = torch.empty((n, H, W), dtype=torch.int32, device=x.device) if want_pred else None
+    check(lib().pp_eval_confusion_upsampled(_ptr(x), n, Cc, h, w, H, W, _ptr(labels), code, _ptr(confusion), _ptr(pred),
+                                            _stream(x)), "pp_eval_confusion_upsampled")
+    return pred
 
 
 def upsample_bilinear_ac(x, size):

@@ -133,6 +133,59 @@ __global__ void __launch_bounds__(256) upsample_ac_bwd_kernel(const float* __res
 }  // namespace pp
 
 namespace pp {
+// Validation path (model.py:177-239, eval.py:15-94): pred = argmax_c F.interpolate(logits_lowres, (H, W), bilinear,
+// align_corners=True); RunningScore.update(y, pred).  One pass: every thread interpolates its pixel's C logits from the
+// 1/4-resolution head output (full-resolution logits and the int64 prediction map never exist), takes the first maximum
+// (torch.argmax), and the (label, prediction) pair goes into a per-CTA shared-memory confusion matrix that is flushed with
+// one atomic per non-empty cell.  label dtype: 0 int64, 1 int32, 2 uint8.
+template <int C>
+__global__ void __launch_bounds__(256) eval_confusion_up_kernel(const float* __restrict__ logits, int h_in, int w_in, int H, int W,
+                                                                float scale_h, float scale_w, const void* __restrict__ labels,
+                                                                int label_dtype, unsigned long long* __restrict__ confusion,
+                                                                int32_t* __restrict__ pred_out) {
+  __shared__ uint32_t sh[C * C];
+  for (int i = threadIdx.x; i < C * C; i += 256) sh[i] = 0;
+  __syncthreads();
+  const int img = blockIdx.y;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t plane = (int64_t)h_in * w_in;
+  const float* __restrict__ base = logits + (int64_t)img * C * plane;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < HW; i += (int64_t)gridDim.x * 256) {
+    const int y = (int)(i / W);
+    const int x = (int)(i - (int64_t)y * W);
+    const Lerp ly = lerp_ac(y, h_in, H, scale_h);
+    const Lerp lx = lerp_ac(x, w_in, W, scale_w);
+    const float* r0 = base + (int64_t)ly.i0 * w_in;
+    const float* r1 = base + (int64_t)ly.i1 * w_in;
+    float best = 0.f;
+    int arg = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float v00 = __ldg(r0 + c * plane + lx.i0), v01 = __ldg(r0 + c * plane + lx.i1);
+      const float v10 = __ldg(r1 + c * plane + lx.i0), v11 = __ldg(r1 + c * plane + lx.i1);
+      const float v = ly.l0 * (lx.l0 * v00 + lx.l1 * v01) + ly.l1 * (lx.l0 * v10 + lx.l1 * v11);
+      if (c == 0 || v > best || (v != v && best == best)) {  // first maximum; NaN counts as the maximum (torch.argmax)
+        best = v;
+        arg = c;
+      }
+    }
+    const int64_t pix = (int64_t)img * HW + i;
+    if (pred_out) pred_out[pix] = arg;
+    long long lt;
+    if (label_dtype == 0) lt = reinterpret_cast<const long long*>(labels)[pix];
+    else if (label_dtype == 1) lt = reinterpret_cast<const int32_t*>(labels)[pix];
+    else lt = reinterpret_cast<const uint8_t*>(labels)[pix];
+    if (lt >= 0 && lt < C) atomicAdd(&sh[(int)lt * C + arg], 1u);  // utils/metrics.py:168-173 (_fast_hist mask)
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * C; i += 256) {
+    const uint32_t v = sh[i];
+    if (v) atomicAdd(confusion + i, (unsigned long long)v);
+  }
+}
+}  // namespace pp
+
+namespace pp {
 __global__ void metrics_accumulate_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ preds,
                                           const int32_t* __restrict__ n_valid_dev, int n_max, int n_classes,
                                           const float* __restrict__ loss, unsigned long long* __restrict__ confusion,
@@ -218,6 +271,33 @@ int pp_metrics_accumulate(const int32_t* labels, const int32_t* preds, const int
   pp::metrics_accumulate_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       labels, preds, n_valid_dev, n_max, n_classes, loss, reinterpret_cast<unsigned long long*>(confusion), loss_sum,
       reinterpret_cast<unsigned long long*>(n_steps));
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+
+int pp_eval_confusion_upsampled(const float* logits_lowres, int n_img, int C, int h_in, int w_in, int H, int W,
+                                const void* labels, int label_dtype, long long* confusion, int32_t* pred_out,
+                                void* stream) {
+  PP_CHECK_ARG(logits_lowres && labels && confusion, "pp_eval_confusion_upsampled: null pointer");
+  PP_CHECK_ARG(n_img > 0 && n_img <= 65535 && h_in > 0 && w_in > 0 && H > 0 && W > 0, "pp_eval_confusion_upsampled: bad shape");
+  PP_CHECK_ARG(label_dtype >= 0 && label_dtype <= 2, "pp_eval_confusion_upsampled: label_dtype=%d (0 int64, 1 int32, 2 uint8)",
+               label_dtype);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t HW = (int64_t)H * W;
+  int64_t gx = (HW + 256 * 4 - 1) / (256 * 4);  // ~4 pixels per thread: amortises the shared-memory matrix flush
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, n_img);
+  const float sh_ = pp::ac_scale(h_in, H), sw_ = pp::ac_scale(w_in, W);
+  unsigned long long* cf = reinterpret_cast<unsigned long long*>(confusion);
+  switch (C) {
+    case 11: pp::eval_confusion_up_kernel<11><<<grid, 256, 0, st>>>(logits_lowres, h_in, w_in, H, W, sh_, sw_, labels, label_dtype, cf, pred_out); break;
+    case 19: pp::eval_confusion_up_kernel<19><<<grid, 256, 0, st>>>(logits_lowres, h_in, w_in, H, W, sh_, sw_, labels, label_dtype, cf, pred_out); break;
+    case 21: pp::eval_confusion_up_kernel<21><<<grid, 256, 0, st>>>(logits_lowres, h_in, w_in, H, W, sh_, sw_, labels, label_dtype, cf, pred_out); break;
+    default:
+      pp::set_error("pp_eval_confusion_upsampled: C=%d not instantiated (11, 19, 21)", C);
+      return PP_ERR_UNSUPPORTED;
+  }
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

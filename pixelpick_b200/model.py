@@ -196,19 +196,12 @@ class Model:
 
     @torch.no_grad()
     def _val(self, epoch, model):
-        """model.py:177-239: bs=1 eval over the validation set, full-map confusion matrix, best-mIoU checkpoint."""
-        model.eval()
-        for dict_data in self.dataloader_val:
-            x, y = dict_data["x"].to(self.device), dict_data["y"]
-            h, w = y.shape[1:]
-            if self.dataset_name == "voc":
-                pad_h = ceil(h / self.stride_total) * self.stride_total - x.shape[2]
-                pad_w = ceil(w / self.stride_total) * self.stride_total - x.shape[3]
-                x = F.pad(x, pad=(0, pad_w, 0, pad_h), mode="reflect")
-            pred = model(x)["pred"][:, :, :h, :w].argmax(dim=1)
-            self.running_score.update(y.numpy(), pred.cpu().numpy())
-            if self.debug:
-                break
+        """model.py:177-239: eval over the validation set, full-map confusion matrix, best-mIoU checkpoint.  The
+        confusion matrix is accumulated on the device (eval.confusion_over_loader: micro-batched forward, fused
+        upsample + argmax + binning kernel) and read back once."""
+        from .eval import confusion_over_loader
+        self.running_score.update_confusion(confusion_over_loader(
+            model, self.dataloader_val, self.n_classes, self.device, self.dataset_name, self.stride_total, self.debug))
         scores = self.running_score.get_scores()[0]
         miou, pixel_acc = scores["Mean IoU"], scores["Pixel Acc"]
         print(f"({self.experim_name}) Epoch {epoch} | val mIoU: {miou:.3f} | pixel acc.: {pixel_acc:.3f}")

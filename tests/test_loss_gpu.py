@@ -100,3 +100,73 @@ def test_device_metrics_equal_fast_hist():
     assert np.array_equal(conf, ref.confusion_matrix.astype(np.int64))
     dm.reset()
     assert dm.read()[0].sum() == 0
+
+
+@pytest.mark.parametrize("C,lr,size,dtype", [(19, (16, 32), (64, 128), torch.int64), (11, (23, 30), (90, 120), torch.int32),
+                                             (21, (10, 13), (40, 52), torch.uint8), (19, (64, 128), (256, 512), torch.int64)])
+def test_eval_confusion_fused_upsample_argmax(C, lr, size, dtype):
+    """pp_eval_confusion_upsampled == RunningScore.update(y, argmax(F.interpolate(logits, size, bilinear, align_corners=True)))
+    (model.py:177-239 / eval.py:44-62): bit-exact on logits quantised to 2^-6 (ties resolved like torch.argmax: first
+    maximum), <= 1e-4 of the pixels off on unconstrained fp32 logits (last-ulp differences of the interpolation)."""
+    import numpy as np
+    from pixelpick_b200 import _lib
+    from pixelpick_b200.utils import RunningScore
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(C + lr[0])
+    n = 3
+    ignore = 255 if dtype == torch.uint8 else C
+    y = torch.randint(0, C, (n,) + size, generator=g)
+    y[torch.rand((n,) + size, generator=g) < 0.05] = ignore
+    for quantised in (True, False):
+        logits = torch.randn((n, C) + lr, generator=g) * 3
+        if quantised:
+            logits = torch.round(logits * 4) / 4  # coarse alphabet: exact ties after interpolation are common
+        full = F.interpolate(logits, size=size, mode="bilinear", align_corners=True)
+        ref = RunningScore(C)
+        ref.update(y.numpy(), full.argmax(dim=1).numpy())
+        conf = torch.zeros((C, C), dtype=torch.int64, device=dev)
+        pred = _lib.eval_confusion_upsampled(logits.to(dev), size, y.to(dtype).to(dev), conf, want_pred=True)
+        got = conf.cpu().numpy()
+        assert got.sum() == int((y != ignore).sum())
+        mism = (pred.cpu().long() != full.argmax(dim=1)).float().mean().item()
+        if quantised:
+            # the interpolation weights are multiples of 1/(out-1): products are not exact, so compare through the
+            # mismatch rate as well, but ties on identical neighbours must resolve to the FIRST maximum
+            assert mism < 1e-3, mism
+        else:
+            assert mism < 1e-4, mism
+        assert np.abs(got - ref.confusion_matrix).sum() <= 2 * mism * y.numel() + 1e-9
+    # accumulation: a second call adds to the same matrix
+    before = conf.clone()
+    _lib.eval_confusion_upsampled(logits.to(dev), size, y.to(dtype).to(dev), conf)
+    assert torch.equal(conf, 2 * before)
+
+
+def test_evaluate_mirror_matches_full_resolution_path(tmp_path):
+    """pixelpick_b200.eval.evaluate (micro-batched, fused kernel) == the reference-style loop (one image, full-res pred,
+    host RunningScore) on a synthetic validation set; also the CLI entry point."""
+    import numpy as np
+    from pixelpick_b200.args import Arguments
+    from pixelpick_b200.eval import evaluate, main
+    from pixelpick_b200.utils import RunningScore, get_dataloader, get_model
+    from copy import deepcopy
+    args = Arguments().parse_args(argv=["--dataset_name", "cs", "--dir_root", str(tmp_path), "--n_workers", "0",
+                                        "--synthetic", "6", "64", "128"])
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = get_model(args).to(dev).eval()
+    dl = get_dataloader(deepcopy(args), val=True, query=False, shuffle=False, batch_size=1, n_workers=0)
+    ref = RunningScore(args.n_classes)
+    with torch.no_grad():
+        for d in dl:
+            pred = model(d["x"].to(dev))["pred"].argmax(dim=1)
+            ref.update(d["y"].numpy(), pred.cpu().numpy())
+    want = ref.get_scores()[0]["Mean IoU"]
+    got = evaluate(model, dl, "test", epoch=1, dir_ckpt=str(tmp_path / "ck"), device=dev, batch_imgs=4)
+    assert abs(got - want) < 2e-3, (got, want)
+    assert (tmp_path / "ck" / "e01" / "val" / "log_val.txt").exists()
+    sd = tmp_path / "m.pt"
+    torch.save({"model": model.state_dict()}, sd)
+    got_cli = main(["--dataset_name", "cs", "--dir_root", str(tmp_path), "--n_workers", "0", "--synthetic", "6", "64", "128",
+                    "--p_state_dict", str(sd)])
+    assert abs(got_cli - want) < 2e-3
