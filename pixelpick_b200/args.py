@@ -107,7 +107,9 @@ class Arguments:
         print(f"\nmodel name: {args.experim_name}\n")
         for fn in (random.seed, np.random.seed, torch.manual_seed):
             fn(args.seed)
-        torch.backends.cudnn.benchmark = True
+        # args.py:197 turns the autotuner on; PP_CUDNN_BENCHMARK=0 (set by tests/conftest.py) skips the minute it costs to
+        # tune ~50 conv shapes in short runs
+        torch.backends.cudnn.benchmark = os.environ.get("PP_CUDNN_BENCHMARK", "1") != "0"
         if verbose:
             for k, v in sorted(vars(args).items()):
                 print(k, v)

@@ -1,7 +1,11 @@
 import os
 import sys
 
+import os
+
 import pytest
+
+os.environ.setdefault("PP_CUDNN_BENCHMARK", "0")  # short test runs: no cuDNN autotuning (pixelpick_b200/args.py)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

@@ -166,3 +166,48 @@ def test_model_loop_uses_the_graphed_step_and_matches_eager(tmp_path):
     # ... afterwards the two runs drift chaotically (lr 5e-4 Adam on a handful of pixels), so compare the trajectory loosely
     assert np.allclose(losses["graph"], losses["eager"], rtol=0.35, atol=0.1), losses
     assert losses["graph"][-1] < losses["graph"][0]
+
+
+def test_train_py_mirror_runs_and_supports_human_labels(tmp_path):
+    """pixelpick_b200.train: train() (train.py:106-176) with evaluation every epoch, and train_epoch on human labels
+    (dense `labelled_queries` maps, train.py:44-45) gives the same loss as the masked-ground-truth form of the same batch."""
+    from copy import deepcopy
+    from pixelpick_b200.train import main, train_epoch
+    from pixelpick_b200.utils import AverageMeter, get_dataloader, get_lr_scheduler, get_model, get_optimizer
+    torch.backends.cudnn.benchmark = False
+    argv = ["--dataset_name", "cs", "--dir_root", str(tmp_path), "--n_workers", "0", "--synthetic", "8", "64", "128",
+            "--n_epochs", "1", "--eval_interval", "1"]
+    model = main(argv)
+    ck = [p for p in (tmp_path / "checkpoints").rglob("best_model.pt")]
+    assert len(ck) == 1 and any((tmp_path / "checkpoints").rglob("log_train.txt")) and any((tmp_path / "checkpoints").rglob("log_val.txt"))
+    assert "seg_head.classifier.weight" in torch.load(ck[0])["model"]
+    # human labels == masked ground truth when the dense map holds y at the queried pixels
+    args = Arguments().parse_args(argv=argv[:-2])
+    dl = get_dataloader(deepcopy(args), val=False, query=False, shuffle=False, batch_size=4, n_workers=0)
+
+    class Human:  # the same batches with `labelled_queries` instead of (y, queries)
+        dataset = dl.dataset
+
+        def __len__(self):
+            return len(dl)
+
+        def __iter__(self):
+            for d in dl:
+                lq = torch.full_like(d["y"], args.ignore_index)
+                m = d["queries"].bool()
+                lq[m] = d["y"][m]
+                yield {"x": d["x"], "labelled_queries": lq}
+
+    losses = []
+    for loader, human in ((dl, False), (Human(), True)):
+        torch.manual_seed(0)
+        m = get_model(args).to("cuda:0")
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        opt = get_optimizer(args, m)
+        sched = get_lr_scheduler(args, optimizer=opt, iters_per_epoch=len(dl))
+        meter = AverageMeter()
+        train_epoch(1, loader, m, opt, sched, meter, "t", human_labels=human, device=torch.device("cuda:0"), debug=True)
+        losses.append(meter.avg)
+    assert abs(losses[0] - losses[1]) < 2e-2 * abs(losses[0]), losses
