@@ -1,8 +1,6 @@
 import os
 import sys
 
-import os
-
 import pytest
 
 os.environ.setdefault("PP_CUDNN_BENCHMARK", "0")  # short test runs: no cuDNN autotuning (pixelpick_b200/args.py)
