@@ -123,7 +123,8 @@ def synth(n_img, seed, device=None, pin=False):
     return logits, lab_t, void_t
 
 
-def synth_train_batch(B, seed, pin=False):
+def synth_train_batch(B, seed, pin=False, size=None):
+    H, W = size or (globals()["H"], globals()["W"])
     g = torch.Generator().manual_seed(seed)
     x = torch.randn((B, 3, H, W), generator=g)
     rs = np.random.RandomState(seed)
@@ -412,14 +413,16 @@ def bench_conv_roofline(dev, peak_tf):
             "nominal_flops_per_launch": flops, "traffic": None}
 
 
-def bench_query_model(backbone, n_img, steps, dev, from_host):
+def bench_query_model(backbone, n_img, steps, dev, from_host, size=None):
     """QuerySelector-style querying with the model in the loop (eval forward_lowres + fused upsample/score + top-k).
     n_img = 1 is the reference's own query batch (model.py:36-37: the query dataloader has batch_size 1)."""
     from pixelpick_b200 import _lib
     from pixelpick_b200.deeplab import DeepLab
+    H, W = size or (globals()["H"], globals()["W"])
+    K_TOP = int(H * W * TOP_N_PERCENT)
     torch.manual_seed(0)
     model = DeepLab(MARGS, backbone=backbone).to(dev).eval()
-    hx, hy, hq = synth_train_batch(n_img, 21, pin=True)
+    hx, hy, hq = synth_train_batch(n_img, 21, pin=True, size=(H, W))
     hvoid = (hy == C).pin_memory()
     dx, dq, dvoid = hx.to(dev), hq.to(dev), hvoid.to(dev)
     ws = _lib.TopKWorkspace(n_img, H * W, K_TOP, dev)
@@ -450,6 +453,54 @@ def bench_query_model(backbone, n_img, steps, dev, from_host):
     dt = time.perf_counter() - t0
     return {"value": n_img * H * W * steps / 1e6 / dt, "images_per_s": n_img * steps / dt, "ms_per_step": dt / steps * 1e3,
             "images_per_step": n_img}
+
+
+def bench_strategy_sweep(dev, hbm_peak, n_img=8, Hs=1024, Ws=2048, steps=5):
+    """BASELINE configs[4]: Cityscapes 1024x2048 query sweep over entropy / margin (= BvSB) / least-confidence on logits
+    resident in HBM: scoring-kernel GB/s (algorithmic bytes, CUDA events) and whole-step Mpixels/s (k = 5 % = 104857)."""
+    from pixelpick_b200 import _lib
+    HWs = Hs * Ws
+    k = int(HWs * TOP_N_PERCENT)
+    g = torch.Generator().manual_seed(5)
+    logits = torch.empty((n_img, C, Hs, Ws), dtype=torch.float32, device=dev)
+    for i in range(n_img):
+        logits[i] = (torch.randn((C, Hs, Ws), generator=g) * 3.0).to(dev)
+    rs = np.random.RandomState(5)
+    lab = torch.from_numpy((rs.rand(n_img, Hs, Ws) < 100.0 / HWs).astype(np.uint8)).to(dev)
+    void = torch.from_numpy((rs.rand(n_img, Hs, Ws) < 0.01).astype(np.uint8)).to(dev)
+    ws = _lib.TopKWorkspace(n_img, HWs, k, dev)
+    score = torch.empty((n_img, Hs, Ws), dtype=torch.float32, device=dev)
+    pos = torch.from_numpy(np.stack([rs.permutation(k)[:N_SEL] for _ in range(n_img)]).astype(np.int32)).to(dev)
+    out = {"workload": f"cityscapes {Hs}x{Ws} C={C} top-5% (k={k}) n={N_SEL}, {n_img} images / step, logits in HBM "
+                       f"({n_img * C * HWs * 4 / 1e6:.0f} MB > L2)"}
+    for strat in ("entropy", "margin_sampling", "least_confidence"):
+        largest = _lib.LARGEST[strat]
+
+        def step(ea=None, eb=None):
+            ws.prepare()
+            if ea is not None:
+                ea.record()
+            _lib.acq_score(logits, strat, lab, void, out=score, hist0_ws=ws)
+            if eb is not None:
+                eb.record()
+            return _lib.acq_select_pick(score.view(n_img, HWs), k, largest, pos, ws=ws, hist0_valid=True)
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for ea, eb in ev:
+            step(ea, eb)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        sms = float(np.mean([x.elapsed_time(y) for x, y in ev]))
+        ach = n_img * HWs * ALG_BYTES_PER_PX / (sms / 1e3) / 1e9
+        out[strat] = {"step_mpixels_per_sec": n_img * HWs / 1e6 / (ms / 1e3), "ms_per_step": ms, "score_kernel_ms": sms,
+                      "score_kernel_gbs": ach, "score_kernel_frac_of_hbm_peak": ach / hbm_peak}
+    return out
 
 
 def main():
@@ -617,6 +668,7 @@ def main():
                       "resnet50_host": bench_query_model("resnet", 32, 5, dev, True),
                       "mobilenetv2_bs1_host": bench_query_model("mobilenet", 1, 50, dev, True),
                       "resnet50_bs1_host": bench_query_model("resnet", 1, 50, dev, True),
+                      "resnet50_1024x2048_bs1_host": bench_query_model("resnet", 1, 10, dev, True, size=(1024, 2048)),
                       "note": "bs1 = the reference's query loop (one image per forward, query.py:159-212); "
                               "hbm/host = 64 (MobileNetV2) / 32 (ResNet-50) images per step"}
     barrier()
@@ -651,6 +703,7 @@ def main():
         if train is not None:
             out["train"] = train
             out["query_model"] = qmodel
+            out["strategy_sweep_1024x2048"] = bench_strategy_sweep(dev, hbm_peak)
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n_cpu = 32

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) acq_score_vec_kernel(cons
     else *reinterpret_cast<float2*>(p.score + pix) = make_float2(out[0], out[1]);
     if (HIST) {
 #pragma unroll
-      for (int j = 0; j < PX; ++j) atomicAdd(&sh_hist[ord_key(out[j], largest) >> 21], 1u);
+      for (int j = 0; j < PX; ++j) atomicAdd(&sh_hist[bucket0(out[j], largest)], 1u);
     }
   }
   if (HIST) {
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kScoreThreads) acq_score_scalar_kernel(const S
     if (p.keep) masked |= p.keep[pix] == 0;
     if (masked) s = p.fill;
     p.score[pix] = s;
-    if (hist) atomicAdd(&sh_hist[ord_key(s, p.largest != 0) >> 21], 1u);
+    if (hist) atomicAdd(&sh_hist[bucket0(s, p.largest != 0)], 1u);
   }
   if (hist) {
     __syncthreads();
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kScoreThreads) acq_score_up_kernel(const Score
     if (p.keep) masked |= p.keep[pix] == 0;
     if (masked) s = p.fill;
     p.score[pix] = s;
-    if (hist) atomicAdd(&sh_hist[ord_key(s, p.largest != 0) >> 21], 1u);
+    if (hist) atomicAdd(&sh_hist[bucket0(s, p.largest != 0)], 1u);
   }
   if (hist) {
     __syncthreads();
@@ -366,6 +366,8 @@ struct SelState {
   uint32_t remaining;
   uint32_t done;
   uint32_t bucket;  // level-0 bucket (written by pick_bucket0_kernel, read by select_l0_kernel)
+  uint32_t klo;     // smallest ordering key that falls in `bucket`
+  uint32_t khi;     // largest ordering key that falls in `bucket` (inclusive)
   uint32_t pad;
 };
 
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(kSelThreads) hist0_kernel(const float* __restr
   const int img = blockIdx.y;
   const float* s = scores + (size_t)img * HW;
   for (int i = blockIdx.x * kSelThreads + threadIdx.x; i < HW; i += gridDim.x * kSelThreads)
-    atomicAdd(&sh_hist[ord_key(__ldg(s + i), largest != 0) >> 21], 1u);
+    atomicAdd(&sh_hist[bucket0(__ldg(s + i), largest != 0)], 1u);
   __syncthreads();
   uint32_t* gh = hist0 + (size_t)img * kHistBins;
   for (int i = threadIdx.x; i < kHistBins; i += kSelThreads) {
@@ -447,8 +449,9 @@ __global__ void __launch_bounds__(kSelThreads) hist0_kernel(const float* __restr
 // One CTA per image: find the bucket of the level-0 histogram that holds the k-th element; state[img] = {rank inside
 // the bucket, whole bucket selected?, bucket}.  Done once here instead of in the prologue of every select_l0 CTA.
 __global__ void __launch_bounds__(kSelThreads) pick_bucket0_kernel(const uint32_t* __restrict__ hist0, SelState* __restrict__ state,
-                                                                    uint32_t k) {
+                                                                    uint32_t k, bool largest) {
   __shared__ uint32_t sh_warp[kSelThreads / 32];
+  __shared__ uint32_t sh_bucket;
   const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint4* hc = reinterpret_cast<const uint4*>(hist0 + (size_t)img * kHistBins) + tid * 2;
   const uint4 ha = hc[0], hb = hc[1];
@@ -476,10 +479,63 @@ __global__ void __launch_bounds__(kSelThreads) pick_bucket0_kernel(const uint32_
       st.remaining = k - run;
       st.done = (h[i] == k - run) ? 1u : 0u;
       st.bucket = (uint32_t)(tid * 8 + i);
+      st.klo = st.khi = 0u;  // filled by warp 0 below
       st.pad = 0u;
       state[img] = st;
+      sh_bucket = st.bucket;
     }
     run += h[i];
+  }
+  __syncthreads();
+  // key range [klo, khi] of the bucket: bucket0(score) is monotone in the ordering key, so "bucket(s) < b" is
+  // "key(s) < klo" — select_l0 then classifies with unsigned compares instead of re-quantising every score.  Warp 0 finds
+  // the two thresholds by 32-ary search over the key space (7 rounds each).
+  if (warp == 0) {
+    auto bucket_of_key = [&](uint32_t key) -> uint32_t {
+      // keys that no score produces (the NaN payload ranges beyond +-inf) are clamped so the map stays monotone
+      uint32_t u = largest ? ~key : key;
+      if (u == 0xFFFFFFFFu) return largest ? 0u : 2047u;  // the canonical NaN key
+      u = u < 0x007FFFFFu ? 0x007FFFFFu : (u > 0xFF800000u ? 0xFF800000u : u);  // [-inf, +inf]
+      const uint32_t bits = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+      return bucket0(__uint_as_float(bits), largest);
+    };
+    auto first_key_with_bucket_ge = [&](uint32_t b, bool& none) -> uint32_t {
+      none = bucket_of_key(0xFFFFFFFFu) < b;
+      if (none) return 0u;
+      uint64_t lo = 0, hi = 0xFFFFFFFFull;  // invariant: the answer is in [lo, hi]
+      while (lo < hi) {
+        const uint64_t step = (hi - lo + 32) / 33;  // lanes probe lo + (lane + 1) * step - 1 (clamped to hi)
+        uint64_t probe = lo + (uint64_t)(lane + 1) * step - 1;
+        probe = probe > hi ? hi : probe;
+        const bool ok = bucket_of_key((uint32_t)probe) >= b;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+        if (m == 0u) {
+          lo = lo + 32 * step;  // beyond the last probe (which is < hi here, otherwise ok would hold for hi)
+          lo = lo > hi ? hi : lo;
+        } else {
+          const int first = __ffs(m) - 1;
+          const uint64_t p_first = lo + (uint64_t)(first + 1) * step - 1;
+          hi = p_first > hi ? hi : p_first;
+          if (first > 0) lo = lo + (uint64_t)first * step;  // one past the previous probe
+        }
+      }
+      return (uint32_t)lo;
+    };
+    const uint32_t b = sh_bucket;
+    if (!largest) {  // bucket = the key's leading 11 bits: the range is explicit
+      if (lane == 0) {
+        state[img].klo = b << 21;
+        state[img].khi = (b << 21) | 0x1FFFFFu;
+      }
+    } else {
+      bool none;
+      const uint32_t klo = first_key_with_bucket_ge(b, none);
+      const uint32_t nxt = first_key_with_bucket_ge(b + 1u, none);
+      if (lane == 0) {
+        state[img].klo = klo;
+        state[img].khi = none ? 0xFFFFFFFFu : nxt - 1u;
+      }
+    }
   }
 }
 
@@ -516,15 +572,15 @@ __global__ void __launch_bounds__(kSelThreads, 8) select_l0_kernel(const SelPara
                    : "=r"(key[4 * j]), "=r"(key[4 * j + 1]), "=r"(key[4 * j + 2]), "=r"(key[4 * j + 3])
                    : "l"(src));
     }
-#pragma unroll
-    for (int i = 0; i < kL0Items; ++i) key[i] = ord_key(__uint_as_float(key[i]), largest);
   } else {
 #pragma unroll
     for (int i = 0; i < kL0Items; ++i) {
       const uint32_t idx = chunk0 + (uint32_t)(i * kSelThreads + tid);
-      key[i] = ord_key((idx < n_in) ? __ldg(sc + idx) : 0.f, largest);
+      key[i] = __float_as_uint((idx < n_in) ? __ldg(sc + idx) : 0.f);
     }
   }
+#pragma unroll
+  for (int i = 0; i < kL0Items; ++i) key[i] = ord_key(__uint_as_float(key[i]), largest);
   const uint32_t idx0 = FULL ? chunk0 + (uint32_t)tid * 4u : chunk0 + (uint32_t)tid;
   auto index_of = [&](int i) -> uint32_t {
     return FULL ? idx0 + (uint32_t)((i >> 2) * kSelThreads * 4 + (i & 3)) : idx0 + (uint32_t)(i * kSelThreads);
@@ -532,21 +588,20 @@ __global__ void __launch_bounds__(kSelThreads, 8) select_l0_kernel(const SelPara
 
   // ---- level-0 bucket of this image (pick_bucket0_kernel) ----
   const SelState st0 = p.state_next[img];
-  const uint32_t bucket = st0.bucket;
   const bool take_all = st0.done != 0u;
 
-  // ---- classify on the full key: selected <=> key <= sel_max; boundary <=> key - lo <= 0x1FFFFF (and !take_all) ----
-  const uint32_t lo = bucket << 21;
-  const bool sel_any = take_all || bucket > 0;
-  const uint32_t sel_max = take_all ? (lo | 0x1FFFFFu) : lo - 1u;
-  const uint32_t bnd_span = take_all ? 0u : 0x200000u;  // width of the boundary range (0: none)
+  // ---- classify on the ordering key against the bucket's key range [klo, khi] (pick_bucket0_kernel): selected <=>
+  // below the bucket (or inside it when the whole bucket is taken), boundary <=> inside it ----
+  const uint32_t klo = st0.klo, khi = st0.khi;
+  const bool sel_any = take_all || klo > 0u;
+  const uint32_t sel_max = take_all ? khi : klo - 1u;
   static_assert(kL0Items <= 32, "one 32-bit mask per class");
   uint32_t sel_m = 0, bnd_m = 0;  // bit i = item i
 #pragma unroll
   for (int i = 0; i < kL0Items; ++i) {
     const bool in = FULL || index_of(i) < n_in;
     const bool s1 = in && sel_any && key[i] <= sel_max;
-    const bool s2 = in && (key[i] - lo) < bnd_span;
+    const bool s2 = in && !take_all && key[i] >= klo && key[i] <= khi;
     sel_m |= (uint32_t)s1 << i;
     bnd_m |= (uint32_t)s2 << i;
   }
@@ -595,7 +650,7 @@ __global__ void __launch_bounds__(kSelThreads, 8) select_l0_kernel(const SelPara
   }
 }
 
-// Levels 1..4 for one image in ONE CTA: the boundary bucket of level 0 is small (L2-resident), so the remaining
+// The radix tail for one image in ONE CTA: the boundary bucket of level 0 is small (L2-resident), so all key-digit
 // radix levels (histogram in shared memory -> pick -> partition) run back to back without further launches or
 // global histogram traffic.  Appends are warp-aggregated shared-memory atomics; order is irrelevant (sorted later).
 constexpr int kRestThreads = 1024;
@@ -607,6 +662,7 @@ struct RestParams {
   uint32_t* cand_count;
   const SelState* state1;  // {remaining, done} after level 0
   int HW, kpad;
+  int first_level;  // 1 when level 0 was the key's leading digit (it is constant in the boundary list), else 0
 };
 
 __global__ void __launch_bounds__(kRestThreads) select_rest_kernel(const RestParams p) {
@@ -624,7 +680,7 @@ __global__ void __launch_bounds__(kRestThreads) select_rest_kernel(const RestPar
   uint64_t* cand = p.cand + (size_t)img * p.kpad;
   uint32_t n = p.count_a[img];
   if (tid == 0) sh_cnt[0] = p.cand_count[img];
-  for (int level = 1; level < kLevels; ++level) {
+  for (int level = p.first_level; level < kLevels; ++level) {  // from the key's first digit when level 0 was the linear bucket0
     const int shift = c_shift[level];
     const uint32_t dmask = (1u << c_bits[level]) - 1u;
     for (int i = tid; i < kHistBins; i += kRestThreads) sh_hist[i] = 0;
@@ -702,9 +758,233 @@ struct PickParams {
   int kpad, k, n;
   const int32_t* pos;    // [n_img][n] ranks (nullptr: 0..n-1)
   int32_t* out;          // [n_img][n]
+  uint32_t* fallback;    // [n_img]: written by the fast kernel (1 = this image needs the generic kernel), read by the generic one
 };
 
 constexpr int kPickItems = 16;  // candidates cached in registers when k <= 512 * 16
+
+// Fast path of the order-statistics pick (n <= kPickRanks ranks, the common case n = 10): THREE cheap passes over the
+// k candidates instead of five 12-way compare passes.
+//   pass 1  histogram of the leading 11-bit digit (shared by all ranks)            -> per rank: bucket b0, rank inside it
+//   pass 2  ranks that share b0 form a group; map0[digit0] -> group (one byte table lookup); candidates of a group are
+//           histogrammed by their second digit                                     -> per rank: bucket b1, count, rank
+//   pass 3  candidates whose 22-bit prefix equals a rank's are appended to that rank's list (<= 32 entries), one warp
+//           ranks each list directly
+// A candidate costs a load, two shifts and one table lookup per pass (the generic kernel compares every live candidate
+// with every rank's 64-bit prefix at every level: ~3000 instructions per thread at k = 6553, and at k = 104857 — 5 % of a
+// 1024x2048 image — its single CTA per image took ~0.35 ms).  If a 22-bit group holds more than 32 candidates (heavy
+// ties) or n > kPickRanks, the image is flagged and the generic kernel below finishes it.
+__global__ void __launch_bounds__(kPickThreads, 2) pick_ranks_fast_kernel(const PickParams p) {
+  extern __shared__ uint32_t sh_h[];  // [kPickRanks][2048]: hist0 = sh_h[0..2048), hist1[g] = sh_h[g * 2048 ...)
+  __shared__ uint8_t map0[kHistBins];
+  __shared__ uint32_t sh_b0[kPickRanks], sh_b1[kPickRanks], sh_rem[kPickRanks], sh_cnt[kPickRanks], sh_grp[kPickRanks];
+  __shared__ uint32_t sh_n[kPickRanks];
+  __shared__ uint64_t sh_res[kPickRanks];
+  __shared__ uint32_t sh_ng, sh_ok;
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t* c = p.cand + (size_t)img * p.kpad;
+  const int nr = p.n;
+  if (nr > kPickRanks) {  // more ranks than one pass handles: generic kernel
+    if (tid == 0) p.fallback[img] = 1u;
+    return;
+  }
+  const bool cached = p.k <= kPickThreads * kPickItems;
+  uint64_t reg[kPickItems];
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < kPickItems; ++i) {
+      const int idx = i * kPickThreads + tid;
+      reg[i] = (idx < p.k) ? c[idx < p.k ? idx : 0] : ~0ull;
+    }
+  }
+  const int s0 = c_shift[0], s1 = c_shift[1];
+  const uint32_t m0 = (1u << c_bits[0]) - 1u, m1 = (1u << c_bits[1]) - 1u;
+  for (int i = tid; i < kHistBins; i += kPickThreads) sh_h[i] = 0;
+  if (tid < nr) {
+    int r = p.pos ? p.pos[(size_t)img * p.n + tid] : tid;
+    r = r < 0 ? 0 : (r >= p.k ? p.k - 1 : r);
+    sh_rem[tid] = (uint32_t)r + 1u;
+  }
+  __syncthreads();
+  // ---- pass 1: leading digit (few distinct values: aggregate equal digits inside the warp) ----
+  auto hist0_add = [&](uint64_t v, bool valid) {
+    const uint32_t d = valid ? ((uint32_t)(v >> s0) & m0) : 0xFFFFFFFFu;
+    const uint32_t m = __match_any_sync(0xFFFFFFFFu, d);
+    if (valid && lane == __ffs(m) - 1) atomicAdd(&sh_h[d], (uint32_t)__popc(m));
+  };
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < kPickItems; ++i) hist0_add(reg[i], i * kPickThreads + tid < p.k);
+  } else {
+    for (int i0 = 0; i0 < p.k; i0 += kPickThreads) {
+      const int i = i0 + tid;
+      hist0_add(i < p.k ? c[i] : 0ull, i < p.k);
+    }
+  }
+  __syncthreads();
+  // narrowing: warp j finds the bin of `h` that holds the element of 1-based rank sh_rem[j]
+  auto narrow = [&](const uint32_t* h, int j, uint32_t* bucket_out) {
+    const uint32_t rem = sh_rem[j];
+    uint32_t mine = 0;
+    for (int b = 0; b < 64; ++b) mine += h[lane * 64 + ((b + lane) & 63)];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    uint32_t run = incl - mine;
+    const bool here = run < rem && rem <= incl;
+    int found = -1;
+    uint32_t before = 0, in_bin = 0;
+    if (here) {
+      for (int b = 0; b < 64; ++b) {
+        const uint32_t hb = h[lane * 64 + b];
+        if (run < rem && rem <= run + hb) { found = lane * 64 + b; before = run; in_bin = hb; break; }
+        run += hb;
+      }
+    }
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, found >= 0);
+    const int src = __ffs(m) - 1;
+    found = __shfl_sync(0xFFFFFFFFu, found, src);
+    before = __shfl_sync(0xFFFFFFFFu, before, src);
+    in_bin = __shfl_sync(0xFFFFFFFFu, in_bin, src);
+    if (lane == 0) {
+      bucket_out[j] = (uint32_t)found;
+      sh_rem[j] = rem - before;
+      sh_cnt[j] = in_bin;
+    }
+  };
+  for (int j = warp; j < nr; j += kPickThreads / 32) narrow(sh_h, j, sh_b0);
+  for (int i = tid; i < kHistBins; i += kPickThreads) map0[i] = 255;
+  __syncthreads();
+  // ---- groups of ranks sharing the leading bucket ----
+  if (tid == 0) {
+    uint32_t ng = 0;
+    for (int j = 0; j < nr; ++j) {
+      const uint32_t b = sh_b0[j];
+      if (map0[b] == 255) map0[b] = (uint8_t)ng++;
+      sh_grp[j] = map0[b];
+    }
+    sh_ng = ng;
+  }
+  __syncthreads();
+  const uint32_t ng = sh_ng;
+  for (int i = tid; i < (int)ng * kHistBins; i += kPickThreads) sh_h[i] = 0;  // hist0 is dead: reuse as hist1[g]
+  if (tid < kPickRanks) sh_n[tid] = 0;
+  __syncthreads();
+  // ---- pass 2: second digit of the candidates that fall in a rank's leading bucket ----
+  auto hist1_add = [&](uint64_t v) {
+    const uint32_t g = map0[(uint32_t)(v >> s0) & m0];
+    if (g != 255u) atomicAdd(&sh_h[g * kHistBins + ((uint32_t)(v >> s1) & m1)], 1u);
+  };
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < kPickItems; ++i)
+      if (i * kPickThreads + tid < p.k) hist1_add(reg[i]);
+  } else {
+    for (int i = tid; i < p.k; i += kPickThreads) hist1_add(c[i]);
+  }
+  __syncthreads();
+  for (int j = warp; j < nr; j += kPickThreads / 32) narrow(sh_h + sh_grp[j] * kHistBins, j, sh_b1);
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t mx = 0;
+    for (int j = 0; j < nr; ++j) mx = sh_cnt[j] > mx ? sh_cnt[j] : mx;
+    sh_ok = (mx <= 32u) ? 1u : 0u;
+  }
+  __syncthreads();
+  int gshift = s1;  // candidates are compared with a rank's prefix above this bit
+  if (!sh_ok) {
+    // ---- optional pass 2b: a 22-bit group is still larger than a warp (scores packed into a narrow range, e.g. the
+    // top 5 % of entropies of a 1024x2048 image): split it by the remaining 10 key bits -> the whole float is resolved
+    const int s2 = c_shift[2];
+    const uint32_t m2 = (1u << c_bits[2]) - 1u;
+    __shared__ uint32_t gp2[kPickRanks], sh_b2[kPickRanks], sh_ng2;
+    if (tid == 0) {
+      uint32_t n2 = 0;
+      for (int j = 0; j < nr; ++j) {
+        const uint32_t pj = (sh_b0[j] << c_bits[1]) | sh_b1[j];
+        uint32_t g = 0;
+        while (g < n2 && gp2[g] != pj) ++g;
+        if (g == n2) gp2[n2++] = pj;
+        sh_grp[j] = g;
+      }
+      sh_ng2 = n2;
+    }
+    __syncthreads();
+    const uint32_t ng2 = sh_ng2;
+    for (int i = tid; i < (int)ng2 * kHistBins; i += kPickThreads) sh_h[i] = 0;
+    __syncthreads();
+    uint32_t gpr[kPickRanks];
+#pragma unroll
+    for (int j = 0; j < kPickRanks; ++j) gpr[j] = (j < (int)ng2) ? gp2[j] : 0xFFFFFFFFu;
+    auto hist2_add = [&](uint64_t v) {
+      if (map0[(uint32_t)(v >> s0) & m0] == 255u) return;
+      const uint32_t key = (uint32_t)(v >> s1);
+#pragma unroll
+      for (int g = 0; g < kPickRanks; ++g)
+        if (key == gpr[g]) atomicAdd(&sh_h[g * kHistBins + ((uint32_t)(v >> s2) & m2)], 1u);
+    };
+    if (cached) {
+#pragma unroll
+      for (int i = 0; i < kPickItems; ++i)
+        if (i * kPickThreads + tid < p.k) hist2_add(reg[i]);
+    } else {
+      for (int i = tid; i < p.k; i += kPickThreads) hist2_add(c[i]);
+    }
+    __syncthreads();
+    for (int j = warp; j < nr; j += kPickThreads / 32) narrow(sh_h + sh_grp[j] * kHistBins, j, sh_b2);
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t mx = 0;
+      for (int j = 0; j < nr; ++j) {
+        mx = sh_cnt[j] > mx ? sh_cnt[j] : mx;
+        sh_b1[j] = (sh_b1[j] << c_bits[2]) | sh_b2[j];  // b1 now carries 21 bits: prefix = b0 : b1 : b2 = the 32 key bits
+      }
+      sh_ok = (mx <= 32u) ? 1u : 0u;
+    }
+    __syncthreads();
+    gshift = s2;
+  }
+  if (tid == 0) p.fallback[img] = sh_ok ? 0u : 1u;
+  if (!sh_ok) return;  // exact ties beyond a warp: the generic kernel finishes this image
+  // ---- pass 3: gather each rank's group and rank it directly ----
+  uint64_t* lists = reinterpret_cast<uint64_t*>(sh_h);  // [kPickRanks][32]; the histograms are dead
+  __syncthreads();
+  const int b1_bits = (gshift == s1) ? c_bits[1] : c_bits[1] + c_bits[2];
+  uint32_t pre[kPickRanks];  // every rank's key prefix above gshift
+#pragma unroll
+  for (int j = 0; j < kPickRanks; ++j) pre[j] = (j < nr) ? ((sh_b0[j] << b1_bits) | sh_b1[j]) : 0xFFFFFFFFu;
+  auto gather = [&](uint64_t v) {
+    if (map0[(uint32_t)(v >> s0) & m0] == 255u) return;
+    const uint32_t key = (uint32_t)(v >> gshift);  // the top 22 (or all 32) key bits
+#pragma unroll
+    for (int j = 0; j < kPickRanks; ++j)
+      if (key == pre[j]) lists[j * 32 + atomicAdd(&sh_n[j], 1u)] = v;
+  };
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < kPickItems; ++i)
+      if (i * kPickThreads + tid < p.k) gather(reg[i]);
+  } else {
+    for (int i = tid; i < p.k; i += kPickThreads) gather(c[i]);
+  }
+  __syncthreads();
+  for (int j = warp; j < nr; j += kPickThreads / 32) {
+    const uint32_t cnt = sh_n[j];
+    const uint64_t x = (uint32_t)lane < cnt ? lists[j * 32 + lane] : ~0ull;
+    uint32_t below = 0;
+    for (int o = 0; o < 32; ++o) {
+      const uint64_t y = __shfl_sync(0xFFFFFFFFu, x, o);
+      below += (y < x) ? 1u : 0u;
+    }
+    if ((uint32_t)lane < cnt && below + 1u == sh_rem[j]) sh_res[j] = x;  // composites are unique
+  }
+  __syncthreads();
+  if (tid < nr) p.out[(size_t)img * p.n + tid] = (int32_t)(uint32_t)(sh_res[tid] & 0xFFFFFFFFull);
+}
 
 __global__ void __launch_bounds__(kPickThreads, 2) pick_ranks_kernel(const PickParams p) {
   extern __shared__ uint32_t sh_h[];  // [kPickRanks][2048]
@@ -714,6 +994,7 @@ __global__ void __launch_bounds__(kPickThreads, 2) pick_ranks_kernel(const PickP
   __shared__ uint32_t sh_n[kPickRanks];
   __shared__ uint32_t sh_small;
   const int img = blockIdx.x;
+  if (p.fallback && p.fallback[img] == 0u) return;  // finished by pick_ranks_fast_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t* c = p.cand + (size_t)img * p.kpad;
   // the k candidates are read ONCE into registers (all loads in flight together) and reused by every level;
@@ -1228,7 +1509,7 @@ static int select_impl(const float* score_map, int n_img, int HW, int k, int lar
     p.kpad = w.kpad;
     p.largest = largest;
     p.build_next_hist = 0;
-    pick_bucket0_kernel<<<n_img, kSelThreads, 0, st>>>(w.hist, w.state + (size_t)n_img, (uint32_t)k);
+    pick_bucket0_kernel<<<n_img, kSelThreads, 0, st>>>(w.hist, w.state + (size_t)n_img, (uint32_t)k, largest != 0);
     PP_LAUNCH_CHECK();
     const int gx = (HW + kL0Chunk - 1) / kL0Chunk;  // one chunk of scores per CTA
     const bool full = (HW % kL0Chunk == 0) && ((reinterpret_cast<uintptr_t>(score_map) & 15) == 0);
@@ -1244,6 +1525,7 @@ static int select_impl(const float* score_map, int n_img, int HW, int k, int lar
     r.state1 = w.state + (size_t)n_img;
     r.HW = HW;
     r.kpad = w.kpad;
+    r.first_level = largest ? 0 : 1;
     select_rest_kernel<<<n_img, kRestThreads, 0, st>>>(r);
     PP_LAUNCH_CHECK();
   }
@@ -1428,6 +1710,8 @@ int pp_acq_pick(void* workspace, size_t workspace_bytes, int n_img, int HW, int 
     PP_CUDA(cudaFuncSetAttribute(pick_ranks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     // two 97 KB CTAs per SM (64 registers / thread): 256 images are then ONE wave on 148 SMs instead of two
     PP_CUDA(cudaFuncSetAttribute(pick_ranks_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PP_CUDA(cudaFuncSetAttribute(pick_ranks_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PP_CUDA(cudaFuncSetAttribute(pick_ranks_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
   PickParams p;
@@ -1437,7 +1721,11 @@ int pp_acq_pick(void* workspace, size_t workspace_bytes, int n_img, int HW, int 
   p.n = n;
   p.pos = pos;
   p.out = out;
-  pick_ranks_kernel<<<n_img, kPickThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  p.fallback = w.filt_count + n_img;  // second half of the boundary-count array: free once the select has finished
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  pick_ranks_fast_kernel<<<n_img, kPickThreads, smem, st>>>(p);  // three cheap passes; flags the images it cannot finish
+  PP_LAUNCH_CHECK();
+  pick_ranks_kernel<<<n_img, kPickThreads, smem, st>>>(p);  // generic radix walk for the flagged images (heavy ties)
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

@@ -59,6 +59,31 @@ __host__ __device__ inline uint32_t ord_key(float s, bool largest) {
   return largest ? ~u : u;
 }
 
+// Level-0 bucket of the radix select: a LINEAR quantisation of the score instead of the key's leading bits.  Every
+// acquisition score lives in [0, ln C] (entropy) or [0, 1] (least confidence, margin), where the leading 11 float bits
+// resolve poorly: [0.5, 1) is only 4 buckets, so the "largest" strategies left ~25 % of an image in the boundary bucket
+// for the single-CTA radix tail.  2047 linear buckets over [0, 4) put < 1 % there (used for largest-first selections:
+// entropy, least confidence).  Any monotone map keeps the select
+// exact (ascending bucket <=> ascending ordering key, ties in a bucket are resolved on the full key afterwards); out of
+// range scores are clamped (still monotone, just coarse).  NaN: bucket 0 for largest (first), 2047 otherwise (last).
+__host__ __device__ inline uint32_t ord_key(float s, bool largest);
+__host__ __device__ inline uint32_t bucket0(float s, bool largest) {
+  // smallest-first selections (margin, random) pick values near 0, where the float's own exponent bits already spread the
+  // candidates over many buckets: keep the key's leading 11 bits there (measured: the linear map cost them 3 %)
+  if (!largest) return ord_key(s, false) >> 21;
+  if (s != s) return largest ? 0u : 2047u;
+  // round(clamp(s, 0, 4) * 511.5) read out of the mantissa after adding 2^23 (one FFMA + one mask; a float->int
+  // conversion runs on the quarter-rate pipe and the scoring kernel is close to issue-bound).  Monotone in s.
+  const float c = s < 0.f ? 0.f : (s > 4.f ? 4.f : s);
+  const float t = c * 511.5f + 8388608.0f;
+#ifdef __CUDA_ARCH__
+  const uint32_t q = __float_as_uint(t) & 0x7FFFFFu;
+#else
+  union { float f; uint32_t u; } cv; cv.f = t; const uint32_t q = cv.u & 0x7FFFFFu;
+#endif
+  return largest ? 2047u - q : q;
+}
+
 __host__ __device__ inline float ord_key_inv(uint32_t k, bool largest) {
   uint32_t u = largest ? ~k : k;
   if (u == 0xFFFFFFFFu) u = 0x7FC00000u;
