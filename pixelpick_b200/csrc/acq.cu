@@ -2,12 +2,16 @@
 //
 //   K1  acq_score_*      logits[n,C,H,W] (+masks) -> score[n,H*W] (+ level-0 radix histogram)
 //                        one coalesced, vectorised pass over the logits: HBM-bound, C*4+2 B/px.
-//   K2  select_level     MSD radix select on the 64-bit composite (ord_key(score) << 32 | flat idx):
-//                        level L partitions its input by digit L into {selected, boundary bucket}
-//                        and builds the histogram of digit L+1 over the boundary bucket, so the
-//                        score map is read exactly once after K1 and later levels touch only the
-//                        (small) boundary bucket.  Exits as soon as a bucket is wholly selected.
-//   K3  bitonic_*        sort the k selected composites (ties -> lower flat index first).
+//   K2  pick_bucket0     per image: the level-0 bucket holding the k-th score, and that bucket's ordering-key range.
+//       select_l0        ONE pass over the score map: composites (ord_key(score) << 32 | flat idx) below the bucket go
+//                        to the candidate list, those inside it to the (small) boundary list.  Level 0 is bucket0()
+//                        (pp_common.cuh): the key's leading 11 bits for smallest-first selections, a linear
+//                        quantisation of [0, 4) for largest-first ones.
+//       select_rest      MSD radix levels on the boundary list, one CTA per image, until the k-th is isolated.
+//   K3a pick_ranks_fast  the reference only reads n random RANKS of the sorted list (query.py:63-64): three
+//                        table-lookup passes over the k unsorted candidates return exactly those order statistics;
+//       pick_ranks       generic 5-level radix walk for images the fast kernel flags (> 32 exact ties).
+//   K3b bitonic_*        full sort of the k composites when the list itself is wanted (ties -> lower flat index first).
 //
 // Reference semantics restated (query.py:33-69,190-201,224-247): see include/pixelpick_b200.h.
 #include "pp_common.cuh"
@@ -424,7 +428,6 @@ struct SelParams {
   const SelState* state_cur;
   SelState* state_next;
   int level, n_img, HW, k, kpad, largest;
-  int build_next_hist;  // 0: the single-CTA tail kernel builds its own histograms (no merge atomics here)
 };
 
 // standalone level-0 histogram (used when pp_acq_score did not fuse it)
@@ -1508,7 +1511,6 @@ static int select_impl(const float* score_map, int n_img, int HW, int k, int lar
     p.k = k;
     p.kpad = w.kpad;
     p.largest = largest;
-    p.build_next_hist = 0;
     pick_bucket0_kernel<<<n_img, kSelThreads, 0, st>>>(w.hist, w.state + (size_t)n_img, (uint32_t)k, largest != 0);
     PP_LAUNCH_CHECK();
     const int gx = (HW + kL0Chunk - 1) / kL0Chunk;  // one chunk of scores per CTA
