@@ -129,8 +129,14 @@ def main():
         if s == "entropy":
             out["call_logits"], out["call_y"], out["call_lab"] = logits.numpy(), y, lab
     # ---- a full-size Cityscapes-shape image, inputs regenerated from the seed in the test -------
-    logits, y, lab = make_inputs(900, 1, 19, 256, 512)
-    out["big_logits_checksum"] = np.array([float(logits.double().sum()), float(logits.double().abs().sum())])
+    # logits from NumPy's legacy RandomState (bit-identical on every platform; torch.randn's CPU stream depends on the
+    # vectorised code path of the host, which made this case skip on some GPU boxes)
+    _, y, lab = make_inputs(900, 1, 19, 256, 512)
+    logits = torch.from_numpy((np.random.RandomState(900).standard_normal((1, 19, 256, 512)) * 3.0).astype(np.float32))
+    # exact, order-independent checksum: sums of the raw bit patterns (a float sum depends on the host's vector width)
+    bits = logits.numpy().view(np.uint32).astype(np.uint64)
+    out["big_logits_checksum"] = np.array([bits.sum(), (bits * (np.arange(bits.size, dtype=np.uint64).reshape(bits.shape) % 65521)).sum()],
+                                          dtype=np.uint64)
     for s in STRATS:
         qs = refq.QuerySelector(make_args(s, 19, 19), None, device=torch.device("cpu"))
         uc = refq.UncertaintySampler(s)(torch.softmax(logits, dim=1))[0]
