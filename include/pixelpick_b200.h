@@ -43,6 +43,12 @@ const char* pp_last_error(void);
 /* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
 long long pp_launch_count(void);
 /* number of SMs / device name of the current device: used by bench.py for the grid/roofline note */
+/* Host-side (no GPU needed) evaluation of the select's two ordering maps, exported for property tests:
+ * pp_host_ord_key  = the uint32 whose ascending order is the selection order (descending score for largest, NaN first;
+ *                    ascending score otherwise, NaN last; -0.0 == +0.0);
+ * pp_host_bucket0  = the level-0 bucket of the radix select (0..2047), monotone non-decreasing in pp_host_ord_key. */
+unsigned int pp_host_ord_key(float score, int largest);
+unsigned int pp_host_bucket0(float score, int largest);
 int pp_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
 
 /* ------------------------------------------------------------------------------------------

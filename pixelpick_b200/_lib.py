@@ -31,6 +31,8 @@ _SIGNATURES = {
     "pp_version": ([], _i),
     "pp_last_error": ([], C.c_char_p),
     "pp_launch_count": ([], C.c_longlong),
+    "pp_host_ord_key": ([_f, _i], C.c_uint),
+    "pp_host_bucket0": ([_f, _i], C.c_uint),
     "pp_device_info": ([C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.c_char_p, _i], _i),
     "pp_acq_score": ([_vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp], _i),
     "pp_acq_score_upsampled": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp], _i),

@@ -17,6 +17,10 @@ extern "C" {
 int pp_version(void) { return 100; }
 long long pp_launch_count(void) { return pp::g_launches; }
 const char* pp_last_error(void) { return pp::g_err; }
+/* host-side views of the two ordering maps of the radix select (pp_common.cuh), for the CPU property tests: the select is
+ * exact iff bucket0 is monotone in ord_key */
+unsigned int pp_host_ord_key(float score, int largest) { return pp::ord_key(score, largest != 0); }
+unsigned int pp_host_bucket0(float score, int largest) { return pp::bucket0(score, largest != 0); }
 int pp_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len) {
   int dev = 0;
   PP_CUDA(cudaGetDevice(&dev));

@@ -76,3 +76,42 @@ def test_spatial_coverage_matches_reference_formula():
     pts = np.stack([ys, xs], 1).astype(float)
     d = [np.linalg.norm(pts[i] - pts[j]) for i in range(3) for j in range(3) if i != j]
     assert abs(got - np.mean(d)) < 1e-12
+
+
+def test_select_ordering_maps_are_consistent_on_the_host():
+    """The radix select is exact iff (a) pp_host_ord_key orders scores like torch.topk (descending for `largest` with NaN
+    first, ascending otherwise with NaN last, -0.0 == +0.0) and (b) the level-0 bucket is monotone non-decreasing in that
+    key.  Both maps are host functions of the library: checked here without a GPU on specials, dense sweeps of the score
+    ranges and random bit patterns."""
+    import ctypes
+    import numpy as np
+    from pixelpick_b200 import _lib
+    lib = _lib.lib()
+    rs = np.random.RandomState(0)
+    specials = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1e-38, 3.4e38, -3.4e38, 0.5, 0.999999,
+                         2.9444, 4.0, 4.0000005, 3.9999998, 0.0019550342, 0.001955], dtype=np.float32)
+    dense = np.concatenate([np.linspace(0, 1, 4001), np.linspace(0, 3.05, 4001), np.linspace(-0.01, 4.2, 3001)]).astype(np.float32)
+    rand_bits = rs.randint(0, 2 ** 32, size=4000, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    xs = np.concatenate([specials, dense, rand_bits])
+    for largest in (0, 1):
+        key = np.array([lib.pp_host_ord_key(ctypes.c_float(float(x)), largest) for x in xs], dtype=np.uint64)
+        bkt = np.array([lib.pp_host_bucket0(ctypes.c_float(float(x)), largest) for x in xs], dtype=np.int64)
+        assert bkt.min() >= 0 and bkt.max() <= 2047
+        # (a) key order == the selection order of torch.topk / sort with NaN as the largest value
+        nan = np.isnan(xs)
+        assert len(set(key[nan])) == 1 and (key[nan][0] == (0 if largest else 2 ** 32 - 1))
+        fin = ~nan
+        order = np.argsort(key[fin], kind="stable")
+        v = xs[fin][order].astype(np.float64)
+        assert np.all(np.diff(v) <= 0) if largest else np.all(np.diff(v) >= 0)
+        z = key[(xs == 0)]
+        assert len(set(z)) == 1  # -0.0 and +0.0 share a key
+        # (b) monotone: sort by key, buckets must be non-decreasing
+        o = np.argsort(key, kind="stable")
+        assert np.all(np.diff(bkt[o]) >= 0), "bucket0 is not monotone in the ordering key"
+        # equal keys -> equal buckets
+        for k_ in np.unique(key):
+            assert len(set(bkt[key == k_])) == 1
+    # resolution where the strategies live: largest-first scores in [0.5, 1) must spread over many buckets
+    b_lo, b_hi = lib.pp_host_bucket0(ctypes.c_float(0.5), 1), lib.pp_host_bucket0(ctypes.c_float(0.999), 1)
+    assert abs(int(b_lo) - int(b_hi)) > 200
