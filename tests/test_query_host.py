@@ -115,3 +115,66 @@ def test_select_ordering_maps_are_consistent_on_the_host():
     # resolution where the strategies live: largest-first scores in [0.5, 1) must spread over many buckets
     b_lo, b_hi = lib.pp_host_bucket0(ctypes.c_float(0.5), 1), lib.pp_host_bucket0(ctypes.c_float(0.999), 1)
     assert abs(int(b_lo) - int(b_hi)) > 200
+
+
+def test_eval_loader_batching_and_voc_padding_on_the_host_path(tmp_path):
+    """eval.confusion_over_loader with a model that has no fused path (plain `model(x)["pred"]`): same-sized images are
+    micro-batched, size changes flush, the VOC branch reflect-pads to a stride multiple and crops (eval.py:49-55); counts
+    equal RunningScore.update image by image."""
+    import numpy as np
+    import torch
+    from pixelpick_b200.eval import confusion_over_loader, evaluate
+    from pixelpick_b200.utils import RunningScore
+
+    class Stub(torch.nn.Module):
+        calls = []
+
+        def forward(self, x):
+            Stub.calls.append(tuple(x.shape))
+            # 5 "classes" from simple functions of the input, defined for any (padded) size
+            return {"pred": torch.stack([x[:, 0], -x[:, 0], x[:, 1], x[:, 2], x.sum(1) * 0.3], dim=1)}
+
+    g = torch.Generator().manual_seed(0)
+    sizes = [(20, 28)] * 5 + [(17, 23)] * 2 + [(20, 28)]
+    items = [{"x": torch.randn((1, 3) + s, generator=g), "y": torch.randint(0, 6, (1,) + s, generator=g)} for s in sizes]
+
+    class DS:
+        n_classes, dataset_name = 5, "voc"
+
+    class Loader(list):
+        dataset = DS()
+
+    for name in ("cs", "voc"):
+        Stub.calls = []
+        conf = confusion_over_loader(Stub(), Loader(items), 5, torch.device("cpu"), dataset_name=name, stride_total=8, batch_imgs=4)
+        ref = RunningScore(5)
+        m = Stub()
+        for it in items:
+            ref.update(it["y"].numpy(), m(it["x"])["pred"].argmax(1).numpy())
+        assert np.array_equal(conf, ref.confusion_matrix)
+        batches = [c for c in Stub.calls if c[0] > 1 or True][:4]
+        assert [c[0] for c in Stub.calls[:4]] == [4, 1, 2, 1]  # 4 + 1 of the first size, 2 of the second, 1 again
+        if name == "voc":
+            assert Stub.calls[0][2:] == (24, 32) and Stub.calls[2][2:] == (24, 24)  # padded to multiples of 8
+    DS.dataset_name = "cs"
+    miou = evaluate(Stub(), Loader(items), "stub", epoch=3, dir_ckpt=str(tmp_path), device=torch.device("cpu"), batch_imgs=4)
+    assert 0.0 <= miou <= 1.0 and (tmp_path / "e03" / "val" / "log_val.txt").read_text().startswith("epoch,miou,pixel_acc")
+
+
+def test_train_cli_detects_human_label_files(tmp_path):
+    """train.py:199-203: earlier `*/queries.pkl` files that carry `category_id` switch the run to human labels; query files
+    written by the selector itself (no category_id) do not."""
+    import pickle
+    import numpy as np
+    from pixelpick_b200.query import gather_previous_query_files, merge_previous_query_files
+    from pixelpick_b200.train import _has_human_labels
+    own = {"a.png": {"height": 4, "width": 5, "x_coords": np.array([1, 2]), "y_coords": np.array([0, 3])}}
+    human = {"a.png": dict(own["a.png"], category_id=np.array([2, 7]))}
+    for d, q in (("0_query", own), ("1_query", human)):
+        (tmp_path / d).mkdir()
+        pickle.dump(q, open(tmp_path / d / "queries.pkl", "wb"))
+    files = sorted(gather_previous_query_files(str(tmp_path)))
+    assert [_has_human_labels(f) for f in files] == [False, True]
+    merged = merge_previous_query_files([files[1]], ignore_index=19, verbose=False)
+    assert merged["a.png"].shape == (4, 5) and merged["a.png"][0, 1] == 2 and merged["a.png"][3, 2] == 7
+    assert (merged["a.png"] != 19).sum() == 2
