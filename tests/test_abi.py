@@ -48,3 +48,26 @@ def test_product_path_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), f
+
+
+def test_every_entry_point_rejects_null_arguments_before_any_cuda_call():
+    """Each int-returning entry point, called with NULL pointers and zero sizes, returns PP_ERR_INVALID_ARG and a message
+    naming itself (or the entry point it forwards to) - no CUDA call, no crash, so it holds on a host without a GPU."""
+    l = _lib.lib()
+    skip = {"pp_device_info",            # queries the device first (PP_ERR_CUDA here)
+            "pp_acq_session_destroy"}    # destroy(NULL) is a no-op, like free(NULL)
+    checked = 0
+    for name, (argtypes, restype) in sorted(_lib._SIGNATURES.items()):
+        if restype is not ctypes.c_int or not argtypes or name in skip:
+            continue
+        args = []
+        for a in argtypes:
+            if a in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(a, type) and issubclass(a, ctypes._Pointer)):
+                args.append(None)
+            else:
+                args.append(0.0 if a is ctypes.c_float else 0)
+        assert getattr(l, name)(*args) == -1, name
+        assert l.pp_last_error().startswith(b"pp_"), (name, l.pp_last_error())
+        checked += 1
+    assert checked >= 35
+    assert l.pp_acq_session_destroy(None) == 0
