@@ -1,4 +1,5 @@
 """CPU: host-side logic of pixelpick_b200/query.py that needs no GPU (wire format, merge, RNG identity)."""
+import os
 import pickle
 from argparse import Namespace
 
@@ -178,3 +179,62 @@ def test_train_cli_detects_human_label_files(tmp_path):
     merged = merge_previous_query_files([files[1]], ignore_index=19, verbose=False)
     assert merged["a.png"].shape == (4, 5) and merged["a.png"][0, 1] == 2 and merged["a.png"][3, 2] == 7
     assert (merged["a.png"] != 19).sum() == 2
+
+
+# ---- wire format pinned to the reference: tests/golden/wire_golden.pkl from make_golden_wire.py ----
+def _wire_golden():
+    import pickle
+    return pickle.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wire_golden.pkl"), "rb"))
+
+
+def _same_tree(a, b):
+    assert type(a) is type(b), (type(a), type(b))
+    if isinstance(a, dict):
+        assert list(a.keys()) == list(b.keys())          # insertion order is part of the pickle image
+        for k in a:
+            _same_tree(a[k], b[k])
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            _same_tree(x, y)
+    elif isinstance(a, np.ndarray):
+        assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+    else:
+        assert a == b
+
+
+def test_wire_format_encode_is_byte_compatible_with_the_reference():
+    """queries.pkl written through our encode_query is the reference's file byte for byte (query.py:72-88, model.py / main_al
+    dump it with pickle) - so via/ tooling and train.py keep reading it."""
+    import pickle
+    from pixelpick_b200.query import QuerySelector
+    g = _wire_golden()
+    enc = {}
+    for p, m in zip(g["paths"], g["masks"]):
+        enc.update(QuerySelector.encode_query(p, m.shape, m))
+    _same_tree(enc, g["encoded"])
+    assert pickle.dumps(enc, protocol=4) == g["encoded_bytes"]
+
+
+def test_wire_format_decode_matches_the_reference():
+    from pixelpick_b200.query import QuerySelector
+    g = _wire_golden()
+    _same_tree(QuerySelector.decode_queries(g["encoded"]), g["decoded_list"])
+    _same_tree(QuerySelector.decode_queries(g["encoded"], return_as_dict=True), g["decoded_dict"])
+    _same_tree(QuerySelector.decode_queries({g["paths"][0]: g["encoded"][g["paths"][0]]}), g["decoded_one"])
+    _same_tree(QuerySelector.decode_queries(g["human"], ignore_index=255, return_as_dict=True), g["human_255"])
+    _same_tree(QuerySelector.decode_queries(g["human"], ignore_index=19), g["human_19"])
+
+
+def test_merge_previous_query_files_matches_the_reference(tmp_path):
+    import pickle
+    from pixelpick_b200.query import gather_previous_query_files, merge_previous_query_files
+    g = _wire_golden()
+    files = []
+    for r, d in enumerate(g["rounds"]):
+        os.makedirs(tmp_path / f"{r}_query")
+        f = str(tmp_path / f"{r}_query" / "queries.pkl")
+        pickle.dump(d, open(f, "wb"))
+        files.append(f)
+    assert sorted(gather_previous_query_files(str(tmp_path))) == sorted(files)
+    _same_tree(merge_previous_query_files(files, ignore_index=255, verbose=False), g["merged"])
