@@ -14,6 +14,8 @@ The reference (NoelShin/PixelPick @ 43c2981) is imported from /root/reference; n
                  with ignore_index 255 and 19
   merged         merge_previous_query_files (query.py:316-351) over three rounds of `*/queries.pkl` files whose
                  pixels overlap with DIFFERENT labels (later file wins), with ignore_index 255
+  stats          QueryStats.update / save (query.py:250-308) over three images: the inputs (query masks, labels, logits)
+                 and the `query_stats.pkl` dict the reference writes
 """
 import os
 import pickle
@@ -21,6 +23,7 @@ import sys
 import tempfile
 
 import numpy as np
+import torch
 
 REF = "/root/reference"
 sys.dont_write_bytecode = True
@@ -79,7 +82,25 @@ def main():
         assert sorted(found) == sorted(files)
         merged = refq.merge_previous_query_files(files, ignore_index=255, verbose=False)
 
-    out = {"paths": paths, "masks": masks, "encoded": encoded, "encoded_bytes": pickle.dumps(encoded, protocol=4),
+    # QueryStats over three images (C = 11, 24x32)
+    from argparse import Namespace
+    g = torch.Generator().manual_seed(77)
+    st_q, st_y, st_logits = [], [], []
+    with tempfile.TemporaryDirectory() as tmp:
+        qs = refq.QueryStats(Namespace(dir_root=tmp, experim_name="golden", n_classes=11))
+        for i in range(3):
+            logits = torch.randn((1, 11, 24, 32), generator=g) * 2.0
+            y = rs.randint(0, 11, size=(24, 32)).astype(np.int64)
+            qm = np.zeros(24 * 32, dtype=bool)
+            qm[rs.choice(24 * 32, 10, replace=False)] = True
+            qm = qm.reshape(24, 32)
+            qs.update(qm, y, torch.softmax(logits, dim=1))
+            st_q.append(qm), st_y.append(y), st_logits.append(logits.numpy())
+        qs.save(0)
+        st_saved = pickle.load(open(os.path.join(tmp, "checkpoints", "golden", "0_query", "query_stats.pkl"), "rb"))
+    stats = {"queries": st_q, "y": st_y, "logits": st_logits, "saved": st_saved, "list_entropy": list(qs.list_entropy)}
+
+    out = {"stats": stats, "paths": paths, "masks": masks, "encoded": encoded, "encoded_bytes": pickle.dumps(encoded, protocol=4),
            "decoded_list": decoded_list, "decoded_dict": decoded_dict, "decoded_one": decoded_one, "human": human,
            "human_255": human_255, "human_19": human_19, "rounds": rounds, "merged": merged}
     pickle.dump(out, open(OUT, "wb"), protocol=4)

@@ -238,3 +238,26 @@ def test_merge_previous_query_files_matches_the_reference(tmp_path):
         files.append(f)
     assert sorted(gather_previous_query_files(str(tmp_path))) == sorted(files)
     _same_tree(merge_previous_query_files(files, ignore_index=255, verbose=False), g["merged"])
+
+
+def test_query_stats_matches_the_reference(tmp_path, capsys):
+    """QueryStats (query.py:250-308): the reference recomputes a full entropy map per image and masks it; ours is fed the picks
+    and the entropy AT the picks (pp_acq_entropy_at on the device).  Same inputs -> the same query_stats.pkl."""
+    import pickle
+    g = _wire_golden()["stats"]
+    qs = q.QueryStats(Namespace(dir_root=str(tmp_path), experim_name="t", n_classes=11))
+    for qm, y, logits in zip(g["queries"], g["y"], g["logits"]):
+        idx = np.flatnonzero(qm)                                    # row-major ascending == np.where order
+        prob = torch.softmax(torch.from_numpy(logits), dim=1)
+        ent = (-prob * torch.log(prob)).sum(dim=1)[0].reshape(-1)[torch.from_numpy(idx)]
+        qs.update_selected(idx, qm.shape[1], y, ent.numpy())
+    qs.save(0)
+    capsys.readouterr()
+    got = pickle.load(open(tmp_path / "checkpoints" / "t" / "0_query" / "query_stats.pkl", "rb"))
+    want = g["saved"]
+    assert list(got.keys()) == list(want.keys())
+    assert got["label_distribution"] == want["label_distribution"]
+    assert got["avg_n_unique_labels"] == want["avg_n_unique_labels"]
+    assert got["avg_spatial_coverage"] == pytest.approx(want["avg_spatial_coverage"], rel=1e-12)
+    assert got["avg_entropy"] == pytest.approx(want["avg_entropy"], rel=1e-6)
+    assert np.allclose(qs.list_entropy, g["list_entropy"], rtol=1e-6, atol=0)
