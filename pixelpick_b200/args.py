@@ -34,7 +34,7 @@ class Arguments:
         p.add_argument("--max_budget", type=int, default=100)
         p.add_argument("--nth_query", type=int, default=1)
         p.add_argument("--dataset_name", type=str, default="cv", choices=["cs", "cv", "voc"])
-        p.add_argument("--dir_datasets", type=str, default="")
+        p.add_argument("--dir_datasets", type=str, default="/scratch/shared/beegfs/gyungin/datasets")
         p.add_argument("--downsample", type=int, default=4)
         p.add_argument("--use_aug", type=bool, default=True)
         p.add_argument("--use_augmented_dataset", action="store_true", default=False)
@@ -56,12 +56,20 @@ class Arguments:
         n_epochs = getattr(args, "n_epochs", None)
         if args.dataset_name == "cs":
             args.batch_size, args.ignore_index, args.n_classes = 4, 19, 19
+            args.dir_dataset = "/scratch/shared/beegfs/gyungin/datasets/cityscapes"
+            args.mean, args.std = [0.28689554, 0.32513303, 0.28389177], [0.18696375, 0.19017339, 0.18720214]
             args.optimizer_type, args.lr_scheduler_type, args.optimizer_params = "Adam", "Poly", adam
         elif args.dataset_name == "cv":
             args.batch_size, args.ignore_index, args.n_classes, args.downsample = 4, 11, 11, 1
+            args.dir_dataset = "/Users/noel/Desktop/pixelpick/pixelpick_via_launch/camvid"
+            args.mean = [0.41189489566336, 0.4251328133025, 0.4326707089857]
+            args.std = [0.27413549931506, 0.28506257482912, 0.28284674400252]
             args.optimizer_type, args.lr_scheduler_type, args.optimizer_params = "Adam", "MultiStepLR", adam
         elif args.dataset_name == "voc":
             args.batch_size, args.ignore_index, args.n_classes = 10, 255, 21
+            args.dir_dataset = "/scratch/shared/beegfs/gyungin/datasets/VOC2012"
+            args.dir_augmented_dataset = f"{args.dir_dataset}/VOCdevkit/VOC2012/train_aug"
+            args.mean, args.std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
             args.size_base, args.size_crop = 400, 320
             args.optimizer_type, args.lr_scheduler_type = "SGD", "Poly"
             args.optimizer_params = {"lr": 1e-2, "weight_decay": 1e-4, "momentum": 0.9}
@@ -72,6 +80,9 @@ class Arguments:
 
     def parse_args(self, verbose: bool = False, argv=None):
         args = self.parser.parse_args(argv)
+        aug = args.use_aug  # args.py:63-76: consumed by the dataset readers (out of scope here), kept for a plugged-in dataset
+        args.augmentations = {"geometric": {"random_scale": aug, "random_hflip": aug, "crop": aug},
+                              "photometric": {"random_color_jitter": aug, "random_grayscale": aug, "random_gaussian_blur": aug}}
         args.stride_total = 8 if args.use_dilated_resnet else 32
         if args.p_dataset_config is not None:
             import yaml

@@ -18,7 +18,7 @@ import torch.nn.functional as F
 from . import dist as ppdist
 from .loss import sparse_cross_entropy
 from .query import QuerySelector
-from .utils import AverageMeter, RunningScore, get_dataloader, get_lr_scheduler, get_model, get_optimizer, write_log
+from .utils import AverageMeter, RunningScore, get_dataloader, get_lr_scheduler, get_model, get_optimizer, optimizer_kind, write_log
 
 
 class Model:
@@ -179,7 +179,7 @@ class Model:
         model.base_seed = self.args.seed * 131 + self.nth_query + 1
         ppdist.broadcast_parameters(model)
         # whole-step CUDA graph (Adam configs, sparse labels); --no_cuda_graph or SGD / fully-supervised runs stay eager
-        self._use_graph = (getattr(self.args, "cuda_graph", True) and self.args.optimizer_type == "Adam"
+        self._use_graph = (getattr(self.args, "cuda_graph", True) and optimizer_kind(self.args) == "Adam"
                            and self.n_pixels_by_us != 0)
         self._graph, self._graph_labels = None, None
         optimizer = get_optimizer(self.args, model, capturable=self._use_graph)

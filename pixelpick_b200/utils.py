@@ -25,21 +25,31 @@ def get_model(args):
     raise NotImplementedError(f"network_name={args.network_name}: only the DeepLabv3+ hot path is implemented")
 
 
+def optimizer_kind(args) -> str:
+    """The optimizer class utils/utils.py:112-306 ends up building: `cs` is always Adam, `voc` always SGD."""
+    return {"cs": "Adam", "voc": "SGD"}.get(args.dataset_name, args.optimizer_type)
+
+
 def get_optimizer(args, model, capturable=False):
-    """utils/utils.py:112-306 for the deeplab branch: backbone lr/10, rest lr; note that the declared Adam eps/betas
-    are NOT forwarded by the reference (torch defaults apply, utils.py:141,206) — mirrored.
+    """utils/utils.py:112-306 for the deeplab branch.  Mirrored quirks: `cs` is always Adam and `voc` always SGD whatever
+    `optimizer_type` says (utils.py:114,141,208-233); the SGD groups are hard-coded (backbone 1e-3, rest 1e-2, weight decay
+    5e-4, momentum 0.9 - NOT `optimizer_params`, so VOC's declared 1e-4 never applies); Adam takes lr / weight decay from
+    `optimizer_params` with the backbone at lr/10, but its declared eps/betas are not forwarded (torch defaults apply).
     capturable: Adam with tensor learning rates, usable inside a captured CUDA graph (pixelpick_b200/graph.py)."""
-    op = args.optimizer_params
-    groups = [{"params": model.backbone.parameters(), "lr": op["lr"] / 10, "weight_decay": op["weight_decay"]}]
-    for part in (model.aspp, model.low_level_conv, model.seg_head):
-        groups.append({"params": part.parameters(), "lr": op["lr"], "weight_decay": op["weight_decay"]})
-    if args.optimizer_type == "Adam":
+    kind = optimizer_kind(args)
+    parts = (model.backbone, model.aspp, model.low_level_conv, model.seg_head)
+    if kind == "Adam":
+        op = args.optimizer_params
+        groups = [{"params": m.parameters(), "lr": op["lr"] / 10 if i == 0 else op["lr"], "weight_decay": op["weight_decay"]}
+                  for i, m in enumerate(parts)]
         if capturable:
             from .graph import make_capturable_adam
             return make_capturable_adam(groups)
         return torch.optim.Adam(groups, fused=next(model.parameters()).is_cuda)
-    if args.optimizer_type == "SGD":
-        return torch.optim.SGD(groups, momentum=op["momentum"])
+    if kind == "SGD":
+        groups = [{"params": m.parameters(), "lr": 1e-3 if i == 0 else 1e-2, "weight_decay": 5e-4, "momentum": 0.9}
+                  for i, m in enumerate(parts)]
+        return torch.optim.SGD(groups)
     raise ValueError(args.optimizer_type)
 
 
@@ -65,8 +75,8 @@ class Poly(_LRScheduler):
 
 
 def get_lr_scheduler(args, optimizer, iters_per_epoch=-1):
-    """utils/utils.py:309-335."""
-    if args.lr_scheduler_type == "MultiStepLR":
+    """utils/utils.py:309-335 (`voc` is always Poly, utils.py:323-325)."""
+    if args.lr_scheduler_type == "MultiStepLR" and args.dataset_name != "voc":
         return torch.optim.lr_scheduler.MultiStepLR(optimizer, milestones=[20, 40], gamma=0.1)
     return Poly(optimizer, args.n_epochs, iters_per_epoch)
 

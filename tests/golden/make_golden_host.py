@@ -1,0 +1,139 @@
+"""Generate golden vectors for the HOST logic around the train step by running the UNMODIFIED reference.
+
+    python tests/golden/make_golden_host.py       # needs /root/reference (build container only)
+
+The reference (NoelShin/PixelPick @ 43c2981) is imported from /root/reference; nothing is copied.  Output
+`tests/golden/host_golden.pkl`:
+
+  args        vars(Arguments().parse_args()) for cs / cv / voc and a few flag combinations (args.py:10-205).  The shipped
+              parser never registers `--p_dataset_config` although parse_args reads it (args.py:79); the reference's own
+              entry scripts add it (query.py:365), and so does this script.
+  optim       get_optimizer (utils/utils.py:112-306) on a stub DeepLab-shaped module for each dataset / optimizer type:
+              class name and per-group hyper-parameters
+  poly        the learning rates Poly (utils/lr_scheduler.py:4-21) hands out when driven the way model.py:138-139 drives
+              it (`step(epoch=epoch-1)` once per iteration), 3 epochs x 5 iterations, two parameter groups
+  multistep   the same for the MultiStepLR branch (model.py:144-145, utils.py:309-335)
+  score       RunningScore.update / get_scores (utils/metrics.py:162-207) on seeded label maps with void pixels
+  meter       AverageMeter (utils/metrics.py) running values
+"""
+import contextlib
+import io
+import os
+import pickle
+import sys
+import tempfile
+import warnings
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+import args as refargs  # noqa: E402
+import utils.metrics as refmetrics  # noqa: E402
+import utils.utils as refutils  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_golden.pkl")
+
+ARG_CASES = {
+    "cs": ["--dataset_name", "cs"],
+    "cv": ["--dataset_name", "cv"],
+    "voc": ["--dataset_name", "voc"],
+    "cs_entropy_rev": ["--dataset_name", "cs", "-qs", "entropy", "--reverse_order", "--seed", "3", "--suffix", "x"],
+    "cv_fully_sup": ["--dataset_name", "cv", "--n_pixels_by_us", "0", "--debug"],
+    "cv_top0_mc": ["--dataset_name", "cv", "--top_n_percent", "0", "--use_mc_dropout", "--vote_type", "hard"],
+}
+
+
+def stub_model():
+    m = torch.nn.Module()
+    m.backbone = torch.nn.Conv2d(3, 4, 1)
+    m.aspp = torch.nn.Conv2d(4, 4, 1)
+    m.low_level_conv = torch.nn.Conv2d(4, 2, 1)
+    m.seg_head = torch.nn.Conv2d(6, 3, 1)
+    return m
+
+
+def groups_of(opt):
+    return [{k: v for k, v in g.items() if k != "params" and isinstance(v, (int, float, bool, tuple, type(None)))}
+            for g in opt.param_groups]
+
+
+def drive(sched, opt, kind, n_epochs=3, iters=5):
+    out = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for epoch in range(1, n_epochs + 1):
+            for _ in range(iters):
+                out.append([g["lr"] for g in opt.param_groups])
+                opt.step()
+                if kind == "Poly":
+                    sched.step(epoch=epoch - 1)
+            if kind == "MultiStepLR":
+                sched.step(epoch=epoch - 1)
+    out.append([g["lr"] for g in opt.param_groups])
+    return out
+
+
+def main():
+    g = {}
+    cwd, argv0 = os.getcwd(), sys.argv
+    g["args"] = {}
+    for name, argv in ARG_CASES.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            os.chdir(tmp)
+            a = refargs.Arguments()
+            a.parser.add_argument("--p_dataset_config", "-pdc", type=str, default=None)
+            sys.argv = ["x", "--dir_root", "root"] + argv
+            with contextlib.redirect_stdout(io.StringIO()):
+                ns = a.parse_args()
+            os.chdir(cwd)
+        g["args"][name] = dict(vars(ns))
+    sys.argv = argv0
+    os.environ.pop("CUDA_VISIBLE_DEVICES", None)
+    torch.backends.cudnn.benchmark = False
+
+    g["optim"] = {}
+    for ds, types in {"cs": ["Adam"], "cv": ["Adam", "SGD"], "voc": ["SGD"]}.items():
+        for t in types:
+            ns = Namespace(**g["args"][ds])
+            ns.optimizer_type = t
+            opt = refutils.get_optimizer(ns, stub_model())
+            g["optim"][f"{ds}_{t}"] = {"cls": type(opt).__name__, "groups": groups_of(opt),
+                                       "n_params": [len(pg["params"]) for pg in opt.param_groups]}
+
+    for kind in ("Poly", "MultiStepLR"):
+        m = stub_model()
+        opt = torch.optim.SGD([{"params": m.backbone.parameters(), "lr": 1e-3}, {"params": m.aspp.parameters(), "lr": 1e-2}])
+        ns = Namespace(dataset_name="cs", lr_scheduler_type=kind, n_epochs=3)
+        sched = refutils.get_lr_scheduler(ns, opt, iters_per_epoch=5)
+        g["poly" if kind == "Poly" else "multistep"] = {"cls": type(sched).__name__, "lrs": drive(sched, opt, kind)}
+
+    rs = np.random.RandomState(5)
+    score = refmetrics.RunningScore(11)
+    batches = []
+    for _ in range(3):
+        lt = rs.randint(0, 12, size=(2, 9, 13)).astype(np.int64)   # 11 == void
+        lp = rs.randint(0, 11, size=(2, 9, 13)).astype(np.int64)
+        score.update(lt, lp)
+        batches.append((lt, lp))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        scores, cls_iu = score.get_scores()
+    g["score"] = {"batches": batches, "confusion": score.confusion_matrix.copy(), "scores": scores, "cls_iu": cls_iu}
+
+    meter = refmetrics.AverageMeter()
+    vals = []
+    for v, n in [(0.5, 1), (1.25, 4), (3.0, 2)]:
+        meter.update(v, n)
+        vals.append({k: float(getattr(meter, k)) for k in ("val", "avg", "sum", "count") if hasattr(meter, k)})
+    g["meter"] = vals
+
+    pickle.dump(g, open(OUT, "wb"), protocol=4)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()

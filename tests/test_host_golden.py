@@ -1,0 +1,136 @@
+"""CPU: host logic around the train step (args, optimizer groups, LR schedules, running metrics) against goldens produced by
+the UNMODIFIED reference - tests/golden/host_golden.pkl, written by tests/golden/make_golden_host.py."""
+import os
+import pickle
+import warnings
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+from pixelpick_b200.args import Arguments
+from pixelpick_b200.utils import AverageMeter, RunningScore, get_lr_scheduler, get_optimizer, optimizer_kind
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def g():
+    return pickle.load(open(os.path.join(HERE, "golden", "host_golden.pkl"), "rb"))
+
+
+ARG_CASES = {
+    "cs": ["--dataset_name", "cs"],
+    "cv": ["--dataset_name", "cv"],
+    "voc": ["--dataset_name", "voc"],
+    "cs_entropy_rev": ["--dataset_name", "cs", "-qs", "entropy", "--reverse_order", "--seed", "3", "--suffix", "x"],
+    "cv_fully_sup": ["--dataset_name", "cv", "--n_pixels_by_us", "0", "--debug"],
+    "cv_top0_mc": ["--dataset_name", "cv", "--top_n_percent", "0", "--use_mc_dropout", "--vote_type", "hard"],
+}
+OURS_ONLY = {"synthetic", "cuda_graph"}  # switches this framework adds (documented in README.md)
+
+
+@pytest.mark.parametrize("case", sorted(ARG_CASES))
+def test_arguments_match_the_reference(g, case, tmp_path, monkeypatch, capsys):
+    """args.py:10-205: every field the reference's parse_args produces, same name and value (incl. experim_name and the
+    checkpoint directory layout); the reference also exports CUDA_VISIBLE_DEVICES from --gpu_ids, which a one-process-per-GPU
+    launcher must not do, so that side effect is not mirrored."""
+    monkeypatch.chdir(tmp_path)
+    ours = vars(Arguments().parse_args(argv=["--dir_root", "root"] + ARG_CASES[case]))
+    capsys.readouterr()
+    want = g["args"][case]
+    assert set(want) - set(ours) == set()
+    assert set(ours) - set(want) == OURS_ONLY
+    for k, v in want.items():
+        assert ours[k] == v, (k, ours[k], v)
+    assert os.path.exists(tmp_path / "root" / "checkpoints" / want["experim_name"] / "args.txt")
+
+
+def _stub_model():
+    m = torch.nn.Module()
+    m.backbone = torch.nn.Conv2d(3, 4, 1)
+    m.aspp = torch.nn.Conv2d(4, 4, 1)
+    m.low_level_conv = torch.nn.Conv2d(4, 2, 1)
+    m.seg_head = torch.nn.Conv2d(6, 3, 1)
+    return m
+
+
+@pytest.mark.parametrize("case", ["cs_Adam", "cv_Adam", "cv_SGD", "voc_SGD"])
+def test_optimizer_groups_match_the_reference(g, case):
+    """utils/utils.py:112-306: class and per-group lr / weight decay / momentum / betas / eps - including that VOC's declared
+    weight decay (1e-4) and Adam's declared eps (1e-7) never reach the optimizer."""
+    ds, kind = case.split("_")
+    ns = Namespace(**g["args"][ds])
+    ns.optimizer_type = kind
+    want = g["optim"][case]
+    opt = get_optimizer(ns, _stub_model())
+    assert type(opt).__name__ == want["cls"] == optimizer_kind(ns)
+    assert [len(pg["params"]) for pg in opt.param_groups] == want["n_params"]
+    for got, ref in zip(opt.param_groups, want["groups"]):
+        for k in ("lr", "weight_decay", "momentum", "dampening", "nesterov", "betas", "eps", "amsgrad", "maximize"):
+            if k in ref:
+                assert got[k] == ref[k], (k, got[k], ref[k])
+
+
+def test_dataset_overrides_the_declared_optimizer_type(g):
+    """`cs` builds Adam and `voc` builds SGD whatever optimizer_type says (utils.py:114,208)."""
+    ns = Namespace(**g["args"]["cs"])
+    ns.optimizer_type = "SGD"
+    assert type(get_optimizer(ns, _stub_model())).__name__ == "Adam"
+    ns = Namespace(**g["args"]["voc"])
+    ns.optimizer_type, ns.lr_scheduler_type = "Adam", "MultiStepLR"
+    opt = get_optimizer(ns, _stub_model())
+    assert type(opt).__name__ == "SGD"
+    assert type(get_lr_scheduler(ns, opt, iters_per_epoch=5)).__name__ == "Poly"  # utils.py:323-325
+
+
+@pytest.mark.parametrize("kind,key", [("Poly", "poly"), ("MultiStepLR", "multistep")])
+def test_lr_schedule_matches_the_reference(g, kind, key):
+    """The learning rates of every iteration when the scheduler is driven as model.py:138-145 drives it."""
+    m = _stub_model()
+    opt = torch.optim.SGD([{"params": m.backbone.parameters(), "lr": 1e-3}, {"params": m.aspp.parameters(), "lr": 1e-2}])
+    sched = get_lr_scheduler(Namespace(dataset_name="cs", lr_scheduler_type=kind, n_epochs=3), opt, iters_per_epoch=5)
+    assert type(sched).__name__ == g[key]["cls"]
+    lrs = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for epoch in range(1, 4):
+            for _ in range(5):
+                lrs.append([pg["lr"] for pg in opt.param_groups])
+                opt.step()
+                if kind == "Poly":
+                    sched.step(epoch=epoch - 1)
+            if kind == "MultiStepLR":
+                sched.step(epoch=epoch - 1)
+    lrs.append([pg["lr"] for pg in opt.param_groups])
+    assert lrs == g[key]["lrs"]  # same float operations in the same order: exact
+
+
+def test_running_score_matches_the_reference(g):
+    s = g["score"]
+    rs_full, rs_pairs, rs_conf = RunningScore(11), RunningScore(11), RunningScore(11)
+    for lt, lp in s["batches"]:
+        rs_full.update(lt, lp)
+        keep = lt < 11                                   # what the train loop hands over: labelled pixels only
+        rs_pairs.update_pairs(lt[keep], lp[keep])
+        conf = np.zeros((11, 11))
+        np.add.at(conf, (lt[keep], lp[keep]), 1)         # what the device accumulator hands over
+        rs_conf.update_confusion(conf)
+    for rs in (rs_full, rs_pairs, rs_conf):
+        assert np.array_equal(rs.confusion_matrix, s["confusion"])
+        scores, cls_iu = rs.get_scores()
+        assert list(scores) == list(s["scores"])
+        for k in scores:
+            assert scores[k] == s["scores"][k], k
+        assert all(cls_iu[c] == s["cls_iu"][c] for c in range(11))
+    rs_full.reset()
+    assert rs_full.confusion_matrix.sum() == 0
+
+
+def test_average_meter_matches_the_reference(g):
+    m = AverageMeter()
+    for (v, n), want in zip([(0.5, 1), (1.25, 4), (3.0, 2)], g["meter"]):
+        m.update(v, n)
+        for k, w in want.items():
+            assert float(getattr(m, k)) == w, k
