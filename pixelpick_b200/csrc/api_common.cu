@@ -4,7 +4,7 @@
 
 namespace pp {
 static thread_local char g_err[512] = "";
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...) {
 
 extern "C" {
 int pp_version(void) { return 100; }
-long long pp_launch_count(void) { return pp::g_launches; }
+long long pp_launch_count(void) { return pp::g_launches.load(std::memory_order_relaxed); }
 const char* pp_last_error(void) { return pp::g_err; }
 /* host-side views of the two ordering maps of the radix select (pp_common.cuh), for the CPU property tests: the select is
  * exact iff bucket0 is monotone in ord_key */

@@ -5,13 +5,14 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 
 #include "../../include/pixelpick_b200.h"
 
 namespace pp {
 
 void set_error(const char* fmt, ...);
-extern long long g_launches;  // kernels launched by this library (bench.py's gpu_launches)
+extern std::atomic<long long> g_launches;  // kernels launched by this library (bench.py's gpu_launches)
 
 #define PP_CHECK_ARG(cond, ...)                 \
   do {                                          \

@@ -59,7 +59,10 @@ int pp_acq_session_create(pp_acq_session** out, int chunk_imgs, int C, int H, in
   const int64_t HW = (int64_t)H * W;
   PP_CHECK_ARG(HW <= (1 << 22) && k > 0 && k <= HW && n_sel > 0 && n_sel <= k, "pp_acq_session_create: bad k/n_sel");
   pp_acq_session* s = new (std::nothrow) pp_acq_session();
-  PP_CHECK_ARG(s, "pp_acq_session_create: out of host memory");
+  if (!s) {
+    set_error("pp_acq_session_create: out of host memory");
+    return PP_ERR_WORKSPACE;
+  }
   memset(s, 0, sizeof(*s));
   s->chunk = chunk_imgs; s->C = C; s->H = H; s->W = W; s->k = k; s->n_sel = n_sel;
   int rc = pp_acq_topk_workspace_bytes(chunk_imgs, (int)HW, k, &s->ws_bytes);
@@ -155,6 +158,7 @@ int pp_acq_session_run_host(pp_acq_session* s, const float* h_logits, const uint
                             int32_t* h_sel_idx, int32_t* h_topk_idx) {
   PP_CHECK_ARG(s && h_logits && h_sel_idx && n_img > 0, "pp_acq_session_run_host: bad args");
   PP_CHECK_ARG(strategy >= 0 && strategy <= 2, "pp_acq_session_run_host: bad strategy %d", strategy);
+  PP_CHECK_ARG(s->pending_n == 0, "pp_acq_session_run_host: a begin_host is pending on this session (finish it first)");
   const int64_t HW = (int64_t)s->H * s->W;
   const int largest = strategy == PP_STRAT_MARGIN ? 0 : 1;
   int ci = 0;
