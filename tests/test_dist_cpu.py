@@ -31,7 +31,8 @@ def _worker(rank, world, port, out):
     # per-rank shards with DIFFERENT numbers of labelled samples
     g = torch.Generator().manual_seed(1)
     X, Y = torch.randn((10, 6), generator=g), torch.randint(0, 3, (10,), generator=g)
-    lo, hi = (0, 3) if rank == 0 else (3, 10)
+    cuts = {2: [0, 3, 10], 3: [0, 1, 4, 10], 4: [0, 1, 3, 6, 10]}[world]
+    lo, hi = cuts[rank], cuts[rank + 1]
     loss = torch.nn.functional.cross_entropy(model(X[lo:hi]), Y[lo:hi])
     scale = ppdist.global_mean_loss_scale(torch.tensor(float(hi - lo)))
     (loss * scale).backward()
@@ -47,9 +48,14 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_dp_gradients_equal_single_process(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_dp_gradients_equal_single_process(tmp_path, world):
+    """world 3 / 4: 7 images do not divide evenly, so the per-rank pick lists differ in length (all_gather_rows pads)."""
     out = str(tmp_path / "r0.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     got = torch.load(out)
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
