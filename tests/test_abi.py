@@ -71,3 +71,18 @@ def test_every_entry_point_rejects_null_arguments_before_any_cuda_call():
         checked += 1
     assert checked >= 35
     assert l.pp_acq_session_destroy(None) == 0
+
+
+def test_integration_doc_covers_every_entry_point():
+    """INTEGRATION.md maps each C entry point to the reference call site it replaces (families are written `pp_x(_suffix)`
+    or `pp_x*` / `pp_x_*`)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stems = set(re.findall(r"pp_[a-z0-9_]+", doc))
+    families = [m[:-1] for m in re.findall(r"pp_[a-z0-9_]+\*", doc)]
+    for base, suf in re.findall(r"`(pp_[a-z0-9_]+)\((_[a-z0-9_]+)\)`", doc):
+        stems.add(base + suf)
+    for short in re.findall(r"`(_[a-z0-9_]+)`", doc):          # "`pp_dwconv3x3_fwd`, `_fwd_bnact`, `_dgrad`"
+        stems.update(s.rsplit("_", 1)[0] + short for s in list(stems) if s.count("_") >= 2)
+        stems.update(re.sub(r"_[a-z0-9]+$", "", s) + short for s in list(stems))
+    missing = [n for n in _header_functions() if n not in stems and not any(n.startswith(f) for f in families)]
+    assert not missing, missing
