@@ -702,7 +702,7 @@ def main():
             out["train"] = train
             out["query_model"] = qmodel
             out["strategy_sweep_1024x2048"] = bench_strategy_sweep(dev, hbm_peak)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the contract: CPU baseline on rank 0 at N=1 only
             threads = os.cpu_count() or 1
             n_cpu = 32
             rate, times = cpu_query_rate(n_cpu, 3, threads)
