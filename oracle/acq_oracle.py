@@ -7,9 +7,9 @@ Each function restates one piece of the reference `query.py` (NoelShin/PixelPick
 same torch-CPU / NumPy primitives the reference itself executes (the reference has no native code:
 its arithmetic *is* torch's CPU kernels and NumPy's legacy RandomState).
 
-Pinning: the reference ships no tests or golden vectors ("parity unpinned" by the reference itself).
-This oracle is pinned against the imported reference run in the build container — see
-`tests/golden/make_golden.py` (generator) and `tests/test_oracle_golden.py` (checker).
+Pinning: PINNED.  The reference ships no tests or golden vectors of its own, so this oracle is pinned against
+outputs of the UNMODIFIED reference imported and run in the build container: `tests/golden/make_golden.py`
+(generator, committed) -> `tests/golden/query_golden.npz` -> `tests/test_oracle_golden.py` (checker, bit-exact).
 """
 from typing import Dict, Optional
 
