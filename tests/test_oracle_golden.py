@@ -72,11 +72,6 @@ def test_query_call_end_to_end(golden, strat):
         assert np.array_equal(np.stack([info["x_coords"], info["y_coords"]]), golden[f"call_{strat}_{i}_xy"])
 
 
-def _big_inputs():
-    from tests.golden.make_golden import make_inputs  # pure helper, does not need /root/reference
-    return make_inputs(900, 1, 19, 256, 512)
-
-
 @pytest.mark.parametrize("strat", STRATS)
 def test_full_size_image(golden, strat):
     # NumPy's legacy RandomState is bit-identical on every platform (tests/golden/make_golden.py)
