@@ -61,6 +61,16 @@ def global_mean_loss_scale(n_local: torch.Tensor) -> torch.Tensor:
     return n_local.float() * world() / tot.clamp_min(1.0)
 
 
+def all_gather_objects(obj):
+    """[obj of rank 0, obj of rank 1, ...] on every rank (picklable Python objects: the per-rank pick dicts / statistics of
+    one query round, KBs).  One collective."""
+    if world() == 1:
+        return [obj]
+    out = [None] * world()
+    dist.all_gather_object(out, obj)
+    return out
+
+
 def shard_indices(n_items):
     return list(range(rank(), n_items, world()))
 

@@ -76,7 +76,8 @@ class Model:
             self.nth_query = nth_query
             model = self._train()
             queries = self.query_selector(nth_query, model)
-            self.dataloader.dataset.label_queries(queries, nth_query + 1)
+            # every rank keeps its dataset object current; only rank 0 writes {nth_query+1}_query/queries.pkl
+            self.dataloader.dataset.label_queries(queries, nth_query + 1 if ppdist.rank() == 0 else None)
             if nth_query == n_stages - 1:
                 break
 

@@ -11,7 +11,10 @@ Differences that do not change results:
   * `np.random.choice(ind, n, False)` is evaluated as `ind[np.random.permutation(len(ind))[:n]]`
     (bit-identical, incl. the RNG state afterwards) so only n positions per image leave the device;
   * `QueryStats` evaluates the entropy only at the selected pixels (reference recomputes the full map,
-    query.py:260-264).
+    query.py:260-264);
+  * under `torch.distributed` (one process per GPU) image i is scored by rank i % world; every rank still walks the
+    whole dataloader and draws every image's random numbers, so the picks are those of a single-process run, and the
+    round ends with ONE all-gather of the per-rank picks / statistics.
 Tie rule of the top-k: equal scores -> lower flat index first (CPU `torch.topk` leaves it unspecified).
 """
 import os
@@ -25,6 +28,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
+from . import dist as ppdist
 
 
 class UncertaintySampler:
@@ -67,6 +71,36 @@ class QueryStats:
         self.dir_checkpoints = f"{args.dir_root}/checkpoints/{args.experim_name}"
         self.list_entropy, self.list_n_unique_labels, self.list_spatial_coverage = list(), list(), list()
         self.dict_label_cnt = {l: 0 for l in range(args.n_classes)}
+
+    def begin_round(self):
+        """The lists are cumulative over query rounds, as in the reference (never reset): remember where this round starts."""
+        self._round_start = (len(self.list_entropy), len(self.list_n_unique_labels), dict(self.dict_label_cnt))
+
+    def round_payload(self, image_ids: List[int]):
+        """Multi-GPU: this rank's records of the current round - `image_ids` are the dataloader positions of the images it
+        updated since `begin_round`, in update order.  Travels in the round's all-gather next to the picks."""
+        e0, u0, cnt0 = self._round_start
+        ent, uniq, cov = self.list_entropy[e0:], self.list_n_unique_labels[u0:], self.list_spatial_coverage[u0:]
+        n = len(image_ids)
+        assert n == len(uniq) == len(cov) and (len(ent) % n == 0 if n else not ent)
+        per = len(ent) // n if n else 0
+        return ([(i, ent[j * per:(j + 1) * per], uniq[j], cov[j]) for j, i in enumerate(image_ids)],
+                {l: c - cnt0[l] for l, c in self.dict_label_cnt.items()})
+
+    def absorb_round(self, payloads):
+        """Replace this round's local records by every rank's, in dataloader order: `save` then writes what a single process
+        would have written."""
+        e0, u0, cnt0 = self._round_start
+        records, counts = [], dict(cnt0)
+        for recs, delta in payloads:
+            records.extend(recs)
+            for l, c in delta.items():
+                counts[l] += c
+        records.sort(key=lambda r: r[0])
+        self.list_entropy[e0:] = [e for r in records for e in r[1]]
+        self.list_n_unique_labels[u0:] = [r[2] for r in records]
+        self.list_spatial_coverage[u0:] = [r[3] for r in records]
+        self.dict_label_cnt = counts
 
     def _count_labels(self, labels):
         for l in labels:
@@ -236,13 +270,15 @@ class QuerySelector:
         void = None
         if batch[0]["y"] is not None:
             void = torch.from_numpy(np.stack([b["y"] == self.ignore_index for b in batch])).to(self.device)
-        keep_np, pos_np = self._draw_positions(n, h, w)
+        # drawn per image when the loop saw it (dataloader order, on every rank): query.py:40,64
+        keep_np = None if batch[0]["keep"] is None else np.concatenate([b["keep"] for b in batch])
+        pos_np = None if batch[0]["pos"] is None else np.concatenate([b["pos"] for b in batch])
         keep = None if keep_np is None else torch.from_numpy(keep_np).to(self.device)
         n_top = self.n_pixels_by_us if self.reverse_order else k
         largest = _lib.LARGEST[st]
         pos_t = None if pos_np is None else torch.from_numpy(pos_np)
         if st == "random":
-            uc = torch.stack([self.uncertainty_sampler(torch.empty(1, 1, h, w))[0] for _ in range(n)]).to(self.device)
+            uc = torch.stack([b["rand"] for b in batch]).to(self.device)
             excl = labelled if void is None else (labelled | void)
             if keep is not None:
                 excl = excl | ~keep.view(n, h, w)
@@ -287,26 +323,51 @@ class QuerySelector:
         dict_queries: dict = dict()
         y = None
         batch: List[dict] = []
+        world, rank = ppdist.world(), ppdist.rank()
+        order: List[str] = []      # every image path in dataloader order (all ranks walk the whole loader)
+        mine: List[int] = []       # dataloader positions of the images this rank scores
+        self.query_stats.begin_round()
         with torch.no_grad():
             for batch_ind, dict_data in enumerate(self.dataloader):
                 x = dict_data["x"]
                 y = dict_data.get("y", None)
+                h, w = tuple(x.shape[2:])
+                # the random numbers of EVERY image are drawn here, in dataloader order, on every rank (query.py:40,64 and
+                # UncertaintySampler._random): the streams, hence the picks, do not depend on the world size
+                keep, pos = self._draw_positions(1, h, w)
+                rand = self.uncertainty_sampler(torch.empty(1, 1, h, w))[0] if self.query_strategy == "random" else None
+                order.append(dict_data["p_img"][0])
+                n_imgs += 1
+                if batch_ind % world != rank:
+                    continue
                 if y is not None:
                     y = y.squeeze(dim=0).numpy()
-                item = {"x": x, "y": y, "mask": np.asarray(prev_queries[batch_ind]), "hw": tuple(x.shape[2:]),
-                        "p_img": dict_data["p_img"][0]}
+                item = {"x": x, "y": y, "mask": np.asarray(prev_queries[batch_ind]), "hw": (h, w), "p_img": order[-1],
+                        "keep": keep, "pos": pos, "rand": rand}
                 if batch and (item["hw"] != batch[0]["hw"] or len(batch) == self.batch_imgs):
                     n_pixels += self._flush(model, batch, human_labels, dict_queries, not human_labels and batch[0]["y"] is not None)
                     batch = []
                 batch.append(item)
-                n_imgs += 1
+                mine.append(batch_ind)
             if batch:
                 n_pixels += self._flush(model, batch, human_labels, dict_queries, not human_labels and batch[0]["y"] is not None)
         assert n_imgs > 0, "no queries are chosen!"
-        if not human_labels and y is not None:
-            self.query_stats.save(nth_query)
+        stats_on = not human_labels and y is not None
+        if world > 1:  # the round's ONE exchange: per-rank picks (and statistics) -> every rank, back in dataloader order
+            gathered = ppdist.all_gather_objects((dict_queries, self.query_stats.round_payload(mine) if stats_on else None))
+            merged: dict = dict()
+            for d, _ in gathered:
+                merged.update(d)
+            dict_queries = {p: merged[p] for p in order}
+            n_pixels = sum(len(info["x_coords"]) for info in dict_queries.values())
+            if stats_on:
+                self.query_stats.absorb_round([payload for _, payload in gathered])
+        if stats_on:
+            if rank == 0:
+                self.query_stats.save(nth_query)
             print(f"{n_pixels} labelled pixels  are chosen by {self.query_strategy} strategy")
-            self.dataloader.dataset.label_queries(dict_queries, nth_query)
+            # every rank merges the picks into its own dataset object; only rank 0 writes {nth_query}_query/queries.pkl
+            self.dataloader.dataset.label_queries(dict_queries, nth_query if rank == 0 else None)
         return dict_queries
 
 
