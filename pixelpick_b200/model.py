@@ -138,6 +138,9 @@ class Model:
                   f"({self.dataloader.dataset.n_pixels_total} labelled pixels)")
         model.train()
         miou = pixel_acc = float("nan")
+        sampler = getattr(self.dataloader, "sampler", None)
+        if hasattr(sampler, "set_epoch"):  # multi-GPU: per-rank shards, reshuffled every epoch
+            sampler.set_epoch(epoch + 1000 * max(self.nth_query, 0))
         it = iter(self.dataloader)
         dict_data = next(it, None)
         while dict_data is not None:

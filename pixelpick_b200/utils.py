@@ -204,5 +204,18 @@ def get_dataloader(args, batch_size, n_workers, shuffle, val=False, query=False,
                                   "or plug a dataset with the reference interface into Model(dataloaders=...)")
     n, H, W = args.synthetic
     ds = SyntheticDataset(args, n if not val else max(2, n // 4), (H, W), val=val, query=query, seed=args.seed)
+    return make_loader(ds, batch_size, n_workers, shuffle, sharded=not val and not query, seed=args.seed)
+
+
+def make_loader(ds, batch_size, n_workers, shuffle, sharded=False, seed=0):
+    """DataLoader with the reference's settings (utils/utils.py:100-108).  Under torch.distributed the TRAIN loader is sharded
+    over ranks (disjoint per-rank batches of `batch_size`, reshuffled per epoch through `sampler.set_epoch`); the query and
+    validation loaders stay whole - the selector shards the images itself and needs every rank to walk all of them."""
+    from . import dist as ppdist
+    if sharded and ppdist.world() > 1:
+        from torch.utils.data.distributed import DistributedSampler
+        sampler = DistributedSampler(ds, num_replicas=ppdist.world(), rank=ppdist.rank(), shuffle=shuffle, seed=seed)
+        per_rank = len(sampler)
+        return DataLoader(ds, batch_size=batch_size, num_workers=n_workers, sampler=sampler, drop_last=per_rank % batch_size == 1)
     return DataLoader(ds, batch_size=batch_size, num_workers=n_workers, shuffle=shuffle,
                       drop_last=len(ds) % batch_size == 1)

@@ -42,8 +42,19 @@ def _worker(rank, world, port, out):
     idx = ppdist.shard_indices(7)
     rows = torch.tensor([[i, i * 10] for i in idx])
     allrows = ppdist.all_gather_rows(rows)
+    # sharded train loader: disjoint per-rank index sets that cover the dataset, reshuffled by set_epoch
+    from pixelpick_b200.utils import make_loader
+    ds = torch.utils.data.TensorDataset(torch.arange(11))
+    dl = make_loader(ds, batch_size=1, n_workers=0, shuffle=True, sharded=True, seed=3)
+    epochs = []
+    for e in (1, 2):
+        dl.sampler.set_epoch(e)
+        epochs.append(torch.cat([b[0] for b in dl]).tolist())
+    seen = ppdist.all_gather_objects(epochs)
+    whole = make_loader(ds, batch_size=4, n_workers=0, shuffle=False, sharded=False)  # query / val loaders stay whole
+    assert torch.cat([b[0] for b in whole]).tolist() == list(range(11))
     if rank == 0:
-        torch.save({"grads": grads, "rows": allrows, "params": [p.detach().clone() for p in model.parameters()]}, out)
+        torch.save({"seen": seen, "grads": grads, "rows": allrows, "params": [p.detach().clone() for p in model.parameters()]}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -67,3 +78,10 @@ def test_dp_gradients_equal_single_process(tmp_path, world):
     ref = torch.cat([p.grad.flatten() for p in model.parameters()])
     assert torch.allclose(got["grads"], ref, atol=1e-6)
     assert np.array_equal(got["rows"].numpy(), np.array([[i, i * 10] for i in range(7)]))
+    per_rank = -(-11 // world)
+    for e in range(2):
+        shards = [got["seen"][r][e] for r in range(world)]
+        assert all(len(s) == per_rank for s in shards)                      # equal work per rank (sampler pads by wrapping)
+        assert sorted(set(sum(shards, []))) == list(range(11))               # together they cover the dataset
+        assert sum(len(set(s)) for s in shards) <= 11 + world                # overlap only from the padding
+    assert got["seen"][0][0] != got["seen"][0][1]                           # set_epoch reshuffles
