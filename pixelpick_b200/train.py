@@ -63,18 +63,16 @@ def train(args, dataloader, eval_interval: int = 0, dir_ckpt: Optional[str] = No
     model = get_model(args).to(device)
     optimizer = get_optimizer(args, model)
     lr_scheduler = get_lr_scheduler(args, optimizer=optimizer, iters_per_epoch=len(dataloader))
-    loss_tracker = AverageMeter()
-    best_miou = -1.0
+    loss_tracker, best_miou = AverageMeter(), -1.0
+    epoch_kw = dict(dir_ckpt=dir_ckpt, visualizer=visualizer, visualize_interval=visualize_interval, human_labels=human_labels,
+                    device=device, debug=debug)
     for e in range(1, 1 + n_epochs):
-        model, optimizer, lr_scheduler = train_epoch(
-            epoch=e, model=model, dataloader=dataloader, optimizer=optimizer, lr_scheduler=lr_scheduler,
-            loss_tracker=loss_tracker, experim_name=experim_name, dir_ckpt=dir_ckpt, human_labels=human_labels,
-            visualizer=visualizer, visualize_interval=visualize_interval, device=device, debug=debug)
+        model, optimizer, lr_scheduler = train_epoch(e, dataloader, model, optimizer, lr_scheduler, loss_tracker,
+                                                     experim_name, **epoch_kw)
         if eval_interval > 0 and e % eval_interval == 0:
-            eval_dataloader = get_dataloader(deepcopy(args), val=True, query=False, shuffle=False, batch_size=1,
-                                             n_workers=args.n_workers)
-            current_miou = evaluate(model=model, dataloader=eval_dataloader, experim_name=experim_name, epoch=e,
-                                    dir_ckpt=dir_ckpt, stride_total=args.stride_total, device=device, debug=debug)
+            val_loader = get_dataloader(deepcopy(args), 1, args.n_workers, False, val=True, query=False)
+            current_miou = evaluate(model, val_loader, experim_name, e, dir_ckpt=dir_ckpt, stride_total=args.stride_total,
+                                    device=device, debug=debug)
             if current_miou > best_miou and dir_ckpt is not None:  # train.py:171-172 (best_miou is never updated there)
                 torch.save({"model": model.state_dict()}, f"{dir_ckpt}/best_model.pt")
         if debug:
