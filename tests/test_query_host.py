@@ -261,3 +261,53 @@ def test_query_stats_matches_the_reference(tmp_path, capsys):
     assert got["avg_spatial_coverage"] == pytest.approx(want["avg_spatial_coverage"], rel=1e-12)
     assert got["avg_entropy"] == pytest.approx(want["avg_entropy"], rel=1e-6)
     assert np.allclose(qs.list_entropy, g["list_entropy"], rtol=1e-6, atol=0)
+
+
+def test_train_mirror_host_plumbing_with_standin_kernels(tmp_path, monkeypatch, capsys):
+    """train.py:14-176 host logic of pixelpick_b200.train (epoch loop, scheduler stepping, logs, evaluation interval, best-model
+    file) on the CPU, with the model and the sparse-CE kernel replaced by TEST-ONLY torch stand-ins (the product has no CPU path)."""
+    import torch.nn.functional as F
+    from pixelpick_b200 import train as T
+    from pixelpick_b200.args import Arguments
+    from pixelpick_b200.loss import labelled_pixel_list
+
+    class Tiny(torch.nn.Module):
+        def __init__(self, n_classes):
+            super().__init__()
+            self.backbone = torch.nn.Conv2d(3, 8, 3, stride=4, padding=1)
+            self.aspp, self.low_level_conv = torch.nn.Conv2d(8, 8, 1), torch.nn.Conv2d(8, 8, 1)
+            self.seg_head = torch.nn.Conv2d(8, n_classes, 1)
+
+        def forward_lowres(self, x):
+            return self.seg_head(self.low_level_conv(self.aspp(torch.relu(self.backbone(x)))))
+
+    def standin_ce(lowres, y, queries, ignore_index, size=None, return_pred=False, px=None, n_valid=None):
+        px = labelled_pixel_list(y, queries, ignore_index)
+        up = F.interpolate(lowres, size=tuple(y.shape[-2:]), mode="bilinear", align_corners=True)
+        at = up.permute(0, 2, 3, 1).reshape(up.shape[0], -1, up.shape[1])[px[0].long(), px[1].long()]
+        loss = F.cross_entropy(at, px[2].long())
+        return (loss, at.argmax(1).to(torch.int32), px) if return_pred else loss
+
+    evals = []
+
+    def standin_evaluate(model, dataloader, experim_name, epoch=None, dir_ckpt=None, **kw):
+        evals.append((epoch, len(dataloader), kw["stride_total"]))
+        return 0.1 * epoch
+
+    monkeypatch.setattr(T, "get_model", lambda args: Tiny(args.n_classes))
+    monkeypatch.setattr(T, "sparse_cross_entropy", standin_ce)
+    monkeypatch.setattr(T, "evaluate", standin_evaluate)
+    args = Arguments().parse_args(argv=["--dataset_name", "cs", "--dir_root", str(tmp_path), "--n_workers", "0", "--synthetic", "6", "32", "64",
+                                        "--n_epochs", "4"])
+    loader = T.get_dataloader(args, args.batch_size, 0, True)
+    ck = str(tmp_path / "ck")
+    model = T.train(args, loader, eval_interval=2, dir_ckpt=ck, device=torch.device("cpu"))
+    capsys.readouterr()
+    assert isinstance(model, Tiny)
+    assert [e[0] for e in evals] == [2, 4] and all(e[2] == 8 for e in evals)      # every eval_interval epochs, on the val loader
+    assert os.path.exists(os.path.join(ck, "best_model.pt"))
+    assert sorted(torch.load(os.path.join(ck, "best_model.pt"))["model"]) == sorted(model.state_dict())
+    for e in range(1, 5):                                                        # train.py:96-101: one log per epoch directory
+        rows = open(os.path.join(ck, f"e{e:02d}", "log_train.txt")).read().strip().splitlines()
+        assert rows[-1].split(",")[0] == str(e) and len(rows[-1].split(",")) == 4
+    assert open(os.path.join(ck, "e01", "log_train.txt")).read().startswith("epoch,miou,pixel_acc,loss")
