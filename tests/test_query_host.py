@@ -311,3 +311,30 @@ def test_train_mirror_host_plumbing_with_standin_kernels(tmp_path, monkeypatch, 
         rows = open(os.path.join(ck, f"e{e:02d}", "log_train.txt")).read().strip().splitlines()
         assert rows[-1].split(",")[0] == str(e) and len(rows[-1].split(",")) == 4
     assert open(os.path.join(ck, "e01", "log_train.txt")).read().startswith("epoch,miou,pixel_acc,loss")
+
+
+def test_labelled_pixel_lists_host_and_device_forms_agree():
+    """loss.labelled_pixel_list (torch, used by the eager step) and labelled_pixel_list_host (NumPy, feeds the captured graph's
+    fixed-capacity staging buffers) build the same (image, flat index, label) list: y != ignore_index and queries != 0
+    (model.py:108-110 + F.cross_entropy's ignore_index), row-major; the host form pads to `capacity` and refuses to overflow."""
+    from pixelpick_b200.loss import labelled_pixel_list, labelled_pixel_list_host
+    rs = np.random.RandomState(4)
+    y = torch.from_numpy(rs.randint(0, 12, size=(3, 9, 14)).astype(np.int64))       # 11 == ignore_index
+    qm = torch.from_numpy((rs.rand(3, 9, 14) < 0.2).astype(np.uint8))
+    for queries in (qm, None):
+        a = labelled_pixel_list(y, queries, 11)
+        b = labelled_pixel_list_host(y, queries, 11)
+        n = int(b[3])
+        assert n == a[0].numel() and all(t.dtype == torch.int32 for t in a + b[:3])
+        for u, v in zip(a, b[:3]):
+            assert torch.equal(u, v)
+        want = ((y != 11) & (queries.bool() if queries is not None else True)).reshape(3, -1)
+        assert n == int(want.sum())
+        flat = a[0].long() * want.shape[1] + a[1].long()
+        assert torch.equal(flat, torch.sort(flat).values) and bool(want.reshape(-1)[flat].all())
+        assert torch.equal(a[2].long(), y.reshape(-1)[flat])
+        padded = labelled_pixel_list_host(y, queries, 11, capacity=n + 7)
+        assert all(t.numel() == n + 7 for t in padded[:3]) and int(padded[3]) == n
+        assert all(torch.equal(t[:n], u) and not t[n:].any() for t, u in zip(padded[:3], a))
+        with pytest.raises(_lib.PixelPickError):
+            labelled_pixel_list_host(y, queries, 11, capacity=n - 1)
