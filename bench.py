@@ -515,6 +515,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sorted-topk", action="store_true", help="query step materialises the sorted top-k list (pp_acq_topk)")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--overlap-select", action="store_true",
+                    help="EXPERIMENTAL (written in round 1 without GPU time left to verify it; default off): run the "
+                         "latency-bound select + pick of step i on a high-priority side stream while step i+1 is scored")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -562,7 +565,39 @@ def main():
     ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
 
-    def step(i=None):
+    if args.overlap_select and not args.sorted_topk:
+        # two slots (workspace + score map); slot p's select + pick run on `side` behind an event while the main stream
+        # already scores the next batch into slot p ^ 1.  DESIGN.md §7 item 1.
+        side = torch.cuda.Stream(device=dev, priority=-1)
+        slots = [(ws, score), (_lib.TopKWorkspace(B, HW, K_TOP, dev), torch.empty_like(score))]
+        scored = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+        turn = [0]
+
+        def step(i=None):
+            p = turn[0] & 1
+            turn[0] += 1
+            ws_p, score_p = slots[p]
+            main = torch.cuda.current_stream()
+            main.wait_event(free[p])  # the select + pick that used this slot two steps ago (no-op before its first record)
+            ws_p.prepare()
+            if i is not None:
+                ev_a[i].record()
+            _lib.acq_score(logits, STRATEGY, lab, void, out=score_p, hist0_ws=ws_p)
+            if i is not None:
+                ev_b[i].record()
+            scored[p].record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(scored[p])
+                sel = _lib.acq_select_pick(score_p.view(B, HW), K_TOP, largest, pos, ws=ws_p, hist0_valid=True)
+                if world > 1 and i is not None:
+                    sel_round[i].copy_(sel)
+                free[p].record(side)
+            return sel
+    else:
+        side = None
+
+    def step_serial(i=None):
         ws.prepare()
         if i is not None:
             ev_a[i].record()
@@ -577,6 +612,9 @@ def main():
         if world > 1 and i is not None:
             sel_round[i].copy_(sel)
         return sel
+
+    if side is None:
+        step = step_serial
 
     def barrier():
         if world > 1:
@@ -594,6 +632,8 @@ def main():
     t_start.record()
     for i in range(K):
         step(i)
+    if side is not None:  # the last steps' select + pick belong to the timed region
+        torch.cuda.current_stream().wait_stream(side)
     if world > 1:  # the round's exchange, inside the timed region: per-rank picks -> every rank (rank 0 builds the dict)
         dist.all_gather(gathered, sel_round)
     t_end.record()
@@ -682,7 +722,8 @@ def main():
             "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_step_per_gpu": B, "e2e_images_per_step_per_gpu": Be,
-                       "selection": "sorted top-k list + gather" if args.sorted_topk else "radix select + order statistics at the drawn ranks (no sort; identical picks)",
+                       "selection": "sorted top-k list + gather" if args.sorted_topk else "radix select + order statistics at the drawn ranks (no sort; identical picks)"
+                                    + ("; select + pick of step i overlapped with the scoring of step i+1 (side stream)" if side is not None else ""),
                        "l2": f"inputs larger than L2 ({B * C * HW * 4 / 1e6:.0f} MB of logits per step)",
                        "parallelism": f"images sharded over {world} rank(s); one all_gather of the round's picks "
                                       f"({K} steps = one query round)" if world > 1 else "single GPU"},
