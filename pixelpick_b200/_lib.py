@@ -655,6 +655,32 @@ def to_nhwc_bf16(x_nchw, out=None, c_off=0, ld=None):
     return out
 
 
+def session_check_host_buffers(what, n, Cc, H, W, k, n_sel, logits=None, masks=(), pos=None, sel=None, topk=None):
+    """Host-buffer contract of pp_acq_session_* (include/pixelpick_b200.h): contiguous CPU tensors,
+    logits f32 [n, C, H, W]; labelled / void masks 1 byte per pixel [n, H, W]; pick positions int32 [n, n_sel] in [0, k);
+    outputs int32 [n, n_sel] (and [n, k] for the sorted list).  The library memcpy's exactly these sizes."""
+    def want(name, t, shape, dtypes):
+        if t is None:
+            return
+        if t.is_cuda or not t.is_contiguous():
+            raise PixelPickError(f"{what}: {name} must be a contiguous host tensor")
+        numel = 1
+        for d in shape:
+            numel *= d
+        if t.numel() != numel or t.shape[0] != shape[0] or t.dtype not in dtypes:  # any view of the right block is fine
+            raise PixelPickError(f"{what}: {name} is {t.dtype} {tuple(t.shape)}, expected {dtypes[0]} {tuple(shape)}")
+    if n <= 0:
+        raise PixelPickError(f"{what}: empty batch")
+    want("logits", logits, (n, Cc, H, W), (torch.float32,))
+    for name, m in zip(("labelled mask", "void mask"), masks):
+        want(name, m, (n, H, W), (torch.uint8, torch.bool))
+    want("pick positions", pos, (n, n_sel), (torch.int32,))
+    if pos is not None and pos.numel() and (int(pos.min()) < 0 or int(pos.max()) >= k):
+        raise PixelPickError(f"{what}: pick positions must lie in [0, {k})")
+    want("selected indices (output)", sel, (n, n_sel), (torch.int32,))
+    want("sorted top-k indices (output)", topk, (n, k), (torch.int32,))
+
+
 class AcqSession:
     """Host-buffer acquisition session (pp_acq_session_*): numpy / pinned-torch in, numpy out."""
 
@@ -665,12 +691,15 @@ class AcqSession:
         self.shape = (Cc, H, W)
         self.k, self.n_sel = k, n_sel
 
+    def _check(self, what, n, logits=None, masks=(), pos=None, sel=None, topk=None):
+        """The C side copies fixed-size blocks out of / into these host buffers: shapes and dtypes must be exact."""
+        Cc, H, W = self.shape
+        session_check_host_buffers(what, n, Cc, H, W, self.k, self.n_sel, logits, masks, pos, sel, topk)
+
     def run(self, h_logits, h_labelled, h_void, strategy, h_pos, h_sel, h_topk=None):
         """All arguments are CPU torch tensors (pinned for speed); h_sel (and h_topk) are outputs."""
         n = h_logits.shape[0]
-        for t in (h_logits, h_labelled, h_void, h_pos, h_sel, h_topk):
-            if t is not None and (t.is_cuda or not t.is_contiguous()):
-                raise PixelPickError("AcqSession.run wants contiguous host tensors")
+        self._check("AcqSession.run", n, h_logits, (h_labelled, h_void), h_pos, h_sel, h_topk)
         check(lib().pp_acq_session_run_host(self._h, _ptr(h_logits), _ptr(h_labelled), _ptr(h_void), n,
                                             STRATEGIES[strategy], _ptr(h_pos), _ptr(h_sel), _ptr(h_topk)),
               "pp_acq_session_run_host")
@@ -678,16 +707,14 @@ class AcqSession:
 
     def begin(self, h_logits, h_labelled, h_void, strategy):
         """asynchronous first half (H2D + scoring + radix select); draw the pick positions, then call finish()."""
-        for t in (h_logits, h_labelled, h_void):
-            if t is not None and (t.is_cuda or not t.is_contiguous()):
-                raise PixelPickError("AcqSession.begin wants contiguous host tensors")
+        self._check("AcqSession.begin", h_logits.shape[0], h_logits, (h_labelled, h_void))
         check(lib().pp_acq_session_begin_host(self._h, _ptr(h_logits), _ptr(h_labelled), _ptr(h_void), h_logits.shape[0],
                                               STRATEGIES[strategy]), "pp_acq_session_begin_host")
+        self._pending_n = h_logits.shape[0]
 
     def finish(self, h_pos, h_sel):
-        for t in (h_pos, h_sel):
-            if t is not None and (t.is_cuda or not t.is_contiguous()):
-                raise PixelPickError("AcqSession.finish wants contiguous host tensors")
+        self._check("AcqSession.finish", getattr(self, "_pending_n", None) or h_sel.shape[0], pos=h_pos, sel=h_sel)
+        self._pending_n = None
         check(lib().pp_acq_session_finish_host(self._h, _ptr(h_pos), _ptr(h_sel)), "pp_acq_session_finish_host")
         return h_sel
 

@@ -338,3 +338,25 @@ def test_labelled_pixel_lists_host_and_device_forms_agree():
         assert all(torch.equal(t[:n], u) and not t[n:].any() for t, u in zip(padded[:3], a))
         with pytest.raises(_lib.PixelPickError):
             labelled_pixel_list_host(y, queries, 11, capacity=n - 1)
+
+
+def test_session_host_buffer_contract_is_checked_before_the_library_copies():
+    """pp_acq_session_* memcpy fixed-size blocks from / to the caller's host buffers; the Python layer rejects any buffer whose
+    size, dtype or placement does not match before the call (no GPU needed for the check itself)."""
+    chk = _lib.session_check_host_buffers
+    n, C, H, W, k, ns = 3, 19, 8, 16, 6, 4
+    logits = torch.zeros((n, C, H, W))
+    m8, mb = torch.zeros((n, H, W), dtype=torch.uint8), torch.zeros((n, H * W), dtype=torch.bool)
+    pos = torch.tensor([[0, 1, 2, 5]] * n, dtype=torch.int32)
+    sel, topk = torch.zeros((n, ns), dtype=torch.int32), torch.zeros((n, k), dtype=torch.int32)
+    chk("t", n, C, H, W, k, ns, logits, (m8, mb), pos, sel, topk)                  # the accepted forms (flat mask views included)
+    chk("t", n, C, H, W, k, ns, logits, (None, None), None, sel)
+    bad = [dict(logits=logits.double()), dict(logits=logits[:, :18].contiguous()), dict(logits=logits.permute(0, 1, 3, 2)),
+           dict(masks=(m8.int(), None)), dict(masks=(m8[:, :4].contiguous(), None)), dict(pos=pos.long()),
+           dict(pos=torch.tensor([[0, 1, 2, 6]] * n, dtype=torch.int32)), dict(pos=-pos - 1), dict(sel=sel[:2]),
+           dict(sel=sel.long()), dict(topk=topk[:, :5].contiguous())]
+    for kw in bad:
+        with pytest.raises(_lib.PixelPickError):
+            chk("t", n, C, H, W, k, ns, **{**dict(logits=logits, masks=(m8, mb), pos=pos, sel=sel, topk=topk), **kw})
+    with pytest.raises(_lib.PixelPickError):
+        chk("t", 0, C, H, W, k, ns, logits[:0])
