@@ -142,6 +142,16 @@ def _mask(t, n, H, W):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _check_score_outputs(what, n, H, W, out, hist0_ws):
+    """the kernel writes n*H*W floats into `out` and n level-0 histograms into the workspace: reject anything smaller."""
+    if out is not None and (not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != n * H * W):
+        raise PixelPickError(f"{what}: out must be a contiguous CUDA float32 tensor of {n}x{H}x{W} elements, got "
+                             f"{out.dtype} {tuple(out.shape)}")
+    if hist0_ws is not None and (hist0_ws.n_img < n or hist0_ws.HW != H * W):
+        raise PixelPickError(f"{what}: workspace was sized for {hist0_ws.n_img} images of {hist0_ws.HW} pixels, "
+                             f"the batch has {n} of {H * W}")
+
+
 class TopKWorkspace:
     """Device workspace of the radix-select/sort, reusable across batches of the same shape."""
 
@@ -169,6 +179,7 @@ def acq_score(logits, strategy, labelled=None, void_mask=None, keep=None, out=No
     if logits.stride(3) != 1:
         logits = logits.contiguous()
     labelled, void_mask, keep = (_mask(m, n, H, W) for m in (labelled, void_mask, keep))
+    _check_score_outputs("acq_score", n, H, W, out, hist0_ws)
     if out is None:
         out = torch.empty((n, H, W), dtype=torch.float32, device=logits.device)
     check(lib().pp_acq_score(_ptr(logits), _dtype_code(logits), n, Cc, H, W, logits.stride(0), logits.stride(1),
@@ -186,6 +197,7 @@ def acq_score_upsampled(logits_lowres, size, strategy, labelled=None, void_mask=
     H, W = size
     logits_lowres = logits_lowres.float().contiguous()
     labelled, void_mask, keep = (_mask(m, n, H, W) for m in (labelled, void_mask, keep))
+    _check_score_outputs("acq_score_upsampled", n, H, W, out, hist0_ws)
     if out is None:
         out = torch.empty((n, H, W), dtype=torch.float32, device=logits_lowres.device)
     check(lib().pp_acq_score_upsampled(_ptr(logits_lowres), n, Cc, h, w, H, W, _ptr(labelled), _ptr(void_mask),

@@ -360,3 +360,17 @@ def test_session_host_buffer_contract_is_checked_before_the_library_copies():
             chk("t", n, C, H, W, k, ns, **{**dict(logits=logits, masks=(m8, mb), pos=pos, sel=sel, topk=topk), **kw})
     with pytest.raises(_lib.PixelPickError):
         chk("t", 0, C, H, W, k, ns, logits[:0])
+
+
+def test_score_output_and_workspace_sizes_are_checked():
+    class WS:
+        n_img, HW = 4, 32 * 48
+    ok = torch.empty((4, 32, 48), dtype=torch.float32, device="meta")  # a meta tensor: sizes without memory or a device
+    with pytest.raises(_lib.PixelPickError):   # not a CUDA tensor
+        _lib._check_score_outputs("t", 4, 32, 48, ok, None)
+    with pytest.raises(_lib.PixelPickError):   # workspace sized for fewer images
+        _lib._check_score_outputs("t", 5, 32, 48, None, WS)
+    with pytest.raises(_lib.PixelPickError):   # or for another image size
+        _lib._check_score_outputs("t", 4, 32, 64, None, WS)
+    _lib._check_score_outputs("t", 4, 32, 48, None, WS)
+    _lib._check_score_outputs("t", 3, 32, 48, None, WS)
