@@ -112,12 +112,13 @@ int pp_acq_pick(void* workspace, size_t workspace_bytes, int n_img, int HW, int 
 
 /* out[i, j] = topk_idx[i, pos[i, j]] — the device half of
  *   np.random.choice(ind_queries, n_pixels_by_us, False)                       query.py:63-64
- * (the host draws pos = np.random.permutation(k)[:n] from the global NumPy stream). */
+ * (the host draws pos = np.random.permutation(k)[:n] from the global NumPy stream).  pos lives on the device, so it
+ * cannot be validated by the call: values outside [0, k) are clamped (here and in pp_acq_pick), never read out of bounds. */
 int pp_acq_gather(const int32_t* topk_idx, int n_img, int k, const int32_t* pos, int n,
                   int32_t* out, void* stream);
 
 /* entropy of softmax(logits) at given flat pixel indices — the device half of
- * QueryStats._get_entropy (query.py:260-264), evaluated only at the selected pixels. */
+ * QueryStats._get_entropy (query.py:260-264), evaluated only at the selected pixels.  Indices outside [0, H*W) are clamped. */
 int pp_acq_entropy_at(const void* logits, int dtype, int n_img, int C, int H, int W,
                       int64_t stride_n, int64_t stride_c, int64_t stride_h,
                       const int32_t* px_idx, int n, float* out, void* stream);

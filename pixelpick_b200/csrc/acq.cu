@@ -1347,18 +1347,20 @@ __global__ void gather_kernel(const int32_t* __restrict__ topk_idx, int k, const
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int img = i / n;
-  const int ps = pos ? pos[i] : (i - img * n);
+  int ps = pos ? pos[i] : (i - img * n);
+  ps = ps < 0 ? 0 : (ps >= k ? k - 1 : ps);  // ranks outside [0, k) are clamped like in the pick kernels, never read out of bounds
   out[i] = topk_idx[(size_t)img * k + ps];
 }
 
 template <typename T>
-__global__ void entropy_at_kernel(const T* __restrict__ logits, int C, int W, int64_t sn, int64_t sc,
+__global__ void entropy_at_kernel(const T* __restrict__ logits, int C, int W, int HW, int64_t sn, int64_t sc,
                                   int64_t sh, const int32_t* __restrict__ px, int n, float* __restrict__ out,
                                   int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int img = i / n;
-  const int idx = px[i];
+  int idx = px[i];
+  idx = idx < 0 ? 0 : (idx >= HW ? HW - 1 : idx);  // a pixel index outside the image is clamped, never read out of bounds
   const int y = idx / W, x = idx - y * W;
   const T* src = logits + (int64_t)img * sn + (int64_t)y * sh + x;
   out[i] = score_runtime_c<PP_STRAT_ENTROPY>(C, [&](int c) { return Ld4<T>::ld1(src + (int64_t)c * sc); });
@@ -1370,7 +1372,8 @@ __global__ void entropy_at_up_kernel(const float* __restrict__ logits, int C, in
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int img = i / n;
-  const int idx = px[i];
+  int idx = px[i];
+  idx = idx < 0 ? 0 : (idx >= H * W ? H * W - 1 : idx);
   const int y = idx / W, x = idx - y * W;
   const Lerp ly = lerp_ac(y, h_in, H, scale_h);
   const Lerp lx = lerp_ac(x, w_in, W, scale_w);
@@ -1750,9 +1753,9 @@ int pp_acq_entropy_at(const void* logits, int dtype, int n_img, int C, int H, in
   const int total = n_img * n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == PP_F32)
-    entropy_at_kernel<float><<<(total + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float*>(logits), C, W, stride_n, stride_c, stride_h, px_idx, n, out, total);
+    entropy_at_kernel<float><<<(total + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float*>(logits), C, W, H * W, stride_n, stride_c, stride_h, px_idx, n, out, total);
   else if (dtype == PP_BF16)
-    entropy_at_kernel<__nv_bfloat16><<<(total + 127) / 128, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(logits), C, W, stride_n, stride_c, stride_h, px_idx, n, out, total);
+    entropy_at_kernel<__nv_bfloat16><<<(total + 127) / 128, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(logits), C, W, H * W, stride_n, stride_c, stride_h, px_idx, n, out, total);
   else {
     set_error("pp_acq_entropy_at: bad dtype %d", dtype);
     return PP_ERR_INVALID_ARG;
