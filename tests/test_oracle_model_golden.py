@@ -86,3 +86,17 @@ def test_train_step_loss_grads_and_running_stats(mg):
     assert np.allclose(ctx.new_stats["aspp.bn1"][0].numpy(), mg["mnv2_train_running_mean::aspp.bn1"], atol=1e-6)
     assert np.allclose(ctx.new_stats["seg_head.segment_head.1"][1].numpy(),
                        mg["mnv2_train_running_var::seg_head.segment_head.1"], atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("backbone", ["mobilenet", "resnet"])
+def test_state_dict_layout_equals_the_reference(backbone):
+    """A checkpoint of the reference (`{"model": model.state_dict()}`, model.py:207-212) loads into the drop-in with strict=True
+    and vice versa: same keys in the same order, same shapes and dtypes (tests/golden/state_dict_keys.json, written from the
+    reference modules by tests/golden/make_golden_keys.py)."""
+    import json
+    from pixelpick_b200.deeplab import DeepLab
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))[backbone]
+    sd = DeepLab(ARGS, backbone=backbone).state_dict()
+    got = [[k, list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in sd.items()]
+    assert [g[0] for g in got] == [w[0] for w in want]
+    assert got == want
