@@ -1,7 +1,6 @@
 """Host glue mirrored from the reference `utils/utils.py`, `utils/lr_scheduler.py`, `utils/metrics.py` — the parts
 the hot paths' callers need (model factory, optimiser groups, schedulers, meters, CSV log) plus a synthetic
 dataset with the reference dataset interface (no real datasets exist offline)."""
-import csv
 import os
 import pickle as pkl
 from typing import Dict, List
@@ -82,9 +81,11 @@ def get_lr_scheduler(args, optimizer, iters_per_epoch=-1):
 
 
 def write_log(fp, list_entities=None, header=None):
-    """utils/utils.py:66-72."""
+    """utils/utils.py:66-72: a header truncates the file, rows append; plain comma-joined str() values, "\n" line ends."""
     with open(fp, "w" if header is not None else "a") as f:
-        csv.writer(f).writerow(header if header is not None else list_entities)
+        for row in (header, list_entities):
+            if row is not None:
+                f.write(",".join(str(e) for e in row) + "\n")
 
 
 class AverageMeter:

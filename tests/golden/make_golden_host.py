@@ -15,6 +15,7 @@ The reference (NoelShin/PixelPick @ 43c2981) is imported from /root/reference; n
   multistep   the same for the MultiStepLR branch (model.py:144-145, utils.py:309-335)
   score       RunningScore.update / get_scores (utils/metrics.py:162-207) on seeded label maps with void pixels
   meter       AverageMeter (utils/metrics.py) running values
+  log         the bytes write_log (utils/utils.py:66-72) leaves in a file after header / rows / header+row calls
 """
 import contextlib
 import io
@@ -130,6 +131,15 @@ def main():
         meter.update(v, n)
         vals.append({k: float(getattr(meter, k)) for k in ("val", "avg", "sum", "count") if hasattr(meter, k)})
     g["meter"] = vals
+
+    with tempfile.TemporaryDirectory() as tmp:
+        fp = os.path.join(tmp, "log.txt")
+        refutils.write_log(fp, header=["epoch", "mIoU", "pixel_acc", "loss"])
+        refutils.write_log(fp, list_entities=[1, np.float64(0.25), 0.5, 1.75])
+        refutils.write_log(fp, list_entities=[2, float("nan"), np.float32(0.5), "x"])
+        a = open(fp, "rb").read()
+        refutils.write_log(fp, list_entities=[7, 8], header=["a", "b"])
+        g["log"] = {"rows": a, "header_and_row": open(fp, "rb").read()}
 
     pickle.dump(g, open(OUT, "wb"), protocol=4)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

@@ -134,3 +134,14 @@ def test_average_meter_matches_the_reference(g):
         m.update(v, n)
         for k, w in want.items():
             assert float(getattr(m, k)) == w, k
+
+
+def test_write_log_bytes_match_the_reference(g, tmp_path):
+    from pixelpick_b200.utils import write_log
+    fp = str(tmp_path / "log.txt")
+    write_log(fp, header=["epoch", "mIoU", "pixel_acc", "loss"])
+    write_log(fp, list_entities=[1, np.float64(0.25), 0.5, 1.75])
+    write_log(fp, list_entities=[2, float("nan"), np.float32(0.5), "x"])
+    assert open(fp, "rb").read() == g["log"]["rows"]
+    write_log(fp, list_entities=[7, 8], header=["a", "b"])
+    assert open(fp, "rb").read() == g["log"]["header_and_row"]
