@@ -15,6 +15,8 @@ The reference (NoelShin/PixelPick @ 43c2981) is imported from /root/reference; n
   multistep   the same for the MultiStepLR branch (model.py:144-145, utils.py:309-335)
   score       RunningScore.update / get_scores (utils/metrics.py:162-207) on seeded label maps with void pixels
   meter       AverageMeter (utils/metrics.py) running values
+  evaluate    eval.evaluate (eval.py:15-94) with a stub model over a stub 5-class validation loader: returned mIoU and the
+              bytes of e03/val/log_val.txt
   log         the bytes write_log (utils/utils.py:66-72) leaves in a file after header / rows / header+row calls
 """
 import contextlib
@@ -140,6 +142,25 @@ def main():
         a = open(fp, "rb").read()
         refutils.write_log(fp, list_entities=[7, 8], header=["a", "b"])
         g["log"] = {"rows": a, "header_and_row": open(fp, "rb").read()}
+
+    import eval as refeval  # the reference module eval.py
+
+    class Stub(torch.nn.Module):
+        def forward(self, x):
+            return {"pred": torch.stack([x[:, 0], -x[:, 0], x[:, 1], x[:, 2], x.sum(1) * 0.3], dim=1)}
+
+    class DS:
+        n_classes, dataset_name = 5, "cs"
+
+    class Loader(list):
+        dataset = DS()
+
+    gen = torch.Generator().manual_seed(0)
+    sizes = [(20, 28)] * 5 + [(17, 23)] * 2 + [(20, 28)]
+    items = [{"x": torch.randn((1, 3) + s, generator=gen), "y": torch.randint(0, 6, (1,) + s, generator=gen)} for s in sizes]
+    with tempfile.TemporaryDirectory() as tmp, contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        miou = refeval.evaluate(Stub(), Loader(items), "stub", epoch=3, dir_ckpt=tmp, device=torch.device("cpu"))
+        g["evaluate"] = {"miou": float(miou), "log": open(os.path.join(tmp, "e03", "val", "log_val.txt"), "rb").read()}
 
     pickle.dump(g, open(OUT, "wb"), protocol=4)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

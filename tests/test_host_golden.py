@@ -145,3 +145,27 @@ def test_write_log_bytes_match_the_reference(g, tmp_path):
     assert open(fp, "rb").read() == g["log"]["rows"]
     write_log(fp, list_entities=[7, 8], header=["a", "b"])
     assert open(fp, "rb").read() == g["log"]["header_and_row"]
+
+
+def test_evaluate_matches_the_reference(g, tmp_path, capsys):
+    """eval.py:15-94 on the same stub model / loader the reference was run on: identical mIoU and log_val.txt bytes, although the
+    images are micro-batched here (the stub has no fused path, so this is the plain `model(x)["pred"]` route, on the CPU)."""
+    from pixelpick_b200.eval import evaluate
+
+    class Stub(torch.nn.Module):
+        def forward(self, x):
+            return {"pred": torch.stack([x[:, 0], -x[:, 0], x[:, 1], x[:, 2], x.sum(1) * 0.3], dim=1)}
+
+    class DS:
+        n_classes, dataset_name = 5, "cs"
+
+    class Loader(list):
+        dataset = DS()
+
+    gen = torch.Generator().manual_seed(0)
+    sizes = [(20, 28)] * 5 + [(17, 23)] * 2 + [(20, 28)]
+    items = [{"x": torch.randn((1, 3) + s, generator=gen), "y": torch.randint(0, 6, (1,) + s, generator=gen)} for s in sizes]
+    miou = evaluate(Stub(), Loader(items), "stub", epoch=3, dir_ckpt=str(tmp_path), device=torch.device("cpu"), batch_imgs=4)
+    capsys.readouterr()
+    assert float(miou) == g["evaluate"]["miou"]
+    assert open(tmp_path / "e03" / "val" / "log_val.txt", "rb").read() == g["evaluate"]["log"]
