@@ -17,6 +17,10 @@ The reference (NoelShin/PixelPick @ 43c2981) is imported from /root/reference; n
   meter       AverageMeter (utils/metrics.py) running values
   evaluate    eval.evaluate (eval.py:15-94) with a stub model over a stub 5-class validation loader: returned mIoU and the
               bytes of e03/val/log_val.txt
+  train       train.train_epoch (train.py:14-103) driven for 3 epochs on the CPU over a fixed 3-batch loader with a tiny
+              DeepLab-shaped network, the reference's get_optimizer (cs: Adam) and Poly schedule: running loss after every
+              epoch, final parameters, final learning rates.  dir_ckpt=None (with a directory the reference raises
+              NameError: train.py never imports os)
   log         the bytes write_log (utils/utils.py:66-72) leaves in a file after header / rows / header+row calls
 """
 import contextlib
@@ -161,6 +165,55 @@ def main():
     with tempfile.TemporaryDirectory() as tmp, contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
         miou = refeval.evaluate(Stub(), Loader(items), "stub", epoch=3, dir_ckpt=tmp, device=torch.device("cpu"))
         g["evaluate"] = {"miou": float(miou), "log": open(os.path.join(tmp, "e03", "val", "log_val.txt"), "rb").read()}
+
+    import train as reftrain  # the reference module train.py
+    import torch.nn.functional as F
+
+    class Tiny(torch.nn.Module):
+        def __init__(self, n_classes):
+            super().__init__()
+            self.backbone = torch.nn.Conv2d(3, 8, 3, stride=4, padding=1)
+            self.aspp, self.low_level_conv = torch.nn.Conv2d(8, 8, 1), torch.nn.Conv2d(8, 8, 1)
+            self.seg_head = torch.nn.Conv2d(8, n_classes, 1)
+
+        def forward_lowres(self, x):
+            return self.seg_head(self.low_level_conv(self.aspp(torch.relu(self.backbone(x)))))
+
+        def forward(self, x):
+            return {"pred": F.interpolate(self.forward_lowres(x), size=x.shape[2:], mode="bilinear", align_corners=True)}
+
+    def train_batches():
+        gen = torch.Generator().manual_seed(42)
+        out = []
+        for _ in range(3):
+            q = torch.rand((4, 32, 64), generator=gen) < 0.01
+            out.append({"x": torch.randn((4, 3, 32, 64), generator=gen), "y": torch.randint(0, 20, (4, 32, 64), generator=gen),
+                        "queries": q.to(torch.uint8)})
+        return out
+
+    class TrainDS:
+        ignore_index, n_classes = 19, 19
+
+    class TrainLoader(list):
+        dataset = TrainDS()
+
+    torch.manual_seed(0)
+    model = Tiny(19)
+    ns = Namespace(**g["args"]["cs"])
+    ns.n_epochs = 3
+    loader = TrainLoader(train_batches())
+    opt = refutils.get_optimizer(ns, model)
+    sched = refutils.get_lr_scheduler(ns, optimizer=opt, iters_per_epoch=len(loader))
+    tracker = refmetrics.AverageMeter()
+    avg = []
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for e in range(1, 4):
+            fresh = TrainLoader([{k: v.clone() for k, v in b.items()} for b in loader])  # train_epoch overwrites y in place
+            model, opt, sched = reftrain.train_epoch(e, fresh, model, opt, sched, tracker, "golden", device=torch.device("cpu"))
+            avg.append(float(tracker.avg))
+    g["train"] = {"avg_loss": avg, "params": torch.cat([p.detach().flatten() for p in model.parameters()]).numpy(),
+                  "lrs": [pg["lr"] for pg in opt.param_groups]}
 
     pickle.dump(g, open(OUT, "wb"), protocol=4)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

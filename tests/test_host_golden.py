@@ -169,3 +169,64 @@ def test_evaluate_matches_the_reference(g, tmp_path, capsys):
     capsys.readouterr()
     assert float(miou) == g["evaluate"]["miou"]
     assert open(tmp_path / "e03" / "val" / "log_val.txt", "rb").read() == g["evaluate"]["log"]
+
+
+def test_train_epoch_trajectory_matches_the_reference(g, monkeypatch, capsys):
+    """train.py:14-103 for three epochs: the reference ran dense `F.cross_entropy(model(x)["pred"], y*, ignore_index)`; ours runs
+    the sparse labelled-pixel loss (a TEST-ONLY torch stand-in for pp_sparse_ce here) on `forward_lowres`.  Same data, same
+    initial weights, our get_optimizer / Poly: the running loss after each epoch, the final parameters and the final learning
+    rates agree (float32 round-off of a different but equivalent evaluation order)."""
+    import torch.nn.functional as F
+    from pixelpick_b200 import train as T
+    from pixelpick_b200.loss import labelled_pixel_list
+
+    class Tiny(torch.nn.Module):
+        def __init__(self, n_classes):
+            super().__init__()
+            self.backbone = torch.nn.Conv2d(3, 8, 3, stride=4, padding=1)
+            self.aspp, self.low_level_conv = torch.nn.Conv2d(8, 8, 1), torch.nn.Conv2d(8, 8, 1)
+            self.seg_head = torch.nn.Conv2d(8, n_classes, 1)
+
+        def forward_lowres(self, x):
+            return self.seg_head(self.low_level_conv(self.aspp(torch.relu(self.backbone(x)))))
+
+    def standin_ce(lowres, y, queries, ignore_index, size=None, return_pred=False, px=None, n_valid=None):
+        px = labelled_pixel_list(y, queries, ignore_index)
+        up = F.interpolate(lowres, size=tuple(y.shape[-2:]), mode="bilinear", align_corners=True)
+        at = up.permute(0, 2, 3, 1).reshape(up.shape[0], -1, up.shape[1])[px[0].long(), px[1].long()]
+        loss = F.cross_entropy(at, px[2].long())
+        return (loss, at.argmax(1).to(torch.int32), px) if return_pred else loss
+
+    gen = torch.Generator().manual_seed(42)
+    batches = []
+    for _ in range(3):
+        q = torch.rand((4, 32, 64), generator=gen) < 0.01
+        batches.append({"x": torch.randn((4, 3, 32, 64), generator=gen), "y": torch.randint(0, 20, (4, 32, 64), generator=gen),
+                        "queries": q.to(torch.uint8)})
+
+    class DS:
+        ignore_index, n_classes = 19, 19
+
+    class Loader(list):
+        dataset = DS()
+
+    monkeypatch.setattr(T, "sparse_cross_entropy", standin_ce)
+    torch.manual_seed(0)
+    model = Tiny(19)
+    ns = Namespace(**g["args"]["cs"])
+    ns.n_epochs = 3
+    loader = Loader(batches)
+    opt = get_optimizer(ns, model)
+    sched = get_lr_scheduler(ns, optimizer=opt, iters_per_epoch=len(loader))
+    tracker, avg = AverageMeter(), []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for e in range(1, 4):
+            model, opt, sched = T.train_epoch(e, loader, model, opt, sched, tracker, "golden", device=torch.device("cpu"))
+            avg.append(float(tracker.avg))
+    capsys.readouterr()
+    want = g["train"]
+    assert np.allclose(avg, want["avg_loss"], rtol=1e-5, atol=0)
+    got = torch.cat([p.detach().flatten() for p in model.parameters()]).numpy()
+    assert np.allclose(got, want["params"], rtol=1e-3, atol=2e-5)
+    assert [pg["lr"] for pg in opt.param_groups] == want["lrs"]
