@@ -21,6 +21,9 @@ The reference (NoelShin/PixelPick @ 43c2981) is imported from /root/reference; n
               DeepLab-shaped network, the reference's get_optimizer (cs: Adam) and Poly schedule: running loss after every
               epoch, final parameters, final learning rates.  dir_ckpt=None (with a directory the reference raises
               NameError: train.py never imports os)
+  model_epoch Model._train_epoch (model.py:93-159) on a bare Model object (no datasets / visualiser: `object.__new__`, only the
+              attributes the method reads) for cs (Adam + Poly, stepped per iteration) and cv (Adam + MultiStepLR, stepped per
+              epoch): the bytes of log_train.txt after 3 epochs and the final parameters
   log         the bytes write_log (utils/utils.py:66-72) leaves in a file after header / rows / header+row calls
 """
 import contextlib
@@ -214,6 +217,46 @@ def main():
             avg.append(float(tracker.avg))
     g["train"] = {"avg_loss": avg, "params": torch.cat([p.detach().flatten() for p in model.parameters()]).numpy(),
                   "lrs": [pg["lr"] for pg in opt.param_groups]}
+
+    import model as refmodel  # the reference module model.py
+    g["model_epoch"] = {}
+    for ds in ("cs", "cv"):
+        ns = Namespace(**g["args"][ds])
+        ns.n_epochs = 3
+        nc = ns.n_classes
+        gen = torch.Generator().manual_seed(7)
+        batches = []
+        for _ in range(3):
+            q = torch.rand((4, 32, 64), generator=gen) < 0.01
+            batches.append({"x": torch.randn((4, 3, 32, 64), generator=gen), "y": torch.randint(0, nc + 1, (4, 32, 64), generator=gen),
+                            "queries": q.to(torch.uint8)})
+
+        class EpochDS:
+            n_pixels_total = 0
+
+        class EpochLoader(list):
+            dataset = EpochDS()
+
+        torch.manual_seed(0)
+        net = Tiny(nc)
+        with tempfile.TemporaryDirectory() as tmp:
+            m = object.__new__(refmodel.Model)
+            m.n_pixels_by_us, m.nth_query, m.dir_checkpoints, m.experim_name = 10, 0, tmp, "golden"
+            m.device, m.ignore_index, m.debug, m.lr_scheduler_type = torch.device("cpu"), ns.ignore_index, False, ns.lr_scheduler_type
+            m.running_loss, m.running_score = refmetrics.AverageMeter(), refmetrics.RunningScore(nc)
+            m.vis = lambda dict_tensors, fp=None: None
+            m.log_train = os.path.join(tmp, "log_train.txt")
+            refutils.write_log(m.log_train, header=["epoch", "mIoU", "pixel_acc", "loss"])
+            opt = refutils.get_optimizer(ns, net)
+            sched = refutils.get_lr_scheduler(ns, optimizer=opt, iters_per_epoch=3)
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                for e in range(1, 4):
+                    m.dataloader = EpochLoader([{k: v.clone() for k, v in b.items()} for b in batches])
+                    net, opt, sched = m._train_epoch(e, net, opt, sched)
+            g["model_epoch"][ds] = {"log": open(m.log_train, "rb").read(),
+                                    "params": torch.cat([p.detach().flatten() for p in net.parameters()]).numpy(),
+                                    "lrs": [pg["lr"] for pg in opt.param_groups]}
 
     pickle.dump(g, open(OUT, "wb"), protocol=4)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

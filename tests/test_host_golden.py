@@ -230,3 +230,79 @@ def test_train_epoch_trajectory_matches_the_reference(g, monkeypatch, capsys):
     got = torch.cat([p.detach().flatten() for p in model.parameters()]).numpy()
     assert np.allclose(got, want["params"], rtol=1e-3, atol=2e-5)
     assert [pg["lr"] for pg in opt.param_groups] == want["lrs"]
+
+
+@pytest.mark.parametrize("ds", ["cs", "cv"])
+def test_model_train_epoch_log_matches_the_reference(g, ds, tmp_path, monkeypatch, capsys):
+    """model.py:93-159 for three epochs on a bare Model object (eager step, TEST-ONLY torch stand-in for pp_sparse_ce):
+    log_train.txt - epoch, running mIoU / pixel accuracy of the labelled pixels, running loss, meters reset per epoch - and the
+    final parameters / learning rates equal the reference's, for the per-iteration Poly schedule (cs) and the per-epoch
+    MultiStepLR (cv)."""
+    import torch.nn.functional as F
+    from pixelpick_b200 import model as M
+    from pixelpick_b200.loss import labelled_pixel_list
+    from pixelpick_b200.utils import write_log
+
+    class Tiny(torch.nn.Module):
+        def __init__(self, n_classes):
+            super().__init__()
+            self.backbone = torch.nn.Conv2d(3, 8, 3, stride=4, padding=1)
+            self.aspp, self.low_level_conv = torch.nn.Conv2d(8, 8, 1), torch.nn.Conv2d(8, 8, 1)
+            self.seg_head = torch.nn.Conv2d(8, n_classes, 1)
+
+        def forward_lowres(self, x):
+            return self.seg_head(self.low_level_conv(self.aspp(torch.relu(self.backbone(x)))))
+
+    def standin_ce(lowres, y, queries, ignore_index, size=None, return_pred=False, px=None, n_valid=None):
+        px = labelled_pixel_list(y, queries, ignore_index)
+        up = F.interpolate(lowres, size=tuple(y.shape[-2:]), mode="bilinear", align_corners=True)
+        at = up.permute(0, 2, 3, 1).reshape(up.shape[0], -1, up.shape[1])[px[0].long(), px[1].long()]
+        loss = F.cross_entropy(at, px[2].long())
+        return (loss, at.argmax(1).to(torch.int32), px) if return_pred else loss
+
+    monkeypatch.setattr(M, "sparse_cross_entropy", standin_ce)
+    ns = Namespace(**g["args"][ds])
+    ns.n_epochs = 3
+    nc = ns.n_classes
+    gen = torch.Generator().manual_seed(7)
+    batches = []
+    for _ in range(3):
+        q = torch.rand((4, 32, 64), generator=gen) < 0.01
+        batches.append({"x": torch.randn((4, 3, 32, 64), generator=gen), "y": torch.randint(0, nc + 1, (4, 32, 64), generator=gen),
+                        "queries": q.to(torch.uint8)})
+
+    class DS:
+        n_pixels_total = 0
+
+    class Loader(list):
+        dataset = DS()
+
+    torch.manual_seed(0)
+    net = Tiny(nc)
+    m = object.__new__(M.Model)
+    m.n_pixels_by_us, m.nth_query, m.dir_checkpoints, m.experim_name = 10, 0, str(tmp_path), "golden"
+    m.device, m.ignore_index, m.debug, m.lr_scheduler_type = torch.device("cpu"), ns.ignore_index, False, ns.lr_scheduler_type
+    m.running_loss, m.running_score = AverageMeter(), RunningScore(nc)
+    m._use_graph, m._graph, m._graph_labels, m._graph_shape = False, None, None, None
+    m.dataloader = Loader(batches)
+    m.log_train = str(tmp_path / "log_train.txt")
+    write_log(m.log_train, header=["epoch", "mIoU", "pixel_acc", "loss"])
+    opt = get_optimizer(ns, net)
+    sched = get_lr_scheduler(ns, optimizer=opt, iters_per_epoch=3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for e in range(1, 4):
+            net, opt, sched = m._train_epoch(e, net, opt, sched)
+    capsys.readouterr()
+    want = g["model_epoch"][ds]
+    got_rows = open(m.log_train).read().splitlines()
+    want_rows = want["log"].decode().splitlines()
+    assert got_rows[0] == want_rows[0] and len(got_rows) == len(want_rows) == 4
+    for a, b in zip(got_rows[1:], want_rows[1:]):
+        a, b = a.split(","), b.split(",")
+        assert a[0] == b[0]
+        assert float(a[1]) == pytest.approx(float(b[1]), rel=1e-12) and float(a[2]) == pytest.approx(float(b[2]), rel=1e-12)
+        assert float(a[3]) == pytest.approx(float(b[3]), rel=1e-5)
+    got = torch.cat([p.detach().flatten() for p in net.parameters()]).numpy()
+    assert np.allclose(got, want["params"], rtol=1e-3, atol=2e-5)
+    assert [pg["lr"] for pg in opt.param_groups] == want["lrs"]
