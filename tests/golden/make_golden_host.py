@@ -24,6 +24,8 @@ The reference (NoelShin/PixelPick @ 43c2981) is imported from /root/reference; n
   model_epoch Model._train_epoch (model.py:93-159) on a bare Model object (no datasets / visualiser: `object.__new__`, only the
               attributes the method reads) for cs (Adam + Poly, stepped per iteration) and cv (Adam + MultiStepLR, stepped per
               epoch): the bytes of log_train.txt after 3 epochs and the final parameters
+  model_val   Model._val (model.py:177-239) on a bare Model object, four epochs with stub models of varying quality: the bytes
+              of log_val.txt and the epochs at which best_miou_model.pt was rewritten
   log         the bytes write_log (utils/utils.py:66-72) leaves in a file after header / rows / header+row calls
 """
 import contextlib
@@ -257,6 +259,46 @@ def main():
             g["model_epoch"][ds] = {"log": open(m.log_train, "rb").read(),
                                     "params": torch.cat([p.detach().flatten() for p in net.parameters()]).numpy(),
                                     "lrs": [pg["lr"] for pg in opt.param_groups]}
+
+    class ValStub(torch.nn.Module):
+        def __init__(self, noise):
+            super().__init__()
+            self.noise = torch.nn.Parameter(torch.tensor(float(noise)), requires_grad=False)
+
+        def forward(self, x):  # channel c of x carries a one-hot of the true class; `noise` degrades the prediction
+            return {"pred": x + self.noise * torch.roll(x, 1, dims=1) * 2.0}
+
+    gen = torch.Generator().manual_seed(3)
+    val_items = []
+    for _ in range(4):
+        y = torch.randint(0, 6, (1, 12, 16), generator=gen)           # 5 == void
+        x = torch.nn.functional.one_hot(y.clamp(max=4), 5).permute(0, 3, 1, 2).float() + 0.1 * torch.randn((1, 5, 12, 16), generator=gen)
+        val_items.append({"x": x, "y": y})
+
+    class ValLoader(list):
+        dataset = None
+
+    with tempfile.TemporaryDirectory() as tmp:
+        m = object.__new__(refmodel.Model)
+        m.n_pixels_by_us, m.nth_query, m.dir_checkpoints, m.experim_name = 10, 2, tmp, "golden"
+        m.device, m.dataset_name, m.stride_total, m.debug, m.best_miou = torch.device("cpu"), "cs", 8, False, -1.0
+        m.running_loss, m.running_score = refmetrics.AverageMeter(), refmetrics.RunningScore(5)
+        m.vis = lambda dict_tensors, fp=None: None
+        m.dataloader_val = ValLoader(val_items)
+        os.makedirs(os.path.join(tmp, "2_query"))
+        m.log_val = os.path.join(tmp, "2_query", "log_val.txt")
+        refutils.write_log(m.log_val, header=["epoch", "mIoU", "pixel_acc"])
+        saved = []
+        ck = os.path.join(tmp, "2_query", "best_miou_model.pt")
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            for e, noise in ((1, 0.5), (2, 1.0), (3, 0.47), (4, 0.49)):
+                before = os.path.getmtime(ck) if os.path.exists(ck) else None
+                if os.path.exists(ck):
+                    os.remove(ck)
+                m._val(e, ValStub(noise))
+                if os.path.exists(ck):
+                    saved.append(e)
+        g["model_val"] = {"log": open(m.log_val, "rb").read(), "saved_at": saved, "best": float(m.best_miou)}
 
     pickle.dump(g, open(OUT, "wb"), protocol=4)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

@@ -306,3 +306,48 @@ def test_model_train_epoch_log_matches_the_reference(g, ds, tmp_path, monkeypatc
     got = torch.cat([p.detach().flatten() for p in net.parameters()]).numpy()
     assert np.allclose(got, want["params"], rtol=1e-3, atol=2e-5)
     assert [pg["lr"] for pg in opt.param_groups] == want["lrs"]
+
+
+def test_model_val_log_and_best_checkpoint_match_the_reference(g, tmp_path, capsys):
+    """model.py:177-239 on a bare Model object over four epochs with stub models of varying quality: log_val.txt bytes and the
+    epochs at which best_miou_model.pt is rewritten (only on a strict improvement) equal the reference's."""
+    from pixelpick_b200 import model as M
+    from pixelpick_b200.utils import write_log
+
+    class ValStub(torch.nn.Module):
+        def __init__(self, noise):
+            super().__init__()
+            self.noise = torch.nn.Parameter(torch.tensor(float(noise)), requires_grad=False)
+
+        def forward(self, x):
+            return {"pred": x + self.noise * torch.roll(x, 1, dims=1) * 2.0}
+
+    gen = torch.Generator().manual_seed(3)
+    items = []
+    for _ in range(4):
+        y = torch.randint(0, 6, (1, 12, 16), generator=gen)
+        x = torch.nn.functional.one_hot(y.clamp(max=4), 5).permute(0, 3, 1, 2).float() + 0.1 * torch.randn((1, 5, 12, 16), generator=gen)
+        items.append({"x": x, "y": y})
+
+    class Loader(list):
+        dataset = None
+
+    m = object.__new__(M.Model)
+    m.n_pixels_by_us, m.nth_query, m.dir_checkpoints, m.experim_name = 10, 2, str(tmp_path), "golden"
+    m.device, m.dataset_name, m.stride_total, m.debug, m.best_miou, m.n_classes = torch.device("cpu"), "cs", 8, False, -1.0, 5
+    m.running_loss, m.running_score = AverageMeter(), RunningScore(5)
+    m.dataloader_val = Loader(items)
+    os.makedirs(tmp_path / "2_query")
+    m.log_val = str(tmp_path / "2_query" / "log_val.txt")
+    write_log(m.log_val, header=["epoch", "mIoU", "pixel_acc"])
+    ck, saved = tmp_path / "2_query" / "best_miou_model.pt", []
+    for e, noise in ((1, 0.5), (2, 1.0), (3, 0.47), (4, 0.49)):
+        if ck.exists():
+            ck.unlink()
+        m._val(e, ValStub(noise))
+        if ck.exists():
+            saved.append(e)
+    capsys.readouterr()
+    want = g["model_val"]
+    assert open(m.log_val, "rb").read() == want["log"]
+    assert saved == want["saved_at"] and float(m.best_miou) == want["best"]
