@@ -14,6 +14,10 @@ The reference (NoelShin/PixelPick @ 43c2981) is imported from /root/reference; n
                  with ignore_index 255 and 19
   merged         merge_previous_query_files (query.py:316-351) over three rounds of `*/queries.pkl` files whose
                  pixels overlap with DIFFERENT labels (later file wins), with ignore_index 255
+  human_call     QuerySelector.__call__(nth_query, model, human_labels=True) (query.py:144-222) on the inputs of
+                 query_golden.npz's `call_*` case: the masks are `dataset.list_labelled_queries` (int64 label maps, ignore_index
+                 where unlabelled), no statistics are written and label_queries is not called; picks per image for
+                 margin_sampling and entropy under np.random.seed(0)
   stats          QueryStats.update / save (query.py:250-308) over three images: the inputs (query masks, labels, logits)
                  and the `query_stats.pkl` dict the reference writes
 """
@@ -100,7 +104,44 @@ def main():
         st_saved = pickle.load(open(os.path.join(tmp, "checkpoints", "golden", "0_query", "query_stats.pkl"), "rb"))
     stats = {"queries": st_q, "y": st_y, "logits": st_logits, "saved": st_saved, "list_entropy": list(qs.list_entropy)}
 
-    out = {"stats": stats, "paths": paths, "masks": masks, "encoded": encoded, "encoded_bytes": pickle.dumps(encoded, protocol=4),
+    # QuerySelector.__call__ with human labels, on the call_* inputs of query_golden.npz
+    qg = np.load(os.path.join(os.path.dirname(OUT), "query_golden.npz"))
+    c_logits, c_y, c_lab = torch.from_numpy(qg["call_logits"]), qg["call_y"], qg["call_lab"]
+
+    class HumanDS:
+        list_labelled_queries = [np.where(c_lab[i], c_y[i], 19).astype(np.int64) for i in range(3)]
+        called = False
+
+        def label_queries(self, *a, **k):
+            HumanDS.called = True
+
+    class HumanLoader:
+        dataset = HumanDS()
+
+        def __iter__(self):
+            for i in range(3):
+                yield {"x": c_logits[i:i + 1], "y": torch.from_numpy(c_y[i:i + 1]), "p_img": [f"img_{i:04d}.png"]}
+
+    class PredIsInput:
+        def eval(self):
+            return self
+
+        def __call__(self, x):
+            return {"pred": x}
+
+    human_call = {}
+    for strat in ("margin_sampling", "entropy"):
+        with tempfile.TemporaryDirectory() as tmp:
+            a = Namespace(dataset_name="cs", debug=False, dir_root=tmp, experim_name="golden", ignore_index=19, mc_n_steps=20,
+                          n_classes=19, n_pixels_by_us=10, network_name="deeplab", query_strategy=strat, reverse_order=False,
+                          stride_total=8, top_n_percent=0.05, use_mc_dropout=False, vote_type="soft")
+            sel = refq.QuerySelector(a, HumanLoader(), device=torch.device("cpu"))
+            np.random.seed(0)
+            d = sel(1, PredIsInput(), human_labels=True)
+            assert not HumanDS.called and not os.path.exists(os.path.join(tmp, "checkpoints"))
+        human_call[strat] = [np.stack([d[f"img_{i:04d}.png"]["x_coords"], d[f"img_{i:04d}.png"]["y_coords"]]) for i in range(3)]
+
+    out = {"human_call": human_call, "stats": stats, "paths": paths, "masks": masks, "encoded": encoded, "encoded_bytes": pickle.dumps(encoded, protocol=4),
            "decoded_list": decoded_list, "decoded_dict": decoded_dict, "decoded_one": decoded_one, "human": human,
            "human_255": human_255, "human_19": human_19, "rounds": rounds, "merged": merged}
     pickle.dump(out, open(OUT, "wb"), protocol=4)

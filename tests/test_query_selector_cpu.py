@@ -255,3 +255,35 @@ def test_sharded_query_equals_single_process(tmp_path, strat, kw):
             for k in ("avg_entropy", "avg_n_unique_labels", "avg_spatial_coverage"):
                 # same lists in the same order: exact (the random strategy has no logits to take an entropy from: NaN)
                 assert a[k] == b[k] or (np.isnan(a[k]) and np.isnan(b[k])), (world, r, k)
+
+
+@pytest.mark.parametrize("strat", ["margin_sampling", "entropy"])
+def test_call_with_human_labels_matches_reference_golden(golden, tmp_path, standins, capsys, strat):
+    """query.py:144-222 with human_labels=True: the exclusion masks come from `dataset.list_labelled_queries` (label maps,
+    ignore_index where unlabelled); no statistics file, no label_queries call; picks equal the reference's (wire_golden.pkl)."""
+    q = standins()
+    want = pickle.load(open(os.path.join(ROOT, "tests", "golden", "wire_golden.pkl"), "rb"))["human_call"][strat]
+    logits, y, lab = torch.from_numpy(golden["call_logits"]), golden["call_y"], golden["call_lab"]
+
+    class DS:
+        list_labelled_queries = [np.where(lab[i], y[i], 19).astype(np.int64) for i in range(3)]
+        called = False
+
+        def label_queries(self, *a, **k):
+            DS.called = True
+
+    class Loader:
+        dataset = DS()
+
+        def __iter__(self):
+            for i in range(3):
+                yield {"x": logits[i:i + 1], "y": torch.from_numpy(y[i:i + 1]), "p_img": [f"img_{i:04d}.png"]}
+
+    qs = make_selector(q, make_args(strat, 19, 19, str(tmp_path)), Loader(), 2)
+    np.random.seed(0)
+    d = qs(1, StubModel(), human_labels=True)
+    capsys.readouterr()
+    assert not DS.called and not (tmp_path / "checkpoints").exists()
+    for i in range(3):
+        info = d[f"img_{i:04d}.png"]
+        assert np.array_equal(np.stack([info["x_coords"], info["y_coords"]]), want[i])
