@@ -309,6 +309,8 @@ class _ASPPModule(nn.Module):
         self.atrous_conv = nn.Conv2d(inplanes, planes, kernel_size, 1, padding, dilation, bias=False)
         self.bn = nn.BatchNorm2d(planes)
         self.relu = nn.ReLU()
+        _init_head(self)  # aspp.py:14: each branch initialises itself, then ASPP re-initialises everything (aspp.py:62) -
+        # drawn twice, so that a seeded construction consumes the RNG exactly like the reference
 
 
 class ASPP(nn.Module):
@@ -644,8 +646,7 @@ class DeepLab(nn.Module):
         self.aspp = ASPP(backbone, output_stride)
         self.low_level_conv = nn.Sequential(nn.Conv2d(self.backbone.low_channels, 48, 1, bias=False), nn.BatchNorm2d(48),
                                             nn.ReLU())
-        self.seg_head = SegmentHead(args)
-        _init_head(self.low_level_conv)
+        self.seg_head = SegmentHead(args)  # low_level_conv keeps nn.Conv2d's default initialisation (deeplab.py:23-26)
         self.return_features = False
         self.return_attention = False
         self._rng_step = None  # device int64 [1]: dropout step counter (device-side so CUDA-graph replays advance it)

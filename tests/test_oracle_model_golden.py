@@ -100,3 +100,29 @@ def test_state_dict_layout_equals_the_reference(backbone):
     got = [[k, list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in sd.items()]
     assert [g[0] for g in got] == [w[0] for w in want]
     assert got == want
+
+
+def test_seeded_construction_starts_from_the_reference_weights():
+    """DeepLab(args) built right after torch.manual_seed(0) holds, bit for bit, the tensors the reference's DeepLab holds after
+    the same seed (aspp.py:14,62 draws every ASPP branch twice; deeplab.py:23-26 leaves low_level_conv at nn.Conv2d's default):
+    a seeded run of the drop-in starts where the reference starts.  Exact checksums of the raw bit patterns from
+    tests/golden/make_golden_keys.py; skipped where this host's torch CPU normal stream differs from the generating host's."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from pixelpick_b200.deeplab import DeepLab
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))
+
+    def bits_checksum(t):
+        a = t.detach().contiguous().cpu().numpy()
+        a = a.view(np.uint32) if a.dtype == np.float32 else a.astype(np.int64).view(np.uint64)
+        return int(a.astype(np.uint64).sum() % (1 << 63))
+
+    torch.manual_seed(123)
+    w = torch.empty(64, 32, 3, 3)
+    torch.nn.init.kaiming_normal_(w)
+    if [bits_checksum(torch.randn(4096)), bits_checksum(w)] != gold["canary"]:
+        pytest.skip("torch's CPU normal stream on this host differs from the host that generated the golden")
+    torch.manual_seed(0)
+    got = {k: bits_checksum(v) for k, v in DeepLab(ARGS).state_dict().items()}
+    diff = [k for k in gold["init_seed0"] if got.get(k) != gold["init_seed0"][k]]
+    assert not diff, diff[:10]
