@@ -16,6 +16,7 @@ PP_F32, PP_BF16 = 0, 1
 STRATEGIES = {"entropy": 0, "least_confidence": 1, "margin_sampling": 2}
 # fill value for excluded pixels and top-k direction (query.py:50,57-61,198)
 FILL = {"entropy": 0.0, "least_confidence": 0.0, "margin_sampling": 1.0, "random": 1.0}
+UPSAMPLED_SCORE_CLASSES = (11, 19, 21)  # class counts pp_acq_score_upsampled / pp_eval_confusion_upsampled are instantiated for
 LARGEST = {"entropy": True, "least_confidence": True, "margin_sampling": False, "random": False}
 
 _lib = None

@@ -28,6 +28,15 @@ __global__ void __launch_bounds__(kCeThreads) sparse_ce_kernel(
   float acc = 0.f;  // lane 0 accumulates this warp's NLL in pixel order
   for (int i = blockIdx.x * warps_per_block + warp; i < n_px; i += gridDim.x * warps_per_block) {
     const int img = px_img[i], idx = px_idx[i], label = px_label[i];
+    // malformed entry (F.cross_entropy raises "Target out of bounds" here, model.py:116): no out-of-bounds access, no
+    // silent training on a wrong class - the entry is skipped and the loss is poisoned with NaN so the step fails loudly
+    if ((unsigned)img >= (unsigned)n_img || (unsigned)idx >= (unsigned)(H * W) || (unsigned)label >= (unsigned)C) {
+      if (lane == 0) {
+        acc = __int_as_float(0x7FC00000);
+        if (pred_at) pred_at[i] = -1;
+      }
+      continue;
+    }
     const int y = idx / W, x = idx - y * W;
     const Lerp ly = lerp_ac(y, h_in, H, scale_h);
     const Lerp lx = lerp_ac(x, w_in, W, scale_w);

@@ -23,33 +23,126 @@ def broadcast_parameters(model, src=0):
             dist.broadcast(t.data, src)
 
 
-class GradAllReducer:
-    """Flattens every gradient into one fp32 buffer, all-reduces it once and scatters the mean back."""
+def average_buffers(model):
+    """BatchNorm running statistics drift apart between ranks (per-rank batches, no SyncBN as in the reference): average
+    the floating-point buffers over the ranks - ONE all-reduce of the flattened statistics - so that validation, the saved
+    checkpoint and the query round see the same eval-mode network on every rank.  Integer buffers (num_batches_tracked)
+    advance identically on every rank and are left alone."""
+    if world() == 1:
+        return
+    with torch.no_grad():
+        bufs = [b for b in model.buffers() if b.is_floating_point()]
+        if not bufs:
+            return
+        flat = torch.cat([b.detach().reshape(-1).float() for b in bufs])
+        dist.all_reduce(flat)
+        flat.div_(world())
+        off = 0
+        for b in bufs:
+            n = b.numel()
+            b.copy_(flat[off:off + n].view_as(b))
+            off += n
 
-    def __init__(self, model):
+
+class GradAllReducer:
+    """Data-parallel gradient exchange of the train step: bucketed, overlapped with backward, no copies.
+
+    * every parameter's `.grad` is a VIEW into one flat fp32 buffer, laid out in reverse parameter order (the order in
+      which backward produces gradients), so autograd accumulates straight into the buffer the collective reduces and the
+      optimiser reads the reduced values in place - no flatten / unflatten passes;
+    * the buffer is cut into buckets of ~`bucket_mb`; a post-accumulate hook counts a bucket's parameters and, when the
+      last one has its gradient, launches that bucket's all-reduce (`async_op`: NCCL's own stream) while backward keeps
+      running on the compute stream.  NVSwitch makes the cost per bucket latency-, not link-bound, so buckets are few
+      and large;
+    * `reducer()` after backward launches whatever is left (parameters that received no gradient) and makes the compute
+      stream wait for the collectives.  The whole sequence is capturable in the step's CUDA graph.
+    Average = ReduceOp.AVG on NCCL (no separate division pass); SUM + in-place division on gloo (CPU tests).
+    Usage per step:  reducer.zero_grad(); loss.backward(); reducer(); optimizer.step()."""
+
+    def __init__(self, model, bucket_mb: float = 32.0, overlap: bool = True):
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.flat = None
+        order = list(reversed(self.params))
+        n = sum(p.numel() for p in order)
+        dev = order[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.overlap = overlap and world() > 1
+        self._avg = dist.ReduceOp.AVG if (world() > 1 and dist.get_backend() == "nccl") else None
+        cap = max(1, int(bucket_mb * (1 << 20) / 4))
+        self.buckets = []      # [lo, hi) element ranges of the flat buffer
+        self._bucket_of = {}   # parameter -> bucket index
+        self._need = []        # parameters per bucket
+        off = lo = 0
+        cnt = 0
+        for p in order:
+            if p.dtype != torch.float32:
+                raise TypeError("GradAllReducer expects fp32 master parameters")
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self._bucket_of[p] = len(self.buckets)
+            off += p.numel()
+            cnt += 1
+            if off - lo >= cap:
+                self.buckets.append((lo, off))
+                self._need.append(cnt)
+                lo, cnt = off, 0
+        if off > lo:
+            self.buckets.append((lo, off))
+            self._need.append(cnt)
+        self._ready = [0] * len(self.buckets)
+        self._works = [None] * len(self.buckets)
+        self._handles = []
+        if self.overlap:
+            for p in order:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
+
+    def zero_grad(self):
+        """one memset of the flat buffer (the parameters' .grad views stay in place)"""
+        self.flat.zero_()
+        for p in self.params:  # an optimiser / user may have dropped the view (set_to_none): restore it
+            if p.grad is None or p.grad.data_ptr() != self._view_ptr(p):
+                self._rebind()
+                break
+        self._ready = [0] * len(self.buckets)
+        self._works = [None] * len(self.buckets)
+
+    def _view_ptr(self, p):
+        if not hasattr(self, "_ptrs"):
+            self._ptrs, off = {}, 0
+            for q in reversed(self.params):
+                self._ptrs[q] = self.flat.data_ptr() + 4 * off
+                off += q.numel()
+        return self._ptrs[p]
+
+    def _rebind(self):
+        off = 0
+        for q in reversed(self.params):
+            q.grad = self.flat[off:off + q.numel()].view_as(q)
+            off += q.numel()
+
+    def _launch(self, b):
+        lo, hi = self.buckets[b]
+        seg = self.flat[lo:hi]
+        if self._avg is not None:
+            self._works[b] = dist.all_reduce(seg, op=self._avg, async_op=True)
+        else:
+            self._works[b] = dist.all_reduce(seg, async_op=True)
+
+    def _hook(self, p):
+        b = self._bucket_of[p]
+        self._ready[b] += 1
+        if self._ready[b] == self._need[b] and self._works[b] is None:
+            self._launch(b)
 
     def __call__(self):
         if world() == 1:
             return
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        n = sum(g.numel() for g in grads)
-        if self.flat is None or self.flat.numel() != n:
-            self.flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
-        off = 0
-        views = []
-        for g in grads:
-            v = self.flat[off:off + g.numel()].view_as(g)
-            views.append(v)
-            off += g.numel()
-        torch._foreach_copy_(views, grads)
-        dist.all_reduce(self.flat)
-        self.flat.div_(world())
-        for p, v in zip(self.params, views):
-            if p.grad is None:
-                p.grad = v.clone()
-        torch._foreach_copy_([p.grad for p in self.params], views)
+        for b in range(len(self.buckets)):
+            if self._works[b] is None:
+                self._launch(b)
+        for b, w in enumerate(self._works):
+            w.wait()
+            if self._avg is None:
+                lo, hi = self.buckets[b]
+                self.flat[lo:hi].div_(world())
 
 
 def global_mean_loss_scale(n_local: torch.Tensor) -> torch.Tensor:

@@ -7,7 +7,7 @@ count on the device), the dropout step counter (device int64 advanced inside the
 import torch
 
 from . import dist as ppdist
-from .loss import labelled_pixel_list_host, sparse_cross_entropy
+from .loss import LabelCapacityError, labelled_pixel_list_host, sparse_cross_entropy
 
 
 def make_capturable_adam(param_groups):
@@ -55,7 +55,15 @@ class GraphedTrainStep:
         self.graph = None
         self._warm = warmup
 
+    def _zero_grad(self):
+        if self.reducer is not None:
+            self.reducer.zero_grad()  # gradients live in the reducer's flat buffer: one memset, views stay bound
+        else:
+            self.opt.zero_grad(set_to_none=True)
+
     def _step(self):
+        if self.reducer is not None:
+            self.reducer.zero_grad()  # inside the captured step: every replay starts from a zeroed flat buffer
         lowres = self.model.forward_lowres(self.x)
         loss, pred, _ = sparse_cross_entropy(lowres, None, None, self.ignore_index, size=self.size, return_pred=True,
                                              px=self.px, n_valid=self.n_valid)
@@ -69,8 +77,15 @@ class GraphedTrainStep:
 
     def prefetch(self, x, y, queries):
         """host batch (CPU tensors from the dataloader) -> device STAGING buffers, asynchronously on the copy stream (it
-        overlaps whatever the main stream is running); returns the host label list.  Follow with commit()."""
-        pi, px, pl, n = labelled_pixel_list_host(y, queries, self.ignore_index, self.capacity)
+        overlaps whatever the main stream is running); returns the host label list.  Follow with commit().
+        Returns None (nothing staged) when the batch holds more labelled pixels than the captured capacity: the caller
+        runs that batch through the eager step."""
+        try:
+            pi, px, pl, n = labelled_pixel_list_host(y, queries, self.ignore_index, self.capacity,
+                                                     n_classes=self.metrics.n_classes if self.metrics is not None else None)
+        except LabelCapacityError:
+            self._staged = False
+            return None
         self.commit_done.synchronize()  # the previous commit has consumed the staging / pinned buffers
         cap = self.capacity
         mh = self.meta_host
@@ -82,6 +97,10 @@ class GraphedTrainStep:
             self.stage_ready.record(self.copy_stream)
         self._staged = True
         return pl[: int(n)].clone()
+
+    def drop_staged(self):
+        """forget a prefetched batch (the loop decided not to run it through the graph)."""
+        self._staged = False
 
     def commit(self):
         """staging -> the graph's static inputs (device-to-device, on the current stream)."""
@@ -138,12 +157,12 @@ class GraphedTrainStep:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(self._warm):
-                self.opt.zero_grad(set_to_none=True)
+                self._zero_grad()
                 self._step()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        self.opt.zero_grad(set_to_none=True)
+        self._zero_grad()
         with torch.cuda.graph(self.graph):
             self.loss, self.pred = self._step()
         if snap is not None:

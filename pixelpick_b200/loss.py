@@ -41,9 +41,15 @@ class _SparseCE(torch.autograd.Function):
         return (grad * g_loss).to(ctx.in_dtype), None, None, None, None, None
 
 
-def labelled_pixel_list_host(y, queries, ignore_index, capacity=None):
+class LabelCapacityError(_lib.PixelPickError):
+    """more labelled pixels in a batch than the fixed-capacity list of a captured step can hold"""
+
+
+def labelled_pixel_list_host(y, queries, ignore_index, capacity=None, n_classes=None):
     """Host-side (NumPy) version for CPU batches straight from the dataloader: no device sync, optional padding to a
-    fixed `capacity` (CUDA graphs).  Returns (px_img, px_idx, px_label, n_valid) as int32 CPU tensors."""
+    fixed `capacity` (CUDA graphs).  Returns (px_img, px_idx, px_label, n_valid) as int32 CPU tensors.
+    Labels are validated like F.cross_entropy does (model.py:116): a target that is neither `ignore_index` nor in
+    [0, n_classes) raises instead of silently training on a wrong class."""
     import numpy as np
     yn = y.numpy() if isinstance(y, torch.Tensor) else np.asarray(y)
     B = yn.shape[0]
@@ -55,9 +61,12 @@ def labelled_pixel_list_host(y, queries, ignore_index, capacity=None):
     img, idx = np.nonzero(keep)
     lab = yf[img, idx]
     n = img.size
+    if n and (lab.min() < 0 or (n_classes is not None and lab.max() >= n_classes)):
+        bad = lab[(lab < 0) | (lab >= (n_classes if n_classes is not None else np.iinfo(np.int64).max))]
+        raise IndexError(f"Target {int(bad[0])} is out of bounds.")  # the message of F.cross_entropy on the CPU
     cap = n if capacity is None else capacity
     if n > cap:
-        raise _lib.PixelPickError(f"{n} labelled pixels exceed the captured capacity {cap}")
+        raise LabelCapacityError(f"{n} labelled pixels exceed the captured capacity {cap}")
     out = [np.zeros(cap, dtype=np.int32) for _ in range(3)]
     out[0][:n], out[1][:n], out[2][:n] = img, idx, lab
     return tuple(torch.from_numpy(a) for a in out) + (torch.tensor([n], dtype=torch.int32),)

@@ -88,11 +88,14 @@ class Model:
         mask = dict_data["queries"].to(self.device, torch.bool) if self.n_pixels_by_us != 0 else None
         lowres = model.forward_lowres(x)
         loss, pred_at, (_, _, px_label) = sparse_cross_entropy(lowres, y, mask, self.ignore_index, return_pred=True)
-        optimizer.zero_grad(set_to_none=True)
+        if reducer is not None:
+            reducer.zero_grad()  # gradients are views of the reducer's flat buffer
+        else:
+            optimizer.zero_grad(set_to_none=True)
         if ppdist.world() > 1:
             n_local = torch.tensor(float(px_label.numel()), device=self.device)
             (loss * ppdist.global_mean_loss_scale(n_local)).backward()
-            reducer()
+            reducer()  # bucketed all-reduce, launched from backward hooks; this waits for the tail
         else:
             loss.backward()
         optimizer.step()
@@ -107,16 +110,26 @@ class Model:
         gs = self._graph
         if gs is None:
             from .graph import GraphedTrainStep
-            per_img = min(shape[1] * shape[2], self.init_n_pixels + self.max_budget + self.n_pixels_by_us + 16)
+            # labelled pixels per crop: the reference's NEAREST rescale (x0.5-2.0) + crop of the `queries` mask
+            # (base_dataset.py:55-98) can multiply a crop's count by up to 4 -> capacity with that factor, capped at the
+            # crop size; a batch that still overflows takes the eager step (below) instead of aborting the epoch
+            per_img = min(shape[1] * shape[2], 4 * (self.init_n_pixels + self.max_budget + self.n_pixels_by_us) + 16)
             gs = GraphedTrainStep(model, optimizer, shape, self.ignore_index, capacity=shape[0] * per_img,
                                   device=self.device, reducer=reducer, n_classes=self.n_classes)
-            gs.load(x, y, q)
+            if gs.prefetch(x, y, q) is None:
+                return None  # nothing captured yet: try again with the next batch
+            gs.commit()
             gs.capture(restore_state=True)  # warm-up steps leave no trace: the first replay is the first update
             self._graph, self._graph_shape = gs, shape
+            self._graph_labels = None
+            gs()
+            return True
         if shape != self._graph_shape:
+            gs.drop_staged()
+            self._graph_labels = None
             return None
-        if self._graph_labels is None:
-            gs.prefetch(x, y, q)
+        if self._graph_labels is None and gs.prefetch(x, y, q) is None:
+            return None  # more labelled pixels than the captured capacity: eager step for this batch
         self._graph_labels = None
         gs.commit()
         gs()  # loss / predictions / confusion matrix stay on the device until the end of the epoch
@@ -129,8 +142,8 @@ class Model:
             return
         x = dict_data["x"]
         if (x.shape[0], x.shape[2], x.shape[3]) == self._graph_shape:
-            gs.prefetch(x, dict_data["y"], dict_data["queries"])
-            self._graph_labels = True
+            # None = the batch overflows the captured capacity: nothing staged, _graphed_step will send it to the eager step
+            self._graph_labels = True if gs.prefetch(x, dict_data["y"], dict_data["queries"]) is not None else None
 
     def _train_epoch(self, epoch, model, optimizer, lr_scheduler, reducer=None):
         if self.n_pixels_by_us != 0:
@@ -191,6 +204,10 @@ class Model:
         reducer = ppdist.GradAllReducer(model) if ppdist.world() > 1 else None
         for e in range(1, 1 + self.n_epochs):
             model, optimizer, lr_scheduler = self._train_epoch(e, model, optimizer, lr_scheduler, reducer)
+            # BatchNorm running statistics are per-rank during the epoch (the reference has no SyncBN); average them
+            # before anything evaluates the model (validation, best-mIoU checkpoint, the query round that scores image
+            # i on rank i % world) so every rank holds the SAME eval-mode network
+            ppdist.average_buffers(model)
             self._val(e, model)
             if self.debug:
                 break

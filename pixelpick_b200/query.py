@@ -13,8 +13,10 @@ Differences that do not change results:
   * `QueryStats` evaluates the entropy only at the selected pixels (reference recomputes the full map,
     query.py:260-264);
   * under `torch.distributed` (one process per GPU) image i is scored by rank i % world; every rank still walks the
-    whole dataloader and draws every image's random numbers, so the picks are those of a single-process run, and the
-    round ends with ONE all-gather of the per-rank picks / statistics.
+    whole dataloader and draws every image's random numbers, so for the SAME model the picks are those of a
+    single-process run (the caller makes the model identical on every rank: gradients are all-reduced and
+    `dist.average_buffers` equalises the BatchNorm running statistics before the round), and the round ends with ONE
+    all-gather of the per-rank picks / statistics.
 Tie rule of the top-k: equal scores -> lower flat index first (CPU `torch.topk` leaves it unspecified).
 """
 import os
@@ -244,7 +246,10 @@ class QuerySelector:
         """model forward + fused scoring for a [b, 3, H', W'] batch -> (score [b, h*w], logits handle)."""
         st = self.query_strategy
         lowres = getattr(model, "forward_lowres", None)
-        if lowres is not None and x.shape[2] == h and x.shape[3] == w:
+        # the fused upsample+score kernel is instantiated for the reference datasets' class counts (cv 11, cs 19, voc 21);
+        # any other n_classes (a --p_dataset_config dataset) takes the full-resolution path below, whose scalar scoring
+        # kernel handles every C
+        if lowres is not None and x.shape[2] == h and x.shape[3] == w and self.n_classes in _lib.UPSAMPLED_SCORE_CLASSES:
             lr = lowres(x)  # [b, C, h/4, w/4] fp32: the ×4 upsample is fused into the kernel
             score = _lib.acq_score_upsampled(lr, (h, w), st, labelled, void, keep, hist0_ws=ws)
             return score, ("lowres", lr)

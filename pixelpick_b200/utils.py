@@ -60,6 +60,9 @@ class Poly(_LRScheduler):
         self.cur_iter = 0
         self.N = num_epochs * iters_per_epoch
         self.warmup_iters = warmup_epochs * iters_per_epoch
+        # capturable Adam keeps its learning rates as DEVICE tensors: read the base values back ONCE here instead of one
+        # blocking .item() per parameter group per iteration (the graph path exists to remove per-step syncs)
+        self._host_base_lrs = [float(g.get("initial_lr", g["lr"])) for g in optimizer.param_groups]
         super().__init__(optimizer, last_epoch)
 
     def get_lr(self):
@@ -70,7 +73,7 @@ class Poly(_LRScheduler):
         self.cur_iter %= self.iters_per_epoch
         self.cur_iter += 1
         assert factor >= 0, "error in lr_scheduler"
-        return [float(base_lr) * factor for base_lr in self.base_lrs]  # float(): base lrs may be device tensors
+        return [base_lr * factor for base_lr in self._host_base_lrs]
 
 
 def get_lr_scheduler(args, optimizer, iters_per_epoch=-1):

@@ -35,9 +35,30 @@ def _worker(rank, world, port, out):
     lo, hi = cuts[rank], cuts[rank + 1]
     loss = torch.nn.functional.cross_entropy(model(X[lo:hi]), Y[lo:hi])
     scale = ppdist.global_mean_loss_scale(torch.tensor(float(hi - lo)))
+    # tiny buckets: several collectives are launched from the backward hooks, the call after backward waits for them
+    reducer = ppdist.GradAllReducer(model, bucket_mb=64 / (1 << 20))
+    assert len(reducer.buckets) >= 2
+    reducer.zero_grad()
     (loss * scale).backward()
-    ppdist.GradAllReducer(model)()
+    reducer()
     grads = torch.cat([p.grad.flatten() for p in model.parameters()])
+    assert all(p.grad.data_ptr() == reducer._view_ptr(p) for p in model.parameters())  # still views of the flat buffer
+    # second step through the same reducer: zero_grad() re-arms the buckets; a dropped view is re-bound
+    for p in list(model.parameters())[:1]:
+        p.grad = None
+    reducer.zero_grad()
+    (torch.nn.functional.cross_entropy(model(X[lo:hi]), Y[lo:hi]) * scale).backward()
+    reducer()
+    assert torch.allclose(torch.cat([p.grad.flatten() for p in model.parameters()]), grads, atol=1e-6)
+    # BatchNorm running statistics: per-rank during training, averaged before evaluation (dist.average_buffers)
+    bn = torch.nn.BatchNorm1d(4)
+    bn.running_mean.fill_(float(rank))
+    bn.running_var.fill_(1.0 + rank)
+    bn.num_batches_tracked.fill_(7)
+    ppdist.average_buffers(bn)
+    m_want = sum(range(world)) / world
+    assert torch.allclose(bn.running_mean, torch.full((4,), m_want)) and torch.allclose(bn.running_var, torch.full((4,), 1.0 + m_want))
+    assert int(bn.num_batches_tracked) == 7
     # sharded query bookkeeping
     idx = ppdist.shard_indices(7)
     rows = torch.tensor([[i, i * 10] for i in idx])
