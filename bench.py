@@ -1,27 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the pixelpick_b200 hot paths (contract: see the task statement).
+"""bench.py - headline benchmark of pixelpick_b200 (contract: see the task statement).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-BASELINE.json metric: "train images/sec + query Mpixels/sec, Cityscapes 256x512" (configs[1]/[2]).  One JSON line:
+BASELINE.json metric: "train images/sec + query Mpixels/sec, Cityscapes 256x512 RN50 @1/2/4/8 B200" (configs[2]).
+ONE JSON line:
 
-  primary (metric/value/roofline/e2e/cpu_baseline) = the QUERY hot path, margin_sampling, top-5 % (k=6553), n=10:
-      step     = one pass over a batch of B images per GPU: fused softmax+margin+mask score -> per-image sorted
-                 top-k -> gather of the n picks                                   [all hand-written CUDA]
-      value    = Mpixels/s over all ranks, logits resident in HBM (CUDA events, max over ranks)
-      e2e      = the same metric through the C-ABI host-buffer call (pp_acq_session_run_host): pinned host
-                 logits/masks -> H2D -> kernels -> D2H of the picks, incl. the host NumPy draw of the pick positions
-      roofline = the scoring kernel alone, timed with CUDA events INSIDE the timed steps; algorithmic bytes
-                 (C*4 + 2) B/px over MEASURED_PEAKS.json hbm_gbs
-  "train"  = images/s of the DeepLabv3+ train step (encoder bf16 channels_last -> tcgen05 ASPP/decoder head ->
-             fused upsample+sparse-CE -> custom backward -> fused Adam), dropout on, 10 labelled px/image,
-             for MobileNetV2 (configs[1]) and ResNet-50 (configs[2]) at the reference batch (4/GPU) and a
-             throughput batch; its own e2e (pinned host batch -> H2D every step, loss read back every step) and the
-             tensor-core roofline of the SegmentHead 3x3 conv kernel (nominal FLOPs / CUDA-event time / measured bf16 peak)
-  "query_model" = Mpixels/s of QuerySelector-style querying with the model in the loop (forward_lowres + fused
-             upsample/score + top-k), images resident in HBM and from pinned host memory.
-  cpu_baseline / --impl reference = the oracle port of the reference's CPU path (torch CPU + NumPy, all host
-             threads) on a bounded sample of the same workloads.
+  metric / value = train images/s of the RN50-DeepLabv3+ step (model.py:103-142 through networks/deeplab.py, dilated
+             ResNet-50 encoder, ASPP OS8, SegmentHead) on synthetic Cityscapes-shape batches: forward_lowres -> fused x4
+             upsample + sparse CE -> backward -> bucketed gradient all-reduce (NCCL, launched from backward hooks) ->
+             Adam, replayed from ONE captured CUDA graph per step; batch resident in HBM; CUDA events, max over ranks;
+             whole-job aggregate over the N ranks (weak scaling: the per-GPU batch is fixed).
+  e2e      = the same metric with the batch coming from PINNED HOST memory every step (H2D on a copy stream under the
+             previous step) and the loss read back every step - the way pixelpick_b200.Model._train_epoch drives it.
+  config   = the workload plus the secondary numbers of the metric as scalars: the reference batch (4 / GPU), the
+             MobileNetV2 network (BASELINE configs[1]), query Mpixels/s with the model in the loop through
+             QuerySelector.__call__ (host images in, dict of picks out: query.py:159-221), the acquisition-kernel step.
+  roofline = the fused acquisition scoring kernel (north star: >= 80 % of the HBM roofline), timed with CUDA events
+             inside its own timed steps: algorithmic bytes (C*4 + 2) B/px over MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline / --impl reference = the oracle port of the reference's CPU train step (fp32 torch CPU, every host
+             thread) on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -43,7 +41,8 @@ STRATEGY = "margin_sampling"
 TOP_N_PERCENT, N_SEL = 0.05, 10
 K_TOP = int(H * W * TOP_N_PERCENT)
 ALG_BYTES_PER_PX = C * 4 + 2  # logits + labelled mask + void mask
-WORKLOAD = f"cityscapes 256x512 C={C} {STRATEGY} top-5% (k={K_TOP}) n={N_SEL}: logits -> score -> top-k select -> n random ranks"
+WORKLOAD = (f"cityscapes 256x512 C={C} ResNet50-DeepLabv3+ train step (10 labelled px/image, Adam lr 5e-4 / encoder lr/10, wd 2e-4, "
+            f"dropout on) + {STRATEGY} query top-5% (k={K_TOP}) n={N_SEL}")
 MARGS = Namespace(use_mc_dropout=False, mc_dropout_p=0.2, n_classes=C)
 OPT = {"lr": 5e-4, "weight_decay": 2e-4}  # args.py:101-106 (cs)
 
@@ -208,183 +207,91 @@ def cpu_query_model_rate(backbone, n_img, threads):
     return n_img * H * W / 1e6 / dt, dt
 
 
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the oracle port of the reference's CPU path, same metric / config as our arm
+# ----------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the train step (model.py:103-122 through
+    networks/deeplab.py with the dilated ResNet-50 encoder), restated by oracle/deeplab_oracle.py on torch CPU with every
+    host thread.  The reference is pure Python and cannot travel to the GPU box, so kind = "port" (the port is pinned to
+    the imported reference by tests/golden/make_golden_model.py)."""
     if rank != 0:
         return
+    from oracle import deeplab_oracle as dorc
+    from pixelpick_b200.deeplab import DeepLab  # parameter names / shapes only
     threads = os.cpu_count() or 1
-    n_img = 16
-    W_, K_ = max(args.warmup, 1), args.steps
-    from oracle import acq_oracle as orc
     torch.set_num_threads(threads)
-    logits, lab, void = synth(n_img, 1234)
-    lab_np, void_np = lab.numpy().astype(bool), void.numpy().astype(bool)
-    imgs = [logits[i:i + 1] for i in range(n_img)]
-    names = [f"img_{i:05d}.png" for i in range(n_img)]
-    np.random.seed(0)
-    for _ in range(W_):
-        orc.query_images(imgs, STRATEGY, lab_np, void_np, names, N_SEL, TOP_N_PERCENT)
+    W_, K_ = max(args.warmup, 1), args.steps
+    shapes = {k: tuple(v.shape) for k, v in DeepLab(MARGS, backbone="resnet").state_dict().items()}
+    sd = dorc.synthetic_state_dict(shapes, seed=1)
+    params = []
+    for k in sorted(sd):
+        if sd[k].dtype.is_floating_point and not k.endswith(("running_mean", "running_var")):
+            sd[k] = sd[k].clone().requires_grad_(True)
+            params.append(sd[k])
+    opt = torch.optim.Adam(params, lr=OPT["lr"], weight_decay=OPT["weight_decay"])
+
+    def step(x, y, q):
+        out = dorc.deeplab_forward(sd, x, backbone="resnet", training=True, drop=(0.5, 0.5, 0.2))
+        loss = dorc.sparse_ce_loss(out["pred"], y, q, C)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    # bounded sample: the reference batch (4) when the whole run fits ~3 minutes on this host, else 2 images / step
+    B = 4
+    x, y, q = synth_train_batch(B, 7)
+    t0 = time.perf_counter()
+    step(x, y, q)
+    t_first = time.perf_counter() - t0
+    if t_first * (K_ + W_) > 150.0:
+        B = 2
+        x, y, q = synth_train_batch(B, 7)
+    for _ in range(W_ - 1 if B == 4 else W_):
+        step(x, y, q)
     t0 = time.perf_counter()
     for _ in range(K_):
-        orc.query_images(imgs, STRATEGY, lab_np, void_np, names, N_SEL, TOP_N_PERCENT)
+        step(x, y, q)
     dt = time.perf_counter() - t0
-    val = K_ * n_img * H * W / 1e6 / dt
-    sample = f"{n_img} images of 256x512x19 fp32 per step (logits pre-computed), torch CPU + NumPy, {threads} threads"
+    val = K_ * B / dt
+    sample = (f"RN50-DeepLabv3+ train step on {B} images of 256x512 per step (fp32, torch CPU, Adam, dropout on), "
+              f"{threads} threads, {K_} timed steps, {dt:.1f} s")
+    cfg = {"workload": WORKLOAD, "batch_per_step": B, "parallelism": "CPU, one process"}
+    if not args.no_query:
+        qm, qdt = cpu_query_model_rate("resnet", 2, threads)
+        cfg["query_rn50_mpix_s"] = _r(qm)
+        cfg["query_sample"] = f"oracle port of query.py:159-212 incl. the RN50-DeepLab forward, 2 images one per forward, {qdt:.1f} s"
     out = {
-        "impl": "reference", "metric": "query_mpixels_per_sec", "value": val, "unit": "Mpixels/s", "n_gpus": world,
-        "steps": K_, "warmup": W_, "ms_per_step": dt / K_ * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_step": n_img},
-        "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": "train_images_per_sec", "value": _r(val), "unit": "images/s", "n_gpus": world,
+        "steps": K_, "warmup": W_, "ms_per_step": _r(dt / K_ * 1e3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": _r(val), "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": _r(val), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    if not args.no_train:
-        qm, qdt = cpu_query_model_rate("mobilenet", 8, threads)
-        out["query_model"] = {"unit": "Mpixels/s", "mobilenetv2_bs1_host": {"value": qm, "images_per_s": 8 / qdt},
-                              "sample": "oracle port of query.py:159-212 incl. the MobileNetV2-DeepLab forward (fp32 torch CPU), "
-                                        "8 images, one per forward"}
-        r_mn, t_mn = cpu_train_rate("mobilenet", 4, 2, threads)
-        out["train"] = {"metric": "train_images_per_sec", "unit": "images/s", "dtype": "f32",
-                        "mobilenetv2_b4": {"value": r_mn, "ms_per_step": float(np.mean(t_mn)) * 1e3, "steps": len(t_mn)},
-                        "sample": "oracle port of model.py:103-122 (fp32, torch CPU, Adam, dropout on), B=4, 2 timed steps"}
-    print(json.dumps(out))
+    print(json.dumps(out, separators=(",", ":")))
 
 
-# ----------------------------------------------------------------------------------------------
-# our arm
-# ----------------------------------------------------------------------------------------------
-def bench_train_graph(backbone, B, steps, warmup, dev, world, e2e=False, loop=False):
-    """Same train step captured ONCE as a CUDA graph (pixelpick_b200/graph.py) and replayed: removes the ~1000 kernel
-    launches / step of CPU overhead that bound the reference batch size."""
-    import torch.distributed as dist
-    from pixelpick_b200 import _lib, dist as ppdist
-    from pixelpick_b200.deeplab import DeepLab
-    from pixelpick_b200.graph import GraphedTrainStep, make_capturable_adam
-    torch.manual_seed(0)
-    model = DeepLab(MARGS, backbone=backbone).to(dev)
-    model.train()
-    ppdist.broadcast_parameters(model)
-    groups = [{"params": model.backbone.parameters(), "lr": OPT["lr"] / 10, "weight_decay": OPT["weight_decay"]}]
-    for part in (model.aspp, model.low_level_conv, model.seg_head):
-        groups.append({"params": part.parameters(), "lr": OPT["lr"], "weight_decay": OPT["weight_decay"]})
-    opt = make_capturable_adam(groups)
-    reducer = ppdist.GradAllReducer(model) if world > 1 else None
-    hx, hy, hq = synth_train_batch(B, 11 + ppdist.rank(), pin=True)
-    # loop=True is what pixelpick_b200.Model._train_epoch runs: host batch -> H2D every step (prefetched during the
-    # previous step's graph), running metrics accumulated on the device, ONE device->host read at the end of the epoch
-    gs = GraphedTrainStep(model, opt, (B, H, W), C, capacity=B * 16, device=dev, reducer=reducer,
-                          n_classes=C if loop else None)
-    gs.load(hx, hy, hq)
-    gs.capture()
-    loss_host = torch.zeros(1).pin_memory()
-
-    if e2e or loop:
-        gs.prefetch(hx, hy, hq)
-
-    def step():
-        if e2e or loop:
-            gs.commit()  # staging -> static inputs (the H2D of this batch ran during the previous step's graph)
-        loss, _ = gs()
-        if e2e or loop:
-            gs.prefetch(hx, hy, hq)  # next host batch -> staging on the copy stream, overlapping the graph (H2D every step)
-        if e2e:
-            loss_host.copy_(loss.detach().reshape(1))  # D2H read of this step's loss every step
-        return loss
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(warmup):
-        step()
-    barrier()
-    l0 = _lib.lib().pp_launch_count()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    a.record()
-    for _ in range(steps):
-        last = step()
-    if loop:
-        gs.metrics.read()  # the epoch's confusion matrix + loss sum: the loop's only device->host read
-    b.record()
-    barrier()
-    wall = time.perf_counter() - t0
-    ms = a.elapsed_time(b) if not (e2e or loop) else wall * 1e3
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    host = e2e or loop
-    return {"value": world * B * steps / (ms / 1e3), "ms_per_step": ms / steps, "batch_per_gpu": B, "steps": steps,
-            "cuda_graph": True, "final_loss": float(last.item()),
-            "h2d_bytes_per_step": B * (3 * H * W * 4) + 3 * B * 16 * 4 + 4 if host else 0,
-            "d2h_bytes_per_step": 4 if e2e else (C * C * 8 + 16) / steps if loop else 0}
+def _r(v, sig=5):
+    """round to `sig` significant digits (keeps the JSON line short enough for the driver's tail)."""
+    if v is None or isinstance(v, (int, str, bool)):
+        return v
+    v = float(v)
+    if v == 0 or not np.isfinite(v):
+        return v
+    return float(f"{v:.{sig}g}")
 
 
-def bench_train(backbone, B, steps, warmup, dev, world, e2e=False):
-    """images/s of the full train step; returns dict(value, ms_per_step, ...)."""
-    import torch.distributed as dist
-    from pixelpick_b200 import _lib, dist as ppdist
-    from pixelpick_b200.deeplab import DeepLab
-    from pixelpick_b200.loss import sparse_cross_entropy
-    torch.manual_seed(0)
-    model = DeepLab(MARGS, backbone=backbone).to(dev)
-    model.train()
-    ppdist.broadcast_parameters(model)
-    groups = [{"params": model.backbone.parameters(), "lr": OPT["lr"] / 10, "weight_decay": OPT["weight_decay"]}]
-    for part in (model.aspp, model.low_level_conv, model.seg_head):
-        groups.append({"params": part.parameters(), "lr": OPT["lr"], "weight_decay": OPT["weight_decay"]})
-    opt = torch.optim.Adam(groups, fused=True)
-    reducer = ppdist.GradAllReducer(model) if world > 1 else None
-    hx, hy, hq = synth_train_batch(B, 11 + ppdist.rank(), pin=True)
-    dx, dy, dq = hx.to(dev), hy.to(dev), hq.to(dev)
-    loss_host = torch.zeros(1).pin_memory()
-
-    def step(from_host):
-        if from_host:
-            x, y, q = hx.to(dev, non_blocking=True), hy.to(dev, non_blocking=True), hq.to(dev, non_blocking=True)
-        else:
-            x, y, q = dx, dy, dq
-        lowres = model.forward_lowres(x)
-        loss = sparse_cross_entropy(lowres, y, q.bool(), C)
-        opt.zero_grad(set_to_none=True)
-        if world > 1:
-            n_local = torch.tensor(float(B * 10), device=dev)
-            (loss * ppdist.global_mean_loss_scale(n_local)).backward()
-            reducer()
-        else:
-            loss.backward()
-        opt.step()
-        if from_host:
-            loss_host.copy_(loss.detach().reshape(1), non_blocking=False)  # D2H read of the step's result
-        return loss
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(warmup):
-        step(e2e)
-    barrier()
-    l0 = _lib.lib().pp_launch_count()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    a.record()
-    for _ in range(steps):
-        last = step(e2e)
-    b.record()
-    barrier()
-    wall = time.perf_counter() - t0
-    ms = a.elapsed_time(b) if not e2e else wall * 1e3
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    return {"value": world * B * steps / (ms / 1e3), "ms_per_step": ms / steps, "batch_per_gpu": B, "steps": steps,
-            "our_kernel_launches_per_step": (_lib.lib().pp_launch_count() - l0) / steps, "final_loss": float(last.item()),
-            "h2d_bytes_per_step": B * (3 * H * W * 4 + H * W * 8 + H * W) if e2e else 0, "d2h_bytes_per_step": 4 if e2e else 0}
+def _round_tree(o):
+    if isinstance(o, dict):
+        return {k: _round_tree(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_round_tree(v) for v in o]
+    if isinstance(o, float):
+        return _r(o)
+    return o
 
 
 def bench_conv_roofline(dev, peak_tf):
@@ -502,6 +409,238 @@ def bench_strategy_sweep(dev, hbm_peak, n_img=8, Hs=1024, Ws=2048, steps=5):
                       "score_kernel_gbs": ach, "score_kernel_frac_of_hbm_peak": ach / hbm_peak}
     return out
 
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def _barrier(world):
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(vals, dev, world):
+    import torch.distributed as dist
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.cpu()]
+
+
+def build_train(backbone, B, dev, world, loop=False):
+    """model + capturable Adam (args.py:101-106 cs groups) + bucketed gradient all-reduce + the captured step."""
+    from pixelpick_b200 import _lib, dist as ppdist
+    from pixelpick_b200.deeplab import DeepLab
+    from pixelpick_b200.graph import GraphedTrainStep, make_capturable_adam
+    torch.manual_seed(0)
+    model = DeepLab(MARGS, backbone=backbone).to(dev)
+    model.train()
+    ppdist.broadcast_parameters(model)
+    groups = [{"params": model.backbone.parameters(), "lr": OPT["lr"] / 10, "weight_decay": OPT["weight_decay"]}]
+    for part in (model.aspp, model.low_level_conv, model.seg_head):
+        groups.append({"params": part.parameters(), "lr": OPT["lr"], "weight_decay": OPT["weight_decay"]})
+    opt = make_capturable_adam(groups)
+    reducer = ppdist.GradAllReducer(model) if world > 1 else None
+    hx, hy, hq = synth_train_batch(B, 11 + ppdist.rank(), pin=True)
+    gs = GraphedTrainStep(model, opt, (B, H, W), C, capacity=B * 16, device=dev, reducer=reducer,
+                          n_classes=C if loop else None)
+    gs.load(hx, hy, hq)
+    l0 = _lib.lib().pp_launch_count()
+    gs.capture()
+    # our kernels are counted when they are LAUNCHED (captured); a replay re-issues the same list: 3 warm-up steps + 1 capture
+    per_step = (_lib.lib().pp_launch_count() - l0) / 4.0
+    return model, gs, (hx, hy, hq), per_step, reducer
+
+
+def bench_train_graph(backbone, B, steps, warmup, dev, world, mode="hbm"):
+    """images/s of the whole train step (forward_lowres -> fused upsample + sparse CE -> backward -> bucketed gradient
+    all-reduce -> Adam) replayed from ONE captured CUDA graph - what pixelpick_b200.Model._train_epoch runs.
+      mode "hbm"  : batch resident in HBM, CUDA events around the K replays (device time, max over ranks)
+      mode "e2e"  : every step uploads its batch from PINNED HOST memory (prefetched on a copy stream under the previous
+                    step's graph) and reads the step's loss back to the host; wall clock, max over ranks
+      mode "loop" : as Model._train_epoch: host batch every step, metrics accumulated on the device, ONE read per epoch"""
+    model, gs, (hx, hy, hq), per_step, reducer = build_train(backbone, B, dev, world, loop=(mode == "loop"))
+    loss_host = torch.zeros(1).pin_memory()
+    host = mode in ("e2e", "loop")
+    if host:
+        gs.prefetch(hx, hy, hq)
+
+    def step():
+        if host:
+            gs.commit()  # staging -> static inputs (the H2D of this batch ran during the previous step's graph)
+        loss, _ = gs()
+        if host:
+            gs.prefetch(hx, hy, hq)  # next host batch -> staging on the copy stream, overlapping the graph
+        if mode == "e2e":
+            loss_host.copy_(loss.detach().reshape(1))  # D2H read of this step's loss every step
+        return loss
+
+    for _ in range(warmup):
+        step()
+    _barrier(world)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(steps):
+        last = step()
+    if mode == "loop":
+        gs.metrics.read()  # the epoch's confusion matrix + loss sum: the loop's only device->host read
+    b.record()
+    _barrier(world)
+    wall = time.perf_counter() - t0
+    ms = a.elapsed_time(b) if not host else wall * 1e3
+    (ms,) = _max_over_ranks([ms], dev, world)
+    final_loss = float(last.item())
+    del gs, model, reducer
+    torch.cuda.empty_cache()
+    return {"value": world * B * steps / (ms / 1e3), "ms_per_step": ms / steps, "batch_per_gpu": B, "steps": steps,
+            "launches_per_step": per_step, "final_loss": final_loss,
+            "h2d_bytes_per_step": B * (3 * H * W * 4) + 3 * B * 16 * 4 + 4 if host else 0,
+            "d2h_bytes_per_step": 4 if mode == "e2e" else (C * C * 8 + 16) / steps if mode == "loop" else 0}
+
+
+class _HostImages(torch.utils.data.Dataset):
+    """Reference dataset interface (datasets/base_dataset.py:18-46) over pre-generated HOST tensors: items
+    {'x','y','p_img'}, `.queries`, `.label_queries` - what QuerySelector.__call__ reads (query.py:144-221)."""
+
+    def __init__(self, n, seed):
+        self.x, self.y, q = synth_train_batch(n, seed)
+        self.queries = [m.numpy().astype(bool) for m in q]
+        self.labelled = None
+
+    def __len__(self):
+        return self.x.shape[0]
+
+    def __getitem__(self, i):
+        return {"x": self.x[i], "y": self.y[i], "p_img": f"synthetic/{i:06d}.png"}
+
+    def label_queries(self, dict_queries, nth_query=None):
+        self.labelled = dict_queries
+
+
+def bench_query_selector(backbone, n_img_total, dev, world, tmpdir, reps=2):
+    """Query Mpixels/s with the model in the loop, through the public API: QuerySelector.__call__(nth_query, model) over a
+    DataLoader of HOST images (batch_size 1, as model.py:36-37) -> dict of picks (query.py:159-221): forward, fused
+    upsample + margin score, per-image top-k select, n random ranks, QueryStats, the round's all-gather at N > 1.
+    Wall clock, max over ranks; best of `reps` rounds after one warm-up round."""
+    from pixelpick_b200.deeplab import DeepLab
+    from pixelpick_b200.query import QuerySelector
+    torch.manual_seed(0)
+    model = DeepLab(MARGS, backbone=backbone).to(dev).eval()
+    ds = _HostImages(n_img_total, 21)
+    dl = torch.utils.data.DataLoader(ds, batch_size=1, shuffle=False, num_workers=0)
+    qargs = Namespace(dataset_name="cs", debug=False, dir_root=tmpdir, experim_name=f"bench_{backbone}", ignore_index=C,
+                      mc_n_steps=20, n_classes=C, n_pixels_by_us=N_SEL, network_name="deeplab", query_strategy=STRATEGY,
+                      reverse_order=False, stride_total=16, top_n_percent=TOP_N_PERCENT, use_mc_dropout=False, vote_type="soft")
+    qs = QuerySelector(qargs, dl, device=dev)
+    times = []
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    try:
+        sys.stdout.flush()
+        os.dup2(devnull, 1)  # QuerySelector prints the reference's progress lines: keep stdout = ONE JSON line
+        for r in range(reps + 1):
+            np.random.seed(0)
+            _barrier(world)
+            t0 = time.perf_counter()
+            picks = qs(r, model)
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+    assert len(picks) == n_img_total and all(len(v["x_coords"]) == N_SEL for v in picks.values())
+    (dt,) = _max_over_ranks([min(times[1:])], dev, world)
+    del model, qs
+    torch.cuda.empty_cache()
+    return {"value": n_img_total * H * W / 1e6 / dt, "images_per_s": n_img_total / dt, "images": n_img_total, "s_per_round": dt,
+            "h2d_bytes_per_image": 3 * H * W * 4 + 2 * H * W, "d2h_bytes_per_image": N_SEL * 8 + N_SEL * 4}
+
+
+def bench_acq_pipeline(B, K, Wm, dev, world, rank, overlap, sorted_topk=False):
+    """The acquisition kernels alone on logits resident in HBM (B images / step / GPU, 2.55 GB of fp32 logits per step at
+    B = 256 >> L2): fused softmax + margin + mask fills + level-0 histogram -> radix select -> order statistics at the n
+    drawn ranks; at N > 1 one all-gather of the round's picks.  Returns step / score-kernel times (CUDA events)."""
+    import torch.distributed as dist
+    from pixelpick_b200 import _lib
+    lib = _lib.lib()
+    HW = H * W
+    largest = _lib.LARGEST[STRATEGY]
+    logits, lab, void = synth(B, 100 + rank, device=dev)
+    np.random.seed(rank)
+    pos = torch.from_numpy(np.stack([np.random.permutation(K_TOP)[:N_SEL] for _ in range(B)]).astype(np.int32)).to(dev)
+    sel_round = torch.empty((K, B, N_SEL), dtype=torch.int32, device=dev) if world > 1 else None
+    gathered = torch.empty((world, K, B, N_SEL), dtype=torch.int32, device=dev) if world > 1 else None
+    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    n_slots = 2 if overlap else 1
+    slots = [(_lib.TopKWorkspace(B, HW, K_TOP, dev), torch.empty((B, H, W), dtype=torch.float32, device=dev)) for _ in range(n_slots)]
+    side = torch.cuda.Stream(device=dev, priority=-1) if overlap else None
+    scored = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    turn = [0]
+
+    def step(i=None):
+        p = (turn[0] % n_slots)
+        turn[0] += 1
+        ws_p, score_p = slots[p]
+        main = torch.cuda.current_stream()
+        if overlap:
+            main.wait_event(free[p])  # the select + pick that used this slot two steps ago
+        ws_p.prepare()
+        if i is not None:
+            ev_a[i].record()
+        _lib.acq_score(logits, STRATEGY, lab, void, out=score_p, hist0_ws=ws_p)
+        if i is not None:
+            ev_b[i].record()
+
+        def tail():
+            if sorted_topk:
+                sel = _lib.acq_gather(_lib.acq_topk(score_p.view(B, HW), K_TOP, largest, ws=ws_p, hist0_valid=True), pos)
+            else:  # what QuerySelector runs: only the n drawn ranks are needed (query.py:63-64) -> radix pick, no sort
+                sel = _lib.acq_select_pick(score_p.view(B, HW), K_TOP, largest, pos, ws=ws_p, hist0_valid=True)
+            if world > 1 and i is not None:
+                sel_round[i].copy_(sel)
+            return sel
+
+        if not overlap:
+            return tail()
+        scored[p].record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(scored[p])
+            sel = tail()
+            free[p].record(side)
+        return sel
+
+    if world > 1:  # pre-warm the communicator for this shape: the first call of a collective builds its plan
+        dist.all_gather_into_tensor(gathered, sel_round)
+    for _ in range(Wm):
+        step()
+    if overlap:
+        torch.cuda.current_stream().wait_stream(side)
+    _barrier(world)
+    l0 = lib.pp_launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(K):
+        step(i)
+    if overlap:  # the last steps' select + pick belong to the timed region
+        torch.cuda.current_stream().wait_stream(side)
+    if world > 1:  # the round's exchange: per-rank picks -> every rank, ONE collective
+        dist.all_gather_into_tensor(gathered, sel_round)
+    t_end.record()
+    _barrier(world)
+    launches = lib.pp_launch_count() - l0
+    ms_total = t_start.elapsed_time(t_end)
+    score_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ev_a, ev_b)]))
+    ms_total, score_ms = _max_over_ranks([ms_total, score_ms], dev, world)
+    del logits, slots
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms_total / K, "score_ms": score_ms, "launches": int(launches),
+            "mpix_s": world * B * HW * K / 1e6 / (ms_total / 1e3)}
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -509,15 +648,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per step per GPU (device-resident query leg)")
-    ap.add_argument("--e2e-batch", type=int, default=64, help="images per step per GPU (host-buffer query leg)")
-    ap.add_argument("--train-batch", type=int, default=32, help="throughput batch of the train leg (per GPU)")
+    ap.add_argument("--train-batch", type=int, default=32, help="throughput batch of the headline train step (per GPU)")
+    ap.add_argument("--acq-batch", type=int, default=256, help="images per step per GPU of the acquisition-kernel leg")
+    ap.add_argument("--query-images", type=int, default=96, help="images per GPU of the QuerySelector.__call__ leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sorted-topk", action="store_true", help="query step materialises the sorted top-k list (pp_acq_topk)")
-    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-query", action="store_true", help="skip the model-in-the-loop query legs")
+    ap.add_argument("--no-extras", action="store_true", help="headline train leg + acquisition roofline only")
     ap.add_argument("--overlap-select", action="store_true",
-                    help="EXPERIMENTAL (written in round 1 without GPU time left to verify it; default off): run the "
-                         "latency-bound select + pick of step i on a high-priority side stream while step i+1 is scored")
+                    help="acquisition leg: run the select + pick of step i on a side stream under the scoring of step i+1 "
+                         "(measured SLOWER on B200: 0.61 vs 0.55 ms/step - the concurrent kernels take HBM bandwidth from the "
+                         "scoring kernel; kept for the record, default is one stream)")
+    ap.add_argument("--sweep", action="store_true", help="also run the 1024x2048 strategy sweep (BASELINE configs[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -528,6 +669,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import tempfile
     import torch.distributed as dist
     from pixelpick_b200 import _lib
 
@@ -547,228 +689,99 @@ def main():
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    lib = _lib.lib()
+    _lib.lib()
     hbm_peak, tf_burst, tf_sust, peak_src = peaks()
+    K, Wm, Bt = args.steps, args.warmup, args.train_batch
+    tmpdir = tempfile.mkdtemp(prefix="pp_bench_")
 
-    B, K, Wm = args.batch, args.steps, args.warmup
-    HW = H * W
-    largest = _lib.LARGEST[STRATEGY]
-    logits, lab, void = synth(B, 100 + rank, device=dev)
-    ws = _lib.TopKWorkspace(B, HW, K_TOP, dev)
-    score = torch.empty((B, H, W), dtype=torch.float32, device=dev)
-    np.random.seed(rank)
-    pos = torch.from_numpy(np.stack([np.random.permutation(K_TOP)[:N_SEL] for _ in range(B)]).astype(np.int32)).to(dev)
-    # multi-GPU: the path's ONE exchange is an all-gather of the per-rank picks per query ROUND: the K
-    # timed steps are one round, so every step parks its picks in sel_round and the round ends with one all_gather
-    sel_round = torch.empty((K, B, N_SEL), dtype=torch.int32, device=dev) if world > 1 else None
-    gathered = [torch.empty((K, B, N_SEL), dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
-    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-
-    if args.overlap_select and not args.sorted_topk:
-        # two slots (workspace + score map); slot p's select + pick run on `side` behind an event while the main stream
-        # already scores the next batch into slot p ^ 1.  DESIGN.md §7 item 1.
-        side = torch.cuda.Stream(device=dev, priority=-1)
-        slots = [(ws, score), (_lib.TopKWorkspace(B, HW, K_TOP, dev), torch.empty_like(score))]
-        scored = [torch.cuda.Event() for _ in range(2)]
-        free = [torch.cuda.Event() for _ in range(2)]
-        turn = [0]
-
-        def step(i=None):
-            p = turn[0] & 1
-            turn[0] += 1
-            ws_p, score_p = slots[p]
-            main = torch.cuda.current_stream()
-            main.wait_event(free[p])  # the select + pick that used this slot two steps ago (no-op before its first record)
-            ws_p.prepare()
-            if i is not None:
-                ev_a[i].record()
-            _lib.acq_score(logits, STRATEGY, lab, void, out=score_p, hist0_ws=ws_p)
-            if i is not None:
-                ev_b[i].record()
-            scored[p].record(main)
-            with torch.cuda.stream(side):
-                side.wait_event(scored[p])
-                sel = _lib.acq_select_pick(score_p.view(B, HW), K_TOP, largest, pos, ws=ws_p, hist0_valid=True)
-                if world > 1 and i is not None:
-                    sel_round[i].copy_(sel)
-                free[p].record(side)
-            return sel
-    else:
-        side = None
-
-    def step_serial(i=None):
-        ws.prepare()
-        if i is not None:
-            ev_a[i].record()
-        _lib.acq_score(logits, STRATEGY, lab, void, out=score, hist0_ws=ws)
-        if i is not None:
-            ev_b[i].record()
-        if args.sorted_topk:  # materialise the whole sorted top-k list, then gather the drawn ranks
-            topk = _lib.acq_topk(score.view(B, HW), K_TOP, largest, ws=ws, hist0_valid=True)
-            sel = _lib.acq_gather(topk, pos)
-        else:  # what QuerySelector runs: only the n drawn ranks are needed (query.py:63-64) -> radix pick, no sort
-            sel = _lib.acq_select_pick(score.view(B, HW), K_TOP, largest, pos, ws=ws, hist0_valid=True)
-        if world > 1 and i is not None:
-            sel_round[i].copy_(sel)
-        return sel
-
-    if side is None:
-        step = step_serial
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(Wm):
-        step()
-    barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    l0 = lib.pp_launch_count()
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for i in range(K):
-        step(i)
-    if side is not None:  # the last steps' select + pick belong to the timed region
-        torch.cuda.current_stream().wait_stream(side)
-    if world > 1:  # the round's exchange, inside the timed region: per-rank picks -> every rank (rank 0 builds the dict)
-        dist.all_gather(gathered, sel_round)
-    t_end.record()
-    barrier()
-    launches = lib.pp_launch_count() - l0
-    ms_total = t_start.elapsed_time(t_end)
-    score_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ev_a, ev_b)]))
 
-    # ---- e2e: host buffers through the C-ABI session ------------------------------------------
-    Be = args.e2e_batch
-    h_logits, h_lab, h_void = synth(Be, 500 + rank, pin=True)
-    # one chunk per call: on this pod every host<->device copy pays ~0.9 ms before its first byte (scripts/bench_h2d.py),
-    # so one 650 MB logits copy (48.7 GiB/s) beats four 160 MB ones (33 GiB/s); the kernels take ~0.15 ms
-    sess = _lib.AcqSession(Be, C, H, W, K_TOP, N_SEL)
-    h_pos = torch.empty((Be, N_SEL), dtype=torch.int32).pin_memory()
-    h_sel = torch.empty((Be, N_SEL), dtype=torch.int32).pin_memory()
-
-    def e2e_step():
-        sess.begin(h_logits, h_lab, h_void, STRATEGY)  # H2D + score + select in flight ...
-        h_pos.numpy()[:] = np.stack([np.random.permutation(K_TOP)[:N_SEL] for _ in range(Be)])  # ... while the host draws
-        sess.finish(h_pos, h_sel)
-        return h_sel
-
-    Ke = max(3, min(K, 10))
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    le0 = lib.pp_launch_count()
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    launches_e2e = lib.pp_launch_count() - le0
-    barrier()
-    sess.close()
-    del logits, score, ws, h_logits
-    torch.cuda.empty_cache()
-
-    t = torch.tensor([ms_total, score_ms, e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, score_ms, e2e_s = [float(v) for v in t.cpu()]
-
-    # ---- train leg + model-in-the-loop query -------------------------------------------------------
-    train = None
-    qmodel = None
-    if not args.no_train:
-        train = {"metric": "train_images_per_sec", "unit": "images/s", "dtype": "bf16 (fp32 accumulate, fp32 master weights)",
-                 "config": "cityscapes 256x512, 10 labelled px/image, Adam lr 5e-4 (encoder lr/10) wd 2e-4, dropout on; "
-                           "synthetic batch resident in HBM (value) / pinned host -> H2D every step + loss D2H (e2e)"}
+    # ---- headline: RN50-DeepLabv3+ train step, throughput batch, graph replay; then the same through host batches ----
+    head = bench_train_graph("resnet", Bt, K, Wm, dev, world, mode="hbm")
+    e2e = bench_train_graph("resnet", Bt, K, Wm, dev, world, mode="e2e")
+    cfg = {"workload": WORKLOAD, "batch_per_gpu": Bt, "global_batch": Bt * world, "parallelism": f"dp{world}",
+           "step": "forward_lowres (bf16 NHWC, tcgen05 head) -> fused x4 upsample + sparse CE -> backward -> bucketed grad "
+                   "all-reduce from backward hooks -> Adam; ONE captured CUDA graph per step, dropout on, 10 labelled px/image",
+           "l2": "per-step working set (activations + 160 MB of fp32 gradients) far larger than the 126 MB L2; no flush needed",
+           "train_rn50_ms_per_step": head["ms_per_step"], "train_rn50_e2e_ms_per_step": e2e["ms_per_step"]}
+    extras = {}
+    if not args.no_extras:
         ts = max(5, min(K, 20))
-        for name, bb in (("mobilenetv2", "mobilenet"), ("resnet50", "resnet")):
-            train[f"{name}_b4"] = bench_train(bb, 4, ts, 5, dev, world)
-            train[f"{name}_b4_graph"] = bench_train_graph(bb, 4, ts, 5, dev, world)
-            train[f"{name}_b4_graph_e2e"] = bench_train_graph(bb, 4, ts, 5, dev, world, e2e=True)
-            train[f"{name}_b4_graph_loop"] = bench_train_graph(bb, 4, ts, 5, dev, world, loop=True)
-            train[f"{name}_b{args.train_batch}"] = bench_train(bb, args.train_batch, ts, 3, dev, world)
-            train[f"{name}_b{args.train_batch}_graph"] = bench_train_graph(bb, args.train_batch, ts, 3, dev, world)
-            train[f"{name}_b{args.train_batch}_graph_e2e"] = bench_train_graph(bb, args.train_batch, ts, 3, dev, world, e2e=True)
-            torch.cuda.empty_cache()
-        if rank == 0:
-            train["roofline_tensor"] = bench_conv_roofline(dev, tf_burst)
-            train["roofline_tensor"]["peak_source"] = peak_src + " bf16_tflops (burst; kernel timed alone)"
-            qmodel = {"unit": "Mpixels/s",
-                      "mobilenetv2_hbm": bench_query_model("mobilenet", 64, 5, dev, False),
-                      "mobilenetv2_host": bench_query_model("mobilenet", 64, 5, dev, True),
-                      "resnet50_hbm": bench_query_model("resnet", 32, 5, dev, False),
-                      "resnet50_host": bench_query_model("resnet", 32, 5, dev, True),
-                      "mobilenetv2_bs1_host": bench_query_model("mobilenet", 1, 50, dev, True),
-                      "resnet50_bs1_host": bench_query_model("resnet", 1, 50, dev, True),
-                      "resnet50_1024x2048_bs1_host": bench_query_model("resnet", 1, 10, dev, True, size=(1024, 2048)),
-                      "note": "bs1 = the reference's query loop (one image per forward, query.py:159-212); "
-                              "hbm/host = 64 (MobileNetV2) / 32 (ResNet-50) images per step"}
-    barrier()
+        r4 = bench_train_graph("resnet", 4, ts, 5, dev, world, mode="hbm")
+        r4e = bench_train_graph("resnet", 4, ts, 5, dev, world, mode="e2e")
+        m32 = bench_train_graph("mobilenet", Bt, ts, 5, dev, world, mode="hbm")
+        m4 = bench_train_graph("mobilenet", 4, ts, 5, dev, world, mode="hbm")
+        m4l = bench_train_graph("mobilenet", 4, ts, 5, dev, world, mode="loop")
+        cfg.update({"train_rn50_b4_img_s": r4["value"], "train_rn50_b4_e2e_img_s": r4e["value"],
+                    f"train_mnv2_b{Bt}_img_s": m32["value"], "train_mnv2_b4_img_s": m4["value"],
+                    "train_mnv2_b4_loop_img_s": m4l["value"]})
+        extras["train"] = {"resnet50_b4": r4, "resnet50_b4_e2e": r4e, f"mobilenetv2_b{Bt}": m32, "mobilenetv2_b4": m4,
+                           "mobilenetv2_b4_loop": m4l}
+    # ---- query with the model in the loop, through QuerySelector.__call__ (host images in, dict of picks out) ----
+    if not args.no_query:
+        q_rn = bench_query_selector("resnet", args.query_images * world, dev, world, tmpdir)
+        cfg.update({"query_rn50_mpix_s": q_rn["value"], "query_rn50_img_s": q_rn["images_per_s"], "query_images": q_rn["images"]})
+        extras["query_model"] = {"resnet50": q_rn}
+        if not args.no_extras:
+            q_mn = bench_query_selector("mobilenet", args.query_images * world, dev, world, tmpdir)
+            cfg["query_mnv2_mpix_s"] = q_mn["value"]
+            extras["query_model"]["mobilenetv2"] = q_mn
+            if rank == 0 and world == 1:
+                b1 = bench_query_model("resnet", 1, 50, dev, True)
+                cfg["query_rn50_bs1_mpix_s"] = b1["value"]  # the reference's own query batch (one image per forward)
+    # ---- acquisition kernels alone (north star: >= 80 % of the HBM roofline on the fused scoring kernel) ----
+    acq = bench_acq_pipeline(args.acq_batch, K, Wm, dev, world, rank, overlap=args.overlap_select)
+    HW = H * W
+    alg = args.acq_batch * HW * ALG_BYTES_PER_PX
+    achieved = alg / (acq["score_ms"] / 1e3) / 1e9
+    cfg.update({"acq_images_per_step_per_gpu": args.acq_batch, "acq_step_ms": acq["ms_per_step"], "acq_step_gpix_s": acq["mpix_s"] / 1e3,
+                "acq_step_frac_of_hbm": alg / (acq["ms_per_step"] / 1e3) / 1e9 / hbm_peak,
+                "acq_select": "radix select + order statistics at the drawn ranks; " +
+                              ("select+pick of step i on a side stream under the scoring of step i+1" if args.overlap_select else "one stream")})
+    roof = {"kernel": "acq_score_vec_kernel<19, margin, f32, fused hist0>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": acq["score_ms"],
+            "alg_bytes_per_launch": alg, "share_of_acq_step": acq["score_ms"] / acq["ms_per_step"]}
+    if rank == 0 and not args.no_extras:
+        conv = bench_conv_roofline(dev, tf_burst)
+        cfg.update({"conv_seghead_tflops": conv["achieved"], "conv_seghead_frac_of_bf16_peak": conv["frac"]})
+        extras["roofline_tensor"] = conv
+        if args.sweep and world == 1:
+            extras["strategy_sweep_1024x2048"] = bench_strategy_sweep(dev, hbm_peak)
+    _barrier(world)
     clk = clocks.stop() if rank == 0 else None
 
     if rank == 0:
-        value = world * B * HW * K / 1e6 / (ms_total / 1e3)
-        achieved = B * HW * ALG_BYTES_PER_PX / (score_ms / 1e3) / 1e9
-        e2e_val = world * Be * HW * Ke / 1e6 / e2e_s
-        h2d = Be * (C * HW * 4 + 2 * HW + N_SEL * 4)
-        d2h = Be * N_SEL * 4
         out = {
-            "metric": "query_mpixels_per_sec", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": K,
-            "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "images_per_step_per_gpu": B, "e2e_images_per_step_per_gpu": Be,
-                       "selection": "sorted top-k list + gather" if args.sorted_topk else "radix select + order statistics at the drawn ranks (no sort; identical picks)"
-                                    + ("; select + pick of step i overlapped with the scoring of step i+1 (side stream)" if side is not None else ""),
-                       "l2": f"inputs larger than L2 ({B * C * HW * 4 / 1e6:.0f} MB of logits per step)",
-                       "parallelism": f"images sharded over {world} rank(s); one all_gather of the round's picks "
-                                      f"({K} steps = one query round)" if world > 1 else "single GPU"},
-            "roofline": {"kernel": "acq_score_vec_kernel<19, margin, f32, fused hist0>", "bound": "hbm",
-                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": score_ms,
-                         "alg_bytes_per_launch": B * HW * ALG_BYTES_PER_PX,
-                         "share_of_step": score_ms / (ms_total / K)},
-            "e2e": {"value": e2e_val, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3,
-                    "api": "pp_acq_session_begin_host / finish_host (pinned host buffers) + host np.random.permutation draws "
-                           "overlapped with the H2D copy"},
-            "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
+            "metric": "train_images_per_sec", "value": head["value"], "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "gpu_launches": int(round(head["launches_per_step"] * K)),
+            "config": cfg, "roofline": roof,
+            "e2e": {"value": e2e["value"], "unit": "images/s", "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": e2e["d2h_bytes_per_step"], "ms_per_step": e2e["ms_per_step"],
+                    "api": "GraphedTrainStep.prefetch/commit/replay as Model._train_epoch drives it: pinned host batch -> H2D on a "
+                           "copy stream under the previous step, loss read back every step"},
             "clocks": clk,
         }
-        if train is not None:
-            out["train"] = train
-            out["query_model"] = qmodel
-            out["strategy_sweep_1024x2048"] = bench_strategy_sweep(dev, hbm_peak)
-        if not args.no_cpu_baseline and world == 1:  # the contract: CPU baseline on rank 0 at N=1 only
-            threads = os.cpu_count() or 1
-            n_cpu = 32
-            rate, times = cpu_query_rate(n_cpu, 3, threads)
-            out["cpu_baseline"] = {"value": rate, "unit": "Mpixels/s", "cores": threads, "kind": "port",
-                                   "sample": f"{n_cpu} images of the same workload x 3 repetitions (best), "
-                                             f"oracle port of query.py:159-212 on torch CPU + NumPy, {sum(times):.1f} s"}
-            if train is not None:
-                qm, qdt = cpu_query_model_rate("mobilenet", 8, threads)
-                out["query_model"]["cpu_baseline"] = {"value": qm, "unit": "Mpixels/s", "cores": threads, "kind": "port",
-                                                      "sample": f"MobileNetV2-DeepLab forward + query, 8 images one per forward "
-                                                                f"(oracle port, fp32 torch CPU), {qdt:.1f} s"}
-                r_mn, t_mn = cpu_train_rate("mobilenet", 4, 2, threads)
-                out["train"]["cpu_baseline"] = {"value": r_mn, "unit": "images/s", "cores": threads, "kind": "port",
-                                                "sample": f"MobileNetV2-DeepLab B=4, 2 timed steps of the oracle train "
-                                                          f"step (fp32 torch CPU, Adam), {sum(t_mn):.1f} s"}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                tj = json.load(open(tpath))
-                out["roofline"]["traffic"] = tj.get("acq_score_bytes_per_px") * B * HW
-                if train is not None and tj.get("conv_d1_b32_bytes"):
-                    out["train"]["roofline_tensor"]["traffic"] = tj.get("conv_d1_b32_bytes")
+                out["roofline"]["traffic"] = json.load(open(tpath)).get("acq_score_bytes_per_px") * args.acq_batch * HW
+                out["roofline"]["traffic_source"] = "ncu --set full capture of the same launch (profiles/), not re-measured in this run"
             except Exception:
                 pass
-        print(json.dumps(out))
+        if not args.no_cpu_baseline and world == 1:  # the contract: CPU baseline on rank 0 at N=1 only
+            threads = os.cpu_count() or 1
+            r_rn, t_rn = cpu_train_rate("resnet", 4, 2, threads)
+            out["cpu_baseline"] = {"value": r_rn, "unit": "images/s", "cores": threads, "kind": "port",
+                                   "sample": f"RN50-DeepLabv3+ B=4, 2 timed steps of the oracle train step (fp32 torch CPU, Adam, "
+                                             f"dropout on), {sum(t_rn):.1f} s"}
+            if not args.no_query:
+                qm, qdt = cpu_query_model_rate("resnet", 2, threads)
+                out["config"]["cpu_query_rn50_mpix_s"] = qm
+        out.update(extras)
+        print(json.dumps(_round_tree(out), separators=(",", ":")))
     if world > 1:
         dist.destroy_process_group()
 

@@ -176,3 +176,91 @@ def sparse_ce_loss(pred, y, queries, ignore_index):
     y = y.clone()
     y.flatten()[~queries.flatten().bool()] = ignore_index
     return F.cross_entropy(pred, y, ignore_index=ignore_index)
+
+
+def reference_init_state_dict(shapes: dict, seed: int = 0) -> dict:
+    """Host-independent weights with the DISTRIBUTIONS of the reference's own initialisation (torch's seeded CPU normal
+    stream depends on the host's vector width, NumPy's RandomState does not): MobileNetV2 / ASPP / SegmentHead conv
+    weights kaiming-normal, std = sqrt(2 / fan_in) (mobilenet_v2.py:149-155, aspp.py:81-88, decoders.py:125-132);
+    ResNet conv weights N(0, sqrt(2 / (k*k*out))) (resnet_models.py:131-137); low_level_conv and every conv bias keep
+    nn.Conv2d's default U(-1/sqrt(fan_in), 1/sqrt(fan_in)) (deeplab.py:23-26); BatchNorm weight 1 / bias 0, running
+    statistics 0 / 1.  This is the well-conditioned network a real run starts from (unlike synthetic_state_dict, whose
+    random BatchNorm scales are a stress case)."""
+    import numpy as np
+    sd = {}
+    canon_cache = {}
+    for name in sorted(shapes):
+        shape = tuple(shapes[name])
+        canon = name
+        for alias in ("backbone.low_level_features.", "backbone.high_level_features."):
+            if name.startswith(alias):
+                idx, rest = name[len(alias):].split(".", 1)
+                canon = f"backbone.features.{int(idx)}.{rest}"
+        if canon in canon_cache:
+            sd[name] = canon_cache[canon].clone()
+            continue
+        rs = np.random.RandomState((zlib.crc32(canon.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
+        if name.endswith("num_batches_tracked"):
+            t = torch.zeros(shape, dtype=torch.long)
+        elif name.endswith("running_var"):
+            t = torch.ones(shape)
+        elif name.endswith("running_mean"):
+            t = torch.zeros(shape)
+        elif len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            if canon.startswith("low_level_conv."):
+                b = 1.0 / fan_in ** 0.5
+                t = torch.from_numpy(rs.uniform(-b, b, size=shape).astype(np.float32))
+            elif canon.startswith("backbone.") and ("layer" in canon or "prefix" in canon):
+                std = (2.0 / (shape[2] * shape[3] * shape[0])) ** 0.5
+                t = torch.from_numpy((rs.standard_normal(size=shape) * std).astype(np.float32))
+            else:
+                t = torch.from_numpy((rs.standard_normal(size=shape) * (2.0 / fan_in) ** 0.5).astype(np.float32))
+        elif canon == "seg_head.classifier.bias":
+            b = 1.0 / 256 ** 0.5
+            t = torch.from_numpy(rs.uniform(-b, b, size=shape).astype(np.float32))
+        elif name.endswith("weight"):
+            t = torch.ones(shape)
+        else:
+            t = torch.zeros(shape)
+        canon_cache[canon] = t
+        sd[name] = t
+    return sd
+
+
+def train_steps(sd, batches, backbone, ignore_index, lr=5e-4, weight_decay=2e-4, drop=(0.0, 0.0, 0.0)):
+    """k optimisation steps of model.py:103-122 (one per (x, y, queries) batch) with the cs optimiser of
+    utils/utils.py:117-141 (Adam, encoder lr/10, torch default betas/eps) on a COPY of `sd`; BatchNorm running statistics
+    are updated like nn.BatchNorm2d does.  Returns (new state dict, [loss_k], gradients of step 0 by name)."""
+    sd = {k: v.clone() for k, v in sd.items()}
+    names = [k for k in sorted(sd) if sd[k].dtype.is_floating_point and not k.endswith(("running_mean", "running_var"))
+             and not k.startswith(("backbone.low_level_features.", "backbone.high_level_features."))]
+    for k in names:
+        sd[k].requires_grad_(True)
+    enc = [sd[k] for k in names if k.startswith("backbone.")]
+    rest = [sd[k] for k in names if not k.startswith("backbone.")]
+    opt = torch.optim.Adam([{"params": enc, "lr": lr / 10, "weight_decay": weight_decay},
+                            {"params": rest, "lr": lr, "weight_decay": weight_decay}])
+    losses, grads0 = [], None
+    for i, (x, y, q) in enumerate(batches):
+        out = deeplab_forward(sd, x, backbone=backbone, training=True, drop=drop, return_ctx=True)
+        loss = sparse_ce_loss(out["pred"], y, q, ignore_index)
+        opt.zero_grad()
+        loss.backward()
+        if i == 0:
+            grads0 = {k: sd[k].grad.detach().clone() for k in names}
+        opt.step()
+        losses.append(float(loss))
+        with torch.no_grad():
+            for prefix, (rm, rv) in out["ctx"].new_stats.items():
+                sd[prefix + ".running_mean"].copy_(rm)
+                sd[prefix + ".running_var"].copy_(rv)
+                if prefix + ".num_batches_tracked" in sd:
+                    sd[prefix + ".num_batches_tracked"] += 1
+            # MobileNetV2's aliased registrations follow their canonical tensors
+            for k in sd:
+                for alias in ("backbone.low_level_features.", "backbone.high_level_features."):
+                    if k.startswith(alias):
+                        idx, rest_k = k[len(alias):].split(".", 1)
+                        sd[k] = sd[f"backbone.features.{int(idx)}.{rest_k}"]
+    return {k: v.detach() for k, v in sd.items()}, losses, grads0
