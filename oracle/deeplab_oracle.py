@@ -50,18 +50,59 @@ def synthetic_state_dict(shapes: dict, seed: int = 0) -> dict:
     return sd
 
 
+class _RoundStorage(torch.autograd.Function):
+    """x -> x rounded to `dtype` and back to fp32, in BOTH directions (the activation and its gradient are stored in
+    `dtype` between layers).  Used only by the storage-precision mode below."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.dtype = dtype
+        return x.to(dtype).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dtype).float(), None
+
+
+class _RoundWeight(torch.autograd.Function):
+    """forward: the bf16 operand copy of an fp32 master weight; backward: identity (weight gradients are fp32)."""
+
+    @staticmethod
+    def forward(ctx, w, dtype):
+        return w.to(dtype).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
 class _Ctx:
-    def __init__(self, sd, training, dropout_p_scale=1.0):
+    """storage_dtype = None: the reference's fp32 arithmetic, exactly.  storage_dtype = torch.bfloat16: the SAME graph with
+    every activation (and, in training, its gradient) rounded to bf16 where a layer hands it to the next one - after each
+    BatchNorm (+ activation: ReLU / ReLU6 commute with the rounding) - and dense conv weights rounded to bf16, everything
+    else (accumulation, statistics, normalisation) in fp32.  That is the error a bf16-STORAGE implementation of the reference
+    carries by construction; the GPU parity tests bound the CUDA path by it (error budget)."""
+
+    def __init__(self, sd, training, dropout_p_scale=1.0, storage_dtype=None):
         self.sd, self.training = sd, training
         self.new_stats = {}
+        self.storage_dtype = storage_dtype
+        if storage_dtype is not None:
+            self.sd = {k: (_RoundWeight.apply(v, storage_dtype) if v.dim() == 4 and v.shape[1] > 1 and v.is_floating_point() else v)
+                       for k, v in sd.items()}  # dense conv weights; depthwise (in/groups = 1) weights stay fp32 as in the kernels
+
+    def store(self, x):
+        return x if self.storage_dtype is None else _RoundStorage.apply(x, self.storage_dtype)
 
     def bn(self, x, prefix, eps=1e-5, momentum=0.1):
         sd = self.sd
+        if self.training:
+            x = self.store(x)  # training keeps the raw conv output (BatchNorm's input) for the backward pass: stored too
         rm, rv = sd[prefix + ".running_mean"].clone(), sd[prefix + ".running_var"].clone()
         y = F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], self.training, momentum, eps)
         if self.training:
             self.new_stats[prefix] = (rm, rv)
-        return y
+        return self.store(y)
 
 
 def _fixed_padding(x, dilation):  # mobilenet_v2.py:15-21
@@ -95,7 +136,7 @@ def mobilenet_v2(c: _Ctx, x, output_stride=16):
                 j = 3
             y = F.relu6(c.bn(F.conv2d(y, sd[q + f"{j}.weight"], None, st, 0, dil, hidden), q + f"{j + 1}"))
             y = c.bn(F.conv2d(y, sd[q + f"{j + 3}.weight"]), q + f"{j + 4}")
-            x = x + y if (st == 1 and inp == ch) else y
+            x = c.store(x + y) if (st == 1 and inp == ch) else y
             inp = ch
             if idx == 3:
                 low = x  # features[0:4]
@@ -123,7 +164,7 @@ def resnet50_dilated8(c: _Ctx, x, prefix="backbone."):
             y = c.bn(F.conv2d(y, sd[q + "conv3.weight"]), q + "bn3")
             if q + "downsample.0.weight" in sd:
                 idn = c.bn(F.conv2d(x, sd[q + "downsample.0.weight"], None, stride), q + "downsample.1")
-            x = F.relu(y + idn)
+            x = c.store(F.relu(y + idn))
         if li == 1:
             c2 = x
     return x, c2
@@ -154,9 +195,11 @@ def head(c: _Ctx, high, low, dilations, drop=(0.0, 0.0, 0.0)):
     return pred, emb
 
 
-def deeplab_forward(sd, x, backbone="mobilenet", training=False, drop=(0.0, 0.0, 0.0), return_ctx=False):
-    """deeplab.py:43-61 -> dict(pred=[B,C,H,W] full-res logits, lowres=[B,C,H/4,W/4] head logits)."""
-    c = _Ctx(sd, training)
+def deeplab_forward(sd, x, backbone="mobilenet", training=False, drop=(0.0, 0.0, 0.0), return_ctx=False, storage_dtype=None):
+    """deeplab.py:43-61 -> dict(pred=[B,C,H,W] full-res logits, lowres=[B,C,H/4,W/4] head logits).
+    storage_dtype: see _Ctx (None = the reference's fp32 path)."""
+    c = _Ctx(sd, training, storage_dtype=storage_dtype)
+    x = c.store(x)
     if backbone == "mobilenet":
         high, low = mobilenet_v2(c, x)
         dil = [1, 6, 12, 18]
@@ -228,7 +271,7 @@ def reference_init_state_dict(shapes: dict, seed: int = 0) -> dict:
     return sd
 
 
-def train_steps(sd, batches, backbone, ignore_index, lr=5e-4, weight_decay=2e-4, drop=(0.0, 0.0, 0.0)):
+def train_steps(sd, batches, backbone, ignore_index, lr=5e-4, weight_decay=2e-4, drop=(0.0, 0.0, 0.0), storage_dtype=None):
     """k optimisation steps of model.py:103-122 (one per (x, y, queries) batch) with the cs optimiser of
     utils/utils.py:117-141 (Adam, encoder lr/10, torch default betas/eps) on a COPY of `sd`; BatchNorm running statistics
     are updated like nn.BatchNorm2d does.  Returns (new state dict, [loss_k], gradients of step 0 by name)."""
@@ -243,14 +286,14 @@ def train_steps(sd, batches, backbone, ignore_index, lr=5e-4, weight_decay=2e-4,
                             {"params": rest, "lr": lr, "weight_decay": weight_decay}])
     losses, grads0 = [], None
     for i, (x, y, q) in enumerate(batches):
-        out = deeplab_forward(sd, x, backbone=backbone, training=True, drop=drop, return_ctx=True)
+        out = deeplab_forward(sd, x, backbone=backbone, training=True, drop=drop, return_ctx=True, storage_dtype=storage_dtype)
         loss = sparse_ce_loss(out["pred"], y, q, ignore_index)
         opt.zero_grad()
         loss.backward()
         if i == 0:
             grads0 = {k: sd[k].grad.detach().clone() for k in names}
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
         with torch.no_grad():
             for prefix, (rm, rv) in out["ctx"].new_stats.items():
                 sd[prefix + ".running_mean"].copy_(rm)

@@ -140,6 +140,31 @@ class QueryStats:
         pkl.dump(dict_stats, open(f"{self.dir_checkpoints}/{nth_query}_query/query_stats.pkl", "wb"))
 
 
+class _Slot:
+    """Host staging of one batch (pinned when a GPU is present): images and masks are written straight into these buffers as
+    the loader yields them (no torch.cat, no pageable copies) and go up with ONE async copy each.  Two slots alternate, so
+    the host fills batch i+1 while the GPU works on batch i."""
+
+    def __init__(self, n, x_shape, hw, pin):
+        def mk(shape, dt):
+            return torch.empty(shape, dtype=dt, pin_memory=pin)
+        self.x = mk((n,) + tuple(x_shape), torch.float32)
+        self.lab = mk((n,) + tuple(hw), torch.uint8)
+        self.void = mk((n,) + tuple(hw), torch.uint8)
+        self.event = None
+
+
+class _Batch:
+    """one batch in flight: its items (host bookkeeping), staging slot, device intermediates and pinned results"""
+
+    def __init__(self, slot, hw, x_shape):
+        self.items, self.slot, self.hw, self.x_shape = [], slot, hw, x_shape
+        self.score = self.handle = self.ws = None
+        self.n_top = 0
+        self.stats_on = False
+        self.sel_host = self.ent_host = self.done = None
+
+
 class QuerySelector:
     """Drop-in for the reference QuerySelector (query.py:12-221)."""
 
@@ -259,60 +284,134 @@ class QuerySelector:
         score = _lib.acq_score(pred, st, labelled, void, keep, hist0_ws=ws)
         return score, ("full", pred)
 
-    def _flush(self, model, batch, human_labels, dict_queries, stats_on):
-        xs = torch.cat([b["x"] for b in batch], dim=0).to(self.device, non_blocking=True)
-        h, w = batch[0]["hw"]
-        n = len(batch)
+    # ---- batches: pinned staging, asynchronous launch, deferred collection --------------------------------------
+    def _slot_for(self, x_shape, hw):
+        """one of two alternating staging slots for batches of this geometry (host fills one while the GPU reads the other)"""
+        key = (self.batch_imgs, tuple(x_shape), tuple(hw), self.n_pixels_by_us)
+        if getattr(self, "_slot_key", None) != key:
+            pin = self.device.type == "cuda" and torch.cuda.is_available()
+            self._slots = [_Slot(self.batch_imgs, x_shape, hw, pin) for _ in range(2)]
+            self._slot_key, self._slot_turn = key, 0
+        slot = self._slots[self._slot_turn & 1]
+        self._slot_turn += 1
+        if slot.event is not None:
+            slot.event.synchronize()  # the upload that last used this slot (two batches ago) has read it
+        return slot
+
+    def _add(self, batch, item, x, mask, human_labels):
+        """write one image's inputs straight into the batch's staging slot"""
+        j = len(batch.items)
+        s = batch.slot
+        s.x[j].copy_(x[0])
+        lab = s.lab[j].numpy()
+        if human_labels:
+            np.not_equal(mask, self.ignore_index, out=lab.view(bool))
+        else:
+            lab[...] = mask
+        if item["y"] is not None:
+            np.equal(item["y"], self.ignore_index, out=s.void[j].numpy().view(bool))  # query.py:196-201: void pixels
+        batch.items.append(item)
+
+    def _launch(self, model, batch, pick):
+        """H2D + forward + fused scoring (+ select / pick when the drawn ranks are known) for one batch, all asynchronous."""
+        n = len(batch.items)
+        h, w = batch.hw
         hw = h * w
-        k = self._k(h, w)
         st = self.query_strategy
+        s = batch.slot
+        dev = self.device
+        xs = s.x[:n].to(dev, non_blocking=True)
+        labelled = s.lab[:n].to(dev, non_blocking=True).view(torch.bool)
+        has_y = batch.items[0]["y"] is not None
+        void = s.void[:n].to(dev, non_blocking=True).view(torch.bool) if has_y else None
+        if dev.type == "cuda":
+            if s.event is None:
+                s.event = torch.cuda.Event()
+            s.event.record()
         if self.dataset_name == "voc":  # query.py:171-174
             pad_h = ceil(h / self.stride_total) * self.stride_total - h
             pad_w = ceil(w / self.stride_total) * self.stride_total - w
             xs = F.pad(xs, pad=(0, pad_w, 0, pad_h), mode="reflect")
-        lab = np.stack([b["mask"] for b in batch])
-        labelled = torch.from_numpy((lab != self.ignore_index) if human_labels else lab.astype(bool)).to(self.device)
-        void = None
-        if batch[0]["y"] is not None:
-            void = torch.from_numpy(np.stack([b["y"] == self.ignore_index for b in batch])).to(self.device)
-        # drawn per image when the loop saw it (dataloader order, on every rank): query.py:40,64
-        keep_np = None if batch[0]["keep"] is None else np.concatenate([b["keep"] for b in batch])
-        pos_np = None if batch[0]["pos"] is None else np.concatenate([b["pos"] for b in batch])
-        keep = None if keep_np is None else torch.from_numpy(keep_np).to(self.device)
-        n_top = self.n_pixels_by_us if self.reverse_order else k
-        largest = _lib.LARGEST[st]
-        pos_t = None if pos_np is None else torch.from_numpy(pos_np)
+        keep_np = None if batch.items[0]["keep"] is None else np.concatenate([b["keep"] for b in batch.items])
+        keep = None if keep_np is None else torch.from_numpy(keep_np).to(dev)
+        batch.n_top = self.n_pixels_by_us if self.reverse_order else self._k(h, w)
         if st == "random":
-            uc = torch.stack([b["rand"] for b in batch]).to(self.device)
+            uc = torch.stack([b["rand"] for b in batch.items]).to(dev)
             excl = labelled if void is None else (labelled | void)
             if keep is not None:
                 excl = excl | ~keep.view(n, h, w)
             uc[excl] = _lib.FILL[st]
-            sel = _lib.acq_select_pick(uc.view(n, hw), n_top, largest, pos_t, n=self.n_pixels_by_us)
-            handle = None
+            batch.score, batch.handle, batch.ws = uc.view(n, hw), None, None
         else:
-            ws = self._workspace(n, hw, n_top)
-            ws.prepare()
-            score, handle = self._score_batch(model, xs, h, w, labelled, void, keep, ws)
-            # only the n drawn ranks of the sorted top-k are needed (query.py:63-64): radix pick, no sort
-            sel = _lib.acq_select_pick(score.view(n, hw), n_top, largest, pos_t, n=self.n_pixels_by_us, ws=ws, hist0_valid=True)
+            # immediate mode: one workspace per geometry (stream order protects it); deferred picks: one per batch, its
+            # level-0 histogram must survive until the ranks are drawn
+            batch.ws = self._workspace(n, hw, batch.n_top) if pick else _lib.TopKWorkspace(n, hw, batch.n_top, dev)
+            batch.ws.prepare()
+            score, batch.handle = self._score_batch(model, xs, h, w, labelled, void, keep, batch.ws)
+            batch.score = score.view(n, hw)
+        if pick:
+            self._pick(batch)
+
+    def _pick(self, batch):
+        """select + order statistics at the drawn ranks, entropy at the picks, results -> pinned host buffers (async)"""
+        n = len(batch.items)
+        h, w = batch.hw
+        st = self.query_strategy
+        largest = _lib.LARGEST[st]
+        pos_np = None if batch.items[0]["pos"] is None else np.concatenate([b["pos"] for b in batch.items])
+        pos_t = None if pos_np is None else torch.from_numpy(pos_np)
+        # only the n drawn ranks of the sorted top-k are needed (query.py:63-64): radix pick, no sort
+        if batch.ws is None:
+            sel = _lib.acq_select_pick(batch.score, batch.n_top, largest, pos_t, n=self.n_pixels_by_us)
+        else:
+            sel = _lib.acq_select_pick(batch.score, batch.n_top, largest, pos_t, n=self.n_pixels_by_us, ws=batch.ws, hist0_valid=True)
         sel, _ = torch.sort(sel.long(), dim=1)  # np.where order: row-major ascending (query.py:77)
         ent = None
-        if stats_on and handle is not None:
-            kind, t = handle
-            ent = (_lib.acq_entropy_at_upsampled(t, (h, w), sel) if kind == "lowres"
-                   else _lib.acq_entropy_at(t, sel)).cpu().numpy()
-        sel_np = sel.cpu().numpy()
+        if batch.stats_on and batch.handle is not None:
+            kind, t = batch.handle
+            ent = _lib.acq_entropy_at_upsampled(t, (h, w), sel) if kind == "lowres" else _lib.acq_entropy_at(t, sel)
+        pin = sel.is_cuda
+        batch.sel_host = torch.empty(sel.shape, dtype=sel.dtype, pin_memory=pin)
+        batch.sel_host.copy_(sel, non_blocking=True)
+        batch.ent_host = None
+        if ent is not None:
+            batch.ent_host = torch.empty(ent.shape, dtype=ent.dtype, pin_memory=pin)
+            batch.ent_host.copy_(ent, non_blocking=True)
+        batch.done = torch.cuda.Event() if pin else None
+        if batch.done is not None:
+            batch.done.record()
+        batch.score = batch.handle = batch.ws = None  # device buffers go back to the allocator (stream-ordered)
+
+    def _collect(self, batch, dict_queries):
+        """wait for one launched batch and do its host bookkeeping: wire-format entries + QueryStats"""
+        if batch.done is not None:
+            batch.done.synchronize()
+        h, w = batch.hw
+        sel_np = batch.sel_host.numpy()
+        ent = None if batch.ent_host is None else batch.ent_host.numpy()
         n_new = 0
-        for i, b in enumerate(batch):
+        for i, b in enumerate(batch.items):
             idx = sel_np[i]
-            info = {"height": h, "width": w, "x_coords": idx % w, "y_coords": idx // w}
-            dict_queries[b["p_img"]] = info
+            dict_queries[b["p_img"]] = {"height": h, "width": w, "x_coords": idx % w, "y_coords": idx // w}
             n_new += idx.size
-            if stats_on:
+            if batch.stats_on:
                 e = ent[i] if ent is not None else np.full(idx.size, np.nan)
                 self.query_stats.update_selected(idx, w, b["y"], e)
         return n_new
+
+    def _own_loader(self, world, rank):
+        """multi-GPU: a loader over THIS rank's images only (image i -> rank i % world), built from the caller's loader, so a
+        rank reads 1/world of the dataset instead of all of it.  None when the loader cannot be re-targeted (not a map-style
+        DataLoader in sequential order with batch_size 1) - the caller then walks the whole loader."""
+        from torch.utils.data import DataLoader, IterableDataset, SequentialSampler, Subset
+        dl = self.dataloader
+        if not isinstance(dl, DataLoader) or isinstance(dl.dataset, IterableDataset) or dl.batch_size != 1 \
+                or not isinstance(dl.sampler, SequentialSampler):
+            return None
+        idx = list(range(rank, len(dl.dataset), world))
+        sub = DataLoader(Subset(dl.dataset, idx), batch_size=1, shuffle=False, num_workers=dl.num_workers,
+                         collate_fn=dl.collate_fn, pin_memory=dl.pin_memory)
+        return sub, idx
 
     def __call__(self, nth_query, model, human_labels: bool = False):
         if human_labels:
@@ -326,39 +425,99 @@ class QuerySelector:
         print(f"Choosing pixels by {self.query_strategy}")
         n_pixels, n_imgs = 0, 0
         dict_queries: dict = dict()
-        y = None
-        batch: List[dict] = []
         world, rank = ppdist.world(), ppdist.rank()
-        order: List[str] = []      # every image path in dataloader order (all ranks walk the whole loader)
+        order: List[str] = []      # every image path in dataloader order
         mine: List[int] = []       # dataloader positions of the images this rank scores
         self.query_stats.begin_round()
+        # Multi-GPU fast path: every rank loads and scores ONLY its own images; the random ranks - which the reference draws
+        # from the global NumPy stream once per image in dataloader order (query.py:40,64) and which depend on every image's
+        # size - are drawn after ONE small all-gather of the image sizes, then the picks are finished.  The draws are the
+        # same numbers in the same order as in a single process (a query dataset draws nothing itself:
+        # base_dataset.py:172-181).  reverse_order / random need their draws BEFORE scoring and keep the walk-everything path.
+        own = None
+        if world > 1 and not self.reverse_order and self.query_strategy != "random":
+            own = self._own_loader(world, rank)
+        any_y = [False]
+        launched: List[_Batch] = []   # launched, not yet collected (immediate mode: at most one in flight)
+        scored: List[_Batch] = []     # deferred mode: scored, waiting for their ranks
+        cur = [None]
+
+        def close_batch(pick):
+            b = cur[0]
+            cur[0] = None
+            if b is None or not b.items:
+                return
+            b.stats_on = not human_labels and b.items[0]["y"] is not None
+            self._launch(model, b, pick)
+            if pick:
+                launched.append(b)
+                while len(launched) > 1:  # collect the PREVIOUS batch while this one runs
+                    nonlocal_counts[0] += self._collect(launched.pop(0), dict_queries)
+            else:
+                scored.append(b)
+
+        nonlocal_counts = [0]
+
+        def feed(batch_ind, dict_data, keep, pos, rand, pick):
+            x = dict_data["x"]
+            y = dict_data.get("y", None)
+            h, w = tuple(x.shape[2:])
+            if y is not None:
+                y = y.squeeze(dim=0).numpy()
+                any_y[0] = True
+            item = {"y": y, "hw": (h, w), "p_img": dict_data["p_img"][0], "keep": keep, "pos": pos, "rand": rand, "gpos": batch_ind}
+            b = cur[0]
+            if b is not None and (b.hw != (h, w) or b.x_shape != tuple(x.shape[1:]) or len(b.items) == self.batch_imgs
+                                  or (b.items[0]["y"] is None) != (y is None)):
+                close_batch(pick)
+                b = None
+            if b is None:
+                b = cur[0] = _Batch(self._slot_for(x.shape[1:], (h, w)), (h, w), tuple(x.shape[1:]))
+            self._add(b, item, x, np.asarray(prev_queries[batch_ind]), human_labels)
+            mine.append(batch_ind)
+
         with torch.no_grad():
-            for batch_ind, dict_data in enumerate(self.dataloader):
-                x = dict_data["x"]
-                y = dict_data.get("y", None)
-                h, w = tuple(x.shape[2:])
-                # the random numbers of EVERY image are drawn here, in dataloader order, on every rank (query.py:40,64 and
-                # UncertaintySampler._random): the streams, hence the picks, do not depend on the world size
-                keep, pos = self._draw_positions(1, h, w)
-                rand = self.uncertainty_sampler(torch.empty(1, 1, h, w))[0] if self.query_strategy == "random" else None
-                order.append(dict_data["p_img"][0])
-                n_imgs += 1
-                if batch_ind % world != rank:
-                    continue
-                if y is not None:
-                    y = y.squeeze(dim=0).numpy()
-                item = {"x": x, "y": y, "mask": np.asarray(prev_queries[batch_ind]), "hw": (h, w), "p_img": order[-1],
-                        "keep": keep, "pos": pos, "rand": rand}
-                if batch and (item["hw"] != batch[0]["hw"] or len(batch) == self.batch_imgs):
-                    n_pixels += self._flush(model, batch, human_labels, dict_queries, not human_labels and batch[0]["y"] is not None)
-                    batch = []
-                batch.append(item)
-                mine.append(batch_ind)
-            if batch:
-                n_pixels += self._flush(model, batch, human_labels, dict_queries, not human_labels and batch[0]["y"] is not None)
+            if own is None:
+                for batch_ind, dict_data in enumerate(self.dataloader):
+                    h, w = tuple(dict_data["x"].shape[2:])
+                    # the random numbers of EVERY image are drawn here, in dataloader order, on every rank (query.py:40,64
+                    # and UncertaintySampler._random): the streams, hence the picks, do not depend on the world size
+                    keep, pos = self._draw_positions(1, h, w)
+                    rand = self.uncertainty_sampler(torch.empty(1, 1, h, w))[0] if self.query_strategy == "random" else None
+                    order.append(dict_data["p_img"][0])
+                    n_imgs += 1
+                    if batch_ind % world != rank:
+                        continue
+                    feed(batch_ind, dict_data, keep, pos, rand, pick=True)
+                close_batch(pick=True)
+            else:
+                loader, positions = own
+                for j, dict_data in enumerate(loader):
+                    feed(positions[j], dict_data, None, None, None, pick=False)
+                close_batch(pick=False)
+                # ONE small exchange: (position, height, width, path) of every image -> the draws, in dataloader order
+                sizes = [(it["gpos"], it["hw"][0], it["hw"][1], it["p_img"]) for b in scored for it in b.items]
+                everyone = sorted(s for part in ppdist.all_gather_objects(sizes) for s in part)
+                draws = {}
+                for gpos, h, w, p_img in everyone:
+                    _, pos = self._draw_positions(1, h, w)
+                    order.append(p_img)
+                    if gpos % world == rank:
+                        draws[gpos] = pos
+                n_imgs = len(everyone)
+                for b in scored:
+                    for it in b.items:
+                        it["pos"] = draws[it["gpos"]]
+                    self._pick(b)
+                    launched.append(b)
+            for b in launched:
+                nonlocal_counts[0] += self._collect(b, dict_queries)
+        n_pixels = nonlocal_counts[0]
         assert n_imgs > 0, "no queries are chosen!"
-        stats_on = not human_labels and y is not None
-        if world > 1:  # the round's ONE exchange: per-rank picks (and statistics) -> every rank, back in dataloader order
+        stats_on = not human_labels and any_y[0]
+        if world > 1:
+            stats_on = any(ppdist.all_gather_objects(stats_on))
+            # the round's exchange: per-rank picks (and statistics) -> every rank, back in dataloader order
             gathered = ppdist.all_gather_objects((dict_queries, self.query_stats.round_payload(mine) if stats_on else None))
             merged: dict = dict()
             for d, _ in gathered:

@@ -192,7 +192,28 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, root, strat, kw, n_rounds):
+class MapDataset(torch.utils.data.Dataset):
+    """map-style dataset with the reference interface (base_dataset.py:151-189 items, .queries, .label_queries) behind a real
+    torch DataLoader: lets QuerySelector re-target the loader at this rank's images only; records what it served."""
+
+    def __init__(self, logits, y, lab):
+        self.logits, self.y = logits, y
+        self.queries = [m.copy() for m in lab]
+        self.labelled = None
+        self.served = []
+
+    def __len__(self):
+        return self.logits.shape[0]
+
+    def __getitem__(self, i):
+        self.served.append(i)
+        return {"x": self.logits[i], "y": torch.from_numpy(self.y[i]), "p_img": f"img_{i:04d}.png"}
+
+    def label_queries(self, dict_queries, nth_query=None):
+        self.labelled = (dict_queries, nth_query)
+
+
+def _worker(rank, world, port, root, strat, kw, n_rounds, real_loader=False):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -206,15 +227,18 @@ def _worker(rank, world, port, root, strat, kw, n_rounds):
     y[:3] = golden["call_y"]
     lab = rs.rand(7, 32, 48) < 0.01
     lab[:3] = golden["call_lab"]
-    ds = StubDataset(logits, y, lab)
-    qs = make_selector(q, make_args(strat, 19, 19, os.path.join(root, f"w{world}"), **kw), StubLoader(ds), 2)
+    ds = MapDataset(logits, y, lab) if real_loader else StubDataset(logits, y, lab)
+    loader = torch.utils.data.DataLoader(ds, batch_size=1, shuffle=False, num_workers=0) if real_loader else StubLoader(ds)
+    qs = make_selector(q, make_args(strat, 19, 19, os.path.join(root, f"w{world}"), **kw), loader, 2)
     np.random.seed(0)
     torch.manual_seed(0)
     out = []
     for r in range(n_rounds):
+        if real_loader:
+            ds.served = []
         d = qs(r, StubModel())
         out.append({"dict": d, "label_queries_nth": ds.labelled[1], "same_object": ds.labelled[0] is d,
-                    "np_state": np.random.get_state()[1].copy()})
+                    "np_state": np.random.get_state()[1].copy(), "served": list(getattr(ds, "served", []))})
     pickle.dump(out, open(os.path.join(root, f"w{world}_r{rank}.pkl"), "wb"))
     dist.barrier()
     dist.destroy_process_group()
@@ -255,6 +279,34 @@ def test_sharded_query_equals_single_process(tmp_path, strat, kw):
             for k in ("avg_entropy", "avg_n_unique_labels", "avg_spatial_coverage"):
                 # same lists in the same order: exact (the random strategy has no logits to take an entropy from: NaN)
                 assert a[k] == b[k] or (np.isnan(a[k]) and np.isnan(b[k])), (world, r, k)
+
+
+@pytest.mark.parametrize("strat,kw", [("margin_sampling", dict(top_n_percent=0.05)), ("entropy", dict(top_n_percent=0.0))])
+def test_sharded_query_over_a_real_dataloader_reads_only_its_own_images(tmp_path, strat, kw):
+    """multi-GPU fast path: with a map-style DataLoader every rank loads ONLY image i = rank (mod world), scores them, and
+    the random ranks are drawn after one all-gather of the image sizes - same picks, same statistics file and the same NumPy
+    stream state as the single-process walk over the whole loader."""
+    import torch.multiprocessing as mp
+    root = str(tmp_path)
+    mp.spawn(_worker, args=(1, _free_port(), root, strat, kw, 2, False), nprocs=1, join=True)
+    single = pickle.load(open(os.path.join(root, "w1_r0.pkl"), "rb"))
+    names = [f"img_{i:04d}.png" for i in range(7)]
+    for world in (2, 3):
+        mp.spawn(_worker, args=(world, _free_port(), root, strat, kw, 2, True), nprocs=world, join=True)
+        for rank in range(world):
+            got = pickle.load(open(os.path.join(root, f"w{world}_r{rank}.pkl"), "rb"))
+            for r in range(2):
+                assert got[r]["served"] == list(range(rank, 7, world))               # 1/world of the dataset, nothing else
+                assert list(got[r]["dict"]) == names
+                for p in names:
+                    for k in ("x_coords", "y_coords"):
+                        assert np.array_equal(got[r]["dict"][p][k], single[r]["dict"][p][k]), (world, rank, r, p)
+                assert np.array_equal(got[r]["np_state"], single[r]["np_state"])
+        for r in range(2):
+            f1 = os.path.join(root, "w1", "checkpoints", "t", f"{r}_query", "query_stats.pkl")
+            fw = os.path.join(root, f"w{world}", "checkpoints", "t", f"{r}_query", "query_stats.pkl")
+            a, b = pickle.load(open(f1, "rb")), pickle.load(open(fw, "rb"))
+            assert a == b or all(a[k] == b[k] for k in a)
 
 
 @pytest.mark.parametrize("strat", ["margin_sampling", "entropy"])
