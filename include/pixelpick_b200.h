@@ -207,12 +207,36 @@ int pp_conv_igemm_multi(const void* x, int N, int H, int W, int a_channels, int 
                         const float* pre_bias, const float* scale, const float* shift, int relu, const void* res,
                         int ld_res, void* out, int out_mode, int ld_out, int c_off, int block_n, void* stream);
 
+/* pp_conv_igemm_multi + per-channel statistics of the output, for TRAIN-mode BatchNorm (replaces the reduction pass of
+ * nn.BatchNorm2d over the conv output: mobilenet_v2.py:7-12,34-58, resnet_models.py:74-94, aspp.py:16-20): stats[0][c] +=
+ * sum, stats[1][c] += sum of squares (over every pixel of this launch, of the bf16-rounded values written to `out`);
+ * stats = float [2][Cout], zeroed by the caller, may be NULL.  Output mode 0 only. */
+int pp_conv_igemm_stats(const void* x, int N, int H, int W, int a_channels, int ld_in, int Cin, const void* w_packed,
+                        int n_entries, const int* tap_dy, const int* tap_dx, const int* tap_c0, int Cout_pad, int Cout,
+                        const float* pre_bias, const float* scale, const float* shift, int relu, const void* res,
+                        int ld_res, void* out, int out_mode, int ld_out, int c_off, int block_n, float* stats, void* stream);
+
+/* Epilogue of the bf16 NHWC output mode of pp_conv_igemm*: 1 (default) = shared-memory staging + TMA store, 0 = direct
+ * register -> global stores (the round-1 path; launches that take statistics always stage).  Returns the previous setting.
+ * Process-wide, for A/B measurements and tests; the environment variable PP_CONV_TMA_STORE=0 sets the initial value. */
+int pp_conv_set_epilogue(int tma_store);
+
 /* Weight gradient of the same convolution on tcgen05 (both operands MN-major, split over pixels):
  *   dw[tap][ci][co] += sum_p x[p + shift(tap)][ci] * dy[p][co]
  * x: bf16 [N,H,W,ld_x] (Cin valid channels); dy: bf16 [N,H,W,ld_dy] (first Cout_pad channels, 64/128/256);
  * dw: f32 [taps][Cin_rows][Cout_pad], ZEROED by the caller (Cin_rows >= Cin); splits: 0 = auto. */
 int pp_conv_wgrad(const void* x, int ld_x, int Cin, const void* dy, int ld_dy, int Cout_pad, int N, int H, int W,
                   int taps, int dil, float* dw, int Cin_rows, int splits, void* stream);
+
+/* General form of pp_conv_wgrad for the ENCODER convolutions (mobilenet_v2.py:34-58 1x1 expansions / projections,
+ * resnet_models.py:74-94 bottleneck 1x1 / 3x3 / downsample): any Cout (tiled by 64 / 128 / 256 output channels, the tensor
+ * map zero-fills the ragged tail), a tap table like pp_conv_igemm_multi's (entry t pairs dY[p] with x[p + (dy, dx)] read at
+ * channel offset c0 - the four space-to-depth phases of a stride-2 convolution sit side by side in x's channels), and an
+ * explicit row pitch of dw.  dw = float [n_entries][Cin_rows][ld_dw], zeroed by the caller, ld_dw >= Cout rounded up to
+ * the tile width (64 if Cout <= 64, 128 if <= 128, else 256). */
+int pp_conv_wgrad_multi(const void* x, int x_channels, int ld_x, int Cin, const void* dy, int ld_dy, int Cout, int N, int H,
+                        int W, int n_entries, const int* tap_dy, const int* tap_dx, const int* tap_c0, float* dw, int Cin_rows,
+                        int ld_dw, int splits, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * T path: the HBM-bound layers between the convolutions, NHWC bf16 (channel counts multiples of 8).

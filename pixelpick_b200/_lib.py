@@ -72,6 +72,10 @@ _SIGNATURES = {
                          _vp, _vp, _vp, _i, _i, _vp, _vp], _i),
     "pp_conv_igemm_multi": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i,
                              _i, _i, _i, _vp], _i),
+    "pp_conv_igemm_stats": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i,
+                             _i, _i, _i, _vp, _vp], _i),
+    "pp_conv_set_epilogue": ([_i], _i),
+    "pp_conv_wgrad_multi": ([_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "pp_dwconv3x3_fwd": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "pp_dwconv3x3_fwd_bnact": ([_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "pp_dwconv3x3_dgrad": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
@@ -446,31 +450,64 @@ def conv_igemm_multi(x_nhwc, w_packed, entries, cout, out=None, block_n=0):
 _TAPS = {}
 
 
-def conv_fused(x_nhwc, w_packed, cout, dil=1, scale=None, shift=None, act=0, res=None, out=None, flatten=True):
-    """Inference-time conv + folded BatchNorm + activation (+ residual) in one launch on activations whose channel count
-    need not be a multiple of 64 (TMA zero-fills the K padding).  x_nhwc bf16 [N,H,W,C]; w_packed [taps][cout_pad][Cin_pad];
-    act 0/1/2 = none/ReLU/ReLU6; res bf16 [N,H,W,cout].  1x1 convs are run on the flattened pixel list (no ragged tiles)."""
-    _need_cuda(x_nhwc, w_packed, res)
+def _tap_arrays(entries):
+    n = len(entries)
+    return tuple((C.c_int * n)(*[int(e[k]) for e in entries]) for k in range(3))
+
+
+def conv_fused(x_nhwc, w_packed, cout, dil=1, scale=None, shift=None, act=0, res=None, out=None, flatten=True, stats=None,
+               entries=None, c_off=0):
+    """conv + per-channel affine (folded BatchNorm) + activation (+ residual) in one launch on activations whose channel
+    count need not be a multiple of 64 (TMA zero-fills the K padding).  x_nhwc bf16 [N,H,W,C]; w_packed [taps][cout_pad][Cin_pad];
+    act 0/1/2 = none/ReLU/ReLU6; res bf16 [N,H,W,cout].  1x1 convs are run on the flattened pixel list (no ragged tiles).
+    stats: f32 [2, cout] zeroed accumulator -> += per-channel (sum, sum of squares) of the written values (TRAIN-mode
+    BatchNorm statistics straight from the conv epilogue).  entries: explicit tap table [(dy, dx, c0), ...] (default: the
+    1x1 / dilated 3x3 table of `dil`), e.g. the space-to-depth form of a stride-2 convolution."""
+    _need_cuda(x_nhwc, w_packed, res, stats)
     assert x_nhwc.dtype == torch.bfloat16 and x_nhwc.is_contiguous() and w_packed.dtype == torch.bfloat16
     N, H, W, Cc = x_nhwc.shape
     taps, cout_pad, cin_pad = w_packed.shape
     if out is None:
         out = torch.empty((N, H, W, cout), dtype=torch.bfloat16, device=x_nhwc.device)
-    key = (taps, dil)
-    if key not in _TAPS:
-        ent = [(0, 0, 0)] if taps == 1 else [((t // 3 - 1) * dil, (t % 3 - 1) * dil, 0) for t in range(9)]
-        _TAPS[key] = tuple((C.c_int * taps)(*[e[k] for e in ent]) for k in range(3))
-    dy, dx, c0 = _TAPS[key]
+    if entries is None:
+        key = (taps, dil)
+        if key not in _TAPS:
+            ent = [(0, 0, 0)] if taps == 1 else [((t // 3 - 1) * dil, (t % 3 - 1) * dil, 0) for t in range(9)]
+            _TAPS[key] = _tap_arrays(ent)
+        dy, dx, c0 = _TAPS[key]
+    else:
+        assert len(entries) == taps
+        dy, dx, c0 = _tap_arrays(entries)
     n_, h_, w_ = N, H, W
     M = N * H * W
-    if taps == 1 and flatten and M % 16 == 0:
+    if taps == 1 and flatten and M % 16 == 0 and entries is None:
         n_, h_, w_ = 1, M // 16, 16  # a 1x1 conv is a plain GEMM over pixels: 8x16 tiles of the flattened list
     for t in (scale, shift):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == cout_pad)
-    check(lib().pp_conv_igemm_multi(_ptr(x_nhwc), n_, h_, w_, Cc, Cc, cin_pad, _ptr(w_packed), taps, dy, dx, c0, cout_pad, cout,
+    if stats is not None:
+        assert stats.dtype == torch.float32 and stats.is_contiguous() and tuple(stats.shape) == (2, cout)
+    check(lib().pp_conv_igemm_stats(_ptr(x_nhwc), n_, h_, w_, Cc, Cc, cin_pad, _ptr(w_packed), taps, dy, dx, c0, cout_pad, cout,
                                     None, _ptr(scale), _ptr(shift), int(act), _ptr(res), res.shape[-1] if res is not None else 0,
-                                    _ptr(out), 0, out.shape[3], 0, 0, _stream(x_nhwc)), "pp_conv_igemm_multi")
+                                    _ptr(out), 0, out.shape[3], c_off, 0, _ptr(stats), _stream(x_nhwc)), "pp_conv_igemm_stats")
     return out
+
+
+def conv_wgrad_multi(x_nhwc, cin, dy_nhwc, cout, entries, splits=0):
+    """weight gradient of a conv given as a tap table: f32 [taps][Cin_rows][ld] with entry t = sum_p x[p + (dy, dx), c0 + ci] *
+    dy[p, co]; Cin_rows = cin rounded up to 8, ld = cout rounded up to the kernel's output-channel tile."""
+    _need_cuda(x_nhwc, dy_nhwc)
+    assert x_nhwc.dtype == torch.bfloat16 and dy_nhwc.dtype == torch.bfloat16 and x_nhwc.is_contiguous() and dy_nhwc.is_contiguous()
+    N, H, W, ld_x = x_nhwc.shape
+    assert tuple(dy_nhwc.shape[:3]) == (N, H, W) and dy_nhwc.shape[3] >= cout
+    bn = 256 if cout > 128 else (128 if cout > 64 else 64)
+    ld = -(-cout // bn) * bn
+    rows = -(-cin // 8) * 8
+    taps = len(entries)
+    dw = torch.zeros((taps, rows, ld), dtype=torch.float32, device=x_nhwc.device)
+    dy, dx, c0 = _tap_arrays(entries)
+    check(lib().pp_conv_wgrad_multi(_ptr(x_nhwc), ld_x, ld_x, cin, _ptr(dy_nhwc), dy_nhwc.shape[3], cout, N, H, W, taps, dy, dx, c0,
+                                    _ptr(dw), rows, ld, splits, _stream(x_nhwc)), "pp_conv_wgrad_multi")
+    return dw
 
 
 def conv_wgrad(x_nhwc, cin, dy_nhwc, cout_pad, taps, dil=1, splits=0):

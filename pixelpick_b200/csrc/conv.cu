@@ -14,6 +14,8 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
 // warps 2-9 = epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter).  Persistent over output tiles; the
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cstdlib>
+#include <cstring>
 #include "tc_common.cuh"
 
 namespace pp {
@@ -38,6 +40,11 @@ static EncodeTiledFn get_encode() {
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box) {
+  return make_tmap_bf16_sw(out, base, rank, dims, strides_bytes, box, 128);
+}
+
+int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not found");
@@ -52,7 +59,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     if (i > 0) s[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r, rank,
@@ -93,6 +101,8 @@ struct ConvParams {
   int ld_out, c_off;
   const __nv_bfloat16* res;  // optional residual [pixel][ld_res], channel c of the output adds res[c]; before the activation
   int ld_res;
+  int tma_store;  // bf16 NHWC output leaves through shared-memory staging + TMA store (full-line writes, ragged edges clipped)
+  float* stats;   // optional [2][Cout]: per-channel sum / sum of squares of the (bf16-rounded) outputs += this launch
 };
 
 template <int BN>
@@ -102,7 +112,8 @@ struct ConvCfg {
   static constexpr uint32_t B_BYTES = BN * kBK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two for BN in {16..256}
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t STAGING_BYTES = 8 * 2 * 2048;  // 8 epilogue warps x 2 buffers x (32 pixels x 32 channels bf16)
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ bool tap_skipped(const ConvParams& p, int tap, int y0, int x0, int& dy, int& dx) {
@@ -111,13 +122,23 @@ __device__ __forceinline__ bool tap_skipped(const ConvParams& p, int tap, int y0
   return (y0 + dy + p.TH <= 0) || (y0 + dy >= p.H) || (x0 + dx + p.TW <= 0) || (x0 + dx >= p.W);
 }
 
-template <int BN>
+// EPI: the per-element work of the staged (TMA-store) epilogue, fixed at compile time - with 8 epilogue warps on 4 schedulers
+// the epilogue of a short-K conv is bound by the instructions it issues (ncu: 2.3 IPC, 58 % issue slots busy on the 64 -> 256
+// 1x1), so flag tests, selects and dead arithmetic per element cost as much as the stores:
+//   kEpiGeneric : pre-bias, affine, residual, activation all optional at run time (also the only variant with the direct path)
+//   kEpiRaw     : out = bf16(acc)                        - training forward (BatchNorm follows) and every data gradient
+//   kEpiAffine  : out = clamp(acc * scale + shift)       - inference convs with folded BatchNorm + ReLU / ReLU6
+constexpr int kEpiGeneric = 0, kEpiRaw = 1, kEpiAffine = 2;
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmO, const ConvParams p) {
   using Cfg = ConvCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t stg_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;  // 1024-aligned: stage sizes are multiples of 4 KB
+  const uint32_t bar_base = stg_base + Cfg::STAGING_BYTES;
   auto sA = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES; };
   auto sB = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -137,6 +158,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmB);
+    if (p.tma_store) tc::tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -238,6 +260,153 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int row = quarter * 32 + lane;
     const int ty_in = row / p.TW, tx_in = row - ty_in * p.TW;
     uint32_t tile_iter = 0;
+    if (p.out_mode == 0 && p.tma_store) {
+      // ---- bf16 NHWC output through shared memory + TMA store ----
+      // A unit = this warp's 32 pixels x one 32-channel chunk = 2 KB, written to a 64-byte-swizzled staging buffer (each lane
+      // its pixel's 64 B as four conflict-free 16-byte stores) and shipped by ONE bulk tensor store: the memory system sees
+      // whole 64-byte runs instead of 32 scattered 16-byte pieces per instruction, ragged channel counts / image edges are
+      // clipped by the tensor map, and the warp moves on while the store drains (two buffers per warp).
+      // With p.stats the per-channel sum and sum of squares of the ROUNDED outputs (what BatchNorm will read back) are
+      // accumulated from the staged tile: the BatchNorm forward then needs no statistics pass over the tensor.
+      const uint32_t my_stage = stg_base + (uint32_t)(warp - 2) * 4096u;
+      const int rows_per_q = 32 / p.TW;  // tile rows covered by one TMEM lane quarter
+      const float act_lo = p.relu ? 0.f : -INFINITY, act_hi = p.relu == 2 ? 6.f : INFINITY;  // none / ReLU / ReLU6 as a clamp
+      uint32_t unit_iter = 0;
+      constexpr int NSLOT = BN >= 64 ? BN / 64 : 1;  // 32-channel chunks per warp and tile (the two warps of a quarter alternate)
+      float st_s[NSLOT][2], st_q[NSLOT][2];
+#pragma unroll
+      for (int i = 0; i < NSLOT; ++i) st_s[i][0] = st_s[i][1] = st_q[i][0] = st_q[i][1] = 0.f;
+      int n0_cta = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+        int n0, img, y0, x0;
+        decode(tile, n0, img, y0, x0);
+        n0_cta = n0;
+        const uint32_t acc = tile_iter & 1u, aph = (tile_iter >> 1) & 1u;
+        tc::mbar_wait(tfull_bar(acc), aph);
+        tc::tc_fence_after();
+        const int y = y0 + ty_in, x = x0 + tx_in;
+        const bool valid = (y < p.H) && (x < p.W);
+        const size_t pix = ((size_t)img * p.H + y) * p.W + x;
+#pragma unroll
+        for (int slot = 0; slot < NSLOT; ++slot) {
+          const int j = eh + 2 * slot;
+          const int cbase = n0 + j * 32;
+          if (j >= BN / 32 || cbase >= p.Cout) continue;  // warp-uniform: no such chunk / entirely in the channel padding
+          uint32_t r[32];
+          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + j * 32, r);
+          tc::tmem_ld_wait();
+          uint32_t pk[16];
+          if constexpr (EPI == kEpiRaw) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r[c]), __uint_as_float(r[c + 1]));
+              pk[c / 2] = *reinterpret_cast<uint32_t*>(&t0);
+            }
+          } else if constexpr (EPI == kEpiAffine) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              const float4 sc4 = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + c));
+              const float4 sf4 = __ldg(reinterpret_cast<const float4*>(p.shift + cbase + c));
+              const float a0 = fminf(fmaxf(fmaf(__uint_as_float(r[c]), sc4.x, sf4.x), act_lo), act_hi);
+              const float a1 = fminf(fmaxf(fmaf(__uint_as_float(r[c + 1]), sc4.y, sf4.y), act_lo), act_hi);
+              const float a2 = fminf(fmaxf(fmaf(__uint_as_float(r[c + 2]), sc4.z, sf4.z), act_lo), act_hi);
+              const float a3 = fminf(fmaxf(fmaf(__uint_as_float(r[c + 3]), sc4.w, sf4.w), act_lo), act_hi);
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(a0, a1);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(a2, a3);
+              pk[c / 2] = *reinterpret_cast<uint32_t*>(&t0);
+              pk[c / 2 + 1] = *reinterpret_cast<uint32_t*>(&t1);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              float4 pb = make_float4(0.f, 0.f, 0.f, 0.f), sc4 = make_float4(1.f, 1.f, 1.f, 1.f), sf4 = pb;
+              if (p.pre_bias) pb = __ldg(reinterpret_cast<const float4*>(p.pre_bias + (size_t)img * p.Cout_pad + cbase + c));
+              if (p.scale) sc4 = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + c));
+              if (p.shift) sf4 = __ldg(reinterpret_cast<const float4*>(p.shift + cbase + c));
+              const float pbv[4] = {pb.x, pb.y, pb.z, pb.w}, scv[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sfv[4] = {sf4.x, sf4.y, sf4.z, sf4.w};
+              float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+              if (p.res && valid && cbase + c + 4 <= p.Cout) {
+                const uint2 q = __ldg(reinterpret_cast<const uint2*>(p.res + pix * p.ld_res + cbase + c));
+                rs4[0] = __uint_as_float(q.x << 16);
+                rs4[1] = __uint_as_float(q.x & 0xFFFF0000u);
+                rs4[2] = __uint_as_float(q.y << 16);
+                rs4[3] = __uint_as_float(q.y & 0xFFFF0000u);
+              }
+              float a4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                a4[e] = fminf(fmaxf(fmaf(__uint_as_float(r[c + e]) + pbv[e], scv[e], sfv[e]) + rs4[e], act_lo), act_hi);
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(a4[0], a4[1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(a4[2], a4[3]);
+              pk[c / 2] = *reinterpret_cast<uint32_t*>(&t0);
+              pk[c / 2 + 1] = *reinterpret_cast<uint32_t*>(&t1);
+            }
+          }
+          const uint32_t buf = my_stage + (unit_iter & 1u) * 2048u;
+          if (unit_iter >= 2) {  // the store issued from this buffer two units ago must have read it
+            if (lane == 0) tc::bulk_wait_group_read<1>();
+            __syncwarp();
+          }
+          const uint32_t rowaddr = buf + (uint32_t)lane * 64u;
+          const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (((uint32_t)u ^ sw) << 4)), "r"(pk[4 * u]),
+                         "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
+                         : "memory");
+          if (p.stats) {
+            __syncwarp();
+            // lane -> channel pair w = lane & 15 of the rows with parity lane >> 4: one 4-byte word per row, conflict-free
+            const uint32_t w = (uint32_t)lane & 15u, par = (uint32_t)lane >> 4;
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t rr = 2u * i + par;
+              uint32_t word;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(word) : "r"(buf + rr * 64u + (((w >> 2) ^ ((rr >> 1) & 3u)) << 4) + (w & 3u) * 4u));
+              const float lo = __uint_as_float(word << 16), hi = __uint_as_float(word & 0xFFFF0000u);
+              s0 += lo; s1 += hi;
+              q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
+            }
+            s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, 16);
+            s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, 16);
+            q0 += __shfl_xor_sync(0xFFFFFFFFu, q0, 16);
+            q1 += __shfl_xor_sync(0xFFFFFFFFu, q1, 16);
+            st_s[slot][0] += s0; st_s[slot][1] += s1;
+            st_q[slot][0] += q0; st_q[slot][1] += q1;
+          }
+          tc::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tc::tma_store_4d(&tmO, buf, cbase, x0, y0 + quarter * rows_per_q, img);
+            tc::bulk_commit_group();
+          }
+          ++unit_iter;
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tempty_bar(acc));
+      }
+      if (p.stats && tile_iter > 0 && lane < 16) {
+        // every tile of this CTA has the same channel range (the launch makes the grid a multiple of the N tiles)
+#pragma unroll
+        for (int slot = 0; slot < NSLOT; ++slot) {
+          const int j = eh + 2 * slot;
+          const int c = n0_cta + j * 32 + 2 * lane;
+          if (j >= BN / 32) continue;
+          if (c < p.Cout) {
+            atomicAdd(p.stats + c, st_s[slot][0]);
+            atomicAdd(p.stats + p.Cout + c, st_q[slot][0]);
+          }
+          if (c + 1 < p.Cout) {
+            atomicAdd(p.stats + c + 1, st_s[slot][1]);
+            atomicAdd(p.stats + p.Cout + c + 1, st_q[slot][1]);
+          }
+        }
+      }
+      if (lane == 0) tc::bulk_wait_group<0>();
+      __syncwarp();
+    } else if constexpr (EPI == kEpiGeneric)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
       int n0, img, y0, x0;
       decode(tile, n0, img, y0, x0);
@@ -353,19 +522,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int BN>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int sm_count, cudaStream_t st) {
+template <int BN, int EPI>
+static int launch_conv_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvParams& p, int sm_count,
+                           cudaStream_t st) {
   using Cfg = ConvCfg<BN>;
   static bool attr = false;
   if (!attr) {
-    PP_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    PP_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr = true;
   }
   const int total = p.N * p.tiles_y * p.tiles_x * p.n_tiles_n;
-  const int grid = total < sm_count ? total : sm_count;
-  conv_igemm_kernel<BN><<<grid, kConvThreads, Cfg::SMEM, st>>>(tmA, tmB, p);
+  int grid = total < sm_count ? total : sm_count;
+  // statistics are kept in registers per CTA: every tile of a CTA must cover the same channel range, i.e. the grid is a
+  // multiple of the number of N tiles (tile -> N tile = tile % n_tiles_n; total is a multiple of it by construction)
+  if (p.stats && p.n_tiles_n > 1) grid = grid / p.n_tiles_n * p.n_tiles_n;
+  if (grid < 1) grid = p.n_tiles_n;
+  conv_igemm_kernel<BN, EPI><<<grid, kConvThreads, Cfg::SMEM, st>>>(tmA, tmB, tmO, p);
   PP_LAUNCH_CHECK();
   return PP_OK;
+}
+
+template <int BN>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvParams& p, int sm_count,
+                       cudaStream_t st) {
+  if (p.tma_store && !p.pre_bias && !p.res) {
+    if (!p.scale && !p.shift && p.relu == 0) return launch_conv_epi<BN, kEpiRaw>(tmA, tmB, tmO, p, sm_count, st);
+    if (p.scale && p.shift) return launch_conv_epi<BN, kEpiAffine>(tmA, tmB, tmO, p, sm_count, st);
+  }
+  return launch_conv_epi<BN, kEpiGeneric>(tmA, tmB, tmO, p, sm_count, st);
 }
 
 static int sm_count_cached() {
@@ -404,7 +588,32 @@ int pp_conv_igemm_multi(const void* x, int N, int H, int W, int a_channels, int 
                         int n_entries, const int* tap_dy, const int* tap_dx, const int* tap_c0, int Cout_pad, int Cout,
                         const float* pre_bias, const float* scale, const float* shift, int relu, const void* res,
                         int ld_res, void* out, int out_mode, int ld_out, int c_off, int block_n, void* stream) {
+  return pp_conv_igemm_stats(x, N, H, W, a_channels, ld_in, Cin, w_packed, n_entries, tap_dy, tap_dx, tap_c0, Cout_pad, Cout,
+                             pre_bias, scale, shift, relu, res, ld_res, out, out_mode, ld_out, c_off, block_n, nullptr, stream);
+}
+
+static int g_conv_tma_store = -1;
+
+static int conv_tma_store_enabled() {
+  if (g_conv_tma_store < 0) {
+    const char* e = getenv("PP_CONV_TMA_STORE");  // "0": the direct register -> global epilogue (kept for A/B measurements)
+    g_conv_tma_store = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_conv_tma_store;
+}
+
+int pp_conv_set_epilogue(int tma_store) {
+  const int prev = conv_tma_store_enabled();
+  g_conv_tma_store = tma_store ? 1 : 0;
+  return prev;
+}
+
+int pp_conv_igemm_stats(const void* x, int N, int H, int W, int a_channels, int ld_in, int Cin, const void* w_packed,
+                        int n_entries, const int* tap_dy, const int* tap_dx, const int* tap_c0, int Cout_pad, int Cout,
+                        const float* pre_bias, const float* scale, const float* shift, int relu, const void* res,
+                        int ld_res, void* out, int out_mode, int ld_out, int c_off, int block_n, float* stats, void* stream) {
   PP_CHECK_ARG(x && w_packed && out, "pp_conv_igemm: null pointer");
+  PP_CHECK_ARG(!stats || out_mode == 0, "pp_conv_igemm: channel statistics need the bf16 NHWC output mode");
   PP_CHECK_ARG(relu >= 0 && relu <= 2, "pp_conv_igemm: relu=%d (0 none, 1 ReLU, 2 ReLU6)", relu);
   PP_CHECK_ARG(!res || (ld_res % 8 == 0 && ld_res >= Cout && (reinterpret_cast<uintptr_t>(res) % 16) == 0),
                "pp_conv_igemm: residual needs ld_res >= Cout, a multiple of 8, and a 16-byte aligned base");
@@ -463,8 +672,21 @@ int pp_conv_igemm_multi(const void* x, int N, int H, int W, int a_channels, int 
   p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.ld_res = ld_res;
   p.n_off = 0;
   p.n_tiles_n = n_main / BN;
+  p.stats = stats;
+  p.tma_store = (out_mode == 0 && (stats || conv_tma_store_enabled())) ? 1 : 0;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
+  if (p.tma_store) {
+    // output view: channels [c_off, c_off + Cout) of the ld_out-wide NHWC tensor; one box = 32 channels x the 32 pixels of a
+    // TMEM lane quarter (TW x 32/TW), 64-byte swizzle.  Channels >= Cout and pixels outside the image are clipped by TMA.
+    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t strides[3] = {(uint64_t)ld_out * 2, (uint64_t)W * ld_out * 2, (uint64_t)H * W * ld_out * 2};
+    const uint32_t box[4] = {32, (uint32_t)p.TW, (uint32_t)(32 / p.TW), 1};
+    int rc = make_tmap_bf16_sw(&tmO, reinterpret_cast<const __nv_bfloat16*>(out) + c_off, 4, dims, strides, box, 64);
+    if (rc != PP_OK) return rc;
+  } else {
+    memset(&tmO, 0, sizeof(tmO));
+  }
   {
     const uint64_t dims[4] = {(uint64_t)a_channels, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     const uint64_t strides[3] = {(uint64_t)ld_in * 2, (uint64_t)W * ld_in * 2, (uint64_t)H * W * ld_in * 2};
@@ -483,10 +705,10 @@ int pp_conv_igemm_multi(const void* x, int N, int H, int W, int a_channels, int 
   const int sms = sm_count_cached();
   int rc;
   switch (BN) {
-    case 256: rc = launch_conv<256>(tmA, tmB, p, sms, st); break;
-    case 128: rc = launch_conv<128>(tmA, tmB, p, sms, st); break;
-    case 64: rc = launch_conv<64>(tmA, tmB, p, sms, st); break;
-    default: rc = launch_conv<32>(tmA, tmB, p, sms, st); break;
+    case 256: rc = launch_conv<256>(tmA, tmB, tmO, p, sms, st); break;
+    case 128: rc = launch_conv<128>(tmA, tmB, tmO, p, sms, st); break;
+    case 64: rc = launch_conv<64>(tmA, tmB, tmO, p, sms, st); break;
+    default: rc = launch_conv<32>(tmA, tmB, tmO, p, sms, st); break;
   }
   if (rc != PP_OK || n_main == Cout_pad) return rc;
   // remainder launch: narrower tiles over output channels [n_main, Cout_pad)
@@ -502,7 +724,7 @@ int pp_conv_igemm_multi(const void* x, int N, int H, int W, int a_channels, int 
   }
   p.n_off = n_main;
   p.n_tiles_n = rem / BR;
-  return BR == 128 ? launch_conv<128>(tmA, tmB2, p, sms, st) : launch_conv<64>(tmA, tmB2, p, sms, st);
+  return BR == 128 ? launch_conv<128>(tmA, tmB2, tmO, p, sms, st) : launch_conv<64>(tmA, tmB2, tmO, p, sms, st);
 }
 
 }  // extern "C"

@@ -17,14 +17,19 @@ constexpr int kWgThreads = 192;
 constexpr int kPB = 8;                       // pixel block is kPB x kPB = 64 pixels (one K block)
 constexpr uint32_t kBoxBytes = 64 * 64 * 2;  // one {64 ch, 8, 8} box = 8 KB
 
+constexpr int kWgMaxTaps = 16;
+
 struct WgradParams {
   int N, H, W;
-  int Cin, Cout_pad;  // valid input channels (rows written), padded output channels (BN multiple)
-  int taps, dil;
+  int Cin;            // valid input channels (rows written)
+  int taps;
+  // tap table: tap t pairs dY[p] with X[p + (tdy, tdx)] read at channel offset tc0 of the X tensor (tc0 != 0: the
+  // space-to-depth phases of a stride-2 convolution live side by side in the channel dimension)
+  short tdy[kWgMaxTaps], tdx[kWgMaxTaps], tc0[kWgMaxTaps];
   int pby, pbx;       // pixel blocks per image
-  int n_ci_tiles, splits;
-  float* dw;          // [taps][Cin_rows][Cout_pad] fp32, Cin_rows = n_ci_tiles * 128 rows allocated >= Cin
-  int Cin_rows;
+  int n_ci_tiles, n_co_tiles, splits;
+  float* dw;          // [taps][Cin_rows][ld_dw] fp32, Cin_rows >= n_ci_tiles * 128 or >= Cin, ld_dw = n_co_tiles * BN
+  int Cin_rows, ld_dw;
 };
 
 template <int BN>
@@ -63,13 +68,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   const int split = item % p.splits;
   item /= p.splits;
   const int ci_tile = item % p.n_ci_tiles;
-  const int tap = item / p.n_ci_tiles;
-  const int ci0 = ci_tile * 128;
-  int dy = 0, dx = 0;
-  if (p.taps == 9) {
-    dy = (tap / 3 - 1) * p.dil;
-    dx = (tap % 3 - 1) * p.dil;
-  }
+  item /= p.n_ci_tiles;
+  const int co_tile = item % p.n_co_tiles;
+  const int tap = item / p.n_co_tiles;
+  const int ci0 = ci_tile * 128, co0 = co_tile * BN;
+  const int dy = p.tdy[tap], dx = p.tdx[tap], xc0 = p.tc0[tap];
   const int pb_per_img = p.pby * p.pbx;
   const int total_pb = p.N * pb_per_img;
   const int pb_lo = (int)((int64_t)total_pb * split / p.splits);
@@ -117,10 +120,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         tc::mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-          tc::tma_load_4d(sA(s) + j * kBoxBytes, &tmX, full_bar(s), ci0 + 64 * j, x0 + dx, y0 + dy, img);
+          tc::tma_load_4d(sA(s) + j * kBoxBytes, &tmX, full_bar(s), xc0 + ci0 + 64 * j, x0 + dx, y0 + dy, img);
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
-          tc::tma_load_4d(sB(s) + j * kBoxBytes, &tmDY, full_bar(s), 64 * j, x0, y0, img);
+          tc::tma_load_4d(sB(s) + j * kBoxBytes, &tmDY, full_bar(s), co0 + 64 * j, x0, y0, img);
         ++it;
       }
     }
@@ -163,7 +166,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     tc::tc_fence_after();
     if (n_valid > 0) {
       const int ci = ci0 + row;
-      float* dst = p.dw + ((size_t)tap * p.Cin_rows + ci) * p.Cout_pad;
+      float* dst = p.dw + ((size_t)tap * p.Cin_rows + ci) * p.ld_dw + co0;
 #pragma unroll 1
       for (int j = 0; j < BN / 32; ++j) {
         uint32_t r[32];
@@ -196,7 +199,7 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const W
     PP_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr = true;
   }
-  const int grid = p.taps * p.n_ci_tiles * p.splits;
+  const int grid = p.taps * p.n_co_tiles * p.n_ci_tiles * p.splits;
   wgrad_kernel<BN><<<grid, kWgThreads, Cfg::SMEM, st>>>(tmX, tmDY, p);
   PP_LAUNCH_CHECK();
   return PP_OK;
@@ -210,26 +213,57 @@ extern "C" {
 
 int pp_conv_wgrad(const void* x, int ld_x, int Cin, const void* dy, int ld_dy, int Cout_pad, int N, int H, int W,
                   int taps, int dil, float* dw, int Cin_rows, int splits, void* stream) {
-  PP_CHECK_ARG(x && dy && dw, "pp_conv_wgrad: null pointer");
-  PP_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0, "pp_conv_wgrad: bad shape");
   PP_CHECK_ARG(taps == 1 || taps == 9, "pp_conv_wgrad: taps=%d", taps);
-  PP_CHECK_ARG(ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_x >= Cin && ld_dy >= Cout_pad, "pp_conv_wgrad: bad leading dims");
   PP_CHECK_ARG(Cout_pad == 64 || Cout_pad == 128 || Cout_pad == 256, "pp_conv_wgrad: Cout_pad=%d (64, 128 or 256)", Cout_pad);
+  int tdy[9], tdx[9], tc0[9];
+  for (int t = 0; t < taps; ++t) {
+    tdy[t] = taps == 1 ? 0 : (t / 3 - 1) * dil;
+    tdx[t] = taps == 1 ? 0 : (t % 3 - 1) * dil;
+    tc0[t] = 0;
+  }
+  return pp_conv_wgrad_multi(x, ld_x, ld_x, Cin, dy, ld_dy, Cout_pad, N, H, W, taps, tdy, tdx, tc0, dw, Cin_rows, Cout_pad,
+                             splits, stream);
+}
+
+int pp_conv_wgrad_multi(const void* x, int x_channels, int ld_x, int Cin, const void* dy, int ld_dy, int Cout, int N, int H,
+                        int W, int n_entries, const int* tap_dy, const int* tap_dx, const int* tap_c0, float* dw, int Cin_rows,
+                        int ld_dw, int splits, void* stream) {
+  PP_CHECK_ARG(x && dy && dw && tap_dy && tap_dx && tap_c0, "pp_conv_wgrad: null pointer");
+  PP_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "pp_conv_wgrad: bad shape");
+  PP_CHECK_ARG(n_entries >= 1 && n_entries <= kWgMaxTaps, "pp_conv_wgrad: %d tap entries (1..%d)", n_entries, kWgMaxTaps);
+  PP_CHECK_ARG(ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_x >= x_channels && x_channels >= Cin && ld_dy >= Cout,
+               "pp_conv_wgrad: bad leading dims (ld_x %d x_channels %d Cin %d ld_dy %d Cout %d)", ld_x, x_channels, Cin, ld_dy, Cout);
+  for (int t = 0; t < n_entries; ++t)
+    PP_CHECK_ARG(tap_c0[t] >= 0 && tap_c0[t] % 8 == 0 && tap_c0[t] + Cin <= x_channels && tap_dy[t] > -8192 && tap_dy[t] < 8192 &&
+                     tap_dx[t] > -8192 && tap_dx[t] < 8192,
+                 "pp_conv_wgrad: bad tap entry %d (dy %d dx %d c0 %d)", t, tap_dy[t], tap_dx[t], tap_c0[t]);
+  // output-channel tile: the widest that the valid channel count fills reasonably (ld_dw tells how many were allocated)
+  const int BN = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
+  const int n_co_tiles = (Cout + BN - 1) / BN;
+  PP_CHECK_ARG(ld_dw >= n_co_tiles * BN && ld_dw % 4 == 0, "pp_conv_wgrad: ld_dw=%d must be >= %d (Cout rounded up to %d)", ld_dw,
+               n_co_tiles * BN, BN);
   const int n_ci_tiles = (Cin + 127) / 128;
-  PP_CHECK_ARG(Cin_rows >= n_ci_tiles * 128 || Cin_rows >= Cin, "pp_conv_wgrad: Cin_rows=%d too small", Cin_rows);
-  PP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(dy) % 16) == 0,
-               "pp_conv_wgrad: x / dy must be 16-byte aligned");
+  PP_CHECK_ARG(Cin_rows >= Cin, "pp_conv_wgrad: Cin_rows=%d too small", Cin_rows);
+  PP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(dy) % 16) == 0 &&
+                   (reinterpret_cast<uintptr_t>(dw) % 16) == 0,
+               "pp_conv_wgrad: x / dy / dw must be 16-byte aligned");
   WgradParams p;
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout_pad = Cout_pad; p.taps = taps; p.dil = dil;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.taps = n_entries;
+  for (int t = 0; t < kWgMaxTaps; ++t) {
+    p.tdy[t] = (short)(t < n_entries ? tap_dy[t] : 0);
+    p.tdx[t] = (short)(t < n_entries ? tap_dx[t] : 0);
+    p.tc0[t] = (short)(t < n_entries ? tap_c0[t] : 0);
+  }
   p.pby = (H + kPB - 1) / kPB;
   p.pbx = (W + kPB - 1) / kPB;
   p.n_ci_tiles = n_ci_tiles;
+  p.n_co_tiles = n_co_tiles;
   const int total_pb = N * p.pby * p.pbx;
   if (splits <= 0) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    splits = (2 * sms) / (taps * n_ci_tiles);  // <= 2 full waves: one extra CTA would cost a whole third wave
+    splits = (2 * sms) / (n_entries * n_ci_tiles * n_co_tiles);  // <= 2 full waves: one extra CTA would cost a whole third wave
     const int max_splits = (total_pb + 7) / 8;  // at least 8 pixel blocks (512 pixels) per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -238,23 +272,24 @@ int pp_conv_wgrad(const void* x, int ld_x, int Cin, const void* dy, int ld_dy, i
   p.splits = splits;
   p.dw = dw;
   p.Cin_rows = Cin_rows;
+  p.ld_dw = ld_dw;
   CUtensorMap tmX, tmDY;
   {
-    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t dims[4] = {(uint64_t)x_channels, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     const uint64_t strides[3] = {(uint64_t)ld_x * 2, (uint64_t)W * ld_x * 2, (uint64_t)H * W * ld_x * 2};
     const uint32_t box[4] = {64, kPB, kPB, 1};
     int rc = make_tmap_bf16(&tmX, x, 4, dims, strides, box);
     if (rc != PP_OK) return rc;
   }
   {
-    const uint64_t dims[4] = {(uint64_t)Cout_pad, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     const uint64_t strides[3] = {(uint64_t)ld_dy * 2, (uint64_t)W * ld_dy * 2, (uint64_t)H * W * ld_dy * 2};
     const uint32_t box[4] = {64, kPB, kPB, 1};
     int rc = make_tmap_bf16(&tmDY, dy, 4, dims, strides, box);
     if (rc != PP_OK) return rc;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (Cout_pad) {
+  switch (BN) {
     case 256: return launch_wgrad<256>(tmX, tmDY, p, st);
     case 128: return launch_wgrad<128>(tmX, tmDY, p, st);
     default: return launch_wgrad<64>(tmX, tmDY, p, st);

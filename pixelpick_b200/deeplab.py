@@ -15,6 +15,7 @@ in bf16 channels_last on the GPU.
 consume (the x4 bilinear upsample of deeplab.py:55 is evaluated inside those kernels, never materialised).
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -528,6 +529,157 @@ class _HeadFn(torch.autograd.Function):
 
 
 # =============================================================================================
+# encoders, training: every dense conv (1x1 expansions / projections, bottleneck 1x1 / dilated 3x3, the stride-2 bottleneck
+# through its space-to-depth form) on pp_conv_igemm_stats / pp_conv_wgrad_multi; the conv epilogue also accumulates the
+# BatchNorm statistics, so a layer's forward is conv -> finalize (C floats) -> normalise+activation(+residual): one read and
+# one write of the activation instead of two reads and a write.  Only the Cin = 3 stems and the max-pool stay library ops.
+# =============================================================================================
+def space_to_depth(x):
+    """[N, H, W, C] -> [N, H/2, W/2, 4C]: phase (a, b) = rows a::2, columns b::2 at channels [(2a+b)C, (2a+b+1)C)."""
+    N, H, W, Cc = x.shape
+    return x.view(N, H // 2, 2, W // 2, 2, Cc).permute(0, 1, 3, 2, 4, 5).reshape(N, H // 2, W // 2, 4 * Cc)
+
+
+def s2d_entries(Cc):
+    """tap table of a 3x3 / stride 2 / pad 1 convolution on the space-to-depth tensor: tap (ky, kx) reads phase
+    ((ky-1)&1, (kx-1)&1) shifted by ((ky-1-a)/2, (kx-1-b)/2) output pixels (resnet_models.py:78: the strided 3x3)."""
+    ent = []
+    for ky in range(3):
+        for kx in range(3):
+            dy, dx = ky - 1, kx - 1
+            a, b = dy & 1, dx & 1
+            ent.append(((dy - a) // 2, (dx - b) // 2, (2 * a + b) * Cc))
+    return ent
+
+
+class _ConvBNActFn(torch.autograd.Function):
+    """y = act(BatchNorm_train(conv(x)) [+ res]) on NHWC bf16 tensors, one autograd node.
+    x [N, H, W, Cin] (or its space-to-depth form for the stride-2 3x3), w fp32 [Cout, Cin, k, k] (the master weight)."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, bn, act, res, dil, s2d):
+        cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+        taps = k * k
+        N, H, W, xc = x.shape
+        cin_pad, rows_pad = -(-cin // 64) * 64, _cpad(cin)
+        need_dx = bool(x.requires_grad)
+        wp, wd = _lib.pack_conv_weights(w, cin, fwd_pad=(_cpad(cout), cin_pad),
+                                        dgrad_pad=(rows_pad, -(-cout // 64) * 64) if need_dx else None)
+        entries = s2d_entries(cin) if s2d else None
+        raw = torch.empty((N, H, W, cout), dtype=torch.bfloat16, device=x.device)
+        stats = torch.zeros((2, cout), dtype=torch.float32, device=x.device)
+        _lib.conv_fused(x, wp, cout, dil=dil, out=raw, stats=stats, entries=entries)
+        st = _lib.bn_finalize(stats, N * H * W, bn)
+        y = torch.empty_like(raw)
+        _lib.bn_apply(raw, 0, cout, st[0], st[1], act, y, 0, res=res)
+        ctx.bn, ctx.act, ctx.cfg, ctx.need_dx = bn, act, (cin, cout, k, dil, s2d), need_dx
+        ctx.save_for_backward(*([x, raw, st, wd if need_dx else st] + ([res] if res is not None else [])))
+        ctx.has_res = res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, raw, st, wd = ctx.saved_tensors[:4]
+        res = ctx.saved_tensors[4] if ctx.has_res else None
+        cin, cout, k, dil, s2d = ctx.cfg
+        N, H, W, _ = raw.shape
+        if dy.dtype != torch.bfloat16 or not dy.is_contiguous():
+            dy = dy.to(torch.bfloat16).contiguous()
+        out = _lib.bn_bwd(dy, 0, raw, 0, cout, st[0], st[1], st[2], st[3], ctx.act, res=res,
+                          scratch=_lib.bn_scratch(ctx.bn, cout, raw.device) if cout <= 2048 else None)
+        draw = out[0].view(N, H, W, cout)
+        sums = out[1]
+        dres = out[2].view(N, H, W, cout) if res is not None else None
+        taps = k * k
+        if s2d:
+            entries = s2d_entries(cin)
+        elif taps == 1:
+            entries = [(0, 0, 0)]
+        else:
+            entries = [((t // 3 - 1) * dil, (t % 3 - 1) * dil, 0) for t in range(9)]
+        dw = _lib.conv_wgrad_multi(x, cin, draw, cout, entries)
+        dW = dw[:, :cin, :cout].permute(2, 1, 0).reshape(cout, cin, k, k)
+        dx = None
+        if ctx.need_dx:
+            if not s2d:
+                dx = _lib.conv_fused(draw, wd, cin, dil=dil)
+            else:
+                # adjoint of the phase form: phase (a, b) of dX collects, from every tap that reads it, W[tap]^T applied to dY
+                # shifted the other way - four small launches (1, 2, 2 and 4 taps) writing the four channel blocks
+                dx = torch.empty((N, H, W, 4 * cin), dtype=torch.bfloat16, device=raw.device)
+                for ph in range(4):
+                    sel = [(t, e) for t, e in enumerate(entries) if e[2] == ph * cin]
+                    wsel = torch.stack([wd[8 - t] for t, _ in sel])  # the dgrad pack holds W^T with the taps flipped
+                    _lib.conv_fused(draw, wsel, cin, out=dx, c_off=ph * cin, entries=[(-e[0], -e[1], 0) for _, e in sel])
+        return dx, dW, sums[1], sums[0], None, None, dres, None, None
+
+
+def _cba(x, conv, bn, res=None, s2d=False):
+    """conv -> train-mode BatchNorm -> bn.act (-> + res before the activation) on an NHWC bf16 tensor"""
+    return _ConvBNActFn.apply(x, conv.weight, bn.weight, bn.bias, bn, bn.act, res, conv.dilation[0], s2d)
+
+
+def _bn_act_nhwc(x, bn, res=None):
+    return _BNActFn.apply(x, bn.weight, bn.bias, bn, bn.act, res)
+
+
+def _stem_nhwc(mods, x, autocast_dtype):
+    with torch.autocast("cuda", dtype=autocast_dtype):
+        t = mods(x)  # Cin = 3 stem conv (library) + fused NHWC BatchNorm / activation (+ max-pool)
+    t = t.permute(0, 2, 3, 1)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _mnv2_train_forward(bb, x, autocast_dtype):
+    """mobilenet_v2.py:130-137 in train mode on NHWC bf16 tensors."""
+    t = _stem_nhwc(bb.features[0], x, autocast_dtype)
+    low = None
+    for i, blk in enumerate(bb.features[1:]):
+        if not isinstance(blk, InvertedResidual):
+            return None
+        mods = list(blk.conv)
+        d = blk.dilation
+        h = F.pad(t, (0, 0, d, d, d, d))  # fixed_padding (mobilenet_v2.py:15-21) BEFORE the expansion conv
+        if len(mods) == 8:
+            h = _cba(h, mods[0], mods[1])
+            dw, dw_bn, proj, proj_bn = mods[3], mods[4], mods[6], mods[7]
+        else:
+            dw, dw_bn, proj, proj_bn = mods[0], mods[1], mods[3], mods[4]
+        h = _DWConvFn.apply(h, dw.weight, dw.stride[0], dw.dilation[0])
+        h = _bn_act_nhwc(h, dw_bn)
+        t = _cba(h, proj, proj_bn, res=t if blk.use_res_connect else None)  # x + conv(x): the add rides in the BatchNorm pass
+        if i == 2:
+            low = t  # features[0:4] = stem + 3 blocks (mobilenet_v2.py:125)
+    return t.permute(0, 3, 1, 2), low.permute(0, 3, 1, 2)
+
+
+def _rn50_train_forward(bb, x, autocast_dtype):
+    """resnet_backbone.py:87-104 / resnet_models.py:74-94 in train mode on NHWC bf16 tensors."""
+    with torch.autocast("cuda", dtype=autocast_dtype):
+        t = bb.maxpool(bb.prefix(x))  # 7x7 s2 stem (Cin = 3) + max-pool: library ops
+    t = t.permute(0, 2, 3, 1)
+    if not t.is_contiguous():
+        t = t.contiguous()
+    c2 = None
+    for li, layer in enumerate((bb.layer1, bb.layer2, bb.layer3, bb.layer4)):
+        for blk in layer:
+            strided = blk.conv2.stride != (1, 1)
+            o = _cba(t, blk.conv1, blk.bn1)
+            if strided:  # layer2.0: 3x3 stride 2 as nine stride-1 taps on the space-to-depth tensor
+                o = _cba(space_to_depth(o), blk.conv2, blk.bn2, s2d=True)
+            else:
+                o = _cba(o, blk.conv2, blk.bn2)
+            idn = t
+            if blk.downsample is not None:
+                src = t[:, ::2, ::2].contiguous() if blk.downsample[0].stride != (1, 1) else t  # 1x1 stride 2 = subsample
+                idn = _cba(src, blk.downsample[0], blk.downsample[1])
+            t = _cba(o, blk.conv3, blk.bn3, res=idn)  # relu(bn3(conv3) + identity)
+        if li == 0:
+            c2 = t
+    return t.permute(0, 3, 1, 2), c2.permute(0, 3, 1, 2)
+
+
+# =============================================================================================
 # encoders, inference: every 1x1 / dilated 3x3 conv on pp_conv_igemm with the folded BatchNorm, the activation and the
 # residual add in its epilogue; depthwise 3x3 + BatchNorm + ReLU6 in one kernel.  (Training keeps the module path above:
 # train-mode BatchNorm needs the batch statistics of the raw conv output first.)
@@ -660,6 +812,9 @@ class DeepLab(nn.Module):
         # to 32 images of 256x512 per call (3x at batch 1; above that the library convs + fused BatchNorm kernels are
         # ~10 % ahead because the 1x1 expansions are bound by our conv epilogue — scripts/bench_enc_layers.py)
         self.fused_eval_encoder = "auto"
+        # training: the encoders' dense convs on the tcgen05 kernels with the BatchNorm statistics taken in the conv epilogue
+        # (PP_TRAIN_ENCODER=module keeps the PyTorch-module path with library convs: A/B measurements only)
+        self.fused_train_encoder = os.environ.get("PP_TRAIN_ENCODER", "fused") != "module"
 
     # ---- reference API ----
     def turn_on_dropout(self):
@@ -723,6 +878,11 @@ class DeepLab(nn.Module):
             if c["enc"] is not None:
                 fwd = _mnv2_eval_forward if isinstance(self.backbone, MobileNetV2) else _rn50_eval_forward
                 return fwd(self.backbone, c["enc"], x, self.encoder_autocast)
+        if self.fused_train_encoder and self.backbone.training and torch.is_grad_enabled():
+            fwd = _mnv2_train_forward if isinstance(self.backbone, MobileNetV2) else _rn50_train_forward
+            out = fwd(self.backbone, x, self.encoder_autocast)
+            if out is not None:
+                return out
         with torch.autocast("cuda", dtype=self.encoder_autocast):
             return self.backbone(x)
 

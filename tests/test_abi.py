@@ -55,7 +55,8 @@ def test_every_entry_point_rejects_null_arguments_before_any_cuda_call():
     naming itself (or the entry point it forwards to) - no CUDA call, no crash, so it holds on a host without a GPU."""
     l = _lib.lib()
     skip = {"pp_device_info",            # queries the device first (PP_ERR_CUDA here)
-            "pp_acq_session_destroy"}    # destroy(NULL) is a no-op, like free(NULL)
+            "pp_acq_session_destroy",    # destroy(NULL) is a no-op, like free(NULL)
+            "pp_conv_set_epilogue"}      # a process-wide switch: takes no pointer, returns the previous setting
     checked = 0
     for name, (argtypes, restype) in sorted(_lib._SIGNATURES.items()):
         if restype is not ctypes.c_int or not argtypes or name in skip:
