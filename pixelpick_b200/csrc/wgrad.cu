@@ -9,6 +9,7 @@
 // the instruction descriptor carries a_major = b_major = MN.  The shifted X box is zero-filled by TMA
 // outside the image (the conv's padding).  K is split over CTAs; partial tiles are reduced with
 // fp32 red.global.add.v4 into dW (zeroed by the caller; rows are 16-byte aligned: Cout_pad is a multiple of 64).
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace pp {
@@ -32,13 +33,18 @@ struct WgradParams {
   int Cin_rows, ld_dw;
 };
 
-template <int BN>
+// NX = X tiles per CTA that share ONE dY tile.  With NX = 2 a stage carries dY (BN channels) + two X tiles (2 x 128 channels)
+// for two 128 x BN x 64 MMAs: 64 KB per 8.4 MFLOP instead of 48 KB per 4.2 - the single-tile form is bound by the fill rate
+// of shared memory (ncu on the 512 -> 512 3x3: tensor pipe 57-62 % busy, L2 hit 82 %, DRAM 13 %), the pair form by the
+// tensor pipe.  The two X tiles are consecutive entries of the list (tap, ci-tile): two input-channel tiles of one tap, or
+// two taps of one channel tile when Cin <= 128.
+template <int BN, int NX>
 struct WgCfg {
-  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
-  static constexpr uint32_t A_BYTES = 2 * kBoxBytes;
+  static constexpr uint32_t A_BYTES = NX * 2 * kBoxBytes;
   static constexpr uint32_t B_BYTES = (BN / 64) * kBoxBytes;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int STAGES = (int)((200u * 1024u) / STAGE_BYTES) > 6 ? 6 : (int)((200u * 1024u) / STAGE_BYTES);
+  static constexpr uint32_t TMEM_COLS = (NX * BN) < 32 ? 32 : NX * BN;  // 64 .. 512, a power of two
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
 };
 
@@ -46,14 +52,14 @@ __device__ __forceinline__ bool pb_skipped(int dy, int dx, int y0, int x0, int H
   return (y0 + dy + kPB <= 0) || (y0 + dy >= H) || (x0 + dx + kPB <= 0) || (x0 + dx >= W);
 }
 
-template <int BN>
+template <int BN, int NX>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WgradParams p) {
-  using Cfg = WgCfg<BN>;
+  using Cfg = WgCfg<BN, NX>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  auto sA = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES; };
+  auto sA = [&](int s, int a) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES + (uint32_t)a * 2u * kBoxBytes; };
   auto sB = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
@@ -63,16 +69,29 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - tc::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // work item
+  // work item: (x-tile group, co-tile, split); the x-tile group varies fastest so that CTAs resident together read the
+  // same dY tile (L2 hits) - x tile = (tap, ci-tile), group g covers tiles NX*g .. NX*g + NX-1
+  const int n_xtiles = p.taps * p.n_ci_tiles;
+  const int n_groups = (n_xtiles + NX - 1) / NX;
   int item = blockIdx.x;
-  const int split = item % p.splits;
-  item /= p.splits;
-  const int ci_tile = item % p.n_ci_tiles;
-  item /= p.n_ci_tiles;
+  const int group = item % n_groups;
+  item /= n_groups;
   const int co_tile = item % p.n_co_tiles;
-  const int tap = item / p.n_co_tiles;
-  const int ci0 = ci_tile * 128, co0 = co_tile * BN;
-  const int dy = p.tdy[tap], dx = p.tdx[tap], xc0 = p.tc0[tap];
+  const int split = item / p.n_co_tiles;
+  const int co0 = co_tile * BN;
+  int tap[NX], ci0[NX], dy[NX], dx[NX], xc0[NX];
+  bool act[NX];
+#pragma unroll
+  for (int a = 0; a < NX; ++a) {
+    const int xt = group * NX + a;
+    act[a] = xt < n_xtiles;
+    const int xtc = act[a] ? xt : 0;
+    tap[a] = xtc / p.n_ci_tiles;
+    ci0[a] = (xtc - tap[a] * p.n_ci_tiles) * 128;
+    dy[a] = p.tdy[tap[a]];
+    dx[a] = p.tdx[tap[a]];
+    xc0[a] = p.tc0[tap[a]];
+  }
   const int pb_per_img = p.pby * p.pbx;
   const int total_pb = p.N * pb_per_img;
   const int pb_lo = (int)((int64_t)total_pb * split / p.splits);
@@ -106,6 +125,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     y0 = ty * kPB;
     x0 = (r - ty * p.pbx) * kPB;
   };
+  // a pixel block is skipped when the shifted X box of EVERY active tile lies outside the image (its products are zero);
+  // a tile that is outside while its partner is not is loaded anyway: TMA zero-fills it
+  auto skipped = [&](int y0, int x0) {
+    bool sk = true;
+#pragma unroll
+    for (int a = 0; a < NX; ++a)
+      if (act[a]) sk = sk && pb_skipped(dy[a], dx[a], y0, x0, p.H, p.W);
+    return sk;
+  };
+  const uint32_t stage_tx = Cfg::B_BYTES + (uint32_t)((act[0] ? 1 : 0) + (NX > 1 && act[NX - 1] ? 1 : 0)) * 2u * kBoxBytes;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -113,17 +142,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       for (int pb = pb_lo; pb < pb_hi; ++pb) {
         int img, y0, x0;
         decode(pb, img, y0, x0);
-        if (pb_skipped(dy, dx, y0, x0, p.H, p.W)) continue;
+        if (skipped(y0, x0)) continue;
         const int s = it % Cfg::STAGES;
         const uint32_t ph = (it / Cfg::STAGES) & 1u;
         tc::mbar_wait(empty_bar(s), ph ^ 1u);
-        tc::mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-          tc::tma_load_4d(sA(s) + j * kBoxBytes, &tmX, full_bar(s), xc0 + ci0 + 64 * j, x0 + dx, y0 + dy, img);
+        tc::mbar_expect_tx(full_bar(s), stage_tx);
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
           tc::tma_load_4d(sB(s) + j * kBoxBytes, &tmDY, full_bar(s), co0 + 64 * j, x0, y0, img);
+#pragma unroll
+        for (int a = 0; a < NX; ++a)
+          if (act[a]) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              tc::tma_load_4d(sA(s, a) + j * kBoxBytes, &tmX, full_bar(s), xc0[a] + ci0[a] + 64 * j, x0 + dx[a], y0 + dy[a], img);
+          }
         ++it;
       }
     }
@@ -135,16 +168,20 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       for (int pb = pb_lo; pb < pb_hi; ++pb) {
         int img, y0, x0;
         decode(pb, img, y0, x0);
-        if (pb_skipped(dy, dx, y0, x0, p.H, p.W)) continue;
+        if (skipped(y0, x0)) continue;
         const int s = it % Cfg::STAGES;
         const uint32_t ph = (it / Cfg::STAGES) & 1u;
         tc::mbar_wait(full_bar(s), ph);
         tc::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // 64 pixels = 4 x K16; 16 pixel rows = 2048 B
-          const uint64_t da = tc::umma_desc_sw128(sA(s) + k * 2048, kBoxBytes, 1024);
           const uint64_t db = tc::umma_desc_sw128(sB(s) + k * 2048, kBoxBytes, 1024);
-          tc::umma_bf16(tmem_base, da, db, idesc, accumulate);
+#pragma unroll
+          for (int a = 0; a < NX; ++a)
+            if (act[a]) {
+              const uint64_t da = tc::umma_desc_sw128(sA(s, a) + k * 2048, kBoxBytes, 1024);
+              tc::umma_bf16(tmem_base + (uint32_t)a * BN, da, db, idesc, accumulate);
+            }
           accumulate = 1;
         }
         tc::umma_commit(empty_bar(s));
@@ -160,25 +197,29 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     for (int pb = pb_lo; pb < pb_hi; ++pb) {
       int img, y0, x0;
       decode(pb, img, y0, x0);
-      n_valid += pb_skipped(dy, dx, y0, x0, p.H, p.W) ? 0 : 1;
+      n_valid += skipped(y0, x0) ? 0 : 1;
     }
     tc::mbar_wait(tfull_bar, 0);
     tc::tc_fence_after();
     if (n_valid > 0) {
-      const int ci = ci0 + row;
-      float* dst = p.dw + ((size_t)tap * p.Cin_rows + ci) * p.ld_dw + co0;
-#pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + j * 32, r);
-        tc::tmem_ld_wait();
-        if (ci < p.Cin) {
-          // 16-byte vector reductions (red.global.add.v4.f32, sm_90+): 8 L2 operations per row chunk instead of 32
 #pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j * 32 + c), "f"(__uint_as_float(r[c])),
-                         "f"(__uint_as_float(r[c + 1])), "f"(__uint_as_float(r[c + 2])), "f"(__uint_as_float(r[c + 3]))
-                         : "memory");
+      for (int a = 0; a < NX; ++a) {
+        if (!act[a]) continue;
+        const int ci = ci0[a] + row;
+        float* dst = p.dw + ((size_t)tap[a] * p.Cin_rows + ci) * p.ld_dw + co0;
+#pragma unroll 1
+        for (int j = 0; j < BN / 32; ++j) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * BN + j * 32, r);
+          tc::tmem_ld_wait();
+          if (ci < p.Cin) {
+            // 16-byte vector reductions (red.global.add.v4.f32, sm_90+): 8 L2 operations per row chunk instead of 32
+#pragma unroll
+            for (int c = 0; c < 32; c += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j * 32 + c), "f"(__uint_as_float(r[c])),
+                           "f"(__uint_as_float(r[c + 1])), "f"(__uint_as_float(r[c + 2])), "f"(__uint_as_float(r[c + 3]))
+                           : "memory");
+          }
         }
       }
     }
@@ -191,16 +232,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   }
 }
 
-template <int BN>
+template <int BN, int NX>
 static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradParams& p, cudaStream_t st) {
-  using Cfg = WgCfg<BN>;
+  using Cfg = WgCfg<BN, NX>;
   static bool attr = false;
   if (!attr) {
-    PP_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    PP_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr = true;
   }
-  const int grid = p.taps * p.n_co_tiles * p.n_ci_tiles * p.splits;
-  wgrad_kernel<BN><<<grid, kWgThreads, Cfg::SMEM, st>>>(tmX, tmDY, p);
+  const int n_groups = (p.taps * p.n_ci_tiles + NX - 1) / NX;
+  const int grid = n_groups * p.n_co_tiles * p.splits;
+  wgrad_kernel<BN, NX><<<grid, kWgThreads, Cfg::SMEM, st>>>(tmX, tmDY, p);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
@@ -259,11 +301,22 @@ int pp_conv_wgrad_multi(const void* x, int x_channels, int ld_x, int Cin, const 
   p.n_ci_tiles = n_ci_tiles;
   p.n_co_tiles = n_co_tiles;
   const int total_pb = N * p.pby * p.pbx;
+  // two X tiles per CTA (sharing the dY tile) whenever there are at least two of them
+  static int force_nx = -1;
+  if (force_nx < 0) {
+    const char* e = getenv("PP_WGRAD_NX");  // "1": the single-tile form (A/B measurements)
+    force_nx = (e && e[0] == '1') ? 1 : 0;
+  }
+  const int NX = (n_entries * n_ci_tiles >= 2 && !force_nx) ? 2 : 1;
+  const int n_groups = (n_entries * n_ci_tiles + NX - 1) / NX;
   if (splits <= 0) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    splits = (2 * sms) / (n_entries * n_ci_tiles * n_co_tiles);  // <= 2 full waves: one extra CTA would cost a whole third wave
+    const int items = n_groups * n_co_tiles;
+    // whole waves: the largest split count that keeps the grid within one wave if the items allow it, else two
+    splits = sms / items;
+    if (splits < 1) splits = (2 * sms) / items;
     const int max_splits = (total_pb + 7) / 8;  // at least 8 pixel blocks (512 pixels) per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -289,10 +342,17 @@ int pp_conv_wgrad_multi(const void* x, int x_channels, int ld_x, int Cin, const 
     if (rc != PP_OK) return rc;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (NX == 2) {
+    switch (BN) {
+      case 256: return launch_wgrad<256, 2>(tmX, tmDY, p, st);
+      case 128: return launch_wgrad<128, 2>(tmX, tmDY, p, st);
+      default: return launch_wgrad<64, 2>(tmX, tmDY, p, st);
+    }
+  }
   switch (BN) {
-    case 256: return launch_wgrad<256>(tmX, tmDY, p, st);
-    case 128: return launch_wgrad<128>(tmX, tmDY, p, st);
-    default: return launch_wgrad<64>(tmX, tmDY, p, st);
+    case 256: return launch_wgrad<256, 1>(tmX, tmDY, p, st);
+    case 128: return launch_wgrad<128, 1>(tmX, tmDY, p, st);
+    default: return launch_wgrad<64, 1>(tmX, tmDY, p, st);
   }
 }
 
