@@ -127,6 +127,15 @@ int pp_acq_entropy_at(const void* logits, int dtype, int n_img, int C, int H, in
 int pp_acq_entropy_at_upsampled(const float* logits_lowres, int n_img, int C, int h_in, int w_in,
                                 int H, int W, const int32_t* px_idx, int n, float* out, void* stream);
 
+/* QueryStats.update at the picks (query.py:296-308) + the wire-format coordinates of encode_query (query.py:72-87), on the
+ * device: for every image's n picks (flat indices sorted ascending = np.where order) -> x_coords / y_coords (int64 [n_img][n]),
+ * the labels at the picks (labels: uint8 [n_img][HW] or NULL), their histogram (label_hist[n_classes] += , _count_labels), the
+ * number of distinct labels per image and the spatial coverage = mean pairwise distance over the n (n - 1) ordered pairs in
+ * float64 with NumPy's pairwise summation order (bit-identical to np.mean; NaN for n < 2). */
+int pp_query_stats_at(const long long* sel_sorted, int n_img, int n, int W, int HW, const uint8_t* labels, int n_classes,
+                      long long* x_coords, long long* y_coords, int32_t* labels_at, long long* label_hist, int32_t* n_unique,
+                      double* coverage, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Q path through HOST buffers (the call a non-PyTorch host makes; bench.py's `e2e`).
  * A session owns device staging buffers, pinned host buffers and two streams; `run_host` copies
@@ -328,6 +337,11 @@ int pp_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, 
  * fwd [taps][Cout_pad][Cin_pad] and/or dgrad [taps][Cin_rows][Cout_cols] (taps flipped); zero padded; either NULL. */
 int pp_pack_conv_weight(const float* w, int Cout, int Cin, int Cin_total, int taps, void* fwd, int Cout_pad,
                         int Cin_pad, void* dgrad, int Cin_rows, int Cout_cols, void* stream);
+
+/* The same for EVERY convolution of a network in one launch (a train step re-packs ~50 weights after each optimiser
+ * update): table_dev = device array of n rows of 11 int64 {w, fwd, dgrad pointers, Cout, Cin, Cin_total, taps, Cout_pad,
+ * Cin_pad, Cin_rows, Cout_cols} with the meaning of pp_pack_conv_weight's arguments; blocks_per_conv CTAs work on each row. */
+int pp_pack_conv_weights_batched(const long long* table_dev, int n, int blocks_per_conv, void* stream);
 /* strided [N,C,H,W] f32/bf16 -> bf16 NHWC channel slice (backbone boundary, d(logits) for the classifier) */
 int pp_to_nhwc_bf16(const void* in, int dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw, int N, int C, int H,
                     int W, void* out, int ld, int c_off, void* stream);

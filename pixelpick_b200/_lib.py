@@ -46,6 +46,7 @@ _SIGNATURES = {
     "pp_acq_gather": ([_vp, _i, _i, _vp, _i, _vp, _vp], _i),
     "pp_acq_entropy_at": ([_vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _i, _vp, _vp], _i),
     "pp_acq_entropy_at_upsampled": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp], _i),
+    "pp_query_stats_at": ([_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "pp_acq_session_create": ([C.POINTER(_vp), _i, _i, _i, _i, _i, _i], _i),
     "pp_acq_session_destroy": ([_vp], _i),
     "pp_acq_session_run_host": ([_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp], _i),
@@ -83,6 +84,7 @@ _SIGNATURES = {
     "pp_upsample_nhwc_bf16": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp], _i),
     "pp_upsample_nhwc_bf16_bwd": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_pack_conv_weight": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp], _i),
+    "pp_pack_conv_weights_batched": ([_vp, _i, _i, _vp], _i),
     "pp_to_nhwc_bf16": ([_vp, _i, _i64, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_conv_igemm": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp], _i),
 }
@@ -291,6 +293,28 @@ def acq_entropy_at_upsampled(logits_lowres, size, px_idx):
     return out
 
 
+def query_stats_at(sel_sorted, W, HW, labels=None, n_classes=1, label_hist=None):
+    """QueryStats at the picks on the device: sel_sorted int64 [n_img, n] (ascending flat indices), labels uint8 [n_img, HW]
+    or None -> (x_coords, y_coords int64 [n_img, n], labels_at int32 | None, n_unique int32 | None, coverage f64 [n_img]);
+    label_hist (int64 [n_classes], device) is incremented in place."""
+    _need_cuda(sel_sorted, labels, label_hist)
+    assert sel_sorted.dtype == torch.int64 and sel_sorted.is_contiguous()
+    n_img, n = sel_sorted.shape
+    dev = sel_sorted.device
+    xs = torch.empty((n_img, n), dtype=torch.int64, device=dev)
+    ys = torch.empty((n_img, n), dtype=torch.int64, device=dev)
+    cov = torch.empty(n_img, dtype=torch.float64, device=dev)
+    lab_at = uniq = None
+    if labels is not None:
+        assert labels.dtype == torch.uint8 and labels.is_contiguous() and labels.numel() == n_img * HW
+        assert label_hist is not None and label_hist.dtype == torch.int64 and label_hist.numel() == n_classes
+        lab_at = torch.empty((n_img, n), dtype=torch.int32, device=dev)
+        uniq = torch.empty(n_img, dtype=torch.int32, device=dev)
+    check(lib().pp_query_stats_at(_ptr(sel_sorted), n_img, n, W, HW, _ptr(labels), n_classes, _ptr(xs), _ptr(ys), _ptr(lab_at),
+                                  _ptr(label_hist), _ptr(uniq), _ptr(cov), _stream(sel_sorted)), "pp_query_stats_at")
+    return xs, ys, lab_at, uniq, cov
+
+
 def sparse_ce(logits_lowres, size, px_img, px_idx, px_label, grad_scale=1.0, want_grad=True, want_pred=False,
               n_valid=None):
     """(loss[1], grad_lowres | None, pred_at | None); see pp_sparse_ce in the header.  n_valid: optional device int32
@@ -407,6 +431,13 @@ def pack_conv_weights(w, cin=None, fwd_pad=None, dgrad_pad=None, dgrad_out=None)
     return fwd, dgr
 
 
+def pack_conv_weights_batched(table, n, blocks_per_conv=256):
+    """table: device int64 [n, 11] (see pp_pack_conv_weights_batched): re-packs every listed conv weight in one launch."""
+    _need_cuda(table)
+    assert table.dtype == torch.int64 and table.is_contiguous() and table.numel() == 11 * n
+    check(lib().pp_pack_conv_weights_batched(_ptr(table), n, blocks_per_conv, _stream(table)), "pp_pack_conv_weights_batched")
+
+
 def conv_igemm(x_nhwc, w_packed, cout, dil=1, pre_bias=None, scale=None, shift=None, relu=False, out=None,
                out_mode=0, c_off=0, cin=None, block_n=0):
     """x_nhwc: bf16 [N, H, W, ld_in]; returns bf16 NHWC [N, H, W, ld_out] (out_mode 0) or f32 NCHW (out_mode 1)."""
@@ -492,7 +523,7 @@ def conv_fused(x_nhwc, w_packed, cout, dil=1, scale=None, shift=None, act=0, res
     return out
 
 
-def conv_wgrad_multi(x_nhwc, cin, dy_nhwc, cout, entries, splits=0):
+def conv_wgrad_multi(x_nhwc, cin, dy_nhwc, cout, entries, splits=0, out=None):
     """weight gradient of a conv given as a tap table: f32 [taps][Cin_rows][ld] with entry t = sum_p x[p + (dy, dx), c0 + ci] *
     dy[p, co]; Cin_rows = cin rounded up to 8, ld = cout rounded up to the kernel's output-channel tile."""
     _need_cuda(x_nhwc, dy_nhwc)
@@ -503,7 +534,11 @@ def conv_wgrad_multi(x_nhwc, cin, dy_nhwc, cout, entries, splits=0):
     ld = -(-cout // bn) * bn
     rows = -(-cin // 8) * 8
     taps = len(entries)
-    dw = torch.zeros((taps, rows, ld), dtype=torch.float32, device=x_nhwc.device)
+    if out is None:
+        dw = torch.zeros((taps, rows, ld), dtype=torch.float32, device=x_nhwc.device)
+    else:  # a zeroed slice of a per-network gradient arena
+        dw = out
+        assert dw.dtype == torch.float32 and dw.is_contiguous() and tuple(dw.shape) == (taps, rows, ld)
     dy, dx, c0 = _tap_arrays(entries)
     check(lib().pp_conv_wgrad_multi(_ptr(x_nhwc), ld_x, ld_x, cin, _ptr(dy_nhwc), dy_nhwc.shape[3], cout, N, H, W, taps, dy, dx, c0,
                                     _ptr(dw), rows, ld, splits, _stream(x_nhwc)), "pp_conv_wgrad_multi")
@@ -536,7 +571,7 @@ def bn_stats(raw, c_off, C):
     return sums
 
 
-def bn_finalize(sums, M, bn, Cpad=None, update_running=True):
+def bn_finalize(sums, M, bn, Cpad=None, update_running=True, count=True):
     """f32 [4, Cpad] = (scale, shift, mean, rstd) from bn_stats output and an nn.BatchNorm2d's parameters."""
     C = sums.shape[1]
     Cpad = Cpad or C
@@ -546,7 +581,7 @@ def bn_finalize(sums, M, bn, Cpad=None, update_running=True):
     check(lib().pp_bn_finalize(_ptr(sums), C, M, bn.eps, mom, _ptr(bn.weight.detach()), _ptr(bn.bias.detach()),
                                _ptr(bn.running_mean) if upd else None, _ptr(bn.running_var) if upd else None,
                                _ptr(out), Cpad, _stream(sums)), "pp_bn_finalize")
-    if upd:
+    if upd and count:  # count=False: the caller advances the counters of many layers with one batched op
         bn.num_batches_tracked += 1
     return out
 

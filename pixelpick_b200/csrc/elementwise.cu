@@ -1060,6 +1060,46 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
 }
 }  // namespace pp
 
+namespace pp {
+// every conv of a network in ONE launch: blockIdx.y = table row (w, fwd, dgrad pointers + the shapes of pack_weight_kernel)
+__global__ void __launch_bounds__(256) pack_weight_batched_kernel(const long long* __restrict__ table) {
+  const long long* d = table + (size_t)blockIdx.y * 11;
+  const float* w = reinterpret_cast<const float*>(d[0]);
+  __nv_bfloat16* fwd = reinterpret_cast<__nv_bfloat16*>(d[1]);
+  __nv_bfloat16* dgr = reinterpret_cast<__nv_bfloat16*>(d[2]);
+  const int Cout = (int)d[3], Cin = (int)d[4], Cin_total = (int)d[5], taps = (int)d[6];
+  const int Cout_pad = (int)d[7], Cin_pad = (int)d[8], Cin_rows = (int)d[9], Cout_cols = (int)d[10];
+  const int64_t n_f = fwd ? (int64_t)taps * Cout_pad * Cin_pad : 0;
+  const int64_t n_d = dgr ? (int64_t)taps * Cin_rows * Cout_cols : 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_f + n_d; i += (int64_t)gridDim.x * 256) {
+    if (i < n_f) {
+      const int ci = (int)(i % Cin_pad);
+      const int64_t t = i / Cin_pad;
+      const int co = (int)(t % Cout_pad), tap = (int)(t / Cout_pad);
+      float v = 0.f;
+      if (ci < Cin && co < Cout) v = w[((int64_t)co * Cin_total + ci) * taps + tap];
+      fwd[i] = __float2bfloat16(v);
+    } else {
+      const int64_t j = i - n_f;
+      const int co = (int)(j % Cout_cols);
+      const int64_t t = j / Cout_cols;
+      const int ci = (int)(t % Cin_rows), tap = (int)(t / Cin_rows);
+      float v = 0.f;
+      if (ci < Cin && co < Cout) v = w[((int64_t)co * Cin_total + ci) * taps + (taps - 1 - tap)];
+      dgr[j] = __float2bfloat16(v);
+    }
+  }
+}
+}  // namespace pp
+
+extern "C" int pp_pack_conv_weights_batched(const long long* table_dev, int n, int blocks_per_conv, void* stream) {
+  PP_CHECK_ARG(table_dev && n > 0 && n <= 65535 && blocks_per_conv > 0, "pp_pack_conv_weights_batched: bad args");
+  dim3 grid((unsigned)blocks_per_conv, (unsigned)n);
+  pp::pack_weight_batched_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table_dev);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
 extern "C" int pp_pack_conv_weight(const float* w, int Cout, int Cin, int Cin_total, int taps, void* fwd, int Cout_pad,
                                    int Cin_pad, void* dgrad, int Cin_rows, int Cout_cols, void* stream) {
   PP_CHECK_ARG(w && (fwd || dgrad) && Cout > 0 && Cin > 0 && Cin <= Cin_total && taps > 0, "pp_pack_conv_weight: bad args");

@@ -552,24 +552,97 @@ def s2d_entries(Cc):
     return ent
 
 
+class _Slot:
+    """per-conv views into the arenas of an _EncoderTrainPlan"""
+    __slots__ = ("wp", "wd", "stats", "dw", "dirty")
+
+
+class _EncoderTrainPlan:
+    """Per-step buffers of ALL dense encoder convs in a few arenas, so a train step issues one weight-pack launch and two
+    memsets for the whole encoder instead of three small launches per conv (at the reference batch of 4 the step is bound
+    by the number of graph nodes, not by their work): packed bf16 weights (forward + data-gradient images), the
+    BatchNorm-statistics accumulators the conv epilogues add into, and the fp32 weight-gradient accumulators of the
+    split-K wgrad."""
+
+    def __init__(self, convs, device):
+        def a16(n):  # 16-byte aligned element counts
+            return -(-n // 8) * 8
+        sizes, rows = [], []
+        n_wp = n_wd = n_st = n_dw = 0
+        for conv in convs:
+            co, ci, k = conv.out_channels, conv.in_channels, conv.kernel_size[0]
+            taps = k * k
+            fwd = (taps, _cpad(co), -(-ci // 64) * 64)
+            dgr = (taps, _cpad(ci), -(-co // 64) * 64)
+            bn = 256 if co > 128 else (128 if co > 64 else 64)
+            dw = (taps, -(-ci // 8) * 8, -(-co // bn) * bn)
+            sizes.append((fwd, dgr, dw, co, ci, taps, n_wp, n_wd, n_st, n_dw))
+            n_wp += a16(fwd[0] * fwd[1] * fwd[2])
+            n_wd += a16(dgr[0] * dgr[1] * dgr[2])
+            n_st += a16(2 * co)
+            n_dw += a16(dw[0] * dw[1] * dw[2])
+        self.wp = torch.empty(n_wp, dtype=torch.bfloat16, device=device)
+        self.wd = torch.empty(n_wd, dtype=torch.bfloat16, device=device)
+        self.stats = torch.zeros(n_st, dtype=torch.float32, device=device)
+        self.dw = torch.zeros(n_dw, dtype=torch.float32, device=device)
+        self.slots = {}
+        for conv, (fwd, dgr, dw, co, ci, taps, o_wp, o_wd, o_st, o_dw) in zip(convs, sizes):
+            sl = _Slot()
+            sl.wp = self.wp[o_wp:o_wp + fwd[0] * fwd[1] * fwd[2]].view(fwd)
+            sl.wd = self.wd[o_wd:o_wd + dgr[0] * dgr[1] * dgr[2]].view(dgr)
+            sl.stats = self.stats[o_st:o_st + 2 * co].view(2, co)
+            sl.dw = self.dw[o_dw:o_dw + dw[0] * dw[1] * dw[2]].view(dw)
+            sl.dirty = False
+            self.slots[id(conv)] = sl
+            rows.append([conv.weight.data_ptr(), sl.wp.data_ptr(), sl.wd.data_ptr(), co, ci, ci, taps, fwd[1], fwd[2], dgr[1], dgr[2]])
+        self.counters = []  # num_batches_tracked of the BatchNorm layers that follow these convs (filled by the forward)
+        self.weights = [conv.weight for conv in convs]
+        self.ptrs = [w.data_ptr() for w in self.weights]
+        self.table = torch.tensor(rows, dtype=torch.int64).to(device)
+        self.n = len(rows)
+
+    def valid(self):
+        return all(w.data_ptr() == p for w, p in zip(self.weights, self.ptrs))
+
+    def begin_step(self):
+        """zero the accumulators, re-pack every weight (they changed in the optimiser step): three launches"""
+        self.stats.zero_()
+        self.dw.zero_()
+        for sl in self.slots.values():
+            sl.dirty = False
+        self.step_counters = []
+        _lib.pack_conv_weights_batched(self.table, self.n)
+
+    def end_forward(self):
+        """nn.BatchNorm2d.num_batches_tracked += 1 for every layer the forward went through: one multi-tensor launch"""
+        if self.step_counters:
+            torch._foreach_add_(self.step_counters, 1)
+            self.step_counters = []
+
+
 class _ConvBNActFn(torch.autograd.Function):
     """y = act(BatchNorm_train(conv(x)) [+ res]) on NHWC bf16 tensors, one autograd node.
-    x [N, H, W, Cin] (or its space-to-depth form for the stride-2 3x3), w fp32 [Cout, Cin, k, k] (the master weight)."""
+    x [N, H, W, Cin] (or its space-to-depth form for the stride-2 3x3), w fp32 [Cout, Cin, k, k] (the master weight);
+    slot: this conv's views into the step's arenas (_EncoderTrainPlan) or None (self-contained: packs / zeroes per call)."""
 
     @staticmethod
-    def forward(ctx, x, w, gamma, beta, bn, act, res, dil, s2d):
+    def forward(ctx, x, w, gamma, beta, bn, act, res, dil, s2d, slot):
         cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
         taps = k * k
         N, H, W, xc = x.shape
         cin_pad, rows_pad = -(-cin // 64) * 64, _cpad(cin)
         need_dx = bool(x.requires_grad)
-        wp, wd = _lib.pack_conv_weights(w, cin, fwd_pad=(_cpad(cout), cin_pad),
-                                        dgrad_pad=(rows_pad, -(-cout // 64) * 64) if need_dx else None)
         entries = s2d_entries(cin) if s2d else None
         raw = torch.empty((N, H, W, cout), dtype=torch.bfloat16, device=x.device)
-        stats = torch.zeros((2, cout), dtype=torch.float32, device=x.device)
+        if slot is None:
+            wp, wd = _lib.pack_conv_weights(w, cin, fwd_pad=(_cpad(cout), cin_pad),
+                                            dgrad_pad=(rows_pad, -(-cout // 64) * 64) if need_dx else None)
+            stats = torch.zeros((2, cout), dtype=torch.float32, device=x.device)
+        else:
+            wp, wd, stats = slot.wp, slot.wd, slot.stats
+        ctx.slot = slot
         _lib.conv_fused(x, wp, cout, dil=dil, out=raw, stats=stats, entries=entries)
-        st = _lib.bn_finalize(stats, N * H * W, bn)
+        st = _lib.bn_finalize(stats, N * H * W, bn, count=slot is None)  # with a plan: counters advance in one batched op
         y = torch.empty_like(raw)
         _lib.bn_apply(raw, 0, cout, st[0], st[1], act, y, 0, res=res)
         ctx.bn, ctx.act, ctx.cfg, ctx.need_dx = bn, act, (cin, cout, k, dil, s2d), need_dx
@@ -597,7 +670,14 @@ class _ConvBNActFn(torch.autograd.Function):
             entries = [(0, 0, 0)]
         else:
             entries = [((t // 3 - 1) * dil, (t % 3 - 1) * dil, 0) for t in range(9)]
-        dw = _lib.conv_wgrad_multi(x, cin, draw, cout, entries)
+        slot = ctx.slot
+        out_dw = None
+        if slot is not None:
+            if slot.dirty:  # a second backward through this conv before the next forward: start from zero again
+                slot.dw.zero_()
+            slot.dirty = True
+            out_dw = slot.dw
+        dw = _lib.conv_wgrad_multi(x, cin, draw, cout, entries, out=out_dw)
         dW = dw[:, :cin, :cout].permute(2, 1, 0).reshape(cout, cin, k, k)
         dx = None
         if ctx.need_dx:
@@ -611,12 +691,23 @@ class _ConvBNActFn(torch.autograd.Function):
                     sel = [(t, e) for t, e in enumerate(entries) if e[2] == ph * cin]
                     wsel = torch.stack([wd[8 - t] for t, _ in sel])  # the dgrad pack holds W^T with the taps flipped
                     _lib.conv_fused(draw, wsel, cin, out=dx, c_off=ph * cin, entries=[(-e[0], -e[1], 0) for _, e in sel])
-        return dx, dW, sums[1], sums[0], None, None, dres, None, None
+        return dx, dW, sums[1], sums[0], None, None, dres, None, None, None
 
 
-def _cba(x, conv, bn, res=None, s2d=False):
+def _cba(x, conv, bn, res=None, s2d=False, plan=None):
     """conv -> train-mode BatchNorm -> bn.act (-> + res before the activation) on an NHWC bf16 tensor"""
-    return _ConvBNActFn.apply(x, conv.weight, bn.weight, bn.bias, bn, bn.act, res, conv.dilation[0], s2d)
+    slot = plan.slots.get(id(conv)) if plan is not None else None
+    if slot is not None and bn.track_running_stats and bn.num_batches_tracked is not None:
+        plan.step_counters.append(bn.num_batches_tracked)
+    return _ConvBNActFn.apply(x, conv.weight, bn.weight, bn.bias, bn, bn.act, res, conv.dilation[0], s2d, slot)
+
+
+def _train_plan(cache, convs, device):
+    plan = cache.get("train_plan")
+    if plan is None or not plan.valid():
+        plan = cache["train_plan"] = _EncoderTrainPlan(convs, device)
+    plan.begin_step()
+    return plan
 
 
 def _bn_act_nhwc(x, bn, res=None):
@@ -630,31 +721,36 @@ def _stem_nhwc(mods, x, autocast_dtype):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def _mnv2_train_forward(bb, x, autocast_dtype):
+def _mnv2_train_forward(bb, x, autocast_dtype, cache):
     """mobilenet_v2.py:130-137 in train mode on NHWC bf16 tensors."""
+    if not all(isinstance(blk, InvertedResidual) for blk in bb.features[1:]):
+        return None  # MC-dropout variant: module path
+    convs = [m for blk in bb.features[1:] for m in blk.conv if isinstance(m, nn.Conv2d) and m.groups == 1]
+    plan = _train_plan(cache, convs, x.device)
     t = _stem_nhwc(bb.features[0], x, autocast_dtype)
     low = None
     for i, blk in enumerate(bb.features[1:]):
-        if not isinstance(blk, InvertedResidual):
-            return None
         mods = list(blk.conv)
         d = blk.dilation
         h = F.pad(t, (0, 0, d, d, d, d))  # fixed_padding (mobilenet_v2.py:15-21) BEFORE the expansion conv
         if len(mods) == 8:
-            h = _cba(h, mods[0], mods[1])
+            h = _cba(h, mods[0], mods[1], plan=plan)
             dw, dw_bn, proj, proj_bn = mods[3], mods[4], mods[6], mods[7]
         else:
             dw, dw_bn, proj, proj_bn = mods[0], mods[1], mods[3], mods[4]
         h = _DWConvFn.apply(h, dw.weight, dw.stride[0], dw.dilation[0])
         h = _bn_act_nhwc(h, dw_bn)
-        t = _cba(h, proj, proj_bn, res=t if blk.use_res_connect else None)  # x + conv(x): the add rides in the BatchNorm pass
+        t = _cba(h, proj, proj_bn, res=t if blk.use_res_connect else None, plan=plan)  # x + conv(x): the add rides in the BatchNorm pass
         if i == 2:
             low = t  # features[0:4] = stem + 3 blocks (mobilenet_v2.py:125)
+    plan.end_forward()
     return t.permute(0, 3, 1, 2), low.permute(0, 3, 1, 2)
 
 
-def _rn50_train_forward(bb, x, autocast_dtype):
+def _rn50_train_forward(bb, x, autocast_dtype, cache):
     """resnet_backbone.py:87-104 / resnet_models.py:74-94 in train mode on NHWC bf16 tensors."""
+    convs = [m for layer in (bb.layer1, bb.layer2, bb.layer3, bb.layer4) for m in layer.modules() if isinstance(m, nn.Conv2d)]
+    plan = _train_plan(cache, convs, x.device)
     with torch.autocast("cuda", dtype=autocast_dtype):
         t = bb.maxpool(bb.prefix(x))  # 7x7 s2 stem (Cin = 3) + max-pool: library ops
     t = t.permute(0, 2, 3, 1)
@@ -664,18 +760,19 @@ def _rn50_train_forward(bb, x, autocast_dtype):
     for li, layer in enumerate((bb.layer1, bb.layer2, bb.layer3, bb.layer4)):
         for blk in layer:
             strided = blk.conv2.stride != (1, 1)
-            o = _cba(t, blk.conv1, blk.bn1)
+            o = _cba(t, blk.conv1, blk.bn1, plan=plan)
             if strided:  # layer2.0: 3x3 stride 2 as nine stride-1 taps on the space-to-depth tensor
-                o = _cba(space_to_depth(o), blk.conv2, blk.bn2, s2d=True)
+                o = _cba(space_to_depth(o), blk.conv2, blk.bn2, s2d=True, plan=plan)
             else:
-                o = _cba(o, blk.conv2, blk.bn2)
+                o = _cba(o, blk.conv2, blk.bn2, plan=plan)
             idn = t
             if blk.downsample is not None:
                 src = t[:, ::2, ::2].contiguous() if blk.downsample[0].stride != (1, 1) else t  # 1x1 stride 2 = subsample
-                idn = _cba(src, blk.downsample[0], blk.downsample[1])
-            t = _cba(o, blk.conv3, blk.bn3, res=idn)  # relu(bn3(conv3) + identity)
+                idn = _cba(src, blk.downsample[0], blk.downsample[1], plan=plan)
+            t = _cba(o, blk.conv3, blk.bn3, res=idn, plan=plan)  # relu(bn3(conv3) + identity)
         if li == 0:
             c2 = t
+    plan.end_forward()
     return t.permute(0, 3, 1, 2), c2.permute(0, 3, 1, 2)
 
 
@@ -804,6 +901,9 @@ class DeepLab(nn.Module):
         self._rng_step = None  # device int64 [1]: dropout step counter (device-side so CUDA-graph replays advance it)
         self.base_seed = 0
         self._cache = {}
+        # arenas of the training encoder (_EncoderTrainPlan): NOT dropped by train() / load_state_dict() - a captured CUDA
+        # graph replays on these addresses; rebuilt only when the parameters themselves move (plan.valid())
+        self._train_cache = {}
         # encoder precision: torch.bfloat16 (default, BASELINE config 2) or None = fp32 (used by the parity tests to
         # separate the encoder's bf16 rounding from the head kernels')
         self.encoder_autocast = torch.bfloat16
@@ -880,7 +980,7 @@ class DeepLab(nn.Module):
                 return fwd(self.backbone, c["enc"], x, self.encoder_autocast)
         if self.fused_train_encoder and self.backbone.training and torch.is_grad_enabled():
             fwd = _mnv2_train_forward if isinstance(self.backbone, MobileNetV2) else _rn50_train_forward
-            out = fwd(self.backbone, x, self.encoder_autocast)
+            out = fwd(self.backbone, x, self.encoder_autocast, self._train_cache)
             if out is not None:
                 return out
         with torch.autocast("cuda", dtype=self.encoder_autocast):

@@ -127,6 +127,19 @@ class QueryStats:
         self.list_n_unique_labels.append(len(set(labels.tolist())))
         self.list_spatial_coverage.append(self._spatial_coverage(flat_idx_sorted // width, flat_idx_sorted % width))
 
+    def update_from_device(self, labels_at, n_unique, coverage, entropies, label_hist):
+        """the same bookkeeping from what pp_query_stats_at computed for a whole batch: labels_at [b, n], n_unique [b],
+        coverage [b] (float64, NumPy's summation order), entropies [b, n], label_hist [n_classes] (this batch's counts)"""
+        n_classes = len(self.dict_label_cnt)
+        if (labels_at < 0).any() or (labels_at >= n_classes).any():
+            raise KeyError(int(labels_at[(labels_at < 0) | (labels_at >= n_classes)][0]))  # as dict_label_cnt[l] would (query.py:268)
+        for l, c in enumerate(label_hist.tolist()):
+            self.dict_label_cnt[l] += int(c)
+        for i in range(labels_at.shape[0]):
+            self.list_entropy.extend([float(e) for e in entropies[i]])
+            self.list_n_unique_labels.append(int(n_unique[i]))
+            self.list_spatial_coverage.append(np.float64(coverage[i]))
+
     def save(self, nth_query):
         dict_stats = {
             "label_distribution": self.dict_label_cnt,
@@ -163,6 +176,7 @@ class _Batch:
         self.n_top = 0
         self.stats_on = False
         self.sel_host = self.ent_host = self.done = None
+        self.lab8 = self.dev_stats = None
 
 
 class QuerySelector:
@@ -189,6 +203,8 @@ class QuerySelector:
         self.vote_type = args.vote_type
         self.batch_imgs = batch_imgs
         self._ws = {}
+        # label maps travel as uint8 when every label (and ignore_index) fits: void mask + QueryStats come from them on the device
+        self._labels_u8 = 0 <= args.ignore_index <= 255 and args.n_classes <= 256
         if self.device.type != "cuda":
             raise _lib.PixelPickError("QuerySelector needs a CUDA device (no CPU fallback)")
 
@@ -309,7 +325,10 @@ class QuerySelector:
         else:
             lab[...] = mask
         if item["y"] is not None:
-            np.equal(item["y"], self.ignore_index, out=s.void[j].numpy().view(bool))  # query.py:196-201: void pixels
+            if self._labels_u8:  # the label map itself (uint8): void mask AND the labels at the picks come from it on the device
+                np.copyto(s.void[j].numpy(), item["y"], casting="unsafe")
+            else:
+                np.equal(item["y"], self.ignore_index, out=s.void[j].numpy().view(bool))  # query.py:196-201: void pixels
         batch.items.append(item)
 
     def _launch(self, model, batch, pick):
@@ -323,7 +342,13 @@ class QuerySelector:
         xs = s.x[:n].to(dev, non_blocking=True)
         labelled = s.lab[:n].to(dev, non_blocking=True).view(torch.bool)
         has_y = batch.items[0]["y"] is not None
-        void = s.void[:n].to(dev, non_blocking=True).view(torch.bool) if has_y else None
+        void = None
+        batch.lab8 = None
+        if has_y and self._labels_u8:
+            batch.lab8 = s.void[:n].to(dev, non_blocking=True)
+            void = batch.lab8 == self.ignore_index
+        elif has_y:
+            void = s.void[:n].to(dev, non_blocking=True).view(torch.bool)
         if dev.type == "cuda":
             if s.event is None:
                 s.event = torch.cuda.Event()
@@ -371,6 +396,17 @@ class QuerySelector:
             kind, t = batch.handle
             ent = _lib.acq_entropy_at_upsampled(t, (h, w), sel) if kind == "lowres" else _lib.acq_entropy_at(t, sel)
         pin = sel.is_cuda
+        batch.dev_stats = None
+        if batch.stats_on and sel.is_cuda and batch.lab8 is not None:
+            # QueryStats + wire coordinates for the whole batch in one launch (pp_query_stats_at), read back with the picks
+            hist = torch.zeros(self.n_classes, dtype=torch.int64, device=sel.device)
+            outs = _lib.query_stats_at(sel.contiguous(), w, h * w, batch.lab8.view(n, -1), self.n_classes, hist)
+            batch.dev_stats = []
+            for t in outs + (hist,):
+                th = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                th.copy_(t, non_blocking=True)
+                batch.dev_stats.append(th)
+        batch.lab8 = None
         batch.sel_host = torch.empty(sel.shape, dtype=sel.dtype, pin_memory=pin)
         batch.sel_host.copy_(sel, non_blocking=True)
         batch.ent_host = None
@@ -390,6 +426,13 @@ class QuerySelector:
         sel_np = batch.sel_host.numpy()
         ent = None if batch.ent_host is None else batch.ent_host.numpy()
         n_new = 0
+        if batch.dev_stats is not None:
+            xs, ys, lab_at, uniq, cov, hist = [t.numpy() for t in batch.dev_stats]
+            for i, b in enumerate(batch.items):
+                dict_queries[b["p_img"]] = {"height": h, "width": w, "x_coords": xs[i].copy(), "y_coords": ys[i].copy()}
+                n_new += xs[i].size
+            self.query_stats.update_from_device(lab_at, uniq, cov, ent if ent is not None else np.full(lab_at.shape, np.nan), hist)
+            return n_new
         for i, b in enumerate(batch.items):
             idx = sel_np[i]
             dict_queries[b["p_img"]] = {"height": h, "width": w, "x_coords": idx % w, "y_coords": idx // w}
@@ -556,3 +599,54 @@ def merge_previous_query_files(list_previous_query_files: List[str], ignore_inde
     if verbose:
         print(f"# merged pixels: {cnt}")
     return merged
+
+
+def main(argv=None):
+    """`python -m pixelpick_b200.query` - the human-in-the-loop query step of the reference (query.py:354-437,
+    scripts/query.sh): with --p_state_dict, load the trained model, merge every `*/queries.pkl` under --dir_checkpoints
+    (the annotated pixels so far, query.py:311-351), point the query dataset at exactly those images, choose the next
+    pixels with `human_labels=True` (labelled pixels = where the merged map differs from ignore_index) and write
+    `{dir_checkpoints}/{nth_query}_query/queries.pkl`.  Without --p_state_dict: build the query dataloader with fresh initial
+    queries (the dataset constructor writes `0_query/label.npy`, nothing else happens - as in the reference)."""
+    from copy import deepcopy
+    from torch.utils.data import DataLoader
+    from .args import Arguments
+    from .utils import get_dataloader, get_model
+    parser = Arguments()
+    parser.parser.add_argument("--p_state_dict", type=str, default="", help="path to a state_dict file")
+    args = parser.parse_args(argv=argv, verbose=True) if argv is not None else parser.parse_args(verbose=True)
+    if not torch.cuda.is_available():
+        raise _lib.PixelPickError("pixelpick_b200.query needs a CUDA device (no CPU fallback)")
+    device = torch.device("cuda", torch.cuda.current_device())
+    if args.p_state_dict == "":
+        get_dataloader(deepcopy(args), query=True, val=False, generate_init_queries=True, shuffle=False, batch_size=1,
+                       n_workers=args.n_workers)
+        return None
+    model = get_model(args).to(device)
+    model.load_state_dict(torch.load(args.p_state_dict, map_location=device)["model"])
+    print(f"pretrained model is loaded from {args.p_state_dict}")
+    list_prev = gather_previous_query_files(args.dir_checkpoints)
+    merged = merge_previous_query_files(list_prev, ignore_index=args.ignore_index)
+    dataset = get_dataloader(deepcopy(args), query=True, val=False, generate_init_queries=False, shuffle=False, batch_size=1,
+                             n_workers=args.n_workers).dataset
+    list_inputs, list_merged = [], []
+    for p_img, q in sorted(merged.items()):  # query.py:389-397: the images that carry annotations, by file name
+        if getattr(args, "synthetic", None) is None:
+            p_img = f"{args.dir_dataset}/train/{p_img.split('/')[-1]}"
+            assert os.path.exists(p_img), p_img
+        list_inputs.append(p_img)
+        list_merged.append(q)
+    dataset.list_inputs = list_inputs
+    dataset.update_labelled_queries(list_merged)
+    dataloader = DataLoader(dataset, batch_size=1, num_workers=args.n_workers, shuffle=False)
+    nth_query = len(list_prev)
+    qs = QuerySelector(args, dataloader, device=device)
+    dict_queries = qs(nth_query=nth_query, model=model, human_labels=True)
+    os.makedirs(f"{args.dir_checkpoints}/{nth_query}_query", exist_ok=True)
+    pkl.dump(dict_queries, open(f"{args.dir_checkpoints}/{nth_query}_query/queries.pkl", "wb"))
+    print(f"Queries are saved at {args.dir_checkpoints}/{nth_query}_query/queries.pkl")
+    return dict_queries
+
+
+if __name__ == "__main__":
+    main()

@@ -157,6 +157,7 @@ class SyntheticDataset(Dataset):
         self.dir_checkpoints = f"{args.dir_root}/checkpoints/{args.experim_name}"
         self.seed = seed + (10_000 if val else 0)
         self.list_labelled_queries = None
+        self.list_inputs = None  # optional re-targeting: paths "synthetic/<id>.png" -> the images with those ids, in that order
         rs = np.random.RandomState(self.seed)
         n_init = args.n_pixels_by_us if args.n_pixels_by_us > 0 else 0
         self.queries: List[np.ndarray] = []
@@ -168,7 +169,18 @@ class SyntheticDataset(Dataset):
         self.n_pixels_total = int(sum(q.sum() for q in self.queries))
 
     def __len__(self):
-        return self.n
+        return self.n if self.list_inputs is None else len(self.list_inputs)
+
+    def update_labelled_queries(self, labelled_queries):
+        """datasets/base_dataset.py:143-149: human-labelled maps (ignore_index where unlabelled), one per entry of
+        `list_inputs` (the human-in-the-loop flow of query.py:389-412 / train.py:214-226 re-targets the dataset at the
+        annotated images first)."""
+        self.list_labelled_queries = labelled_queries
+
+    def _image_id(self, i):
+        if self.list_inputs is None:
+            return i
+        return int(os.path.splitext(os.path.basename(self.list_inputs[i]))[0])
 
     def _xy(self, i):
         g = torch.Generator().manual_seed(self.seed * 1_000_003 + i)
@@ -181,10 +193,13 @@ class SyntheticDataset(Dataset):
         return x, y
 
     def __getitem__(self, i):
-        x, y = self._xy(i)
-        d = {"x": x, "y": y, "p_img": f"synthetic/{i:06d}.png"}
+        j = self._image_id(i)
+        x, y = self._xy(j)
+        d = {"x": x, "y": y, "p_img": f"synthetic/{j:06d}.png"}
         if not self.val:
-            d["queries"] = torch.from_numpy(self.queries[i].astype(np.uint8))
+            d["queries"] = torch.from_numpy(self.queries[j].astype(np.uint8))
+        if self.list_labelled_queries is not None:  # base_dataset.py:165-170
+            d["labelled_queries"] = torch.from_numpy(np.asarray(self.list_labelled_queries[i]))
         return d
 
     def label_queries(self, dict_queries: Dict[str, dict], nth_query=None):

@@ -35,6 +35,38 @@ def test_two_rounds_on_synthetic_data(tmp_path):
     assert rows[0].startswith("epoch") and len(rows) == 2 and np.isfinite(float(rows[1].split(",")[3]))
 
 
+def test_query_cli_picks_new_pixels_from_human_annotations(tmp_path, capsys):
+    """`python -m pixelpick_b200.query --p_state_dict ...` (query.py:354-437): one active-learning round writes a checkpoint and
+    queries.pkl; a human "annotates" those pixels (category_id, as via/convert_json_to_pkl.py does); the CLI merges the
+    annotation files, loads the checkpoint and writes the NEXT queries.pkl - n new pixels per annotated image, none of them
+    already annotated."""
+    from pixelpick_b200 import query as Q
+    common = ["--dataset_name", "cs", "--dir_root", str(tmp_path), "--n_workers", "0", "--synthetic", "6", "64", "128"]
+    args = Arguments().parse_args(argv=common + ["--max_budget", "10", "--n_epochs", "1"])
+    torch.backends.cudnn.benchmark = False
+    m = Model(args)
+    m()
+    ck = tmp_path / "checkpoints" / args.experim_name
+    picks = pickle.load(open(ck / "1_query" / "queries.pkl", "rb"))
+    ds = m.dataloader_query.dataset
+    for p_img, info in picks.items():  # the annotator's answer: the true label of every queried pixel
+        y = ds._xy(int(p_img.split("/")[-1].split(".")[0]))[1].numpy()
+        info["category_id"] = y[info["y_coords"], info["x_coords"]]
+    for r in (0, 1):  # the loop leaves the same picks in 0_query (QuerySelector) and 1_query (Model): annotate both files
+        assert (ck / f"{r}_query" / "queries.pkl").exists()
+        pickle.dump(picks, open(ck / f"{r}_query" / "queries.pkl", "wb"))
+    new = Q.main(common + ["--p_state_dict", str(ck / "0_query" / "best_miou_model.pt")])
+    capsys.readouterr()
+    out = pickle.load(open(ck / "2_query" / "queries.pkl", "rb"))  # nth_query = number of annotation files found (query.py:419)
+    assert sorted(out) == sorted(picks) == sorted(new)
+    for p_img, info in out.items():
+        assert len(info["x_coords"]) == args.n_pixels_by_us and info["height"] == 64 and info["width"] == 128
+        old = set(zip(picks[p_img]["y_coords"].tolist(), picks[p_img]["x_coords"].tolist()))
+        y = ds._xy(int(p_img.split("/")[-1].split(".")[0]))[1].numpy()
+        for yy, xx in zip(info["y_coords"].tolist(), info["x_coords"].tolist()):
+            assert (yy, xx) not in old or y[yy, xx] == args.ignore_index  # void annotations stay unlabelled (merged map == ignore)
+
+
 def test_loss_decreases_on_a_fixed_batch(tmp_path):
     args = Arguments().parse_args(argv=["--dataset_name", "cs", "--dir_root", str(tmp_path), "--n_workers", "0",
                                         "--synthetic", "4", "64", "128"])

@@ -207,3 +207,29 @@ def test_query_selector_with_deeplab_model_in_the_loop(tmp_path):
     assert same >= n - 1, same
     for p in want:
         assert len(got[p]["x_coords"]) == 10
+
+
+def test_device_query_stats_equal_the_host_bookkeeping():
+    """pp_query_stats_at vs QueryStats.update_selected (the NumPy restatement of query.py:266-308 pinned to the reference's
+    query_stats.pkl in tests/test_query_host.py): coordinates, labels at the picks, histogram, unique labels, and the
+    spatial coverage BIT for bit (float64 mean in NumPy's pairwise order), n = 10 and n > 128 pairs."""
+    from pixelpick_b200 import _lib
+    from pixelpick_b200.query import QueryStats
+    rs = np.random.RandomState(3)
+    for n, H, W, C in ((10, 256, 512, 19), (5, 40, 48, 11), (13, 64, 96, 21), (2, 8, 8, 3)):
+        n_img = 7
+        y = rs.randint(0, C, size=(n_img, H * W)).astype(np.uint8)
+        sel = np.stack([np.sort(rs.choice(H * W, n, replace=False)) for _ in range(n_img)]).astype(np.int64)
+        hist = torch.zeros(C, dtype=torch.int64, device=DEV)
+        xs, ys, lab_at, uniq, cov = _lib.query_stats_at(torch.from_numpy(sel).to(DEV), W, H * W, torch.from_numpy(y).to(DEV), C, hist)
+        torch.cuda.synchronize()
+        host = QueryStats(Namespace(dir_root="/tmp", experim_name="x", n_classes=C))
+        for i in range(n_img):
+            host.update_selected(sel[i], W, y[i].reshape(H, W).astype(np.int64), np.zeros(n))
+            assert np.array_equal(xs[i].cpu().numpy(), sel[i] % W) and np.array_equal(ys[i].cpu().numpy(), sel[i] // W)
+            assert np.array_equal(lab_at[i].cpu().numpy(), y[i][sel[i]])
+        assert [int(u) for u in uniq.cpu()] == host.list_n_unique_labels
+        got = cov.cpu().numpy()
+        want = np.array(host.list_spatial_coverage, dtype=np.float64)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (n, got, want)
+        assert hist.cpu().tolist() == [host.dict_label_cnt[l] for l in range(C)]
