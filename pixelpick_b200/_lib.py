@@ -461,7 +461,7 @@ def conv_igemm(x_nhwc, w_packed, cout, dil=1, pre_bias=None, scale=None, shift=N
     return out
 
 
-def conv_igemm_multi(x_nhwc, w_packed, entries, cout, out=None, block_n=0):
+def conv_igemm_multi(x_nhwc, w_packed, entries, cout, out=None, block_n=0, pre_bias=None):
     """Generalised implicit GEMM: entries = [(dy, dx, c0), ...]; entry t convolves channels [c0, c0 + Cin) of x shifted by
     (dy, dx) with weight slice t of w_packed [n_entries][cout_pad][Cin]; all entries accumulate into one output."""
     _need_cuda(x_nhwc, w_packed)
@@ -472,8 +472,10 @@ def conv_igemm_multi(x_nhwc, w_packed, entries, cout, out=None, block_n=0):
     if out is None:
         out = torch.empty((N, H, W, cout), dtype=torch.bfloat16, device=x_nhwc.device)
     arr = lambda k: (C.c_int * n_e)(*[int(e[k]) for e in entries])
+    if pre_bias is not None:  # per-image bias [N, cout_pad] added to every pixel of the image (fp32)
+        assert pre_bias.dtype == torch.float32 and pre_bias.is_contiguous() and tuple(pre_bias.shape) == (N, cout_pad)
     check(lib().pp_conv_igemm_multi(_ptr(x_nhwc), N, H, W, ld_in, ld_in, cin, _ptr(w_packed), n_e, arr(0), arr(1), arr(2),
-                                    cout_pad, cout, None, None, None, 0, None, 0, _ptr(out), 0, out.shape[3], 0, block_n,
+                                    cout_pad, cout, _ptr(pre_bias), None, None, 0, None, 0, _ptr(out), 0, out.shape[3], 0, block_n,
                                     _stream(x_nhwc)), "pp_conv_igemm_multi")
     return out
 

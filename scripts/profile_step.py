@@ -37,8 +37,8 @@ print(f"  encoder fwd (no grad): {t_enc:.2f} ms")
 hi_g, lo_g = hi.detach().requires_grad_(True), lo.detach().requires_grad_(True)
 from pixelpick_b200.deeplab import _HeadFn
 def head_fb():
-    pre = model._pooled_branch(hi_g)
-    out = _HeadFn.apply(model, 1, hi_g, lo_g, pre, *model._head_params())
+    gap = model.aspp.global_avg_pool
+    out = _HeadFn.apply(model, 1, hi_g, lo_g, *model._head_params(), gap[1].weight, gap[2].weight, gap[2].bias)
     loss = sparse_cross_entropy(out, y, q.bool(), 19)
     loss.backward()
     return loss
