@@ -338,6 +338,19 @@ int pp_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int N, int Hi, 
 int pp_pack_conv_weight(const float* w, int Cout, int Cin, int Cin_total, int taps, void* fwd, int Cout_pad,
                         int Cin_pad, void* dgrad, int Cin_rows, int Cout_cols, void* stream);
 
+/* Joint geometric augmentation of a training batch on the device - datasets/base_dataset.py:48-127 (random scale: PIL BILINEAR
+ * for the image, PIL NEAREST for the label map, torch nearest for the query / human-label masks; pad to the crop size with
+ * mean_val / ignore_index / 0; random crop; horizontal flip) fused with TF.to_tensor + TF.normalize (base_dataset.py:183).
+ * x uint8 [B][H][W][3]; y / q / lq uint8 [B][H][W] (each may be NULL); header int32 [B][20] = {h_rs, w_rs, start_h, start_w,
+ * flip, ksize_x, ksize_y, then the offsets into `tables` of: PIL-nearest x / y indices, torch-nearest x / y indices, and per
+ * axis the bilinear filter's first source index, tap count and 22-bit fixed-point taps [out][ksize]} - built by the host in
+ * double precision as Pillow does (pixelpick_b200/augment.py).  Outputs: x_out f32 [B][3][crop_h][crop_w] normalised,
+ * y_out / q_out (0 / 1) / lq_out uint8 [B][crop_h][crop_w].  The image equals PIL's two-pass resample bit for bit. */
+int pp_augment_geometric(const uint8_t* x, const uint8_t* y, const uint8_t* q, const uint8_t* lq, int B, int H, int W,
+                         const int32_t* header, const int32_t* tables, int crop_h, int crop_w, const float* mean3,
+                         const float* std3, const int* mean_val3, int ignore_index, float* x_out, uint8_t* y_out,
+                         uint8_t* q_out, uint8_t* lq_out, void* stream);
+
 /* The same for EVERY convolution of a network in one launch (a train step re-packs ~50 weights after each optimiser
  * update): table_dev = device array of n rows of 11 int64 {w, fwd, dgrad pointers, Cout, Cin, Cin_total, taps, Cout_pad,
  * Cin_pad, Cin_rows, Cout_cols} with the meaning of pp_pack_conv_weight's arguments; blocks_per_conv CTAs work on each row. */

@@ -85,6 +85,7 @@ _SIGNATURES = {
     "pp_upsample_nhwc_bf16_bwd": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_pack_conv_weight": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_pack_conv_weights_batched": ([_vp, _i, _i, _vp], _i),
+    "pp_augment_geometric": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "pp_to_nhwc_bf16": ([_vp, _i, _i64, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_conv_igemm": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp], _i),
 }
