@@ -247,6 +247,13 @@ int pp_conv_wgrad_multi(const void* x, int x_channels, int ld_x, int Cin, const 
                         int W, int n_entries, const int* tap_dy, const int* tap_dx, const int* tap_c0, float* dw, int Cin_rows,
                         int ld_dw, int splits, void* stream);
 
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of the ResNet stem (resnet_models.py:116, resnet_backbone.py:56) on NHWC bf16:
+ * y [N][Ho][Wo][C] with Ho = (H - 1) / 2 + 1; `code` (optional, one byte per output element) = position 3 * ky + kx of the
+ * maximum inside its window (first maximum in row-major order, NaN wins: ATen's rule).  Backward: dx [N][H][W][C] gathers, for
+ * every input pixel, the gradients of the windows whose code points at it (no atomics, no zero-fill).  C % 8 == 0. */
+int pp_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* y, unsigned char* code, void* stream);
+int pp_maxpool3x3s2_bwd(const void* dy, const unsigned char* code, int N, int H, int W, int C, void* dx, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * T path: the HBM-bound layers between the convolutions, NHWC bf16 (channel counts multiples of 8).
  * Replaces nn.BatchNorm2d (train mode) + nn.ReLU + nn.Dropout (aspp.py:16-20,73-79; decoders.py:107-114;

@@ -77,6 +77,8 @@ _SIGNATURES = {
                              _i, _i, _i, _vp, _vp], _i),
     "pp_conv_set_epilogue": ([_i], _i),
     "pp_conv_wgrad_multi": ([_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    "pp_maxpool3x3s2_fwd": ([_vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "pp_maxpool3x3s2_bwd": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
     "pp_dwconv3x3_fwd": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "pp_dwconv3x3_fwd_bnact": ([_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "pp_dwconv3x3_dgrad": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
@@ -661,6 +663,28 @@ def bn_bwd(dy, c_off_dy, raw, c_off_raw, C, scale, shift, mean, rstd, relu, drop
     if res is not None:
         return draw, sums, dres
     return draw, sums
+
+
+def maxpool3x3s2_fwd(x, want_code=True):
+    """nn.MaxPool2d(3, 2, 1) on contiguous NHWC bf16 -> (y, code uint8 | None)"""
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    N, H, W, Cc = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((N, Ho, Wo, Cc), dtype=torch.bfloat16, device=x.device)
+    code = torch.empty((N, Ho, Wo, Cc), dtype=torch.uint8, device=x.device) if want_code else None
+    check(lib().pp_maxpool3x3s2_fwd(_ptr(x), N, H, W, Cc, _ptr(y), _ptr(code), _stream(x)), "pp_maxpool3x3s2_fwd")
+    return y, code
+
+
+def maxpool3x3s2_bwd(dy, code, in_hw):
+    _need_cuda(dy, code)
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and code.dtype == torch.uint8 and code.is_contiguous()
+    N, Ho, Wo, Cc = dy.shape
+    H, W = in_hw
+    dx = torch.empty((N, H, W, Cc), dtype=torch.bfloat16, device=dy.device)
+    check(lib().pp_maxpool3x3s2_bwd(_ptr(dy), _ptr(code), N, H, W, Cc, _ptr(dx), _stream(dy)), "pp_maxpool3x3s2_bwd")
+    return dx
 
 
 def _dw_out(Hi, Wi, stride, dil):

@@ -125,6 +125,25 @@ class _DWConvFn(torch.autograd.Function):
         return dx, dw, None, None
 
 
+class _MaxPoolFn(torch.autograd.Function):
+    """nn.MaxPool2d(3, 2, 1) on NHWC bf16 (the ResNet stem's pool) through pp_maxpool3x3s2_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, xn):
+        y, code = _lib.maxpool3x3s2_fwd(xn, want_code=xn.requires_grad)
+        if code is not None:
+            ctx.save_for_backward(code)
+        ctx.in_hw = tuple(xn.shape[1:3])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (code,) = ctx.saved_tensors
+        if dy.dtype != torch.bfloat16 or not dy.is_contiguous():
+            dy = dy.to(torch.bfloat16).contiguous()
+        return _lib.maxpool3x3s2_bwd(dy, code, ctx.in_hw)
+
+
 class DepthwiseConv3x3(nn.Conv2d):
     """nn.Conv2d(C, C, 3, stride, 0, dilation, groups=C, bias=False) (same parameter / state_dict key) whose CUDA bf16
     forward/backward run on the hand-written NHWC kernels; fp32 parity mode and CPU construction use torch."""
@@ -771,11 +790,7 @@ def _rn50_train_forward(bb, x, autocast_dtype, cache):
     """resnet_backbone.py:87-104 / resnet_models.py:74-94 in train mode on NHWC bf16 tensors."""
     convs = [m for layer in (bb.layer1, bb.layer2, bb.layer3, bb.layer4) for m in layer.modules() if isinstance(m, nn.Conv2d)]
     plan = _train_plan(cache, convs, x.device)
-    with torch.autocast("cuda", dtype=autocast_dtype):
-        t = bb.maxpool(bb.prefix(x))  # 7x7 s2 stem (Cin = 3) + max-pool: library ops
-    t = t.permute(0, 2, 3, 1)
-    if not t.is_contiguous():
-        t = t.contiguous()
+    t = _MaxPoolFn.apply(_stem_nhwc(bb.prefix, x, autocast_dtype))  # 7x7 s2 stem conv (Cin = 3): library; BN + ReLU + pool: ours
     c2 = None
     for li, layer in enumerate((bb.layer1, bb.layer2, bb.layer3, bb.layer4)):
         for blk in layer:
@@ -870,11 +885,7 @@ def _rn50_eval_plan(bb):
 
 
 def _rn50_eval_forward(bb, plan, x, autocast_dtype):
-    with torch.autocast("cuda", dtype=autocast_dtype):
-        t = bb.maxpool(bb.prefix(x))  # 7x7 s2 stem (Cin = 3) + maxpool: library ops
-    t = t.permute(0, 2, 3, 1)
-    if not t.is_contiguous():
-        t = t.contiguous()
+    t = _lib.maxpool3x3s2_fwd(_stem_nhwc(bb.prefix, x, autocast_dtype), want_code=False)[0]  # stem conv (Cin = 3): library
     i, c2 = 0, None
     for li, layer in enumerate((bb.layer1, bb.layer2, bb.layer3, bb.layer4)):
         for blk in layer:

@@ -302,3 +302,27 @@ def test_single_launch_bn_matches_separate_kernels(M, C, relu, p, with_res):
     torch.cuda.synchronize()
     dg = (out_a.float() - out_g.float()).abs()
     assert float(dg.max()) <= 2 ** -7 * float(out_a.float().abs().max()) and float((dg > 0).float().mean()) < 1e-2
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 128, 256, 64), (1, 33, 47, 16), (3, 8, 8, 8)])
+def test_maxpool_stem_matches_torch(N, H, W, C):
+    """pp_maxpool3x3s2_fwd / _bwd vs nn.MaxPool2d(3, 2, 1) (resnet_models.py:116): forward exact, backward = the gradient routed
+    to the first maximum of each window (odd sizes, ties and NaN included)."""
+    from pixelpick_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn((N, C, H, W), generator=g) * 2).to(torch.bfloat16)
+    x[0, 0, 0, 0] = float("nan")
+    x[0, 1, 2:4, 2:4] = 1.5  # a tie: the first maximum in row-major window order wins
+    dev = torch.device("cuda:0")
+    xr = x.to(dev).float().requires_grad_(True)
+    want = torch.nn.functional.max_pool2d(xr, 3, 2, 1)
+    dy = torch.randn(want.shape, generator=g).to(torch.bfloat16)
+    want.backward(dy.to(dev).float())
+    xn = x.permute(0, 2, 3, 1).contiguous().to(dev)
+    y, code = _lib.maxpool3x3s2_fwd(xn)
+    got = y.permute(0, 3, 1, 2).float()
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want.detach(), nan=-7.0))
+    dx = _lib.maxpool3x3s2_bwd(dy.permute(0, 2, 3, 1).contiguous().to(dev), code, (H, W))
+    ref = xr.grad
+    d = (dx.permute(0, 3, 1, 2).float() - ref).abs()
+    assert d.max().item() <= 2 ** -6 * ref.abs().max().item()  # up to 4 bf16 gradients summed in fp32, rounded once

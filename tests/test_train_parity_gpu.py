@@ -21,7 +21,7 @@ that "bf16-storage floor" as well as in absolute terms:
                                   zero-init-residual practice) or the ReLUs mostly open (MobileNetV2: BatchNorm bias + 1.5) -
                                   the floor's gradient cosine is then 0.97 / 0.93 (RN50 head / encoder) and 0.99 / 0.91
                                   (MobileNetV2), a regime where a wrong kernel shows.  Per tensor: 1 - cos <= 2x the floor's
-                                  + 3e-2 (norm ratio within 2x the floor's deviation + 10 %); per group (head / encoder): mean cosine >= the floor's mean - 3e-2.
+                                  + 3e-2 (norm ratio within 2x the floor's deviation + 25 %: single BatchNorm scales of the first blocks move by 10-20 % between two runs of the SAME kernels, fp32 atomics order); per group (head / encoder): mean cosine >= the floor's mean - 3e-2.
   K = 3 graphed Adam steps      : every loss within 2 % of the REFERENCE's logged trajectory and within 3x the floor's own
                                   deviation + 1 % (measured 0.02-1.2 %; the floor run itself drifts 0.1-0.6 %)
 """
@@ -138,7 +138,7 @@ def test_train_step_gradients_match_the_reference(backbone, state):
             continue  # a gradient that is numerically nothing (a direction BatchNorm cancels)
         if state == "init":
             assert abs(rn - gold_norm[n]) < 5e-3 * gold_norm[n] + 1e-9, (n, rn, gold_norm[n])  # oracle == reference
-        elif not ((1 - cos) <= 2 * (1 - f_cos) + 3e-2 and abs(ratio - 1) <= 2 * abs(f_ratio - 1) + 1e-1):
+        elif not ((1 - cos) <= 2 * (1 - f_cos) + 3e-2 and abs(ratio - 1) <= 2 * abs(f_ratio - 1) + 0.25):
             bad.append((n, round(cos, 4), round(f_cos, 4), round(ratio, 3), round(f_ratio, 3)))
     big = [r for r in rows if r[3] >= 1e-4 * total]
     for name, grp in (("head", [r for r in big if not r[0].startswith("backbone.")]),
