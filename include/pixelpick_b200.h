@@ -254,6 +254,14 @@ int pp_conv_wgrad_multi(const void* x, int x_channels, int ld_x, int Cin, const 
 int pp_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* y, unsigned char* code, void* stream);
 int pp_maxpool3x3s2_bwd(const void* dy, const unsigned char* code, int N, int H, int W, int C, void* dx, void* stream);
 
+/* pp_bn_finalize + pp_bn_apply(_res) in ONE launch, for per-channel sums that already exist (pp_conv_igemm_stats): every thread
+ * derives scale / shift of its 8 channels from sums [2][C] (same arithmetic as pp_bn_finalize), block 0 writes stats_out
+ * [4][C] = (scale, shift, mean, rstd) for pp_bn_bwd and updates running_mean / running_var (may be NULL) as nn.BatchNorm2d
+ * does (momentum, unbiased variance).  out = act(raw * scale + shift [+ res]). */
+int pp_bn_apply_stats(const void* raw, int64_t M, int ld_in, int c_off_in, int C, const float* sums, const float* gamma,
+                      const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* stats_out,
+                      int relu, const void* res, int ld_res, void* out, int ld_out, int c_off_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * T path: the HBM-bound layers between the convolutions, NHWC bf16 (channel counts multiples of 8).
  * Replaces nn.BatchNorm2d (train mode) + nn.ReLU + nn.Dropout (aspp.py:16-20,73-79; decoders.py:107-114;

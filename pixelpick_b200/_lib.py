@@ -63,6 +63,7 @@ _SIGNATURES = {
     "pp_bn_apply": ([_vp, _i64, _i, _i, _i, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i, _i, _vp], _i),
     "pp_bn_bwd": ([_vp, _i, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp,
                    _vp, _vp], _i),
+    "pp_bn_apply_stats": ([_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp], _i),
     "pp_bn_apply_res": ([_vp, _i64, _i, _i, _i, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i, _vp, _i, _i, _vp], _i),
     "pp_bn_bwd_res": ([_vp, _i, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _f, C.c_uint64, C.c_uint64, _vp, _vp, _i,
                        _vp, _vp, _vp, _i, _i, _vp], _i),
@@ -600,6 +601,22 @@ def bn_apply(raw, c_off_in, C, scale, shift, relu, out, c_off_out, drop_p=0.0, s
                                 int(seed), int(offset), _ptr(seed_dev), _ptr(res), res.shape[-1] if res is not None else 0,
                                 _ptr(out), ld_out, c_off_out, _stream(raw)), "pp_bn_apply")
     return out
+
+
+def bn_apply_stats(raw, C, sums, bn, act, out, res=None, update_running=True):
+    """finalize (sums [2, C] from the conv epilogue -> scale / shift / mean / rstd, running statistics) + normalise + activation
+    (+ residual) in one launch; returns stats f32 [4, C] for bn_bwd.  num_batches_tracked is the caller's business."""
+    _need_cuda(raw, out, res, sums)
+    ld_in, ld_out = raw.shape[-1], out.shape[-1]
+    M = raw.numel() // ld_in
+    stats = torch.empty((4, C), dtype=torch.float32, device=raw.device)
+    upd = update_running and bn.track_running_stats and bn.running_mean is not None
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    check(lib().pp_bn_apply_stats(_ptr(raw), M, ld_in, 0, C, _ptr(sums), _ptr(bn.weight.detach()), _ptr(bn.bias.detach()), bn.eps,
+                                  mom, _ptr(bn.running_mean) if upd else None, _ptr(bn.running_var) if upd else None,
+                                  _ptr(stats), int(act), _ptr(res), res.shape[-1] if res is not None else 0, _ptr(out), ld_out, 0,
+                                  _stream(raw)), "pp_bn_apply_stats")
+    return stats
 
 
 # Single-launch (cooperative) BatchNorm passes.  PP_BN_FUSED=0 falls back to the separate stats/finalize/apply kernels

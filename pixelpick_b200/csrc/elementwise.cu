@@ -211,6 +211,47 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_apply_kernel(const BnApplyPa
   bn_apply_body<RES, DROP>(p, sc, sf);
 }
 
+// finalize + apply in one launch: the per-channel sums come from the conv epilogue (pp_conv_igemm_stats); every thread derives the
+// scale / shift of its 8 channels itself (same arithmetic as bn_finalize_kernel) and block 0 also publishes (scale, shift, mean,
+// rstd) for the backward pass and updates the running statistics - one launch less per BatchNorm layer.
+struct BnFinalizeArgs {
+  const float* sums;  // [2][C]
+  const float* gamma;
+  const float* beta;
+  float inv_m, unbias, eps, momentum;
+  float* running_mean;  // may be null
+  float* running_var;
+  float* stats_out;  // [4][C]
+};
+template <bool RES>
+__global__ void __launch_bounds__(kEwThreads, 4) bn_apply_stats_kernel(const BnApplyParams p, const BnFinalizeArgs a) {
+  const int groups = p.C >> 3;
+  const int g = threadIdx.x % groups;
+  float sc[8], sf[8];
+  const bool publish = blockIdx.x == 0 && threadIdx.x < groups;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    const float mean = __ldg(a.sums + c) * a.inv_m;
+    float var = fmaf(-mean, mean, __ldg(a.sums + p.C + c) * a.inv_m);
+    var = fmaxf(var, 0.f);
+    const float rstd = rsqrtf(var + a.eps);
+    sc[j] = __ldg(a.gamma + c) * rstd;
+    sf[j] = fmaf(-mean, sc[j], __ldg(a.beta + c));
+    if (publish) {
+      a.stats_out[c] = sc[j];
+      a.stats_out[p.C + c] = sf[j];
+      a.stats_out[2 * p.C + c] = mean;
+      a.stats_out[3 * p.C + c] = rstd;
+      if (a.running_mean) {
+        a.running_mean[c] = fmaf(a.momentum, mean - a.running_mean[c], a.running_mean[c]);
+        a.running_var[c] = fmaf(a.momentum, var * a.unbias - a.running_var[c], a.running_var[c]);
+      }
+    }
+  }
+  bn_apply_body<RES, false>(p, sc, sf);
+}
+
 // ---- BN backward -----------------------------------------------------------------------------
 struct BnBwdParams {
   const __nv_bfloat16* dy;  // grad wrt the layer output (after dropout), [M][ld_dy] slice c_off_dy
@@ -807,6 +848,35 @@ int pp_bn_apply_res(const void* raw, int64_t M, int ld_in, int c_off_in, int C, 
     else if (drop) bn_apply_kernel<false, true><<<(int)blocks, kEwThreads, 0, st>>>(p);
     else bn_apply_kernel<false, false><<<(int)blocks, kEwThreads, 0, st>>>(p);
   }
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
+
+int pp_bn_apply_stats(const void* raw, int64_t M, int ld_in, int c_off_in, int C, const float* sums, const float* gamma,
+                      const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* stats_out,
+                      int relu, const void* res, int ld_res, void* out, int ld_out, int c_off_out, void* stream) {
+  PP_CHECK_ARG(raw && out && sums && gamma && beta && stats_out && M > 0, "pp_bn_apply_stats: bad args");
+  PP_CHECK_ARG(!res || (ld_res % 8 == 0 && ld_res >= C), "pp_bn_apply_stats: residual ld=%d", ld_res);
+  PP_CHECK_ARG(C % 8 == 0 && C <= 2048 && ld_in % 8 == 0 && c_off_in % 8 == 0 && ld_out % 8 == 0 && c_off_out % 8 == 0,
+               "pp_bn_apply_stats: channel counts/offsets must be multiples of 8 (C <= 2048)");
+  PP_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "pp_bn_apply_stats: running_mean / running_var go together");
+  BnApplyParams p;
+  p.raw = reinterpret_cast<const __nv_bfloat16*>(raw);
+  p.M = M; p.ld_in = ld_in; p.c_off_in = c_off_in; p.C = C; p.scale = nullptr; p.shift = nullptr; p.relu = relu;
+  p.drop_p = 0.f; p.seed = 0; p.offset = 0; p.seed_dev = nullptr;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ld_out = ld_out; p.c_off_out = c_off_out;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.ld_res = ld_res;
+  BnFinalizeArgs a;
+  a.sums = sums; a.gamma = gamma; a.beta = beta;
+  a.inv_m = 1.f / (float)M;
+  a.unbias = M > 1 ? (float)M / (float)(M - 1) : 1.f;
+  a.eps = eps; a.momentum = momentum; a.running_mean = running_mean; a.running_var = running_var; a.stats_out = stats_out;
+  const int rows_per_block = kEwThreads / (C / 8);
+  int64_t blocks = (M + rows_per_block * 4 - 1) / (rows_per_block * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (res) bn_apply_stats_kernel<true><<<(int)blocks, kEwThreads, 0, st>>>(p, a);
+  else bn_apply_stats_kernel<false><<<(int)blocks, kEwThreads, 0, st>>>(p, a);
   PP_LAUNCH_CHECK();
   return PP_OK;
 }

@@ -681,9 +681,14 @@ class _ConvBNActFn(torch.autograd.Function):
             wp, wd, stats = slot.wp, slot.wd, slot.stats
         ctx.slot = slot
         _lib.conv_fused(x, wp, cout, dil=dil, out=raw, stats=stats, entries=entries)
-        st = _lib.bn_finalize(stats, N * H * W, bn, count=slot is None)  # with a plan: counters advance in one batched op
         y = torch.empty_like(raw)
-        _lib.bn_apply(raw, 0, cout, st[0], st[1], act, y, 0, res=res)
+        if cout % 8 == 0 and cout <= 2048:
+            st = _lib.bn_apply_stats(raw, cout, stats, bn, act, y, res=res)  # finalize + normalise: one launch
+            if slot is None and bn.track_running_stats and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1  # with a plan the counters advance in one batched op
+        else:
+            st = _lib.bn_finalize(stats, N * H * W, bn, count=slot is None)
+            _lib.bn_apply(raw, 0, cout, st[0], st[1], act, y, 0, res=res)
         ctx.bn, ctx.act, ctx.cfg, ctx.need_dx = bn, act, (cin, cout, k, dil, s2d), need_dx
         ctx.save_for_backward(*([x, raw, st, wd if need_dx else st] + ([res] if res is not None else [])))
         ctx.has_res = res is not None
