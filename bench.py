@@ -412,6 +412,11 @@ def bench_strategy_sweep(dev, hbm_peak, n_img=8, Hs=1024, Ws=2048, steps=5):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def ppdist_rank():
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
 def _barrier(world):
     import torch.distributed as dist
     if world > 1:
@@ -543,7 +548,13 @@ def bench_query_selector(backbone, n_img_total, dev, world, tmpdir, reps=2):
             np.random.seed(0)
             _barrier(world)
             t0 = time.perf_counter()
-            picks = qs(r, model)
+            if os.environ.get("PP_QUERY_PROFILE") and r == reps and ppdist_rank() == 0:
+                import cProfile, pstats
+                prof = cProfile.Profile()
+                picks = prof.runcall(qs, r, model)
+                pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(35)
+            else:
+                picks = qs(r, model)
             torch.cuda.synchronize()
             times.append(time.perf_counter() - t0)
     finally:
@@ -690,6 +701,10 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     _lib.lib()
+    if world > 1:
+        # torchrun exports OMP_NUM_THREADS=1: the host side of the query round (DataLoader collate, 1.5 MB staging copies) would
+        # run on one thread per rank and take twice as long as in the single-process run; give every rank its share of the cores
+        torch.set_num_threads(max(1, (os.cpu_count() or world) // world))
     hbm_peak, tf_burst, tf_sust, peak_src = peaks()
     K, Wm, Bt = args.steps, args.warmup, args.train_batch
     tmpdir = tempfile.mkdtemp(prefix="pp_bench_")

@@ -24,6 +24,8 @@ def join_process_group():
     torch.cuda.set_device(local)
     if not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if os.environ.get("OMP_NUM_THREADS") == "1":  # torchrun's default: one host thread per rank starves the loader / staging copies
+        torch.set_num_threads(max(1, (os.cpu_count() or world) // world))
     return dist.get_rank(), world
 
 

@@ -153,6 +153,48 @@ class QueryStats:
         pkl.dump(dict_stats, open(f"{self.dir_checkpoints}/{nth_query}_query/query_stats.pkl", "wb"))
 
 
+class _AsyncDraws:
+    """The random ranks of EVERY image of a query round, drawn in dataloader order from the global NumPy stream (query.py:40,64)
+    on a background thread while the main thread loads and scores this rank's images.  The sizes the draws depend on are known
+    up-front on every rank: `dataset.queries` holds one [h, w] mask per image.  NumPy's legacy shuffle releases the GIL, so the
+    ~60 us per image (a full Fisher-Yates pass over k = 5 % of the pixels, needed to leave the stream where the reference
+    leaves it) overlap the host loop instead of adding world x n_own x 60 us to every rank's round."""
+
+    def __init__(self, selector, shapes):
+        import threading
+        self.shapes, self.pos, self.done, self.err = shapes, [None] * len(shapes), 0, None
+        self.cv = threading.Condition()
+        self.selector = selector
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        try:
+            for i, (h, w) in enumerate(self.shapes):
+                _, p = self.selector._draw_positions(1, h, w)
+                with self.cv:
+                    self.pos[i] = p
+                    self.done = i + 1
+                    self.cv.notify_all()
+        except BaseException as e:  # surfaced by get() / join() on the main thread
+            with self.cv:
+                self.err = e
+                self.cv.notify_all()
+
+    def get(self, i):
+        with self.cv:
+            while self.done <= i and self.err is None:
+                self.cv.wait()
+            if self.err is not None:
+                raise self.err
+            return self.pos[i]
+
+    def join(self):
+        self.thread.join()
+        if self.err is not None:
+            raise self.err
+
+
 class _Slot:
     """Host staging of one batch (pinned when a GPU is present): images and masks are written straight into these buffers as
     the loader yields them (no torch.cat, no pageable copies) and go up with ONE async copy each.  Two slots alternate, so
@@ -176,7 +218,7 @@ class _Batch:
         self.n_top = 0
         self.stats_on = False
         self.sel_host = self.ent_host = self.done = None
-        self.lab8 = self.dev_stats = None
+        self.lab8 = self.dev_stats = self.pos_host = None
 
 
 class QuerySelector:
@@ -384,7 +426,14 @@ class QuerySelector:
         st = self.query_strategy
         largest = _lib.LARGEST[st]
         pos_np = None if batch.items[0]["pos"] is None else np.concatenate([b["pos"] for b in batch.items])
-        pos_t = None if pos_np is None else torch.from_numpy(pos_np)
+        pos_t = None
+        if pos_np is not None:
+            if batch.score.is_cuda:  # through pinned memory: a pageable upload would wait for the forward queued ahead of it
+                batch.pos_host = torch.empty(pos_np.shape, dtype=torch.int32, pin_memory=True)
+                batch.pos_host.numpy()[...] = pos_np
+                pos_t = batch.pos_host.to(batch.score.device, non_blocking=True)
+            else:
+                pos_t = torch.from_numpy(pos_np)
         # only the n drawn ranks of the sorted top-k are needed (query.py:63-64): radix pick, no sort
         if batch.ws is None:
             sel = _lib.acq_select_pick(batch.score, batch.n_top, largest, pos_t, n=self.n_pixels_by_us)
@@ -474,9 +523,10 @@ class QuerySelector:
         self.query_stats.begin_round()
         # Multi-GPU fast path: every rank loads and scores ONLY its own images; the random ranks - which the reference draws
         # from the global NumPy stream once per image in dataloader order (query.py:40,64) and which depend on every image's
-        # size - are drawn after ONE small all-gather of the image sizes, then the picks are finished.  The draws are the
-        # same numbers in the same order as in a single process (a query dataset draws nothing itself:
-        # base_dataset.py:172-181).  reverse_order / random need their draws BEFORE scoring and keep the walk-everything path.
+        # size - are drawn for ALL images on a background thread (_AsyncDraws: the sizes come from the per-image masks every
+        # rank holds).  The draws are the same numbers in the same order as in a single process (a query dataset draws nothing
+        # itself: base_dataset.py:172-181).  reverse_order / random need their draws BEFORE scoring and keep the
+        # walk-everything path.
         own = None
         if world > 1 and not self.reverse_order and self.query_strategy != "random":
             own = self._own_loader(world, rank)
@@ -485,11 +535,16 @@ class QuerySelector:
         scored: List[_Batch] = []     # deferred mode: scored, waiting for their ranks
         cur = [None]
 
+        drawer = [None]
+
         def close_batch(pick):
             b = cur[0]
             cur[0] = None
             if b is None or not b.items:
                 return
+            if drawer[0] is not None:
+                for it in b.items:
+                    it["pos"] = drawer[0].get(it["gpos"])
             b.stats_on = not human_labels and b.items[0]["y"] is not None
             self._launch(model, b, pick)
             if pick:
@@ -535,40 +590,38 @@ class QuerySelector:
                 close_batch(pick=True)
             else:
                 loader, positions = own
+                shapes = [tuple(np.shape(q)[-2:]) for q in prev_queries]
+                drawer[0] = _AsyncDraws(self, shapes) if self.top_n_percent > 0.0 else None
                 for j, dict_data in enumerate(loader):
-                    feed(positions[j], dict_data, None, None, None, pick=False)
-                close_batch(pick=False)
-                # ONE small exchange: (position, height, width, path) of every image -> the draws, in dataloader order
-                sizes = [(it["gpos"], it["hw"][0], it["hw"][1], it["p_img"]) for b in scored for it in b.items]
-                everyone = sorted(s for part in ppdist.all_gather_objects(sizes) for s in part)
-                draws = {}
-                for gpos, h, w, p_img in everyone:
-                    _, pos = self._draw_positions(1, h, w)
-                    order.append(p_img)
-                    if gpos % world == rank:
-                        draws[gpos] = pos
-                n_imgs = len(everyone)
-                for b in scored:
-                    for it in b.items:
-                        it["pos"] = draws[it["gpos"]]
-                    self._pick(b)
-                    launched.append(b)
+                    h, w = tuple(dict_data["x"].shape[2:])
+                    if (h, w) != shapes[positions[j]]:
+                        raise _lib.PixelPickError(f"image {positions[j]} is {h}x{w} but its query mask is {shapes[positions[j]]}")
+                    feed(positions[j], dict_data, None, None, None, pick=True)
+                close_batch(pick=True)
+                if drawer[0] is not None:
+                    drawer[0].join()  # the stream ends where a single process leaves it: every image's draw is consumed
+                n_imgs = len(shapes)
             for b in launched:
                 nonlocal_counts[0] += self._collect(b, dict_queries)
         n_pixels = nonlocal_counts[0]
         assert n_imgs > 0, "no queries are chosen!"
         stats_on = not human_labels and any_y[0]
         if world > 1:
-            stats_on = any(ppdist.all_gather_objects(stats_on))
-            # the round's exchange: per-rank picks (and statistics) -> every rank, back in dataloader order
-            gathered = ppdist.all_gather_objects((dict_queries, self.query_stats.round_payload(mine) if stats_on else None))
-            merged: dict = dict()
-            for d, _ in gathered:
+            # the round's ONE exchange: per-rank picks with their dataloader positions (and statistics) -> every rank
+            local_pos = {it_p: g for g, it_p in zip(mine, list(dict_queries))}
+            gathered = ppdist.all_gather_objects((dict_queries, local_pos, stats_on,
+                                                  self.query_stats.round_payload(mine) if stats_on else None))
+            stats_on = any(g[2] for g in gathered)
+            merged, where = dict(), dict()
+            for d, lp, _, _ in gathered:
                 merged.update(d)
+                where.update(lp)
+            if own is not None:
+                order = sorted(merged, key=lambda p_: where[p_])
             dict_queries = {p: merged[p] for p in order}
             n_pixels = sum(len(info["x_coords"]) for info in dict_queries.values())
             if stats_on:
-                self.query_stats.absorb_round([payload for _, payload in gathered])
+                self.query_stats.absorb_round([g[3] for g in gathered if g[3] is not None])
         if stats_on:
             if rank == 0:
                 self.query_stats.save(nth_query)
