@@ -342,6 +342,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               pk[c / 2 + 1] = *reinterpret_cast<uint32_t*>(&t1);
             }
           }
+          if (p.stats && !valid) {
+            // a tile that overhangs the image edge: its out-of-image pixels still see in-image taps of a 3x3 conv; they are
+            // clipped by the TMA store but must not enter the BatchNorm statistics
+#pragma unroll
+            for (int c = 0; c < 16; ++c) pk[c] = 0u;
+          }
           const uint32_t buf = my_stage + (unit_iter & 1u) * 2048u;
           if (unit_iter >= 2) {  // the store issued from this buffer two units ago must have read it
             if (lane == 0) tc::bulk_wait_group_read<1>();

@@ -19,7 +19,8 @@ def _rand(shape, seed, scale=1.0):
 
 @pytest.mark.parametrize("N,H,W,cin,cout,k,dil", [(2, 64, 128, 64, 256, 1, 1), (2, 32, 64, 512, 2048, 1, 1), (2, 32, 64, 256, 256, 3, 2),
                                                   (2, 66, 130, 24, 144, 1, 1), (2, 16, 32, 960, 320, 1, 1), (1, 20, 36, 144, 24, 1, 1),
-                                                  (2, 32, 64, 512, 512, 3, 4), (3, 17, 23, 96, 576, 1, 1)])
+                                                  (2, 32, 64, 512, 512, 3, 4), (3, 17, 23, 96, 576, 1, 1), (2, 18, 34, 64, 96, 3, 2),
+                                                  (1, 13, 21, 64, 64, 3, 1)])
 def test_forward_with_epilogue_statistics(N, H, W, cin, cout, k, dil):
     x = _rand((N, cin, H, W), 1).to(torch.bfloat16)
     w = _rand((cout, cin, k, k), 2, (2.0 / (cin * k * k)) ** 0.5)
