@@ -445,7 +445,7 @@ def build_train(backbone, B, dev, world, loop=False):
     for part in (model.aspp, model.low_level_conv, model.seg_head):
         groups.append({"params": part.parameters(), "lr": OPT["lr"], "weight_decay": OPT["weight_decay"]})
     opt = make_capturable_adam(groups)
-    reducer = ppdist.GradAllReducer(model) if world > 1 else None
+    reducer = ppdist.GradAllReducer(model) if (world > 1 or os.environ.get("PP_FORCE_REDUCER")) else None
     hx, hy, hq = synth_train_batch(B, 11 + ppdist.rank(), pin=True)
     gs = GraphedTrainStep(model, opt, (B, H, W), C, capacity=B * 16, device=dev, reducer=reducer,
                           n_classes=C if loop else None)

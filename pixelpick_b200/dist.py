@@ -60,6 +60,11 @@ class GradAllReducer:
     Usage per step:  reducer.zero_grad(); loss.backward(); reducer(); optimizer.step()."""
 
     def __init__(self, model, bucket_mb: float = 32.0, overlap: bool = True):
+        import os
+        # measurement knobs (A/B runs of bench.py): bucket size, hooks off = one exchange after backward, no exchange at all
+        bucket_mb = float(os.environ.get("PP_DP_BUCKET_MB", bucket_mb))
+        overlap = overlap and os.environ.get("PP_DP_OVERLAP", "1") != "0"
+        self._nocomm = os.environ.get("PP_DP_NOCOMM", "0") == "1"
         self.params = [p for p in model.parameters() if p.requires_grad]
         order = list(reversed(self.params))
         n = sum(p.numel() for p in order)
@@ -121,6 +126,9 @@ class GradAllReducer:
     def _launch(self, b):
         lo, hi = self.buckets[b]
         seg = self.flat[lo:hi]
+        if self._nocomm:
+            self._works[b] = False
+            return
         if self._avg is not None:
             self._works[b] = dist.all_reduce(seg, op=self._avg, async_op=True)
         else:
@@ -139,6 +147,8 @@ class GradAllReducer:
             if self._works[b] is None:
                 self._launch(b)
         for b, w in enumerate(self._works):
+            if w is False:
+                continue
             w.wait()
             if self._avg is None:
                 lo, hi = self.buckets[b]
