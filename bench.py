@@ -570,7 +570,7 @@ def bench_query_selector(backbone, n_img_total, dev, world, tmpdir, reps=2):
             "h2d_bytes_per_image": 3 * H * W * 4 + 2 * H * W, "d2h_bytes_per_image": N_SEL * 8 + N_SEL * 4}
 
 
-def bench_acq_pipeline(B, K, Wm, dev, world, rank, overlap, sorted_topk=False):
+def bench_acq_pipeline(B, K, Wm, dev, world, rank, overlap, sorted_topk=False, fused=False):
     """The acquisition kernels alone on logits resident in HBM (B images / step / GPU, 2.55 GB of fp32 logits per step at
     B = 256 >> L2): fused softmax + margin + mask fills + level-0 histogram -> radix select -> order statistics at the n
     drawn ranks; at N > 1 one all-gather of the round's picks.  Returns step / score-kernel times (CUDA events)."""
@@ -593,7 +593,23 @@ def bench_acq_pipeline(B, K, Wm, dev, world, rank, overlap, sorted_topk=False):
     free = [torch.cuda.Event() for _ in range(2)]
     turn = [0]
 
+    fused = fused and not overlap and not sorted_topk and _lib.acq_score_select_supported(logits, C, H, W)
+
+    def step_fused(i=None):
+        # ONE pass over the logits: a cluster per image scores, keeps the scores in shared memory, merges the level-0 histograms
+        # and classifies (pp_acq_score_select), then the radix tail + the order statistics at the drawn ranks
+        ws_p, _ = slots[0]
+        ws_p.prepare()
+        if i is not None:
+            ev_a[i].record()
+        sel = _lib.acq_score_select_pick(logits, STRATEGY, K_TOP, pos, lab, void, ws=ws_p, mark=(ev_b[i] if i is not None else None))
+        if world > 1 and i is not None:
+            sel_round[i].copy_(sel)
+        return sel
+
     def step(i=None):
+        if fused:
+            return step_fused(i)
         p = (turn[0] % n_slots)
         turn[0] += 1
         ws_p, score_p = slots[p]
@@ -649,7 +665,7 @@ def bench_acq_pipeline(B, K, Wm, dev, world, rank, overlap, sorted_topk=False):
     ms_total, score_ms = _max_over_ranks([ms_total, score_ms], dev, world)
     del logits, slots
     torch.cuda.empty_cache()
-    return {"ms_per_step": ms_total / K, "score_ms": score_ms, "launches": int(launches),
+    return {"ms_per_step": ms_total / K, "score_ms": score_ms, "launches": int(launches), "fused": bool(fused),
             "mpix_s": world * B * HW * K / 1e6 / (ms_total / 1e3)}
 
 
@@ -669,6 +685,12 @@ def main():
                     help="acquisition leg: run the select + pick of step i on a side stream under the scoring of step i+1 "
                          "(measured SLOWER on B200: 0.61 vs 0.55 ms/step - the concurrent kernels take HBM bandwidth from the "
                          "scoring kernel; kept for the record, default is one stream)")
+    ap.add_argument("--fused-acq", action="store_true",
+                    help="acquisition leg through pp_acq_score_select (scoring + level-0 select in one pass, a cluster per image, the "
+                         "score map never written).  Bit-identical picks; measured SLOWER on B200 (0.583 vs 0.536 ms / 256 images: the "
+                         "fused kernel takes 512 us against 407 + 5 + 53 us - 18 % of every CTA's life is cluster barriers, the "
+                         "leader's bucket pick and the classification, during which it does not stream), so the default stays the "
+                         "three-kernel form")
     ap.add_argument("--sweep", action="store_true", help="also run the 1024x2048 strategy sweep (BASELINE configs[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -747,15 +769,17 @@ def main():
                 b1 = bench_query_model("resnet", 1, 50, dev, True)
                 cfg["query_rn50_bs1_mpix_s"] = b1["value"]  # the reference's own query batch (one image per forward)
     # ---- acquisition kernels alone (north star: >= 80 % of the HBM roofline on the fused scoring kernel) ----
-    acq = bench_acq_pipeline(args.acq_batch, K, Wm, dev, world, rank, overlap=args.overlap_select)
+    acq = bench_acq_pipeline(args.acq_batch, K, Wm, dev, world, rank, overlap=args.overlap_select, fused=args.fused_acq)
     HW = H * W
     alg = args.acq_batch * HW * ALG_BYTES_PER_PX
     achieved = alg / (acq["score_ms"] / 1e3) / 1e9
     cfg.update({"acq_images_per_step_per_gpu": args.acq_batch, "acq_step_ms": acq["ms_per_step"], "acq_step_gpix_s": acq["mpix_s"] / 1e3,
                 "acq_step_frac_of_hbm": alg / (acq["ms_per_step"] / 1e3) / 1e9 / hbm_peak,
-                "acq_select": "radix select + order statistics at the drawn ranks; " +
+                "acq_select": ("scoring fused with the level-0 select (scores stay in shared memory), radix tail, order statistics at "
+                               "the drawn ranks; " if acq["fused"] else "radix select + order statistics at the drawn ranks; ") +
                               ("select+pick of step i on a side stream under the scoring of step i+1" if args.overlap_select else "one stream")})
-    roof = {"kernel": "acq_score_vec_kernel<19, margin, f32, fused hist0>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+    roof = {"kernel": ("acq_score_select_kernel<19, margin> (softmax + margin + mask fills + level-0 select in one pass, cluster of 8 "
+                       "CTAs per image)" if acq["fused"] else "acq_score_vec_kernel<19, margin, f32, fused hist0>"), "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
             "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": acq["score_ms"],
             "alg_bytes_per_launch": alg, "share_of_acq_step": acq["score_ms"] / acq["ms_per_step"]}
     if rank == 0 and not args.no_extras:

@@ -81,6 +81,17 @@ int pp_acq_score_upsampled(const float* logits_lowres, int n_img, int C, int h_i
                            const uint8_t* labelled, const uint8_t* void_mask, const uint8_t* keep,
                            int strategy, float* score_map, uint32_t* hist0, void* stream);
 
+/* pp_acq_score + pp_acq_select in ONE pass over the logits (query.py:190-201 softmax / uncertainty / mask fills, then the
+ * selection half of uc_map.topk(k) query.py:57-61): a thread-block cluster per image keeps the scores in shared memory, merges
+ * the level-0 histograms through distributed shared memory and classifies its own scores - the score map is neither written
+ * nor re-read (score_map may be NULL; when given it is also written).  Leaves the k unsorted candidates in the workspace
+ * exactly like pp_acq_select; follow with pp_acq_pick / pp_acq_topk's sort.  The workspace must have been prepared
+ * (pp_acq_topk_prepare).  Covers f32 logits, W % 4 == 0, C in {11, 19, 21}, H*W = cluster x (a multiple of 4096 <= 16384)
+ * with cluster <= 16 (e.g. 256x512); other shapes return PP_ERR_UNSUPPORTED: use the two-call form. */
+int pp_acq_score_select(const void* logits, int dtype, int n_img, int C, int H, int W, int64_t stride_n, int64_t stride_c,
+                        int64_t stride_h, const uint8_t* labelled, const uint8_t* void_mask, const uint8_t* keep, int strategy,
+                        int k, float* score_map, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Q path: per-image sorted top-k of a score map.
  * Replaces  uc_map.flatten().topk(k, largest=strategy in {entropy, LC}).indices   query.py:57-61

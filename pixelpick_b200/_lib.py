@@ -36,6 +36,7 @@ _SIGNATURES = {
     "pp_host_bucket0": ([_f, _i], C.c_uint),
     "pp_device_info": ([C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.c_char_p, _i], _i),
     "pp_acq_score": ([_vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp], _i),
+    "pp_acq_score_select": ([_vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp], _i),
     "pp_acq_score_upsampled": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp], _i),
     "pp_acq_topk_workspace_bytes": ([_i, _i, _i, C.POINTER(_sz)], _i),
     "pp_acq_topk_prepare": ([_vp, _sz, _i, _i, _i, _vp], _i),
@@ -258,6 +259,41 @@ def acq_select_pick(score_map, k, largest, pos, n=None, ws=None, hist0_valid=Fal
     check(lib().pp_acq_select(_ptr(sm), n_img, HW, k, int(bool(largest)), int(bool(hist0_valid)), _ptr(ws.buf), ws.nbytes,
                               _stream(sm)), "pp_acq_select")
     check(lib().pp_acq_pick(_ptr(ws.buf), ws.nbytes, n_img, HW, k, _ptr(pos), n, _ptr(out), _stream(sm)), "pp_acq_pick")
+    return out
+
+
+def acq_score_select_supported(logits, C, H, W):
+    """shapes the fused scoring + select kernel covers (see pp_acq_score_select)"""
+    if logits.dtype != torch.float32 or W % 4 or C not in UPSAMPLED_SCORE_CLASSES or logits.stride(3) != 1:
+        return False
+    if any(s % 4 for s in logits.stride()[:3]) or logits.data_ptr() % 16:
+        return False
+    HW = H * W
+    return any(HW % (c * 4096) == 0 and HW // c <= 16384 for c in (1, 2, 4, 8, 16))
+
+
+def acq_score_select_pick(logits, strategy, k, pos, labelled=None, void_mask=None, keep=None, n=None, ws=None, score_out=None,
+                          mark=None):
+    """acq_select_pick(acq_score(logits, ...)) in one pass over the logits: flat indices [n_img, n] at ranks `pos` of the sorted
+    top-k list; the score map is only written when `score_out` is given.  `ws` must be prepared (TopKWorkspace.prepare)."""
+    _need_cuda(logits, labelled, void_mask, keep)
+    n_img, Cc, H, W = logits.shape
+    HW = H * W
+    labelled, void_mask, keep = (_mask(m, n_img, H, W) for m in (labelled, void_mask, keep))
+    if ws is None:
+        ws = TopKWorkspace(n_img, HW, k, logits.device)
+        ws.prepare()
+    _check_score_outputs("acq_score_select_pick", n_img, H, W, score_out, ws)
+    check(lib().pp_acq_score_select(_ptr(logits), _dtype_code(logits), n_img, Cc, H, W, logits.stride(0), logits.stride(1),
+                                    logits.stride(2), _ptr(labelled), _ptr(void_mask), _ptr(keep), STRATEGIES[strategy], k,
+                                    _ptr(score_out), _ptr(ws.buf), ws.nbytes, _stream(logits)), "pp_acq_score_select")
+    if mark is not None:
+        mark.record()  # bench.py: a CUDA event between the fused kernel (+ radix tail) and the pick
+    if pos is not None:
+        pos = pos.to(device=logits.device, dtype=torch.int32).contiguous()
+        n = pos.shape[1]
+    out = torch.empty((n_img, n), dtype=torch.int32, device=logits.device)
+    check(lib().pp_acq_pick(_ptr(ws.buf), ws.nbytes, n_img, HW, k, _ptr(pos), n, _ptr(out), _stream(logits)), "pp_acq_pick")
     return out
 
 

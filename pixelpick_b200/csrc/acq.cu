@@ -14,6 +14,7 @@
 //   K3b bitonic_*        full sort of the k composites when the list itself is wanted (ties -> lower flat index first).
 //
 // Reference semantics restated (query.py:33-69,190-201,224-247): see include/pixelpick_b200.h.
+#include <cooperative_groups.h>
 #include "pp_common.cuh"
 #include <stdlib.h>
 
@@ -665,6 +666,265 @@ __global__ void __launch_bounds__(kSelThreads, 6) select_l0_kernel(const SelPara
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused scoring + level-0 select: ONE pass over the logits, the score map never touches HBM.
+// A thread-block cluster owns one image: every CTA scores HW / cluster pixels (the same 4-pixel vector loop as
+// acq_score_vec_kernel), keeps its scores in shared memory and builds its level-0 histogram there; the histograms are added into
+// the leader CTA's shared memory through distributed shared memory, the leader finds the bucket of the k-th score and its key
+// range (the work of pick_bucket0_kernel), every CTA reads that back and classifies ITS OWN scores out of shared memory -
+// selected -> candidate list, inside the bucket -> boundary list for select_rest_kernel.  Against the three-kernel form
+// (score: 78 B/px read + 4 B/px written; pick_bucket0; select_l0: 4 B/px re-read) this moves 78 B/px and saves two launches.
+// ------------------------------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int kFusedMaxPx = 16384;  // scores per CTA held in shared memory (64 KB)
+
+struct FusedSelParams {
+  SelState* state;       // [n_img] level-0 state (what pick_bucket0_kernel writes)
+  uint64_t* cand;        // [n_img][kpad]
+  uint32_t* cand_count;  // [n_img]
+  uint64_t* bnd;         // [n_img][HW] boundary list
+  uint32_t* bnd_count;   // [n_img]
+  uint32_t k;
+  int kpad, pxc;         // pixels per CTA (HW / cluster size, a multiple of 1024)
+};
+
+// the body of pick_bucket0_kernel on a histogram in shared memory; every thread of the CTA calls it, result in *out (shared)
+__device__ void pick_bucket0_block(const uint32_t* hist, SelState* out, uint32_t k, bool largest, uint32_t* sh_warp, uint32_t* sh_bucket) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t h[8];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = hist[tid * 8 + i];
+    mine += h[i];
+  }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) sh_warp[warp] = incl;
+  __syncthreads();
+  uint32_t wbase = 0;
+#pragma unroll
+  for (int w = 0; w < kSelThreads / 32; ++w)
+    if (w < warp) wbase += sh_warp[w];
+  uint32_t run = wbase + incl - mine;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (run < k && k <= run + h[i]) {  // exactly one (thread, i) matches
+      out->remaining = k - run;
+      out->done = (h[i] == k - run) ? 1u : 0u;
+      out->bucket = (uint32_t)(tid * 8 + i);
+      out->klo = out->khi = 0u;
+      out->pad = 0u;
+      *sh_bucket = out->bucket;
+    }
+    run += h[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    auto bucket_of_key = [&](uint32_t key) -> uint32_t {
+      uint32_t u = largest ? ~key : key;
+      if (u == 0xFFFFFFFFu) return largest ? 0u : 2047u;
+      u = u < 0x007FFFFFu ? 0x007FFFFFu : (u > 0xFF800000u ? 0xFF800000u : u);
+      const uint32_t bits = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+      return bucket0(__uint_as_float(bits), largest);
+    };
+    auto first_key_with_bucket_ge = [&](uint32_t b, bool& none) -> uint32_t {
+      none = bucket_of_key(0xFFFFFFFFu) < b;
+      if (none) return 0u;
+      uint64_t lo = 0, hi = 0xFFFFFFFFull;
+      while (lo < hi) {
+        const uint64_t step = (hi - lo + 32) / 33;
+        uint64_t probe = lo + (uint64_t)(lane + 1) * step - 1;
+        probe = probe > hi ? hi : probe;
+        const bool ok = bucket_of_key((uint32_t)probe) >= b;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+        if (m == 0u) {
+          lo = lo + 32 * step;
+          lo = lo > hi ? hi : lo;
+        } else {
+          const int first = __ffs(m) - 1;
+          const uint64_t p_first = lo + (uint64_t)(first + 1) * step - 1;
+          hi = p_first > hi ? hi : p_first;
+          if (first > 0) lo = lo + (uint64_t)first * step;
+        }
+      }
+      return (uint32_t)lo;
+    };
+    const uint32_t b = *sh_bucket;
+    if (!largest) {
+      if (lane == 0) {
+        out->klo = b << 21;
+        out->khi = (b << 21) | 0x1FFFFFu;
+      }
+    } else {
+      bool none;
+      const uint32_t klo = first_key_with_bucket_ge(b, none);
+      const uint32_t nxt = first_key_with_bucket_ge(b + 1u, none);
+      if (lane == 0) {
+        out->klo = klo;
+        out->khi = none ? 0xFFFFFFFFu : nxt - 1u;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <int C, int STRAT>
+__global__ void __launch_bounds__(kScoreThreads, 2) acq_score_select_kernel(const ScoreParams p, const FusedSelParams f) {
+  extern __shared__ __align__(16) uint8_t fs_raw[];
+  float* sh_score = reinterpret_cast<float*>(fs_raw);                                   // [pxc]
+  uint32_t* sh_hist = reinterpret_cast<uint32_t*>(fs_raw + (size_t)kFusedMaxPx * 4);    // [2048] this CTA
+  uint32_t* sh_tot = sh_hist + kHistBins;                                               // [2048] cluster total (leader's copy is used)
+  uint32_t* sh_idx = sh_tot + kHistBins;                                                // [8 warps][512] survivors of the pre-filter
+  __shared__ SelState sh_state;
+  __shared__ uint32_t sh_warp[kScoreThreads / 32];
+  __shared__ uint32_t sh_bucket;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kHistBins; i += kScoreThreads) {
+    sh_hist[i] = 0;
+    sh_tot[i] = 0;
+  }
+  cluster.sync();  // the leader's total is zero before any peer adds into it
+
+  const int img = blockIdx.y;
+  const int Wv = p.W / 4;
+  const int64_t HW = (int64_t)p.H * p.W;
+  const float* __restrict__ base = reinterpret_cast<const float*>(p.logits) + (int64_t)img * p.sn;
+  const bool largest = p.largest != 0;
+  const int iters = f.pxc / (kScoreThreads * 4);
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    const int q = (blockIdx.x * iters + it) * kScoreThreads + tid;
+    const int y = q / Wv;
+    const int x = (q - y * Wv) * 4;
+    const float* __restrict__ src = base + (int64_t)y * p.sh + x;
+    float v[C][4];
+#pragma unroll
+    for (int c = 0; c < C; ++c) LdPx<float, 4>::ld(src + (int64_t)c * p.sc, v[c]);
+    const int64_t pix = (int64_t)img * HW + (int64_t)y * p.W + x;
+    uint32_t msk = 0;
+    if (p.lab) msk |= ld_mask<4>(p.lab + pix);
+    if (p.vd) msk |= ld_mask<4>(p.vd + pix);
+    if (p.keep) {
+      const uint32_t k4 = ld_mask<4>(p.keep + pix);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (((k4 >> (8 * j)) & 0xFFu) == 0) msk |= 0xFFu << (8 * j);
+    }
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float xs[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) xs[c] = v[c][j];
+      out[j] = score_from_logits<C, STRAT>(xs);
+      if ((msk >> (8 * j)) & 0xFFu) out[j] = p.fill;
+    }
+    const float4 o4 = make_float4(out[0], out[1], out[2], out[3]);
+    reinterpret_cast<float4*>(sh_score)[it * kScoreThreads + tid] = o4;
+    if (p.score) *reinterpret_cast<float4*>(p.score + pix) = o4;  // optional: the caller also wants the map
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(&sh_hist[bucket0(out[j], largest)], 1u);
+  }
+  __syncthreads();
+  {  // this CTA's histogram -> the leader's total (distributed shared memory)
+    uint32_t* tot0 = cluster.map_shared_rank(sh_tot, 0);
+    for (int i = tid; i < kHistBins; i += kScoreThreads) {
+      const uint32_t c = sh_hist[i];
+      if (c) atomicAdd(tot0 + i, c);
+    }
+  }
+  cluster.sync();
+  if (cluster.block_rank() == 0) {
+    pick_bucket0_block(sh_tot, &sh_state, f.k, largest, sh_warp, &sh_bucket);
+    if (tid == 0) f.state[img] = sh_state;  // select_rest_kernel reads {remaining, done}
+  }
+  cluster.sync();
+  const SelState st0 = *cluster.map_shared_rank(&sh_state, 0);
+  // ---- classify this CTA's scores out of shared memory (the scheme of select_l0_kernel: float pre-filter, ballot compaction
+  // of the survivors per warp, exact key compares one survivor per lane, one warp-aggregated atomic pair per 512 scores) ----
+  const bool take_all = st0.done != 0u;
+  const uint32_t klo = st0.klo, khi = st0.khi;
+  const bool sel_any = take_all || klo > 0u;
+  const uint32_t sel_max = take_all ? khi : klo - 1u;
+  const float f_t = ord_key_inv(khi, largest);
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t* my_idx = sh_idx + warp * 512;
+  uint64_t* cand = f.cand + (size_t)img * f.kpad;
+  uint64_t* ol = f.bnd + (size_t)img * HW;
+  const uint32_t cta0 = blockIdx.x * (uint32_t)f.pxc;
+  const int per_warp = f.pxc / (kScoreThreads / 32);
+  for (int r0 = 0; r0 < per_warp; r0 += 512) {
+    const uint32_t wbase = (uint32_t)(warp * per_warp + r0);
+    uint32_t n_pass = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 s4 = reinterpret_cast<const float4*>(sh_score + wbase)[j * 32 + lane];
+      const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ps = largest ? !(sv[e] < f_t) : !(sv[e] > f_t);
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, ps);
+        if (ps) my_idx[n_pass + (uint32_t)__popc(b & lt)] = wbase + (uint32_t)((j * 32 + lane) * 4 + e);
+        n_pass += (uint32_t)__popc(b);
+      }
+    }
+    __syncwarp();
+    if (n_pass == 0u) continue;  // warp-uniform
+    uint32_t nc = 0, nf = 0;
+    for (uint32_t e = (uint32_t)lane; e < n_pass; e += 32u) {
+      const uint32_t li = my_idx[e];
+      const uint32_t kk = ord_key(sh_score[li], largest);
+      const bool s1 = sel_any && kk <= sel_max;
+      const bool s2 = !take_all && kk >= klo && kk <= khi;
+      my_idx[e] = li | ((uint32_t)s1 << 30) | ((uint32_t)s2 << 31);
+      nc += s1;
+      nf += s2;
+    }
+    const uint32_t packed = nc | (nf << 16);
+    uint32_t inc = packed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const uint32_t tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    if (tot != 0u) {
+      uint32_t base_c = 0, base_f = 0;
+      if (lane == 0) {
+        const uint32_t tc = tot & 0xFFFFu, tf = tot >> 16;
+        if (tc) base_c = atomicAdd(f.cand_count + img, tc);
+        if (tf) base_f = atomicAdd(f.bnd_count + img, tf);
+      }
+      base_c = __shfl_sync(0xFFFFFFFFu, base_c, 0);
+      base_f = __shfl_sync(0xFFFFFFFFu, base_f, 0);
+      const uint32_t excl = inc - packed;
+      uint32_t oc = base_c + (excl & 0xFFFFu);
+      uint32_t of = base_f + (excl >> 16);
+      for (uint32_t e = (uint32_t)lane; e < n_pass; e += 32u) {
+        const uint32_t ix = my_idx[e];
+        if (ix >> 30) {
+          const uint32_t li = ix & 0x3FFFFFFFu;
+          const uint64_t comp = ((uint64_t)ord_key(sh_score[li], largest) << 32) | (cta0 + li);
+          if (ix & 0x40000000u) {
+            if (oc < (uint32_t)f.kpad) cand[oc] = comp;
+            ++oc;
+          } else {
+            ol[of++] = comp;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  cluster.sync();  // no CTA may exit while a peer can still read its shared memory
 }
 
 // The radix tail for one image in ONE CTA: the boundary bucket of level 0 is small (L2-resident), so all key-digit
@@ -1688,11 +1948,101 @@ __global__ void __launch_bounds__(128) query_stats_kernel(const long long* __res
   }
 }
 
+
+template <int C>
+static int launch_score_select(const ScoreParams& p, const FusedSelParams& f, int strategy, int cl, int n_img, cudaStream_t st) {
+  const size_t smem = (size_t)kFusedMaxPx * 4 + 2 * kHistBins * 4 + 8 * 512 * 4;
+  auto go = [&](auto kernel) -> int {
+    PP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (cl > 8) PP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)cl, (unsigned)n_img);
+    cfg.blockDim = dim3(kScoreThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    PP_CUDA(cudaLaunchKernelEx(&cfg, kernel, p, f));
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+  };
+  if (strategy == PP_STRAT_ENTROPY) return go(acq_score_select_kernel<C, PP_STRAT_ENTROPY>);
+  if (strategy == PP_STRAT_LEAST_CONFIDENCE) return go(acq_score_select_kernel<C, PP_STRAT_LEAST_CONFIDENCE>);
+  return go(acq_score_select_kernel<C, PP_STRAT_MARGIN>);
+}
+
 }  // namespace pp
 
 using namespace pp;
 
 extern "C" {
+
+int pp_acq_score_select(const void* logits, int dtype, int n_img, int C, int H, int W, int64_t stride_n, int64_t stride_c,
+                        int64_t stride_h, const uint8_t* labelled, const uint8_t* void_mask, const uint8_t* keep, int strategy,
+                        int k, float* score_map, void* workspace, size_t workspace_bytes, void* stream) {
+  PP_CHECK_ARG(logits && workspace, "pp_acq_score_select: null pointer");
+  PP_CHECK_ARG(n_img > 0 && n_img <= 65535 && C >= 2 && H > 0 && W > 0, "pp_acq_score_select: bad shape n=%d C=%d H=%d W=%d", n_img, C, H, W);
+  PP_CHECK_ARG(strategy >= 0 && strategy <= 2, "pp_acq_score_select: bad strategy %d", strategy);
+  PP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) % 256) == 0, "pp_acq_score_select: workspace must be 256-B aligned");
+  const int64_t HW64 = (int64_t)H * W;
+  PP_CHECK_ARG(HW64 <= (1 << 22) && k > 0 && k <= HW64, "pp_acq_score_select: bad H*W=%lld k=%d", (long long)HW64, k);
+  const int HW = (int)HW64;
+  auto al = [](const void* q, size_t a) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % a) == 0; };
+  const bool vec_ok = dtype == PP_F32 && (W % 4 == 0) && (stride_n % 4 == 0) && (stride_c % 4 == 0) && (stride_h % 4 == 0) &&
+                      stride_h >= W && al(logits, 16) && al(score_map, 16) && al(labelled, 4) && al(void_mask, 4) && al(keep, 4);
+  int cl = 0;
+  for (int c = 1; c <= 16; c <<= 1)
+    if (HW % (c * 4096) == 0 && HW / c <= kFusedMaxPx) { cl = c; break; }
+  if (!vec_ok || cl == 0 || !(C == 11 || C == 19 || C == 21)) {
+    set_error("pp_acq_score_select: shape not covered by the fused kernel (f32, W %% 4 == 0, 16-byte aligned, C in {11, 19, 21}, H*W a "
+              "multiple of 4096 x cluster size <= 16 with <= 16384 pixels per CTA): use pp_acq_score + pp_acq_select");
+    return PP_ERR_UNSUPPORTED;
+  }
+  Workspace w = carve(workspace, n_img, HW, k);
+  if (workspace_bytes < w.total_bytes) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, w.total_bytes);
+    return PP_ERR_WORKSPACE;
+  }
+  ScoreParams p;
+  p.logits = logits;
+  p.sn = stride_n; p.sc = stride_c; p.sh = stride_h;
+  p.n_img = n_img; p.C = C; p.H = H; p.W = W;
+  p.lab = labelled; p.vd = void_mask; p.keep = keep;
+  p.score = score_map; p.hist0 = nullptr;
+  p.fill = (strategy == PP_STRAT_MARGIN) ? 1.0f : 0.0f;
+  p.largest = (strategy == PP_STRAT_MARGIN) ? 0 : 1;
+  FusedSelParams f;
+  f.state = w.state + (size_t)n_img;
+  f.cand = w.cand; f.cand_count = w.cand_count;
+  f.bnd = w.filt; f.bnd_count = w.filt_count;
+  f.k = (uint32_t)k; f.kpad = w.kpad; f.pxc = HW / cl;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc;
+  switch (C) {
+    case 11: rc = launch_score_select<11>(p, f, strategy, cl, n_img, st); break;
+    case 19: rc = launch_score_select<19>(p, f, strategy, cl, n_img, st); break;
+    default: rc = launch_score_select<21>(p, f, strategy, cl, n_img, st); break;
+  }
+  if (rc != PP_OK) return rc;
+  RestParams r;
+  r.list_a = w.filt;
+  r.list_b = w.filt + (size_t)n_img * HW;
+  r.count_a = w.filt_count;
+  r.cand = w.cand;
+  r.cand_count = w.cand_count;
+  r.state1 = w.state + (size_t)n_img;
+  r.HW = HW;
+  r.kpad = w.kpad;
+  r.first_level = p.largest ? 0 : 1;
+  select_rest_kernel<<<n_img, kRestThreads, 0, st>>>(r);
+  PP_LAUNCH_CHECK();
+  return PP_OK;
+}
 
 int pp_acq_score(const void* logits, int dtype, int n_img, int C, int H, int W, int64_t stride_n,
                  int64_t stride_c, int64_t stride_h, const uint8_t* labelled, const uint8_t* void_mask,

@@ -339,3 +339,44 @@ def test_pick_ranks_equals_sorted_topk_gather(n, hw, k, nsel, largest):
         assert torch.equal(got, want)
         first = _lib.acq_select_pick(scores.to(DEV), k, largest, None, n=nsel)
         assert torch.equal(first, topk[:, :nsel])
+
+
+@pytest.mark.parametrize("strat", ["entropy", "least_confidence", "margin_sampling"])
+@pytest.mark.parametrize("n,C,H,W", [(5, 19, 256, 512), (3, 11, 64, 128), (2, 21, 128, 256)])
+def test_fused_score_select_equals_the_two_call_path(strat, n, C, H, W):
+    """pp_acq_score_select (one pass over the logits, scores in shared memory, cluster-merged histogram) leaves the same candidate
+    set as pp_acq_score + pp_acq_select: identical picks at random ranks, identical sorted top-k list, identical optional score
+    map - incl. masked pixels, exact ties and a NaN score."""
+    from pixelpick_b200 import _lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(H + C)
+    logits = (torch.randn((n, C, H, W), generator=g) * 3).float()
+    logits[0, :, :4, :64] = logits[0, :, 4:8, :64]  # exact ties
+    logits[1, :, 10, 10] = 0.0                       # uniform pixel: margin 0, entropy ln C
+    if strat == "entropy":
+        logits[n - 1, 0, 3, 3] = -200.0              # an underflowing class: NaN entropy ranks first
+    rs = np.random.RandomState(1)
+    lab = torch.from_numpy(rs.rand(n, H, W) < 0.001)
+    void = torch.from_numpy(rs.rand(n, H, W) < 0.01)
+    k = int(H * W * 0.05)
+    assert _lib.acq_score_select_supported(logits.to(dev), C, H, W)
+    pos = torch.from_numpy(np.stack([rs.permutation(k)[:10] for _ in range(n)]).astype(np.int32))
+    lg, lb, vd = logits.to(dev), lab.to(dev), void.to(dev)
+    ws_a = _lib.TopKWorkspace(n, H * W, k, dev)
+    ws_a.prepare()
+    score = _lib.acq_score(lg, strat, lb, vd, hist0_ws=ws_a)
+    want = _lib.acq_select_pick(score.view(n, -1), k, _lib.LARGEST[strat], pos, ws=ws_a, hist0_valid=True)
+    ws_b = _lib.TopKWorkspace(n, H * W, k, dev)
+    ws_b.prepare()
+    score_b = torch.empty_like(score)
+    got = _lib.acq_score_select_pick(lg, strat, k, pos, lb, vd, ws=ws_b, score_out=score_b)
+    torch.cuda.synchronize()
+    assert torch.equal(got.cpu(), want.cpu())
+    assert torch.equal(torch.nan_to_num(score_b, nan=-1.0), torch.nan_to_num(score, nan=-1.0))
+    # without the optional score map, and the full sorted list out of the fused candidates
+    ws_c = _lib.TopKWorkspace(n, H * W, k, dev)
+    ws_c.prepare()
+    got2 = _lib.acq_score_select_pick(lg, strat, k, None, lb, vd, n=k, ws=ws_c)
+    ref_sorted = _lib.acq_topk(score.view(n, -1), k, _lib.LARGEST[strat])
+    torch.cuda.synchronize()
+    assert torch.equal(got2.cpu(), ref_sorted.cpu())
