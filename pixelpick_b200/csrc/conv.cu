@@ -128,7 +128,9 @@ __device__ __forceinline__ bool tap_skipped(const ConvParams& p, int tap, int y0
 //   kEpiGeneric : pre-bias, affine, residual, activation all optional at run time (also the only variant with the direct path)
 //   kEpiRaw     : out = bf16(acc)                        - training forward (BatchNorm follows) and every data gradient
 //   kEpiAffine  : out = clamp(acc * scale + shift)       - inference convs with folded BatchNorm + ReLU / ReLU6
-constexpr int kEpiGeneric = 0, kEpiRaw = 1, kEpiAffine = 2;
+//   kEpiRawRes  : out = bf16(acc + res)                  - a data gradient that lands on a residual fork: the other branch's
+//                                                          gradient is added here instead of by a separate pass (Cout % 32 == 0)
+constexpr int kEpiGeneric = 0, kEpiRaw = 1, kEpiAffine = 2, kEpiRawRes = 3;
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -293,10 +295,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int cbase = n0 + j * 32;
           if (j >= BN / 32 || cbase >= p.Cout) continue;  // warp-uniform: no such chunk / entirely in the channel padding
           uint32_t r[32];
+          uint4 rq[4];
+          if constexpr (EPI == kEpiRawRes) {  // this pixel's 64 B of the other branch, in flight while TMEM is read
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              rq[u] = valid ? __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.ld_res + cbase) + u) : make_uint4(0u, 0u, 0u, 0u);
+          }
           tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + j * 32, r);
           tc::tmem_ld_wait();
           uint32_t pk[16];
-          if constexpr (EPI == kEpiRaw) {
+          if constexpr (EPI == kEpiRawRes) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t w4[4] = {rq[u].x, rq[u].y, rq[u].z, rq[u].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = 8 * u + 2 * e;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r[c]) + __uint_as_float(w4[e] << 16),
+                                                          __uint_as_float(r[c + 1]) + __uint_as_float(w4[e] & 0xFFFF0000u));
+                pk[c / 2] = *reinterpret_cast<uint32_t*>(&t0);
+              }
+            }
+          } else if constexpr (EPI == kEpiRaw) {
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
               __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r[c]), __uint_as_float(r[c + 1]));
@@ -555,6 +575,9 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (!p.scale && !p.shift && p.relu == 0) return launch_conv_epi<BN, kEpiRaw>(tmA, tmB, tmO, p, sm_count, st);
     if (p.scale && p.shift) return launch_conv_epi<BN, kEpiAffine>(tmA, tmB, tmO, p, sm_count, st);
   }
+  if (p.tma_store && p.res && !p.pre_bias && !p.scale && !p.shift && p.relu == 0 && !p.stats && p.Cout % 32 == 0 &&
+      p.ld_res % 8 == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15u) == 0)
+    return launch_conv_epi<BN, kEpiRawRes>(tmA, tmB, tmO, p, sm_count, st);
   return launch_conv_epi<BN, kEpiGeneric>(tmA, tmB, tmO, p, sm_count, st);
 }
 

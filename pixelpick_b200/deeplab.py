@@ -659,13 +659,27 @@ class _EncoderTrainPlan:
             self.step_counters = []
 
 
+class _ResLink:
+    """The gradient of a block's shortcut branch, handed to the node that opens the block (role "take": its data-gradient
+    conv adds it in the epilogue, kEpiRawRes) so that the fork's add never becomes a separate pass over the tensor.
+    Identity shortcut: role "give" on the closing conv (its BatchNorm backward produces d(res)); the opening conv feeds the
+    closing one, so "give" always runs first.  Projection shortcut (same-resolution 1x1 downsample): role "give_dx" on the
+    downsample conv, which was recorded after conv1 / conv2 and becomes ready together with conv2, so autograd's
+    latest-first order runs it before conv1 ("take" asserts that it did)."""
+    __slots__ = ("grad",)
+
+    def __init__(self):
+        self.grad = None
+
+
 class _ConvBNActFn(torch.autograd.Function):
     """y = act(BatchNorm_train(conv(x)) [+ res]) on NHWC bf16 tensors, one autograd node.
     x [N, H, W, Cin] (or its space-to-depth form for the stride-2 3x3), w fp32 [Cout, Cin, k, k] (the master weight);
-    slot: this conv's views into the step's arenas (_EncoderTrainPlan) or None (self-contained: packs / zeroes per call)."""
+    slot: this conv's views into the step's arenas (_EncoderTrainPlan) or None (self-contained: packs / zeroes per call);
+    link = (_ResLink, "give" | "take") or None."""
 
     @staticmethod
-    def forward(ctx, x, w, gamma, beta, bn, act, res, dil, s2d, slot):
+    def forward(ctx, x, w, gamma, beta, bn, act, res, dil, s2d, slot, link=None):
         cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
         taps = k * k
         N, H, W, xc = x.shape
@@ -692,6 +706,8 @@ class _ConvBNActFn(torch.autograd.Function):
         ctx.bn, ctx.act, ctx.cfg, ctx.need_dx = bn, act, (cin, cout, k, dil, s2d), need_dx
         ctx.save_for_backward(*([x, raw, st, wd if need_dx else st] + ([res] if res is not None else [])))
         ctx.has_res = res is not None
+        ctx.link = link
+        assert link is None or (link[1] == "give" and res is not None) or (link[1] in ("take", "give_dx") and need_dx and not s2d)
         return y
 
     @staticmethod
@@ -726,7 +742,11 @@ class _ConvBNActFn(torch.autograd.Function):
         dx = None
         if ctx.need_dx:
             if not s2d:
-                dx = _lib.conv_fused(draw, wd, cin, dil=dil)
+                other = None
+                if ctx.link is not None and ctx.link[1] == "take":
+                    other, ctx.link[0].grad = ctx.link[0].grad, None
+                    assert other is not None, "residual link: the closing conv of the block has not run its backward"
+                dx = _lib.conv_fused(draw, wd, cin, dil=dil, res=other)
             else:
                 # adjoint of the phase form: phase (a, b) of dX collects, from every tap that reads it, W[tap]^T applied to dY
                 # shifted the other way - four small launches (1, 2, 2 and 4 taps) writing the four channel blocks
@@ -735,15 +755,22 @@ class _ConvBNActFn(torch.autograd.Function):
                     sel = [(t, e) for t, e in enumerate(entries) if e[2] == ph * cin]
                     wsel = torch.stack([wd[8 - t] for t, _ in sel])  # the dgrad pack holds W^T with the taps flipped
                     _lib.conv_fused(draw, wsel, cin, out=dx, c_off=ph * cin, entries=[(-e[0], -e[1], 0) for _, e in sel])
-        return dx, dW, sums[1], sums[0], None, None, dres, None, None, None
+        if ctx.link is not None and ctx.link[1] == "give":
+            ctx.link[0].grad, dres = dres, None
+        elif ctx.link is not None and ctx.link[1] == "give_dx":
+            ctx.link[0].grad, dx = dx, None
+        return dx, dW, sums[1], sums[0], None, None, dres, None, None, None, None
 
 
-def _cba(x, conv, bn, res=None, s2d=False, plan=None):
+def _cba(x, conv, bn, res=None, s2d=False, plan=None, link=None):
     """conv -> train-mode BatchNorm -> bn.act (-> + res before the activation) on an NHWC bf16 tensor"""
     slot = plan.slots.get(id(conv)) if plan is not None else None
     if slot is not None and bn.track_running_stats and bn.num_batches_tracked is not None:
         plan.step_counters.append(bn.num_batches_tracked)
-    return _ConvBNActFn.apply(x, conv.weight, bn.weight, bn.bias, bn, bn.act, res, conv.dilation[0], s2d, slot)
+    return _ConvBNActFn.apply(x, conv.weight, bn.weight, bn.bias, bn, bn.act, res, conv.dilation[0], s2d, slot, link)
+
+
+_RES_LINK = os.environ.get("PP_RES_LINK", "1") != "0"  # A/B: 0 = the shortcut's gradient goes through autograd's add
 
 
 def _train_plan(cache, convs, device):
@@ -800,7 +827,10 @@ def _rn50_train_forward(bb, x, autocast_dtype, cache):
     for li, layer in enumerate((bb.layer1, bb.layer2, bb.layer3, bb.layer4)):
         for blk in layer:
             strided = blk.conv2.stride != (1, 1)
-            o = _cba(t, blk.conv1, blk.bn1, plan=plan)
+            # identity blocks: t feeds conv1 and the shortcut; the shortcut's gradient is added in conv1's dgrad epilogue
+            same_res = blk.downsample is None or blk.downsample[0].stride == (1, 1)
+            link = _ResLink() if same_res and t.requires_grad and _RES_LINK and blk.conv1.in_channels % 32 == 0 else None
+            o = _cba(t, blk.conv1, blk.bn1, plan=plan, link=(link, "take") if link else None)
             if strided:  # layer2.0: 3x3 stride 2 as nine stride-1 taps on the space-to-depth tensor
                 o = _cba(space_to_depth(o), blk.conv2, blk.bn2, s2d=True, plan=plan)
             else:
@@ -808,8 +838,9 @@ def _rn50_train_forward(bb, x, autocast_dtype, cache):
             idn = t
             if blk.downsample is not None:
                 src = t[:, ::2, ::2].contiguous() if blk.downsample[0].stride != (1, 1) else t  # 1x1 stride 2 = subsample
-                idn = _cba(src, blk.downsample[0], blk.downsample[1], plan=plan)
-            t = _cba(o, blk.conv3, blk.bn3, res=idn, plan=plan)  # relu(bn3(conv3) + identity)
+                idn = _cba(src, blk.downsample[0], blk.downsample[1], plan=plan, link=(link, "give_dx") if link else None)
+            t = _cba(o, blk.conv3, blk.bn3, res=idn, plan=plan,  # relu(bn3(conv3) + identity)
+                     link=(link, "give") if link and blk.downsample is None else None)
         if li == 0:
             c2 = t
     plan.end_forward()

@@ -86,3 +86,65 @@ def test_stride_two_bottleneck_convs_through_space_to_depth():
     dw = _lib.conv_wgrad_multi(xs, cin, dyn, cout, ent)
     gotw = dw[:, :cin, :cout].permute(2, 1, 0).reshape(cout, cin, 3, 3).cpu()
     assert (gotw - wr.grad).abs().max().item() < 2e-3 * wr.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k,dil", [(2, 64, 128, 64, 256, 1, 1), (2, 32, 64, 512, 2048, 1, 1), (3, 17, 23, 256, 1024, 1, 1),
+                                                  (1, 13, 21, 64, 64, 3, 1)])
+def test_residual_added_in_the_raw_epilogue(N, H, W, cin, cout, k, dil):
+    """the data gradient that lands on a residual fork (kEpiRawRes): out = bf16(conv + res), one rounding, equal to the
+    generic epilogue's result on the direct path"""
+    x = _rand((N, cin, H, W), 11).to(torch.bfloat16)
+    w = _rand((cout, cin, k, k), 12, (2.0 / (cin * k * k)) ** 0.5)
+    res = _rand((N, cout, H, W), 13).to(torch.bfloat16)
+    want = F.conv2d(x.float(), w.to(torch.bfloat16).float(), None, 1, dil * (k // 2), dil) + res.float()
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    rn = res.permute(0, 2, 3, 1).contiguous().to(DEV)
+    wp, _ = _lib.pack_conv_weights(w.to(DEV), cin, fwd_pad=(_cpad(cout), -(-cin // 64) * 64))
+    got = _lib.conv_fused(xn, wp, cout, dil=dil, res=rn)
+    torch.cuda.synchronize()
+    g = got.float().permute(0, 3, 1, 2).cpu()
+    assert (g - want).abs().max().item() < 1e-2 * want.abs().max().item()
+    prev = _lib.lib().pp_conv_set_epilogue(0)
+    try:
+        assert torch.equal(got, _lib.conv_fused(xn, wp, cout, dil=dil, res=rn))
+    finally:
+        _lib.lib().pp_conv_set_epilogue(prev)
+
+
+def test_identity_shortcut_gradient_through_the_link():
+    """resnet_models.py:74-94 in train mode: with the shortcut's gradient handed to conv1's dgrad epilogue (_ResLink) the
+    input / weight gradients are those of the autograd-add form.  The step's fp32 atomics make two runs of the SAME form
+    differ (more so towards the stem: 50 train-mode BatchNorm layers amplify the last bit), so the yardstick is that
+    run-to-run floor, measured here, not zero."""
+    import pixelpick_b200.deeplab as dl
+    from pixelpick_b200.deeplab import ResNet50Dilated8
+
+    torch.manual_seed(3)
+    bb = ResNet50Dilated8().to(DEV).train()
+    with torch.no_grad():
+        for n, p in bb.named_parameters():
+            if n.endswith("bn3.weight"):
+                p.mul_(0.05)  # the residual branches start small, as in a trained / zero-init-residual network
+    x = torch.randn(4, 3, 128, 256, device=DEV)
+    grads = []
+    for mode in (True, False, False):
+        dl._RES_LINK = mode
+        try:
+            bb.zero_grad(set_to_none=True)
+            xi = x.clone().requires_grad_(True)
+            t, c2 = dl._rn50_train_forward(bb, xi, torch.bfloat16, {})
+            (t.float().square().mean() + c2.float().square().mean()).backward()
+            g = {n: p.grad.detach().float().clone() for n, p in bb.named_parameters()}
+            g["x"] = xi.grad.detach().float().clone()
+            grads.append(g)
+        finally:
+            dl._RES_LINK = True
+    link, ref, ref2 = grads
+    worst = 0.0
+    for n, g in link.items():
+        cos = F.cosine_similarity(g.flatten(), ref[n].flatten(), dim=0).item()
+        floor = F.cosine_similarity(ref2[n].flatten(), ref[n].flatten(), dim=0).item()
+        worst = max(worst, 1 - cos)
+        assert 1 - cos <= 3 * (1 - floor) + 0.02, (n, cos, floor)
+        assert abs(g.norm().item() / max(ref[n].norm().item(), 1e-20) - 1) < 0.1 + 3 * abs(ref2[n].norm().item() / max(ref[n].norm().item(), 1e-20) - 1), n
+    print("shortcut link: worst 1 - cos over the parameters", worst)
