@@ -284,30 +284,38 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         decode(tile, n0, img, y0, x0);
         n0_cta = n0;
         const uint32_t acc = tile_iter & 1u, aph = (tile_iter >> 1) & 1u;
-        tc::mbar_wait(tfull_bar(acc), aph);
-        tc::tc_fence_after();
         const int y = y0 + ty_in, x = x0 + tx_in;
         const bool valid = (y < p.H) && (x < p.W);
         const size_t pix = ((size_t)img * p.H + y) * p.W + x;
+        uint4 rq[EPI == kEpiRawRes ? NSLOT : 1][4];
+        if constexpr (EPI == kEpiRawRes) {
+          // this pixel's 64 B per chunk of the other branch: issued BEFORE waiting for the accumulator, so the loads fly
+          // under the tile's main loop instead of stalling every unit for a DRAM round trip
+#pragma unroll
+          for (int slot = 0; slot < NSLOT; ++slot) {
+            const int cb = n0 + (eh + 2 * slot) * 32;
+            const bool on = valid && (eh + 2 * slot) < BN / 32 && cb < p.Cout;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              rq[slot][u] = on ? __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.ld_res + cb) + u) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        tc::mbar_wait(tfull_bar(acc), aph);
+        tc::tc_fence_after();
 #pragma unroll
         for (int slot = 0; slot < NSLOT; ++slot) {
           const int j = eh + 2 * slot;
           const int cbase = n0 + j * 32;
           if (j >= BN / 32 || cbase >= p.Cout) continue;  // warp-uniform: no such chunk / entirely in the channel padding
           uint32_t r[32];
-          uint4 rq[4];
-          if constexpr (EPI == kEpiRawRes) {  // this pixel's 64 B of the other branch, in flight while TMEM is read
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              rq[u] = valid ? __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.ld_res + cbase) + u) : make_uint4(0u, 0u, 0u, 0u);
-          }
           tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + j * 32, r);
           tc::tmem_ld_wait();
           uint32_t pk[16];
           if constexpr (EPI == kEpiRawRes) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const uint32_t w4[4] = {rq[u].x, rq[u].y, rq[u].z, rq[u].w};
+              const uint4 q4 = rq[EPI == kEpiRawRes ? slot : 0][u];
+              const uint32_t w4[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int c = 8 * u + 2 * e;
