@@ -265,6 +265,19 @@ int pp_conv_wgrad_multi(const void* x, int x_channels, int ld_x, int Cin, const 
 int pp_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* y, unsigned char* code, void* stream);
 int pp_maxpool3x3s2_bwd(const void* dy, const unsigned char* code, int N, int H, int W, int C, void* dx, void* stream);
 
+/* model.py:121 `self.optimizer.step()` with the Adam that utils/utils.py:112-141 builds for `cs` (torch.optim.Adam: L2 weight
+ * decay folded into the gradient, bias-corrected moments, no amsgrad): the update of ALL n_tensors fp32 parameter tensors in one
+ * launch.  params / grads / exp_avg / exp_avg_sq: HOST arrays of n_tensors DEVICE pointers (tensor i holds numel[i] floats and
+ * belongs to parameter group group[i] < n_groups <= 8); lr[g] = DEVICE fp32 scalar of group g (a scheduler may rewrite it between
+ * CUDA-graph replays); beta1 / beta2 / eps / weight_decay: HOST arrays of n_groups doubles; step = DEVICE fp32 scalar holding
+ * the step count t >= 1 of THIS update (the caller increments it first, as torch does).  Per element, in fp32 with the
+ * hyper-parameters rounded to fp32 and the fused multiply-adds of ATen's fused_adam_utils.cuh:
+ *   g += wd * p;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps). */
+int pp_adam_step_multi(int n_tensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                       void* const* exp_avg_sq, const long long* numel, const int* group, int n_groups,
+                       const float* const* lr, const double* beta1, const double* beta2, const double* eps,
+                       const double* weight_decay, const float* step, void* stream);
+
 /* pp_bn_finalize + pp_bn_apply(_res) in ONE launch, for per-channel sums that already exist (pp_conv_igemm_stats): every thread
  * derives scale / shift of its 8 channels from sums [2][C] (same arithmetic as pp_bn_finalize), block 0 writes stats_out
  * [4][C] = (scale, shift, mean, rstd) for pp_bn_bwd and updates running_mean / running_var (may be NULL) as nn.BatchNorm2d

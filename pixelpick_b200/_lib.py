@@ -81,6 +81,7 @@ _SIGNATURES = {
     "pp_conv_wgrad_multi": ([_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
     "pp_maxpool3x3s2_fwd": ([_vp, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "pp_maxpool3x3s2_bwd": ([_vp, _vp, _i, _i, _i, _i, _vp, _vp], _i),
+    "pp_adam_step_multi": ([_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "pp_dwconv3x3_fwd": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "pp_dwconv3x3_fwd_bnact": ([_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     "pp_dwconv3x3_dgrad": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
@@ -893,3 +894,40 @@ class AcqSession:
             self.close()
         except Exception:
             pass
+
+
+class AdamPlan:
+    """The argument arrays of pp_adam_step_multi for a fixed list of tensors (host arrays of device pointers): built once,
+    reused while no tensor moves (`key` = the data pointers it was built from)."""
+
+    def __init__(self, params, grads, exp_avg, exp_avg_sq, group, lrs, beta1, beta2, eps, weight_decay, step):
+        _need_cuda(*params, *grads, *exp_avg, *exp_avg_sq, *lrs, step)
+        for ts in (params, grads, exp_avg, exp_avg_sq):
+            for t in ts:
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    raise PixelPickError("pp_adam_step_multi: parameters, gradients and moments must be contiguous fp32")
+        if any(g.numel() != p.numel() or m.numel() != p.numel() or v.numel() != p.numel()
+               for p, g, m, v in zip(params, grads, exp_avg, exp_avg_sq)):
+            raise PixelPickError("pp_adam_step_multi: gradient / moment sizes differ from the parameter's")
+        if step.dtype != torch.float32 or any(lr.dtype != torch.float32 for lr in lrs):
+            raise PixelPickError("pp_adam_step_multi: step and learning rates must be fp32 device scalars")
+        n, ng = len(params), len(lrs)
+        self.n, self.ng = n, ng
+        self.key = self.make_key(params, grads, exp_avg, exp_avg_sq, lrs, step)
+        arr = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        self.p, self.g, self.m, self.v, self.lr = arr(params), arr(grads), arr(exp_avg), arr(exp_avg_sq), arr(lrs)
+        self.numel = (C.c_longlong * n)(*[t.numel() for t in params])
+        self.group = (C.c_int * n)(*group)
+        dbl = lambda xs: (C.c_double * ng)(*[float(x) for x in xs])
+        self.b1, self.b2, self.eps, self.wd = dbl(beta1), dbl(beta2), dbl(eps), dbl(weight_decay)
+        self.step = step
+        self.keep = (params, grads, exp_avg, exp_avg_sq, lrs)
+
+    @staticmethod
+    def make_key(params, grads, exp_avg, exp_avg_sq, lrs, step):
+        return tuple(t.data_ptr() for ts in (params, grads, exp_avg, exp_avg_sq, lrs) for t in ts) + (step.data_ptr(),)
+
+    def launch(self):
+        check(lib().pp_adam_step_multi(self.n, self.p, self.g, self.m, self.v, self.numel, self.group, self.ng, self.lr,
+                                       self.b1, self.b2, self.eps, self.wd, _ptr(self.step), _stream(self.step)),
+              "pp_adam_step_multi")

@@ -4,6 +4,8 @@
 Static inputs: the image batch, a fixed-capacity labelled-pixel list + its device-side count (pp_sparse_ce reads the
 count on the device), the dropout step counter (device int64 advanced inside the graph) and tensor learning rates.
 """
+import os
+
 import torch
 
 from . import dist as ppdist
@@ -11,7 +13,8 @@ from .loss import LabelCapacityError, labelled_pixel_list_host, sparse_cross_ent
 
 
 def make_capturable_adam(param_groups):
-    """torch.optim.Adam(fused, capturable) with TENSOR learning rates so a scheduler can change them between replays."""
+    """torch.optim.Adam(fused, capturable) with TENSOR learning rates so a scheduler can change them between replays; its
+    step is one launch of pp_adam_step_multi (optim.FusedAdam; PP_ADAM=torch keeps torch's multi-tensor kernel: A/B only)."""
     dev = param_groups[0]["params"][0].device if not hasattr(param_groups[0]["params"], "__next__") else None
     groups = []
     for g in param_groups:
@@ -20,7 +23,10 @@ def make_capturable_adam(param_groups):
         dev = g["params"][0].device
         g["lr"] = torch.tensor(float(g["lr"]), dtype=torch.float32, device=dev)
         groups.append(g)
-    return torch.optim.Adam(groups, fused=True, capturable=True)
+    if os.environ.get("PP_ADAM", "ours") == "torch":
+        return torch.optim.Adam(groups, fused=True, capturable=True)
+    from .optim import FusedAdam
+    return FusedAdam(groups)
 
 
 class GraphedTrainStep:

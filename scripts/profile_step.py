@@ -11,7 +11,8 @@ dev = torch.device("cuda:0")
 backbone = sys.argv[1] if len(sys.argv) > 1 else "mobilenet"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 model = DeepLab(bench.MARGS, backbone=backbone).to(dev).train()
-opt = torch.optim.Adam(model.parameters(), lr=5e-4, fused=True)
+from pixelpick_b200.graph import make_capturable_adam
+opt = make_capturable_adam([{"params": list(model.parameters()), "lr": 5e-4, "weight_decay": 2e-4}])  # optim.FusedAdam
 x, y, q = [t.to(dev) for t in bench.synth_train_batch(B, 1)]
 def step():
     lr = model.forward_lowres(x)
