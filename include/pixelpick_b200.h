@@ -391,9 +391,14 @@ int pp_augment_geometric(const uint8_t* x, const uint8_t* y, const uint8_t* q, c
                          uint8_t* q_out, uint8_t* lq_out, void* stream);
 
 /* The same for EVERY convolution of a network in one launch (a train step re-packs ~50 weights after each optimiser
- * update): table_dev = device array of n rows of 11 int64 {w, fwd, dgrad pointers, Cout, Cin, Cin_total, taps, Cout_pad,
- * Cin_pad, Cin_rows, Cout_cols} with the meaning of pp_pack_conv_weight's arguments; blocks_per_conv CTAs work on each row. */
-int pp_pack_conv_weights_batched(const long long* table_dev, int n, int blocks_per_conv, void* stream);
+ * update): table_dev = device array of n rows of 12 int64 {w, fwd, dgrad pointers, Cout, Cin, Cin_total, taps, Cout_pad,
+ * Cin_pad, Cin_rows, Cout_cols, first_tile} with the meaning of pp_pack_conv_weight's arguments.  The work is cut into tiles
+ * of 64 x 64 (1x1) / 32 x 32 x 9 (3x3) weights, one CTA each: pp_pack_conv_weights_tiles() gives a row's tile count (taps must
+ * be 1 or 9, the inner extents Cin_pad / Cout_cols multiples of 8 and the images 16-byte aligned; pass 0, 0 for an image that
+ * is not wanted), first_tile is the running
+ * sum over the rows before it and total_tiles the sum over all rows. */
+int pp_pack_conv_weights_tiles(int Cout_pad, int Cin_pad, int Cin_rows, int Cout_cols, int taps);
+int pp_pack_conv_weights_batched(const long long* table_dev, int n, int total_tiles, void* stream);
 /* strided [N,C,H,W] f32/bf16 -> bf16 NHWC channel slice (backbone boundary, d(logits) for the classifier) */
 int pp_to_nhwc_bf16(const void* in, int dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw, int N, int C, int H,
                     int W, void* out, int ld, int c_off, void* stream);

@@ -90,6 +90,7 @@ _SIGNATURES = {
     "pp_upsample_nhwc_bf16_bwd": ([_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_pack_conv_weight": ([_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_pack_conv_weights_batched": ([_vp, _i, _i, _vp], _i),
+    "pp_pack_conv_weights_tiles": ([_i, _i, _i, _i, _i], _i),
     "pp_augment_geometric": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "pp_to_nhwc_bf16": ([_vp, _i, _i64, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_conv_igemm": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp], _i),
@@ -472,11 +473,19 @@ def pack_conv_weights(w, cin=None, fwd_pad=None, dgrad_pad=None, dgrad_out=None)
     return fwd, dgr
 
 
-def pack_conv_weights_batched(table, n, blocks_per_conv=256):
-    """table: device int64 [n, 11] (see pp_pack_conv_weights_batched): re-packs every listed conv weight in one launch."""
+def pack_conv_weights_tiles(fwd_pad, dgrad_pad, taps):
+    """tiles (CTAs) pp_pack_conv_weights_batched spends on one conv; fwd_pad / dgrad_pad as in pack_conv_weights (or None)"""
+    n = lib().pp_pack_conv_weights_tiles(*(fwd_pad or (0, 0)), *(dgrad_pad or (0, 0)), int(taps))
+    if n < 0:
+        raise PixelPickError(f"pp_pack_conv_weights_tiles: {lib().pp_last_error().decode()}")
+    return n
+
+
+def pack_conv_weights_batched(table, n, total_tiles):
+    """table: device int64 [n, 12] (see pp_pack_conv_weights_batched): re-packs every listed conv weight in one launch."""
     _need_cuda(table)
-    assert table.dtype == torch.int64 and table.is_contiguous() and table.numel() == 11 * n
-    check(lib().pp_pack_conv_weights_batched(_ptr(table), n, blocks_per_conv, _stream(table)), "pp_pack_conv_weights_batched")
+    assert table.dtype == torch.int64 and table.is_contiguous() and table.numel() == 12 * n
+    check(lib().pp_pack_conv_weights_batched(_ptr(table), n, int(total_tiles), _stream(table)), "pp_pack_conv_weights_batched")
 
 
 def conv_igemm(x_nhwc, w_packed, cout, dil=1, pre_bias=None, scale=None, shift=None, relu=False, out=None,

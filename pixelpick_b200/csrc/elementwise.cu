@@ -1131,43 +1131,143 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
 }  // namespace pp
 
 namespace pp {
-// every conv of a network in ONE launch: blockIdx.y = table row (w, fwd, dgrad pointers + the shapes of pack_weight_kernel)
-__global__ void __launch_bounds__(256) pack_weight_batched_kernel(const long long* __restrict__ table) {
-  const long long* d = table + (size_t)blockIdx.y * 11;
-  const float* w = reinterpret_cast<const float*>(d[0]);
-  __nv_bfloat16* fwd = reinterpret_cast<__nv_bfloat16*>(d[1]);
-  __nv_bfloat16* dgr = reinterpret_cast<__nv_bfloat16*>(d[2]);
-  const int Cout = (int)d[3], Cin = (int)d[4], Cin_total = (int)d[5], taps = (int)d[6];
-  const int Cout_pad = (int)d[7], Cin_pad = (int)d[8], Cin_rows = (int)d[9], Cout_cols = (int)d[10];
-  const int64_t n_f = fwd ? (int64_t)taps * Cout_pad * Cin_pad : 0;
-  const int64_t n_d = dgr ? (int64_t)taps * Cin_rows * Cout_cols : 0;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_f + n_d; i += (int64_t)gridDim.x * 256) {
-    if (i < n_f) {
-      const int ci = (int)(i % Cin_pad);
-      const int64_t t = i / Cin_pad;
-      const int co = (int)(t % Cout_pad), tap = (int)(t / Cout_pad);
+// Tiled form (taps = 1 or 9, the only kernel sizes packed in this network): a CTA owns a T x T block of (co, ci) with all
+// its taps - T = 64 for 1x1, 32 for 3x3 - reads it as T runs of T * taps CONTIGUOUS floats, keeps it in shared memory as
+// bf16 and writes both operand images in contiguous runs of T elements (forward along ci, data gradient along co).  The
+// gather form above reads the fp32 master with a stride of taps (forward) or Cin * taps (data gradient) floats per thread
+// and ran at ~1 TB/s; this one touches every byte once.
+struct PackDesc {
+  const float* w;
+  __nv_bfloat16* fwd;
+  __nv_bfloat16* dgr;
+  int Cout, Cin, Cin_total, taps, Cout_pad, Cin_pad, Cin_rows, Cout_cols;
+};
+
+__host__ __device__ inline int pack_tile_edge(int taps) { return taps == 1 ? 64 : 32; }
+__host__ __device__ inline int pack_co_extent(const PackDesc& d) {
+  const int a = d.fwd ? d.Cout_pad : 0, b = d.dgr ? d.Cout_cols : 0;
+  return a > b ? a : b;
+}
+__host__ __device__ inline int pack_ci_extent(const PackDesc& d) {
+  const int a = d.fwd ? d.Cin_pad : 0, b = d.dgr ? d.Cin_rows : 0;
+  return a > b ? a : b;
+}
+__host__ __device__ inline int pack_num_tiles(const PackDesc& d) {
+  const int T = pack_tile_edge(d.taps);
+  return ((pack_co_extent(d) + T - 1) / T) * ((pack_ci_extent(d) + T - 1) / T);
+}
+static bool pack_tiled_ok(const PackDesc& d) {
+  return (d.taps == 1 || d.taps == 9) && (!d.fwd || (d.Cin_pad % 8 == 0 && (reinterpret_cast<uintptr_t>(d.fwd) & 15u) == 0)) &&
+         (!d.dgr || (d.Cout_cols % 8 == 0 && (reinterpret_cast<uintptr_t>(d.dgr) & 15u) == 0));
+}
+
+constexpr int kPackSmemElems = 9 * (32 * 34 + 2);  // >= 64 * 66
+
+template <int TAPS, int T>
+__device__ __forceinline__ void pack_tile(const PackDesc& d, int tile, __nv_bfloat16* sm) {
+  constexpr int P = T + 2;  // row pitch: even (4-byte pair reads along ci), odd in 4-byte words (conflict-free reads along co)
+  constexpr int TS = T * P + 2;  // tap pitch: one word past a multiple of 32 words, so the 9 taps of a pixel hit 9 banks
+  constexpr int RUN = T * TAPS;  // contiguous floats of one output channel inside the tile
+  const int n_ci_t = (pack_ci_extent(d) + T - 1) / T;
+  const int co0 = (tile / n_ci_t) * T, ci0 = (tile % n_ci_t) * T;
+  const bool full = co0 + T <= d.Cout && ci0 + T <= d.Cin && (((int64_t)d.Cin_total * TAPS) & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d.w) & 15u) == 0;  // RUN * ci0 / T is a multiple of 4 floats by construction
+  if (full) {
+    for (int e4 = threadIdx.x; e4 < T * RUN / 4; e4 += 256) {
+      const int co_l = e4 / (RUN / 4), r4 = (e4 - co_l * (RUN / 4)) * 4;
+      const float4 q = __ldg(reinterpret_cast<const float4*>(d.w + ((int64_t)(co0 + co_l) * d.Cin_total + ci0) * TAPS + r4));
+      const float qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r4 + u, ci_l = r / TAPS, tap = r - ci_l * TAPS;
+        sm[tap * TS + co_l * P + ci_l] = __float2bfloat16(qv[u]);
+      }
+    }
+  } else {
+    for (int e = threadIdx.x; e < T * RUN; e += 256) {
+      const int co_l = e / RUN, r = e - co_l * RUN;
+      const int ci_l = r / TAPS, tap = r - ci_l * TAPS;
+      const int co = co0 + co_l, ci = ci0 + ci_l;
       float v = 0.f;
-      if (ci < Cin && co < Cout) v = w[((int64_t)co * Cin_total + ci) * taps + tap];
-      fwd[i] = __float2bfloat16(v);
-    } else {
-      const int64_t j = i - n_f;
-      const int co = (int)(j % Cout_cols);
-      const int64_t t = j / Cout_cols;
-      const int ci = (int)(t % Cin_rows), tap = (int)(t / Cin_rows);
-      float v = 0.f;
-      if (ci < Cin && co < Cout) v = w[((int64_t)co * Cin_total + ci) * taps + (taps - 1 - tap)];
-      dgr[j] = __float2bfloat16(v);
+      if (co < d.Cout && ci < d.Cin) v = __ldg(d.w + ((int64_t)co * d.Cin_total + ci) * TAPS + tap);
+      sm[tap * TS + co_l * P + ci_l] = __float2bfloat16(v);
+    }
+  }
+  __syncthreads();
+  // stores: 8 elements (16 bytes) per thread
+  if (d.fwd) {
+    for (int e = threadIdx.x; e < TAPS * T * (T / 8); e += 256) {
+      const int ci_l = (e % (T / 8)) * 8, t2 = e / (T / 8);
+      const int co_l = t2 % T, tap = t2 / T;
+      const int co = co0 + co_l, ci = ci0 + ci_l;
+      if (co < d.Cout_pad && ci < d.Cin_pad) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(sm + tap * TS + co_l * P + ci_l);
+        *reinterpret_cast<uint4*>(d.fwd + ((int64_t)tap * d.Cout_pad + co) * d.Cin_pad + ci) = make_uint4(src[0], src[1], src[2], src[3]);
+      }
+    }
+  }
+  if (d.dgr) {
+    for (int e = threadIdx.x; e < TAPS * T * (T / 8); e += 256) {
+      const int co_l = (e % (T / 8)) * 8, t2 = e / (T / 8);
+      const int ci_l = t2 % T, tap = t2 / T;
+      const int co = co0 + co_l, ci = ci0 + ci_l;
+      if (ci < d.Cin_rows && co < d.Cout_cols) {
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(sm + tap * TS + co_l * P + ci_l);
+        uint32_t o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[u] = (uint32_t)src[(2 * u) * P] | ((uint32_t)src[(2 * u + 1) * P] << 16);
+        *reinterpret_cast<uint4*>(d.dgr + ((int64_t)(TAPS - 1 - tap) * d.Cin_rows + ci) * d.Cout_cols + co) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
 }
+
+__global__ void __launch_bounds__(256) pack_weight_tiled_kernel(const PackDesc d) {
+  __shared__ __align__(16) __nv_bfloat16 sm[kPackSmemElems];
+  if (d.taps == 1) pack_tile<1, 64>(d, blockIdx.x, sm);
+  else pack_tile<9, 32>(d, blockIdx.x, sm);
+}
+
+// every conv of a network in ONE launch: table row = (w, fwd, dgrad pointers, the 8 shapes of PackDesc, first tile of the row);
+// blockIdx.x = tile, its row found by bisection
+__global__ void __launch_bounds__(256) pack_weight_batched_kernel(const long long* __restrict__ table, int n) {
+  __shared__ __align__(16) __nv_bfloat16 sm[kPackSmemElems];
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((int)table[(size_t)mid * 12 + 11] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const long long* r = table + (size_t)lo * 12;
+  PackDesc d;
+  d.w = reinterpret_cast<const float*>(r[0]);
+  d.fwd = reinterpret_cast<__nv_bfloat16*>(r[1]);
+  d.dgr = reinterpret_cast<__nv_bfloat16*>(r[2]);
+  d.Cout = (int)r[3]; d.Cin = (int)r[4]; d.Cin_total = (int)r[5]; d.taps = (int)r[6];
+  d.Cout_pad = (int)r[7]; d.Cin_pad = (int)r[8]; d.Cin_rows = (int)r[9]; d.Cout_cols = (int)r[10];
+  const int tile = (int)blockIdx.x - (int)r[11];
+  if (tile >= pack_num_tiles(d)) return;
+  if (d.taps == 1) pack_tile<1, 64>(d, tile, sm);
+  else pack_tile<9, 32>(d, tile, sm);
+}
 }  // namespace pp
 
-extern "C" int pp_pack_conv_weights_batched(const long long* table_dev, int n, int blocks_per_conv, void* stream) {
-  PP_CHECK_ARG(table_dev && n > 0 && n <= 65535 && blocks_per_conv > 0, "pp_pack_conv_weights_batched: bad args");
-  dim3 grid((unsigned)blocks_per_conv, (unsigned)n);
-  pp::pack_weight_batched_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table_dev);
+extern "C" int pp_pack_conv_weights_batched(const long long* table_dev, int n, int total_tiles, void* stream) {
+  PP_CHECK_ARG(table_dev && n > 0 && n <= 65535 && total_tiles > 0, "pp_pack_conv_weights_batched: bad args");
+  pp::pack_weight_batched_kernel<<<(unsigned)total_tiles, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table_dev, n);
   PP_LAUNCH_CHECK();
   return PP_OK;
+}
+
+extern "C" int pp_pack_conv_weights_tiles(int Cout_pad, int Cin_pad, int Cin_rows, int Cout_cols, int taps) {
+  pp::PackDesc d{};
+  d.fwd = Cout_pad > 0 ? reinterpret_cast<__nv_bfloat16*>(16) : nullptr;
+  d.dgr = Cin_rows > 0 ? reinterpret_cast<__nv_bfloat16*>(16) : nullptr;
+  d.taps = taps; d.Cout_pad = Cout_pad; d.Cin_pad = Cin_pad; d.Cin_rows = Cin_rows; d.Cout_cols = Cout_cols;
+  if (!(taps == 1 || taps == 9) || (d.fwd && Cin_pad % 8) || (d.dgr && Cout_cols % 8) || (!d.fwd && !d.dgr)) {
+    pp::set_error("pp_pack_conv_weights_tiles: taps must be 1 or 9 and the inner extents multiples of 8");
+    return -1;
+  }
+  return pp::pack_num_tiles(d);
 }
 
 extern "C" int pp_pack_conv_weight(const float* w, int Cout, int Cin, int Cin_total, int taps, void* fwd, int Cout_pad,
@@ -1175,6 +1275,15 @@ extern "C" int pp_pack_conv_weight(const float* w, int Cout, int Cin, int Cin_to
   PP_CHECK_ARG(w && (fwd || dgrad) && Cout > 0 && Cin > 0 && Cin <= Cin_total && taps > 0, "pp_pack_conv_weight: bad args");
   PP_CHECK_ARG(!fwd || (Cout_pad >= Cout && Cin_pad >= Cin), "pp_pack_conv_weight: fwd padding smaller than the tensor");
   PP_CHECK_ARG(!dgrad || (Cin_rows >= Cin && Cout_cols >= Cout), "pp_pack_conv_weight: dgrad padding smaller than the tensor");
+  {
+    pp::PackDesc d{w, reinterpret_cast<__nv_bfloat16*>(fwd), reinterpret_cast<__nv_bfloat16*>(dgrad), Cout, Cin, Cin_total, taps,
+                   Cout_pad, Cin_pad, Cin_rows, Cout_cols};
+    if (pp::pack_tiled_ok(d)) {
+      pp::pack_weight_tiled_kernel<<<(unsigned)pp::pack_num_tiles(d), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d);
+      PP_LAUNCH_CHECK();
+      return PP_OK;
+    }
+  }
   const int64_t total = (fwd ? (int64_t)taps * Cout_pad * Cin_pad : 0) + (dgrad ? (int64_t)taps * Cin_rows * Cout_cols : 0);
   pp::pack_weight_kernel<<<pp::ew_grid(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       w, Cout, Cin, Cin_total, taps, reinterpret_cast<__nv_bfloat16*>(fwd), Cout_pad, Cin_pad,

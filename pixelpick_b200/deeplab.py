@@ -625,6 +625,7 @@ class _EncoderTrainPlan:
         self.stats = torch.zeros(n_st, dtype=torch.float32, device=device)
         self.dw = torch.zeros(n_dw, dtype=torch.float32, device=device)
         self.slots = {}
+        n_tiles = 0
         for conv, (fwd, dgr, dw, co, ci, taps, o_wp, o_wd, o_st, o_dw) in zip(convs, sizes):
             sl = _Slot()
             sl.wp = self.wp[o_wp:o_wp + fwd[0] * fwd[1] * fwd[2]].view(fwd)
@@ -633,12 +634,14 @@ class _EncoderTrainPlan:
             sl.dw = self.dw[o_dw:o_dw + dw[0] * dw[1] * dw[2]].view(dw)
             sl.dirty = False
             self.slots[id(conv)] = sl
-            rows.append([conv.weight.data_ptr(), sl.wp.data_ptr(), sl.wd.data_ptr(), co, ci, ci, taps, fwd[1], fwd[2], dgr[1], dgr[2]])
+            rows.append([conv.weight.data_ptr(), sl.wp.data_ptr(), sl.wd.data_ptr(), co, ci, ci, taps, fwd[1], fwd[2], dgr[1], dgr[2],
+                         n_tiles])
+            n_tiles += _lib.pack_conv_weights_tiles(fwd[1:], dgr[1:], taps)
         self.counters = []  # num_batches_tracked of the BatchNorm layers that follow these convs (filled by the forward)
         self.weights = [conv.weight for conv in convs]
         self.ptrs = [w.data_ptr() for w in self.weights]
         self.table = torch.tensor(rows, dtype=torch.int64).to(device)
-        self.n = len(rows)
+        self.n, self.n_tiles = len(rows), n_tiles
 
     def valid(self):
         return all(w.data_ptr() == p for w, p in zip(self.weights, self.ptrs))
@@ -650,7 +653,7 @@ class _EncoderTrainPlan:
         for sl in self.slots.values():
             sl.dirty = False
         self.step_counters = []
-        _lib.pack_conv_weights_batched(self.table, self.n)
+        _lib.pack_conv_weights_batched(self.table, self.n, self.n_tiles)
 
     def end_forward(self):
         """nn.BatchNorm2d.num_batches_tracked += 1 for every layer the forward went through: one multi-tensor launch"""

@@ -144,3 +144,38 @@ def test_conv_fused_epilogue_ragged_channels(N, H, W, Cin, Cout, k, dil, act, wi
     assert tuple(out.shape) == (N, H, W, Cout)
     got = out.float().permute(0, 3, 1, 2).cpu()
     assert (got - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("co,ci_tot,cin,k", [(256, 64, 64, 1), (64, 256, 256, 1), (2048, 512, 512, 1), (24, 144, 144, 1), (256, 1280, 1024, 1),
+                                            (256, 304, 304, 3), (128, 128, 128, 3), (96, 40, 40, 3), (19, 256, 256, 1), (48, 24, 24, 5)])
+def test_weight_packing_kernels_equal_the_torch_layout(co, ci_tot, cin, k):
+    """pp_pack_conv_weight (tiled through shared memory for 1x1 / 3x3, gather form otherwise): both operand images, bit for bit,
+    with ragged channel counts, a channel sub-range (cin < Cin_total) and the padding written as zeros"""
+    w = torch.randn((co, ci_tot, k, k), generator=torch.Generator().manual_seed(co + ci_tot)).to(DEV)
+    taps = k * k
+    fwd_pad = (-(-co // 32) * 32 if co > 32 else 32, -(-cin // 64) * 64)
+    dgr_pad = (-(-cin // 64) * 64, -(-co // 64) * 64)
+    fwd, dgr = _lib.pack_conv_weights(w, cin, fwd_pad=fwd_pad, dgrad_pad=dgr_pad)
+    ws = w[:, :cin].contiguous()
+    assert torch.equal(fwd, _lib.pack_conv_weight(ws, fwd_pad[1], fwd_pad[0]))
+    assert torch.equal(dgr, _lib.pack_conv_weight(ws, dgr_pad[1], dgr_pad[0], transpose_for_dgrad=True))
+    only_d = torch.full((taps,) + dgr_pad, 7.0, dtype=torch.bfloat16, device=DEV)
+    _lib.pack_conv_weights(w, cin, dgrad_pad=dgr_pad, dgrad_out=only_d)
+    assert torch.equal(only_d, dgr)
+
+
+def test_batched_weight_packing_equals_the_per_conv_launches():
+    import torch.nn as nn
+    from pixelpick_b200.deeplab import _EncoderTrainPlan
+    torch.manual_seed(0)
+    convs = [nn.Conv2d(64, 256, 1, bias=False), nn.Conv2d(256, 64, 1, bias=False), nn.Conv2d(64, 64, 3, padding=1, bias=False),
+             nn.Conv2d(24, 144, 1, bias=False), nn.Conv2d(512, 512, 3, padding=4, dilation=4, bias=False), nn.Conv2d(960, 320, 1, bias=False)]
+    convs = [c.to(DEV) for c in convs]
+    plan = _EncoderTrainPlan(convs, DEV)
+    plan.wp.fill_(3.0)
+    plan.wd.fill_(3.0)
+    plan.begin_step()
+    for c in convs:
+        sl = plan.slots[id(c)]
+        f, d = _lib.pack_conv_weights(c.weight, c.in_channels, fwd_pad=tuple(sl.wp.shape[1:]), dgrad_pad=tuple(sl.wd.shape[1:]))
+        assert torch.equal(sl.wp, f) and torch.equal(sl.wd, d), c
