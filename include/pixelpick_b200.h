@@ -390,6 +390,27 @@ int pp_augment_geometric(const uint8_t* x, const uint8_t* y, const uint8_t* q, c
                          const float* std3, const int* mean_val3, int ignore_index, float* x_out, uint8_t* y_out,
                          uint8_t* q_out, uint8_t* lq_out, void* stream);
 
+/* pp_augment_geometric with the image left as uint8 [B][crop_h][crop_w][3] (HWC, what the PIL image holds after
+ * base_dataset.py:48-127) instead of the normalised tensor: the input of pp_augment_photometric. */
+int pp_augment_geometric_u8(const uint8_t* x, const uint8_t* y, const uint8_t* q, const uint8_t* lq, int B, int H, int W,
+                            const int32_t* header, const int32_t* tables, int crop_h, int crop_w, const int* mean_val3,
+                            int ignore_index, uint8_t* x_u8_out, uint8_t* y_out, uint8_t* q_out, uint8_t* lq_out, void* stream);
+
+/* Photometric augmentation of a uint8 batch on the device - datasets/base_dataset.py:129-141: RandomApply([ColorJitter(0.8, 0.8,
+ * 0.8, 0.2)], p = 0.8), RandomGrayscale(0.2), GaussianBlur (cv2, p = 0.5; base_dataset.py:192-210) - followed by TF.to_tensor +
+ * TF.normalize (base_dataset.py:183).  The arithmetic is Pillow's (ImageEnhance / Blend.c, Convert.c RGB<->HSV, the L conversion)
+ * and OpenCV's bit-exact uint8 Gaussian, so the result equals the reference's bit for bit given the same draws.
+ * x uint8 [B][H][W][3]; header int32 [B][16] = {jitter_on, the four steps in their drawn order (0 brightness, 1 contrast,
+ * 2 saturation, 3 hue), brightness / contrast / saturation factors (fp32 bit patterns), hue shift in [0, 255] (= int32(hue * 255)
+ * mod 256), grayscale_on, blur_on, 0...}; blur_taps int32 [B][ksize] = the 8-bit fixed-point Gaussian taps of each image (sum 256;
+ * ignored where blur_on = 0; ksize = 0: no image is blurred).  The draws and the taps are made by the host
+ * (pixelpick_b200/augment.py: draw_photometric, gaussian_taps_q8).  Outputs (either may be NULL): x_out f32 [B][3][H][W]
+ * normalised with mean3 / std3, x_u8_out uint8 [B][H][W][3].  workspace: pp_augment_photometric_workspace_bytes(). */
+int pp_augment_photometric_workspace_bytes(int B, int H, int W, size_t* bytes);
+int pp_augment_photometric(const uint8_t* x, int B, int H, int W, const int32_t* header, const int32_t* blur_taps, int ksize,
+                           const float* mean3, const float* std3, void* workspace, size_t workspace_bytes, float* x_out,
+                           uint8_t* x_u8_out, void* stream);
+
 /* The same for EVERY convolution of a network in one launch (a train step re-packs ~50 weights after each optimiser
  * update): table_dev = device array of n rows of 12 int64 {w, fwd, dgrad pointers, Cout, Cin, Cin_total, taps, Cout_pad,
  * Cin_pad, Cin_rows, Cout_cols, first_tile} with the meaning of pp_pack_conv_weight's arguments.  The work is cut into tiles

@@ -92,6 +92,9 @@ _SIGNATURES = {
     "pp_pack_conv_weights_batched": ([_vp, _i, _i, _vp], _i),
     "pp_pack_conv_weights_tiles": ([_i, _i, _i, _i, _i], _i),
     "pp_augment_geometric": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "pp_augment_geometric_u8": ([_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    "pp_augment_photometric_workspace_bytes": ([_i, _i, _i, C.POINTER(C.c_size_t)], _i),
+    "pp_augment_photometric": ([_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp], _i),
     "pp_to_nhwc_bf16": ([_vp, _i, _i64, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "pp_conv_igemm": ([_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp], _i),
 }

@@ -113,7 +113,8 @@ class GpuGeometricAugment:
         self.mean_val = torch.tensor(list(mv), dtype=torch.int32)
         self.ignore_index = int(ignore_index)
 
-    def __call__(self, x_u8, y_u8=None, q_u8=None, lq_u8=None, params=None):
+    def __call__(self, x_u8, y_u8=None, q_u8=None, lq_u8=None, params=None, as_uint8=False):
+        """as_uint8: leave the image as uint8 [B, ch, cw, 3] (the PIL image before to_tensor) for the photometric step"""
         _lib._need_cuda(x_u8, y_u8, q_u8, lq_u8)
         B, H, W, C3 = x_u8.shape
         assert C3 == 3 and x_u8.dtype == torch.uint8 and x_u8.is_contiguous() and len(params) == B
@@ -124,11 +125,138 @@ class GpuGeometricAugment:
         hdr_d = torch.from_numpy(hdr).to(dev, non_blocking=True)
         tab_d = torch.from_numpy(tab).to(dev, non_blocking=True)
         ch, cw = self.crop
-        x_out = torch.empty((B, 3, ch, cw), dtype=torch.float32, device=dev)
         mk = lambda src: torch.empty((B, ch, cw), dtype=torch.uint8, device=dev) if src is not None else None
         y_out, q_out, lq_out = mk(y_u8), mk(q_u8), mk(lq_u8)
+        if as_uint8:
+            x_out = torch.empty((B, ch, cw, 3), dtype=torch.uint8, device=dev)
+            _lib.check(_lib.lib().pp_augment_geometric_u8(
+                _lib._ptr(x_u8), _lib._ptr(y_u8), _lib._ptr(q_u8), _lib._ptr(lq_u8), B, H, W, _lib._ptr(hdr_d), _lib._ptr(tab_d), ch, cw,
+                self.mean_val.data_ptr(), self.ignore_index, _lib._ptr(x_out), _lib._ptr(y_out), _lib._ptr(q_out), _lib._ptr(lq_out),
+                _lib._stream(x_u8)), "pp_augment_geometric_u8")
+            return x_out, y_out, q_out, lq_out
+        x_out = torch.empty((B, 3, ch, cw), dtype=torch.float32, device=dev)
         _lib.check(_lib.lib().pp_augment_geometric(
             _lib._ptr(x_u8), _lib._ptr(y_u8), _lib._ptr(q_u8), _lib._ptr(lq_u8), B, H, W, _lib._ptr(hdr_d), _lib._ptr(tab_d), ch, cw,
             self.mean.data_ptr(), self.std.data_ptr(), self.mean_val.data_ptr(), self.ignore_index, _lib._ptr(x_out),
             _lib._ptr(y_out), _lib._ptr(q_out), _lib._ptr(lq_out), _lib._stream(x_u8)), "pp_augment_geometric")
         return x_out, y_out, q_out, lq_out
+
+
+# =====================================================================================================================
+# photometric augmentation (datasets/base_dataset.py:129-141) - host side of `pp_augment_photometric`
+# =====================================================================================================================
+_PHDR = 16
+_JITTER = (0.8, 0.8, 0.8, 0.2)  # ColorJitter(brightness, contrast, saturation, hue) of base_dataset.py:131
+
+
+def draw_photometric(color_jitter=True, grayscale=True, blur=True):
+    """The draws of BaseDataset._photometric_augmentations for one sample, from the same global streams in the same order as
+    torchvision / the reference consume them: RandomApply (`torch.rand(1)`), ColorJitter.get_params (`torch.randperm(4)`, four
+    `torch.empty(1).uniform_`), RandomGrayscale (`torch.rand(1)`), GaussianBlur (`np.random.random_sample()` once or twice).
+    -> {"jitter": None | (order, brightness, contrast, saturation, hue), "gray": bool, "blur": None | sigma}"""
+    jitter = None
+    if color_jitter and not (0.8 < torch.rand(1)):
+        b, c, s, h = _JITTER
+        order = [int(i) for i in torch.randperm(4)]
+        fac = [float(torch.empty(1).uniform_(lo, hi)) for lo, hi in ((max(0.0, 1 - b), 1 + b), (max(0.0, 1 - c), 1 + c),
+                                                                     (max(0.0, 1 - s), 1 + s), (-h, h))]
+        jitter = (order, fac[0], fac[1], fac[2], fac[3])
+    gray = bool(torch.rand(1) < 0.2) if grayscale else False
+    sigma = None
+    if blur and np.random.random_sample() < 0.5:
+        sigma = (2.0 - 0.1) * np.random.random_sample() + 0.1
+    return {"jitter": jitter, "gray": gray, "blur": sigma}
+
+
+def blur_ksize(h: int, w: int) -> int:
+    return int((0.1 * min(w, h) // 2 * 2) + 1)  # base_dataset.py:138-140
+
+
+def gaussian_taps_q8(ksize: int, sigma: float) -> np.ndarray:
+    """The taps OpenCV's uint8 GaussianBlur uses: the double Gaussian scaled to 256, rounded half to even from the outside in
+    with the rounding error carried along, the centre tap taking the rest (smooth.dispatch.cpp, the bit-exact path)."""
+    x = np.arange(ksize, dtype=np.float64) - (ksize - 1) * 0.5
+    k = np.exp(-0.5 * x * x / (sigma * sigma))
+    k = k / k.sum()
+    res = np.zeros(ksize, dtype=np.int64)
+    err, s = 0.0, 0
+    for i in range(ksize // 2):
+        adj = k[i] * 256.0 + err
+        v0 = int(np.rint(adj))
+        err = adj - v0
+        res[i] = res[ksize - 1 - i] = v0
+        s += v0
+    res[ksize // 2] = 256 - 2 * s
+    return res.astype(np.int32)
+
+
+def build_photometric_header(draws, H: int, W: int):
+    """-> (header int32 [B, 16], taps int32 [B, ksize] or None, ksize) for pp_augment_photometric."""
+    hdr = np.zeros((len(draws), _PHDR), dtype=np.int32)
+    ks = blur_ksize(H, W)
+    any_blur = any(d["blur"] is not None for d in draws) and ks / 2 < min(H, W)
+    taps = np.zeros((len(draws), ks), dtype=np.int32) if any_blur else None
+    for b, d in enumerate(draws):
+        if d["jitter"] is not None:
+            order, fb, fc, fs, hue = d["jitter"]
+            hdr[b, 0] = 1
+            hdr[b, 1:5] = order
+            hdr[b, 5:8] = np.array([fb, fc, fs], dtype=np.float32).view(np.int32)  # Blend.c takes a C float
+            hdr[b, 8] = int(np.int32(hue * 255).astype(np.uint8))  # torchvision's uint8 hue shift
+        hdr[b, 9] = int(bool(d["gray"]))
+        if d["blur"] is not None and any_blur:
+            hdr[b, 10] = 1
+            taps[b] = gaussian_taps_q8(ks, d["blur"])
+    return hdr, taps, (ks if any_blur else 0)
+
+
+class GpuPhotometricAugment:
+    """`x = aug(x_u8, draws)`: x_u8 uint8 [B, H, W, 3] on CUDA (the crop the geometric step leaves), draws = one
+    `draw_photometric()` per sample -> float32 [B, 3, H, W] normalised (and the uint8 image with return_u8=True)."""
+
+    def __init__(self, mean, std):
+        self.mean = torch.tensor(list(mean), dtype=torch.float32)
+        self.std = torch.tensor(list(std), dtype=torch.float32)
+        self._ws = None
+
+    def __call__(self, x_u8, draws, return_u8=False):
+        _lib._need_cuda(x_u8)
+        B, H, W, C3 = x_u8.shape
+        assert C3 == 3 and x_u8.dtype == torch.uint8 and x_u8.is_contiguous() and len(draws) == B
+        hdr, taps, ks = build_photometric_header(draws, H, W)
+        dev = x_u8.device
+        hdr_d = torch.from_numpy(hdr).to(dev, non_blocking=True)
+        taps_d = torch.from_numpy(taps).to(dev, non_blocking=True) if taps is not None else None
+        need = _lib.C.c_size_t()
+        _lib.check(_lib.lib().pp_augment_photometric_workspace_bytes(B, H, W, _lib.C.byref(need)), "pp_augment_photometric_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need.value or self._ws.device != dev:
+            self._ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        out = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+        out_u8 = torch.empty_like(x_u8) if return_u8 else None
+        _lib.check(_lib.lib().pp_augment_photometric(
+            _lib._ptr(x_u8), B, H, W, _lib._ptr(hdr_d), _lib._ptr(taps_d), ks, self.mean.data_ptr(), self.std.data_ptr(),
+            _lib._ptr(self._ws), self._ws.numel(), _lib._ptr(out), _lib._ptr(out_u8), _lib._stream(x_u8)), "pp_augment_photometric")
+        return (out, out_u8) if return_u8 else out
+
+
+class GpuAugment:
+    """The reference's whole training-sample pipeline (base_dataset.py:174-183) for a raw uint8 batch on the device:
+    joint geometric augmentation -> photometric augmentation of the image -> to_tensor + normalize.
+    `x, y, queries, labelled = aug(x_u8, y_u8, q_u8, lq_u8)` draws per sample from the streams the reference uses (Python's
+    `random` for the geometry, torch / NumPy for the photometric part), or takes the draws as arguments."""
+
+    def __init__(self, crop_size, mean, std, ignore_index, mean_val=None, photometric=True):
+        self.geo = GpuGeometricAugment(crop_size, mean, std, ignore_index, mean_val)
+        self.photo = GpuPhotometricAugment(mean, std) if photometric else None
+
+    def __call__(self, x_u8, y_u8=None, q_u8=None, lq_u8=None, geo_params=None, photo_draws=None):
+        B, H, W, _ = x_u8.shape
+        if geo_params is None or (self.photo is not None and photo_draws is None):
+            geo_params, photo_draws = [], []
+            for _ in range(B):  # per sample: geometry first, then the photometric draws (base_dataset.py:175-178)
+                geo_params.append(draw_geometric(H, W, self.geo.crop))
+                photo_draws.append(draw_photometric())
+        if self.photo is None:
+            return self.geo(x_u8, y_u8, q_u8, lq_u8, geo_params)
+        x_crop, y, q, lq = self.geo(x_u8, y_u8, q_u8, lq_u8, geo_params, as_uint8=True)
+        return self.photo(x_crop, photo_draws), y, q, lq
