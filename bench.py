@@ -294,6 +294,28 @@ def _round_tree(o):
     return o
 
 
+def bench_augment(dev, B=32):
+    """datasets/base_dataset.py:174-183 on the device for one raw uint8 batch of B Cityscapes crops (256x512): host draws +
+    resampling tables + pp_augment_geometric_u8 + pp_augment_photometric, wall time per batch in ms."""
+    import random
+    from pixelpick_b200.augment import GpuAugment
+    random.seed(0)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    x = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev)
+    y = torch.randint(0, C + 1, (B, H, W), dtype=torch.uint8, device=dev)
+    q = (torch.rand((B, H, W), device=dev) < 0.01).to(torch.uint8) * 255
+    aug = GpuAugment((H, W), [0.28689554, 0.32513303, 0.28389177], [0.18696375, 0.19017339, 0.18720214], C)
+    for _ in range(2):
+        aug(x, y, q, q)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        aug(x, y, q, q)
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / 5 * 1e3
+
+
 def bench_conv_roofline(dev, peak_tf):
     """SegmentHead conv #1 (3x3, 304(320)->256) at B=32, 64x128: nominal FLOPs / CUDA-event time."""
     from pixelpick_b200 import _lib
@@ -783,6 +805,7 @@ def main():
             "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": acq["score_ms"],
             "alg_bytes_per_launch": alg, "share_of_acq_step": acq["score_ms"] / acq["ms_per_step"]}
     if rank == 0 and not args.no_extras:
+        cfg["augment_b32_ms"] = bench_augment(dev)  # the device input pipeline (geometric + photometric) for one batch of 32
         conv = bench_conv_roofline(dev, tf_burst)
         cfg.update({"conv_seghead_tflops": conv["achieved"], "conv_seghead_frac_of_bf16_peak": conv["frac"]})
         extras["roofline_tensor"] = conv
