@@ -710,7 +710,7 @@ def main():
     ap.add_argument("--fused-acq", action="store_true",
                     help="acquisition leg through pp_acq_score_select (scoring + level-0 select in one pass, a cluster per image, the "
                          "score map never written).  Bit-identical picks; measured SLOWER on B200 (0.583 vs 0.536 ms / 256 images: the "
-                         "fused kernel takes 512 us against 407 + 5 + 53 us - 18 % of every CTA's life is cluster barriers, the "
+                         "fused kernel takes 512 us against 407 + 5 + 53 us - 18 %% of every CTA's life is cluster barriers, the "
                          "leader's bucket pick and the classification, during which it does not stream), so the default stays the "
                          "three-kernel form")
     ap.add_argument("--sweep", action="store_true", help="also run the 1024x2048 strategy sweep (BASELINE configs[4])")
