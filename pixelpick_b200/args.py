@@ -47,6 +47,7 @@ _SURFACE = [
     (("--downsample",), dict(type=int, default=4, help="Cityscapes training-set downsampling")),
     (("--use_aug",), dict(type=bool, default=True)),
     (("--use_augmented_dataset",), _FLAG),
+    (("--gpu_augment",), _FLAG),  # ours: the dataset delivers raw uint8 samples, augmentation + normalise run on the device
     # encoder
     (("--n_layers",), dict(type=int, default=50, choices=[18, 34, 50, 101])),
     (("--use_dilated_resnet",), dict(type=bool, default=True)),

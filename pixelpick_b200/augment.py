@@ -245,17 +245,24 @@ class GpuAugment:
     `x, y, queries, labelled = aug(x_u8, y_u8, q_u8, lq_u8)` draws per sample from the streams the reference uses (Python's
     `random` for the geometry, torch / NumPy for the photometric part), or takes the draws as arguments."""
 
-    def __init__(self, crop_size, mean, std, ignore_index, mean_val=None, photometric=True):
+    def __init__(self, crop_size, mean, std, ignore_index, mean_val=None, photometric=True, geometric_flags=None,
+                 photometric_flags=None):
+        """geometric_flags / photometric_flags: `args.augmentations["geometric" | "photometric"]` (args.py:62-76); default all on"""
         self.geo = GpuGeometricAugment(crop_size, mean, std, ignore_index, mean_val)
-        self.photo = GpuPhotometricAugment(mean, std) if photometric else None
+        g, f = geometric_flags or {}, photometric_flags or {}
+        self.geo_flags = dict(random_scale=g.get("random_scale", True), do_crop=g.get("crop", True), random_hflip=g.get("random_hflip", True))
+        self.photo_flags = dict(color_jitter=f.get("random_color_jitter", True), grayscale=f.get("random_grayscale", True),
+                                blur=f.get("random_gaussian_blur", True))
+        self.photo = GpuPhotometricAugment(mean, std) if photometric and any(self.photo_flags.values()) else None
 
     def __call__(self, x_u8, y_u8=None, q_u8=None, lq_u8=None, geo_params=None, photo_draws=None):
         B, H, W, _ = x_u8.shape
         if geo_params is None or (self.photo is not None and photo_draws is None):
             geo_params, photo_draws = [], []
             for _ in range(B):  # per sample: geometry first, then the photometric draws (base_dataset.py:175-178)
-                geo_params.append(draw_geometric(H, W, self.geo.crop))
-                photo_draws.append(draw_photometric())
+                geo_params.append(draw_geometric(H, W, self.geo.crop, **self.geo_flags))
+                if self.photo is not None:
+                    photo_draws.append(draw_photometric(**self.photo_flags))
         if self.photo is None:
             return self.geo(x_u8, y_u8, q_u8, lq_u8, geo_params)
         x_crop, y, q, lq = self.geo(x_u8, y_u8, q_u8, lq_u8, geo_params, as_uint8=True)

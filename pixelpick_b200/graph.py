@@ -86,6 +86,8 @@ class GraphedTrainStep:
         overlaps whatever the main stream is running); returns the host label list.  Follow with commit().
         Returns None (nothing staged) when the batch holds more labelled pixels than the captured capacity: the caller
         runs that batch through the eager step."""
+        if x.is_cuda:
+            return self._prefetch_device(x, y, queries)
         try:
             pi, px, pl, n = labelled_pixel_list_host(y, queries, self.ignore_index, self.capacity,
                                                      n_classes=self.metrics.n_classes if self.metrics is not None else None)
@@ -103,6 +105,35 @@ class GraphedTrainStep:
             self.stage_ready.record(self.copy_stream)
         self._staged = True
         return pl[: int(n)].clone()
+
+    def _prefetch_device(self, x, y, queries):
+        """The batch is already on the device (augmented there, Model._device_augment): the labelled-pixel list is built with
+        device ops (one host sync for its length) and the staging buffers are filled on the copy stream."""
+        from .loss import labelled_pixel_list
+        self.commit_done.synchronize()
+        cap = self.capacity
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_stream(cur)  # no-op when the caller already works on the copy stream
+            pi, px, pl = labelled_pixel_list(y, queries, self.ignore_index)
+            n = int(pi.numel())
+            if n > cap:
+                self._staged = False
+                return None
+            n_classes = self.metrics.n_classes if self.metrics is not None else None
+            if n and n_classes is not None and (int(pl.min()) < 0 or int(pl.max()) >= n_classes):
+                raise IndexError(f"Target {int(pl[(pl < 0) | (pl >= n_classes)][0])} is out of bounds.")
+            ms = self.meta_stage
+            ms.zero_()
+            ms[:n], ms[cap:cap + n], ms[2 * cap:2 * cap + n] = pi, px, pl
+            ms[3 * cap] = n
+            self.x_stage.copy_(x, non_blocking=True)
+            self.stage_ready.record(self.copy_stream)
+        for t in (x, y, queries):
+            if t is not None:
+                t.record_stream(self.copy_stream)
+        self._staged = True
+        return pl
 
     def drop_staged(self):
         """forget a prefetched batch (the loop decided not to run it through the graph)."""

@@ -53,6 +53,7 @@ class Model:
         self.lr_scheduler_type = args.lr_scheduler_type
         self.query_selector = QuerySelector(args, self.dataloader_query, device=self.device)
         self._use_graph, self._graph, self._graph_shape, self._graph_labels = False, None, None, None
+        self._gpu_aug = None  # --gpu_augment: augment.GpuAugment, built for the first raw batch
         self.running_loss, self.running_score = AverageMeter(), RunningScore(args.n_classes)
 
     def __call__(self):
@@ -83,6 +84,11 @@ class Model:
 
     def train_step(self, model, optimizer, dict_data, reducer=None):
         """model.py:103-129 for one batch; returns (loss tensor, labels, predictions at the labelled pixels)."""
+        if "_ready" in dict_data:  # a batch made on the device by _device_augment, possibly on the copy stream
+            cur = torch.cuda.current_stream()
+            cur.wait_event(dict_data["_ready"])
+            for k in ("x", "y", "queries"):
+                dict_data[k].record_stream(cur)
         x = dict_data["x"].to(self.device, non_blocking=True)
         y = dict_data["y"].to(self.device, non_blocking=True)
         mask = dict_data["queries"].to(self.device, torch.bool) if self.n_pixels_by_us != 0 else None
@@ -101,12 +107,38 @@ class Model:
         optimizer.step()
         return loss.detach(), px_label, pred_at
 
+    def _device_augment(self, dict_data):
+        """--gpu_augment: a batch of RAW samples ({'x_raw' uint8 [B,H,W,3], 'y_raw' uint8 [B,H,W], 'queries_raw' uint8}) ->
+        the batch the reference's dataset would have delivered (base_dataset.py:174-183: joint geometric augmentation,
+        photometric augmentation, to_tensor + normalize), made on the DEVICE (augment.GpuAugment; the draws come from the
+        streams the reference uses, per sample in its order).  Runs on the graph's copy stream when there is one, so it
+        overlaps the step that is replaying.  Other batches pass through unchanged."""
+        if dict_data is None or "x_raw" not in dict_data:
+            return dict_data
+        xr = dict_data["x_raw"]
+        if self._gpu_aug is None:
+            from .augment import GpuAugment
+            aug = getattr(self.args, "augmentations", None) or {}
+            self._gpu_aug = GpuAugment(tuple(xr.shape[1:3]), self.args.mean, self.args.std, self.ignore_index,
+                                       geometric_flags=aug.get("geometric"), photometric_flags=aug.get("photometric"))
+        stream = self._graph.copy_stream if self._graph is not None else torch.cuda.current_stream()
+        with torch.cuda.stream(stream):
+            up = lambda t: None if t is None else t.to(self.device, non_blocking=True).contiguous()
+            x, y, q, _ = self._gpu_aug(up(xr), up(dict_data.get("y_raw")), up(dict_data.get("queries_raw")), None)
+            ready = torch.cuda.Event()
+            ready.record(stream)
+        out = {k: v for k, v in dict_data.items() if not k.endswith("_raw")}
+        out.update(x=x, y=y, queries=q if q is not None else torch.ones_like(y), _ready=ready)
+        return out
+
     def _graphed_step(self, model, optimizer, dict_data, reducer):
         """The same step replayed from ONE captured CUDA graph (graph.py): at the reference batch of 4 the eager step is
         ~900 kernel launches and CPU-bound (4.8x slower).  Captured lazily for the loop's batch shape; other shapes (a
         ragged last batch) take the eager step.  Returns None when this batch cannot use the graph."""
         x, y, q = dict_data["x"], dict_data["y"], dict_data["queries"]
         shape = (x.shape[0], x.shape[2], x.shape[3])
+        if "_ready" in dict_data:  # made by _device_augment on some stream: order the current one (and through it the copy stream) after it
+            torch.cuda.current_stream().wait_event(dict_data["_ready"])
         gs = self._graph
         if gs is None:
             from .graph import GraphedTrainStep
@@ -141,6 +173,8 @@ class Model:
         if gs is None or dict_data is None:
             return
         x = dict_data["x"]
+        if "_ready" in dict_data:
+            torch.cuda.current_stream().wait_event(dict_data["_ready"])
         if (x.shape[0], x.shape[2], x.shape[3]) == self._graph_shape:
             # None = the batch overflows the captured capacity: nothing staged, _graphed_step will send it to the eager step
             self._graph_labels = True if gs.prefetch(x, dict_data["y"], dict_data["queries"]) is not None else None
@@ -155,14 +189,14 @@ class Model:
         if hasattr(sampler, "set_epoch"):  # multi-GPU: per-rank shards, reshuffled every epoch
             sampler.set_epoch(epoch + 1000 * max(self.nth_query, 0))
         it = iter(self.dataloader)
-        dict_data = next(it, None)
+        dict_data = self._device_augment(next(it, None))
         while dict_data is not None:
             graphed = self._graphed_step(model, optimizer, dict_data, reducer) if self._use_graph else None
             if graphed is None:  # eager step: metrics from the labelled pixels, read back per step (model.py:124-136)
                 loss, labels, preds = self.train_step(model, optimizer, dict_data, reducer)
                 self.running_score.update_pairs(labels.cpu().numpy(), preds.cpu().numpy())
                 self.running_loss.update(loss.item())
-            nxt = next(it, None)
+            nxt = self._device_augment(next(it, None))
             if graphed:
                 self._prefetch_next(nxt)  # H2D of the next batch overlaps this batch's graph
             dict_data = nxt

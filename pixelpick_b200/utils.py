@@ -156,6 +156,10 @@ class SyntheticDataset(Dataset):
         self.n_classes, self.ignore_index = args.n_classes, args.ignore_index
         self.dir_checkpoints = f"{args.dir_root}/checkpoints/{args.experim_name}"
         self.seed = seed + (10_000 if val else 0)
+        # --gpu_augment: TRAIN items are the raw sample (uint8 image HWC, label map, query mask as 0 / 255) - what the reference's
+        # __getitem__ holds before base_dataset.py:174-183; the loop augments and normalises the batch on the device
+        self.raw = bool(getattr(args, "gpu_augment", False)) and not val and not query
+        self.mean, self.std = getattr(args, "mean", None), getattr(args, "std", None)
         self.list_labelled_queries = None
         self.list_inputs = None  # optional re-targeting: paths "synthetic/<id>.png" -> the images with those ids, in that order
         rs = np.random.RandomState(self.seed)
@@ -195,6 +199,12 @@ class SyntheticDataset(Dataset):
     def __getitem__(self, i):
         j = self._image_id(i)
         x, y = self._xy(j)
+        if self.raw:
+            mean = torch.tensor(self.mean if self.mean is not None else [0.5] * 3)[:, None, None]
+            std = torch.tensor(self.std if self.std is not None else [0.25] * 3)[:, None, None]
+            x_u8 = ((x * std + mean).clamp(0, 1) * 255).round().to(torch.uint8).permute(1, 2, 0).contiguous()  # de-normalised
+            return {"x_raw": x_u8, "y_raw": y.to(torch.uint8), "queries_raw": torch.from_numpy(self.queries[j].astype(np.uint8) * 255),
+                    "p_img": f"synthetic/{j:06d}.png"}
         d = {"x": x, "y": y, "p_img": f"synthetic/{j:06d}.png"}
         if not self.val:
             d["queries"] = torch.from_numpy(self.queries[j].astype(np.uint8))

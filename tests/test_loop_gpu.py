@@ -243,3 +243,44 @@ def test_train_py_mirror_runs_and_supports_human_labels(tmp_path):
         train_epoch(1, loader, m, opt, sched, meter, "t", human_labels=human, device=torch.device("cuda:0"), debug=True)
         losses.append(meter.avg)
     assert abs(losses[0] - losses[1]) < 2e-2 * abs(losses[0]), losses
+
+
+def test_rounds_with_the_input_pipeline_on_the_device(tmp_path):
+    """--gpu_augment: the train dataset delivers RAW uint8 samples; Model._device_augment makes the batch the reference's
+    dataset would have delivered (base_dataset.py:174-183) on the device and the captured step consumes it (labelled-pixel
+    list built with device ops).  The augmented batch equals the oracle pipeline under the same seeds, bit for bit."""
+    import random
+    from oracle import augment_oracle as orc
+    from pixelpick_b200.augment import draw_geometric, draw_photometric
+    args = Arguments().parse_args(argv=["--dataset_name", "cs", "--dir_root", str(tmp_path), "--n_workers", "0", "--gpu_augment",
+                                        "--max_budget", "20", "--n_epochs", "2", "--synthetic", "8", "64", "128"])
+    torch.backends.cudnn.benchmark = False
+    m = Model(args)
+    raw = next(iter(m.dataloader))
+    assert raw["x_raw"].dtype == torch.uint8 and tuple(raw["x_raw"].shape[1:]) == (64, 128, 3) and "x" not in raw
+    # one batch through the hook vs the oracle, same streams
+    for s in (random.seed, torch.manual_seed, np.random.seed):
+        s(11)
+    got = m._device_augment(dict(raw))
+    torch.cuda.synchronize()
+    for s in (random.seed, torch.manual_seed, np.random.seed):
+        s(11)
+    B = raw["x_raw"].shape[0]
+    draws = [(draw_geometric(64, 128, (64, 128)), draw_photometric()) for _ in range(B)]
+    mean, std = torch.tensor(args.mean)[:, None, None], torch.tensor(args.std)[:, None, None]
+    mean_val = tuple(int(v * 255) for v in args.mean)
+    for b, ((scale, sh, sw, flip), ph) in enumerate(draws):
+        xr, yr, qr = raw["x_raw"][b].numpy(), raw["y_raw"][b].numpy(), raw["queries_raw"][b].numpy()
+        wx, wy, wq, _ = orc.geometric(xr, yr, qr, qr, scale, (64, 128), (sh, sw), flip, mean_val, args.ignore_index)
+        wx = orc.photometric_oracle(wx, ph)
+        want = torch.from_numpy(wx).permute(2, 0, 1).float().div(255).sub(mean).div(std)
+        assert torch.equal(got["x"][b].cpu(), want), b
+        assert np.array_equal(got["y"][b].cpu().numpy(), wy) and np.array_equal(got["queries"][b].cpu().numpy(), wq)
+    # the whole loop on device-augmented batches: graph path, finite losses, picks grow as usual
+    m()
+    assert m._gpu_aug is not None
+    ck = tmp_path / "checkpoints" / args.experim_name
+    rows = open(ck / "1_query" / "log_train.txt").read().strip().splitlines()
+    assert len(rows) == 3 and all(np.isfinite(float(r.split(",")[3])) for r in rows[1:])
+    q = pickle.load(open(ck / "1_query" / "queries.pkl", "rb"))
+    assert len(q) == 8 and all(len(v["x_coords"]) == 10 for v in q.values())
