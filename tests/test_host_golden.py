@@ -28,7 +28,7 @@ ARG_CASES = {
     "cv_fully_sup": ["--dataset_name", "cv", "--n_pixels_by_us", "0", "--debug"],
     "cv_top0_mc": ["--dataset_name", "cv", "--top_n_percent", "0", "--use_mc_dropout", "--vote_type", "hard"],
 }
-OURS_ONLY = {"synthetic", "cuda_graph"}  # switches this framework adds (documented in README.md)
+OURS_ONLY = {"synthetic", "cuda_graph", "gpu_augment"}  # switches this framework adds (documented in README.md)
 
 
 @pytest.mark.parametrize("case", sorted(ARG_CASES))
