@@ -377,7 +377,7 @@ struct SelState {
 };
 
 struct Workspace {
-  uint32_t* hist;        // [kLevels][n_img][2048]
+  uint32_t* hist;        // [n_img][2048] level-0 histogram (the later levels are histogrammed in shared memory)
   SelState* state;       // [kLevels+1][n_img]
   uint32_t* cand_count;  // [n_img]
   uint32_t* filt_count;  // [2][n_img]
@@ -399,7 +399,7 @@ static Workspace carve(void* base, int n_img, int HW, int k) {
   char* p = reinterpret_cast<char*>(base);
   size_t off = 0;
   w.hist = reinterpret_cast<uint32_t*>(p + off);
-  off += align_up((size_t)kLevels * n_img * kHistBins * sizeof(uint32_t), 256);
+  off += align_up((size_t)n_img * kHistBins * sizeof(uint32_t), 256);
   w.state = reinterpret_cast<SelState*>(p + off);
   off += align_up((size_t)(kLevels + 1) * n_img * sizeof(SelState), 256);
   w.cand_count = reinterpret_cast<uint32_t*>(p + off);
@@ -424,8 +424,6 @@ struct SelParams {
   uint32_t* out_count;
   uint64_t* cand;
   uint32_t* cand_count;
-  const uint32_t* hist_cur;
-  uint32_t* hist_next;
   const SelState* state_cur;
   SelState* state_next;
   int level, n_img, HW, k, kpad, largest;
@@ -666,6 +664,176 @@ __global__ void __launch_bounds__(kSelThreads, 6) select_l0_kernel(const SelPara
       }
     }
   }
+}
+
+// Level 0, staged form (the default when the score map is 16-byte aligned and H*W is a multiple of 512).
+// ncu on select_l0_kernel (256 images of 256x512): ~1 warp instruction per score (512 SASS instructions per 512-score
+// warp chunk: a ballot + two popc + two predicated shared stores for EVERY score) at 2.3-2.5 IPC - the kernel is bound by the
+// instructions it issues, 53 us for 134 MB.  Measured on the way here (same box, select phase = pick_bucket0 + this kernel +
+// select_rest, legacy 68.5 us): a persistent kernel that walks the survivors by set bits out of a cp.async ring, per lane, 76.4;
+// the same with the bucket state loaded one chunk ahead and the output deferred by one chunk 73.7; that one without atomics 61.8,
+// without atomics and stores 53.8 - i.e. neither the atomic round trip nor the scattered stores but the 437 instructions per
+// chunk (two divergent per-lane loops of ~3 trips at 0.8 active lanes) and an L2 load of the image's state on every chunk.  Here
+//   * the grid is persistent (3 CTAs per SM); every warp owns ONE contiguous range of chunks, so the bucket state is reloaded
+//     only when the range crosses into the next image, and walks it through a private 4-stage ring in shared memory filled
+//     with cp.async (16 bytes per lane and piece, three chunks = 6 KB per warp in flight);
+//   * a score costs one float compare + one mask update; the lanes' survivors (~5 %) are compacted into a per-warp list of
+//     9-bit chunk offsets behind one warp scan, and then classified on the exact ordering key and written DENSELY, one survivor
+//     per lane and trip, behind one warp-aggregated atomic pair, as in the legacy kernel.
+// Output = the same two unordered sets (candidates below the bucket, boundary list inside it).
+constexpr int kL0sStages = 4;
+constexpr int kL0sWarps = kSelThreads / 32;
+constexpr int kL0sWarpBytes = kL0sStages * kL0WarpChunk * (int)sizeof(float) + kL0WarpChunk * (int)sizeof(uint16_t);  // 9 KB
+constexpr int kL0sSmemBytes = kL0sWarps * kL0sWarpBytes;  // 72 KB
+constexpr int kL0sCtasPerSm = 3;
+
+struct L0sWalk {
+  uint32_t chunks_per_img;  // H*W / 512
+  uint32_t total_chunks;    // n_img * chunks_per_img
+  uint32_t base, extra;     // warp g of the grid owns base + (g < extra) consecutive chunks
+};
+
+__global__ void __launch_bounds__(kSelThreads, kL0sCtasPerSm) select_l0_staged_kernel(const SelParams p, const L0sWalk w) {
+  extern __shared__ __align__(16) unsigned char l0s_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* ring = reinterpret_cast<float*>(l0s_smem + warp * kL0sWarpBytes);
+  uint16_t* list = reinterpret_cast<uint16_t*>(ring + kL0sStages * kL0WarpChunk);  // survivors of the current chunk
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+  const uint32_t gw = blockIdx.x * (uint32_t)kL0sWarps + (uint32_t)warp;
+  const bool largest = p.largest != 0;
+  const uint32_t full = 0xFFFFFFFFu;
+  const uint32_t first = gw * w.base + (gw < w.extra ? gw : w.extra);
+  const uint32_t last = first + w.base + (gw < w.extra ? 1u : 0u);  // exclusive
+  if (first >= last) return;
+
+  // lane's four 16-byte pieces of chunk wc -> ring slot `slot` (the ring holds a linear copy of the chunk)
+  auto issue = [&](uint32_t wc, int slot) {
+    const float* src = p.scores + (size_t)wc * kL0WarpChunk + lane * 4;
+    const uint32_t dst = ring_s + (uint32_t)(slot * kL0WarpChunk + lane * 4) * 4u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)j * 512u), "l"(src + j * 128) : "memory");
+  };
+#pragma unroll
+  for (int s = 0; s < kL0sStages - 1; ++s) {
+    if (first + s < last) issue(first + s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per stage, empty or not: the count below stays uniform
+  }
+  uint32_t img = first / w.chunks_per_img, rem = first - img * w.chunks_per_img;  // chunk `rem` of image `img`
+  // level-0 bucket of the image (pick_bucket0_kernel)
+  bool take_all = false, sel_any = false;
+  uint32_t klo = 0, khi = 0, sel_max = 0;
+  float f_t = 0.f;
+  auto load_state = [&]() {
+    const SelState* sp = p.state_next + img;
+    take_all = sp->done != 0u;
+    klo = sp->klo, khi = sp->khi;
+    sel_any = take_all || klo > 0u;
+    sel_max = take_all ? khi : klo - 1u;
+    f_t = ord_key_inv(khi, largest);
+  };
+  load_state();
+  uint64_t* cand = p.cand + (size_t)img * p.kpad;
+  uint64_t* ol = p.out_list + (size_t)img * p.HW;
+  int slot = 0;
+  for (uint32_t wc = first; wc < last; ++wc) {
+    {  // refill the slot consumed by the previous iteration
+      int ps = slot + kL0sStages - 1;
+      ps = ps >= kL0sStages ? ps - kL0sStages : ps;
+      if (wc + (kL0sStages - 1) < last) issue(wc + (kL0sStages - 1), ps);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.wait_group %0;" ::"n"(kL0sStages - 1) : "memory");  // the oldest group (this chunk) has landed
+    __syncwarp();  // ... for every lane: the survivors below are read across lanes
+    const float* sl = ring + slot * kL0WarpChunk;
+    slot = slot + 1 == kL0sStages ? 0 : slot + 1;
+    const uint32_t px0 = rem * (uint32_t)kL0WarpChunk;  // flat pixel index of the chunk's first score
+    // ---- stage 1: one compare per score against the score that maps to khi (a superset test: NaN and the threshold's
+    // ties pass); item i = 4 j + e of a lane is the chunk's score (j * 32 + lane) * 4 + e ----
+    uint32_t mask = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(sl + (j * 32 + lane) * 4);
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool ps = largest ? !(e[q] < f_t) : !(e[q] > f_t);
+        mask |= ps ? (1u << (4 * j + q)) : 0u;
+      }
+    }
+    // ---- compaction: the lanes' survivors -> list[0 .. n_pass) of chunk offsets (lane-major) ----
+    const uint32_t mine = (uint32_t)__popc(mask);
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(full, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const uint32_t n_pass = __shfl_sync(full, inc, 31);
+    if (n_pass != 0u) {  // warp-uniform
+      uint32_t off = inc - mine;
+      for (uint32_t m = mask; m; m &= m - 1u) {
+        const int i = __ffs((int)m) - 1;
+        list[off++] = (uint16_t)(((i >> 2) * 32 + lane) * 4 + (i & 3));
+      }
+      __syncwarp();
+      // ---- stage 2: one survivor per lane and trip, exact classification on the ordering key against the bucket's key range:
+      // selected <=> below the bucket (or inside it when the whole bucket is taken), boundary <=> inside it ----
+      uint32_t nc = 0, nf = 0;
+      for (uint32_t e = (uint32_t)lane; e < n_pass; e += 32u) {
+        const uint32_t li = list[e];
+        const uint32_t k = ord_key(sl[li], largest);
+        const bool s1 = sel_any && k <= sel_max;
+        const bool s2 = !take_all && k >= klo && k <= khi;
+        list[e] = (uint16_t)(li | ((uint32_t)s1 << 14) | ((uint32_t)s2 << 15));  // read back by this lane only
+        nc += s1;
+        nf += s2;
+      }
+      const uint32_t packed = nc | (nf << 16);  // a warp holds 512 scores: each count fits 10 bits
+      uint32_t pin = packed;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(full, pin, o);
+        if (lane >= o) pin += t;
+      }
+      const uint32_t tot = __shfl_sync(full, pin, 31);
+      if (tot != 0u) {  // warp-uniform
+        uint32_t base_c = 0, base_f = 0;
+        if (lane == 0) {
+          const uint32_t tc = tot & 0xFFFFu, tf = tot >> 16;
+          if (tc) base_c = atomicAdd(p.cand_count + img, tc);
+          if (tf) base_f = atomicAdd(p.out_count + img, tf);
+        }
+        base_c = __shfl_sync(full, base_c, 0);
+        base_f = __shfl_sync(full, base_f, 0);
+        const uint32_t excl = pin - packed;
+        uint32_t oc = base_c + (excl & 0xFFFFu);
+        uint32_t of = base_f + (excl >> 16);
+        for (uint32_t e = (uint32_t)lane; e < n_pass; e += 32u) {
+          const uint32_t ent = list[e];
+          if (ent >> 14) {
+            const uint32_t li = ent & 0x1FFu;
+            const uint64_t comp = ((uint64_t)ord_key(sl[li], largest) << 32) | (uint64_t)(px0 + li);
+            if (ent & 0x4000u) {
+              if (oc < (uint32_t)p.kpad) cand[oc] = comp;
+              ++oc;
+            } else {
+              ol[of++] = comp;
+            }
+          }
+        }
+      }
+      __syncwarp();  // the list is rewritten by the next chunk
+    }
+    if (++rem == w.chunks_per_img && wc + 1 < last) {  // warp-uniform: the range crosses into the next image
+      rem = 0;
+      ++img;
+      load_state();
+      cand = p.cand + (size_t)img * p.kpad;
+      ol = p.out_list + (size_t)img * p.HW;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");  // nothing of this CTA is in flight when its shared memory is released
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1024,276 +1192,82 @@ __global__ void __launch_bounds__(kRestThreads) select_rest_kernel(const RestPar
 
 // Order statistics instead of a sort: the reference draws n random RANKS of the sorted top-k list
 // (np.random.choice(ind_queries, n, False), query.py:63-64), so only the elements at those ranks are needed.
-// One CTA per image runs the same 5-level radix walk for up to kPickRanks ranks at once over the k unsorted
-// composites: rank j keeps (prefix_j, rem_j); every level histograms the elements matching prefix_j by their next
-// digit, then narrows.  Composites are unique, so after the last level prefix_j IS the element of rank j.  O(5 k).
+// One CTA per image runs a radix walk for up to kPickRanks ranks at once over the k unsorted composites: rank j keeps
+// (prefix_j, rem_j); every level histograms the elements matching prefix_j by their next digit, then narrows.
+// Composites are unique, so after the last level prefix_j IS the element of rank j.
 constexpr int kPickThreads = 512;
-constexpr int kPickRanks = 12;  // 12 x 2048 x 4 B = 96 KB of histograms
+constexpr int kPickRanks = 12;   // 12 x 2048 x 4 B = 96 KB of histograms
+constexpr int kPickItems = 16;   // candidates cached in registers when k <= 512 * 16
+constexpr int kPickUnroll = 8;   // candidates in flight per thread when they are streamed from L2 instead (larger k)
 
 struct PickParams {
   const uint64_t* cand;  // [n_img][kpad]
   int kpad, k, n;
   const int32_t* pos;    // [n_img][n] ranks (nullptr: 0..n-1)
   int32_t* out;          // [n_img][n]
-  uint32_t* fallback;    // [n_img]: written by the fast kernel (1 = this image needs the generic kernel), read by the generic one
 };
 
-constexpr int kPickItems = 16;  // candidates cached in registers when k <= 512 * 16
-
-// Fast path of the order-statistics pick (n <= kPickRanks ranks, the common case n = 10): THREE cheap passes over the
-// k candidates instead of five 12-way compare passes.
-//   pass 1  histogram of the leading 11-bit digit (shared by all ranks)            -> per rank: bucket b0, rank inside it
-//   pass 2  ranks that share b0 form a group; map0[digit0] -> group (one byte table lookup); candidates of a group are
-//           histogrammed by their second digit                                     -> per rank: bucket b1, count, rank
-//   pass 3  candidates whose 22-bit prefix equals a rank's are appended to that rank's list (<= 32 entries), one warp
-//           ranks each list directly
-// A candidate costs a load, two shifts and one table lookup per pass (the generic kernel compares every live candidate
-// with every rank's 64-bit prefix at every level: ~3000 instructions per thread at k = 6553, and at k = 104857 — 5 % of a
-// 1024x2048 image — its single CTA per image took ~0.35 ms).  If a 22-bit group holds more than 32 candidates (heavy
-// ties) or n > kPickRanks, the image is flagged and the generic kernel below finishes it.
-__global__ void __launch_bounds__(kPickThreads, 2) pick_ranks_fast_kernel(const PickParams p) {
-  extern __shared__ uint32_t sh_h[];  // [kPickRanks][2048]: hist0 = sh_h[0..2048), hist1[g] = sh_h[g * 2048 ...)
-  __shared__ uint8_t map0[kHistBins];
-  __shared__ uint32_t sh_b0[kPickRanks], sh_b1[kPickRanks], sh_rem[kPickRanks], sh_cnt[kPickRanks], sh_grp[kPickRanks];
-  __shared__ uint32_t sh_n[kPickRanks];
-  __shared__ uint64_t sh_res[kPickRanks];
-  __shared__ uint32_t sh_ng, sh_ok;
-  const int img = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t* c = p.cand + (size_t)img * p.kpad;
-  const int nr = p.n;
-  if (nr > kPickRanks) {  // more ranks than one pass handles: generic kernel
-    if (tid == 0) p.fallback[img] = 1u;
-    return;
-  }
-  const bool cached = p.k <= kPickThreads * kPickItems;
-  uint64_t reg[kPickItems];
-  if (cached) {
+// The k candidates of one image through f(v, valid), streamed: kPickUnroll independent 8-byte loads per thread are issued
+// before the first is used (5 % of a 1024x2048 image is 205 candidates per thread and pass: one load per trip left every
+// pass a chain of 205 L2 round trips).  Every thread calls f the same number of times (warp collectives inside f are legal).
+template <typename F>
+__device__ __forceinline__ void pick_stream(const uint64_t* __restrict__ c, int k, int tid, F&& f) {
+  const unsigned long long* cc = reinterpret_cast<const unsigned long long*>(c);
+  int i0 = 0;
+  for (; i0 + kPickUnroll * kPickThreads <= k; i0 += kPickUnroll * kPickThreads) {
+    uint64_t v[kPickUnroll];
 #pragma unroll
-    for (int i = 0; i < kPickItems; ++i) {
-      const int idx = i * kPickThreads + tid;
-      reg[i] = (idx < p.k) ? c[idx < p.k ? idx : 0] : ~0ull;
-    }
-  }
-  const int s0 = c_shift[0], s1 = c_shift[1];
-  const uint32_t m0 = (1u << c_bits[0]) - 1u, m1 = (1u << c_bits[1]) - 1u;
-  for (int i = tid; i < kHistBins; i += kPickThreads) sh_h[i] = 0;
-  if (tid < nr) {
-    int r = p.pos ? p.pos[(size_t)img * p.n + tid] : tid;
-    r = r < 0 ? 0 : (r >= p.k ? p.k - 1 : r);
-    sh_rem[tid] = (uint32_t)r + 1u;
-  }
-  __syncthreads();
-  // ---- pass 1: leading digit (few distinct values: aggregate equal digits inside the warp) ----
-  auto hist0_add = [&](uint64_t v, bool valid) {
-    const uint32_t d = valid ? ((uint32_t)(v >> s0) & m0) : 0xFFFFFFFFu;
-    const uint32_t m = __match_any_sync(0xFFFFFFFFu, d);
-    if (valid && lane == __ffs(m) - 1) atomicAdd(&sh_h[d], (uint32_t)__popc(m));
-  };
-  if (cached) {
+    for (int u = 0; u < kPickUnroll; ++u) v[u] = __ldg(cc + i0 + u * kPickThreads + tid);
 #pragma unroll
-    for (int i = 0; i < kPickItems; ++i) hist0_add(reg[i], i * kPickThreads + tid < p.k);
+    for (int u = 0; u < kPickUnroll; ++u) f(v[u], true);
+  }
+  for (; i0 < k; i0 += kPickThreads) {
+    const int i = i0 + tid;
+    const bool ok = i < k;
+    f(ok ? (uint64_t)__ldg(cc + i) : 0ull, ok);
+  }
+}
+template <bool CACHED, typename F>
+__device__ __forceinline__ void pick_for_each(const uint64_t (&reg)[kPickItems], const uint64_t* __restrict__ c, int k,
+                                              int tid, F&& f) {
+  if (CACHED) {
+#pragma unroll
+    for (int i = 0; i < kPickItems; ++i) f(reg[i], i * kPickThreads + tid < k);
   } else {
-    for (int i0 = 0; i0 < p.k; i0 += kPickThreads) {
-      const int i = i0 + tid;
-      hist0_add(i < p.k ? c[i] : 0ull, i < p.k);
-    }
+    pick_stream(c, k, tid, f);
   }
-  __syncthreads();
-  // narrowing: warp j finds the bin of `h` that holds the element of 1-based rank sh_rem[j]
-  auto narrow = [&](const uint32_t* h, int j, uint32_t* bucket_out) {
-    const uint32_t rem = sh_rem[j];
-    uint32_t mine = 0;
-    for (int b = 0; b < 64; ++b) mine += h[lane * 64 + ((b + lane) & 63)];
-    uint32_t incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    uint32_t run = incl - mine;
-    const bool here = run < rem && rem <= incl;
-    int found = -1;
-    uint32_t before = 0, in_bin = 0;
-    if (here) {
-      for (int b = 0; b < 64; ++b) {
-        const uint32_t hb = h[lane * 64 + b];
-        if (run < rem && rem <= run + hb) { found = lane * 64 + b; before = run; in_bin = hb; break; }
-        run += hb;
-      }
-    }
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, found >= 0);
-    const int src = __ffs(m) - 1;
-    found = __shfl_sync(0xFFFFFFFFu, found, src);
-    before = __shfl_sync(0xFFFFFFFFu, before, src);
-    in_bin = __shfl_sync(0xFFFFFFFFu, in_bin, src);
-    if (lane == 0) {
-      bucket_out[j] = (uint32_t)found;
-      sh_rem[j] = rem - before;
-      sh_cnt[j] = in_bin;
-    }
-  };
-  for (int j = warp; j < nr; j += kPickThreads / 32) narrow(sh_h, j, sh_b0);
-  for (int i = tid; i < kHistBins; i += kPickThreads) map0[i] = 255;
-  __syncthreads();
-  // ---- groups of ranks sharing the leading bucket ----
-  if (tid == 0) {
-    uint32_t ng = 0;
-    for (int j = 0; j < nr; ++j) {
-      const uint32_t b = sh_b0[j];
-      if (map0[b] == 255) map0[b] = (uint8_t)ng++;
-      sh_grp[j] = map0[b];
-    }
-    sh_ng = ng;
-  }
-  __syncthreads();
-  const uint32_t ng = sh_ng;
-  for (int i = tid; i < (int)ng * kHistBins; i += kPickThreads) sh_h[i] = 0;  // hist0 is dead: reuse as hist1[g]
-  if (tid < kPickRanks) sh_n[tid] = 0;
-  __syncthreads();
-  // ---- pass 2: second digit of the candidates that fall in a rank's leading bucket ----
-  auto hist1_add = [&](uint64_t v) {
-    const uint32_t g = map0[(uint32_t)(v >> s0) & m0];
-    if (g != 255u) atomicAdd(&sh_h[g * kHistBins + ((uint32_t)(v >> s1) & m1)], 1u);
-  };
-  if (cached) {
-#pragma unroll
-    for (int i = 0; i < kPickItems; ++i)
-      if (i * kPickThreads + tid < p.k) hist1_add(reg[i]);
-  } else {
-    for (int i = tid; i < p.k; i += kPickThreads) hist1_add(c[i]);
-  }
-  __syncthreads();
-  for (int j = warp; j < nr; j += kPickThreads / 32) narrow(sh_h + sh_grp[j] * kHistBins, j, sh_b1);
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t mx = 0;
-    for (int j = 0; j < nr; ++j) mx = sh_cnt[j] > mx ? sh_cnt[j] : mx;
-    sh_ok = (mx <= 32u) ? 1u : 0u;
-  }
-  __syncthreads();
-  int gshift = s1;  // candidates are compared with a rank's prefix above this bit
-  if (!sh_ok) {
-    // ---- optional pass 2b: a 22-bit group is still larger than a warp (scores packed into a narrow range, e.g. the
-    // top 5 % of entropies of a 1024x2048 image): split it by the remaining 10 key bits -> the whole float is resolved
-    const int s2 = c_shift[2];
-    const uint32_t m2 = (1u << c_bits[2]) - 1u;
-    __shared__ uint32_t gp2[kPickRanks], sh_b2[kPickRanks], sh_ng2;
-    if (tid == 0) {
-      uint32_t n2 = 0;
-      for (int j = 0; j < nr; ++j) {
-        const uint32_t pj = (sh_b0[j] << c_bits[1]) | sh_b1[j];
-        uint32_t g = 0;
-        while (g < n2 && gp2[g] != pj) ++g;
-        if (g == n2) gp2[n2++] = pj;
-        sh_grp[j] = g;
-      }
-      sh_ng2 = n2;
-    }
-    __syncthreads();
-    const uint32_t ng2 = sh_ng2;
-    for (int i = tid; i < (int)ng2 * kHistBins; i += kPickThreads) sh_h[i] = 0;
-    __syncthreads();
-    uint32_t gpr[kPickRanks];
-#pragma unroll
-    for (int j = 0; j < kPickRanks; ++j) gpr[j] = (j < (int)ng2) ? gp2[j] : 0xFFFFFFFFu;
-    auto hist2_add = [&](uint64_t v) {
-      if (map0[(uint32_t)(v >> s0) & m0] == 255u) return;
-      const uint32_t key = (uint32_t)(v >> s1);
-#pragma unroll
-      for (int g = 0; g < kPickRanks; ++g)
-        if (key == gpr[g]) atomicAdd(&sh_h[g * kHistBins + ((uint32_t)(v >> s2) & m2)], 1u);
-    };
-    if (cached) {
-#pragma unroll
-      for (int i = 0; i < kPickItems; ++i)
-        if (i * kPickThreads + tid < p.k) hist2_add(reg[i]);
-    } else {
-      for (int i = tid; i < p.k; i += kPickThreads) hist2_add(c[i]);
-    }
-    __syncthreads();
-    for (int j = warp; j < nr; j += kPickThreads / 32) narrow(sh_h + sh_grp[j] * kHistBins, j, sh_b2);
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t mx = 0;
-      for (int j = 0; j < nr; ++j) {
-        mx = sh_cnt[j] > mx ? sh_cnt[j] : mx;
-        sh_b1[j] = (sh_b1[j] << c_bits[2]) | sh_b2[j];  // b1 now carries 21 bits: prefix = b0 : b1 : b2 = the 32 key bits
-      }
-      sh_ok = (mx <= 32u) ? 1u : 0u;
-    }
-    __syncthreads();
-    gshift = s2;
-  }
-  if (tid == 0) p.fallback[img] = sh_ok ? 0u : 1u;
-  if (!sh_ok) return;  // exact ties beyond a warp: the generic kernel finishes this image
-  // ---- pass 3: gather each rank's group and rank it directly ----
-  uint64_t* lists = reinterpret_cast<uint64_t*>(sh_h);  // [kPickRanks][32]; the histograms are dead
-  __syncthreads();
-  const int b1_bits = (gshift == s1) ? c_bits[1] : c_bits[1] + c_bits[2];
-  uint32_t pre[kPickRanks];  // every rank's key prefix above gshift
-#pragma unroll
-  for (int j = 0; j < kPickRanks; ++j) pre[j] = (j < nr) ? ((sh_b0[j] << b1_bits) | sh_b1[j]) : 0xFFFFFFFFu;
-  auto gather = [&](uint64_t v) {
-    if (map0[(uint32_t)(v >> s0) & m0] == 255u) return;
-    const uint32_t key = (uint32_t)(v >> gshift);  // the top 22 (or all 32) key bits
-#pragma unroll
-    for (int j = 0; j < kPickRanks; ++j)
-      if (key == pre[j]) lists[j * 32 + atomicAdd(&sh_n[j], 1u)] = v;
-  };
-  if (cached) {
-#pragma unroll
-    for (int i = 0; i < kPickItems; ++i)
-      if (i * kPickThreads + tid < p.k) gather(reg[i]);
-  } else {
-    for (int i = tid; i < p.k; i += kPickThreads) gather(c[i]);
-  }
-  __syncthreads();
-  for (int j = warp; j < nr; j += kPickThreads / 32) {
-    const uint32_t cnt = sh_n[j];
-    const uint64_t x = (uint32_t)lane < cnt ? lists[j * 32 + lane] : ~0ull;
-    uint32_t below = 0;
-    for (int o = 0; o < 32; ++o) {
-      const uint64_t y = __shfl_sync(0xFFFFFFFFu, x, o);
-      below += (y < x) ? 1u : 0u;
-    }
-    if ((uint32_t)lane < cnt && below + 1u == sh_rem[j]) sh_res[j] = x;  // composites are unique
-  }
-  __syncthreads();
-  if (tid < nr) p.out[(size_t)img * p.n + tid] = (int32_t)(uint32_t)(sh_res[tid] & 0xFFFFFFFFull);
 }
 
-__global__ void __launch_bounds__(kPickThreads, 2) pick_ranks_kernel(const PickParams p) {
-  extern __shared__ uint32_t sh_h[];  // [kPickRanks][2048]
+// Generic walk (any number of ranks, any number of exact ties): all five radix levels, every live candidate compared with
+// every rank's prefix at every level.  Runs for the images the fast kernel below cannot finish.  `pos` / `out` are the image's.
+template <bool CACHED>
+__device__ __noinline__ void pick_ranks_generic(const uint64_t* __restrict__ c, int k, int n, const int32_t* __restrict__ pos,
+                                                int32_t* __restrict__ out, uint32_t* sh_h) {
   __shared__ uint64_t sh_prefix[kPickRanks];
   __shared__ uint32_t sh_rem[kPickRanks];
   __shared__ uint32_t sh_cnt[kPickRanks];  // elements still matching rank j's prefix after the current level
   __shared__ uint32_t sh_n[kPickRanks];
   __shared__ uint32_t sh_small;
-  const int img = blockIdx.x;
-  if (p.fallback && p.fallback[img] == 0u) return;  // finished by pick_ranks_fast_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t* c = p.cand + (size_t)img * p.kpad;
   // the k candidates are read ONCE into registers (all loads in flight together) and reused by every level;
   // larger k (e.g. 5 % of a 1024x2048 image) streams them from L2 at each level instead
-  const bool cached = p.k <= kPickThreads * kPickItems;
   uint64_t reg[kPickItems];
-  if (cached) {
+  if (CACHED) {
 #pragma unroll
     for (int i = 0; i < kPickItems; ++i) {
       const int idx = i * kPickThreads + tid;
-      reg[i] = (idx < p.k) ? c[idx < p.k ? idx : 0] : ~0ull;  // ~0 never matches a prefix below level 0's bucket
+      reg[i] = (idx < k) ? c[idx < k ? idx : 0] : ~0ull;  // ~0 never matches a prefix below level 0's bucket
     }
   }
-  for (int j0 = 0; j0 < p.n; j0 += kPickRanks) {
-    const int nr = (p.n - j0) < kPickRanks ? (p.n - j0) : kPickRanks;
+  for (int j0 = 0; j0 < n; j0 += kPickRanks) {
+    const int nr = (n - j0) < kPickRanks ? (n - j0) : kPickRanks;
     uint32_t alive = 0;
 #pragma unroll
-    for (int i = 0; i < kPickItems; ++i) alive |= (i * kPickThreads + tid < p.k) ? (1u << i) : 0u;
+    for (int i = 0; i < kPickItems; ++i) alive |= (i * kPickThreads + tid < k) ? (1u << i) : 0u;
     if (tid < nr) {
       sh_prefix[tid] = 0;
-      int r = p.pos ? p.pos[(size_t)img * p.n + j0 + tid] : (j0 + tid);
-      r = r < 0 ? 0 : (r >= p.k ? p.k - 1 : r);
+      int r = pos ? pos[j0 + tid] : (j0 + tid);
+      r = r < 0 ? 0 : (r >= k ? k - 1 : r);
       sh_rem[tid] = (uint32_t)r + 1u;  // 1-based rank inside the current bucket
     }
     for (int level = 0; level < kLevels; ++level) {
@@ -1320,17 +1294,17 @@ __global__ void __launch_bounds__(kPickThreads, 2) pick_ranks_kernel(const PickP
           }
         return any;
       };
-      if (cached && level == 0) {
+      if (CACHED && level == 0) {
         // the selected candidates sit in a narrow score range, so their leading digit takes only a few values:
         // aggregate equal digits inside the warp (match.any) and issue ONE shared-memory atomic per distinct digit
 #pragma unroll
         for (int i = 0; i < kPickItems; ++i) {
-          const bool valid = i * kPickThreads + tid < p.k;
+          const bool valid = i * kPickThreads + tid < k;
           const uint32_t d = valid ? ((uint32_t)(reg[i] >> shift) & dmask) : 0xFFFFFFFFu;
           const uint32_t m = __match_any_sync(0xFFFFFFFFu, d);
           if (valid && lane == __ffs(m) - 1) atomicAdd(&sh_h[d], (uint32_t)__popc(m));
         }
-      } else if (cached) {
+      } else if (CACHED) {
         // an element that matches no rank's prefix at this level can never match again: drop it from later levels
         uint32_t still = 0;
 #pragma unroll
@@ -1338,9 +1312,13 @@ __global__ void __launch_bounds__(kPickThreads, 2) pick_ranks_kernel(const PickP
           if ((alive >> i) & 1u) still |= visit(reg[i]) ? (1u << i) : 0u;
         alive = still;
       } else if (level == 0) {
-        for (int i = tid; i < p.k; i += kPickThreads) atomicAdd(&sh_h[(uint32_t)(c[i] >> shift) & dmask], 1u);
+        pick_stream(c, k, tid, [&](uint64_t v, bool valid) {
+          if (valid) atomicAdd(&sh_h[(uint32_t)(v >> shift) & dmask], 1u);
+        });
       } else {
-        for (int i = tid; i < p.k; i += kPickThreads) visit(c[i]);
+        pick_stream(c, k, tid, [&](uint64_t v, bool valid) {
+          if (valid) visit(v);
+        });
       }
       __syncthreads();
       // warp j narrows rank j: lane l owns bins [64 l, 64 l + 64); reads are rotated by the lane id so the 32 lanes
@@ -1382,7 +1360,7 @@ __global__ void __launch_bounds__(kPickThreads, 2) pick_ranks_kernel(const PickP
       // After two levels (22 key bits) a rank's group is normally a handful of elements: finish by ranking each group
       // directly in one warp instead of walking three more radix levels (each: clear 96 KB of histograms, a pass over
       // the candidates, a 2048-bin scan per rank).  Falls through to the remaining levels if any group exceeds a warp.
-      if (cached && level == 1) {
+      if (CACHED && level == 1) {
         if (tid == 0) {
           uint32_t mx = 0;
           for (int j = 0; j < nr; ++j) mx = sh_cnt[j] > mx ? sh_cnt[j] : mx;
@@ -1419,9 +1397,281 @@ __global__ void __launch_bounds__(kPickThreads, 2) pick_ranks_kernel(const PickP
         }
       }
     }
-    if (tid < nr) p.out[(size_t)img * p.n + j0 + tid] = (int32_t)(uint32_t)(sh_prefix[tid] & 0xFFFFFFFFull);
+    if (tid < nr) out[j0 + tid] = (int32_t)(uint32_t)(sh_prefix[tid] & 0xFFFFFFFFull);
     __syncthreads();
   }
+}
+
+// Fast path of the order-statistics pick (n <= kPickRanks ranks, the common case n = 10): THREE cheap passes over the
+// k candidates instead of five 12-way compare passes.
+//   pass 1  histogram of the leading 11-bit digit (shared by all ranks)            -> per rank: bucket b0, rank inside it
+//   pass 2  ranks that share b0 form a group; map0[digit0] -> group (one byte table lookup); candidates of a group are
+//           histogrammed by their second digit                                     -> per rank: bucket b1, count, rank
+//   pass 3  candidates whose 22-bit prefix equals a rank's are appended to that rank's list (<= 32 entries), one warp
+//           ranks each list directly
+// A candidate costs a load, two shifts and one table lookup per pass (the generic walk compares every live candidate
+// with every rank's 64-bit prefix at every level: ~3000 instructions per thread at k = 6553).  If a 22-bit group holds more
+// than 32 candidates the remaining 10 key bits are split off as well (pass 2b); exact ties beyond a warp, or n > kPickRanks,
+// are finished by the generic walk inside the same launch.
+// Narrowing a rank in a 2048-bin histogram is two 32-wide steps: the sums of the 32 groups of 64 bins are made by ALL
+// threads (one 16-byte read + one half-warp redux each), then the rank's warp scans the 32 sums and the 64 bins of the one
+// group that holds it (two bins per lane) - instead of every lane walking 64 bins twice (ncu: the kernel is a latency
+// chain at 0.97 IPC, and those walks were ~1300 of the ~2700 instructions on it).
+template <bool CACHED>
+__global__ void __launch_bounds__(kPickThreads, CACHED ? 2 : 1) pick_ranks_fast_kernel(const PickParams p) {
+  extern __shared__ __align__(16) uint32_t sh_h[];  // [kPickRanks][2048]: hist0 = sh_h[0..2048), hist1[g] = sh_h[g * 2048 ...)
+  __shared__ uint8_t map0[kHistBins];
+  __shared__ uint32_t sh_coarse[kPickRanks][32];
+  __shared__ uint32_t sh_b0[kPickRanks], sh_b1[kPickRanks], sh_rem[kPickRanks], sh_cnt[kPickRanks], sh_grp[kPickRanks];
+  __shared__ uint32_t sh_n[kPickRanks];
+  __shared__ uint64_t sh_res[kPickRanks];
+  __shared__ uint32_t sh_ng, sh_ok;
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t* c = p.cand + (size_t)img * p.kpad;
+  const int32_t* pos = p.pos ? p.pos + (size_t)img * p.n : nullptr;
+  int32_t* out = p.out + (size_t)img * p.n;
+  const int nr = p.n;
+  const uint32_t full = 0xFFFFFFFFu;
+  if (nr > kPickRanks) {  // more ranks than one pass handles
+    pick_ranks_generic<CACHED>(c, p.k, p.n, pos, out, sh_h);
+    return;
+  }
+  uint64_t reg[kPickItems];
+  if (CACHED) {
+#pragma unroll
+    for (int i = 0; i < kPickItems; ++i) {
+      const int idx = i * kPickThreads + tid;
+      reg[i] = (idx < p.k) ? c[idx < p.k ? idx : 0] : ~0ull;
+    }
+  }
+  const int s0 = c_shift[0], s1 = c_shift[1];
+  const uint32_t m0 = (1u << c_bits[0]) - 1u, m1 = (1u << c_bits[1]) - 1u;
+  for (int i = tid; i < kHistBins; i += kPickThreads) sh_h[i] = 0;
+  if (tid < nr) {
+    int r = pos ? pos[tid] : tid;
+    r = r < 0 ? 0 : (r >= p.k ? p.k - 1 : r);
+    sh_rem[tid] = (uint32_t)r + 1u;
+  }
+  __syncthreads();
+  // sums of the 32 groups of 64 bins of the first nh histograms (all threads; the caller synchronises)
+  auto coarse_sums = [&](int nh) {
+    const uint32_t half = (lane & 16) ? 0xFFFF0000u : 0x0000FFFFu;
+    for (int g = 0; g < nh; ++g) {
+      const uint4 h4 = *reinterpret_cast<const uint4*>(sh_h + g * kHistBins + tid * 4);
+      const uint32_t s = __reduce_add_sync(half, h4.x + h4.y + h4.z + h4.w);
+      if ((lane & 15) == 0) sh_coarse[g][tid >> 4] = s;
+    }
+  };
+  // narrowing: warp j finds the bin of `h` (group sums `cs`) that holds the element of 1-based rank sh_rem[j]
+  auto narrow = [&](const uint32_t* h, const uint32_t* cs, int j, uint32_t* bucket_out) {
+    uint32_t rem = sh_rem[j];
+    uint32_t mine = cs[lane];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(full, incl, o);
+      if (lane >= o) incl += t;
+    }
+    uint32_t run = incl - mine;
+    const int grp = __ffs((int)__ballot_sync(full, run < rem && rem <= incl)) - 1;  // exactly one lane (1 <= rem <= total)
+    rem -= __shfl_sync(full, run, grp);
+    const uint2 hb = *reinterpret_cast<const uint2*>(h + grp * 64 + lane * 2);
+    mine = hb.x + hb.y;
+    incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(full, incl, o);
+      if (lane >= o) incl += t;
+    }
+    run = incl - mine;
+    const int src = __ffs((int)__ballot_sync(full, run < rem && rem <= incl)) - 1;
+    const bool second = rem > run + hb.x;  // meaningful on lane src
+    const uint32_t found = __shfl_sync(full, (uint32_t)(grp * 64 + lane * 2) + (second ? 1u : 0u), src);
+    const uint32_t before = __shfl_sync(full, run + (second ? hb.x : 0u), src);
+    const uint32_t in_bin = __shfl_sync(full, second ? hb.y : hb.x, src);
+    if (lane == 0) {
+      bucket_out[j] = found;
+      sh_rem[j] = rem - before;
+      sh_cnt[j] = in_bin;
+    }
+  };
+  // ---- pass 1: leading digit (few distinct values: aggregate equal digits inside the warp) ----
+  pick_for_each<CACHED>(reg, c, p.k, tid, [&](uint64_t v, bool valid) {
+    const uint32_t d = valid ? ((uint32_t)(v >> s0) & m0) : 0xFFFFFFFFu;
+    const uint32_t m = __match_any_sync(full, d);
+    if (valid && lane == __ffs((int)m) - 1) atomicAdd(&sh_h[d], (uint32_t)__popc(m));
+  });
+  __syncthreads();
+  coarse_sums(1);
+  for (int i = tid; i < kHistBins; i += kPickThreads) map0[i] = 255;
+  __syncthreads();
+  for (int j = warp; j < nr; j += kPickThreads / 32) narrow(sh_h, sh_coarse[0], j, sh_b0);
+  __syncthreads();
+  // ---- groups of ranks sharing the leading bucket ----
+  if (tid == 0) {
+    uint32_t ng = 0;
+    for (int j = 0; j < nr; ++j) {
+      const uint32_t b = sh_b0[j];
+      if (map0[b] == 255) map0[b] = (uint8_t)ng++;
+      sh_grp[j] = map0[b];
+    }
+    sh_ng = ng;
+  }
+  __syncthreads();
+  const uint32_t ng = sh_ng;
+  for (int i = tid; i < (int)ng * (kHistBins / 4); i += kPickThreads)  // hist0 is dead: reuse as hist1[g]
+    reinterpret_cast<uint4*>(sh_h)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < kPickRanks) sh_n[tid] = 0;
+  __syncthreads();
+  // ---- pass 2: second digit of the candidates that fall in a rank's leading bucket ----
+  pick_for_each<CACHED>(reg, c, p.k, tid, [&](uint64_t v, bool valid) {
+    if (!valid) return;
+    const uint32_t g = map0[(uint32_t)(v >> s0) & m0];
+    if (g != 255u) atomicAdd(&sh_h[g * kHistBins + ((uint32_t)(v >> s1) & m1)], 1u);
+  });
+  __syncthreads();
+  coarse_sums((int)ng);
+  __syncthreads();
+  for (int j = warp; j < nr; j += kPickThreads / 32) narrow(sh_h + sh_grp[j] * kHistBins, sh_coarse[sh_grp[j]], j, sh_b1);
+  __syncthreads();
+  // ---- unique 22-bit prefixes of the ranks (g2), and are all their groups at most a warp? ----
+  __shared__ uint32_t gp2[kPickRanks], sh_g2[kPickRanks], sh_b2[kPickRanks], sh_lid[kPickRanks], sh_pre[kPickRanks], sh_ng2;
+  if (tid == 0) {
+    uint32_t mx = 0, n2 = 0;
+    for (int j = 0; j < nr; ++j) {
+      mx = sh_cnt[j] > mx ? sh_cnt[j] : mx;
+      const uint32_t pj = (sh_b0[j] << c_bits[1]) | sh_b1[j];
+      uint32_t g = 0;
+      while (g < n2 && gp2[g] != pj) ++g;
+      if (g == n2) gp2[n2++] = pj;
+      sh_g2[j] = g;
+    }
+    sh_ng2 = n2;
+    sh_ok = (mx <= 32u) ? 1u : 0u;
+  }
+  __syncthreads();
+  const uint32_t ng2 = sh_ng2;
+  // map1[group][second digit] -> g2 (byte table at the END of the histogram area; hist1 is dead).  With it a candidate's
+  // prefix is resolved by two table lookups in the passes below.  (ncu had this kernel waiting for instruction fetch on 45 %
+  // of its issue cycles - every CTA runs its code once - while it compared each candidate with the 12 ranks' prefixes in
+  // 16 x 12 unrolled blocks: 38 -> 24 us for 256 images with the tables.)
+  constexpr int kHistBytes = kPickRanks * kHistBins * (int)sizeof(uint32_t);
+  uint8_t* map1 = reinterpret_cast<uint8_t*>(sh_h) + kHistBytes - (int)ng * kHistBins;
+  for (int i = tid; i < (int)ng * (kHistBins / 16); i += kPickThreads)
+    reinterpret_cast<uint4*>(map1)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  __syncthreads();
+  if (tid < nr) map1[sh_grp[tid] * kHistBins + sh_b1[tid]] = (uint8_t)sh_g2[tid];  // equal prefixes write equal values
+  __syncthreads();
+  uint64_t* lists = reinterpret_cast<uint64_t*>(sh_h);  // [<= kPickRanks][32] (3 KB), filled in pass 3
+  if (sh_ok) {
+    // ---- pass 3: gather the candidates of each unique prefix (<= 32) ----
+    if (tid < nr) sh_lid[tid] = sh_g2[tid];
+    pick_for_each<CACHED>(reg, c, p.k, tid, [&](uint64_t v, bool valid) {
+      if (!valid) return;
+      const uint32_t g = map0[(uint32_t)(v >> s0) & m0];
+      if (g == 255u) return;
+      const uint32_t id = map1[g * kHistBins + ((uint32_t)(v >> s1) & m1)];
+      if (id != 255u) lists[id * 32 + atomicAdd(&sh_n[id], 1u)] = v;
+    });
+  } else {
+    // ---- pass 2b: a 22-bit group is still larger than a warp (scores packed into a narrow range, e.g. the top 5 % of
+    // entropies of a 1024x2048 image): split it by the remaining 10 key bits -> the whole float is resolved ----
+    const int s2 = c_shift[2];
+    const uint32_t m2 = (1u << c_bits[2]) - 1u;
+    const bool fit = (int)ng2 * kHistBins * (int)sizeof(uint32_t) + (int)ng * kHistBins <= kHistBytes;  // hist2 below map1
+    for (int i = tid; i < (int)ng2 * (kHistBins / 4); i += kPickThreads)
+      reinterpret_cast<uint4*>(sh_h)[i] = make_uint4(0u, 0u, 0u, 0u);  // (overwrites map1 when it does not fit)
+    __syncthreads();
+    if (fit) {
+      pick_for_each<CACHED>(reg, c, p.k, tid, [&](uint64_t v, bool valid) {
+        if (!valid) return;
+        const uint32_t g = map0[(uint32_t)(v >> s0) & m0];
+        if (g == 255u) return;
+        const uint32_t g2 = map1[g * kHistBins + ((uint32_t)(v >> s1) & m1)];
+        if (g2 != 255u) atomicAdd(&sh_h[g2 * kHistBins + ((uint32_t)(v >> s2) & m2)], 1u);
+      });
+    } else {  // the table was overwritten by the histograms (> 9 distinct large groups): compare with the prefixes instead
+      pick_for_each<CACHED>(reg, c, p.k, tid, [&](uint64_t v, bool valid) {
+        if (!valid || map0[(uint32_t)(v >> s0) & m0] == 255u) return;
+        const uint32_t key = (uint32_t)(v >> s1);
+#pragma unroll 1
+        for (uint32_t g = 0; g < ng2; ++g)
+          if (key == gp2[g]) {
+            atomicAdd(&sh_h[g * kHistBins + ((uint32_t)(v >> s2) & m2)], 1u);
+            break;
+          }
+      });
+    }
+    __syncthreads();
+    coarse_sums((int)ng2);
+    __syncthreads();
+    for (int j = warp; j < nr; j += kPickThreads / 32) narrow(sh_h + sh_g2[j] * kHistBins, sh_coarse[sh_g2[j]], j, sh_b2);
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t mx = 0;
+      for (int j = 0; j < nr; ++j) mx = sh_cnt[j] > mx ? sh_cnt[j] : mx;
+      sh_ok = (mx <= 32u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!sh_ok) {  // exact ties beyond a warp: the generic walk finishes this image (every thread takes this branch)
+      pick_ranks_generic<CACHED>(c, p.k, p.n, pos, out, sh_h);
+      return;
+    }
+    // ---- pass 3 on all 32 key bits ----
+    if (fit) {
+      // map2[g2][third digit] -> list id (the first rank with that prefix), at byte 4096 of the (dead) histogram area
+      uint8_t* map2 = reinterpret_cast<uint8_t*>(sh_h) + 4096;
+      const int d2n = 1 << c_bits[2];
+      for (int i = tid; i < (int)ng2 * (d2n / 16); i += kPickThreads)
+        reinterpret_cast<uint4*>(map2)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      __syncthreads();
+      if (tid == 0) {
+        for (int j = 0; j < nr; ++j) {
+          uint8_t* e = map2 + sh_g2[j] * d2n + sh_b2[j];
+          if (*e == 255) *e = (uint8_t)j;
+          sh_lid[j] = *e;
+        }
+      }
+      __syncthreads();
+      pick_for_each<CACHED>(reg, c, p.k, tid, [&](uint64_t v, bool valid) {
+        if (!valid) return;
+        const uint32_t g = map0[(uint32_t)(v >> s0) & m0];
+        if (g == 255u) return;
+        const uint32_t g2 = map1[g * kHistBins + ((uint32_t)(v >> s1) & m1)];
+        if (g2 == 255u) return;
+        const uint32_t id = map2[g2 * d2n + ((uint32_t)(v >> s2) & m2)];
+        if (id != 255u) lists[id * 32 + atomicAdd(&sh_n[id], 1u)] = v;
+      });
+    } else {
+      if (tid < nr) {
+        sh_lid[tid] = (uint32_t)tid;
+        sh_pre[tid] = (sh_b0[tid] << (c_bits[1] + c_bits[2])) | (sh_b1[tid] << c_bits[2]) | sh_b2[tid];  // all 32 key bits
+      }
+      __syncthreads();
+      pick_for_each<CACHED>(reg, c, p.k, tid, [&](uint64_t v, bool valid) {
+        if (!valid || map0[(uint32_t)(v >> s0) & m0] == 255u) return;
+        const uint32_t key = (uint32_t)(v >> s2);
+#pragma unroll 1
+        for (int j = 0; j < nr; ++j)
+          if (key == sh_pre[j]) lists[j * 32 + atomicAdd(&sh_n[j], 1u)] = v;
+      });
+    }
+  }
+  __syncthreads();
+  for (int j = warp; j < nr; j += kPickThreads / 32) {
+    const uint32_t id = sh_lid[j];
+    const uint32_t cnt = sh_n[id];
+    const uint64_t x = (uint32_t)lane < cnt ? lists[id * 32 + lane] : ~0ull;
+    uint32_t below = 0;
+    for (int o = 0; o < 32; ++o) {
+      const uint64_t y = __shfl_sync(full, x, o);
+      below += (y < x) ? 1u : 0u;
+    }
+    if ((uint32_t)lane < cnt && below + 1u == sh_rem[j]) sh_res[j] = x;  // composites are unique
+  }
+  __syncthreads();
+  if (tid < nr) out[tid] = (int32_t)(uint32_t)(sh_res[tid] & 0xFFFFFFFFull);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1676,6 +1926,17 @@ static int score_variant() {
   return v;
 }
 
+// PP_SELECT_L0=1: the one-chunk-per-CTA level-0 kernel instead of the staged persistent one (A/B measurements)
+static int select_l0_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PP_SELECT_L0");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 1) v = 0;
+  }
+  return v;
+}
+
 template <int C, int STRAT, typename T, int PX, int MINB>
 static void launch_score_vec_v(const ScoreParams& p, cudaStream_t st) {
   constexpr int ITERS = 4;
@@ -1778,8 +2039,6 @@ static int select_impl(const float* score_map, int n_img, int HW, int k, int lar
     p.out_count = w.filt_count;
     p.cand = w.cand;
     p.cand_count = w.cand_count;
-    p.hist_cur = w.hist;
-    p.hist_next = w.hist + (size_t)n_img * kHistBins;
     p.state_cur = w.state;
     p.state_next = w.state + (size_t)n_img;
     p.level = 0;
@@ -1791,9 +2050,32 @@ static int select_impl(const float* score_map, int n_img, int HW, int k, int lar
     pick_bucket0_kernel<<<n_img, kSelThreads, 0, st>>>(w.hist, w.state + (size_t)n_img, (uint32_t)k, largest != 0);
     PP_LAUNCH_CHECK();
     const int gx = (HW + kL0Chunk - 1) / kL0Chunk;  // one chunk of scores per CTA
-    const bool full = (HW % kL0Chunk == 0) && ((reinterpret_cast<uintptr_t>(score_map) & 15) == 0);
-    if (full) select_l0_kernel<true><<<dim3(gx, n_img), kSelThreads, 0, st>>>(p);
-    else select_l0_kernel<false><<<dim3(gx, n_img), kSelThreads, 0, st>>>(p);
+    const bool aligned = (reinterpret_cast<uintptr_t>(score_map) & 15) == 0;
+    const bool full = (HW % kL0Chunk == 0) && aligned;
+    const int l0v = select_l0_variant();
+    if (aligned && HW % kL0WarpChunk == 0 && l0v != 1) {
+      static int n_sm = 0;
+      if (n_sm == 0) {
+        int dev = 0, sms = 0;
+        PP_CUDA(cudaGetDevice(&dev));
+        PP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        PP_CUDA(cudaFuncSetAttribute(select_l0_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0sSmemBytes));
+        n_sm = sms;
+      }
+      L0sWalk wk;
+      wk.chunks_per_img = (uint32_t)(HW / kL0WarpChunk);
+      wk.total_chunks = (uint32_t)n_img * wk.chunks_per_img;
+      uint32_t ctas = (wk.total_chunks + kL0sWarps - 1) / kL0sWarps;
+      const uint32_t cap = (uint32_t)(n_sm * kL0sCtasPerSm);
+      ctas = ctas < cap ? ctas : cap;
+      wk.base = wk.total_chunks / (ctas * kL0sWarps);
+      wk.extra = wk.total_chunks % (ctas * kL0sWarps);
+      select_l0_staged_kernel<<<ctas, kSelThreads, kL0sSmemBytes, st>>>(p, wk);
+    } else if (full) {
+      select_l0_kernel<true><<<dim3(gx, n_img), kSelThreads, 0, st>>>(p);
+    } else {
+      select_l0_kernel<false><<<dim3(gx, n_img), kSelThreads, 0, st>>>(p);
+    }
     PP_LAUNCH_CHECK();
     RestParams r;
     r.list_a = w.filt;
@@ -2160,11 +2442,11 @@ int pp_acq_pick(void* workspace, size_t workspace_bytes, int n_img, int HW, int 
   static bool attr = false;
   const int smem = kPickRanks * kHistBins * (int)sizeof(uint32_t);
   if (!attr) {
-    PP_CUDA(cudaFuncSetAttribute(pick_ranks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     // two 97 KB CTAs per SM (64 registers / thread): 256 images are then ONE wave on 148 SMs instead of two
-    PP_CUDA(cudaFuncSetAttribute(pick_ranks_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    PP_CUDA(cudaFuncSetAttribute(pick_ranks_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PP_CUDA(cudaFuncSetAttribute(pick_ranks_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PP_CUDA(cudaFuncSetAttribute(pick_ranks_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PP_CUDA(cudaFuncSetAttribute(pick_ranks_fast_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PP_CUDA(cudaFuncSetAttribute(pick_ranks_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PP_CUDA(cudaFuncSetAttribute(pick_ranks_fast_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
   PickParams p;
@@ -2174,11 +2456,10 @@ int pp_acq_pick(void* workspace, size_t workspace_bytes, int n_img, int HW, int 
   p.n = n;
   p.pos = pos;
   p.out = out;
-  p.fallback = w.filt_count + n_img;  // second half of the boundary-count array: free once the select has finished
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  pick_ranks_fast_kernel<<<n_img, kPickThreads, smem, st>>>(p);  // three cheap passes; flags the images it cannot finish
-  PP_LAUNCH_CHECK();
-  pick_ranks_kernel<<<n_img, kPickThreads, smem, st>>>(p);  // generic radix walk for the flagged images (heavy ties)
+  // ONE launch: three cheap passes per image; images it cannot finish (heavy ties, n > 12) run the generic walk inside it
+  if (k <= kPickThreads * kPickItems) pick_ranks_fast_kernel<true><<<n_img, kPickThreads, smem, st>>>(p);   // candidates in registers
+  else pick_ranks_fast_kernel<false><<<n_img, kPickThreads, smem, st>>>(p);                                  // streamed from L2
   PP_LAUNCH_CHECK();
   return PP_OK;
 }
