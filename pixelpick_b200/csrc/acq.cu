@@ -367,6 +367,12 @@ constexpr int kSelThreads = 256;
 constexpr int kSelItems = 16;
 constexpr int kSelTile = kSelThreads * kSelItems;  // 4096
 
+// Per-image output counters live on their OWN 128-byte line (word 0: candidates, word 1: boundary entries).  Packed as two
+// [n_img] arrays, the counters of every image being classified at one time sat in one line, i.e. in ONE L2 slice, which then
+// served all 131 072 atomics of a 256-image step one after the other (ncu: lts__t_tag_requests max over slices 74 % of
+// peak against 28 % on average while the level-0 kernel ran at 3.3 TB/s whatever its occupancy or prefetch depth).
+constexpr int kCntStride = 32;
+
 struct SelState {
   uint32_t remaining;
   uint32_t done;
@@ -379,8 +385,8 @@ struct SelState {
 struct Workspace {
   uint32_t* hist;        // [n_img][2048] level-0 histogram (the later levels are histogrammed in shared memory)
   SelState* state;       // [kLevels+1][n_img]
-  uint32_t* cand_count;  // [n_img]
-  uint32_t* filt_count;  // [2][n_img]
+  uint32_t* cand_count;  // [n_img][kCntStride]: word 0 = candidates written so far
+  uint32_t* filt_count;  // = cand_count + 1: word 1 = entries of the boundary list
   uint64_t* cand;        // [n_img][kpad]
   uint64_t* filt;        // [2][n_img][HW]
   size_t zero_bytes;     // hist..filt_count are contiguous from the workspace base
@@ -403,9 +409,8 @@ static Workspace carve(void* base, int n_img, int HW, int k) {
   w.state = reinterpret_cast<SelState*>(p + off);
   off += align_up((size_t)(kLevels + 1) * n_img * sizeof(SelState), 256);
   w.cand_count = reinterpret_cast<uint32_t*>(p + off);
-  off += align_up((size_t)n_img * sizeof(uint32_t), 256);
-  w.filt_count = reinterpret_cast<uint32_t*>(p + off);
-  off += align_up((size_t)2 * n_img * sizeof(uint32_t), 256);
+  w.filt_count = w.cand_count + 1;
+  off += align_up((size_t)n_img * kCntStride * sizeof(uint32_t), 256);
   w.zero_bytes = off;
   w.kpad = next_pow2(k);
   w.cand = reinterpret_cast<uint64_t*>(p + off);
@@ -642,8 +647,8 @@ __global__ void __launch_bounds__(kSelThreads, 6) select_l0_kernel(const SelPara
   uint32_t base_c = 0, base_f = 0;
   if (lane == 0) {
     const uint32_t tc = tot & 0xFFFFu, tf = tot >> 16;
-    if (tc) base_c = atomicAdd(p.cand_count + img, tc);
-    if (tf) base_f = atomicAdd(p.out_count + img, tf);
+    if (tc) base_c = atomicAdd(p.cand_count + (size_t)img * kCntStride, tc);
+    if (tf) base_f = atomicAdd(p.out_count + (size_t)img * kCntStride, tf);
   }
   base_c = __shfl_sync(0xFFFFFFFFu, base_c, 0);
   base_f = __shfl_sync(0xFFFFFFFFu, base_f, 0);
@@ -681,11 +686,12 @@ __global__ void __launch_bounds__(kSelThreads, 6) select_l0_kernel(const SelPara
 //     9-bit chunk offsets behind one warp scan, and then classified on the exact ordering key and written DENSELY, one survivor
 //     per lane and trip, behind one warp-aggregated atomic pair, as in the legacy kernel.
 // Output = the same two unordered sets (candidates below the bucket, boundary list inside it).
-constexpr int kL0sStages = 4;
 constexpr int kL0sWarps = kSelThreads / 32;
-constexpr int kL0sWarpBytes = kL0sStages * kL0WarpChunk * (int)sizeof(float) + kL0WarpChunk * (int)sizeof(uint16_t);  // 9 KB
-constexpr int kL0sSmemBytes = kL0sWarps * kL0sWarpBytes;  // 72 KB
-constexpr int kL0sCtasPerSm = 3;
+template <int STAGES> struct L0sCfg {
+  static constexpr int kWarpBytes = STAGES * kL0WarpChunk * (int)sizeof(float) + kL0WarpChunk * (int)sizeof(uint16_t);
+  static constexpr int kSmemBytes = kL0sWarps * kWarpBytes;           // 4 stages: 72 KB, 3: 56 KB, 2: 40 KB
+  static constexpr int kCtasPerSm = STAGES >= 4 ? 3 : (STAGES == 3 ? 4 : 5);
+};
 
 struct L0sWalk {
   uint32_t chunks_per_img;  // H*W / 512
@@ -693,7 +699,9 @@ struct L0sWalk {
   uint32_t base, extra;     // warp g of the grid owns base + (g < extra) consecutive chunks
 };
 
-__global__ void __launch_bounds__(kSelThreads, kL0sCtasPerSm) select_l0_staged_kernel(const SelParams p, const L0sWalk w) {
+template <int kL0sStages>
+__global__ void __launch_bounds__(kSelThreads, L0sCfg<kL0sStages>::kCtasPerSm) select_l0_staged_kernel(const SelParams p, const L0sWalk w) {
+  constexpr int kL0sWarpBytes = L0sCfg<kL0sStages>::kWarpBytes;
   extern __shared__ __align__(16) unsigned char l0s_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* ring = reinterpret_cast<float*>(l0s_smem + warp * kL0sWarpBytes);
@@ -800,9 +808,11 @@ __global__ void __launch_bounds__(kSelThreads, kL0sCtasPerSm) select_l0_staged_k
       if (tot != 0u) {  // warp-uniform
         uint32_t base_c = 0, base_f = 0;
         if (lane == 0) {
-          const uint32_t tc = tot & 0xFFFFu, tf = tot >> 16;
-          if (tc) base_c = atomicAdd(p.cand_count + img, tc);
-          if (tf) base_f = atomicAdd(p.out_count + img, tf);
+          // both counters of the image with ONE 64-bit atomic (they share an aligned 8-byte word, see kCntStride)
+          const unsigned long long add = (unsigned long long)(tot & 0xFFFFu) | ((unsigned long long)(tot >> 16) << 32);
+          const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(p.cand_count + (size_t)img * kCntStride), add);
+          base_c = (uint32_t)old;
+          base_f = (uint32_t)(old >> 32);
         }
         base_c = __shfl_sync(full, base_c, 0);
         base_f = __shfl_sync(full, base_f, 0);
@@ -1068,8 +1078,8 @@ __global__ void __launch_bounds__(kScoreThreads, 2) acq_score_select_kernel(cons
       uint32_t base_c = 0, base_f = 0;
       if (lane == 0) {
         const uint32_t tc = tot & 0xFFFFu, tf = tot >> 16;
-        if (tc) base_c = atomicAdd(f.cand_count + img, tc);
-        if (tf) base_f = atomicAdd(f.bnd_count + img, tf);
+        if (tc) base_c = atomicAdd(f.cand_count + (size_t)img * kCntStride, tc);
+        if (tf) base_f = atomicAdd(f.bnd_count + (size_t)img * kCntStride, tf);
       }
       base_c = __shfl_sync(0xFFFFFFFFu, base_c, 0);
       base_f = __shfl_sync(0xFFFFFFFFu, base_f, 0);
@@ -1099,6 +1109,7 @@ __global__ void __launch_bounds__(kScoreThreads, 2) acq_score_select_kernel(cons
 // radix levels (histogram in shared memory -> pick -> partition) run back to back without further launches or
 // global histogram traffic.  Appends are warp-aggregated shared-memory atomics; order is irrelevant (sorted later).
 constexpr int kRestThreads = 1024;
+constexpr int kRestDirect = 256;  // lists up to this length are ranked directly
 struct RestParams {
   uint64_t* list_a;        // [n_img][HW] boundary list written by level 0
   uint64_t* list_b;        // [n_img][HW] scratch
@@ -1115,6 +1126,7 @@ __global__ void __launch_bounds__(kRestThreads) select_rest_kernel(const RestPar
   __shared__ uint32_t sh_warp[kRestThreads / 32];
   __shared__ uint32_t sh_pick[3];
   __shared__ uint32_t sh_cnt[2];  // cand count, next-list count
+  __shared__ uint64_t sh_direct[kRestDirect];
   const int img = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SelState st = p.state1[img];
@@ -1123,9 +1135,27 @@ __global__ void __launch_bounds__(kRestThreads) select_rest_kernel(const RestPar
   uint64_t* in = p.list_a + (size_t)img * p.HW;
   uint64_t* out = p.list_b + (size_t)img * p.HW;
   uint64_t* cand = p.cand + (size_t)img * p.kpad;
-  uint32_t n = p.count_a[img];
-  if (tid == 0) sh_cnt[0] = p.cand_count[img];
+  uint32_t n = p.count_a[(size_t)img * kCntStride];
+  if (tid == 0) sh_cnt[0] = p.cand_count[(size_t)img * kCntStride];
   for (int level = p.first_level; level < kLevels; ++level) {  // from the key's first digit when level 0 was the linear bucket0
+    if (n <= (uint32_t)kRestDirect) {
+      // A short list (the linear level-0 buckets of the largest-first strategies leave ~50-200 entries; after one radix level
+      // any list is this short) is ranked directly: thread t counts the composites below its own - they are unique - and the
+      // `rem` smallest are the selection.  One barrier pair instead of 2-4 more levels of histogram / scan / partition.
+      if (tid < (int)n) sh_direct[tid] = in[tid];
+      __syncthreads();
+      if (tid < (int)n) {
+        const uint64_t v = sh_direct[tid];
+        uint32_t below = 0;
+        for (uint32_t j = 0; j < n; ++j) below += (sh_direct[j] < v) ? 1u : 0u;
+        if (below < rem) {
+          const uint32_t pos = atomicAdd(&sh_cnt[0], 1u);
+          if (pos < (uint32_t)p.kpad) cand[pos] = v;
+        }
+      }
+      __syncthreads();
+      break;
+    }
     const int shift = c_shift[level];
     const uint32_t dmask = (1u << c_bits[level]) - 1u;
     for (int i = tid; i < kHistBins; i += kRestThreads) sh_hist[i] = 0;
@@ -1187,7 +1217,7 @@ __global__ void __launch_bounds__(kRestThreads) select_rest_kernel(const RestPar
     uint64_t* t = in; in = out; out = t;
     __syncthreads();
   }
-  if (tid == 0) p.cand_count[img] = sh_cnt[0];
+  if (tid == 0) p.cand_count[(size_t)img * kCntStride] = sh_cnt[0];
 }
 
 // Order statistics instead of a sort: the reference draws n random RANKS of the sorted top-k list
@@ -1932,7 +1962,7 @@ static int select_l0_variant() {
   if (v < 0) {
     const char* e = getenv("PP_SELECT_L0");
     v = e ? atoi(e) : 0;
-    if (v < 0 || v > 1) v = 0;
+    if (v < 0 || v > 3) v = 0;
   }
   return v;
 }
@@ -2059,18 +2089,24 @@ static int select_impl(const float* score_map, int n_img, int HW, int k, int lar
         int dev = 0, sms = 0;
         PP_CUDA(cudaGetDevice(&dev));
         PP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        PP_CUDA(cudaFuncSetAttribute(select_l0_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL0sSmemBytes));
+        PP_CUDA(cudaFuncSetAttribute(select_l0_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0sCfg<4>::kSmemBytes));
+        PP_CUDA(cudaFuncSetAttribute(select_l0_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0sCfg<3>::kSmemBytes));
+        PP_CUDA(cudaFuncSetAttribute(select_l0_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L0sCfg<2>::kSmemBytes));
         n_sm = sms;
       }
+      const int stages = l0v == 2 ? 3 : (l0v == 3 ? 4 : 2);  // default: 2 stages, 5 CTAs / SM (measured 48.1 / 50.2 / 54.2 us select phase)
+      const int per_sm = stages == 4 ? L0sCfg<4>::kCtasPerSm : (stages == 3 ? L0sCfg<3>::kCtasPerSm : L0sCfg<2>::kCtasPerSm);
       L0sWalk wk;
       wk.chunks_per_img = (uint32_t)(HW / kL0WarpChunk);
       wk.total_chunks = (uint32_t)n_img * wk.chunks_per_img;
       uint32_t ctas = (wk.total_chunks + kL0sWarps - 1) / kL0sWarps;
-      const uint32_t cap = (uint32_t)(n_sm * kL0sCtasPerSm);
+      const uint32_t cap = (uint32_t)(n_sm * per_sm);
       ctas = ctas < cap ? ctas : cap;
       wk.base = wk.total_chunks / (ctas * kL0sWarps);
       wk.extra = wk.total_chunks % (ctas * kL0sWarps);
-      select_l0_staged_kernel<<<ctas, kSelThreads, kL0sSmemBytes, st>>>(p, wk);
+      if (stages == 4) select_l0_staged_kernel<4><<<ctas, kSelThreads, L0sCfg<4>::kSmemBytes, st>>>(p, wk);
+      else if (stages == 3) select_l0_staged_kernel<3><<<ctas, kSelThreads, L0sCfg<3>::kSmemBytes, st>>>(p, wk);
+      else select_l0_staged_kernel<2><<<ctas, kSelThreads, L0sCfg<2>::kSmemBytes, st>>>(p, wk);
     } else if (full) {
       select_l0_kernel<true><<<dim3(gx, n_img), kSelThreads, 0, st>>>(p);
     } else {

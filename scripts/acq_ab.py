@@ -5,7 +5,8 @@
 Every build is loaded into this one process (separate CDLL instances) and run on the same device tensors, so equal
 `picks` checksums mean bit-identical selections; the phase times are score / select (pick_bucket0 + select_l0 +
 select_rest) / pick, means over `steps` steps.  The tree's build is also run with PP_SELECT_L0=1 (one-chunk-per-CTA
-level-0 kernel) from a copy of the file, because the switch is read once per loaded library."""
+level-0 kernel; PP_AB_L0=1,2,3 for more of acq.cu's variants) from a copy of the file, because the switch is read once per
+loaded library."""
 import hashlib
 import json
 import os
@@ -86,9 +87,14 @@ if __name__ == "__main__":
     cfgs = [(256, 256, 512, "margin_sampling"), (256, 256, 512, "entropy"), (32, 360, 480, "least_confidence"),
             (8, 1024, 2048, "entropy"), (8, 1024, 2048, "margin_sampling"), (8, 1024, 2048, "least_confidence"),
             (1, 256, 512, "margin_sampling")]
-    copy = os.path.join(os.path.dirname(TREE_LIB), "build", "libpp_tree_copy.so")
-    shutil.copyfile(TREE_LIB, copy)
-    builds = [(os.path.basename(p), p, None) for p in sys.argv[1:]] + [("tree, PP_SELECT_L0=1", copy, "1"), ("tree", TREE_LIB, None)]
+    builds = [(os.path.basename(p), p, None) for p in sys.argv[1:]]
+    for v in os.environ.get("PP_AB_L0", "1").split(","):  # the tree's build with the other level-0 kernels
+        copy = os.path.join(os.path.dirname(TREE_LIB), "build", f"libpp_tree_l0_{v}.so")
+        shutil.copyfile(TREE_LIB, copy)
+        builds.append((f"tree, PP_SELECT_L0={v}", copy, v))
+    builds.append(("tree", TREE_LIB, None))
+    if os.environ.get("PP_AB_CFGS"):
+        cfgs = cfgs[:int(os.environ["PP_AB_CFGS"])]
     for name, path, sel in builds:
         use(path, sel)
         print("==", name, flush=True)
