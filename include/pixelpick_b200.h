@@ -103,8 +103,11 @@ int pp_acq_score_select(const void* logits, int dtype, int n_img, int C, int H, 
  * where hist0 must be the pointer returned by pp_acq_topk_hist0(workspace).
  * ------------------------------------------------------------------------------------------ */
 int pp_acq_topk_workspace_bytes(int n_img, int HW, int k, size_t* out_bytes);
-/* Zeroes the counters/histograms inside the workspace; must run (on the same stream) before
- * pp_acq_score(hist0=...) / pp_acq_topk for every batch. */
+/* Zeroes the counters/histograms inside the workspace; must run (on the same stream) before the FIRST
+ * pp_acq_score(hist0=...) / pp_acq_topk / pp_acq_select / pp_acq_score_select on it.  A completed select (pp_acq_topk,
+ * pp_acq_select, or pp_acq_score_select) leaves the workspace prepared again for the same (n_img, HW, k) - the kernels zero what
+ * they consumed - so a host that tracks this may skip the call between batches; calling it every batch stays correct.  A
+ * pp_acq_score(hist0=...) that is NOT followed by a select leaves the histogram filled: prepare again before reusing it. */
 int pp_acq_topk_prepare(void* workspace, size_t workspace_bytes, int n_img, int HW, int k, void* stream);
 uint32_t* pp_acq_topk_hist0(void* workspace);
 int pp_acq_topk(const float* score_map, int n_img, int HW, int k, int largest, int hist0_valid,

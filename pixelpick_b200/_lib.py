@@ -179,11 +179,31 @@ class TopKWorkspace:
         self.nbytes = sz.value
         self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
         assert self.buf.data_ptr() % 256 == 0
+        # What is known about the zeroed region (in stream order): None = nothing; "all" = all zero (after prepare());
+        # n = zero for batches of n images - a completed select zeroes what it consumed (include/pixelpick_b200.h:
+        # pp_acq_topk_prepare) but leaves its per-image bucket state behind, and where that lies depends on the batch size.
+        # Reset to None by everything that fills the level-0 histogram or starts a select; an exception keeps it None.
+        self._clean = None
 
-    def prepare(self, n_img=None):
-        n = self.n_img if n_img is None else n_img
-        check(lib().pp_acq_topk_prepare(_ptr(self.buf), self.nbytes, n, self.HW, self.k, _stream(self.buf)),
+    def prepare(self, n_img=None, force=False):
+        """zero the histogram / counters unless a completed select has left them zero already (always the full-capacity
+        region: the regions of smaller batches are prefixes of it)"""
+        if self._clean is not None and not force:
+            return
+        check(lib().pp_acq_topk_prepare(_ptr(self.buf), self.nbytes, self.n_img, self.HW, self.k, _stream(self.buf)),
               "pp_acq_topk_prepare")
+        self._clean = "all"
+
+    def _begin_fill(self, n):
+        """before a kernel accumulates the level-0 histogram of a batch of n images here: it must start from zero"""
+        if self._clean not in ("all", n):
+            self.prepare(force=True)
+        self._clean = None
+
+    def _begin_select(self, n, hist0_valid):
+        if not hist0_valid and self._clean not in ("all", n):
+            self.prepare(force=True)  # the select builds the histogram itself, from zero
+        self._clean = None
 
     def hist0_ptr(self):
         return C.c_void_p(lib().pp_acq_topk_hist0(_ptr(self.buf)))
@@ -199,6 +219,8 @@ def acq_score(logits, strategy, labelled=None, void_mask=None, keep=None, out=No
     _check_score_outputs("acq_score", n, H, W, out, hist0_ws)
     if out is None:
         out = torch.empty((n, H, W), dtype=torch.float32, device=logits.device)
+    if hist0_ws is not None:
+        hist0_ws._begin_fill(n)
     check(lib().pp_acq_score(_ptr(logits), _dtype_code(logits), n, Cc, H, W, logits.stride(0), logits.stride(1),
                              logits.stride(2), _ptr(labelled), _ptr(void_mask), _ptr(keep),
                              STRATEGIES[strategy], _ptr(out),
@@ -217,6 +239,8 @@ def acq_score_upsampled(logits_lowres, size, strategy, labelled=None, void_mask=
     _check_score_outputs("acq_score_upsampled", n, H, W, out, hist0_ws)
     if out is None:
         out = torch.empty((n, H, W), dtype=torch.float32, device=logits_lowres.device)
+    if hist0_ws is not None:
+        hist0_ws._begin_fill(n)
     check(lib().pp_acq_score_upsampled(_ptr(logits_lowres), n, Cc, h, w, H, W, _ptr(labelled), _ptr(void_mask),
                                        _ptr(keep), STRATEGIES[strategy], _ptr(out),
                                        hist0_ws.hist0_ptr() if hist0_ws is not None else None,
@@ -239,8 +263,10 @@ def acq_topk(score_map, k, largest, ws=None, hist0_valid=False, return_values=Fa
         hist0_valid = False
     idx = torch.empty((n, k), dtype=torch.int32, device=sm.device)
     val = torch.empty((n, k), dtype=torch.float32, device=sm.device) if return_values else None
+    ws._begin_select(n, hist0_valid)
     check(lib().pp_acq_topk(_ptr(sm), n, HW, k, int(bool(largest)), int(bool(hist0_valid)), _ptr(idx), _ptr(val),
                             _ptr(ws.buf), ws.nbytes, _stream(sm)), "pp_acq_topk")
+    ws._clean = n  # the select's kernels hand the workspace back zeroed
     return (idx, val) if return_values else idx
 
 
@@ -261,8 +287,10 @@ def acq_select_pick(score_map, k, largest, pos, n=None, ws=None, hist0_valid=Fal
         pos = pos.to(device=sm.device, dtype=torch.int32).contiguous()
         n = pos.shape[1]
     out = torch.empty((n_img, n), dtype=torch.int32, device=sm.device)
+    ws._begin_select(n_img, hist0_valid)
     check(lib().pp_acq_select(_ptr(sm), n_img, HW, k, int(bool(largest)), int(bool(hist0_valid)), _ptr(ws.buf), ws.nbytes,
                               _stream(sm)), "pp_acq_select")
+    ws._clean = n_img  # the select's kernels hand the workspace back zeroed
     check(lib().pp_acq_pick(_ptr(ws.buf), ws.nbytes, n_img, HW, k, _ptr(pos), n, _ptr(out), _stream(sm)), "pp_acq_pick")
     return out
 
@@ -289,9 +317,11 @@ def acq_score_select_pick(logits, strategy, k, pos, labelled=None, void_mask=Non
         ws = TopKWorkspace(n_img, HW, k, logits.device)
         ws.prepare()
     _check_score_outputs("acq_score_select_pick", n_img, H, W, score_out, ws)
+    ws._begin_select(n_img, False)
     check(lib().pp_acq_score_select(_ptr(logits), _dtype_code(logits), n_img, Cc, H, W, logits.stride(0), logits.stride(1),
                                     logits.stride(2), _ptr(labelled), _ptr(void_mask), _ptr(keep), STRATEGIES[strategy], k,
                                     _ptr(score_out), _ptr(ws.buf), ws.nbytes, _stream(logits)), "pp_acq_score_select")
+    ws._clean = n_img  # its radix tail hands the workspace back zeroed
     if mark is not None:
         mark.record()  # bench.py: a CUDA event between the fused kernel (+ radix tail) and the pick
     if pos is not None:

@@ -256,6 +256,98 @@ __global__ void __launch_bounds__(kScoreThreads, MINB) acq_score_vec_kernel(cons
   }
 }
 
+// Vector kernel with the NEXT tile in flight while the current one is scored (fp32 logits, 4 pixels per thread).
+// acq_score_vec_kernel issues a thread's C loads, waits, then spends ~600 instructions on the softmax with nothing of its
+// own in flight: only the other 1-3 warps of the scheduler keep HBM busy meanwhile.  Here a thread's C x 16 bytes travel
+// through a private slot in shared memory (cp.async): the slot is drained into registers, refilled at once with the
+// thread's next tile (and the next tile's mask words are loaded into registers), and only then is the drained tile
+// scored - so every thread has C x 16 bytes in flight during its whole compute phase.  A thread only reads what it copied
+// itself, so cp.async.wait_group is the only synchronisation.  Shared memory: C x 4 KB per CTA (76 KB at C = 19).
+template <int C, int STRAT, bool HIST, int ITERS, int MINB>
+__global__ void __launch_bounds__(kScoreThreads, MINB) acq_score_pf_kernel(const ScoreParams p) {
+  extern __shared__ __align__(16) float4 pf_slot[];  // [C][kScoreThreads]
+  __shared__ uint32_t sh_hist[HIST ? kHistBins : 1];
+  if (HIST) {
+    for (int i = threadIdx.x; i < kHistBins; i += kScoreThreads) sh_hist[i] = 0;
+    __syncthreads();
+  }
+  const int img = blockIdx.y;
+  const int Wv = p.W / 4;
+  const int nvec = p.H * Wv;
+  const int64_t HW = (int64_t)p.H * p.W;
+  const float* __restrict__ base = reinterpret_cast<const float*>(p.logits) + (int64_t)img * p.sn;
+  const bool largest = p.largest != 0;
+  const uint32_t slot_s = (uint32_t)__cvta_generic_to_shared(pf_slot + threadIdx.x);
+
+  bool ok_n = false;
+  int64_t pix_n = 0;
+  uint32_t lab_n = 0, vd_n = 0, keep_n = 0;
+  auto issue = [&](int it) {
+    const int q = (blockIdx.x * ITERS + it) * kScoreThreads + threadIdx.x;
+    ok_n = it < ITERS && q < nvec;
+    if (ok_n) {
+      const int y = q / Wv;
+      const int x = (q - y * Wv) * 4;
+      const float* __restrict__ src = base + (int64_t)y * p.sh + x;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot_s + (uint32_t)(c * kScoreThreads * 16)),
+                     "l"(src + (int64_t)c * p.sc)
+                     : "memory");
+      pix_n = (int64_t)img * HW + (int64_t)y * p.W + x;
+      if (p.lab) lab_n = ld_mask<4>(p.lab + pix_n);
+      if (p.vd) vd_n = ld_mask<4>(p.vd + pix_n);
+      if (p.keep) keep_n = ld_mask<4>(p.keep + pix_n);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0);
+#pragma unroll 1
+  for (int it = 0; it < ITERS; ++it) {
+    if (!ok_n) break;
+    const int64_t pix = pix_n;
+    uint32_t msk = 0;
+    if (p.lab) msk |= lab_n;
+    if (p.vd) msk |= vd_n;
+    if (p.keep) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (((keep_n >> (8 * j)) & 0xFFu) == 0) msk |= 0xFFu << (8 * j);  // keep == 0 -> excluded
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    float v[C][4];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float4 r = pf_slot[c * kScoreThreads + threadIdx.x];
+      v[c][0] = r.x, v[c][1] = r.y, v[c][2] = r.z, v[c][3] = r.w;
+    }
+    issue(it + 1);  // the slot is in registers: refill it before scoring
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float xs[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) xs[c] = v[c][j];
+      out[j] = score_from_logits<C, STRAT>(xs);
+      if ((msk >> (8 * j)) & 0xFFu) out[j] = p.fill;
+    }
+    *reinterpret_cast<float4*>(p.score + pix) = make_float4(out[0], out[1], out[2], out[3]);
+    if (HIST) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&sh_hist[bucket0(out[j], largest)], 1u);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (HIST) {
+    __syncthreads();
+    uint32_t* gh = p.hist0 + (size_t)img * kHistBins;
+    for (int i = threadIdx.x; i < kHistBins; i += kScoreThreads) {
+      const uint32_t c = sh_hist[i];
+      if (c) atomicAdd(gh + i, c);
+    }
+  }
+}
+
 // Scalar fallback: any C, any W, any stride/alignment. One thread = one pixel.
 template <int STRAT, typename T>
 __global__ void __launch_bounds__(kScoreThreads) acq_score_scalar_kernel(const ScoreParams p) {
@@ -455,13 +547,17 @@ __global__ void __launch_bounds__(kSelThreads) hist0_kernel(const float* __restr
 
 // One CTA per image: find the bucket of the level-0 histogram that holds the k-th element; state[img] = {rank inside
 // the bucket, whole bucket selected?, bucket}.  Done once here instead of in the prologue of every select_l0 CTA.
-__global__ void __launch_bounds__(kSelThreads) pick_bucket0_kernel(const uint32_t* __restrict__ hist0, SelState* __restrict__ state,
+__global__ void __launch_bounds__(kSelThreads) pick_bucket0_kernel(uint32_t* __restrict__ hist0, SelState* __restrict__ state,
                                                                     uint32_t k, bool largest) {
   __shared__ uint32_t sh_warp[kSelThreads / 32];
   __shared__ uint32_t sh_bucket;
   const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint4* hc = reinterpret_cast<const uint4*>(hist0 + (size_t)img * kHistBins) + tid * 2;
+  uint4* hc = reinterpret_cast<uint4*>(hist0 + (size_t)img * kHistBins) + tid * 2;
   const uint4 ha = hc[0], hb = hc[1];
+  // this kernel is the histogram's only reader: hand it back zeroed, so that the workspace is "prepared" again once the
+  // select has run (select_rest_kernel resets the counters) and a host that tracks this can skip pp_acq_topk_prepare
+  hc[0] = make_uint4(0u, 0u, 0u, 0u);
+  hc[1] = make_uint4(0u, 0u, 0u, 0u);
   const uint32_t h[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
   uint32_t mine = 0;
 #pragma unroll
@@ -1113,7 +1209,7 @@ constexpr int kRestDirect = 256;  // lists up to this length are ranked directly
 struct RestParams {
   uint64_t* list_a;        // [n_img][HW] boundary list written by level 0
   uint64_t* list_b;        // [n_img][HW] scratch
-  const uint32_t* count_a; // [n_img]
+  uint32_t* count_a;       // boundary-list lengths (kCntStride apart)
   uint64_t* cand;
   uint32_t* cand_count;
   const SelState* state1;  // {remaining, done} after level 0
@@ -1130,7 +1226,13 @@ __global__ void __launch_bounds__(kRestThreads) select_rest_kernel(const RestPar
   const int img = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SelState st = p.state1[img];
-  if (st.done) return;
+  if (st.done) {  // level 0 took a whole bucket: nothing left to resolve; leave the counters zeroed (see pick_bucket0_kernel)
+    if (tid == 0) {
+      p.cand_count[(size_t)img * kCntStride] = 0u;
+      p.count_a[(size_t)img * kCntStride] = 0u;
+    }
+    return;
+  }
   uint32_t rem = st.remaining;
   uint64_t* in = p.list_a + (size_t)img * p.HW;
   uint64_t* out = p.list_b + (size_t)img * p.HW;
@@ -1217,7 +1319,10 @@ __global__ void __launch_bounds__(kRestThreads) select_rest_kernel(const RestPar
     uint64_t* t = in; in = out; out = t;
     __syncthreads();
   }
-  if (tid == 0) p.cand_count[(size_t)img * kCntStride] = sh_cnt[0];
+  if (tid == 0) {  // every thread has read its counters before the barriers above: leave them zeroed for the next step
+    p.cand_count[(size_t)img * kCntStride] = 0u;
+    p.count_a[(size_t)img * kCntStride] = 0u;
+  }
 }
 
 // Order statistics instead of a sort: the reference draws n random RANKS of the sorted top-k list
@@ -1951,7 +2056,7 @@ static int score_variant() {
   if (v < 0) {
     const char* e = getenv("PP_SCORE_VARIANT");
     v = e ? atoi(e) : 0;
-    if (v < 0 || v > 3) v = 0;
+    if (v < 0 || v > 6) v = 0;
   }
   return v;
 }
@@ -1976,8 +2081,33 @@ static void launch_score_vec_v(const ScoreParams& p, cudaStream_t st) {
   else acq_score_vec_kernel<C, STRAT, T, false, ITERS, PX, MINB><<<grid, kScoreThreads, 0, st>>>(p);
 }
 
+template <int C, int STRAT, int ITERS>
+static void launch_score_pf(const ScoreParams& p, cudaStream_t st) {
+  constexpr int smem = C * kScoreThreads * 16;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(acq_score_pf_kernel<C, STRAT, true, ITERS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(acq_score_pf_kernel<C, STRAT, false, ITERS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  const int nvec = p.H * (p.W / 4);
+  dim3 grid((nvec + kScoreThreads * ITERS - 1) / (kScoreThreads * ITERS), p.n_img);
+  if (p.hist0) acq_score_pf_kernel<C, STRAT, true, ITERS, 2><<<grid, kScoreThreads, smem, st>>>(p);
+  else acq_score_pf_kernel<C, STRAT, false, ITERS, 2><<<grid, kScoreThreads, smem, st>>>(p);
+}
+
 template <int C, int STRAT, typename T>
 static void launch_score_vec(const ScoreParams& p, cudaStream_t st) {
+  // fp32 logits, enough CTAs for >= 8 waves: the kernel that keeps the next tile in flight while it scores (256 images of
+  // 256x512: 415 -> 402 us = 6.51 TB/s of algorithmic bytes; 32 images of 360x480: 73 -> 79 us, hence the size rule).
+  // PP_SCORE_VARIANT=4 / 5 force it (4 / 8 tiles per thread), 6 forces the plain kernel.
+  const int sv = score_variant();
+  const long long ctas = (long long)((p.H * (p.W / 4) + kScoreThreads * 4 - 1) / (kScoreThreads * 4)) * p.n_img;
+  if (sizeof(T) == 4 && p.W % 4 == 0 && (sv == 4 || sv == 5 || (sv == 0 && ctas >= 2368))) {
+    if (sv == 5) launch_score_pf<C, STRAT, 8>(p, st);
+    else launch_score_pf<C, STRAT, 4>(p, st);
+    return;
+  }
   switch (score_variant()) {
     case 1: launch_score_vec_v<C, STRAT, T, 4, 3>(p, st); break;
     case 2: launch_score_vec_v<C, STRAT, T, 2, 4>(p, st); break;

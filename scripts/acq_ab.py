@@ -26,11 +26,19 @@ C = bench.C
 TREE_LIB = _lib.LIB_PATH
 
 
-def use(path, select_l0=None):
+SELF_CLEANING = True  # the loaded build's select leaves the workspace prepared (False for builds older than this feature)
+
+
+def use(path, select_l0=None, score=None):
     """make `path` the library behind _lib (a fresh CDLL instance with its own statics)"""
+    global SELF_CLEANING
+    SELF_CLEANING = "prev" not in os.path.basename(path)
     os.environ.pop("PP_SELECT_L0", None)
+    os.environ.pop("PP_SCORE_VARIANT", None)
     if select_l0 is not None:
         os.environ["PP_SELECT_L0"] = select_l0
+    if score is not None:
+        os.environ["PP_SCORE_VARIANT"] = score
     _lib._lib = None
     _lib.LIB_PATH = os.path.abspath(path)
     return _lib.lib()
@@ -53,13 +61,14 @@ def run(n_img, H, W, strat, steps=10, seed=7, scale=3.0):
     st = _lib._stream(score)
 
     def step(ev=None):
-        ws.prepare()
+        ws.prepare()  # skipped by the wrapper when the previous select handed the workspace back zeroed
         if ev:
             ev[0].record()
         _lib.acq_score(logits, strat, lab, void, out=score, hist0_ws=ws)
         if ev:
             ev[1].record()
         _lib.check(lib.pp_acq_select(_lib._ptr(score), n_img, HW, k, largest, 1, _lib._ptr(ws.buf), ws.nbytes, st), "select")
+        ws._clean = n_img if SELF_CLEANING else None  # what _lib.acq_select_pick does for the tree's build
         if ev:
             ev[2].record()
         _lib.check(lib.pp_acq_pick(_lib._ptr(ws.buf), ws.nbytes, n_img, HW, k, _lib._ptr(pos), bench.N_SEL, _lib._ptr(out), st), "pick")
@@ -92,11 +101,18 @@ if __name__ == "__main__":
         copy = os.path.join(os.path.dirname(TREE_LIB), "build", f"libpp_tree_l0_{v}.so")
         shutil.copyfile(TREE_LIB, copy)
         builds.append((f"tree, PP_SELECT_L0={v}", copy, v))
+    for v in [x for x in os.environ.get("PP_AB_SCORE", "").split(",") if x]:  # ... and with the other scoring kernels
+        copy = os.path.join(os.path.dirname(TREE_LIB), "build", f"libpp_tree_sc_{v}.so")
+        shutil.copyfile(TREE_LIB, copy)
+        builds.append((f"tree, PP_SCORE_VARIANT={v}", copy, ("score", v)))
     builds.append(("tree", TREE_LIB, None))
     if os.environ.get("PP_AB_CFGS"):
         cfgs = cfgs[:int(os.environ["PP_AB_CFGS"])]
     for name, path, sel in builds:
-        use(path, sel)
+        if isinstance(sel, tuple):
+            use(path, None, sel[1])
+        else:
+            use(path, sel)
         print("==", name, flush=True)
         for c in cfgs:
             print(json.dumps(run(*c)), flush=True)

@@ -187,6 +187,43 @@ def test_fused_hist0_equals_standalone(strat):
     assert torch.equal(a, c)
 
 
+@pytest.mark.parametrize("strat", STRATS)
+def test_workspace_is_prepared_again_after_a_select(strat):
+    """pp_acq_topk_prepare contract: a completed select zeroes what it consumed, so the wrapper skips the memset between
+    batches.  Batches of different data, sizes and paths (heavy ties -> whole-bucket selections, short boundary lists
+    ranked directly, picks with and without the sort) through ONE workspace must equal fresh workspaces, and the zeroed
+    histograms must read back as zeros.  (The bucket state a select leaves behind sits where a LARGER batch keeps
+    histograms, so the wrapper zeroes again when the batch size changes.)"""
+    g = torch.Generator().manual_seed(17)
+    h, w, k = 64, 128, 409
+    ws = _lib.TopKWorkspace(4, h * w, k, DEV)
+    largest = _lib.LARGEST[strat]
+    for step in range(5):
+        n = 4 if step != 2 else 3  # a smaller batch in between
+        logits = torch.randn((n, 19, h, w), generator=g) * (3.0 if step != 3 else 0.0)  # step 3: every score equal
+        logits = logits.to(DEV)
+        ws.prepare()  # a no-op from the second batch on
+        assert ws._clean is not None
+        score = _lib.acq_score(logits, strat, hist0_ws=ws)
+        assert ws._clean is None
+        pos = torch.from_numpy(np.stack([np.random.RandomState(step * 7 + i).permutation(k)[:10] for i in range(n)]).astype(np.int32))
+        if step % 2 == 0:
+            got = _lib.acq_select_pick(score.view(n, -1), k, largest, pos, ws=ws, hist0_valid=True)
+            want = _lib.acq_gather(_lib.acq_topk(score.view(n, -1), k, largest), pos)
+        else:
+            got = _lib.acq_topk(score.view(n, -1), k, largest, ws=ws, hist0_valid=True)
+            want = _lib.acq_topk(score.view(n, -1), k, largest)
+        assert ws._clean == n
+        assert torch.equal(got, want), step
+        torch.cuda.synchronize()
+        assert int(ws.buf[: n * 2048 * 4].count_nonzero()) == 0, step  # the level-0 histograms of the batch
+    # a score that is not followed by a select leaves the histogram filled: the next fill prepares by itself
+    _lib.acq_score(logits, strat, hist0_ws=ws)
+    score = _lib.acq_score(logits, strat, hist0_ws=ws)
+    got = _lib.acq_topk(score.view(n, -1), k, largest, ws=ws, hist0_valid=True)
+    assert torch.equal(got, _lib.acq_topk(score.view(n, -1), k, largest))
+
+
 # --------------------------------------------------------------------------------------- selection
 @pytest.mark.parametrize("strat", STRATS)
 @pytest.mark.parametrize("C,h,w", [(19, 256, 512), (11, 360, 480)])
