@@ -798,10 +798,10 @@ def main():
     cfg.update({"acq_images_per_step_per_gpu": args.acq_batch, "acq_step_ms": acq["ms_per_step"], "acq_step_gpix_s": acq["mpix_s"] / 1e3,
                 "acq_step_frac_of_hbm": alg / (acq["ms_per_step"] / 1e3) / 1e9 / hbm_peak,
                 "acq_select": ("scoring fused with the level-0 select (scores stay in shared memory), radix tail, order statistics at "
-                               "the drawn ranks; " if acq["fused"] else "radix select + order statistics at the drawn ranks; ") +
+                               "the drawn ranks; " if acq["fused"] else "radix select (persistent level-0 kernel) + order statistics at the drawn ranks; ") +
                               ("select+pick of step i on a side stream under the scoring of step i+1" if args.overlap_select else "one stream")})
     roof = {"kernel": ("acq_score_select_kernel<19, margin> (softmax + margin + mask fills + level-0 select in one pass, cluster of 8 "
-                       "CTAs per image)" if acq["fused"] else "acq_score_vec_kernel<19, margin, f32, fused hist0>"), "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                       "CTAs per image)" if acq["fused"] else "acq_score_pf_kernel<19, margin, f32, fused hist0> (next tile in flight while scoring)"), "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
             "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": acq["score_ms"],
             "alg_bytes_per_launch": alg, "share_of_acq_step": acq["score_ms"] / acq["ms_per_step"]}
     if rank == 0 and not args.no_extras:

@@ -1,17 +1,24 @@
 // Q path — fused acquisition scoring and per-image sorted top-k.
 //
 //   K1  acq_score_*      logits[n,C,H,W] (+masks) -> score[n,H*W] (+ level-0 radix histogram)
-//                        one coalesced, vectorised pass over the logits: HBM-bound, C*4+2 B/px.
+//                        one coalesced, vectorised pass over the logits: HBM-bound, C*4+2 B/px.  Large fp32 batches run
+//                        acq_score_pf_kernel: a thread's next tile is in flight (cp.async into a private shared-memory slot)
+//                        while it scores the current one.
 //   K2  pick_bucket0     per image: the level-0 bucket holding the k-th score, and that bucket's ordering-key range.
 //       select_l0        ONE pass over the score map: composites (ord_key(score) << 32 | flat idx) below the bucket go
 //                        to the candidate list, those inside it to the (small) boundary list.  Level 0 is bucket0()
 //                        (pp_common.cuh): the key's leading 11 bits for smallest-first selections, a linear
-//                        quantisation of [0, 4) for largest-first ones.
-//       select_rest      MSD radix levels on the boundary list, one CTA per image, until the k-th is isolated.
+//                        quantisation of [0, 4) for largest-first ones.  select_l0_staged_kernel: persistent, cp.async
+//                        ring per warp, survivors compacted before they are classified.
+//       select_rest      MSD radix levels on the boundary list, one CTA per image, until the k-th is isolated (short lists
+//                        are ranked directly).
 //   K3a pick_ranks_fast  the reference only reads n random RANKS of the sorted list (query.py:63-64): three
 //                        table-lookup passes over the k unsorted candidates return exactly those order statistics;
-//       pick_ranks       generic 5-level radix walk for images the fast kernel flags (> 32 exact ties).
+//                        images it cannot finish (> 32 exact ties, n > 12) run the generic 5-level walk in the same launch.
 //   K3b bitonic_*        full sort of the k composites when the list itself is wanted (ties -> lower flat index first).
+//
+// The workspace's histograms / counters are zero before a step (pp_acq_topk_prepare) and zero again after its select:
+// select_rest zeroes what the step consumed.
 //
 // Reference semantics restated (query.py:33-69,190-201,224-247): see include/pixelpick_b200.h.
 #include <cooperative_groups.h>
@@ -547,17 +554,13 @@ __global__ void __launch_bounds__(kSelThreads) hist0_kernel(const float* __restr
 
 // One CTA per image: find the bucket of the level-0 histogram that holds the k-th element; state[img] = {rank inside
 // the bucket, whole bucket selected?, bucket}.  Done once here instead of in the prologue of every select_l0 CTA.
-__global__ void __launch_bounds__(kSelThreads) pick_bucket0_kernel(uint32_t* __restrict__ hist0, SelState* __restrict__ state,
+__global__ void __launch_bounds__(kSelThreads) pick_bucket0_kernel(const uint32_t* __restrict__ hist0, SelState* __restrict__ state,
                                                                     uint32_t k, bool largest) {
   __shared__ uint32_t sh_warp[kSelThreads / 32];
   __shared__ uint32_t sh_bucket;
   const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint4* hc = reinterpret_cast<uint4*>(hist0 + (size_t)img * kHistBins) + tid * 2;
+  const uint4* hc = reinterpret_cast<const uint4*>(hist0 + (size_t)img * kHistBins) + tid * 2;
   const uint4 ha = hc[0], hb = hc[1];
-  // this kernel is the histogram's only reader: hand it back zeroed, so that the workspace is "prepared" again once the
-  // select has run (select_rest_kernel resets the counters) and a host that tracks this can skip pp_acq_topk_prepare
-  hc[0] = make_uint4(0u, 0u, 0u, 0u);
-  hc[1] = make_uint4(0u, 0u, 0u, 0u);
   const uint32_t h[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
   uint32_t mine = 0;
 #pragma unroll
@@ -775,9 +778,11 @@ __global__ void __launch_bounds__(kSelThreads, 6) select_l0_kernel(const SelPara
 // the same with the bucket state loaded one chunk ahead and the output deferred by one chunk 73.7; that one without atomics 61.8,
 // without atomics and stores 53.8 - i.e. neither the atomic round trip nor the scattered stores but the 437 instructions per
 // chunk (two divergent per-lane loops of ~3 trips at 0.8 active lanes) and an L2 load of the image's state on every chunk.  Here
-//   * the grid is persistent (3 CTAs per SM); every warp owns ONE contiguous range of chunks, so the bucket state is reloaded
-//     only when the range crosses into the next image, and walks it through a private 4-stage ring in shared memory filled
-//     with cp.async (16 bytes per lane and piece, three chunks = 6 KB per warp in flight);
+//   * the grid is persistent; every warp owns ONE contiguous range of chunks, so the bucket state is reloaded only when the
+//     range crosses into the next image, and walks it through a private ring in shared memory filled with cp.async (16 bytes
+//     per lane and piece).  Once the output counters had their own cache lines (kCntStride) the kernel became sensitive to
+//     occupancy, not to prefetch depth: select phase 54.2 / 50.2 / 48.1 us with 4 / 3 / 2 ring stages at 3 / 4 / 5 CTAs per
+//     SM, hence the default of 2 stages;
 //   * a score costs one float compare + one mask update; the lanes' survivors (~5 %) are compacted into a per-warp list of
 //     9-bit chunk offsets behind one warp scan, and then classified on the exact ordering key and written DENSELY, one survivor
 //     per lane and trip, behind one warp-aggregated atomic pair, as in the legacy kernel.
@@ -1210,6 +1215,7 @@ struct RestParams {
   uint64_t* list_a;        // [n_img][HW] boundary list written by level 0
   uint64_t* list_b;        // [n_img][HW] scratch
   uint32_t* count_a;       // boundary-list lengths (kCntStride apart)
+  uint32_t* hist0;         // [n_img][2048] level-0 histograms (zeroed here)
   uint64_t* cand;
   uint32_t* cand_count;
   const SelState* state1;  // {remaining, done} after level 0
@@ -1225,8 +1231,12 @@ __global__ void __launch_bounds__(kRestThreads) select_rest_kernel(const RestPar
   __shared__ uint64_t sh_direct[kRestDirect];
   const int img = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // The select hands the workspace back "prepared" (pp_acq_topk_prepare): this kernel runs last and zeroes what the step
+  // consumed - the image's level-0 histogram here (its only reader, pick_bucket0_kernel, is done; the stores drain under the
+  // walk below - zeroing inside pick_bucket0_kernel itself cost that kernel 2 us), the two counters at the exits.
+  if (tid < kHistBins / 4) reinterpret_cast<uint4*>(p.hist0 + (size_t)img * kHistBins)[tid] = make_uint4(0u, 0u, 0u, 0u);
   const SelState st = p.state1[img];
-  if (st.done) {  // level 0 took a whole bucket: nothing left to resolve; leave the counters zeroed (see pick_bucket0_kernel)
+  if (st.done) {  // level 0 took a whole bucket: nothing left to resolve
     if (tid == 0) {
       p.cand_count[(size_t)img * kCntStride] = 0u;
       p.count_a[(size_t)img * kCntStride] = 0u;
@@ -2247,6 +2257,7 @@ static int select_impl(const float* score_map, int n_img, int HW, int k, int lar
     r.list_a = w.filt;
     r.list_b = w.filt + (size_t)n_img * HW;
     r.count_a = w.filt_count;
+    r.hist0 = w.hist;
     r.cand = w.cand;
     r.cand_count = w.cand_count;
     r.state1 = w.state + (size_t)n_img;
@@ -2481,6 +2492,7 @@ int pp_acq_score_select(const void* logits, int dtype, int n_img, int C, int H, 
   r.list_a = w.filt;
   r.list_b = w.filt + (size_t)n_img * HW;
   r.count_a = w.filt_count;
+  r.hist0 = w.hist;
   r.cand = w.cand;
   r.cand_count = w.cand_count;
   r.state1 = w.state + (size_t)n_img;
