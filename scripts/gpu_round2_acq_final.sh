@@ -3,6 +3,8 @@
 mkdir -p gpurun_out
 timeout 200 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 tail -1 gpurun_out/smoke.log
+( timeout 300 python -m pytest tests/test_acq_gpu.py tests/test_query_selector_gpu.py tests/test_loop_gpu.py -q ) > gpurun_out/pytest_acq.log 2>&1
+tail -1 gpurun_out/pytest_acq.log
 # acquisition pipeline: launch list with DRAM bytes, then full captures of its kernels
 bash scripts/gpu_ncu_list.sh acq "scripts/acq_step.py 256 3" 200 > gpurun_out/acq_list.log 2>&1
 bash scripts/gpu_ncu.sh ncu_acq "scripts/acq_step.py 256 1" "acq_score|select_l0|pick_ranks_fast|select_rest|pick_bucket0" 5 > /dev/null 2>&1
