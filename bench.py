@@ -803,7 +803,8 @@ def main():
     roof = {"kernel": ("acq_score_select_kernel<19, margin> (softmax + margin + mask fills + level-0 select in one pass, cluster of 8 "
                        "CTAs per image)" if acq["fused"] else "acq_score_pf_kernel<19, margin, f32, fused hist0> (next tile in flight while scoring)"), "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
             "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": acq["score_ms"],
-            "alg_bytes_per_launch": alg, "share_of_acq_step": acq["score_ms"] / acq["ms_per_step"]}
+            "alg_bytes_per_launch": alg, "share_of_acq_step": acq["score_ms"] / acq["ms_per_step"],
+            "peak_note": "peak = the driver's COPY bandwidth (half reads, half writes); this kernel's traffic is 95 % reads, so frac may pass 1"}
     if rank == 0 and not args.no_extras:
         cfg["augment_b32_ms"] = bench_augment(dev)  # the device input pipeline (geometric + photometric) for one batch of 32
         conv = bench_conv_roofline(dev, tf_burst)
