@@ -82,3 +82,48 @@ def test_poly_reads_tensor_learning_rates_once():
 
 def test_upsampled_score_guard_lists_the_instantiated_class_counts():
     assert _lib.UPSAMPLED_SCORE_CLASSES == (11, 19, 21)
+
+
+def test_topk_workspace_tracks_when_the_memset_may_be_skipped(monkeypatch):
+    """include/pixelpick_b200.h, pp_acq_topk_prepare: a completed select hands the workspace back zeroed FOR ITS BATCH SIZE
+    (the bucket state it leaves behind lies where a larger batch keeps histograms), so TopKWorkspace skips the per-batch
+    memset only then.  The kernels are not called here: only the bookkeeping around them."""
+    real = _lib.lib()
+    calls = []
+
+    class Fake:
+        def __getattr__(self, name):
+            return getattr(real, name)
+
+        def pp_acq_topk_prepare(self, *a):
+            calls.append(a[2])  # n_img of the zeroed region
+            return 0
+
+    monkeypatch.setattr(_lib, "_lib", Fake())
+    monkeypatch.setattr(_lib, "_stream", lambda t: None)  # no CUDA stream on the CPU
+    ws = object.__new__(_lib.TopKWorkspace)  # (the constructor wants a 256-byte aligned DEVICE buffer)
+    ws.n_img, ws.HW, ws.k, ws.nbytes, ws.buf, ws._clean = 4, 64 * 128, 409, 1 << 20, torch.empty(1 << 20, dtype=torch.uint8), None
+    ws.prepare()
+    ws.prepare()
+    assert calls == [4] and ws._clean == "all"          # always the full-capacity region, once
+    ws._begin_fill(4)                                    # pp_acq_score(hist0=...) on a zeroed workspace: no memset
+    assert calls == [4] and ws._clean is None
+    ws._begin_select(4, True)
+    ws._clean = 4                                        # what the wrappers set after a completed select
+    ws.prepare()
+    ws._begin_fill(4)                                    # same batch size again: still no memset
+    assert calls == [4]
+    ws._begin_fill(4)                                    # a fill that was NOT followed by a select: zero again
+    assert calls == [4, 4]
+    ws._begin_select(4, True)
+    ws._clean = 4
+    ws._begin_fill(3)                                    # another batch size: the old bucket state is in the way
+    assert calls == [4, 4, 4]
+    ws._clean = 3
+    ws._begin_select(3, False)                           # the select builds the histogram itself: clean for 3 is enough
+    assert calls == [4, 4, 4] and ws._clean is None
+    ws._begin_select(3, False)                           # ... but not after an unfinished select
+    assert calls == [4, 4, 4, 4]
+    ws._clean = 3
+    ws.prepare(force=True)
+    assert calls == [4, 4, 4, 4, 4] and ws._clean == "all"
