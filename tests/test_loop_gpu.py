@@ -234,7 +234,7 @@ def test_train_py_mirror_runs_and_supports_human_labels(tmp_path):
         lowres = net.forward_lowres(d["x"].to(dev)).detach()  # the call train_epoch makes
         l_masked = float(sparse_cross_entropy(lowres, y, q, args.ignore_index))
         l_human = float(sparse_cross_entropy(lowres, lq.to(torch.int64), None, args.ignore_index))
-        assert abs(l_masked - l_human) <= 1e-5 * abs(l_masked), (l_masked, l_human)
+        assert abs(l_masked - l_human) <= 1e-4 * abs(l_masked), (l_masked, l_human)  # (the kernel sums with fp32 atomics)
     del net
 
     class Human:  # the same batches with `labelled_queries` instead of (y, queries)
